@@ -1,0 +1,176 @@
+"""CPU tests of the oracle: pinned against golden vectors produced by the reference's own
+modules.py (tests/golden/make_golden.py), live against the reference when it is mounted,
+and self-checked (analytic gradients of SURVEY Appendix A.3 vs autograd)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import drvish_oracle as O
+
+
+def _load(golden_dir, name):
+    return {k: v for k, v in np.load(os.path.join(golden_dir, name)).items()}
+
+
+def _mods_from_golden(g, tag, dtype):
+    B, G = g[f"{tag}.x"].shape
+    L = g[f"{tag}.z"].shape[1]
+    layers = [g[f"{tag}.enc.fc.2.weight"].shape[0], g[f"{tag}.enc.fc.5.weight"].shape[0]]
+    enc = O.OracleEncoder(G, L, layers).to(dtype)
+    dec = O.OracleNBDecoder(L, G, layers[::-1]).to(dtype)
+    enc.load_state_dict({k[len(tag) + 5:]: torch.from_numpy(v) for k, v in g.items() if k.startswith(f"{tag}.enc.")})
+    dec.load_state_dict({k[len(tag) + 5:]: torch.from_numpy(v) for k, v in g.items() if k.startswith(f"{tag}.dec.")})
+    return enc, dec
+
+
+@pytest.mark.parametrize("tag,dtype,tol", [("f32", torch.float32, 2e-5), ("f64", torch.float64, 1e-12)])
+def test_networks_match_reference_golden(golden_dir, tag, dtype, tol):
+    g = _load(golden_dir, "ref_modules_small.npz")
+    enc, dec = _mods_from_golden(g, tag, dtype)
+    t = lambda k: torch.from_numpy(g[f"{tag}.{k}"])
+    x = t("x")
+    z_loc, z_scale, l_loc, l_scale = enc(x)
+    for name, val in (("z_loc", z_loc), ("z_scale", z_scale), ("l_loc", l_loc), ("l_scale", l_scale)):
+        torch.testing.assert_close(val, t(name), rtol=tol, atol=tol)
+    z = t("z").clone().requires_grad_(True)
+    l = t("l").clone().requires_grad_(True)
+    log_r, logit = dec(z, l)
+    torch.testing.assert_close(log_r, t("log_r"), rtol=tol, atol=tol)
+    torch.testing.assert_close(logit, t("logit"), rtol=tol, atol=tol)
+    gz = torch.autograd.grad((log_r * torch.cos(logit)).sum(), [z, l] + list(dec.parameters()))
+    torch.testing.assert_close(gz[0], t("dz"), rtol=50 * tol, atol=50 * tol)
+    torch.testing.assert_close(gz[1], t("dl"), rtol=50 * tol, atol=50 * tol)
+    for (n, _), gr in zip(dec.named_parameters(), gz[2:]):
+        ref = t(f"dec_grad.{n}")
+        assert (gr - ref).norm() <= 50 * tol * (ref.norm() + 1e-3), n
+    ge = torch.autograd.grad((z_loc * z_scale).sum() + (l_loc * l_scale).sum(), list(enc.parameters()))
+    for (n, _), gr in zip(enc.named_parameters(), ge):
+        ref = t(f"enc_grad.{n}")
+        assert (gr - ref).norm() <= 50 * tol * (ref.norm() + 1e-3), n
+    m = O.logit_mean_sigmoid(t("z").float(), t("w").float(), t("b").float(), t("labels"))
+    torch.testing.assert_close(m, t("m"), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.skipif(not os.path.exists(O.REFERENCE_MODULES_PY), reason="reference not mounted")
+def test_networks_match_reference_live():
+    ref = O.load_reference_modules()
+    torch.manual_seed(3)
+    G, L, layers, B = 50, 4, [20, 10], 16
+    r_enc, r_dec = ref.Encoder(G, L, layers), ref.NBDecoder(L, G, layers[::-1])
+    o_enc, o_dec = O.OracleEncoder(G, L, layers), O.OracleNBDecoder(L, G, layers[::-1])
+    assert list(r_enc.state_dict().keys()) == list(o_enc.state_dict().keys())
+    assert list(r_dec.state_dict().keys()) == list(o_dec.state_dict().keys())
+    o_enc.load_state_dict(r_enc.state_dict())
+    o_dec.load_state_dict(r_dec.state_dict())
+    x = torch.poisson(torch.rand(B, G) * 4)
+    for a, b in zip(r_enc(x), o_enc(x)):
+        assert torch.equal(a, b)
+    z, l = torch.randn(B, L), torch.randn(B, 1)
+    for a, b in zip(r_dec(z, l), o_dec(z, l)):
+        assert torch.equal(a, b)
+    labels = torch.arange(B) % 3
+    w, b = torch.randn(L, 1), torch.randn(5, 1)
+    assert torch.equal(ref.LinearMultiBias.logit_mean_sigmoid(z, w, b, labels), O.logit_mean_sigmoid(z, w, b, labels))
+    with pytest.raises(RuntimeError):
+        O.logit_mean_sigmoid(z, w, b, torch.where(labels == 1, 2, labels))
+
+
+def test_golden_step_reproduces(golden_dir):
+    """The committed full-step fixtures are what the oracle computes today."""
+    g = _load(golden_dir, "oracle_step_tiny.npz")
+    cfg = dict(n_input=203, n_latent=3, layers=[24, 40], batch=77, drugs=0)
+    model = O.build_model(cfg).double()
+    model.load_state_dict({k[3:]: torch.from_numpy(v).double() if v.dtype.kind == "f" else torch.from_numpy(v)
+                           for k, v in g.items() if k.startswith("sd.")})
+    noise = {"eps_z": torch.from_numpy(g["noise.eps_z"]).double(), "eps_l": torch.from_numpy(g["noise.eps_l"]).double()}
+    loss, grads, _ = O.step(model, torch.from_numpy(g["x"]).double(), noise)
+    assert abs(loss - float(g["loss64"])) <= 1e-9 * abs(loss)
+    for k, v in grads.items():
+        ref = torch.from_numpy(g[f"grad64.{k}"])
+        assert (v - ref).norm() <= 1e-8 * (ref.norm() + 1e-6), k
+
+
+def nb_block_analytic(s, rho, l, x, eps, c):
+    """SURVEY Appendix A.3 - the formulas the CUDA epilogue implements."""
+    lse = torch.logsumexp(s, -1, keepdim=True)
+    ls = s - lse
+    ell = l + ls - rho
+    r = torch.exp(rho) + eps
+    sp = torch.nn.functional.softplus(ell)
+    ll = (-(r + x) * sp + x * ell + torch.lgamma(r + x) - torch.lgamma(1 + x) - torch.lgamma(r)).sum(-1)
+    sig = torch.sigmoid(ell)
+    a = x - (x + r) * sig
+    A = a.sum(-1, keepdim=True)
+    ds = a - torch.exp(ls) * A
+    drho = torch.exp(rho) * (-sp + torch.digamma(r + x) - torch.digamma(r)) - a
+    return ll, -c * ds, -c * drho, -c * A
+
+
+def test_nb_block_analytic_matches_autograd():
+    torch.manual_seed(0)
+    B, G = 9, 31
+    s = torch.randn(B, G, dtype=torch.float64, requires_grad=True)
+    rho = torch.randn(B, G, dtype=torch.float64, requires_grad=True)
+    l = (5 + torch.randn(B, 1, dtype=torch.float64)).requires_grad_(True)
+    x = torch.poisson(torch.rand(B, G) * 5).double()
+    c, eps = 0.7, 1e-6
+    logit = l + torch.log_softmax(s, -1) - rho
+    ll = torch.distributions.NegativeBinomial(total_count=torch.exp(rho) + eps, logits=logit).log_prob(x).sum(-1)
+    loss = -c * ll.sum()
+    gs, grho, gl = torch.autograd.grad(loss, [s, rho, l])
+    ll2, ds, drho, dl = nb_block_analytic(s.detach(), rho.detach(), l.detach(), x, eps, c)
+    torch.testing.assert_close(ll2, ll.detach(), rtol=1e-12, atol=1e-10)
+    torch.testing.assert_close(ds, gs, rtol=1e-10, atol=1e-12)
+    torch.testing.assert_close(drho, grho, rtol=1e-10, atol=1e-12)
+    torch.testing.assert_close(dl, gl, rtol=1e-10, atol=1e-12)
+
+
+def test_data_parallel_semantics_is_sum_over_shards():
+    """R-rank result == sum_r oracle(shard_r); this is NOT oracle(concat) because of
+    per-shard BatchNorm statistics."""
+    cfg = dict(n_input=40, n_latent=3, layers=[16, 16], batch=32, drugs=0)
+    model = O.build_model(cfg).double()
+    x = O.synthetic_counts(32, 40, seed=11).double()
+    noise = {k: v.double() for k, v in O.make_noise(model, 32).items()}
+    full, _, _ = O.step(model, x, noise)
+    parts = 0.0
+    for r in range(2):
+        sl = slice(16 * r, 16 * (r + 1))
+        lr, _, _ = O.step(model, x[sl], {k: v[sl] for k, v in noise.items()})
+        parts += lr
+    assert abs(parts - full) > 1e-6 * abs(full)  # BN statistics differ per shard
+
+
+def test_zero_bias_gradients_behind_batchnorm():
+    cfg = dict(n_input=60, n_latent=4, layers=[16, 24], batch=48, drugs=0)
+    model = O.build_model(cfg).double()
+    x = O.synthetic_counts(48, 60, seed=2).double()
+    noise = {k: v.double() for k, v in O.make_noise(model, 48).items()}
+    _, grads, _ = O.step(model, x, noise)
+    for n in ("encoder.fc.2.bias", "encoder.fc.5.bias", "decoder.fc.2.bias", "decoder.fc.5.bias"):
+        wn = n.replace("bias", "weight")
+        assert grads[n].norm() < 1e-9 * grads[wn].norm()
+
+
+def test_drnbvae_oracle_runs_and_guide_factor_sign():
+    cfg = O.CONFIGS[1]
+    model = O.build_model(cfg)
+    B = 32
+    x = O.synthetic_counts(B, cfg["n_input"], seed=3)
+    noise = O.make_noise(model, B)
+    labels = torch.arange(B) % cfg["classes"]
+    y = [torch.randn(cfg["classes"], cfg["doses"], 1) for _ in range(cfg["drugs"])]
+    loss, grads, terms = O.step(model, x, noise, labels, y)
+    assert np.isfinite(loss)
+    assert terms["m"][0].shape == (cfg["classes"], cfg["doses"], 1)
+    # weight_loc / weight_scale never enter the loss (SURVEY 3.2 semantic trap)
+    assert float(grads["lmb_list.0.weight_loc"].abs().max()) == 0.0
+    assert float(grads["lmb_list.0.weight_scale_unconstrained"].abs().max()) == 0.0
+    assert float(grads["lmb_list.0.bias_loc"].abs().max()) > 0.0
+    loss_nf, _, _ = O.loss_and_grads(model, O.drnbvae_loss, x, labels, y, noise["eps_z"], noise["eps_l"],
+                                     noise["w_prior"], noise["b_prior"], noise["eps_bias"],
+                                     include_guide_factor=False)
+    # factor (<=0) sits in the guide: ELBO -= factor, loss += factor
+    assert loss <= loss_nf + 1e-4
