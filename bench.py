@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""Headline benchmark: cells/sec per SVI step (ELBO forward + backward) - BASELINE.json `metric`.
+
+    python bench.py --gpus N --steps K --warmup W              # this framework (one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K ...    # reference CPU path on the host cores
+
+Workload (SURVEY 8d / BASELINE.md 4): config 3 by default - synthetic NB counts, 100k cells x
+5k genes, latent 10, layers [256,256], 8 drugs x 8 doses, K=8 classes, minibatch 4096 cells per
+GPU (weak scaling: every rank steps its own 4096-cell shard, gradients summed with one NCCL
+all-reduce per step).  One "step" = noise -> ELBO -> every parameter gradient (-> all-reduce);
+the optimizer update is excluded (it is not part of the north star).  Inputs rotate over >= 20
+distinct resident minibatches (1.6 GB > the 126 MB L2), so no L2 flush is needed.
+
+Prints ONE JSON line (rank 0).  `value` = device-timed throughput with inputs resident in HBM;
+`e2e` = same metric through the public API (FusedTraceELBO.loss_and_grads, what pyro's SVI.step
+calls) with pinned HOST minibatches copied H2D and the loss read back D2H inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    2: dict(name="cfg2: 10k cells x 2k genes, latent 10, layers [128,128], NBVAE", n_cells=10_000,
+            n_input=2000, n_latent=10, layers=[128, 128], batch=4096, drugs=0, doses=0, classes=0),
+    3: dict(name="cfg3: 100k cells x 5k genes, latent 10, layers [256,256], 8 drugs x 8 doses, K=8, DRNBVAE",
+            n_cells=100_000, n_input=5000, n_latent=10, layers=[256, 256], batch=4096, drugs=8, doses=8, classes=8),
+    4: dict(name="cfg4: 1M cells x 20k genes, latent 32, layers [512,512], NBVAE", n_cells=1_000_000,
+            n_input=20000, n_latent=32, layers=[512, 512], batch=4096, drugs=0, doses=0, classes=0),
+    5: dict(name="cfg5: 4M cells x 30k genes, latent 64, layers [512,512], 96 drugs x 10 doses, K=8, DRNBVAE",
+            n_cells=4_000_000, n_input=30000, n_latent=64, layers=[512, 512], batch=4096, drugs=96, doses=10, classes=8),
+}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tensor=p.get("bf16_tflops_sustained", p["bf16_tflops"]), which="measured")
+    return dict(hbm=6650.0, tensor=1400.0, which="fallback")
+
+
+def decoder_algorithmic(cfg):
+    """bytes_alg(dec) = 8BG + 8Bh + 16Gh ; flops_alg(dec) = 12 B G h."""
+    B, G, h = cfg["batch"], cfg["n_input"], cfg["layers"][0]
+    return 8.0 * B * G + 8.0 * B * h + 16.0 * G * h, 12.0 * B * G * h
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def finish(self):
+        self._stop.set()
+        self.join(timeout=1.0)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def synth_batches(cfg, n_batches, seed, device):
+    """x ~ NB(2, logits=u_b+v_g), generated on the device; labels = b mod K; y ~ N(0,1)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    B, G = cfg["batch"], cfg["n_input"]
+    v = -1.0 + torch.randn(1, G, generator=g, device=device)
+    xs = []
+    for _ in range(n_batches):
+        u = 0.5 * torch.randn(B, 1, generator=g, device=device)
+        rate = torch._standard_gamma(torch.full((B, G), 2.0, device=device), generator=g) * torch.exp(u + v)
+        xs.append(torch.poisson(rate, generator=g).float())
+    labels = y = None
+    if cfg["drugs"]:
+        labels = (torch.arange(B, device=device) % cfg["classes"]).long()
+        y = [torch.randn(cfg["classes"], cfg["doses"], 1, generator=g, device=device) for _ in range(cfg["drugs"])]
+    return xs, labels, y
+
+
+def build_native_model(cfg, device):
+    import drvish_b200 as D
+
+    torch.manual_seed(0)
+    kw = dict(n_input=cfg["n_input"], n_latent=cfg["n_latent"], layers=cfg["layers"])
+    if cfg["drugs"]:
+        m = D.DRNBVAE(n_classes=cfg["classes"], n_drugs=cfg["drugs"], n_conditions=[cfg["doses"]] * cfg["drugs"], **kw)
+    else:
+        m = D.NBVAE(**kw)
+    return m.to(device)
+
+
+def oracle_cpu_rate(cfg, steps, warmup, batch=None):
+    """The reference's CPU implementation of the path: the oracle's PyTorch-eager restatement
+    of the Pyro step (reference Encoder/NBDecoder/logit_mean_sigmoid arithmetic +
+    torch.distributions + .backward()), fp32, all host threads.  Pyro itself cannot be installed
+    (no wheel, no network), so its ~1-2 ms/step of tracing overhead is absent."""
+    from oracle import drvish_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ocfg = dict(cfg)
+    B = batch or cfg["batch"]
+    ocfg["batch"] = B
+    model = O.build_model(ocfg, seed=0)
+    x = O.synthetic_counts(B, cfg["n_input"], seed=1234)
+    noise = O.make_noise(model, B, seed=1)
+    labels = y = None
+    if cfg["drugs"]:
+        labels = torch.arange(B) % cfg["classes"]
+        y = [torch.randn(cfg["classes"], cfg["doses"], 1) for _ in range(cfg["drugs"])]
+    for _ in range(warmup):
+        O.step(model, x, noise, labels, y)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.step(model, x, noise, labels, y)
+    dt = time.perf_counter() - t0
+    return B * steps / dt, dt / steps * 1e3, cores, B
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = min(args.steps, 20)
+    rate, ms, cores, B = oracle_cpu_rate(cfg, steps, min(args.warmup, 3))
+    sample = f"{steps} steps of one {B}-cell minibatch of {cfg['name']}"
+    line = {
+        "impl": "reference", "metric": "cells/sec per SVI step (ELBO fwd+bwd)", "value": rate, "unit": "cells/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["name"], "minibatch_per_step": B, "device": "host CPU"},
+        "cpu_baseline": {"value": rate, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_native(args, cfg):
+    import torch.distributed as dist
+
+    import drvish_b200 as D
+    from drvish_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the native path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    lib = _lib.load()
+    model = build_native_model(cfg, device)
+    rt = model._runtime()
+    elbo = D.FusedTraceELBO(seed=1234, data_parallel=(world > 1))
+    n_batches = max(20, args.batches)
+    xs, labels, y = synth_batches(cfg, n_batches, 1234 + 3 + rank, device)
+    B, G = cfg["batch"], cfg["n_input"]
+
+    def batch_args(i, x=None):
+        a = [xs[i % n_batches] if x is None else x]
+        if cfg["drugs"]:
+            a += [labels, y]
+        return a
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (`value`) ----------------------------------------------------
+    # same code path as loss_and_grads minus the per-step loss read-back (one sync at the end)
+    yflat = elbo._flatten_y(rt, y, device) if cfg["drugs"] else None
+    rt.ensure_flat()
+
+    def device_step(i):
+        noise = elbo._noise(rt, B)
+        rt.elbo_step(xs[i % n_batches], labels, yflat, noise, True, elbo.flags, True)
+        elbo.step_index += 1
+        if world > 1:
+            rt.flat_grads[rt.n_param_floats] = rt._out[0].to(torch.float32)
+            dist.all_reduce(rt.flat_grads, op=dist.ReduceOp.SUM)
+
+    for i in range(args.warmup):
+        device_step(i)
+    launches_per_step = rt.last_launches + (5 if cfg["drugs"] else 2)  # + noise fills
+    barrier()
+    lib.drv_profile_enable(1)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        device_step(args.warmup + i)
+    ev1.record()
+    barrier()
+    clocks = sampler.finish()
+    ms_total = ev0.elapsed_time(ev1)
+    sec = (C.c_float * 7)()
+    nprof = C.c_int()
+    lib.drv_profile_read(sec, C.byref(nprof))
+    lib.drv_profile_enable(0)
+    loss_last, status = rt.read_out()
+    t = torch.tensor([ms_total], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- end-to-end through the public API, host minibatches --------------------------------
+    host_x = [xs[i].cpu().pin_memory() for i in range(min(4, n_batches))]
+    x_dev = torch.empty(B, G, device=device)
+    e2e_steps = max(5, args.steps // 4)
+
+    def e2e_step(i):
+        x_dev.copy_(host_x[i % len(host_x)], non_blocking=True)
+        return elbo.loss_and_grads(model.model, model.guide, *batch_args(i, x_dev))
+
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the fused decoder-last-layer + NB-likelihood section ----------------------
+    peaks = load_peaks()
+    bytes_alg, flops_alg = decoder_algorithmic(cfg)
+    t_dec_ms = sec[2] + sec[4]
+    t_hbm = bytes_alg / (peaks["hbm"] * 1e9)
+    t_tensor = flops_alg / (peaks["tensor"] * 1e12)
+    if t_tensor >= t_hbm:
+        roof = {"bound": "tensor", "achieved": flops_alg / (t_dec_ms * 1e-3) / 1e12, "peak": peaks["tensor"],
+                "unit": "TFLOP/s"}
+    else:
+        roof = {"bound": "hbm", "achieved": bytes_alg / (t_dec_ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["traffic"] = None
+    roof["kernel"] = "decoder last Linear + gene-softmax + NB likelihood, fwd+bwd (sections DEC_NB_FWD + DEC_NB_BWD)"
+    roof["peak_source"] = peaks["which"] + (" bf16 sustained; tf32 operands: nominal tensor peak is half" if roof["bound"] == "tensor" else "")
+    roof["section_ms"] = {k: round(float(sec[i]), 4) for i, k in enumerate(
+        ["enc_fwd", "dec_trunk_fwd", "dec_nb_fwd", "dose_response", "dec_nb_bwd", "dec_trunk_bwd", "enc_bwd"])}
+    roof["profiled_steps"] = int(nprof.value)
+
+    # ---- CPU baseline on the host cores (bounded sample) ---------------------------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        rate, ms, cores, Bc = oracle_cpu_rate(cfg, args.cpu_steps, 2)
+        cpu = {"value": rate, "unit": "cells/s", "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_steps} timed steps (2 warm-up) of one {Bc}-cell minibatch, fp32, PyTorch-eager "
+                         "restatement of the Pyro step (oracle/drvish_oracle.py)", "ms_per_step": ms}
+
+    line = {
+        "metric": "cells/sec per SVI step (ELBO fwd+bwd)", "value": value, "unit": "cells/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (tf32 tensor-core operands where stated in DESIGN.md)",
+        "data": "synthetic",
+        "config": {"workload": cfg["name"], "minibatch_per_gpu": B, "global_batch": B * world,
+                   "parallelism": f"dp{world}", "l2": f"inputs rotate over {n_batches} resident minibatches "
+                   f"({n_batches * B * G * 4 / 1e9:.2f} GB > 126 MB L2), no flush", "optimizer": "excluded",
+                   "noise": "Philox in-kernel draws each step"},
+        "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": B * G * 4, "d2h_bytes_per_step": 16,
+                "steps": e2e_steps, "api": "FusedTraceELBO.loss_and_grads(model.model, model.guide, *batch)"},
+        "gpu_launches": launches_per_step * args.steps,
+        "launches_per_step": launches_per_step,
+        "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "loss_last": loss_last, "status": status,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS))
+    ap.add_argument("--batches", type=int, default=20, help="distinct resident minibatches")
+    ap.add_argument("--cpu-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_native(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,173 @@
+// Reparameterised sampling of the "latent" / "library" sites, their guide and prior log-probs
+// (the KL-like part of the ELBO) and the matching backward.  Reference: Encoder.forward
+// modules.py:56-60 (column order [z_loc(L), l_loc, z_raw_scale(L), l_raw_scale], softplus),
+// NBVAE.guide nbvae.py:89-90 (rsample), NBVAE.model nbvae.py:62-68 (priors), SURVEY Appendix A.2.
+// Also the counter-based noise generators used in production mode.
+#include "kernels.cuh"
+
+namespace drv {
+
+namespace {
+
+constexpr int ST = 128;
+
+__global__ void __launch_bounds__(ST) k_sample_fwd(const float* __restrict__ O, const float* __restrict__ eps_z,
+                                                   const float* __restrict__ eps_l, int B, int L, float c,
+                                                   float lib_loc, float lib_scale, float* __restrict__ z,
+                                                   float* __restrict__ l, drv_step_out* out) {
+  int b = blockIdx.x * ST + threadIdx.x;
+  const int P = 2 * L + 2;
+  float t = 0.f;  // log p - log q of this cell
+  if (b < B) {
+    const float* o = O + (size_t)b * P;
+    for (int d = 0; d < L; ++d) {
+      float loc = o[d], sc = softplus_t(o[L + 1 + d]), e = eps_z[(size_t)b * L + d];
+      float zv = __fmaf_rn(e, sc, loc);
+      z[(size_t)b * L + d] = zv;
+      // Normal(0,1).log_prob(z) - Normal(loc, sc).log_prob(z); (z - loc)/sc == e up to rounding
+      t += (-0.5f * zv * zv) - (-0.5f * e * e - logf(sc));
+    }
+    float loc = o[L], sc = softplus_t(o[2 * L + 1]), e = eps_l[b];
+    float lv = __fmaf_rn(e, sc, loc);
+    l[b] = lv;
+    float dl = (lv - lib_loc) / lib_scale;
+    t += (-0.5f * dl * dl - logf(lib_scale)) - (-0.5f * e * e - logf(sc));
+  }
+  t = warp_sum(t);
+  __shared__ float sh[ST / 32];
+  if (threadIdx.x % 32 == 0) sh[threadIdx.x / 32] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < ST / 32; ++i) s += sh[i];
+    atomicAdd(&out->loss, -(double)c * (double)s);
+  }
+}
+
+// d loss / d (encoder output), loss = -c sum_b (log p_z + log p_l + LL - log q_z - log q_l) + drs terms
+__global__ void __launch_bounds__(ST) k_sample_bwd(const float* __restrict__ O, const float* __restrict__ eps_z,
+                                                   const float* __restrict__ eps_l, const float* __restrict__ z,
+                                                   const float* __restrict__ l, const float* __restrict__ dz_dec,
+                                                   const float* __restrict__ dz_drs, const float* __restrict__ asum,
+                                                   int B, int L, float c, float lib_loc, float lib_scale,
+                                                   float* __restrict__ dO) {
+  int b = blockIdx.x * ST + threadIdx.x;
+  if (b >= B) return;
+  const int P = 2 * L + 2;
+  const float* o = O + (size_t)b * P;
+  float* g = dO + (size_t)b * P;
+  for (int d = 0; d < L; ++d) {
+    size_t i = (size_t)b * L + d;
+    float dz = c * z[i] + dz_dec[i] + (dz_drs ? dz_drs[i] : 0.f);
+    float raw = o[L + 1 + d];
+    float sc = softplus_t(raw);
+    g[d] = dz;
+    g[L + 1 + d] = (dz * eps_z[i] - c / sc) * softplus_grad_t(raw);
+  }
+  // dLL/dl = A[b]   -> d loss/dl = -c A + c (l - mu)/sigma^2
+  float dl = -c * asum[b] + c * (l[b] - lib_loc) / (lib_scale * lib_scale);
+  float raw = o[2 * L + 1];
+  float sc = softplus_t(raw);
+  g[L] = dl;
+  g[2 * L + 1] = (dl * eps_l[b] - c / sc) * softplus_grad_t(raw);
+}
+
+__global__ void k_encoder_outputs(const float* __restrict__ O, int B, int L, float* __restrict__ z_loc,
+                                  float* __restrict__ z_scale, float* __restrict__ l_loc, float* __restrict__ l_scale) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * (L + 1)) return;
+  int b = idx / (L + 1), d = idx % (L + 1);
+  const float* o = O + (size_t)b * (2 * L + 2);
+  if (d < L) {
+    z_loc[(size_t)b * L + d] = o[d];
+    z_scale[(size_t)b * L + d] = softplus_t(o[L + 1 + d]);
+  } else {
+    l_loc[b] = o[L];
+    l_scale[b] = softplus_t(o[2 * L + 1]);
+  }
+}
+
+// Philox4x32-10 (Salmon et al. 2011), counter = element index / 4, key = seed.
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t (&k)[2]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+  uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+  uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+  k[0] += 0x9E3779B9u;
+  k[1] += 0xBB67AE85u;
+}
+
+__device__ __forceinline__ void philox4(uint64_t seed, uint64_t ctr, uint32_t (&r)[4]) {
+  uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0x6472766Bu, 0u};
+  uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+#pragma unroll
+  for (int i = 0; i < 10; ++i) philox_round(c, k);
+  r[0] = c[0]; r[1] = c[1]; r[2] = c[2]; r[3] = c[3];
+}
+
+__device__ __forceinline__ float u01(uint32_t v) { return ((float)(v >> 8) + 0.5f) * (1.0f / 16777216.0f); }  // (0,1)
+
+template <bool LAPLACE>
+__global__ void k_fill(float* __restrict__ out, int64_t n, uint64_t seed, uint64_t offset) {
+  int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // quad index
+  if (q * 4 >= n) return;
+  uint32_t r[4];
+  philox4(seed, offset / 4 + (uint64_t)q, r);
+  float v[4];
+  if (LAPLACE) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float u = 2.f * u01(r[i]) - 1.f;  // (-1,1); Laplace icdf as torch laplace.py:73-85
+      v[i] = -copysignf(1.f, u) * log1pf(-fabsf(u));
+    }
+  } else {
+    // Box-Muller on two pairs
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float rad = sqrtf(-2.f * logf(u01(r[2 * i])));
+      float s, co;
+      sincospif(2.f * u01(r[2 * i + 1]), &s, &co);
+      v[2 * i] = rad * co;
+      v[2 * i + 1] = rad * s;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (q * 4 + i < n) out[q * 4 + i] = v[i];
+}
+
+}  // namespace
+
+void sample_forward(const float* O, const float* eps_z, const float* eps_l, int B, int L, const drv_hparams& hp,
+                    float* z, float* l, drv_step_out* out, cudaStream_t st) {
+  k_sample_fwd<<<cdiv(B, ST), ST, 0, st>>>(O, eps_z, eps_l, B, L, hp.scale_factor, hp.lib_loc, hp.lib_scale, z, l, out);
+  note_launch();
+}
+
+void sample_backward(const float* O, const float* eps_z, const float* eps_l, const float* z, const float* l,
+                     const float* dz_dec, const float* dz_drs, const float* asum, int B, int L, const drv_hparams& hp,
+                     float* dO, cudaStream_t st) {
+  k_sample_bwd<<<cdiv(B, ST), ST, 0, st>>>(O, eps_z, eps_l, z, l, dz_dec, dz_drs, asum, B, L, hp.scale_factor,
+                                           hp.lib_loc, hp.lib_scale, dO);
+  note_launch();
+}
+
+void encoder_outputs(const float* O, int B, int L, float* z_loc, float* z_scale, float* l_loc, float* l_scale,
+                     cudaStream_t st) {
+  k_encoder_outputs<<<cdiv((int64_t)B * (L + 1), 256), 256, 0, st>>>(O, B, L, z_loc, z_scale, l_loc, l_scale);
+  note_launch();
+}
+
+void fill_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, cudaStream_t st) {
+  if (n <= 0) return;
+  k_fill<false><<<cdiv(cdiv(n, 4), 256), 256, 0, st>>>(out, n, seed, offset);
+  note_launch();
+}
+void fill_laplace(float* out, int64_t n, uint64_t seed, uint64_t offset, cudaStream_t st) {
+  if (n <= 0) return;
+  k_fill<true><<<cdiv(cdiv(n, 4), 256), 256, 0, st>>>(out, n, seed, offset);
+  note_launch();
+}
+
+}  // namespace drv

@@ -1,0 +1,190 @@
+// BatchNorm1d (training mode) statistics, running-buffer update and backward
+// (reference modules.py:19: every Linear of make_fc is preceded by BatchNorm1d -> ReLU; the
+// reference never calls .eval(), so batch statistics are used in validation too - SURVEY 3.3).
+// HBM-bound column reductions: 128-byte coalesced rows, fp64 accumulators, the batch split over
+// enough CTAs to fill the 148 SMs, one double atomic per column per CTA.
+#include "kernels.cuh"
+
+namespace drv {
+
+namespace {
+
+constexpr int CW = 32;   // columns per CTA (one 128-byte line per row)
+constexpr int RY = 8;    // row lanes per CTA
+
+inline int row_splits(int B, int D) {
+  int col_blocks = cdiv(D, CW);
+  int want = cdiv(148 * 4, col_blocks);
+  int max_split = cdiv(B, RY * 4);
+  int s = want < 1 ? 1 : want;
+  if (s > max_split) s = max_split;
+  return s < 1 ? 1 : s;
+}
+
+template <bool SQRT>
+__global__ void __launch_bounds__(CW* RY) k_colstats(const float* __restrict__ U, int B, int D, int rows_per_cta,
+                                                      double* __restrict__ acc) {
+  int col = blockIdx.x * CW + threadIdx.x;
+  int r0 = blockIdx.y * rows_per_cta;
+  int r1 = min(B, r0 + rows_per_cta);
+  double s = 0.0, ss = 0.0;
+  if (col < D) {
+    int r = r0 + threadIdx.y;
+    for (; r + 3 * RY < r1; r += 4 * RY) {
+      float v0 = U[(size_t)r * D + col], v1 = U[(size_t)(r + RY) * D + col];
+      float v2 = U[(size_t)(r + 2 * RY) * D + col], v3 = U[(size_t)(r + 3 * RY) * D + col];
+      if (SQRT) { v0 = sqrtf(v0); v1 = sqrtf(v1); v2 = sqrtf(v2); v3 = sqrtf(v3); }
+      s += (double)v0 + (double)v1 + (double)v2 + (double)v3;
+      ss += (double)v0 * v0 + (double)v1 * v1 + (double)v2 * v2 + (double)v3 * v3;
+    }
+    for (; r < r1; r += RY) {
+      float v = U[(size_t)r * D + col];
+      if (SQRT) v = sqrtf(v);
+      s += v;
+      ss += (double)v * v;
+    }
+  }
+  __shared__ double sh[2][RY][CW];
+  sh[0][threadIdx.y][threadIdx.x] = s;
+  sh[1][threadIdx.y][threadIdx.x] = ss;
+  __syncthreads();
+  if (threadIdx.y < 2 && col < D) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < RY; ++i) t += sh[threadIdx.y][i][threadIdx.x];
+    atomicAdd(&acc[(size_t)threadIdx.y * D + col], t);
+  }
+}
+
+__global__ void k_colstats_finalize(const double* __restrict__ acc, int B, int D, float eps, float momentum,
+                                    float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ rmean,
+                                    float* __restrict__ rvar) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D) return;
+  double m = acc[i] / B;
+  double var = acc[D + i] / B - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[i] = (float)m;
+  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+  if (rmean) {
+    double unbiased = var * ((double)B / (double)(B - 1));
+    rmean[i] = (float)((1.0 - momentum) * rmean[i] + momentum * m);
+    rvar[i] = (float)((1.0 - momentum) * rvar[i] + momentum * unbiased);
+  }
+}
+
+__global__ void __launch_bounds__(CW* RY) k_bn_bwd_reduce(const float* __restrict__ dY, const float* __restrict__ U, int B,
+                                                           int D, int rows_per_cta, BnParams bn,
+                                                           double* __restrict__ acc) {
+  int col = blockIdx.x * CW + threadIdx.x;
+  int r0 = blockIdx.y * rows_per_cta;
+  int r1 = min(B, r0 + rows_per_cta);
+  double s1 = 0.0, s2 = 0.0;
+  if (col < D) {
+    float mean = bn.mean[col], rstd = bn.rstd[col];
+    for (int r = r0 + threadIdx.y; r < r1; r += RY) {
+      float g = dY[(size_t)r * D + col];
+      float xh = bn_xhat(U[(size_t)r * D + col], mean, rstd);
+      s1 += g;
+      s2 += (double)g * xh;
+    }
+  }
+  __shared__ double sh[2][RY][CW];
+  sh[0][threadIdx.y][threadIdx.x] = s1;
+  sh[1][threadIdx.y][threadIdx.x] = s2;
+  __syncthreads();
+  if (threadIdx.y < 2 && col < D) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < RY; ++i) t += sh[threadIdx.y][i][threadIdx.x];
+    atomicAdd(&acc[(size_t)threadIdx.y * D + col], t);
+  }
+}
+
+__global__ void k_bn_bwd_apply(float* __restrict__ dY, const float* __restrict__ U, int B, int D, BnParams bn,
+                               const double* __restrict__ acc, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  size_t n = (size_t)B * D;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    int col = (int)(idx % D);
+    float s1 = (float)(acc[col] / B), s2 = (float)(acc[D + col] / B);
+    float rstd = bn.rstd[col];
+    float xh = bn_xhat(U[idx], bn.mean[col], rstd);
+    dY[idx] = bn.gamma[col] * rstd * (dY[idx] - s1 - xh * s2);
+    if (idx < (size_t)D) {
+      dbeta[col] = (float)acc[col];
+      dgamma[col] = (float)acc[D + col];
+    }
+  }
+}
+
+__global__ void k_bn_grad_finalize(const double* __restrict__ acc, int D, float* __restrict__ dgamma,
+                                   float* __restrict__ dbeta) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D) return;
+  dbeta[i] = (float)acc[i];
+  dgamma[i] = (float)acc[D + i];
+}
+
+__global__ void k_bump(int64_t* c, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) c[i] += 1;
+}
+
+__global__ void k_finalize_status(drv_step_out* out) {
+  if (isnan(out->loss)) out->status |= DRV_STATUS_NAN_LOSS;
+}
+
+}  // namespace
+
+void colstats_accumulate(const float* U, int B, int D, bool sqrt_in, double* acc, cudaStream_t st) {
+  int S = row_splits(B, D);
+  int rows = cdiv(B, S);
+  rows = cdiv(rows, RY) * RY;
+  S = cdiv(B, rows);
+  dim3 grid(cdiv(D, CW), S), block(CW, RY);
+  if (sqrt_in) k_colstats<true><<<grid, block, 0, st>>>(U, B, D, rows, acc);
+  else k_colstats<false><<<grid, block, 0, st>>>(U, B, D, rows, acc);
+  note_launch();
+}
+
+void colstats_finalize(const double* acc, int B, int D, float eps, float momentum, float* mean, float* rstd,
+                       float* running_mean, float* running_var, cudaStream_t st) {
+  k_colstats_finalize<<<cdiv(D, 256), 256, 0, st>>>(acc, B, D, eps, momentum, mean, rstd, running_mean, running_var);
+  note_launch();
+}
+
+void bn_bwd_reduce(const float* dY, const float* U, int B, int D, BnParams bn, double* acc, cudaStream_t st) {
+  int S = row_splits(B, D);
+  int rows = cdiv(B, S);
+  rows = cdiv(rows, RY) * RY;
+  S = cdiv(B, rows);
+  dim3 grid(cdiv(D, CW), S), block(CW, RY);
+  k_bn_bwd_reduce<<<grid, block, 0, st>>>(dY, U, B, D, rows, bn, acc);
+  note_launch();
+}
+
+void bn_bwd_apply(float* dY_dU, const float* U, int B, int D, BnParams bn, const double* acc, float* dgamma,
+                  float* dbeta, cudaStream_t st) {
+  size_t n = (size_t)B * D;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_bn_bwd_apply<<<blocks, 256, 0, st>>>(dY_dU, U, B, D, bn, acc, dgamma, dbeta);
+  note_launch();
+}
+
+void bn_grad_finalize(const double* acc, int D, float* dgamma, float* dbeta, cudaStream_t st) {
+  k_bn_grad_finalize<<<cdiv(D, 256), 256, 0, st>>>(acc, D, dgamma, dbeta);
+  note_launch();
+}
+
+void bump_counters(int64_t* counters, int n, cudaStream_t st) {
+  k_bump<<<cdiv(n, 64), 64, 0, st>>>(counters, n);
+  note_launch();
+}
+
+void finalize_status(drv_step_out* out, cudaStream_t st) {
+  k_finalize_status<<<1, 1, 0, st>>>(out);
+  note_launch();
+}
+
+}  // namespace drv

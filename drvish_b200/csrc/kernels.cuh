@@ -1,0 +1,70 @@
+// Host-callable launchers of the drvish_b200 kernels (internal; the public surface is
+// include/drvish_b200.h).
+#pragma once
+#include "common.cuh"
+
+namespace drv {
+
+// ---- k_stats.cu: BatchNorm statistics and their backward ------------------------------------
+// acc: [2][D] doubles, zero on entry.  sum / sum of squares of (sqrt?)U over the batch.
+void colstats_accumulate(const float* U, int B, int D, bool sqrt_in, double* acc, cudaStream_t st);
+// mean / rstd from acc; running buffers updated like torch BatchNorm1d in training mode.
+void colstats_finalize(const double* acc, int B, int D, float eps, float momentum, float* mean, float* rstd,
+                       float* running_mean, float* running_var, cudaStream_t st);
+// acc[0][i] += sum_b dY, acc[1][i] += sum_b dY * xhat
+void bn_bwd_reduce(const float* dY, const float* U, int B, int D, BnParams bn, double* acc, cudaStream_t st);
+// dU = gamma rstd (dY - s1/B - xhat s2/B) in place over dY; also dgamma = s2, dbeta = s1.
+void bn_bwd_apply(float* dY_dU, const float* U, int B, int D, BnParams bn, const double* acc, float* dgamma,
+                  float* dbeta, cudaStream_t st);
+void bn_grad_finalize(const double* acc, int D, float* dgamma, float* dbeta, cudaStream_t st);
+void bump_counters(int64_t* counters, int n, cudaStream_t st);
+
+// ---- k_gemm_simt.cu ---------------------------------------------------------------------------
+void simt_linear_forward(const float* U, int B, int din, int pro_mode, BnParams bn, const float* W, const float* bias,
+                         int dout, float* V, cudaStream_t st);
+void simt_linear_wgrad(const float* dV, int B, int dout, const float* U, int din, int pro_mode, BnParams bn, float* dW,
+                       float* db, cudaStream_t st);
+void simt_linear_dgrad_gate(const float* dV, int B, int dout, const float* W, int din, const float* U, int pro_mode,
+                            BnParams bn, float* dY, cudaStream_t st);
+void simt_linear_dgrad_bngrad(const float* dV, int B, int dout, const float* W, int din, const float* U, int pro_mode,
+                              BnParams bn, double* acc, cudaStream_t st);
+
+// ---- k_nb.cu: gene-softmax + library scaling + NB log-likelihood on materialised logits -------
+// logits [B][2G] = [scale | log_r]; bwd: overwritten with d loss / d logits.
+void nb_rows(float* logits, const float* x, const float* lib, int B, int G, float eps, float scale_factor, bool bwd,
+             float* lse, float* ll, float* asum, drv_step_out* out, cudaStream_t st);
+// NBDecoder.forward outputs from materialised logits
+void nb_decoder_outputs(const float* logits, const float* lib, int B, int G, float* log_r, float* logit, cudaStream_t st);
+
+// ---- k_sample.cu --------------------------------------------------------------------------------
+void sample_forward(const float* O, const float* eps_z, const float* eps_l, int B, int L, const drv_hparams& hp,
+                    float* z, float* l, drv_step_out* out, cudaStream_t st);
+void sample_backward(const float* O, const float* eps_z, const float* eps_l, const float* z, const float* l,
+                     const float* dz_dec, const float* dz_drs, const float* asum, int B, int L, const drv_hparams& hp,
+                     float* dO, cudaStream_t st);
+void encoder_outputs(const float* O, int B, int L, float* z_loc, float* z_scale, float* l_loc, float* l_scale,
+                     cudaStream_t st);
+void fill_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, cudaStream_t st);
+void fill_laplace(float* out, int64_t n, uint64_t seed, uint64_t offset, cudaStream_t st);
+
+// ---- k_dr.cu: dose-response head ----------------------------------------------------------------
+struct DrShape {
+  int B, L, D, K, T;  // T = total doses
+};
+// u[b][i] = z[b,:] . w[i,:]
+void dr_project(const float* z, const float* w, DrShape s, float* u, cudaStream_t st);
+// per (drug, dose) slot: class means of sigmoid(u + bias), clamp+logit -> m[i][k][c] (drug-major);
+// if y != NULL also adds -sum log N(y | m, sigma) to out->loss and writes gfac[k][slot] = d loss / d resp / n_k.
+void dr_means(const float* u, const float* bias, const int64_t* labels, const int32_t* dose_off, DrShape s,
+              const float* y, float sigma, float* m, float* gfac, drv_step_out* out, uint32_t* status, cudaStream_t st);
+// du[b][i] then dz[b][d] = sum_i du[b][i] w[i][d]
+void dr_backward(const float* u, const float* bias, const float* w, const int64_t* labels, const int32_t* dose_off,
+                 const float* gfac, DrShape s, float* du, float* dz, cudaStream_t st);
+// prior log-probs of the prior draws + guide-side monotonic factor and its gradients
+void dr_prior_factor(const float* w_prior, const float* b_prior, const float* eps_bias, const float* bias_loc,
+                     const float* bias_scale_unc, const int32_t* dose_off, DrShape s, const drv_hparams& hp,
+                     float* d_bias_loc, float* d_bias_scale_unc, drv_step_out* out, cudaStream_t st);
+
+void finalize_status(drv_step_out* out, cudaStream_t st);
+
+}  // namespace drv

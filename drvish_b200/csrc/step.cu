@@ -1,0 +1,497 @@
+// Host-side orchestration of one SVI step and the C ABI (include/drvish_b200.h).
+// Replaces, for one minibatch, everything between svi.step(*xs) being entered and the
+// per-parameter .grad tensors being populated: guide trace (encoder, rsample),
+// model trace (priors, decoder, NB likelihood, dose-response head), ELBO assembly and autograd.
+// Everything is enqueued on the caller's stream; no allocation, no host synchronisation.
+#include <string.h>
+
+#include "kernels.cuh"
+#include "tc.cuh"
+
+namespace drv {
+
+thread_local int g_launches = 0;
+thread_local cudaError_t g_err = cudaSuccess;
+
+// Optional section timing with CUDA events recorded on the step's own stream (bench.py's live
+// roofline measurement).  Sections: see DRV_SEC_* in the public header.
+namespace prof {
+constexpr int MAX_STEPS = 64;
+bool enabled = false;
+int n_steps = 0;
+cudaEvent_t ev[MAX_STEPS][DRV_N_SECTIONS + 1];
+bool created = false;
+inline void mark(int i, cudaStream_t st) {
+  if (enabled && n_steps < MAX_STEPS) cudaEventRecord(ev[n_steps][i], st);
+}
+}  // namespace prof
+
+namespace {
+
+constexpr int64_t ALIGN_F = 32;  // tensors start on 128-byte boundaries inside the flat buffers
+
+inline int64_t up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+struct Block {      // one BatchNorm1d -> ReLU -> Linear triple of make_fc (modules.py:15-23)
+  int din, dout;
+  int64_t gamma, beta, W, bias;   // float offsets in the flat parameter buffer
+  int64_t rmean, rvar;            // float offsets in the flat BN-buffer
+};
+
+struct Net {
+  int n_blocks;
+  Block enc[DRV_MAX_LAYERS + 1], dec[DRV_MAX_LAYERS + 1];
+  int64_t w_loc, w_scale, b_loc, b_scale;  // dose-response guide parameters (D > 0)
+  int64_t n_param_floats, n_bn_floats;
+  int n_bn;
+};
+
+bool valid(const drv_dims* d) {
+  if (!d) return false;
+  if (d->n_cells < 2 || d->n_genes < 1 || d->n_latent < 1) return false;
+  if (d->n_layers < 1 || d->n_layers > DRV_MAX_LAYERS) return false;
+  for (int i = 0; i < d->n_layers; ++i)
+    if (d->layers[i] < 1) return false;
+  if (d->n_drugs < 0) return false;
+  if (d->n_drugs > 0 && (d->n_classes < 1 || d->n_doses_total < d->n_drugs)) return false;
+  return true;
+}
+
+Net make_net(const drv_dims& d) {
+  Net n{};
+  n.n_blocks = d.n_layers + 1;
+  int64_t p = 0, q = 0;
+  auto stack = [&](Block* blk, const int* dims) {
+    for (int k = 0; k < n.n_blocks; ++k) {
+      Block& b = blk[k];
+      b.din = dims[k];
+      b.dout = dims[k + 1];
+      b.gamma = p; p = up(p + b.din, ALIGN_F);
+      b.beta = p;  p = up(p + b.din, ALIGN_F);
+      b.W = p;     p = up(p + (int64_t)b.dout * b.din, ALIGN_F);
+      b.bias = p;  p = up(p + b.dout, ALIGN_F);
+      b.rmean = q; q = up(q + b.din, ALIGN_F);
+      b.rvar = q;  q = up(q + b.din, ALIGN_F);
+    }
+  };
+  int ed[DRV_MAX_LAYERS + 2], dd[DRV_MAX_LAYERS + 2];
+  ed[0] = d.n_genes;
+  dd[0] = d.n_latent;
+  for (int i = 0; i < d.n_layers; ++i) {
+    ed[i + 1] = d.layers[i];
+    dd[i + 1] = d.layers[d.n_layers - 1 - i];
+  }
+  ed[d.n_layers + 1] = 2 * d.n_latent + 2;
+  dd[d.n_layers + 1] = 2 * d.n_genes;
+  stack(n.enc, ed);
+  stack(n.dec, dd);
+  if (d.n_drugs > 0) {
+    n.w_loc = p;   p = up(p + (int64_t)d.n_drugs * d.n_latent, ALIGN_F);
+    n.w_scale = p; p = up(p + (int64_t)d.n_drugs * d.n_latent, ALIGN_F);
+    n.b_loc = p;   p = up(p + d.n_doses_total, ALIGN_F);
+    n.b_scale = p; p = up(p + d.n_doses_total, ALIGN_F);
+  }
+  n.n_param_floats = p;
+  n.n_bn_floats = q;
+  n.n_bn = 2 * n.n_blocks;
+  return n;
+}
+
+// workspace carve-up (byte offsets, 256-byte aligned)
+struct Plan {
+  size_t zero_begin, zero_bytes;            // region cleared at the start of every step
+  size_t stat_acc[2][DRV_MAX_LAYERS + 1];   // [enc/dec][block]: double[2*din] forward statistics
+  size_t grad_acc[2][DRV_MAX_LAYERS + 1];   // double[2*din] backward sums
+  size_t status;                             // uint32
+  size_t mean[2][DRV_MAX_LAYERS + 1], rstd[2][DRV_MAX_LAYERS + 1];
+  size_t V[2][DRV_MAX_LAYERS + 1];          // Linear outputs (B x dout); dec last = logits B x 2G
+  size_t Gb[2][DRV_MAX_LAYERS + 1];         // dY / dU of each block input (B x din), block 0 of enc unused
+  size_t z, l, lse, ll, asum, dO;
+  size_t u, m, gfac, du, dz_drs;
+  size_t tc;                                 // scratch of the tcgen05 path
+  size_t total;
+};
+
+Plan make_plan(const drv_dims& d, const Net& n) {
+  Plan p{};
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = (o + bytes + 255) / 256 * 256; return r; };
+  const size_t B = d.n_cells;
+  p.zero_begin = o;
+  for (int s = 0; s < 2; ++s)
+    for (int k = 0; k < n.n_blocks; ++k) {
+      const Block& b = s == 0 ? n.enc[k] : n.dec[k];
+      p.stat_acc[s][k] = take(sizeof(double) * 2 * b.din);
+      p.grad_acc[s][k] = take(sizeof(double) * 2 * b.din);
+    }
+  p.status = take(256);
+  p.zero_bytes = o - p.zero_begin;
+  for (int s = 0; s < 2; ++s)
+    for (int k = 0; k < n.n_blocks; ++k) {
+      const Block& b = s == 0 ? n.enc[k] : n.dec[k];
+      p.mean[s][k] = take(4 * (size_t)b.din);
+      p.rstd[s][k] = take(4 * (size_t)b.din);
+      p.V[s][k] = take(4 * B * b.dout);
+      p.Gb[s][k] = (s == 0 && k == 0) ? 0 : take(4 * B * b.din);
+    }
+  p.z = take(4 * B * d.n_latent);
+  p.l = take(4 * B);
+  p.lse = take(4 * B);
+  p.ll = take(4 * B);
+  p.asum = take(4 * B);
+  p.dO = take(4 * B * (2 * d.n_latent + 2));
+  if (d.n_drugs > 0) {
+    p.u = take(4 * B * d.n_drugs);
+    p.du = take(4 * B * d.n_drugs);
+    p.dz_drs = take(4 * B * d.n_latent);
+    p.m = take(4 * (size_t)d.n_classes * d.n_doses_total);
+    p.gfac = take(4 * (size_t)d.n_classes * d.n_doses_total);
+  }
+  p.tc = o;
+  o += tc_workspace_bytes(d);
+  o = (o + 255) / 256 * 256;
+  p.total = o;
+  return p;
+}
+
+struct Ctx {
+  const drv_dims& d;
+  const drv_hparams& hp;
+  const Net& n;
+  const Plan& p;
+  char* ws;
+  const float* params;
+  float* grads;
+  float* bnbuf;
+  cudaStream_t st;
+  template <class T> T* at(size_t off) const { return reinterpret_cast<T*>(ws + off); }
+  BnParams bn(int s, int k) const {
+    const Block& b = s == 0 ? n.enc[k] : n.dec[k];
+    return BnParams{at<float>(p.mean[s][k]), at<float>(p.rstd[s][k]), params + b.gamma, params + b.beta};
+  }
+};
+
+// One BatchNorm1d -> ReLU -> Linear block, forward: batch statistics (+ running buffers), then
+// optionally the Linear with the BN/ReLU (and sqrt for the encoder input) applied in its prologue.
+void block_forward(const Ctx& c, int s, int k, const float* U0, bool do_linear) {
+  const int B = c.d.n_cells;
+  const bool update = !(c.hp.flags & DRV_FLAG_NO_BN_UPDATE) && c.bnbuf;
+  const Block& b = s == 0 ? c.n.enc[k] : c.n.dec[k];
+  const float* U = k == 0 ? U0 : c.at<float>(c.p.V[s][k - 1]);
+  const bool sq = (s == 0 && k == 0);
+  double* acc = c.at<double>(c.p.stat_acc[s][k]);
+  colstats_accumulate(U, B, b.din, sq, acc, c.st);
+  colstats_finalize(acc, B, b.din, c.hp.bn_eps, c.hp.bn_momentum, c.at<float>(c.p.mean[s][k]),
+                    c.at<float>(c.p.rstd[s][k]), update ? c.bnbuf + b.rmean : nullptr,
+                    update ? c.bnbuf + b.rvar : nullptr, c.st);
+  if (do_linear)
+    simt_linear_forward(U, B, b.din, sq ? 2 : 1, c.bn(s, k), c.params + b.W, c.params + b.bias, b.dout,
+                        c.at<float>(c.p.V[s][k]), c.st);
+}
+
+// Backward of block k given dV of its Linear: dW, db, then dY = (dV W) * relu-gate, then the
+// BatchNorm backward (d gamma, d beta, dU in place).  `linear_done`: dW/db/dY were already
+// produced (fused tcgen05 path).  The first encoder block needs no dU (x is data): its dY is
+// reduced to d gamma / d beta on the fly.
+void block_backward(const Ctx& c, int s, int k, const float* U0, const float* dV, bool linear_done) {
+  const int B = c.d.n_cells;
+  const Block& b = s == 0 ? c.n.enc[k] : c.n.dec[k];
+  const float* U = k == 0 ? U0 : c.at<float>(c.p.V[s][k - 1]);
+  const bool sq = (s == 0 && k == 0);
+  const int pro = sq ? 2 : 1;
+  double* gacc = c.at<double>(c.p.grad_acc[s][k]);
+  if (!linear_done) {
+    simt_linear_wgrad(dV, B, b.dout, U, b.din, pro, c.bn(s, k), c.grads + b.W, c.grads + b.bias, c.st);
+    if (sq)
+      simt_linear_dgrad_bngrad(dV, B, b.dout, c.params + b.W, b.din, U, pro, c.bn(s, k), gacc, c.st);
+    else
+      simt_linear_dgrad_gate(dV, B, b.dout, c.params + b.W, b.din, U, pro, c.bn(s, k), c.at<float>(c.p.Gb[s][k]), c.st);
+  }
+  if (sq) {
+    bn_grad_finalize(gacc, b.din, c.grads + b.gamma, c.grads + b.beta, c.st);
+  } else {
+    float* dY = c.at<float>(c.p.Gb[s][k]);
+    bn_bwd_reduce(dY, U, B, b.din, c.bn(s, k), gacc, c.st);
+    bn_bwd_apply(dY, U, B, b.din, c.bn(s, k), gacc, c.grads + b.gamma, c.grads + b.beta, c.st);
+  }
+}
+
+int finish() {
+  cudaError_t e = g_err;
+  g_err = cudaSuccess;
+  return (int)e;
+}
+
+}  // namespace
+}  // namespace drv
+
+using namespace drv;
+
+extern "C" {
+
+const char* drv_version(void) { return "drvish_b200 0.1.0 sm_100a"; }
+
+int drv_last_launch_count(void) { return g_launches; }
+
+int drv_param_offsets(const drv_dims* dims, int64_t* offsets, int64_t* sizes, int max_n, int64_t* total_floats) {
+  if (!valid(dims)) return DRV_EINVAL;
+  Net n = make_net(*dims);
+  int cnt = 0;
+  auto put = [&](int64_t off, int64_t sz) {
+    if (cnt < max_n) {
+      if (offsets) offsets[cnt] = off;
+      if (sizes) sizes[cnt] = sz;
+    }
+    ++cnt;
+  };
+  for (int s = 0; s < 2; ++s)
+    for (int k = 0; k < n.n_blocks; ++k) {
+      const Block& b = s == 0 ? n.enc[k] : n.dec[k];
+      put(b.gamma, b.din);
+      put(b.beta, b.din);
+      put(b.W, (int64_t)b.dout * b.din);
+      put(b.bias, b.dout);
+    }
+  if (dims->n_drugs > 0) {
+    put(n.w_loc, (int64_t)dims->n_drugs * dims->n_latent);
+    put(n.w_scale, (int64_t)dims->n_drugs * dims->n_latent);
+    put(n.b_loc, dims->n_doses_total);
+    put(n.b_scale, dims->n_doses_total);
+  }
+  if (total_floats) *total_floats = n.n_param_floats;
+  return cnt;
+}
+
+int drv_bn_offsets(const drv_dims* dims, int64_t* offsets, int64_t* sizes, int max_n, int64_t* total_floats) {
+  if (!valid(dims)) return DRV_EINVAL;
+  Net n = make_net(*dims);
+  int cnt = 0;
+  for (int s = 0; s < 2; ++s)
+    for (int k = 0; k < n.n_blocks; ++k) {
+      const Block& b = s == 0 ? n.enc[k] : n.dec[k];
+      if (cnt + 1 < max_n) {
+        if (offsets) { offsets[cnt] = b.rmean; offsets[cnt + 1] = b.rvar; }
+        if (sizes) { sizes[cnt] = b.din; sizes[cnt + 1] = b.din; }
+      }
+      cnt += 2;
+    }
+  if (total_floats) *total_floats = n.n_bn_floats;
+  return cnt;
+}
+
+size_t drv_workspace_bytes(const drv_dims* dims) {
+  if (!valid(dims)) return 0;
+  Net n = make_net(*dims);
+  return make_plan(*dims, n).total;
+}
+
+int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, const int64_t* labels, const float* y,
+                  const float* eps_z, const float* eps_l, const float* w_prior, const float* b_prior,
+                  const float* eps_bias, const int32_t* dose_offsets, const float* params, float* grads,
+                  float* bn_running, int64_t* bn_batches, drv_step_out* out, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+  g_launches = 0;
+  g_err = cudaSuccess;
+  if (!valid(dims) || !hp || !x || !eps_z || !eps_l || !params || !out || !workspace) return DRV_EINVAL;
+  const drv_dims& d = *dims;
+  if (d.n_drugs > 0 && (!labels || !y || !w_prior || !b_prior || !eps_bias || !dose_offsets)) return DRV_EINVAL;
+  Net n = make_net(d);
+  Plan p = make_plan(d, n);
+  if (workspace_bytes < p.total) return DRV_ENOSPC;
+  cudaStream_t st = (cudaStream_t)stream;
+  Ctx c{d, *hp, n, p, (char*)workspace, params, grads, bn_running, st};
+  const int B = d.n_cells, G = d.n_genes, L = d.n_latent;
+  const bool bwd = grads != nullptr;
+
+  cudaMemsetAsync(c.ws + p.zero_begin, 0, p.zero_bytes, st);
+  cudaMemsetAsync(out, 0, sizeof(drv_step_out), st);
+  uint32_t* status = c.at<uint32_t>(p.status);
+
+  const int NB = n.n_blocks;
+  prof::mark(0, st);
+  // ---- guide: encoder + reparameterised draws (nbvae.py:81-90) --------------------------------
+  for (int k = 0; k < NB; ++k) block_forward(c, 0, k, x, true);
+  const float* O = c.at<float>(p.V[0][NB - 1]);
+  float* z = c.at<float>(p.z);
+  float* l = c.at<float>(p.l);
+  sample_forward(O, eps_z, eps_l, B, L, *hp, z, l, out, st);
+  prof::mark(1, st);
+
+  // ---- model: decoder trunk (nbvae.py:70 -> modules.py:93) ------------------------------------
+  const Block& last = n.dec[NB - 1];
+  const bool use_tc = tc_decoder_supported(d, *hp);
+  for (int k = 0; k < NB - 1; ++k) block_forward(c, 1, k, z, true);
+  block_forward(c, 1, NB - 1, z, false);  // statistics of the last BatchNorm only
+  prof::mark(2, st);
+
+  // ---- last Linear + gene softmax + NB likelihood (modules.py:93-96, nbvae.py:72-78) ----------
+  float* dlogits = c.at<float>(p.V[1][NB - 1]);
+  TcDecoderArgs ta{};
+  if (use_tc) {
+    ta.U = c.at<float>(p.V[1][NB - 2]); ta.bn = c.bn(1, NB - 1); ta.W = params + last.W; ta.bias = params + last.bias;
+    ta.x = x; ta.lib = l; ta.B = B; ta.G = G; ta.h = last.din; ta.eps = hp->epsilon; ta.c = hp->scale_factor;
+    ta.lse = c.at<float>(p.lse); ta.ll = c.at<float>(p.ll); ta.asum = c.at<float>(p.asum); ta.out = out;
+    ta.scratch = c.ws + p.tc; ta.dlogits = dlogits; ta.bwd = bwd;
+    ta.dW = bwd ? grads + last.W : nullptr; ta.db = bwd ? grads + last.bias : nullptr;
+    ta.dY = c.at<float>(p.Gb[1][NB - 1]);
+    tc_decoder_forward(ta, st);
+  } else {
+    simt_linear_forward(c.at<float>(p.V[1][NB - 2]), B, last.din, 1, c.bn(1, NB - 1), params + last.W,
+                        params + last.bias, last.dout, dlogits, st);
+    nb_rows(dlogits, x, l, B, G, hp->epsilon, hp->scale_factor, bwd, c.at<float>(p.lse), c.at<float>(p.ll),
+            c.at<float>(p.asum), out, st);
+  }
+  prof::mark(3, st);
+
+  // ---- dose-response head (drnbvae.py:110-116, 131-132) ---------------------------------------
+  DrShape ds{B, L, d.n_drugs, d.n_classes, d.n_doses_total};
+  if (d.n_drugs > 0) {
+    dr_project(z, w_prior, ds, c.at<float>(p.u), st);
+    dr_means(c.at<float>(p.u), b_prior, labels, dose_offsets, ds, y, hp->sigma_scale, c.at<float>(p.m),
+             c.at<float>(p.gfac), out, status, st);
+    if (bwd) {
+      // weight_loc / weight_scale never enter the loss: their gradient is zero
+      cudaMemsetAsync(grads + n.w_loc, 0, sizeof(float) * (size_t)(n.b_loc - n.w_loc), st);
+    }
+    dr_prior_factor(w_prior, b_prior, eps_bias, params + n.b_loc, params + n.b_scale, dose_offsets, ds, *hp,
+                    bwd ? grads + n.b_loc : nullptr, bwd ? grads + n.b_scale : nullptr, out, st);
+    if (bwd)
+      dr_backward(c.at<float>(p.u), b_prior, w_prior, labels, dose_offsets, c.at<float>(p.gfac), ds,
+                  c.at<float>(p.du), c.at<float>(p.dz_drs), st);
+  }
+  prof::mark(4, st);
+
+  if (bwd) {
+    // ---- backward of the last decoder Linear ---------------------------------------------------
+    if (use_tc) {
+      tc_decoder_backward(ta, st);
+    } else {
+      simt_linear_wgrad(dlogits, B, last.dout, c.at<float>(p.V[1][NB - 2]), last.din, 1, c.bn(1, NB - 1),
+                        grads + last.W, grads + last.bias, st);
+      simt_linear_dgrad_gate(dlogits, B, last.dout, params + last.W, last.din, c.at<float>(p.V[1][NB - 2]), 1,
+                             c.bn(1, NB - 1), c.at<float>(p.Gb[1][NB - 1]), st);
+    }
+    prof::mark(5, st);
+    // ---- decoder trunk backward, sampling backward ---------------------------------------------
+    block_backward(c, 1, NB - 1, z, nullptr, true);
+    for (int k = NB - 2; k >= 0; --k) block_backward(c, 1, k, z, c.at<float>(p.Gb[1][k + 1]), false);
+    sample_backward(O, eps_z, eps_l, z, l, c.at<float>(p.Gb[1][0]), d.n_drugs > 0 ? c.at<float>(p.dz_drs) : nullptr,
+                    c.at<float>(p.asum), B, L, *hp, c.at<float>(p.dO), st);
+    prof::mark(6, st);
+    // ---- encoder backward ----------------------------------------------------------------------
+    for (int k = NB - 1; k >= 0; --k)
+      block_backward(c, 0, k, x, k == NB - 1 ? c.at<float>(p.dO) : c.at<float>(p.Gb[0][k + 1]), false);
+    prof::mark(7, st);
+  }
+  if (bn_batches && !(hp->flags & DRV_FLAG_NO_BN_UPDATE)) bump_counters(bn_batches, n.n_bn, st);
+  // fold the status word into the result record
+  {
+    cudaMemcpyAsync(&out->status, status, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
+    finalize_status(out, st);
+  }
+  if (prof::enabled && prof::n_steps < prof::MAX_STEPS) {
+    if (!bwd) for (int i = 5; i <= DRV_N_SECTIONS; ++i) prof::mark(i, st);
+    ++prof::n_steps;
+  }
+  return finish();
+}
+
+int drv_profile_enable(int on) {
+  if (on && !prof::created) {
+    for (int i = 0; i < prof::MAX_STEPS; ++i)
+      for (int j = 0; j <= DRV_N_SECTIONS; ++j)
+        if (cudaEventCreate(&prof::ev[i][j]) != cudaSuccess) return (int)cudaGetLastError();
+    prof::created = true;
+  }
+  prof::enabled = on != 0;
+  prof::n_steps = 0;
+  return 0;
+}
+
+int drv_profile_read(float* h_ms_per_section, int* h_n_steps) {
+  if (!prof::created) return DRV_EINVAL;
+  int ns = prof::n_steps;
+  for (int j = 0; j < DRV_N_SECTIONS; ++j) h_ms_per_section[j] = 0.f;
+  for (int i = 0; i < ns; ++i) {
+    cudaError_t e = cudaEventSynchronize(prof::ev[i][DRV_N_SECTIONS]);
+    if (e != cudaSuccess) return (int)e;
+    for (int j = 0; j < DRV_N_SECTIONS; ++j) {
+      float ms = 0.f;
+      e = cudaEventElapsedTime(&ms, prof::ev[i][j], prof::ev[i][j + 1]);
+      if (e != cudaSuccess) return (int)e;
+      h_ms_per_section[j] += ms / ns;
+    }
+  }
+  if (h_n_steps) *h_n_steps = ns;
+  return 0;
+}
+
+int drv_encoder_forward(const drv_dims* dims, const drv_hparams* hp, const float* x, const float* params,
+                        float* bn_running, int64_t* bn_batches, float* z_loc, float* z_scale, float* l_loc,
+                        float* l_scale, void* workspace, size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  g_err = cudaSuccess;
+  if (!valid(dims) || !hp || !x || !params || !workspace) return DRV_EINVAL;
+  Net n = make_net(*dims);
+  Plan p = make_plan(*dims, n);
+  if (workspace_bytes < p.total) return DRV_ENOSPC;
+  cudaStream_t st = (cudaStream_t)stream;
+  Ctx c{*dims, *hp, n, p, (char*)workspace, params, nullptr, bn_running, st};
+  cudaMemsetAsync(c.ws + p.zero_begin, 0, p.zero_bytes, st);
+  for (int k = 0; k < n.n_blocks; ++k) block_forward(c, 0, k, x, true);
+  encoder_outputs(c.at<float>(p.V[0][n.n_blocks - 1]), dims->n_cells, dims->n_latent, z_loc, z_scale, l_loc, l_scale, st);
+  if (bn_batches && !(hp->flags & DRV_FLAG_NO_BN_UPDATE)) bump_counters(bn_batches, n.n_blocks, st);
+  return finish();
+}
+
+int drv_decoder_forward(const drv_dims* dims, const drv_hparams* hp, const float* z, const float* library,
+                        const float* params, float* bn_running, int64_t* bn_batches, float* log_r, float* logit,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  g_err = cudaSuccess;
+  if (!valid(dims) || !hp || !z || !library || !params || !workspace) return DRV_EINVAL;
+  Net n = make_net(*dims);
+  Plan p = make_plan(*dims, n);
+  if (workspace_bytes < p.total) return DRV_ENOSPC;
+  cudaStream_t st = (cudaStream_t)stream;
+  Ctx c{*dims, *hp, n, p, (char*)workspace, params, nullptr, bn_running, st};
+  cudaMemsetAsync(c.ws + p.zero_begin, 0, p.zero_bytes, st);
+  for (int k = 0; k < n.n_blocks; ++k) block_forward(c, 1, k, z, true);
+  nb_decoder_outputs(c.at<float>(p.V[1][n.n_blocks - 1]), library, dims->n_cells, dims->n_genes, log_r, logit, st);
+  if (bn_batches && !(hp->flags & DRV_FLAG_NO_BN_UPDATE)) bump_counters(bn_batches + n.n_blocks, n.n_blocks, st);
+  return finish();
+}
+
+int drv_logit_mean_sigmoid(const drv_dims* dims, const float* z, const float* w, const float* b, const int64_t* labels,
+                           const int32_t* dose_offsets, float* out, uint32_t* status, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  g_err = cudaSuccess;
+  if (!valid(dims) || dims->n_drugs < 1 || !z || !w || !b || !labels || !dose_offsets || !out || !status || !workspace)
+    return DRV_EINVAL;
+  if (workspace_bytes < sizeof(float) * (size_t)dims->n_cells * dims->n_drugs) return DRV_ENOSPC;
+  cudaStream_t st = (cudaStream_t)stream;
+  DrShape ds{dims->n_cells, dims->n_latent, dims->n_drugs, dims->n_classes, dims->n_doses_total};
+  cudaMemsetAsync(status, 0, sizeof(uint32_t), st);
+  dr_project(z, w, ds, (float*)workspace, st);
+  dr_means((const float*)workspace, b, labels, dose_offsets, ds, nullptr, 1.f, out, nullptr, nullptr, status, st);
+  return finish();
+}
+
+int drv_fill_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
+  g_launches = 0;
+  g_err = cudaSuccess;
+  if (!out || n < 0) return DRV_EINVAL;
+  fill_normal(out, n, seed, offset, (cudaStream_t)stream);
+  return finish();
+}
+
+int drv_fill_laplace(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
+  g_launches = 0;
+  g_err = cudaSuccess;
+  if (!out || n < 0) return DRV_EINVAL;
+  fill_laplace(out, n, seed, offset, (cudaStream_t)stream);
+  return finish();
+}
+
+}  // extern "C"

@@ -1,0 +1,172 @@
+"""The fused ELBO: a drop-in for ``pyro.infer.Trace_ELBO`` / ``TraceGraph_ELBO`` as the ``loss=``
+of ``pyro.infer.SVI`` for the drvish models (reference notebook cell 10; call sites
+src/drvish/train/__init__.py:46,90-93).
+
+``SVI.step(*batch)`` calls ``loss.loss_and_grads(model, guide, *batch)`` and
+``SVI.evaluate_loss`` calls ``loss.loss(model, guide, *batch)``; both are implemented here by ONE
+call into ``drv_elbo_step`` (no tracing, no autograd graph).  Gradients are left in
+``param.grad`` exactly where Pyro's ``loss.backward()`` would leave them, BatchNorm running
+buffers are updated in place, and the Python float loss is returned.
+
+Data parallel: with ``torch.distributed`` initialised (one process per GPU) the
+flat gradient buffer is summed over ranks with ONE NCCL all-reduce per step; the loss rides in
+the tail slot of the same buffer.  The R-rank result is sum_r reference(shard_r).
+"""
+from __future__ import annotations
+
+import warnings
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .models import HAVE_PYRO, NBVAE
+
+if HAVE_PYRO:  # pragma: no cover
+    import pyro
+
+
+class FusedTraceELBO:
+    """:param seed: seed of the counter-based (Philox) noise generator used for the
+        reparameterised draws; every step consumes a fresh counter range.
+    :param data_parallel: ``None`` = all-reduce gradients iff ``torch.distributed`` is initialised.
+    :param include_guide_factor: keep the guide-side monotonic-bias factor (pathwise gradient).
+    :param force_simt: never use the tcgen05 kernels (A/B parity checks).
+    """
+
+    def __init__(self, num_particles: int = 1, seed: int = 0, data_parallel: Optional[bool] = None,
+                 process_group=None, include_guide_factor: bool = True, force_simt: bool = False,
+                 update_bn_stats: bool = True, **_ignored):
+        if num_particles != 1:
+            raise NotImplementedError("the fused ELBO evaluates one particle (the reference notebook's setting)")
+        self.seed = int(seed)
+        self.step_index = 0
+        self.data_parallel = data_parallel
+        self.process_group = process_group
+        self.include_guide_factor = include_guide_factor
+        self.flags = (_lib.DRV_FLAG_FORCE_SIMT if force_simt else 0) | (0 if update_bn_stats else _lib.DRV_FLAG_NO_BN_UPDATE)
+        self._explicit_noise = None
+        self._noise_bufs = {}
+        self.last_status = 0
+
+    # -- noise ------------------------------------------------------------------------------
+    def set_noise(self, noise: Optional[dict]) -> None:
+        """Parity mode: use these noise tensors (``eps_z`` (B,L), ``eps_l`` (B,1) and, for DRNBVAE,
+        lists ``w_prior`` (L,1), ``b_prior`` (C_i,1), ``eps_bias`` (C_i,1)) instead of drawing."""
+        self._explicit_noise = noise
+
+    def _noise(self, rt, B: int) -> dict:
+        dev = rt.device
+        if self._explicit_noise is not None:
+            n = self._explicit_noise
+            out = {"eps_z": n["eps_z"].to(dev, torch.float32).contiguous(),
+                   "eps_l": n["eps_l"].to(dev, torch.float32).reshape(-1).contiguous()}
+            if rt.n_drugs:
+                cat = lambda ts: torch.cat([t.to(dev, torch.float32).reshape(-1) for t in ts]).contiguous()
+                out.update(w_prior=cat(n["w_prior"]), b_prior=cat(n["b_prior"]), eps_bias=cat(n["eps_bias"]))
+            return out
+        key = (B, str(dev))
+        bufs = self._noise_bufs.get(key)
+        L, D, T = rt.n_latent, rt.n_drugs, rt.n_doses_total
+        if bufs is None:
+            bufs = {"eps_z": torch.empty(B * L, device=dev), "eps_l": torch.empty(B, device=dev)}
+            if D:
+                bufs.update(w_prior=torch.empty(D * L, device=dev), b_prior=torch.empty(T, device=dev),
+                            eps_bias=torch.empty(T, device=dev))
+            self._noise_bufs[key] = bufs
+        # production mode: Philox counters (seed, running offset); the draw order follows the
+        # reference (latent, library, then per-drug guide / prior draws - SURVEY 8b)
+        import ctypes as C
+        from .runtime import _ptr, _stream
+
+        lib, st = rt.lib, _stream(dev)
+        per_step = 4 * ((B * L + 3) // 4 + (B + 3) // 4 + (D * L + 3) // 4 + 2 * ((T + 3) // 4))
+        rank = torch.distributed.get_rank() if self._dp_enabled() else 0
+        off = (self.step_index * 4096 + rank) * per_step
+        seed = C.c_uint64(self.seed)
+        _lib.check(lib.drv_fill_normal(_ptr(bufs["eps_z"]), B * L, seed, C.c_uint64(off), st), "drv_fill_normal")
+        off += 4 * ((B * L + 3) // 4)
+        _lib.check(lib.drv_fill_normal(_ptr(bufs["eps_l"]), B, seed, C.c_uint64(off), st), "drv_fill_normal")
+        off += 4 * ((B + 3) // 4)
+        if D:
+            _lib.check(lib.drv_fill_laplace(_ptr(bufs["w_prior"]), D * L, seed, C.c_uint64(off), st), "drv_fill_laplace")
+            off += 4 * ((D * L + 3) // 4)
+            _lib.check(lib.drv_fill_normal(_ptr(bufs["b_prior"]), T, seed, C.c_uint64(off), st), "drv_fill_normal")
+            off += 4 * ((T + 3) // 4)
+            _lib.check(lib.drv_fill_normal(_ptr(bufs["eps_bias"]), T, seed, C.c_uint64(off), st), "drv_fill_normal")
+            bufs["w_prior"].mul_(rt.lmbs[0].lam_scale)
+            bufs["b_prior"].mul_(rt.lmbs[0].prior_bias_scale)
+        return bufs
+
+    # -- helpers ----------------------------------------------------------------------------
+    def _dp_enabled(self) -> bool:
+        if self.data_parallel is False:
+            return False
+        ok = torch.distributed.is_available() and torch.distributed.is_initialized()
+        if self.data_parallel and not ok:
+            raise RuntimeError("data_parallel=True needs torch.distributed.init_process_group first")
+        return ok and torch.distributed.get_world_size(self.process_group) > 1
+
+    @staticmethod
+    def _module_of(model, guide) -> NBVAE:
+        for fn in (model, guide):
+            owner = getattr(fn, "__self__", None)
+            if isinstance(owner, NBVAE):
+                return owner
+        if isinstance(model, NBVAE):
+            return model
+        raise TypeError("FusedTraceELBO expects the bound model/guide methods of a drvish_b200 NBVAE or DRNBVAE")
+
+    @staticmethod
+    def _flatten_y(rt, y, dev):
+        if not rt.n_drugs:
+            return None
+        if torch.is_tensor(y):  # stacked (D, K, C, 1)
+            y = list(y)
+        K = rt.n_classes
+        parts = []
+        for i, t in enumerate(y):
+            if tuple(t.shape) != (K, rt.doses[i], 1):
+                raise RuntimeError(f"y[{i}] must have shape ({K}, {rt.doses[i]}, 1) (reference drnbvae.py:112-116)")
+            parts.append(t.to(dev, torch.float32).reshape(-1))
+        return torch.cat(parts).contiguous()
+
+    def _run(self, model, guide, args, want_grads: bool) -> float:
+        module = self._module_of(model, guide)
+        if HAVE_PYRO:  # pragma: no cover - registers the parameters so SVI's param capture sees them
+            pyro.module(module.pyro_name, module)
+        rt = module._runtime()
+        rt.ensure_flat()
+        x = args[0]
+        labels = args[1] if len(args) > 1 else None
+        y = self._flatten_y(rt, args[2] if len(args) > 2 else None, rt.device)
+        noise = self._noise(rt, x.shape[0])
+        rt.elbo_step(x, labels, y, noise, want_grads, self.flags, self.include_guide_factor)
+        self.step_index += 1
+        if want_grads and self._dp_enabled():
+            # one all-reduce: gradients + the loss in the tail slot
+            rt.flat_grads[rt.n_param_floats] = rt._out[0].to(torch.float32)
+            torch.distributed.all_reduce(rt.flat_grads, op=torch.distributed.ReduceOp.SUM, group=self.process_group)
+        loss, status = rt.read_out()
+        self.last_status = status
+        if status & (_lib.DRV_STATUS_MISSING_CLASS | _lib.DRV_STATUS_BAD_LABEL):
+            raise RuntimeError("index out of bounds: every class 0..n_classes-1 must occur in the minibatch "
+                               "(the reference's scatter_add_ raises the same way, modules.py:175-179)")
+        if status & _lib.DRV_STATUS_NAN_LOSS:
+            warnings.warn("Encountered NaN: loss")  # pyro.util.warn_if_nan
+        if want_grads:
+            rt.attach_grads()
+        return loss
+
+    # -- the two methods pyro.infer.SVI calls -----------------------------------------------------
+    def loss(self, model, guide, *args, **kwargs) -> float:
+        """``SVI.evaluate_loss``: forward only.  BatchNorm still normalises with batch statistics
+        and advances its running buffers, as the reference does (it never calls ``.eval()``)."""
+        return self._run(model, guide, args, want_grads=False)
+
+    def loss_and_grads(self, model, guide, *args, **kwargs) -> float:
+        """``SVI.step``: loss + every parameter gradient."""
+        return self._run(model, guide, args, want_grads=True)
+
+    def differentiable_loss(self, model, guide, *args, **kwargs):
+        raise NotImplementedError("the fused ELBO has no autograd graph; use loss_and_grads")

@@ -1,0 +1,160 @@
+/*
+ * drvish_b200 - C ABI of the B200-native drvish ELBO step.
+ *
+ * The reference (czbiohub/drvish) is pure Python and has no FFI seam of its own; the seam is
+ * the Python object protocol consumed by pyro.infer.SVI.  Every entry point
+ * below therefore cites the reference Python it replaces:
+ *
+ *   drv_elbo_step      svi.step(*xs) / svi.evaluate_loss(*xs) as driven by
+ *                      src/drvish/train/__init__.py:41-46, i.e. one trace of
+ *                      NBVAE.guide + NBVAE.model   (src/drvish/models/nbvae.py:57-90)   or
+ *                      DRNBVAE.guide + DRNBVAE.model (src/drvish/models/drnbvae.py:87-132)
+ *                      plus Pyro's Trace_ELBO loss_and_grads (loss.backward()).
+ *   drv_encoder_forward   Encoder.forward   (src/drvish/models/modules.py:46-60)
+ *   drv_decoder_forward   NBDecoder.forward (src/drvish/models/modules.py:77-98)
+ *   drv_logit_mean_sigmoid LinearMultiBias.logit_mean_sigmoid (modules.py:159-180)
+ *   drv_fill_normal / drv_fill_laplace   Normal.rsample / Laplace.rsample noise draws
+ *                      (nbvae.py:89-90, modules.py:130-135,152-157) in production mode
+ *
+ * Conventions: all pointers are DEVICE pointers unless the name starts with h_; tensors are
+ * fp32, row-major, contiguous; the caller owns every buffer (nothing is allocated or freed
+ * here); all work is enqueued on `stream` with no host synchronisation; the return value is 0
+ * or the cudaError_t of the failed launch / a negative DRV_E* code for invalid arguments.
+ */
+#ifndef DRVISH_B200_H
+#define DRVISH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRV_MAX_LAYERS 8
+
+#define DRV_EINVAL (-1)  /* bad dims / null pointer */
+#define DRV_ENOSPC (-2)  /* workspace too small */
+
+/* status bits written to drv_step_out.status by the kernels */
+#define DRV_STATUS_NAN_LOSS 1u      /* mirrors pyro's warn_if_nan(loss) */
+#define DRV_STATUS_MISSING_CLASS 2u /* a class 0..K-1 has no cell in the batch: the reference's
+                                       scatter_add_ raises "index out of bounds" (modules.py:175-179) */
+#define DRV_STATUS_BAD_LABEL 4u     /* label outside [0, K) */
+
+/* Problem shape.  Encoder dims are [n_genes, layers..., 2*n_latent+2]; the decoder gets the
+ * reversed hidden layers and ends in 2*n_genes (nbvae.py:41-42, modules.py:44,75). */
+typedef struct drv_dims {
+  int32_t n_cells;   /* B: cells in this minibatch */
+  int32_t n_genes;   /* G */
+  int32_t n_latent;  /* L */
+  int32_t n_layers;  /* number of hidden layers, 1..DRV_MAX_LAYERS */
+  int32_t layers[DRV_MAX_LAYERS];
+  int32_t n_drugs;   /* D, 0 for NBVAE */
+  int32_t n_classes; /* K */
+  int32_t n_doses_total; /* sum_i C_i */
+} drv_dims;
+
+typedef struct drv_hparams {
+  float scale_factor;  /* poutine.scale (nbvae.py:61) */
+  float epsilon;       /* added to exp(log_r) (nbvae.py:75) */
+  float lib_loc;       /* library prior (nbvae.py:46-47,66-68) */
+  float lib_scale;
+  float lam_scale;     /* Laplace prior scale of weight_p (modules.py:130-132) */
+  float bias_scale;    /* Normal prior scale of bias_p (modules.py:133-135) */
+  float sigma_scale;   /* drs_i observation noise (drnbvae.py:114) */
+  float alpha;         /* monotonic-bias factor weight (modules.py:193-196) */
+  float bn_eps;        /* BatchNorm1d eps (1e-5) */
+  float bn_momentum;   /* BatchNorm1d momentum (0.1) */
+  int32_t include_guide_factor; /* 1: add the guide-side monotonic factor (pathwise gradient) */
+  int32_t flags;       /* DRV_FLAG_* */
+} drv_hparams;
+
+#define DRV_FLAG_FORCE_SIMT 1   /* never take the tcgen05/TMA kernels (debug / A-B parity) */
+#define DRV_FLAG_NO_BN_UPDATE 2 /* do not touch running_mean/var (gradient checks) */
+
+/* Results of one step: one 16-byte device record, read back with a single D2H copy. */
+typedef struct drv_step_out {
+  double loss;      /* -ELBO of the minibatch (what SVI.step returns) */
+  uint32_t status;  /* DRV_STATUS_* */
+  uint32_t path;    /* bit 0: tcgen05 decoder kernels were used; bit 1: tcgen05 encoder kernels */
+} drv_step_out;
+
+/* Number of tensors / total floats of the flat parameter buffer.  offsets[i] is the float
+ * offset of the i-th tensor in state_dict order:
+ *   encoder.fc.{0,2,...}: bn.weight, bn.bias, linear.weight, linear.bias per block; then
+ *   decoder.fc likewise; then (D > 0) weight_loc[D][L], weight_scale_unconstrained[D][L],
+ *   bias_loc[sum C], bias_scale_unconstrained[sum C].
+ * Returns the tensor count (<= max_n) or a negative error. */
+int drv_param_offsets(const drv_dims* dims, int64_t* offsets, int64_t* sizes, int max_n, int64_t* total_floats);
+
+/* Same for BatchNorm buffers: running_mean, running_var per BatchNorm in module order. */
+int drv_bn_offsets(const drv_dims* dims, int64_t* offsets, int64_t* sizes, int max_n, int64_t* total_floats);
+
+size_t drv_workspace_bytes(const drv_dims* dims);
+
+/* One SVI step.  grads == NULL -> forward only (svi.evaluate_loss; BatchNorm still uses batch
+ * statistics and still updates its running buffers).
+ *   x        [B][G] counts          labels [B] int64 (D>0)      y [sum_i K*C_i] drug-major (k,c)
+ *   eps_z    [B][L], eps_l [B]      standard-normal noise of the two rsample sites
+ *   w_prior  [D][L], b_prior [sum C] draws of i.weight_p / i.bias_p;  eps_bias [sum C]
+ *   dose_offsets [D+1] int32 prefix sums of C_i
+ *   params / grads  flat buffers laid out by drv_param_offsets (grads are OVERWRITTEN)
+ *   bn_running      flat buffer laid out by drv_bn_offsets; bn_batches [n_bn] int64 counters */
+int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp,
+                  const float* x, const int64_t* labels, const float* y,
+                  const float* eps_z, const float* eps_l,
+                  const float* w_prior, const float* b_prior, const float* eps_bias,
+                  const int32_t* dose_offsets,
+                  const float* params, float* grads,
+                  float* bn_running, int64_t* bn_batches,
+                  drv_step_out* out,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Encoder.forward (modules.py:46-60): writes z_loc [B][L], z_scale [B][L], l_loc [B], l_scale [B]. */
+int drv_encoder_forward(const drv_dims* dims, const drv_hparams* hp, const float* x,
+                        const float* params, float* bn_running, int64_t* bn_batches,
+                        float* z_loc, float* z_scale, float* l_loc, float* l_scale,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* NBDecoder.forward (modules.py:77-98): writes log_r [B][G] and logit [B][G]. */
+int drv_decoder_forward(const drv_dims* dims, const drv_hparams* hp, const float* z, const float* library,
+                        const float* params, float* bn_running, int64_t* bn_batches,
+                        float* log_r, float* logit,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* LinearMultiBias.logit_mean_sigmoid for all drugs at once (modules.py:159-180):
+ * out [sum_i K*C_i] drug-major (k,c).  status gets DRV_STATUS_MISSING_CLASS / BAD_LABEL. */
+int drv_logit_mean_sigmoid(const drv_dims* dims, const float* z, const float* w, const float* b,
+                           const int64_t* labels, const int32_t* dose_offsets,
+                           float* out, uint32_t* status,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* Counter-based (Philox4x32-10) noise: out[i] ~ N(0,1) / Laplace(0,1), keyed by (seed, offset+i). */
+int drv_fill_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+int drv_fill_laplace(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+
+/* Section timing with CUDA events recorded on the step's stream (bench.py's live roofline
+ * measurement).  drv_profile_enable(1) arms it (up to 64 steps are kept); drv_profile_read
+ * synchronises on the recorded events and returns the mean milliseconds per section. */
+#define DRV_N_SECTIONS 7
+#define DRV_SEC_ENC_FWD 0        /* encoder forward + sampling/KL */
+#define DRV_SEC_DEC_TRUNK_FWD 1  /* decoder blocks before the last Linear */
+#define DRV_SEC_DEC_NB_FWD 2     /* last Linear + gene softmax + NB likelihood (forward) */
+#define DRV_SEC_DOSE_RESPONSE 3  /* dose-response head forward + backward */
+#define DRV_SEC_DEC_NB_BWD 4     /* fused backward of the last Linear (dlogits, dW, db, dAct) */
+#define DRV_SEC_DEC_TRUNK_BWD 5  /* decoder trunk backward + sampling backward */
+#define DRV_SEC_ENC_BWD 6        /* encoder backward */
+int drv_profile_enable(int on);
+int drv_profile_read(float* h_ms_per_section, int* h_n_steps);
+
+/* Number of kernels the last drv_* call on this thread enqueued (for bench.py's gpu_launches). */
+int drv_last_launch_count(void);
+
+/* "drvish_b200 <version> sm_100a" */
+const char* drv_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
