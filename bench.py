@@ -64,7 +64,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         try:
             import pynvml
 
@@ -86,7 +86,7 @@ class ClockSampler(threading.Thread):
             getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
             getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
         }
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
@@ -101,7 +101,7 @@ class ClockSampler(threading.Thread):
             time.sleep(0.005)
 
     def finish(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=1.0)
         s = sorted(self.samples)
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),

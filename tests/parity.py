@@ -13,6 +13,12 @@ from oracle import drvish_oracle as O
 ZERO_GRAD_BIASES = ("encoder.fc.2.bias", "encoder.fc.5.bias", "decoder.fc.2.bias", "decoder.fc.5.bias")
 
 
+def zero_grad_biases(n_hidden_layers: int):
+    """Linear biases that are immediately followed by a BatchNorm (all but the last Linear of
+    each stack): the BatchNorm subtracts the batch mean, so their exact gradient is 0."""
+    return tuple(f"{s}.fc.{3 * k + 2}.bias" for s in ("encoder", "decoder") for k in range(n_hidden_layers))
+
+
 def make_case(cfg: dict, data_seed: int = 5, noise_seed: int = 1, model_seed: int = 0, bn_affine_random: bool = False):
     model = O.build_model(cfg, seed=model_seed)
     if bn_affine_random:
@@ -84,10 +90,11 @@ def compare_step(case, device="cuda:0", force_simt=False):
     rep = {"loss": loss, "loss64": loss64, "loss_rel": abs(loss - loss64) / abs(loss64),
            "loss32_rel": abs(loss32 - loss64) / abs(loss64), "grads": {}, "launches": model._runtime().last_launches}
     worst, worst_name = 0.0, ""
+    zero_biases = zero_grad_biases(len(case["cfg"]["layers"]))
     for name, g64 in grads64.items():
         g = grads[name]
         assert g is not None, name
-        if name in ZERO_GRAD_BIASES:
+        if name in zero_biases:
             wn = grads64[name.replace("bias", "weight")].norm()
             e = float(g.norm() / (wn + 1e-300))
             floor = float(grads32[name].double().norm() / (wn + 1e-300))
