@@ -29,3 +29,10 @@ void tc_decoder_forward(const TcDecoderArgs& a, cudaStream_t st);   // lse, ll, 
 void tc_decoder_backward(const TcDecoderArgs& a, cudaStream_t st);  // dW, db, dY
 
 }  // namespace drv
+
+namespace drv {
+namespace tc {
+int gemm_tf32(const float* A, int lda, bool a_mn, const float* Bm, int ldb, bool b_mn, float* C, int ldc, int M, int N,
+              int K, int splits, bool accumulate_atomic, cudaStream_t st);
+}
+}  // namespace drv
