@@ -1,7 +1,501 @@
+// Fused decoder-last-layer GEMM + gene softmax + library scaling + NB likelihood on the sm_100a
+// tensor cores (tcgen05.mma.kind::tf32, TMEM accumulators, TMA-fed 128-byte-swizzled operands).
+// The (cells x 2*genes) logits / mean matrix never touches HBM in the forward pass:
+//
+//   phase 1  logits(scale half) tile in TMEM -> per-row online (max, sum exp) partials  -> lse[b]
+//   phase 2  logits(both halves) tile in TMEM + TMA-staged count tile -> NB log-prob row sums
+//            LL[b], A[b] = sum_g dLL/d ell  (= dLL/d library)                 [evaluate_loss stops here]
+//   phase 3  recompute the tile, form d loss/d logits in registers, write it
+//            once (fp32) and reduce the bias gradient; dW = dlogits^T act and dAct = dlogits W then
+//            run as tf32 tcgen05 GEMMs that read dlogits / act / W in the layouts they already have
+//            (MN-major descriptors, tc_gemm.cu).
+//
+// Reference arithmetic: NBDecoder.forward modules.py:93-96, "obs" site nbvae.py:72-78.
+// Persistent CTAs (one per SM), 18 warps: 16 epilogue warps (4 per TMEM lane quarter, each a
+// 16-gene column slice), 1 TMA producer warp, 1 MMA-issuer warp.  Tiles: 128 cells x 64 genes
+// (x 2 halves = 128 accumulator columns), double-buffered in TMEM (256 columns).
+#include "kernels.cuh"
 #include "tc.cuh"
+#include "tc_common.cuh"
+
 namespace drv {
-size_t tc_workspace_bytes(const drv_dims&) { return 0; }
-bool tc_decoder_supported(const drv_dims&, const drv_hparams&) { return false; }
-void tc_decoder_forward(const TcDecoderArgs&, cudaStream_t) {}
-void tc_decoder_backward(const TcDecoderArgs&, cudaStream_t) {}
+
+using namespace tc;
+
+namespace {
+
+constexpr int BM = 128;            // cells per tile
+constexpr int BK = 32;             // k-block (fp32 elements)
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 4;       // 16 KB
+constexpr int B_BYTES = 128 * BK * 4;      // 16 KB (128 weight rows)
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int X_BYTES = 2 * BM * 32 * 4;   // one count tile: two 128x32 boxes = 32 KB
+constexpr int N_EPI_WARPS = 16;
+constexpr int NTHREADS = (N_EPI_WARPS + 2) * 32;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * X_BYTES + 1024 + 256;
+constexpr int TMEM_COLS = 256;
+
+// tcgen05 kind::tf32 TRUNCATES the low 13 mantissa bits of its fp32 operands, which biases every
+// product by ~2^-11; rounding the operands to nearest when they are produced keeps the error
+// unbiased (measured: gradient error 1.3e-3 -> see DESIGN.md).
+__device__ __forceinline__ float rna_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+struct DecParams {
+  int B, G, h;
+  const float* bias;  // [2G]
+  const float* lib;   // [B]
+  float eps, c;
+  // phase 1
+  float* part_m;      // [n_slots][B]
+  float* part_s;
+  // phase 2/3
+  const float* lse;   // [B]
+  float* ll;          // [B] (atomic accumulation, zeroed)
+  float* asum;        // [B]
+  float* dlogits;     // [B][2G]
+  float* db;          // [2G] (atomic accumulation, zeroed)
+};
+
+template <int PHASE, bool WITH_A>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtensorMap tmW,
+      const __grid_constant__ CUtensorMap tmX, DecParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* xbuf = smem + STAGES * STAGE_BYTES;
+  uint64_t* full = (uint64_t*)(xbuf + 2 * X_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;    // [2]
+  uint64_t* acc_empty = acc_full + 2;     // [2]
+  uint64_t* x_full = acc_empty + 2;       // [2]
+  uint64_t* x_empty = x_full + 2;         // [2]
+  uint32_t* tmem_slot = (uint32_t*)(x_empty + 2);
+
+  constexpr int TN = PHASE == 1 ? 128 : 64;  // genes per tile
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int n_gt = (p.G + TN - 1) / TN;
+  const int n_ct = (p.B + BM - 1) / BM;
+  const int n_tiles = n_gt * n_ct;
+  const int t0 = (int)((long long)n_tiles * blockIdx.x / gridDim.x);
+  const int t1 = (int)((long long)n_tiles * (blockIdx.x + 1) / gridDim.x);
+  const int nkb = p.h / BK;
+
+  if (warp == N_EPI_WARPS && lane == 0) {
+    tma_prefetch_desc(&tmAct);
+    tma_prefetch_desc(&tmW);
+    if (PHASE != 1) tma_prefetch_desc(&tmX);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], N_EPI_WARPS);
+      mbar_init(&x_full[s], 1);
+      mbar_init(&x_empty[s], N_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == N_EPI_WARPS + 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == N_EPI_WARPS) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int kit = 0;
+      for (int t = t0, it = 0; t < t1; ++t, ++it) {
+        const int ct = t / n_gt, gt = t % n_gt;
+        const int b0 = ct * BM, g0 = gt * TN;
+        if (PHASE != 1) {
+          const int xs = it & 1, xph = (it >> 1) & 1;
+          mbar_wait(&x_empty[xs], xph ^ 1);
+          mbar_expect_tx(&x_full[xs], X_BYTES);
+          tma_load_2d(xbuf + xs * X_BYTES, &tmX, &x_full[xs], g0, b0);
+          tma_load_2d(xbuf + xs * X_BYTES + X_BYTES / 2, &tmX, &x_full[xs], g0 + 32, b0);
+        }
+        for (int kb = 0; kb < nkb; ++kb, ++kit) {
+          const int s = kit % STAGES, ph = (kit / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          mbar_expect_tx(&full[s], STAGE_BYTES);
+          tma_load_2d(sa, &tmAct, &full[s], kb * BK, b0);
+          if (PHASE == 1) tma_load_2d(sa + A_BYTES, &tmW, &full[s], kb * BK, g0);
+          else tma_load_3d(sa + A_BYTES, &tmW, &full[s], kb * BK, g0, 0);
+        }
+      }
+    }
+  } else if (warp == N_EPI_WARPS + 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(BM, 128, 0, 0);
+      int kit = 0;
+      for (int t = t0, it = 0; t < t1; ++t, ++it) {
+        const int as = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(&acc_empty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * 128);
+        for (int kb = 0; kb < nkb; ++kb, ++kit) {
+          const int s = kit % STAGES, ph = (kit / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BK / 8; ++kk)
+            umma_tf32(d_tmem, smem_desc(sa + kk * 32, 16, 1024), smem_desc(sb + kk * 32, 16, 1024), idesc,
+                      (kb | kk) != 0);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[as]);
+      }
+    }
+  } else {
+    // ===== epilogue warps =====
+    const int q = warp % 4;    // TMEM lane quarter
+    const int cg = warp / 4;   // column group
+    const int r = q * 32 + lane;
+    float ll_acc = 0.f, a_acc = 0.f;
+    int cur_ct = -1;
+    float lib_b = 0.f, lse_b = 0.f, asum_b = 0.f;
+    int b = 0;
+    bool row_ok = false;
+    for (int t = t0, it = 0; t < t1; ++t, ++it) {
+      const int ct = t / n_gt, gt = t % n_gt;
+      const int as = it & 1, aph = (it >> 1) & 1;
+      if (ct != cur_ct) {
+        if (PHASE == 2 && cur_ct >= 0 && row_ok) {
+          atomicAdd(&p.ll[b], ll_acc);
+          if (WITH_A) atomicAdd(&p.asum[b], a_acc);
+        }
+        ll_acc = a_acc = 0.f;
+        cur_ct = ct;
+        b = ct * BM + r;
+        row_ok = b < p.B;
+        if (PHASE != 1 && row_ok) {
+          lib_b = p.lib[b];
+          lse_b = p.lse[b];
+          if (PHASE == 3) asum_b = p.asum[b];
+        }
+      }
+      const int g0 = gt * TN;
+      mbar_wait(&acc_full[as], aph);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 128);
+
+      if (PHASE == 1) {
+        // 32 genes of the scale half per warp: online (max, sum exp)
+        float v0[16], v1[16];
+        tmem_ld16(tbase + cg * 32, v0);
+        tmem_ld16(tbase + cg * 32 + 16, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[as]);
+        const int gbase = g0 + cg * 32;
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          v0[j] = (gbase + j < p.G) ? v0[j] + __ldg(&p.bias[min(gbase + j, p.G - 1)]) : -INFINITY;
+          v1[j] = (gbase + 16 + j < p.G) ? v1[j] + __ldg(&p.bias[min(gbase + 16 + j, p.G - 1)]) : -INFINITY;
+          m = fmaxf(m, fmaxf(v0[j], v1[j]));
+        }
+        float s = 0.f;
+        if (m > -INFINITY) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) s += __expf(v0[j] - m) + __expf(v1[j] - m);
+        }
+        if (row_ok) {
+          const size_t slot = (size_t)(gt * 4 + cg) * p.B + b;
+          p.part_m[slot] = m;
+          p.part_s[slot] = s;
+        }
+      } else {
+        const int xs = it & 1, xph = (it >> 1) & 1;
+        float sv[16], rv[16], xv[16];
+        tmem_ld16(tbase + cg * 16, sv);
+        tmem_ld16(tbase + 64 + cg * 16, rv);
+        mbar_wait(&x_full[xs], xph);
+        {
+          // count tile: box (cg/2), row r, 16-byte chunks (cg%2)*4 + j, XOR-swizzled with r%8
+          const uint8_t* xrow = xbuf + xs * X_BYTES + (cg >> 1) * (X_BYTES / 2) + r * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int chunk = ((cg & 1) * 4 + j) ^ (r & 7);
+            float4 f = *reinterpret_cast<const float4*>(xrow + chunk * 16);
+            xv[4 * j] = f.x; xv[4 * j + 1] = f.y; xv[4 * j + 2] = f.z; xv[4 * j + 3] = f.w;
+          }
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&acc_empty[as]);
+          mbar_arrive(&x_empty[xs]);
+        }
+        const int gbase = g0 + cg * 16;
+        if (PHASE == 2) {
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int g = gbase + j;
+              if (g < p.G) {
+                float s = sv[j] + __ldg(&p.bias[g]);
+                float rho = rv[j] + __ldg(&p.bias[p.G + g]);
+                NbElem e = nb_elem<WITH_A>(s - lse_b, rho, lib_b, xv[j], p.eps);
+                ll_acc += e.ll;
+                if (WITH_A) a_acc += e.a;
+              }
+            }
+          }
+        } else {
+          // backward: ds = -c (a - p A), drho = -c dLL/drho ; bias gradient = column sums
+          float ds[16], dr[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int g = gbase + j;
+            ds[j] = 0.f;
+            dr[j] = 0.f;
+            if (row_ok && g < p.G) {
+              float s = sv[j] + __ldg(&p.bias[g]);
+              float rho = rv[j] + __ldg(&p.bias[p.G + g]);
+              float ls = s - lse_b;
+              NbElem e = nb_elem<true>(ls, rho, lib_b, xv[j], p.eps);
+              ds[j] = rna_tf32(-p.c * (e.a - __expf(ls) * asum_b));
+              dr[j] = rna_tf32(-p.c * e.drho);
+            }
+          }
+          if (row_ok) {
+            float* d0 = p.dlogits + (size_t)b * 2 * p.G + gbase;
+            float* d1 = d0 + p.G;
+            if (gbase + 16 <= p.G) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                reinterpret_cast<float4*>(d0)[j] = make_float4(ds[4 * j], ds[4 * j + 1], ds[4 * j + 2], ds[4 * j + 3]);
+                reinterpret_cast<float4*>(d1)[j] = make_float4(dr[4 * j], dr[4 * j + 1], dr[4 * j + 2], dr[4 * j + 3]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (gbase + j < p.G) { d0[j] = ds[j]; d1[j] = dr[j]; }
+            }
+          }
+          // column sums over the 32 rows of this warp -> one atomic per column per warp
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float a = warp_sum(ds[j]);
+            float c2 = warp_sum(dr[j]);
+            if (lane == j && gbase + j < p.G) {
+              atomicAdd(&p.db[gbase + j], a);
+              atomicAdd(&p.db[p.G + gbase + j], c2);
+            }
+          }
+        }
+      }
+    }
+    if (PHASE == 2 && cur_ct >= 0 && row_ok) {
+      atomicAdd(&p.ll[b], ll_acc);
+      if (WITH_A) atomicAdd(&p.asum[b], a_acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == N_EPI_WARPS + 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// act = relu(bn(U)) materialised once (B x h fp32, L2 resident) as the TMA-fed A operand
+__global__ void k_act(const float* __restrict__ U, int B, int h, BnParams bn, float* __restrict__ act) {
+  size_t n = (size_t)B * h;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int col = (int)(i % h);
+    act[i] = rna_tf32(bn_relu(U[i], bn.mean[col], bn.rstd[col], bn.gamma[col], bn.beta[col]));
+  }
+}
+
+__global__ void k_round_tf32(const float* __restrict__ src, size_t n, float* __restrict__ dst) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = rna_tf32(src[i]);
+}
+
+__global__ void k_lse_combine(const float* __restrict__ pm, const float* __restrict__ ps, int n_slots, int B,
+                              float* __restrict__ lse) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float m = -INFINITY;
+  for (int s = 0; s < n_slots; ++s) m = fmaxf(m, pm[(size_t)s * B + b]);
+  float acc = 0.f;
+  for (int s = 0; s < n_slots; ++s) {
+    float pmv = pm[(size_t)s * B + b];
+    if (pmv > -INFINITY) acc += ps[(size_t)s * B + b] * __expf(pmv - m);
+  }
+  lse[b] = m + logf(acc);
+}
+
+__global__ void k_loss_from_ll(const float* __restrict__ ll, int B, float c, drv_step_out* out) {
+  double t = 0.0;
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) t += (double)ll[b];
+  t = warp_sum(t);
+  __shared__ double sh[8];
+  if (threadIdx.x % 32 == 0) sh[threadIdx.x / 32] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < (int)blockDim.x / 32; ++i) s += sh[i];
+    atomicAdd(&out->loss, -(double)c * s);
+  }
+}
+
+__global__ void k_gate(float* __restrict__ dact, const float* __restrict__ U, int B, int h, BnParams bn) {
+  size_t n = (size_t)B * h;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int col = (int)(i % h);
+    float y = bn_y(bn_xhat(U[i], bn.mean[col], bn.rstd[col]), bn.gamma[col], bn.beta[col]);
+    if (!(y > 0.f)) dact[i] = 0.f;
+  }
+}
+
+struct Scratch {
+  float* act;      // [B][h]  relu(bn(U)) rounded to tf32
+  float* Wr;       // [2G][h] last-layer weight rounded to tf32
+  float* part_m;   // [slots][B]
+  float* part_s;
+  size_t total;
+};
+
+Scratch carve(void* base, int B, int G, int h) {
+  Scratch s{};
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = (o + bytes + 255) / 256 * 256; return r; };
+  size_t slots = (size_t)((G + 127) / 128) * 4;
+  size_t a = take(4 * (size_t)B * h), pm = take(4 * slots * B), ps = take(4 * slots * B);
+  size_t wr = take(4 * (size_t)2 * G * h);
+  s.total = o;
+  if (base) {
+    char* c = (char*)base;
+    s.act = (float*)(c + a);
+    s.part_m = (float*)(c + pm);
+    s.part_s = (float*)(c + ps);
+    s.Wr = (float*)(c + wr);
+  }
+  return s;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+bool make_maps(const TcDecoderArgs& a, const Scratch& s, CUtensorMap* act, CUtensorMap* w1, CUtensorMap* w3, CUtensorMap* x) {
+  if (!tmap_2d(act, s.act, a.B, a.h, a.h, BM, BK)) return false;
+  if (!tmap_2d(w1, s.Wr, a.G, a.h, a.h, 128, BK)) return false;
+  {
+    uint64_t dims[3] = {(uint64_t)a.h, (uint64_t)a.G, 2};
+    uint64_t strides[2] = {(uint64_t)a.h * 4, (uint64_t)a.G * a.h * 4};
+    uint32_t box[3] = {BK, 64, 2};
+    if (!make_tensor_map(w3, s.Wr, 3, dims, strides, box, 1)) return false;
+  }
+  if (!tmap_2d(x, a.x, a.B, a.G, a.G, BM, 32)) return false;
+  return true;
+}
+
+template <class K>
+void launch_dec(K kern, int n_tiles, const CUtensorMap& act, const CUtensorMap& w, const CUtensorMap& x,
+                const DecParams& p, cudaStream_t st) {
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+  kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(act, w, x, p);
+  note_launch();
+}
+
+}  // namespace
+
+size_t tc_workspace_bytes(const drv_dims& d) {
+  int h = d.layers[0];  // the decoder's last hidden width is the encoder's first
+  return carve(nullptr, d.n_cells, d.n_genes, h).total;
+}
+
+bool tc_decoder_supported(const drv_dims& d, const drv_hparams& hp) {
+  if (hp.flags & DRV_FLAG_FORCE_SIMT) return false;
+  int h = d.layers[0];
+  // TMA needs 16-byte row strides; the k loop runs in 32-float blocks; the MN-major GEMMs want h % 32 == 0
+  return d.n_genes % 4 == 0 && d.n_genes >= 64 && h % 32 == 0 && h >= 32 && h <= 512 && d.n_cells >= 32;
+}
+
+void tc_decoder_forward(const TcDecoderArgs& a, cudaStream_t st) {
+  Scratch s = carve(a.scratch, a.B, a.G, a.h);
+  CUtensorMap tAct, tW1, tW3, tX;
+  if (!make_maps(a, s, &tAct, &tW1, &tW3, &tX)) {
+    if (g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
+    return;
+  }
+  int blocks = (int)(((size_t)a.B * a.h + 255) / 256);
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  k_act<<<blocks, 256, 0, st>>>(a.U, a.B, a.h, a.bn, s.act);
+  note_launch();
+  k_round_tf32<<<sm_count() * 4, 256, 0, st>>>(a.W, (size_t)2 * a.G * a.h, s.Wr);
+  note_launch();
+  DecParams p{};
+  p.B = a.B; p.G = a.G; p.h = a.h; p.bias = a.bias; p.lib = a.lib; p.eps = a.eps; p.c = a.c;
+  p.part_m = s.part_m; p.part_s = s.part_s; p.lse = a.lse; p.ll = a.ll; p.asum = a.asum;
+  p.dlogits = a.dlogits; p.db = a.db;
+  const int n_ct = (a.B + BM - 1) / BM;
+  // phase 1: logsumexp over genes
+  const int n_gt1 = (a.G + 127) / 128;
+  launch_dec(k_dec<1, false>, n_ct * n_gt1, tAct, tW1, tX, p, st);
+  k_lse_combine<<<(a.B + 127) / 128, 128, 0, st>>>(s.part_m, s.part_s, n_gt1 * 4, a.B, a.lse);
+  note_launch();
+  // phase 2: NB log-likelihood row sums
+  cudaMemsetAsync(a.ll, 0, sizeof(float) * a.B, st);
+  cudaMemsetAsync(a.asum, 0, sizeof(float) * a.B, st);
+  const int n_gt = (a.G + 63) / 64;
+  if (a.bwd) launch_dec(k_dec<2, true>, n_ct * n_gt, tAct, tW3, tX, p, st);
+  else launch_dec(k_dec<2, false>, n_ct * n_gt, tAct, tW3, tX, p, st);
+  k_loss_from_ll<<<8, 256, 0, st>>>(a.ll, a.B, a.c, a.out);
+  note_launch();
+}
+
+void tc_decoder_backward(const TcDecoderArgs& a, cudaStream_t st) {
+  Scratch s = carve(a.scratch, a.B, a.G, a.h);
+  CUtensorMap tAct, tW1, tW3, tX;
+  if (!make_maps(a, s, &tAct, &tW1, &tW3, &tX)) {
+    if (g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
+    return;
+  }
+  DecParams p{};
+  p.B = a.B; p.G = a.G; p.h = a.h; p.bias = a.bias; p.lib = a.lib; p.eps = a.eps; p.c = a.c;
+  p.lse = a.lse; p.ll = a.ll; p.asum = a.asum; p.dlogits = a.dlogits; p.db = a.db;
+  cudaMemsetAsync(a.db, 0, sizeof(float) * 2 * a.G, st);
+  const int n_ct = (a.B + BM - 1) / BM, n_gt = (a.G + 63) / 64;
+  launch_dec(k_dec<3, true>, n_ct * n_gt, tAct, tW3, tX, p, st);
+  // dW[j][i] = sum_b dlogits[b][j] act[b][i]   (both operands MN-major, K = cells)
+  int rc = gemm_tf32(a.dlogits, 2 * a.G, true, s.act, a.h, true, a.dW, a.h, 2 * a.G, a.h, a.B, 1, false, st);
+  // dAct[b][i] = sum_j dlogits[b][j] W[j][i]   (A K-major, B MN-major, K = 2G, split-K + atomics)
+  cudaMemsetAsync(a.dY, 0, sizeof(float) * (size_t)a.B * a.h, st);
+  int m_tiles = (a.B + 127) / 128, n_tiles = (a.h + 255) / 256;
+  int splits = sm_count() / (m_tiles * n_tiles);
+  if (splits < 1) splits = 1;
+  if (rc == 0) rc = gemm_tf32(a.dlogits, 2 * a.G, false, s.Wr, a.h, true, a.dY, a.h, a.B, a.h, 2 * a.G, splits, true, st);
+  if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
+  int blocks = (int)(((size_t)a.B * a.h + 255) / 256);
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  k_gate<<<blocks, 256, 0, st>>>(a.dY, a.U, a.B, a.h, a.bn);
+  note_launch();
+}
+
 }  // namespace drv
