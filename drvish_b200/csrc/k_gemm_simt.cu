@@ -97,8 +97,16 @@ __global__ void __launch_bounds__(NT) k_gemm(const float* __restrict__ A, int ld
     }
   };
 
-  load_tiles(0);
-  for (int k0 = 0; k0 < K; k0 += BK) {
+  // split-K over gridDim.z (EPI_DW only: partial tiles are combined with atomics into a zeroed C)
+  const int k_per = ((K + gridDim.z - 1) / gridDim.z + BK - 1) / BK * BK;
+  const int k_begin = blockIdx.z * k_per;
+  const int k_end = min(K, k_begin + k_per);
+  if (k_begin >= k_end) return;
+  const int K_full = K;
+  K = k_end;
+  (void)K_full;
+  load_tiles(k_begin);
+  for (int k0 = k_begin; k0 < K; k0 += BK) {
     __syncthreads();
     store_tiles();
     __syncthreads();
@@ -166,8 +174,9 @@ __global__ void __launch_bounds__(NT) k_gemm(const float* __restrict__ A, int ld
       if (EPI == EPI_BIAS) {
         C[(size_t)gm * ldc + gn] = v + ep.bias[gn];
       } else if (EPI == EPI_DW) {
-        if (ONES && gn == N - 1) ep.db[gm] = v;
-        else C[(size_t)gm * ldc + gn] = v;
+        float* dst = (ONES && gn == N - 1) ? &ep.db[gm] : &C[(size_t)gm * ldc + gn];
+        if (gridDim.z > 1) atomicAdd(dst, v);
+        else *dst = v;
       } else if (EPI == EPI_GATE) {
         float u = ep.U[(size_t)gm * ep.ldu + gn];
         if (ep.gate.mode == 2) u = sqrtf(u);
@@ -196,9 +205,23 @@ void simt_linear_wgrad(const float* dV, int B, int dout, const float* U, int din
   Prologue pa{0, {}}, pb{pro_mode, bn};
   Epilogue ep{};
   ep.db = db;
-  // M = dout, N = din + 1 (ones column -> db), K = B
-  k_gemm<false, false, true, EPI_DW><<<grid_for(dout, din + 1), NT, 0, st>>>(dV, dout, U, din, dW, din, dout, din + 1, B,
-                                                                             pa, pb, ep);
+  // M = dout, N = din + 1 (ones column -> db), K = B; split-K when the output is too small to
+  // fill the SMs (the reduction runs over the whole minibatch)
+  dim3 grid = grid_for(dout, din + 1);
+  int ctas = grid.x * grid.y;
+  int splits = 1;
+  if (ctas < 296) {
+    splits = 592 / ctas;
+    int max_splits = B / 128;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+  }
+  if (splits > 1) {
+    cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)dout * din, st);
+    cudaMemsetAsync(db, 0, sizeof(float) * (size_t)dout, st);
+    grid.z = splits;
+  }
+  k_gemm<false, false, true, EPI_DW><<<grid, NT, 0, st>>>(dV, dout, U, din, dW, din, dout, din + 1, B, pa, pb, ep);
   note_launch();
 }
 

@@ -108,7 +108,7 @@ struct Plan {
   size_t Gb[2][DRV_MAX_LAYERS + 1];         // dY / dU of each block input (B x din), block 0 of enc unused
   size_t z, l, lse, ll, asum, dO;
   size_t u, m, gfac, du, dz_drs;
-  size_t tc;                                 // scratch of the tcgen05 path
+  size_t tc, tce;                            // scratch of the tcgen05 decoder / encoder paths
   size_t total;
 };
 
@@ -149,6 +149,9 @@ Plan make_plan(const drv_dims& d, const Net& n) {
   }
   p.tc = o;
   o += tc_workspace_bytes(d);
+  o = (o + 255) / 256 * 256;
+  p.tce = o;
+  o += tc_encoder_workspace_bytes(d);
   o = (o + 255) / 256 * 256;
   p.total = o;
   return p;
@@ -310,7 +313,18 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
   const int NB = n.n_blocks;
   prof::mark(0, st);
   // ---- guide: encoder + reparameterised draws (nbvae.py:81-90) --------------------------------
-  for (int k = 0; k < NB; ++k) block_forward(c, 0, k, x, true);
+  const bool use_tce = tc_encoder_supported(d, *hp);
+  TcEncoderArgs te{};
+  if (use_tce) {
+    const Block& e0 = n.enc[0];
+    block_forward(c, 0, 0, x, false);  // statistics of sqrt(x) only
+    te.x = x; te.bn = c.bn(0, 0); te.W = params + e0.W; te.bias = params + e0.bias; te.B = B; te.G = G; te.h = e0.dout;
+    te.H = c.at<float>(p.V[0][0]); te.scratch = c.ws + p.tce;
+    tc_encoder_forward(te, st);
+  } else {
+    block_forward(c, 0, 0, x, true);
+  }
+  for (int k = 1; k < NB; ++k) block_forward(c, 0, k, x, true);
   const float* O = c.at<float>(p.V[0][NB - 1]);
   float* z = c.at<float>(p.z);
   float* l = c.at<float>(p.l);
@@ -379,8 +393,17 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
                     c.at<float>(p.asum), B, L, *hp, c.at<float>(p.dO), st);
     prof::mark(6, st);
     // ---- encoder backward ----------------------------------------------------------------------
-    for (int k = NB - 1; k >= 0; --k)
+    for (int k = NB - 1; k >= 1; --k)
       block_backward(c, 0, k, x, k == NB - 1 ? c.at<float>(p.dO) : c.at<float>(p.Gb[0][k + 1]), false);
+    if (use_tce) {
+      const Block& e0 = n.enc[0];
+      te.dH = c.at<float>(p.Gb[0][1]); te.dW = grads + e0.W; te.db = grads + e0.bias;
+      te.gacc = c.at<double>(p.grad_acc[0][0]);
+      tc_encoder_backward(te, st);
+      block_backward(c, 0, 0, x, nullptr, true);  // d gamma / d beta from the reduced sums
+    } else {
+      block_backward(c, 0, 0, x, c.at<float>(p.Gb[0][1]), false);
+    }
     prof::mark(7, st);
   }
   if (bn_batches && !(hp->flags & DRV_FLAG_NO_BN_UPDATE)) bump_counters(bn_batches, n.n_bn, st);

@@ -34,5 +34,27 @@ namespace drv {
 namespace tc {
 int gemm_tf32(const float* A, int lda, bool a_mn, const float* Bm, int ldb, bool b_mn, float* C, int ldc, int M, int N,
               int K, int splits, bool accumulate_atomic, cudaStream_t st);
+int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs, int lda, bool a_mn, int ldb, bool b_mn,
+                    float* C, int ldc, int M, int N, int K, int splits, bool accumulate_atomic, const float* bias,
+                    cudaStream_t st);
 }
+
+// Encoder first layer (BatchNorm(G) -> ReLU -> Linear(G, h), reference modules.py:19-21,56) on the
+// tensor cores.  See tc_encoder.cu.
+struct TcEncoderArgs {
+  const float* x;     // [B][G] counts
+  BnParams bn;        // statistics / affine of the input BatchNorm (over sqrt(x))
+  const float* W;     // [h][G]
+  const float* bias;  // [h]
+  int B, G, h;
+  float* H;           // [B][h] output of the Linear
+  void* scratch;
+  const float* dH;    // [B][h] backward input
+  float *dW, *db;     // [h][G], [h]
+  double* gacc;       // [2][G]: sum_b dY, sum_b dY*xhat  (-> d beta, d gamma)
+};
+size_t tc_encoder_workspace_bytes(const drv_dims& d);
+bool tc_encoder_supported(const drv_dims& d, const drv_hparams& hp);
+void tc_encoder_forward(const TcEncoderArgs& a, cudaStream_t st);
+void tc_encoder_backward(const TcEncoderArgs& a, cudaStream_t st);
 }  // namespace drv

@@ -1,0 +1,197 @@
+// Encoder first layer on the sm_100a tensor cores: H = relu(bn(sqrt(x))) W^T + b and its backward.
+// (reference: Encoder.forward modules.py:56 -> make_fc modules.py:19-21.)
+//
+// Precision: this GEMM feeds a BatchNorm -> ReLU directly, so rounding its
+// inputs to tf32 flips ReLU gates and costs ~5e-3 of gradient accuracy.  The forward therefore
+// runs as a 3-term split ("3xTF32"): A = A_hi + A_lo, W = W_hi + W_lo with each part exactly
+// representable in tf32, H = A_lo W_hi^T + A_hi W_lo^T + A_hi W_hi^T accumulated in one TMEM
+// accumulator (fp32) - error ~2^-22 per product, i.e. fp32-class.  The backward GEMMs
+// (dW = dH^T A, dA = dH W) tolerate single-pass tf32 and reuse A_hi / W_hi; dA is reduced to
+// the BatchNorm gradients (the input x is data, so no dX is needed).
+#include "kernels.cuh"
+#include "tc.cuh"
+#include "tc_common.cuh"
+
+namespace drv {
+
+namespace {
+
+__device__ __forceinline__ float rna_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+// a = relu(bn(sqrt(x))) split into tf32 hi/lo parts
+__global__ void k_enc_prep(const float* __restrict__ x, size_t n, int G, BnParams bn, float* __restrict__ hi,
+                           float* __restrict__ lo) {
+  for (size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i4 < n; i4 += (size_t)gridDim.x * blockDim.x * 4) {
+    float4 xv = *reinterpret_cast<const float4*>(x + i4);
+    int col = (int)(i4 % G);  // G % 4 == 0: the four elements share a row
+    float in[4] = {xv.x, xv.y, xv.z, xv.w}, h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int c = col + j;
+      float a = bn_relu(sqrtf(in[j]), bn.mean[c], bn.rstd[c], bn.gamma[c], bn.beta[c]);
+      h[j] = rna_tf32(a);
+      l[j] = rna_tf32(a - h[j]);
+    }
+    *reinterpret_cast<float4*>(hi + i4) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(lo + i4) = make_float4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+__global__ void k_split_tf32(const float* __restrict__ src, size_t n, float* __restrict__ hi, float* __restrict__ lo) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float v = src[i];
+    float h = rna_tf32(v);
+    hi[i] = h;
+    lo[i] = rna_tf32(v - h);
+  }
+}
+
+__global__ void k_round_rows(const float* __restrict__ src, size_t n, float* __restrict__ dst) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = rna_tf32(src[i]);
+}
+
+__global__ void k_colsum_small(const float* __restrict__ V, int B, int D, float* __restrict__ out) {
+  // one CTA per 32 columns, 8 row lanes
+  int col = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (col < D)
+    for (int r = threadIdx.y; r < B; r += 8) s += V[(size_t)r * D + col];
+  __shared__ float sh[8][32];
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < D) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+    out[col] = t;
+  }
+}
+
+// gacc[0][g] += sum_b dA*gate ; gacc[1][g] += sum_b dA*gate*xhat   (gate, xhat recomputed from x)
+constexpr int CW = 32, RY = 8;
+__global__ void __launch_bounds__(CW* RY) k_bn0_grad(const float* __restrict__ dA, const float* __restrict__ x, int B,
+                                                      int G, int rows_per_cta, BnParams bn, double* __restrict__ acc) {
+  int col = blockIdx.x * CW + threadIdx.x;
+  int r0 = blockIdx.y * rows_per_cta;
+  int r1 = min(B, r0 + rows_per_cta);
+  float s1 = 0.f, s2 = 0.f;
+  if (col < G) {
+    float mean = bn.mean[col], rstd = bn.rstd[col], g = bn.gamma[col], be = bn.beta[col];
+    for (int r = r0 + threadIdx.y; r < r1; r += RY) {
+      float xh = bn_xhat(sqrtf(x[(size_t)r * G + col]), mean, rstd);
+      if (bn_y(xh, g, be) > 0.f) {
+        float d = dA[(size_t)r * G + col];
+        s1 += d;
+        s2 = __fmaf_rn(d, xh, s2);
+      }
+    }
+  }
+  __shared__ float sh[2][RY][CW];
+  sh[0][threadIdx.y][threadIdx.x] = s1;
+  sh[1][threadIdx.y][threadIdx.x] = s2;
+  __syncthreads();
+  if (threadIdx.y < 2 && col < G) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < RY; ++i) t += (double)sh[threadIdx.y][i][threadIdx.x];
+    atomicAdd(&acc[(size_t)threadIdx.y * G + col], t);
+  }
+}
+
+struct Scratch {
+  float *a_hi, *a_lo, *w_hi, *w_lo, *dh_r;
+  size_t total;
+};
+
+Scratch carve(void* base, int B, int G, int h) {
+  Scratch s{};
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = (o + bytes + 255) / 256 * 256; return r; };
+  size_t ah = take(4 * (size_t)B * G), al = take(4 * (size_t)B * G);
+  size_t wh = take(4 * (size_t)h * G), wl = take(4 * (size_t)h * G), dh = take(4 * (size_t)B * h);
+  s.total = o;
+  if (base) {
+    char* c = (char*)base;
+    s.a_hi = (float*)(c + ah);
+    s.a_lo = (float*)(c + al);
+    s.w_hi = (float*)(c + wh);
+    s.w_lo = (float*)(c + wl);
+    s.dh_r = (float*)(c + dh);
+  }
+  return s;
+}
+
+int n_sm() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace
+
+size_t tc_encoder_workspace_bytes(const drv_dims& d) { return carve(nullptr, d.n_cells, d.n_genes, d.layers[0]).total; }
+
+bool tc_encoder_supported(const drv_dims& d, const drv_hparams& hp) {
+  if (hp.flags & DRV_FLAG_FORCE_SIMT) return false;
+  int h = d.layers[0];
+  return d.n_genes % 4 == 0 && d.n_genes >= 64 && h % 32 == 0 && h >= 32 && d.n_cells >= 32;
+}
+
+void tc_encoder_forward(const TcEncoderArgs& a, cudaStream_t st) {
+  Scratch s = carve(a.scratch, a.B, a.G, a.h);
+  const size_t n = (size_t)a.B * a.G;
+  k_enc_prep<<<n_sm() * 8, 256, 0, st>>>(a.x, n, a.G, a.bn, s.a_hi, s.a_lo);
+  note_launch();
+  k_split_tf32<<<n_sm() * 4, 256, 0, st>>>(a.W, (size_t)a.h * a.G, s.w_hi, s.w_lo);
+  note_launch();
+  cudaMemsetAsync(a.H, 0, sizeof(float) * (size_t)a.B * a.h, st);
+  const float* As[3] = {s.a_lo, s.a_hi, s.a_hi};
+  const float* Bs[3] = {s.w_hi, s.w_lo, s.w_hi};
+  int m_tiles = (a.B + 127) / 128, n_tiles = (a.h + 255) / 256;
+  int splits = n_sm() / (m_tiles * n_tiles);
+  if (splits < 1) splits = 1;
+  int rc = tc::gemm_tf32_multi(3, As, Bs, a.G, false, a.G, false, a.H, a.h, a.B, a.h, a.G, splits, true, a.bias, st);
+  if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
+}
+
+void tc_encoder_backward(const TcEncoderArgs& a, cudaStream_t st) {
+  Scratch s = carve(a.scratch, a.B, a.G, a.h);
+  // tf32 operands are rounded to nearest when produced (the MMA truncates)
+  k_round_rows<<<n_sm() * 2, 256, 0, st>>>(a.dH, (size_t)a.B * a.h, s.dh_r);
+  note_launch();
+  dim3 cb(32, 8);
+  k_colsum_small<<<(a.h + 31) / 32, cb, 0, st>>>(a.dH, a.B, a.h, a.db);
+  note_launch();
+  // dW[j][g] = sum_b dH[b][j] A[b][g]: both operands MN-major (K = cells), split-K + atomics
+  cudaMemsetAsync(a.dW, 0, sizeof(float) * (size_t)a.h * a.G, st);
+  int m_tiles = (a.h + 127) / 128, n_tiles = (a.G + 255) / 256;
+  int splits = n_sm() / (m_tiles * n_tiles);
+  if (splits < 1) splits = 1;
+  int rc = tc::gemm_tf32(s.dh_r, a.h, true, s.a_hi, a.G, true, a.dW, a.G, a.h, a.G, a.B, splits, true, st);
+  // dA[b][g] = sum_j dH[b][j] W[j][g]: A K-major, B MN-major (K = h); dA reuses the A_lo buffer
+  float* dA = s.a_lo;
+  if (rc == 0) rc = tc::gemm_tf32(s.dh_r, a.h, false, s.w_hi, a.G, true, dA, a.G, a.B, a.G, a.h, 1, false, st);
+  if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
+  // reduce dA to the input-BatchNorm gradients
+  int col_blocks = (a.G + CW - 1) / CW;
+  int S = (n_sm() * 4 + col_blocks - 1) / col_blocks;
+  int max_split = (a.B + RY * 4 - 1) / (RY * 4);
+  if (S > max_split) S = max_split;
+  if (S < 1) S = 1;
+  int rows = ((a.B + S - 1) / S + RY - 1) / RY * RY;
+  S = (a.B + rows - 1) / rows;
+  dim3 grid(col_blocks, S), block(CW, RY);
+  k_bn0_grad<<<grid, block, 0, st>>>(dA, a.x, a.B, a.G, rows, a.bn, a.gacc);
+  note_launch();
+}
+
+}  // namespace drv

@@ -56,8 +56,11 @@ constexpr int NTHREADS = 192;
 
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NTHREADS, 1)
-k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
-          int ldc, int M, int N, int K, int kb_per_split, int n_tile, int use_atomic, int mn_lbo, int mn_sbo, int mn_kstep) {
+k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+          const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+          const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, int n_pairs,
+          float* __restrict__ C, int ldc, int M, int N, int K, int kb_per_split, int n_tile, int use_atomic,
+          const float* __restrict__ bias, int mn_lbo, int mn_sbo, int mn_kstep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
@@ -67,7 +70,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * n_tile;
-  const int kb_total = (K + BK - 1) / BK;
+  // the operand pairs are concatenated along a virtual K axis: sum_p A_p B_p^T accumulates in TMEM
+  const int kb_pair = (K + BK - 1) / BK;
+  const int kb_total = kb_pair * n_pairs;
   const int kb0 = blockIdx.z * kb_per_split;
   const int kb1 = min(kb_total, kb0 + kb_per_split);
   const int nkb = kb1 - kb0;
@@ -98,16 +103,19 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         uint8_t* sa = smem + s * STAGE_BYTES;
         uint8_t* sb = sa + A_BYTES;
         mbar_expect_tx(&full[s], tx);
-        const int k0 = (kb0 + i) * BK;
+        const int pair = (kb0 + i) / kb_pair;
+        const int k0 = ((kb0 + i) - pair * kb_pair) * BK;
+        const CUtensorMap* ma = pair == 0 ? &tmA : (pair == 1 ? &tmA1 : &tmA2);
+        const CUtensorMap* mb = pair == 0 ? &tmB : (pair == 1 ? &tmB1 : &tmB2);
         if (A_MN) {
-          for (int j = 0; j < BM / 32; ++j) tma_load_2d(sa + j * 4096, &tmA, &full[s], m0 + 32 * j, k0);
+          for (int j = 0; j < BM / 32; ++j) tma_load_2d(sa + j * 4096, ma, &full[s], m0 + 32 * j, k0);
         } else {
-          tma_load_2d(sa, &tmA, &full[s], k0, m0);
+          tma_load_2d(sa, ma, &full[s], k0, m0);
         }
         if (B_MN) {
-          for (int j = 0; j < n_tile / 32; ++j) tma_load_2d(sb + j * 4096, &tmB, &full[s], n0 + 32 * j, k0);
+          for (int j = 0; j < n_tile / 32; ++j) tma_load_2d(sb + j * 4096, mb, &full[s], n0 + 32 * j, k0);
         } else {
-          tma_load_2d(sb, &tmB, &full[s], k0, n0);
+          tma_load_2d(sb, mb, &full[s], k0, n0);
         }
       }
     }
@@ -147,8 +155,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             if (n0 + c + j < N) {
-              if (use_atomic) atomicAdd(dst + j, v[j]);
-              else dst[j] = v[j];
+              float o = v[j];
+              if (bias != nullptr && blockIdx.z == 0) o += __ldg(&bias[n0 + c + j]);
+              if (use_atomic) atomicAdd(dst + j, o);
+              else dst[j] = o;
             }
           }
         }
@@ -165,21 +175,27 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
 }  // namespace
 
-// A: K-major [M][K] (lda = K stride... row stride in elements) or MN-major [K][M]; same for B.
-// Requirements: row strides multiples of 4 floats, bases 16-byte aligned, N tile multiple of 16.
-int gemm_tf32(const float* A, int lda, bool a_mn, const float* Bm, int ldb, bool b_mn, float* C, int ldc, int M, int N,
-              int K, int splits, bool accumulate_atomic, cudaStream_t st) {
-  CUtensorMap ta, tb;
+// A: K-major [M][K] (lda = row stride in elements) or MN-major [K][M]; same for B.
+// Requirements: row strides multiples of 4 floats, bases 16-byte aligned, N tile multiple of 16
+// (32 for an MN-major B).  n_pairs operand pairs (same shapes/strides) are summed: C = sum_p A_p B_p^T.
+int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs, int lda, bool a_mn, int ldb, bool b_mn,
+                    float* C, int ldc, int M, int N, int K, int splits, bool accumulate_atomic, const float* bias,
+                    cudaStream_t st) {
+  if (n_pairs < 1 || n_pairs > 3) return -3;
+  CUtensorMap ta[3], tb[3];
   int n_tile = N >= MAXN ? MAXN : ((N + 15) / 16) * 16;
-  bool ok;
-  if (a_mn) ok = tmap_2d(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, 32, 2);
-  else ok = tmap_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK);
-  if (!ok) return -3;
-  if (b_mn) ok = tmap_2d(&tb, Bm, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, 32, 2);
-  else ok = tmap_2d(&tb, Bm, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)n_tile, BK);
-  if (!ok) return -3;
   if (b_mn && n_tile % 32) return -3;
-  int kb_total = (K + BK - 1) / BK;
+  for (int p = 0; p < 3; ++p) {
+    int q = p < n_pairs ? p : 0;
+    bool ok;
+    if (a_mn) ok = tmap_2d(&ta[p], As[q], (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, 32, 2);
+    else ok = tmap_2d(&ta[p], As[q], (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK);
+    if (!ok) return -3;
+    if (b_mn) ok = tmap_2d(&tb[p], Bs[q], (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, 32, 2);
+    else ok = tmap_2d(&tb[p], Bs[q], (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)n_tile, BK);
+    if (!ok) return -3;
+  }
+  int kb_total = ((K + BK - 1) / BK) * n_pairs;
   if (splits < 1) splits = 1;
   if (splits > kb_total) splits = kb_total;
   int kps = (kb_total + splits - 1) / splits;
@@ -188,7 +204,8 @@ int gemm_tf32(const float* A, int lda, bool a_mn, const float* Bm, int ldb, bool
   int atomic = (splits > 1 || accumulate_atomic) ? 1 : 0;
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(ta, tb, C, ldc, M, N, K, kps, n_tile, atomic, g_mn_lbo, g_mn_sbo, g_mn_kstep);
+    kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(ta[0], tb[0], ta[1], tb[1], ta[2], tb[2], n_pairs, C, ldc, M, N, K, kps,
+                                             n_tile, atomic, bias, g_mn_lbo, g_mn_sbo, g_mn_kstep);
   };
   if (a_mn && b_mn) launch(k_tc_gemm<true, true>);
   else if (a_mn) launch(k_tc_gemm<true, false>);
@@ -196,6 +213,11 @@ int gemm_tf32(const float* A, int lda, bool a_mn, const float* Bm, int ldb, bool
   else launch(k_tc_gemm<false, false>);
   note_launch();
   return 0;
+}
+
+int gemm_tf32(const float* A, int lda, bool a_mn, const float* Bm, int ldb, bool b_mn, float* C, int ldc, int M, int N,
+              int K, int splits, bool accumulate_atomic, cudaStream_t st) {
+  return gemm_tf32_multi(1, &A, &Bm, lda, a_mn, ldb, b_mn, C, ldc, M, N, K, splits, accumulate_atomic, nullptr, st);
 }
 
 }  // namespace tc
