@@ -79,12 +79,6 @@ static __constant__ float c_lgamma1p[32] = {
     61.2617017610020020f, 64.5575386270063311f, 67.8897431371815350f, 71.2570389671680090f,
     74.6582363488301644f, 78.0922235533153106f};
 
-__device__ __forceinline__ float lgamma1p_count(float x) {
-  int xi = (int)x;
-  if (x < 32.f && (float)xi == x) return c_lgamma1p[xi];
-  return lgammaf(1.f + x);
-}
-
 // Result of one (cell, gene) element of the NB block.
 struct NbElem {
   float ll;    // log NB(x | r, logits=ell)
@@ -92,52 +86,121 @@ struct NbElem {
   float drho;  // dLL/d rho = e^rho (log sigmoid(-ell) + psi(r+x) - psi(r)) - a
 };
 
-// ls = s - logsumexp(s) (log softmax of the scale half), rho = log_r, l = library, x = count.
+__device__ __forceinline__ float ex2_approx(float v) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float lg2_approx(float v) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+
+// Copies log(x!) for x < 32 into a 32-float shared-memory table (one bank per entry: divergent
+// count lookups are conflict-free, unlike a constant-memory lookup).
+__device__ __forceinline__ void load_lgamma_table(float* tab_smem, int tid) {
+  if (tid < 32) tab_smem[tid] = c_lgamma1p[tid];
+}
+
+// Rare path (non-integer count, count >= 32 or r >= 1e4): generic lgamma / digamma.  Kept out of
+// line so that the hot epilogue loop stays small enough for the instruction cache.
+static __device__ __noinline__ float2 nb_count_slow(float r, float x, bool bwd) {
+  float2 o;
+  o.x = lgammaf(r + x) - lgammaf(r) - lgammaf(1.f + x);
+  o.y = bwd ? digamma_pos(r + x) - digamma_pos(r) : 0.f;
+  return o;
+}
+
+// NV elements of the NB block per thread.  MUST be called by all 32 lanes of a converged warp
+// (lanes / slots without a valid element pass x = 0 and ignore the result): the count-dependent
+// part is ONE warp-uniform loop shared by the NV independent elements (instruction-level
+// parallelism NV, no per-lane divergence).
+//   lsl = library + s - logsumexp(s)  (so ell = lsl - rho),  rho = log_r,  x = count >= 0.
 // Follows torch.distributions.NegativeBinomial.log_prob (negative_binomial.py:130-150):
-//   r logsig(-ell) + x logsig(ell) + lgamma(r+x) - lgamma(1+x) - lgamma(r)
-// with the lgamma / digamma differences formed directly (exact finite products for small
-// integer counts), which is at least as accurate as torch's fp32 evaluation.
-template <bool BWD>
-__device__ __forceinline__ NbElem nb_elem(float ls, float rho, float l, float x, float eps) {
-  NbElem o;
-  float rexp = __expf(rho);
-  float r = rexp + eps;
-  float ell = l + ls - rho;
-  float e = __expf(-fabsf(ell));
-  float lp = log1pf(e);
-  float sp = fmaxf(ell, 0.f) + lp;  // softplus(ell) = -logsigmoid(-ell)
-  float lgd, psd = 0.f;
-  int xi = (int)x;
-  if (x == 0.f) {
-    lgd = 0.f;
-  } else if (x <= 8.f && (float)xi == x && r < 1.0e4f) {
-    // lgamma(r+x) - lgamma(r) = log prod_{k<x} (r+k);  psi(r+x) - psi(r) = P'/P
-    float P = 1.f, Pd = 0.f;
+//   r logsig(-ell) + x logsig(ell) + lgamma(r+x) - lgamma(1+x) - lgamma(r),   r = e^rho + eps
+// written as  x ell - (x + r) softplus(ell) + [lgamma(r+x) - lgamma(r)] - log(x!).
+// For integer counts below 32 the bracket is the exact finite product log prod_{k<x}(r + k) and
+// psi(r+x) - psi(r) = sum_{k<x} 1/(r+k) = P'/P (at least as accurate as torch's fp32 lgamma /
+// digamma differences, and x = 0 - the majority of scRNA entries - costs nothing); other counts
+// take the generic lgamma / digamma route.  No int<->float conversions (they share the SFU pipe).
+template <bool BWD, int NV>
+__device__ __forceinline__ void nb_elems(const float (&lsl)[NV], const float (&rho)[NV], const float (&x)[NV], float eps,
+                                         const float* __restrict__ lgtab, NbElem (&o)[NV]) {
+  const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f, MAGIC = 8388608.f;
+  float rexp[NV], r[NV], ell[NV], e[NV], t[NV], sp[NV], xl[NV], lgx[NV];
+  bool fast[NV];
+  float xm = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (k < xi) {
-        float t = r + (float)k;
-        if (BWD) Pd = __fmaf_rn(Pd, t, P);
-        P *= t;
+  for (int v = 0; v < NV; ++v) {
+    rexp[v] = ex2_approx(rho[v] * LOG2E);
+    r[v] = rexp[v] + eps;
+    ell[v] = lsl[v] - rho[v];
+    e[v] = ex2_approx(-fabsf(ell[v]) * LOG2E);
+    t[v] = 1.f + e[v];
+    sp[v] = __fmaf_rn(lg2_approx(t[v]), LN2, fmaxf(ell[v], 0.f));  // softplus(ell)
+    const float xr = x[v] + MAGIC;                                  // integer test without F2I/I2F
+    fast[v] = ((xr - MAGIC) == x[v]) && (x[v] < 32.f) && (r[v] < 1.0e4f);
+    xl[v] = fast[v] ? x[v] : 0.f;
+    lgx[v] = lgtab[__float_as_int(xr) & 31];
+    xm = fmaxf(xm, xl[v]);
+  }
+  const float xmax = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(xm)));
+  float lg2sum[NV], psd[NV], P[NV], Pd[NV], tk[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    lg2sum[v] = 0.f; psd[v] = 0.f; P[v] = 1.f; Pd[v] = 0.f; tk[v] = r[v];
+  }
+  int k8 = 0;
+  for (float kf = 0.f; kf < xmax; kf += 1.f) {  // warp-uniform trip count
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      if (kf < xl[v]) {
+        if (BWD) Pd[v] = __fmaf_rn(Pd[v], tk[v], P[v]);
+        P[v] *= tk[v];
+      }
+      tk[v] += 1.f;
+    }
+    if (++k8 == 8) {  // fold every 8 factors: no overflow for r < 1e4
+      k8 = 0;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        lg2sum[v] += lg2_approx(P[v]);
+        if (BWD) psd[v] += __fdividef(Pd[v], P[v]);
+        P[v] = 1.f;
+        Pd[v] = 0.f;
       }
     }
-    lgd = __logf(P);
-    if (BWD) psd = __fdividef(Pd, P);
-  } else {
-    lgd = lgammaf(r + x) - lgammaf(r);
-    if (BWD) psd = digamma_pos(r + x) - digamma_pos(r);
   }
-  o.ll = x * ell - (x + r) * sp + lgd - lgamma1p_count(x);
-  if (BWD) {
-    float inv = __fdividef(1.f, 1.f + e);
-    float sig = ell >= 0.f ? inv : e * inv;
-    o.a = x - (x + r) * sig;
-    o.drho = rexp * (psd - sp) - o.a;
-  } else {
-    o.a = 0.f;
-    o.drho = 0.f;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    lg2sum[v] += lg2_approx(P[v]);
+    if (BWD) psd[v] += __fdividef(Pd[v], P[v]);
+    float cnt = __fmaf_rn(lg2sum[v], LN2, -lgx[v]);  // lgamma(r+x) - lgamma(r) - lgamma(1+x)
+    if (!fast[v]) {
+      const float2 sl = nb_count_slow(r[v], x[v], BWD);
+      cnt = sl.x;
+      if (BWD) psd[v] = sl.y;
+    }
+    o[v].ll = __fmaf_rn(x[v], ell[v], cnt) - (x[v] + r[v]) * sp[v];
+    if (BWD) {
+      const float inv = __fdividef(1.f, t[v]);
+      const float sig = ell[v] >= 0.f ? inv : e[v] * inv;
+      o[v].a = x[v] - (x[v] + r[v]) * sig;
+      o[v].drho = rexp[v] * (psd[v] - sp[v]) - o[v].a;
+    } else {
+      o[v].a = 0.f;
+      o[v].drho = 0.f;
+    }
   }
-  return o;
+}
+
+template <bool BWD>
+__device__ __forceinline__ NbElem nb_elem(float lsl, float rho, float x, float eps, const float* __restrict__ lgtab) {
+  const float a[1] = {lsl}, b[1] = {rho}, c[1] = {x};
+  NbElem o[1];
+  nb_elems<BWD, 1>(a, b, c, eps, lgtab, o);
+  return o[0];
 }
 
 // softplus / its derivative exactly as torch.nn.functional.softplus (beta=1, threshold=20)

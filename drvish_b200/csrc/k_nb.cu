@@ -42,6 +42,9 @@ __global__ void __launch_bounds__(NBT) k_nb_rows(float* __restrict__ logits, con
                                                  float* __restrict__ lse_out, float* __restrict__ ll_out,
                                                  float* __restrict__ asum_out, drv_step_out* out) {
   __shared__ float sh[NBT / 32];
+  __shared__ float lgtab[32];
+  load_lgamma_table(lgtab, threadIdx.x);
+  __syncthreads();
   const int b = blockIdx.x;
   float* s = logits + (size_t)b * 2 * G;
   float* rho = s + G;
@@ -57,12 +60,30 @@ __global__ void __launch_bounds__(NBT) k_nb_rows(float* __restrict__ logits, con
   se = block_sum(se, sh);
   const float lse = mx + logf(se);
 
-  // pass 2: log-likelihood and sum_g dLL/d ell
+  // pass 2: log-likelihood and sum_g dLL/d ell (warp-uniform loops: nb_elems needs converged
+  // warps; each lane handles 4 genes per iteration for instruction-level parallelism)
+  const int lane = threadIdx.x % 32, wbase = (threadIdx.x / 32) * 128;
+  const float lml = l - lse;
   float ll = 0.f, asum = 0.f;
-  for (int g = threadIdx.x; g < G; g += NBT) {
-    NbElem e = nb_elem<BWD>(s[g] - lse, rho[g], l, xr[g], eps);
-    ll += e.ll;
-    if (BWD) asum += e.a;
+  for (int g0 = wbase; g0 < G; g0 += NBT * 4) {
+    float a_lsl[4], a_rho[4], a_x[4];
+    bool ok[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int g = g0 + 32 * v + lane;
+      ok[v] = g < G;
+      a_lsl[v] = ok[v] ? lml + s[g] : 0.f;
+      a_rho[v] = ok[v] ? rho[g] : 0.f;
+      a_x[v] = ok[v] ? xr[g] : 0.f;
+    }
+    NbElem e[4];
+    nb_elems<BWD, 4>(a_lsl, a_rho, a_x, eps, lgtab, e);
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+      if (ok[v]) {
+        ll += e[v].ll;
+        if (BWD) asum += e[v].a;
+      }
   }
   ll = block_sum(ll, sh);
   if (BWD) asum = block_sum(asum, sh);
@@ -75,12 +96,27 @@ __global__ void __launch_bounds__(NBT) k_nb_rows(float* __restrict__ logits, con
   if (!BWD) return;
 
   // pass 3: d loss / d logits in place (loss = -c * LL):  ds = -c (a - p A),  drho = -c dLL/drho
-  for (int g = threadIdx.x; g < G; g += NBT) {
-    float ls = s[g] - lse;
-    NbElem e = nb_elem<true>(ls, rho[g], l, xr[g], eps);
-    float p = __expf(ls);
-    s[g] = -c * (e.a - p * asum);
-    rho[g] = -c * e.drho;
+  for (int g0 = wbase; g0 < G; g0 += NBT * 4) {
+    float a_lsl[4], a_rho[4], a_x[4], ls[4];
+    bool ok[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int g = g0 + 32 * v + lane;
+      ok[v] = g < G;
+      ls[v] = ok[v] ? s[g] - lse : 0.f;
+      a_lsl[v] = l + ls[v];
+      a_rho[v] = ok[v] ? rho[g] : 0.f;
+      a_x[v] = ok[v] ? xr[g] : 0.f;
+    }
+    NbElem e[4];
+    nb_elems<true, 4>(a_lsl, a_rho, a_x, eps, lgtab, e);
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+      if (ok[v]) {
+        const int g = g0 + 32 * v + lane;
+        s[g] = -c * (e[v].a - __expf(ls[v]) * asum);
+        rho[g] = -c * e[v].drho;
+      }
   }
 }
 

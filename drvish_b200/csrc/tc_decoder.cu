@@ -33,7 +33,7 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int X_BYTES = 2 * BM * 32 * 4;   // one count tile: two 128x32 boxes = 32 KB
 constexpr int N_EPI_WARPS = 16;
 constexpr int NTHREADS = (N_EPI_WARPS + 2) * 32;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * X_BYTES + 1024 + 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * X_BYTES + 1024 + 512;
 constexpr int TMEM_COLS = 256;
 
 // tcgen05 kind::tf32 TRUNCATES the low 13 mantissa bits of its fp32 operands, which biases every
@@ -75,6 +75,8 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
   uint64_t* x_full = acc_empty + 2;       // [2]
   uint64_t* x_empty = x_full + 2;         // [2]
   uint32_t* tmem_slot = (uint32_t*)(x_empty + 2);
+  float* lgtab = (float*)(tmem_slot + 4);
+  load_lgamma_table(lgtab, threadIdx.x);
 
   constexpr int TN = PHASE == 1 ? 128 : 64;  // genes per tile
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -218,85 +220,121 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
           p.part_s[slot] = s;
         }
       } else {
+        // phases 2/3: this warp owns 16 genes of the 64-gene tile, processed as a ROLLED loop
+        // over 4 groups of 4 columns (compact code: the fully unrolled epilogue thrashed the
+        // instruction cache); nb_elems<.,4> provides the instruction-level parallelism.
         const int xs = it & 1, xph = (it >> 1) & 1;
-        float sv[16], rv[16], xv[16];
-        tmem_ld16(tbase + cg * 16, sv);
-        tmem_ld16(tbase + 64 + cg * 16, rv);
         mbar_wait(&x_full[xs], xph);
-        {
-          // count tile: box (cg/2), row r, 16-byte chunks (cg%2)*4 + j, XOR-swizzled with r%8
-          const uint8_t* xrow = xbuf + xs * X_BYTES + (cg >> 1) * (X_BYTES / 2) + r * 128;
+        const int gbase = g0 + cg * 16;
+        const float lml = lib_b - lse_b;
+        const uint8_t* xrow = xbuf + xs * X_BYTES + (cg >> 1) * (X_BYTES / 2) + r * 128;
+        const bool full_cols = gbase + 16 <= p.G;
+#pragma unroll 1
+        for (int g4 = 0; g4 < 4; ++g4) {
+          float sv[4], rv[4], xv[4], bs[4], br[4];
+          tmem_ld4(tbase + cg * 16 + g4 * 4, sv);
+          tmem_ld4(tbase + 64 + cg * 16 + g4 * 4, rv);
+          {
+            // count tile: box (cg/2), row r, 16-byte chunk (cg%2)*4 + g4, XOR-swizzled with r%8
+            const int chunk = ((cg & 1) * 4 + g4) ^ (r & 7);
+            const float4 f = *reinterpret_cast<const float4*>(xrow + chunk * 16);
+            xv[0] = f.x; xv[1] = f.y; xv[2] = f.z; xv[3] = f.w;
+          }
+          const int gq = gbase + 4 * g4;
+          if (full_cols) {  // warp-uniform addresses -> broadcast loads
+            const float4 f = __ldg(reinterpret_cast<const float4*>(p.bias + gq));
+            const float4 h2 = __ldg(reinterpret_cast<const float4*>(p.bias + p.G + gq));
+            bs[0] = f.x; bs[1] = f.y; bs[2] = f.z; bs[3] = f.w;
+            br[0] = h2.x; br[1] = h2.y; br[2] = h2.z; br[3] = h2.w;
+          } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int chunk = ((cg & 1) * 4 + j) ^ (r & 7);
-            float4 f = *reinterpret_cast<const float4*>(xrow + chunk * 16);
-            xv[4 * j] = f.x; xv[4 * j + 1] = f.y; xv[4 * j + 2] = f.z; xv[4 * j + 3] = f.w;
+            for (int v = 0; v < 4; ++v) {
+              const bool okg = gq + v < p.G;
+              bs[v] = okg ? __ldg(&p.bias[gq + v]) : 0.f;
+              br[v] = okg ? __ldg(&p.bias[p.G + gq + v]) : 0.f;
+            }
+          }
+          tmem_ld_wait();
+          float a_lsl[4], a_rho[4], a_x[4], ls[4];
+          bool ok[4];
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            ok[v] = row_ok && (gq + v < p.G);
+            ls[v] = ok[v] ? sv[v] + bs[v] - lse_b : 0.f;
+            a_lsl[v] = PHASE == 2 ? (ok[v] ? lml + sv[v] + bs[v] : 0.f) : lib_b + ls[v];
+            a_rho[v] = ok[v] ? rv[v] + br[v] : 0.f;
+            a_x[v] = ok[v] ? xv[v] : 0.f;
+          }
+          NbElem e[4];
+          nb_elems<(PHASE == 3) || WITH_A, 4>(a_lsl, a_rho, a_x, p.eps, lgtab, e);
+          if (PHASE == 2) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              if (ok[v]) {
+                ll_acc += e[v].ll;
+                if (WITH_A) a_acc += e[v].a;
+              }
+            }
+          } else {
+            // backward: ds = -c (a - p A), drho = -c dLL/drho (rounded to tf32: MMA operands)
+            float ds[4], dr[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              ds[v] = ok[v] ? rna_tf32(-p.c * (e[v].a - ex2_approx(ls[v] * 1.4426950408889634f) * asum_b)) : 0.f;
+              dr[v] = ok[v] ? rna_tf32(-p.c * e[v].drho) : 0.f;
+            }
+            if (row_ok) {
+              float* d0 = p.dlogits + (size_t)b * 2 * p.G + gq;
+              float* d1 = d0 + p.G;
+              if (gq + 4 <= p.G) {
+                *reinterpret_cast<float4*>(d0) = make_float4(ds[0], ds[1], ds[2], ds[3]);
+                *reinterpret_cast<float4*>(d1) = make_float4(dr[0], dr[1], dr[2], dr[3]);
+              } else {
+#pragma unroll
+                for (int v = 0; v < 4; ++v)
+                  if (gq + v < p.G) { d0[v] = ds[v]; d1[v] = dr[v]; }
+              }
+            }
+            // bias gradient: column sums over the 32 rows of this warp by a transposing butterfly
+            // (8 values x 32 lanes -> 8 sums in 9 shuffles), then one atomic per column
+            float w8[8] = {ds[0], ds[1], ds[2], ds[3], dr[0], dr[1], dr[2], dr[3]};
+            {
+              const bool hi16 = lane & 16;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float send = hi16 ? w8[i] : w8[i + 4];
+                float keep = hi16 ? w8[i + 4] : w8[i];
+                w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+              }
+              const bool hi8 = lane & 8;
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                float send = hi8 ? w8[i] : w8[i + 2];
+                float keep = hi8 ? w8[i + 2] : w8[i];
+                w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+              }
+              const bool hi4 = lane & 4;
+              {
+                float send = hi4 ? w8[0] : w8[1];
+                float keep = hi4 ? w8[1] : w8[0];
+                w8[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+              }
+              w8[0] += __shfl_xor_sync(0xffffffffu, w8[0], 2);
+              w8[0] += __shfl_xor_sync(0xffffffffu, w8[0], 1);
+              // lane holds column index: bit4 -> +4 (dr half), bit3 -> +2, bit2 -> +1
+              if ((lane & 3) == 0) {
+                const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                const int col = idx & 3;
+                if (gq + col < p.G) atomicAdd(&p.db[(idx >> 2) * p.G + gq + col], w8[0]);
+              }
+            }
           }
         }
-        tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(&acc_empty[as]);
           mbar_arrive(&x_empty[xs]);
-        }
-        const int gbase = g0 + cg * 16;
-        if (PHASE == 2) {
-          if (row_ok) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int g = gbase + j;
-              if (g < p.G) {
-                float s = sv[j] + __ldg(&p.bias[g]);
-                float rho = rv[j] + __ldg(&p.bias[p.G + g]);
-                NbElem e = nb_elem<WITH_A>(s - lse_b, rho, lib_b, xv[j], p.eps);
-                ll_acc += e.ll;
-                if (WITH_A) a_acc += e.a;
-              }
-            }
-          }
-        } else {
-          // backward: ds = -c (a - p A), drho = -c dLL/drho ; bias gradient = column sums
-          float ds[16], dr[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int g = gbase + j;
-            ds[j] = 0.f;
-            dr[j] = 0.f;
-            if (row_ok && g < p.G) {
-              float s = sv[j] + __ldg(&p.bias[g]);
-              float rho = rv[j] + __ldg(&p.bias[p.G + g]);
-              float ls = s - lse_b;
-              NbElem e = nb_elem<true>(ls, rho, lib_b, xv[j], p.eps);
-              ds[j] = rna_tf32(-p.c * (e.a - __expf(ls) * asum_b));
-              dr[j] = rna_tf32(-p.c * e.drho);
-            }
-          }
-          if (row_ok) {
-            float* d0 = p.dlogits + (size_t)b * 2 * p.G + gbase;
-            float* d1 = d0 + p.G;
-            if (gbase + 16 <= p.G) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                reinterpret_cast<float4*>(d0)[j] = make_float4(ds[4 * j], ds[4 * j + 1], ds[4 * j + 2], ds[4 * j + 3]);
-                reinterpret_cast<float4*>(d1)[j] = make_float4(dr[4 * j], dr[4 * j + 1], dr[4 * j + 2], dr[4 * j + 3]);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (gbase + j < p.G) { d0[j] = ds[j]; d1[j] = dr[j]; }
-            }
-          }
-          // column sums over the 32 rows of this warp -> one atomic per column per warp
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float a = warp_sum(ds[j]);
-            float c2 = warp_sum(dr[j]);
-            if (lane == j && gbase + j < p.G) {
-              atomicAdd(&p.db[gbase + j], a);
-              atomicAdd(&p.db[p.G + gbase + j], c2);
-            }
-          }
         }
       }
     }
