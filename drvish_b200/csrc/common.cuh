@@ -112,82 +112,70 @@ static __device__ __noinline__ float2 nb_count_slow(float r, float x, bool bwd) 
   return o;
 }
 
-// NV elements of the NB block per thread.  MUST be called by all 32 lanes of a converged warp
-// (lanes / slots without a valid element pass x = 0 and ignore the result): the count-dependent
-// part is ONE warp-uniform loop shared by the NV independent elements (instruction-level
-// parallelism NV, no per-lane divergence).
+// NV elements of the NB block per thread (straight-line code; the NV independent elements give
+// the instruction-level parallelism).
 //   lsl = library + s - logsumexp(s)  (so ell = lsl - rho),  rho = log_r,  x = count >= 0.
 // Follows torch.distributions.NegativeBinomial.log_prob (negative_binomial.py:130-150):
 //   r logsig(-ell) + x logsig(ell) + lgamma(r+x) - lgamma(1+x) - lgamma(r),   r = e^rho + eps
 // written as  x ell - (x + r) softplus(ell) + [lgamma(r+x) - lgamma(r)] - log(x!).
-// For integer counts below 32 the bracket is the exact finite product log prod_{k<x}(r + k) and
-// psi(r+x) - psi(r) = sum_{k<x} 1/(r+k) = P'/P (at least as accurate as torch's fp32 lgamma /
-// digamma differences, and x = 0 - the majority of scRNA entries - costs nothing); other counts
-// take the generic lgamma / digamma route.  No int<->float conversions (they share the SFU pipe).
+// The bracket and psi(r+x) - psi(r) are formed as DIFFERENCES of shifted Stirling series
+//   lgamma(y) = F(y+4) - log(y(y+1)(y+2)(y+3)),  F(z) = (z-1/2) log z - z + 1/(12z) - 1/(360z^3)
+//   psi(y)    = G(y+4) - Q'(y)/Q(y),             G(z) = log z - 1/(2z) - 1/(12z^2) + 1/(120z^4)
+// (truncation error < 1e-6 for z >= 4; the constant log(2 pi)/2 cancels in the difference), with
+// log(x!) from a 32-entry shared-memory table; x = 0 returns exactly 0.  Counts >= 32 or
+// non-integer take the generic lgamma / digamma route.  No int<->float conversions (they share
+// the SFU pipe with the transcendentals).
 template <bool BWD, int NV>
 __device__ __forceinline__ void nb_elems(const float (&lsl)[NV], const float (&rho)[NV], const float (&x)[NV], float eps,
                                          const float* __restrict__ lgtab, NbElem (&o)[NV]) {
   const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f, MAGIC = 8388608.f;
-  float rexp[NV], r[NV], ell[NV], e[NV], t[NV], sp[NV], xl[NV], lgx[NV];
-  bool fast[NV];
-  float xm = 0.f;
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
-    rexp[v] = ex2_approx(rho[v] * LOG2E);
-    r[v] = rexp[v] + eps;
-    ell[v] = lsl[v] - rho[v];
-    e[v] = ex2_approx(-fabsf(ell[v]) * LOG2E);
-    t[v] = 1.f + e[v];
-    sp[v] = __fmaf_rn(lg2_approx(t[v]), LN2, fmaxf(ell[v], 0.f));  // softplus(ell)
-    const float xr = x[v] + MAGIC;                                  // integer test without F2I/I2F
-    fast[v] = ((xr - MAGIC) == x[v]) && (x[v] < 32.f) && (r[v] < 1.0e4f);
-    xl[v] = fast[v] ? x[v] : 0.f;
-    lgx[v] = lgtab[__float_as_int(xr) & 31];
-    xm = fmaxf(xm, xl[v]);
-  }
-  const float xmax = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(xm)));
-  float lg2sum[NV], psd[NV], P[NV], Pd[NV], tk[NV];
-#pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    lg2sum[v] = 0.f; psd[v] = 0.f; P[v] = 1.f; Pd[v] = 0.f; tk[v] = r[v];
-  }
-  int k8 = 0;
-  for (float kf = 0.f; kf < xmax; kf += 1.f) {  // warp-uniform trip count
-#pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      if (kf < xl[v]) {
-        if (BWD) Pd[v] = __fmaf_rn(Pd[v], tk[v], P[v]);
-        P[v] *= tk[v];
-      }
-      tk[v] += 1.f;
-    }
-    if (++k8 == 8) {  // fold every 8 factors: no overflow for r < 1e4
-      k8 = 0;
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        lg2sum[v] += lg2_approx(P[v]);
-        if (BWD) psd[v] += __fdividef(Pd[v], P[v]);
-        P[v] = 1.f;
-        Pd[v] = 0.f;
-      }
-    }
-  }
-#pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    lg2sum[v] += lg2_approx(P[v]);
-    if (BWD) psd[v] += __fdividef(Pd[v], P[v]);
-    float cnt = __fmaf_rn(lg2sum[v], LN2, -lgx[v]);  // lgamma(r+x) - lgamma(r) - lgamma(1+x)
-    if (!fast[v]) {
-      const float2 sl = nb_count_slow(r[v], x[v], BWD);
-      cnt = sl.x;
-      if (BWD) psd[v] = sl.y;
-    }
-    o[v].ll = __fmaf_rn(x[v], ell[v], cnt) - (x[v] + r[v]) * sp[v];
+    const float rexp = ex2_approx(rho[v] * LOG2E);
+    const float r = rexp + eps;
+    const float ell = lsl[v] - rho[v];
+    const float e = ex2_approx(-fabsf(ell) * LOG2E);
+    const float t = 1.f + e;
+    const float sp = __fmaf_rn(lg2_approx(t), LN2, fmaxf(ell, 0.f));  // softplus(ell)
+    const float xr = x[v] + MAGIC;                                     // integer test without F2I/I2F
+    const bool fast = ((xr - MAGIC) == x[v]) && (x[v] < 32.f) && (r < 1.0e8f);
+    // shifted Stirling at y0 = r + 4 and y1 = r + x + 4
+    const float rx = r + x[v];
+    const float y0 = r + 4.f, y1 = rx + 4.f;
+    const float u0 = r * (r + 3.f), w0 = u0 + 2.f, q0 = u0 * w0;      // r(r+1)(r+2)(r+3)
+    const float u1 = rx * (rx + 3.f), w1 = u1 + 2.f, q1 = u1 * w1;
+    const float i0 = __fdividef(1.f, y0), i1 = __fdividef(1.f, y1);
+    const float l0 = lg2_approx(y0) * LN2, l1 = lg2_approx(y1) * LN2;
+    const float i0s = i0 * i0, i1s = i1 * i1;
+    const float iq0 = __fdividef(1.f, q0);
+    const float c0 = i0 * __fmaf_rn(i0s, -2.7777777778e-3f, 8.3333333333e-2f);
+    const float c1 = i1 * __fmaf_rn(i1s, -2.7777777778e-3f, 8.3333333333e-2f);
+    float lgd = __fmaf_rn(y1 - 0.5f, l1, -(y0 - 0.5f) * l0) - x[v] + (c1 - c0) - lg2_approx(q1 * iq0) * LN2;
+    float cnt = lgd - lgtab[__float_as_int(xr) & 31];
+    float psd = 0.f;
     if (BWD) {
-      const float inv = __fdividef(1.f, t[v]);
-      const float sig = ell[v] >= 0.f ? inv : e[v] * inv;
-      o[v].a = x[v] - (x[v] + r[v]) * sig;
-      o[v].drho = rexp[v] * (psd[v] - sp[v]) - o[v].a;
+      const float iq1 = __fdividef(1.f, q1);
+      const float g0 = l0 - 0.5f * i0 - i0s * __fmaf_rn(i0s, -8.3333333333e-3f, 8.3333333333e-2f);
+      const float g1 = l1 - 0.5f * i1 - i1s * __fmaf_rn(i1s, -8.3333333333e-3f, 8.3333333333e-2f);
+      const float qd0 = (u0 + w0) * __fmaf_rn(2.f, r, 3.f);          // Q'(r)
+      const float qd1 = (u1 + w1) * __fmaf_rn(2.f, rx, 3.f);
+      psd = (g1 - g0) - (qd1 * iq1 - qd0 * iq0);
+    }
+    if (x[v] == 0.f) {
+      cnt = 0.f;
+      psd = 0.f;
+    }
+    if (!fast) {
+      const float2 sl = nb_count_slow(r, x[v], BWD);
+      cnt = sl.x;
+      psd = sl.y;
+    }
+    o[v].ll = __fmaf_rn(x[v], ell, cnt) - rx * sp;
+    if (BWD) {
+      const float inv = __fdividef(1.f, t);
+      const float sig = ell >= 0.f ? inv : e * inv;
+      o[v].a = x[v] - rx * sig;
+      o[v].drho = rexp * (psd - sp) - o[v].a;
     } else {
       o[v].a = 0.f;
       o[v].drho = 0.f;
