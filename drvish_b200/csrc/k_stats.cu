@@ -56,6 +56,66 @@ __global__ void __launch_bounds__(CW* RY) k_colstats(const float* __restrict__ U
   }
 }
 
+// Wide version (D % 4 == 0): 128-bit loads, 4 columns per thread, 2 rows in flight per thread.
+// fp32 partial sums over <= 32 rows are folded into fp64 accumulators.
+template <bool SQRT>
+__global__ void __launch_bounds__(CW* RY) k_colstats4(const float* __restrict__ U, int B, int D, int rows_per_cta,
+                                                       double* __restrict__ acc) {
+  const int col = (blockIdx.x * CW + threadIdx.x) * 4;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(B, r0 + rows_per_cta);
+  double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+  if (col < D) {
+    int r = r0 + threadIdx.y;
+    while (r < r1) {
+      float ps[4] = {0.f, 0.f, 0.f, 0.f}, pss[4] = {0.f, 0.f, 0.f, 0.f};
+      int chunk_end = min(r1, r + 32 * RY);
+      for (; r + RY < chunk_end; r += 2 * RY) {
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(U + (size_t)r * D + col));
+        const float4 b = __ldcs(reinterpret_cast<const float4*>(U + (size_t)(r + RY) * D + col));
+        float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (SQRT) v[j] = sqrtf(v[j]);
+          ps[j & 3] += v[j];
+          pss[j & 3] = __fmaf_rn(v[j], v[j], pss[j & 3]);
+        }
+      }
+      for (; r < chunk_end; r += RY) {
+        const float4 a = *reinterpret_cast<const float4*>(U + (size_t)r * D + col);
+        float v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (SQRT) v[j] = sqrtf(v[j]);
+          ps[j] += v[j];
+          pss[j] = __fmaf_rn(v[j], v[j], pss[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[j] += (double)ps[j];
+        ss[j] += (double)pss[j];
+      }
+    }
+  }
+  __shared__ double sh[2][RY][CW * 4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sh[0][threadIdx.y][threadIdx.x * 4 + j] = s[j];
+    sh[1][threadIdx.y][threadIdx.x * 4 + j] = ss[j];
+  }
+  __syncthreads();
+  const int tid = threadIdx.y * CW + threadIdx.x;
+  const int which = tid / (CW * 4), c = tid % (CW * 4);
+  const int gcol = blockIdx.x * CW * 4 + c;
+  if (gcol < D) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < RY; ++i) t += sh[which][i][c];
+    atomicAdd(&acc[(size_t)which * D + gcol], t);
+  }
+}
+
 __global__ void k_colstats_finalize(const double* __restrict__ acc, int B, int D, float eps, float momentum,
                                     float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ rmean,
                                     float* __restrict__ rvar) {
@@ -137,6 +197,20 @@ __global__ void k_finalize_status(drv_step_out* out) {
 }  // namespace
 
 void colstats_accumulate(const float* U, int B, int D, bool sqrt_in, double* acc, cudaStream_t st) {
+  if (D % 4 == 0 && D >= 512 && ((uintptr_t)U % 16) == 0) {
+    int col_blocks = cdiv(D, CW * 4);
+    int S = cdiv(148 * 8, col_blocks);
+    int max_split = cdiv(B, RY * 4);
+    if (S > max_split) S = max_split;
+    if (S < 1) S = 1;
+    int rows = cdiv(cdiv(B, S), RY) * RY;
+    S = cdiv(B, rows);
+    dim3 grid(col_blocks, S), block(CW, RY);
+    if (sqrt_in) k_colstats4<true><<<grid, block, 0, st>>>(U, B, D, rows, acc);
+    else k_colstats4<false><<<grid, block, 0, st>>>(U, B, D, rows, acc);
+    note_launch();
+    return;
+  }
   int S = row_splits(B, D);
   int rows = cdiv(B, S);
   rows = cdiv(rows, RY) * RY;

@@ -165,6 +165,14 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
     const int cg = warp / 4;   // column group
     const int r = q * 32 + lane;
     float ll_acc = 0.f, a_acc = 0.f;
+    float m_run = -INFINITY, s_run = 0.f;  // phase 1: online (max, sum exp) over this CTA's tiles of a cell tile
+    auto flush_lse = [&](int ct_done, int row) {
+      // slot = ordinal of this CTA among the CTAs whose tile range overlaps the cell tile
+      const int first_cta = (int)((((long long)ct_done * n_gt + 1) * gridDim.x - 1) / n_tiles);
+      const size_t slot = (size_t)((blockIdx.x - first_cta) * 4 + cg) * p.B + row;
+      p.part_m[slot] = m_run;
+      p.part_s[slot] = s_run;
+    };
     int cur_ct = -1;
     float lib_b = 0.f, lse_b = 0.f, asum_b = 0.f;
     int b = 0;
@@ -177,7 +185,10 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
           atomicAdd(&p.ll[b], ll_acc);
           if (WITH_A) atomicAdd(&p.asum[b], a_acc);
         }
+        if (PHASE == 1 && cur_ct >= 0 && row_ok) flush_lse(cur_ct, b);
         ll_acc = a_acc = 0.f;
+        m_run = -INFINITY;
+        s_run = 0.f;
         cur_ct = ct;
         b = ct * BM + r;
         row_ok = b < p.B;
@@ -214,10 +225,10 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
 #pragma unroll
           for (int j = 0; j < 16; ++j) s += __expf(v0[j] - m) + __expf(v1[j] - m);
         }
-        if (row_ok) {
-          const size_t slot = (size_t)(gt * 4 + cg) * p.B + b;
-          p.part_m[slot] = m;
-          p.part_s[slot] = s;
+        if (m > -INFINITY) {
+          const float M = fmaxf(m_run, m);
+          s_run = s_run * __expf(m_run - M) + s * __expf(m - M);
+          m_run = M;
         }
       } else {
         // phases 2/3: this warp owns 16 genes of the 64-gene tile, processed as a ROLLED loop
@@ -342,6 +353,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
       atomicAdd(&p.ll[b], ll_acc);
       if (WITH_A) atomicAdd(&p.asum[b], a_acc);
     }
+    if (PHASE == 1 && cur_ct >= 0 && row_ok) flush_lse(cur_ct, b);
   }
   tc_fence_before();
   __syncthreads();
@@ -365,10 +377,14 @@ __global__ void k_round_tf32(const float* __restrict__ src, size_t n, float* __r
     dst[i] = rna_tf32(src[i]);
 }
 
-__global__ void k_lse_combine(const float* __restrict__ pm, const float* __restrict__ ps, int n_slots, int B,
-                              float* __restrict__ lse) {
+__global__ void k_lse_combine(const float* __restrict__ pm, const float* __restrict__ ps, int n_gt, int n_tiles, int grid,
+                              int B, float* __restrict__ lse) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
+  const int ct = b / BM;
+  const int first_cta = (int)((((long long)ct * n_gt + 1) * grid - 1) / n_tiles);
+  const int last_cta = (int)((((long long)ct * n_gt + n_gt) * grid - 1) / n_tiles);
+  const int n_slots = (last_cta - first_cta + 1) * 4;
   float m = -INFINITY;
   for (int s = 0; s < n_slots; ++s) m = fmaxf(m, pm[(size_t)s * B + b]);
   float acc = 0.f;
@@ -496,7 +512,11 @@ void tc_decoder_forward(const TcDecoderArgs& a, cudaStream_t st) {
   // phase 1: logsumexp over genes
   const int n_gt1 = (a.G + 127) / 128;
   launch_dec(k_dec<1, false>, n_ct * n_gt1, tAct, tW1, tX, p, st);
-  k_lse_combine<<<(a.B + 127) / 128, 128, 0, st>>>(s.part_m, s.part_s, n_gt1 * 4, a.B, a.lse);
+  {
+    const int n_tiles1 = n_ct * n_gt1;
+    const int grid1 = n_tiles1 < sm_count() ? n_tiles1 : sm_count();
+    k_lse_combine<<<(a.B + 63) / 64, 64, 0, st>>>(s.part_m, s.part_s, n_gt1, n_tiles1, grid1, a.B, a.lse);
+  }
   note_launch();
   // phase 2: NB log-likelihood row sums
   cudaMemsetAsync(a.ll, 0, sizeof(float) * a.B, st);

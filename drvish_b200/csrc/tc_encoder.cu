@@ -55,50 +55,87 @@ __global__ void k_round_rows(const float* __restrict__ src, size_t n, float* __r
     dst[i] = rna_tf32(src[i]);
 }
 
-__global__ void k_colsum_small(const float* __restrict__ V, int B, int D, float* __restrict__ out) {
-  // one CTA per 32 columns, 8 row lanes
+__global__ void k_colsum_small(const float* __restrict__ V, int B, int D, int rows_per_cta, float* __restrict__ out) {
+  // 32 columns x 8 row lanes per CTA, the batch split over gridDim.y; out must be zeroed
   int col = blockIdx.x * 32 + threadIdx.x;
+  int r0 = blockIdx.y * rows_per_cta, r1 = min(B, r0 + rows_per_cta);
   float s = 0.f;
   if (col < D)
-    for (int r = threadIdx.y; r < B; r += 8) s += V[(size_t)r * D + col];
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) s += V[(size_t)r * D + col];
   __shared__ float sh[8][32];
   sh[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && col < D) {
     float t = 0.f;
     for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
-    out[col] = t;
+    atomicAdd(&out[col], t);
   }
 }
 
 // gacc[0][g] += sum_b dA*gate ; gacc[1][g] += sum_b dA*gate*xhat   (gate, xhat recomputed from x)
+// HBM-bound (reads dA and x once): 128-bit loads, 4 columns per thread, 4 rows in flight.
 constexpr int CW = 32, RY = 8;
 __global__ void __launch_bounds__(CW* RY) k_bn0_grad(const float* __restrict__ dA, const float* __restrict__ x, int B,
                                                       int G, int rows_per_cta, BnParams bn, double* __restrict__ acc) {
-  int col = blockIdx.x * CW + threadIdx.x;
-  int r0 = blockIdx.y * rows_per_cta;
-  int r1 = min(B, r0 + rows_per_cta);
-  float s1 = 0.f, s2 = 0.f;
-  if (col < G) {
-    float mean = bn.mean[col], rstd = bn.rstd[col], g = bn.gamma[col], be = bn.beta[col];
-    for (int r = r0 + threadIdx.y; r < r1; r += RY) {
-      float xh = bn_xhat(sqrtf(x[(size_t)r * G + col]), mean, rstd);
-      if (bn_y(xh, g, be) > 0.f) {
-        float d = dA[(size_t)r * G + col];
-        s1 += d;
-        s2 = __fmaf_rn(d, xh, s2);
+  const int col = (blockIdx.x * CW + threadIdx.x) * 4;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(B, r0 + rows_per_cta);
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  if (col < G) {  // G % 4 == 0
+    const float4 mean = *reinterpret_cast<const float4*>(bn.mean + col);
+    const float4 rstd = *reinterpret_cast<const float4*>(bn.rstd + col);
+    const float4 gam = *reinterpret_cast<const float4*>(bn.gamma + col);
+    const float4 bet = *reinterpret_cast<const float4*>(bn.beta + col);
+    const float mv[4] = {mean.x, mean.y, mean.z, mean.w}, rv[4] = {rstd.x, rstd.y, rstd.z, rstd.w};
+    const float gv[4] = {gam.x, gam.y, gam.z, gam.w}, bv[4] = {bet.x, bet.y, bet.z, bet.w};
+    int r = r0 + threadIdx.y;
+    for (; r + RY < r1; r += 2 * RY) {
+      const float4 xa = __ldcs(reinterpret_cast<const float4*>(x + (size_t)r * G + col));
+      const float4 xb = __ldcs(reinterpret_cast<const float4*>(x + (size_t)(r + RY) * G + col));
+      const float4 da = __ldcs(reinterpret_cast<const float4*>(dA + (size_t)r * G + col));
+      const float4 db = __ldcs(reinterpret_cast<const float4*>(dA + (size_t)(r + RY) * G + col));
+      const float xs[2][4] = {{xa.x, xa.y, xa.z, xa.w}, {xb.x, xb.y, xb.z, xb.w}};
+      const float ds[2][4] = {{da.x, da.y, da.z, da.w}, {db.x, db.y, db.z, db.w}};
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float xh = bn_xhat(sqrtf(xs[u][j]), mv[j], rv[j]);
+          if (bn_y(xh, gv[j], bv[j]) > 0.f) {
+            s1[j] += ds[u][j];
+            s2[j] = __fmaf_rn(ds[u][j], xh, s2[j]);
+          }
+        }
+    }
+    for (; r < r1; r += RY) {
+      const float4 xa = *reinterpret_cast<const float4*>(x + (size_t)r * G + col);
+      const float4 da = *reinterpret_cast<const float4*>(dA + (size_t)r * G + col);
+      const float xs[4] = {xa.x, xa.y, xa.z, xa.w}, ds[4] = {da.x, da.y, da.z, da.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xh = bn_xhat(sqrtf(xs[j]), mv[j], rv[j]);
+        if (bn_y(xh, gv[j], bv[j]) > 0.f) {
+          s1[j] += ds[j];
+          s2[j] = __fmaf_rn(ds[j], xh, s2[j]);
+        }
       }
     }
   }
-  __shared__ float sh[2][RY][CW];
-  sh[0][threadIdx.y][threadIdx.x] = s1;
-  sh[1][threadIdx.y][threadIdx.x] = s2;
+  __shared__ float sh[2][RY][CW * 4 + 4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sh[0][threadIdx.y][threadIdx.x * 4 + j] = s1[j];
+    sh[1][threadIdx.y][threadIdx.x * 4 + j] = s2[j];
+  }
   __syncthreads();
-  if (threadIdx.y < 2 && col < G) {
+  const int tid = threadIdx.y * CW + threadIdx.x;  // 256 threads: 2 x 128 columns
+  const int which = tid / (CW * 4), c = tid % (CW * 4);
+  const int gcol = blockIdx.x * CW * 4 + c;
+  if (gcol < G) {
     double t = 0.0;
 #pragma unroll
-    for (int i = 0; i < RY; ++i) t += (double)sh[threadIdx.y][i][threadIdx.x];
-    atomicAdd(&acc[(size_t)threadIdx.y * G + col], t);
+    for (int i = 0; i < RY; ++i) t += (double)sh[which][i][c];
+    atomicAdd(&acc[(size_t)which * G + gcol], t);
   }
 }
 
@@ -168,9 +205,14 @@ void tc_encoder_backward(const TcEncoderArgs& a, cudaStream_t st) {
   // tf32 operands are rounded to nearest when produced (the MMA truncates)
   k_round_rows<<<n_sm() * 2, 256, 0, st>>>(a.dH, (size_t)a.B * a.h, s.dh_r);
   note_launch();
-  dim3 cb(32, 8);
-  k_colsum_small<<<(a.h + 31) / 32, cb, 0, st>>>(a.dH, a.B, a.h, a.db);
-  note_launch();
+  {
+    dim3 cb(32, 8);
+    int rows = 64;
+    dim3 cgrid((a.h + 31) / 32, (a.B + rows - 1) / rows);
+    cudaMemsetAsync(a.db, 0, sizeof(float) * a.h, st);
+    k_colsum_small<<<cgrid, cb, 0, st>>>(a.dH, a.B, a.h, rows, a.db);
+    note_launch();
+  }
   // dW[j][g] = sum_b dH[b][j] A[b][g]: both operands MN-major (K = cells), split-K + atomics
   cudaMemsetAsync(a.dW, 0, sizeof(float) * (size_t)a.h * a.G, st);
   int m_tiles = (a.h + 127) / 128, n_tiles = (a.G + 255) / 256;
@@ -182,8 +224,8 @@ void tc_encoder_backward(const TcEncoderArgs& a, cudaStream_t st) {
   if (rc == 0) rc = tc::gemm_tf32(s.dh_r, a.h, false, s.w_hi, a.G, true, dA, a.G, a.B, a.G, a.h, 1, false, st);
   if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
   // reduce dA to the input-BatchNorm gradients
-  int col_blocks = (a.G + CW - 1) / CW;
-  int S = (n_sm() * 4 + col_blocks - 1) / col_blocks;
+  int col_blocks = (a.G + CW * 4 - 1) / (CW * 4);
+  int S = (n_sm() * 8 + col_blocks - 1) / col_blocks;
   int max_split = (a.B + RY * 4 - 1) / (RY * 4);
   if (S > max_split) S = max_split;
   if (S < 1) S = 1;
