@@ -189,6 +189,7 @@ def run_native(args, cfg):
 
     import drvish_b200 as D
     from drvish_b200 import _lib
+    from drvish_b200.parallel import allreduce_grads_and_loss
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -228,8 +229,7 @@ def run_native(args, cfg):
         rt.elbo_step(xs[i % n_batches], labels, yflat, noise, True, elbo.flags, True)
         elbo.step_index += 1
         if world > 1:
-            rt.flat_grads[rt.n_param_floats] = rt._out[0].to(torch.float32)
-            dist.all_reduce(rt.flat_grads, op=dist.ReduceOp.SUM)
+            allreduce_grads_and_loss(rt.flat_grads, rt.n_param_floats, rt._out[0])
 
     for i in range(args.warmup):
         device_step(i)

@@ -21,6 +21,7 @@ import torch
 
 from . import _lib
 from .models import HAVE_PYRO, NBVAE
+from .parallel import allreduce_grads_and_loss
 
 if HAVE_PYRO:  # pragma: no cover
     import pyro
@@ -145,8 +146,7 @@ class FusedTraceELBO:
         self.step_index += 1
         if want_grads and self._dp_enabled():
             # one all-reduce: gradients + the loss in the tail slot
-            rt.flat_grads[rt.n_param_floats] = rt._out[0].to(torch.float32)
-            torch.distributed.all_reduce(rt.flat_grads, op=torch.distributed.ReduceOp.SUM, group=self.process_group)
+            allreduce_grads_and_loss(rt.flat_grads, rt.n_param_floats, rt._out[0], self.process_group)
         loss, status = rt.read_out()
         self.last_status = status
         if status & (_lib.DRV_STATUS_MISSING_CLASS | _lib.DRV_STATUS_BAD_LABEL):

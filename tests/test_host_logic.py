@@ -1,0 +1,114 @@
+"""CPU tests of the host side: drop-in module surface (constructor keywords, attributes,
+state_dict keys as in reference nbvae.py / drnbvae.py / modules.py), loud failure without CUDA,
+and the data-parallel reduction under a world_size-2 gloo group."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import drvish_b200 as D
+from oracle import drvish_oracle as O
+
+
+def test_constructor_surface_and_state_dict_keys_match_reference():
+    m = D.DRNBVAE(n_input=40, n_classes=3, n_drugs=2, n_conditions=[4, 5], n_latent=6, layers=[16, 8],
+                  lib_loc=7.0, lib_scale=0.4, lam_scale=2.0, bias_scale=3.0, sigma_scale=0.7, scale_factor=0.5,
+                  epsilon=1e-5)
+    o = O.OracleDRNBVAE(n_input=40, n_classes=3, n_drugs=2, n_conditions=[4, 5], n_latent=6, layers=[16, 8])
+    assert list(m.state_dict().keys()) == list(o.state_dict().keys())
+    for attr in ("encoder", "decoder", "lmb_list", "epsilon", "l_loc", "l_scale", "sigma_scale", "n_latent",
+                 "n_classes", "scale_factor", "model", "guide"):
+        assert hasattr(m, attr), attr
+    assert float(m.l_loc) == 7.0 and float(m.l_scale) == pytest.approx(0.4) and float(m.epsilon) == pytest.approx(1e-5)
+    # decoder gets the reversed layers (reference nbvae.py:42)
+    assert m.decoder.fc[2].out_features == 8 and m.decoder.fc[5].out_features == 16
+    assert m.encoder.fc[2].out_features == 16 and m.encoder.fc[8].out_features == 2 * 6 + 2
+    n = D.NBVAE(n_input=40)
+    assert [n.encoder.fc[i].out_features for i in (2, 5, 8)] == [64, 64, 64] and n.n_latent == 8
+    with pytest.raises(TypeError):
+        D.NBVAE(40)  # keyword-only, like the reference
+
+
+@pytest.mark.skipif(not os.path.exists(O.REFERENCE_MODULES_PY), reason="reference not mounted")
+def test_state_dict_interchange_with_reference_modules():
+    ref = O.load_reference_modules()
+    r_enc, r_dec = ref.Encoder(30, 4, [12, 10]), ref.NBDecoder(4, 30, [10, 12])
+    m = D.NBVAE(n_input=30, n_latent=4, layers=[12, 10])
+    m.encoder.load_state_dict(r_enc.state_dict())
+    m.decoder.load_state_dict(r_dec.state_dict())
+    assert torch.equal(m.encoder.fc[2].weight, r_enc.fc[2].weight)
+
+
+def test_no_cpu_fallback():
+    m = D.NBVAE(n_input=20, n_latent=3, layers=[8, 8])
+    elbo = D.FusedTraceELBO()
+    x = torch.poisson(torch.rand(16, 20) * 3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        elbo.loss_and_grads(m.model, m.guide, x)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.encoder(x)
+    with pytest.raises(NotImplementedError):
+        D.Encoder(20, 3, [8])(x)  # stand-alone sub-module: no owner
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from drvish_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _dp_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from drvish_b200.parallel import allreduce_grads_and_loss, shard_rows
+
+    cfg = dict(n_input=40, n_latent=3, layers=[16, 16], batch=32, drugs=0)
+    model = O.build_model(cfg).double()
+    x = O.synthetic_counts(32, 40, seed=11).double()
+    noise = {k: v.double() for k, v in O.make_noise(model, 32).items()}
+    sl = shard_rows(32, rank, world)
+    loss, grads, _ = O.step(model, x[sl], {k: v[sl] for k, v in noise.items()})
+    names = list(grads)
+    n = sum(g.numel() for g in grads.values())
+    flat = torch.zeros(n + 32, dtype=torch.float64)
+    flat[:n] = torch.cat([grads[k].reshape(-1) for k in names])
+    allreduce_grads_and_loss(flat, n, torch.tensor(loss, dtype=torch.float64))
+    torch.save({"flat": flat, "n": n, "names": names}, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_allreduce_is_sum_over_shards(tmp_path):
+    """R-rank result == sum_r oracle(shard_r), loss in the tail slot, ONE collective."""
+    world, port = 2, _free_port()
+    mp.spawn(_dp_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r0 = torch.load(os.path.join(tmp_path, "r0.pt"))
+    r1 = torch.load(os.path.join(tmp_path, "r1.pt"))
+    assert torch.equal(r0["flat"], r1["flat"])  # replicas agree after the all-reduce
+    cfg = dict(n_input=40, n_latent=3, layers=[16, 16], batch=32, drugs=0)
+    model = O.build_model(cfg).double()
+    x = O.synthetic_counts(32, 40, seed=11).double()
+    noise = {k: v.double() for k, v in O.make_noise(model, 32).items()}
+    tot_loss, tot = 0.0, None
+    for r in range(world):
+        sl = slice(16 * r, 16 * (r + 1))
+        loss, grads, _ = O.step(model, x[sl], {k: v[sl] for k, v in noise.items()})
+        g = torch.cat([grads[k].reshape(-1) for k in r0["names"]])
+        tot = g if tot is None else tot + g
+        tot_loss += loss
+    n = r0["n"]
+    torch.testing.assert_close(r0["flat"][:n], tot, rtol=1e-12, atol=1e-12)
+    assert abs(float(r0["flat"][n]) - tot_loss) <= 1e-9 * abs(tot_loss)
