@@ -33,9 +33,9 @@ void tc_decoder_backward(const TcDecoderArgs& a, cudaStream_t st);  // dW, db, d
 namespace drv {
 namespace tc {
 int gemm_tf32(const float* A, int lda, bool a_mn, const float* Bm, int ldb, bool b_mn, float* C, int ldc, int M, int N,
-              int K, int splits, bool accumulate_atomic, cudaStream_t st);
+              int K, int max_ctas, bool accumulate, cudaStream_t st);
 int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs, int lda, bool a_mn, int ldb, bool b_mn,
-                    float* C, int ldc, int M, int N, int K, int splits, bool accumulate_atomic, const float* bias,
+                    float* C, int ldc, int M, int N, int K, int max_ctas, bool accumulate, const float* bias,
                     cudaStream_t st);
 }
 

@@ -190,13 +190,9 @@ void tc_encoder_forward(const TcEncoderArgs& a, cudaStream_t st) {
   note_launch();
   k_split_tf32<<<n_sm() * 4, 256, 0, st>>>(a.W, (size_t)a.h * a.G, s.w_hi, s.w_lo);
   note_launch();
-  cudaMemsetAsync(a.H, 0, sizeof(float) * (size_t)a.B * a.h, st);
   const float* As[3] = {s.a_lo, s.a_hi, s.a_hi};
   const float* Bs[3] = {s.w_hi, s.w_lo, s.w_hi};
-  int m_tiles = (a.B + 127) / 128, n_tiles = (a.h + 255) / 256;
-  int splits = n_sm() / (m_tiles * n_tiles);
-  if (splits < 1) splits = 1;
-  int rc = tc::gemm_tf32_multi(3, As, Bs, a.G, false, a.G, false, a.H, a.h, a.B, a.h, a.G, splits, true, a.bias, st);
+  int rc = tc::gemm_tf32_multi(3, As, Bs, a.G, false, a.G, false, a.H, a.h, a.B, a.h, a.G, 0, false, a.bias, st);
   if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
 }
 
@@ -213,15 +209,11 @@ void tc_encoder_backward(const TcEncoderArgs& a, cudaStream_t st) {
     k_colsum_small<<<cgrid, cb, 0, st>>>(a.dH, a.B, a.h, rows, a.db);
     note_launch();
   }
-  // dW[j][g] = sum_b dH[b][j] A[b][g]: both operands MN-major (K = cells), split-K + atomics
-  cudaMemsetAsync(a.dW, 0, sizeof(float) * (size_t)a.h * a.G, st);
-  int m_tiles = (a.h + 127) / 128, n_tiles = (a.G + 255) / 256;
-  int splits = n_sm() / (m_tiles * n_tiles);
-  if (splits < 1) splits = 1;
-  int rc = tc::gemm_tf32(s.dh_r, a.h, true, s.a_hi, a.G, true, a.dW, a.G, a.h, a.G, a.B, splits, true, st);
+  // dW[j][g] = sum_b dH[b][j] A[b][g]: both operands MN-major (K = cells)
+  int rc = tc::gemm_tf32(s.dh_r, a.h, true, s.a_hi, a.G, true, a.dW, a.G, a.h, a.G, a.B, 0, false, st);
   // dA[b][g] = sum_j dH[b][j] W[j][g]: A K-major, B MN-major (K = h); dA reuses the A_lo buffer
   float* dA = s.a_lo;
-  if (rc == 0) rc = tc::gemm_tf32(s.dh_r, a.h, false, s.w_hi, a.G, true, dA, a.G, a.B, a.G, a.h, 1, false, st);
+  if (rc == 0) rc = tc::gemm_tf32(s.dh_r, a.h, false, s.w_hi, a.G, true, dA, a.G, a.B, a.G, a.h, 0, false, st);
   if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
   // reduce dA to the input-BatchNorm gradients
   int col_blocks = (a.G + CW * 4 - 1) / (CW * 4);

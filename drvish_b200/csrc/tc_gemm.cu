@@ -54,28 +54,37 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int NTHREADS = 192;
 
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Persistent stream-K kernel: the (tile, k-block) units are dealt out evenly to the CTAs (one per
+// SM); a CTA walks its contiguous unit range as <= a few (tile, k-range) segments.  A segment that
+// covers a whole tile stores it, partial segments are combined with red.global.add into a zeroed C.
+// Two TMEM accumulator stages overlap the epilogue of a segment with the MMAs of the next one.
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
           const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, int n_pairs,
-          float* __restrict__ C, int ldc, int M, int N, int K, int kb_per_split, int n_tile, int use_atomic,
+          float* __restrict__ C, int ldc, int M, int N, int K, int n_tile, int force_atomic,
           const float* __restrict__ bias, int mn_lbo, int mn_sbo, int mn_kstep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
   uint64_t* empty = full + STAGES;
-  uint64_t* acc_full = empty + STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
+  uint64_t* acc_full = empty + STAGES;   // [2]
+  uint64_t* acc_empty = acc_full + 2;    // [2]
+  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * n_tile;
   // the operand pairs are concatenated along a virtual K axis: sum_p A_p B_p^T accumulates in TMEM
   const int kb_pair = (K + BK - 1) / BK;
   const int kb_total = kb_pair * n_pairs;
-  const int kb0 = blockIdx.z * kb_per_split;
-  const int kb1 = min(kb_total, kb0 + kb_per_split);
-  const int nkb = kb1 - kb0;
+  const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + n_tile - 1) / n_tile;
+  const long long units = (long long)m_tiles * n_tiles * kb_total;
+  const long long u_begin = units * blockIdx.x / gridDim.x;
+  const long long u_end = units * (blockIdx.x + 1) / gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -84,10 +93,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(acc_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<MAXN>(tmem_slot);
+  if (warp == 1) tmem_alloc<2 * MAXN>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -95,91 +107,145 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0 && nkb > 0) {
+    if (lane == 0) {
       const uint32_t tx = A_BYTES + (uint32_t)n_tile * BK * 4;
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES, ph = (i / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        uint8_t* sa = smem + s * STAGE_BYTES;
-        uint8_t* sb = sa + A_BYTES;
-        mbar_expect_tx(&full[s], tx);
-        const int pair = (kb0 + i) / kb_pair;
-        const int k0 = ((kb0 + i) - pair * kb_pair) * BK;
-        const CUtensorMap* ma = pair == 0 ? &tmA : (pair == 1 ? &tmA1 : &tmA2);
-        const CUtensorMap* mb = pair == 0 ? &tmB : (pair == 1 ? &tmB1 : &tmB2);
-        if (A_MN) {
-          for (int j = 0; j < BM / 32; ++j) tma_load_2d(sa + j * 4096, ma, &full[s], m0 + 32 * j, k0);
-        } else {
-          tma_load_2d(sa, ma, &full[s], k0, m0);
+      int i = 0;
+      for (long long u = u_begin; u < u_end;) {
+        const int tile = (int)(u / kb_total), kb_b = (int)(u % kb_total);
+        const int kb_e = (int)min((long long)kb_total, kb_b + (u_end - u));
+        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * n_tile;
+        for (int kb = kb_b; kb < kb_e; ++kb, ++i) {
+          const int s = i % STAGES, ph = (i / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_expect_tx(&full[s], tx);
+          const int pair = kb / kb_pair;
+          const int k0 = (kb - pair * kb_pair) * BK;
+          const CUtensorMap* ma = pair == 0 ? &tmA : (pair == 1 ? &tmA1 : &tmA2);
+          const CUtensorMap* mb = pair == 0 ? &tmB : (pair == 1 ? &tmB1 : &tmB2);
+          if (A_MN) {
+            for (int j = 0; j < BM / 32; ++j) tma_load_2d(sa + j * 4096, ma, &full[s], m0 + 32 * j, k0);
+          } else {
+            tma_load_2d(sa, ma, &full[s], k0, m0);
+          }
+          if (B_MN) {
+            for (int j = 0; j < n_tile / 32; ++j) tma_load_2d(sb + j * 4096, mb, &full[s], n0 + 32 * j, k0);
+          } else {
+            tma_load_2d(sb, mb, &full[s], k0, n0);
+          }
         }
-        if (B_MN) {
-          for (int j = 0; j < n_tile / 32; ++j) tma_load_2d(sb + j * 4096, mb, &full[s], n0 + 32 * j, k0);
-        } else {
-          tma_load_2d(sb, mb, &full[s], k0, n0);
-        }
+        u += kb_e - kb_b;
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
-    if (lane == 0 && nkb > 0) {
+    if (lane == 0) {
       const uint32_t idesc = idesc_tf32(BM, n_tile, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES, ph = (i / STAGES) & 1;
-        mbar_wait(&full[s], ph);
+      int i = 0, seg = 0;
+      for (long long u = u_begin; u < u_end; ++seg) {
+        const int kb_b = (int)(u % kb_total);
+        const int kb_e = (int)min((long long)kb_total, kb_b + (u_end - u));
+        const int as = seg & 1, aph = (seg >> 1) & 1;
+        mbar_wait(&acc_empty[as], aph ^ 1);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t sb = sa + A_BYTES;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * MAXN);
+        for (int kb = kb_b; kb < kb_e; ++kb, ++i) {
+          const int s = i % STAGES, ph = (i / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < BK / 8; ++kk) {
-          const uint64_t da = A_MN ? smem_desc(sa + kk * mn_kstep, mn_lbo, mn_sbo, 1) : smem_desc(sa + kk * 32, 16, 1024);
-          const uint64_t db = B_MN ? smem_desc(sb + kk * mn_kstep, mn_lbo, mn_sbo, 1) : smem_desc(sb + kk * 32, 16, 1024);
-          umma_tf32(tmem_base, da, db, idesc, (i | kk) != 0);
+          for (int kk = 0; kk < BK / 8; ++kk) {
+            const uint64_t da = A_MN ? smem_desc(sa + kk * mn_kstep, mn_lbo, mn_sbo, 1) : smem_desc(sa + kk * 32, 16, 1024);
+            const uint64_t db = B_MN ? smem_desc(sb + kk * mn_kstep, mn_lbo, mn_sbo, 1) : smem_desc(sb + kk * 32, 16, 1024);
+            umma_tf32(d_tmem, da, db, idesc, (kb != kb_b) || (kk != 0));
+          }
+          umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
         }
-        umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+        umma_commit(&acc_full[as]);
+        u += kb_e - kb_b;
       }
-      umma_commit(acc_full);
     }
   } else {
     // ===== epilogue: TMEM -> registers -> global =====
     const int q = warp % 4;  // TMEM lane quarter this warp may access
-    const int m = m0 + q * 32 + lane;
-    if (nkb > 0) {
-      mbar_wait(acc_full, 0);
+    int seg = 0;
+    for (long long u = u_begin; u < u_end; ++seg) {
+      const int tile = (int)(u / kb_total), kb_b = (int)(u % kb_total);
+      const int kb_e = (int)min((long long)kb_total, kb_b + (u_end - u));
+      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * n_tile;
+      const bool whole = (kb_b == 0 && kb_e == kb_total) && !force_atomic;
+      const bool add_bias = bias != nullptr && kb_b == 0;
+      const int as = seg & 1, aph = (seg >> 1) & 1;
+      const int m = m0 + q * 32 + lane;
+      mbar_wait(&acc_full[as], aph);
       tc_fence_after();
+      const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * MAXN);
       for (int c = 0; c < n_tile; c += 16) {
         float v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+        tmem_ld16(tb + (uint32_t)c, v);
         tmem_ld_wait();
         if (m < M) {
           float* dst = C + (size_t)m * ldc + n0 + c;
+          if (add_bias) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (n0 + c + j < N) {
-              float o = v[j];
-              if (bias != nullptr && blockIdx.z == 0) o += __ldg(&bias[n0 + c + j]);
-              if (use_atomic) atomicAdd(dst + j, o);
-              else dst[j] = o;
+            for (int j = 0; j < 16; ++j)
+              if (n0 + c + j < N) v[j] += __ldg(&bias[n0 + c + j]);
+          }
+          const bool vec_ok = (n0 + c + 16 <= N) && ((((uintptr_t)dst) & 15) == 0);
+          if (vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              if (whole) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              else red_add_v4(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (n0 + c + j < N) {
+                if (whole) dst[j] = v[j];
+                else atomicAdd(dst + j, v[j]);
+              }
             }
           }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      u += kb_e - kb_b;
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<MAXN>(tmem_base);
+    tmem_dealloc<2 * MAXN>(tmem_base);
   }
 }
 
 }  // namespace
 
+static int n_sm_tc() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 // A: K-major [M][K] (lda = row stride in elements) or MN-major [K][M]; same for B.
 // Requirements: row strides multiples of 4 floats, bases 16-byte aligned, N tile multiple of 16
 // (32 for an MN-major B).  n_pairs operand pairs (same shapes/strides) are summed: C = sum_p A_p B_p^T.
+// accumulate: add into the existing contents of C; otherwise C is overwritten (it is zeroed here
+// first when stream-K splits a tile over several CTAs).  max_ctas <= 0: one CTA per SM.
 int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs, int lda, bool a_mn, int ldb, bool b_mn,
-                    float* C, int ldc, int M, int N, int K, int splits, bool accumulate_atomic, const float* bias,
+                    float* C, int ldc, int M, int N, int K, int max_ctas, bool accumulate, const float* bias,
                     cudaStream_t st) {
   if (n_pairs < 1 || n_pairs > 3) return -3;
   CUtensorMap ta[3], tb[3];
@@ -195,17 +261,24 @@ int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs,
     else ok = tmap_2d(&tb[p], Bs[q], (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)n_tile, BK);
     if (!ok) return -3;
   }
-  int kb_total = ((K + BK - 1) / BK) * n_pairs;
-  if (splits < 1) splits = 1;
-  if (splits > kb_total) splits = kb_total;
-  int kps = (kb_total + splits - 1) / splits;
-  splits = (kb_total + kps - 1) / kps;
-  dim3 grid((M + BM - 1) / BM, (N + n_tile - 1) / n_tile, splits);
-  int atomic = (splits > 1 || accumulate_atomic) ? 1 : 0;
+  const long long kb_total = (long long)((K + BK - 1) / BK) * n_pairs;
+  const long long tiles = (long long)((M + BM - 1) / BM) * ((N + n_tile - 1) / n_tile);
+  const long long units = tiles * kb_total;
+  int grid = max_ctas > 0 ? max_ctas : n_sm_tc();
+  if (grid > n_sm_tc()) grid = n_sm_tc();
+  if ((long long)grid > units) grid = (int)units;
+  // tiles are split across CTAs unless every CTA boundary falls on a tile boundary
+  bool split = false;
+  for (int c = 1; c < grid && !split; ++c) split = ((units * c / grid) % kb_total) != 0;
+  if (split && !accumulate) {
+    if (ldc == N) cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st);
+    else cudaMemset2DAsync(C, sizeof(float) * (size_t)ldc, 0, sizeof(float) * (size_t)N, (size_t)M, st);
+  }
+  const int force_atomic = (split || accumulate) ? 1 : 0;
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(ta[0], tb[0], ta[1], tb[1], ta[2], tb[2], n_pairs, C, ldc, M, N, K, kps,
-                                             n_tile, atomic, bias, g_mn_lbo, g_mn_sbo, g_mn_kstep);
+    kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(ta[0], tb[0], ta[1], tb[1], ta[2], tb[2], n_pairs, C, ldc, M, N, K, n_tile,
+                                             force_atomic, bias, g_mn_lbo, g_mn_sbo, g_mn_kstep);
   };
   if (a_mn && b_mn) launch(k_tc_gemm<true, true>);
   else if (a_mn) launch(k_tc_gemm<true, false>);
@@ -216,8 +289,8 @@ int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs,
 }
 
 int gemm_tf32(const float* A, int lda, bool a_mn, const float* Bm, int ldb, bool b_mn, float* C, int ldc, int M, int N,
-              int K, int splits, bool accumulate_atomic, cudaStream_t st) {
-  return gemm_tf32_multi(1, &A, &Bm, lda, a_mn, ldb, b_mn, C, ldc, M, N, K, splits, accumulate_atomic, nullptr, st);
+              int K, int max_ctas, bool accumulate, cudaStream_t st) {
+  return gemm_tf32_multi(1, &A, &Bm, lda, a_mn, ldb, b_mn, C, ldc, M, N, K, max_ctas, accumulate, nullptr, st);
 }
 
 }  // namespace tc
