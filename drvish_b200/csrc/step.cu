@@ -108,7 +108,8 @@ struct Plan {
   size_t Gb[2][DRV_MAX_LAYERS + 1];         // dY / dU of each block input (B x din), block 0 of enc unused
   size_t z, l, lse, ll, asum, dO;
   size_t u, m, gfac, du, dz_drs;
-  size_t tc, tce;                            // scratch of the tcgen05 decoder / encoder paths
+  size_t tc;                                 // scratch of the fused tcgen05 decoder path
+  size_t tcb[2][DRV_MAX_LAYERS + 1];         // scratch of the tensor-core blocks (0 = block runs on CUDA cores)
   size_t total;
 };
 
@@ -150,9 +151,18 @@ Plan make_plan(const drv_dims& d, const Net& n) {
   p.tc = o;
   o += tc_workspace_bytes(d);
   o = (o + 255) / 256 * 256;
-  p.tce = o;
-  o += tc_encoder_workspace_bytes(d);
-  o = (o + 255) / 256 * 256;
+  for (int s = 0; s < 2; ++s)
+    for (int k = 0; k < n.n_blocks; ++k) {
+      const Block& b = s == 0 ? n.enc[k] : n.dec[k];
+      p.tcb[s][k] = 0;
+      if (s == 1 && k == n.n_blocks - 1) continue;  // fused decoder path
+      drv_hparams hp0{};
+      if (tc_block_forward_supported(d.n_cells, b.din, b.dout, hp0)) {
+        p.tcb[s][k] = o;
+        o += tc_block_workspace_bytes(d.n_cells, b.din, b.dout);
+        o = (o + 255) / 256 * 256;
+      }
+    }
   p.total = o;
   return p;
 }
@@ -187,9 +197,16 @@ void block_forward(const Ctx& c, int s, int k, const float* U0, bool do_linear) 
   colstats_finalize(acc, B, b.din, c.hp.bn_eps, c.hp.bn_momentum, c.at<float>(c.p.mean[s][k]),
                     c.at<float>(c.p.rstd[s][k]), update ? c.bnbuf + b.rmean : nullptr,
                     update ? c.bnbuf + b.rvar : nullptr, c.st);
-  if (do_linear)
+  if (!do_linear) return;
+  if (c.p.tcb[s][k] && tc_block_forward_supported(B, b.din, b.dout, c.hp)) {
+    TcBlockArgs a{};
+    a.U = U; a.sqrt_in = sq; a.bn = c.bn(s, k); a.W = c.params + b.W; a.bias = c.params + b.bias;
+    a.B = B; a.din = b.din; a.dout = b.dout; a.V = c.at<float>(c.p.V[s][k]); a.scratch = c.ws + c.p.tcb[s][k];
+    tc_block_forward(a, c.st);
+  } else {
     simt_linear_forward(U, B, b.din, sq ? 2 : 1, c.bn(s, k), c.params + b.W, c.params + b.bias, b.dout,
                         c.at<float>(c.p.V[s][k]), c.st);
+  }
 }
 
 // Backward of block k given dV of its Linear: dW, db, then dY = (dV W) * relu-gate, then the
@@ -204,11 +221,20 @@ void block_backward(const Ctx& c, int s, int k, const float* U0, const float* dV
   const int pro = sq ? 2 : 1;
   double* gacc = c.at<double>(c.p.grad_acc[s][k]);
   if (!linear_done) {
-    simt_linear_wgrad(dV, B, b.dout, U, b.din, pro, c.bn(s, k), c.grads + b.W, c.grads + b.bias, c.st);
-    if (sq)
-      simt_linear_dgrad_bngrad(dV, B, b.dout, c.params + b.W, b.din, U, pro, c.bn(s, k), gacc, c.st);
-    else
-      simt_linear_dgrad_gate(dV, B, b.dout, c.params + b.W, b.din, U, pro, c.bn(s, k), c.at<float>(c.p.Gb[s][k]), c.st);
+    if (c.p.tcb[s][k] && tc_block_backward_supported(B, b.din, b.dout, c.hp)) {
+      // the forward of this block ran on the tensor cores too: its A_hi / W_hi operands are reused
+      TcBlockArgs a{};
+      a.U = U; a.sqrt_in = sq; a.bn = c.bn(s, k); a.W = c.params + b.W; a.B = B; a.din = b.din; a.dout = b.dout;
+      a.scratch = c.ws + c.p.tcb[s][k]; a.dV = dV; a.dW = c.grads + b.W; a.db = c.grads + b.bias;
+      a.dY = sq ? nullptr : c.at<float>(c.p.Gb[s][k]); a.gacc = gacc;
+      tc_block_backward(a, c.st);
+    } else {
+      simt_linear_wgrad(dV, B, b.dout, U, b.din, pro, c.bn(s, k), c.grads + b.W, c.grads + b.bias, c.st);
+      if (sq)
+        simt_linear_dgrad_bngrad(dV, B, b.dout, c.params + b.W, b.din, U, pro, c.bn(s, k), gacc, c.st);
+      else
+        simt_linear_dgrad_gate(dV, B, b.dout, c.params + b.W, b.din, U, pro, c.bn(s, k), c.at<float>(c.p.Gb[s][k]), c.st);
+    }
   }
   if (sq) {
     bn_grad_finalize(gacc, b.din, c.grads + b.gamma, c.grads + b.beta, c.st);
@@ -313,18 +339,7 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
   const int NB = n.n_blocks;
   prof::mark(0, st);
   // ---- guide: encoder + reparameterised draws (nbvae.py:81-90) --------------------------------
-  const bool use_tce = tc_encoder_supported(d, *hp);
-  TcEncoderArgs te{};
-  if (use_tce) {
-    const Block& e0 = n.enc[0];
-    block_forward(c, 0, 0, x, false);  // statistics of sqrt(x) only
-    te.x = x; te.bn = c.bn(0, 0); te.W = params + e0.W; te.bias = params + e0.bias; te.B = B; te.G = G; te.h = e0.dout;
-    te.H = c.at<float>(p.V[0][0]); te.scratch = c.ws + p.tce;
-    tc_encoder_forward(te, st);
-  } else {
-    block_forward(c, 0, 0, x, true);
-  }
-  for (int k = 1; k < NB; ++k) block_forward(c, 0, k, x, true);
+  for (int k = 0; k < NB; ++k) block_forward(c, 0, k, x, true);
   const float* O = c.at<float>(p.V[0][NB - 1]);
   float* z = c.at<float>(p.z);
   float* l = c.at<float>(p.l);
@@ -393,17 +408,8 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
                     c.at<float>(p.asum), B, L, *hp, c.at<float>(p.dO), st);
     prof::mark(6, st);
     // ---- encoder backward ----------------------------------------------------------------------
-    for (int k = NB - 1; k >= 1; --k)
+    for (int k = NB - 1; k >= 0; --k)
       block_backward(c, 0, k, x, k == NB - 1 ? c.at<float>(p.dO) : c.at<float>(p.Gb[0][k + 1]), false);
-    if (use_tce) {
-      const Block& e0 = n.enc[0];
-      te.dH = c.at<float>(p.Gb[0][1]); te.dW = grads + e0.W; te.db = grads + e0.bias;
-      te.gacc = c.at<double>(p.grad_acc[0][0]);
-      tc_encoder_backward(te, st);
-      block_backward(c, 0, 0, x, nullptr, true);  // d gamma / d beta from the reduced sums
-    } else {
-      block_backward(c, 0, 0, x, c.at<float>(p.Gb[0][1]), false);
-    }
     prof::mark(7, st);
   }
   if (bn_batches && !(hp->flags & DRV_FLAG_NO_BN_UPDATE)) bump_counters(bn_batches, n.n_bn, st);

@@ -39,22 +39,26 @@ int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs,
                     cudaStream_t st);
 }
 
-// Encoder first layer (BatchNorm(G) -> ReLU -> Linear(G, h), reference modules.py:19-21,56) on the
-// tensor cores.  See tc_encoder.cu.
-struct TcEncoderArgs {
-  const float* x;     // [B][G] counts
-  BnParams bn;        // statistics / affine of the input BatchNorm (over sqrt(x))
-  const float* W;     // [h][G]
-  const float* bias;  // [h]
-  int B, G, h;
-  float* H;           // [B][h] output of the Linear
+// One BatchNorm -> ReLU -> Linear block (reference modules.py:19-21) on the tensor cores: 3xTF32
+// forward, single-pass tf32 backward.  Used for the encoder's first layer (sqrt input, B x G) and
+// for the h x h trunk layers.  See tc_block.cu.
+struct TcBlockArgs {
+  const float* U;     // [B][din] block input (x for the first encoder block)
+  bool sqrt_in;       // apply sqrt before the BatchNorm (encoder input, modules.py:56)
+  BnParams bn;        // statistics / affine of the block's BatchNorm
+  const float* W;     // [dout][din]
+  const float* bias;  // [dout]
+  int B, din, dout;
+  float* V;           // [B][dout] output of the Linear
   void* scratch;
-  const float* dH;    // [B][h] backward input
-  float *dW, *db;     // [h][G], [h]
-  double* gacc;       // [2][G]: sum_b dY, sum_b dY*xhat  (-> d beta, d gamma)
+  const float* dV;    // [B][dout] backward input
+  float *dW, *db;     // [dout][din], [dout]
+  float* dY;          // [B][din]: d loss / d (BN output), ReLU-gated; NULL -> reduce to gacc instead
+  double* gacc;       // [2][din]: sum_b dY, sum_b dY*xhat  (-> d beta, d gamma), used when dY == NULL
 };
-size_t tc_encoder_workspace_bytes(const drv_dims& d);
-bool tc_encoder_supported(const drv_dims& d, const drv_hparams& hp);
-void tc_encoder_forward(const TcEncoderArgs& a, cudaStream_t st);
-void tc_encoder_backward(const TcEncoderArgs& a, cudaStream_t st);
+size_t tc_block_workspace_bytes(int B, int din, int dout);
+bool tc_block_forward_supported(int B, int din, int dout, const drv_hparams& hp);
+bool tc_block_backward_supported(int B, int din, int dout, const drv_hparams& hp);
+void tc_block_forward(const TcBlockArgs& a, cudaStream_t st);
+void tc_block_backward(const TcBlockArgs& a, cudaStream_t st);
 }  // namespace drv

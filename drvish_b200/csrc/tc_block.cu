@@ -1,5 +1,6 @@
-// Encoder first layer on the sm_100a tensor cores: H = relu(bn(sqrt(x))) W^T + b and its backward.
-// (reference: Encoder.forward modules.py:56 -> make_fc modules.py:19-21.)
+// One BatchNorm -> ReLU -> Linear block on the sm_100a tensor cores: V = relu(bn(U)) W^T + b and
+// its backward (reference make_fc modules.py:19-21; the encoder's first block takes sqrt(x),
+// Encoder.forward modules.py:56).  Used for the B x G encoder input layer and the h x h trunk.
 //
 // Precision: this GEMM feeds a BatchNorm -> ReLU directly, so rounding its
 // inputs to tf32 flips ReLU gates and costs ~5e-3 of gradient accuracy.  The forward therefore
@@ -23,6 +24,7 @@ __device__ __forceinline__ float rna_tf32(float v) {
 }
 
 // a = relu(bn(sqrt(x))) split into tf32 hi/lo parts
+template <bool SQRT>
 __global__ void k_enc_prep(const float* __restrict__ x, size_t n, int G, BnParams bn, float* __restrict__ hi,
                            float* __restrict__ lo) {
   for (size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i4 < n; i4 += (size_t)gridDim.x * blockDim.x * 4) {
@@ -32,7 +34,7 @@ __global__ void k_enc_prep(const float* __restrict__ x, size_t n, int G, BnParam
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int c = col + j;
-      float a = bn_relu(sqrtf(in[j]), bn.mean[c], bn.rstd[c], bn.gamma[c], bn.beta[c]);
+      float a = bn_relu(SQRT ? sqrtf(in[j]) : in[j], bn.mean[c], bn.rstd[c], bn.gamma[c], bn.beta[c]);
       h[j] = rna_tf32(a);
       l[j] = rna_tf32(a - h[j]);
     }
@@ -139,6 +141,15 @@ __global__ void __launch_bounds__(CW* RY) k_bn0_grad(const float* __restrict__ d
   }
 }
 
+// dY = dA * [bn(U) > 0] in place (same fused-multiply-add sequence as the forward)
+__global__ void k_gate_block(float* __restrict__ dact, const float* __restrict__ U, size_t n, int D, BnParams bn) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int col = (int)(i % D);
+    float y = bn_y(bn_xhat(U[i], bn.mean[col], bn.rstd[col]), bn.gamma[col], bn.beta[col]);
+    if (!(y > 0.f)) dact[i] = 0.f;
+  }
+}
+
 struct Scratch {
   float *a_hi, *a_lo, *w_hi, *w_lo, *dh_r;
   size_t total;
@@ -175,48 +186,70 @@ int n_sm() {
 
 }  // namespace
 
-size_t tc_encoder_workspace_bytes(const drv_dims& d) { return carve(nullptr, d.n_cells, d.n_genes, d.layers[0]).total; }
+size_t tc_block_workspace_bytes(int B, int din, int dout) { return carve(nullptr, B, din, dout).total; }
 
-bool tc_encoder_supported(const drv_dims& d, const drv_hparams& hp) {
+bool tc_block_forward_supported(int B, int din, int dout, const drv_hparams& hp) {
   if (hp.flags & DRV_FLAG_FORCE_SIMT) return false;
-  int h = d.layers[0];
-  return d.n_genes % 4 == 0 && d.n_genes >= 64 && h % 32 == 0 && h >= 32 && d.n_cells >= 32;
+  // TMA: 16-byte row strides; prep kernel: 4 columns per thread
+  return din % 4 == 0 && din >= 32 && dout >= 8 && B >= 32;
 }
 
-void tc_encoder_forward(const TcEncoderArgs& a, cudaStream_t st) {
-  Scratch s = carve(a.scratch, a.B, a.G, a.h);
-  const size_t n = (size_t)a.B * a.G;
-  k_enc_prep<<<n_sm() * 8, 256, 0, st>>>(a.x, n, a.G, a.bn, s.a_hi, s.a_lo);
+bool tc_block_backward_supported(int B, int din, int dout, const drv_hparams& hp) {
+  // dV [B][dout] is a TMA operand (16-byte rows); the MN-major B operand (act / W) needs 32-wide N tiles
+  return tc_block_forward_supported(B, din, dout, hp) && dout % 4 == 0;
+}
+
+void tc_block_forward(const TcBlockArgs& a, cudaStream_t st) {
+  Scratch s = carve(a.scratch, a.B, a.din, a.dout);
+  const size_t n = (size_t)a.B * a.din;
+  int blocks = (int)((n / 4 + 255) / 256);
+  if (blocks > n_sm() * 8) blocks = n_sm() * 8;
+  if (a.sqrt_in) k_enc_prep<true><<<blocks, 256, 0, st>>>(a.U, n, a.din, a.bn, s.a_hi, s.a_lo);
+  else k_enc_prep<false><<<blocks, 256, 0, st>>>(a.U, n, a.din, a.bn, s.a_hi, s.a_lo);
   note_launch();
-  k_split_tf32<<<n_sm() * 4, 256, 0, st>>>(a.W, (size_t)a.h * a.G, s.w_hi, s.w_lo);
+  size_t nw = (size_t)a.dout * a.din;
+  int wb = (int)((nw + 255) / 256);
+  if (wb > n_sm() * 4) wb = n_sm() * 4;
+  k_split_tf32<<<wb, 256, 0, st>>>(a.W, nw, s.w_hi, s.w_lo);
   note_launch();
   const float* As[3] = {s.a_lo, s.a_hi, s.a_hi};
   const float* Bs[3] = {s.w_hi, s.w_lo, s.w_hi};
-  int rc = tc::gemm_tf32_multi(3, As, Bs, a.G, false, a.G, false, a.H, a.h, a.B, a.h, a.G, 0, false, a.bias, st);
+  int rc = tc::gemm_tf32_multi(3, As, Bs, a.din, false, a.din, false, a.V, a.dout, a.B, a.dout, a.din, 0, false, a.bias, st);
   if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
 }
 
-void tc_encoder_backward(const TcEncoderArgs& a, cudaStream_t st) {
-  Scratch s = carve(a.scratch, a.B, a.G, a.h);
+void tc_block_backward(const TcBlockArgs& a, cudaStream_t st) {
+  Scratch s = carve(a.scratch, a.B, a.din, a.dout);
   // tf32 operands are rounded to nearest when produced (the MMA truncates)
-  k_round_rows<<<n_sm() * 2, 256, 0, st>>>(a.dH, (size_t)a.B * a.h, s.dh_r);
+  size_t nd = (size_t)a.B * a.dout;
+  int rb = (int)((nd + 255) / 256);
+  if (rb > n_sm() * 2) rb = n_sm() * 2;
+  k_round_rows<<<rb, 256, 0, st>>>(a.dV, nd, s.dh_r);
   note_launch();
   {
     dim3 cb(32, 8);
     int rows = 64;
-    dim3 cgrid((a.h + 31) / 32, (a.B + rows - 1) / rows);
-    cudaMemsetAsync(a.db, 0, sizeof(float) * a.h, st);
-    k_colsum_small<<<cgrid, cb, 0, st>>>(a.dH, a.B, a.h, rows, a.db);
+    dim3 cgrid((a.dout + 31) / 32, (a.B + rows - 1) / rows);
+    cudaMemsetAsync(a.db, 0, sizeof(float) * a.dout, st);
+    k_colsum_small<<<cgrid, cb, 0, st>>>(a.dV, a.B, a.dout, rows, a.db);
     note_launch();
   }
-  // dW[j][g] = sum_b dH[b][j] A[b][g]: both operands MN-major (K = cells)
-  int rc = tc::gemm_tf32(s.dh_r, a.h, true, s.a_hi, a.G, true, a.dW, a.G, a.h, a.G, a.B, 0, false, st);
-  // dA[b][g] = sum_j dH[b][j] W[j][g]: A K-major, B MN-major (K = h); dA reuses the A_lo buffer
-  float* dA = s.a_lo;
-  if (rc == 0) rc = tc::gemm_tf32(s.dh_r, a.h, false, s.w_hi, a.G, true, dA, a.G, a.B, a.G, a.h, 0, false, st);
+  // dW[j][i] = sum_b dV[b][j] A[b][i]: both operands MN-major (K = cells)
+  int rc = tc::gemm_tf32(s.dh_r, a.dout, true, s.a_hi, a.din, true, a.dW, a.din, a.dout, a.din, a.B, 0, false, st);
+  // dA[b][i] = sum_j dV[b][j] W[j][i]: A K-major, B MN-major (K = dout)
+  float* dA = a.dY ? a.dY : s.a_lo;  // the first encoder block reuses the A_lo buffer
+  if (rc == 0) rc = tc::gemm_tf32(s.dh_r, a.dout, false, s.w_hi, a.din, true, dA, a.din, a.B, a.din, a.dout, 0, false, st);
   if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
-  // reduce dA to the input-BatchNorm gradients
-  int col_blocks = (a.G + CW * 4 - 1) / (CW * 4);
+  if (a.dY) {
+    size_t n = (size_t)a.B * a.din;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > n_sm() * 8) blocks = n_sm() * 8;
+    k_gate_block<<<blocks, 256, 0, st>>>(a.dY, a.U, n, a.din, a.bn);
+    note_launch();
+    return;
+  }
+  // reduce dA to the input-BatchNorm gradients (gate and xhat recomputed from sqrt(x))
+  int col_blocks = (a.din + CW * 4 - 1) / (CW * 4);
   int S = (n_sm() * 8 + col_blocks - 1) / col_blocks;
   int max_split = (a.B + RY * 4 - 1) / (RY * 4);
   if (S > max_split) S = max_split;
@@ -224,7 +257,7 @@ void tc_encoder_backward(const TcEncoderArgs& a, cudaStream_t st) {
   int rows = ((a.B + S - 1) / S + RY - 1) / RY * RY;
   S = (a.B + rows - 1) / rows;
   dim3 grid(col_blocks, S), block(CW, RY);
-  k_bn0_grad<<<grid, block, 0, st>>>(dA, a.x, a.B, a.G, rows, a.bn, a.gacc);
+  k_bn0_grad<<<grid, block, 0, st>>>(dA, a.U, a.B, a.din, rows, a.bn, a.gacc);
   note_launch();
 }
 

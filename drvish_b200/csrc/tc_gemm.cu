@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
           const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, int n_pairs,
-          float* __restrict__ C, int ldc, int M, int N, int K, int n_tile, int force_atomic,
+          float* __restrict__ C, int ldc, int M, int N, int K, int n_tile, int splits, int force_atomic,
           const float* __restrict__ bias, int mn_lbo, int mn_sbo, int mn_kstep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -82,9 +82,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int kb_pair = (K + BK - 1) / BK;
   const int kb_total = kb_pair * n_pairs;
   const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + n_tile - 1) / n_tile;
-  const long long units = (long long)m_tiles * n_tiles * kb_total;
-  const long long u_begin = units * blockIdx.x / gridDim.x;
-  const long long u_end = units * (blockIdx.x + 1) / gridDim.x;
+  // work = (tile, k-part) chunks: every tile's k range is cut into `splits` parts; CTA c owns the
+  // contiguous chunk range [c0, c1)
+  const long long chunks = (long long)m_tiles * n_tiles * splits;
+  const int c0 = (int)(chunks * blockIdx.x / gridDim.x);
+  const int c1 = (int)(chunks * (blockIdx.x + 1) / gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -110,9 +112,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (lane == 0) {
       const uint32_t tx = A_BYTES + (uint32_t)n_tile * BK * 4;
       int i = 0;
-      for (long long u = u_begin; u < u_end;) {
-        const int tile = (int)(u / kb_total), kb_b = (int)(u % kb_total);
-        const int kb_e = (int)min((long long)kb_total, kb_b + (u_end - u));
+      for (int ch = c0; ch < c1; ++ch) {
+        const int tile = ch / splits, part = ch % splits;
+        const int kb_b = (int)((long long)kb_total * part / splits), kb_e = (int)((long long)kb_total * (part + 1) / splits);
         const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * n_tile;
         for (int kb = kb_b; kb < kb_e; ++kb, ++i) {
           const int s = i % STAGES, ph = (i / STAGES) & 1;
@@ -135,7 +137,6 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             tma_load_2d(sb, mb, &full[s], k0, n0);
           }
         }
-        u += kb_e - kb_b;
       }
     }
   } else if (warp == 1) {
@@ -143,9 +144,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (lane == 0) {
       const uint32_t idesc = idesc_tf32(BM, n_tile, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int i = 0, seg = 0;
-      for (long long u = u_begin; u < u_end; ++seg) {
-        const int kb_b = (int)(u % kb_total);
-        const int kb_e = (int)min((long long)kb_total, kb_b + (u_end - u));
+      for (int ch = c0; ch < c1; ++ch, ++seg) {
+        const int part = ch % splits;
+        const int kb_b = (int)((long long)kb_total * part / splits), kb_e = (int)((long long)kb_total * (part + 1) / splits);
         const int as = seg & 1, aph = (seg >> 1) & 1;
         mbar_wait(&acc_empty[as], aph ^ 1);
         tc_fence_after();
@@ -165,19 +166,17 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
         }
         umma_commit(&acc_full[as]);
-        u += kb_e - kb_b;
       }
     }
   } else {
     // ===== epilogue: TMEM -> registers -> global =====
     const int q = warp % 4;  // TMEM lane quarter this warp may access
     int seg = 0;
-    for (long long u = u_begin; u < u_end; ++seg) {
-      const int tile = (int)(u / kb_total), kb_b = (int)(u % kb_total);
-      const int kb_e = (int)min((long long)kb_total, kb_b + (u_end - u));
+    for (int ch = c0; ch < c1; ++ch, ++seg) {
+      const int tile = ch / splits, part = ch % splits;
       const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * n_tile;
-      const bool whole = (kb_b == 0 && kb_e == kb_total) && !force_atomic;
-      const bool add_bias = bias != nullptr && kb_b == 0;
+      const bool whole = !force_atomic;
+      const bool add_bias = bias != nullptr && part == 0;
       const int as = seg & 1, aph = (seg >> 1) & 1;
       const int m = m0 + q * 32 + lane;
       mbar_wait(&acc_full[as], aph);
@@ -215,7 +214,6 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
-      u += kb_e - kb_b;
     }
   }
   tc_fence_before();
@@ -249,8 +247,8 @@ int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs,
                     cudaStream_t st) {
   if (n_pairs < 1 || n_pairs > 3) return -3;
   CUtensorMap ta[3], tb[3];
-  int n_tile = N >= MAXN ? MAXN : ((N + 15) / 16) * 16;
-  if (b_mn && n_tile % 32) return -3;
+  const int nq = b_mn ? 32 : 16;  // an MN-major B is staged in 32-column boxes
+  int n_tile = N >= MAXN ? MAXN : ((N + nq - 1) / nq) * nq;
   for (int p = 0; p < 3; ++p) {
     int q = p < n_pairs ? p : 0;
     bool ok;
@@ -261,15 +259,27 @@ int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs,
     else ok = tmap_2d(&tb[p], Bs[q], (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)n_tile, BK);
     if (!ok) return -3;
   }
-  const long long kb_total = (long long)((K + BK - 1) / BK) * n_pairs;
+  const int kb_total = ((K + BK - 1) / BK) * n_pairs;
   const long long tiles = (long long)((M + BM - 1) / BM) * ((N + n_tile - 1) / n_tile);
-  const long long units = tiles * kb_total;
-  int grid = max_ctas > 0 ? max_ctas : n_sm_tc();
-  if (grid > n_sm_tc()) grid = n_sm_tc();
-  if ((long long)grid > units) grid = (int)units;
-  // tiles are split across CTAs unless every CTA boundary falls on a tile boundary
-  bool split = false;
-  for (int c = 1; c < grid && !split; ++c) split = ((units * c / grid) % kb_total) != 0;
+  const int sms = max_ctas > 0 && max_ctas < n_sm_tc() ? max_ctas : n_sm_tc();
+  // split every tile's k range into `splits` parts so that the (tile, part) chunks fill the SMs:
+  // minimise ceil(chunks / SMs) * (k-blocks per chunk + epilogue cost), epilogue ~6 k-blocks for a
+  // plain store, ~12 for the red.add combine of split tiles
+  int splits = 1;
+  {
+    const int cand[] = {1, 2, 3, 4, 6, 8, 12, 16};
+    long long best = -1;
+    for (int ci = 0; ci < 8; ++ci) {
+      int sp = cand[ci];
+      if (sp > 1 && kb_total / sp < 8) break;
+      long long waves = (tiles * sp + sms - 1) / sms;
+      long long cost = waves * ((kb_total + sp - 1) / sp + (sp > 1 ? 12 : 6));
+      if (best < 0 || cost < best) { best = cost; splits = sp; }
+    }
+  }
+  const long long chunks = tiles * splits;
+  int grid = (int)(chunks < sms ? chunks : sms);
+  const bool split = splits > 1;
   if (split && !accumulate) {
     if (ldc == N) cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st);
     else cudaMemset2DAsync(C, sizeof(float) * (size_t)ldc, 0, sizeof(float) * (size_t)N, (size_t)M, st);
@@ -278,7 +288,7 @@ int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs,
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(ta[0], tb[0], ta[1], tb[1], ta[2], tb[2], n_pairs, C, ldc, M, N, K, n_tile,
-                                             force_atomic, bias, g_mn_lbo, g_mn_sbo, g_mn_kstep);
+                                             splits, force_atomic, bias, g_mn_lbo, g_mn_sbo, g_mn_kstep);
   };
   if (a_mn && b_mn) launch(k_tc_gemm<true, true>);
   else if (a_mn) launch(k_tc_gemm<true, false>);
