@@ -198,7 +198,7 @@ void block_forward(const Ctx& c, int s, int k, const float* U0, bool do_linear) 
                     c.at<float>(c.p.rstd[s][k]), update ? c.bnbuf + b.rmean : nullptr,
                     update ? c.bnbuf + b.rvar : nullptr, c.st);
   if (!do_linear) return;
-  if (c.p.tcb[s][k] && tc_block_forward_supported(B, b.din, b.dout, c.hp)) {
+  if (c.p.tcb[s][k] && tc_block_forward_supported(B, b.din, b.dout, c.hp) && (sq ? !(c.hp.flags & 32) : !(c.hp.flags & 8))) {
     TcBlockArgs a{};
     a.U = U; a.sqrt_in = sq; a.bn = c.bn(s, k); a.W = c.params + b.W; a.bias = c.params + b.bias;
     a.B = B; a.din = b.din; a.dout = b.dout; a.V = c.at<float>(c.p.V[s][k]); a.scratch = c.ws + c.p.tcb[s][k];
@@ -221,7 +221,7 @@ void block_backward(const Ctx& c, int s, int k, const float* U0, const float* dV
   const int pro = sq ? 2 : 1;
   double* gacc = c.at<double>(c.p.grad_acc[s][k]);
   if (!linear_done) {
-    if (c.p.tcb[s][k] && tc_block_backward_supported(B, b.din, b.dout, c.hp)) {
+    if (c.p.tcb[s][k] && tc_block_backward_supported(B, b.din, b.dout, c.hp) && (sq ? !(c.hp.flags & 32) : !(c.hp.flags & 4))) {
       // the forward of this block ran on the tensor cores too: its A_hi / W_hi operands are reused
       TcBlockArgs a{};
       a.U = U; a.sqrt_in = sq; a.bn = c.bn(s, k); a.W = c.params + b.W; a.B = B; a.din = b.din; a.dout = b.dout;
@@ -348,7 +348,7 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
 
   // ---- model: decoder trunk (nbvae.py:70 -> modules.py:93) ------------------------------------
   const Block& last = n.dec[NB - 1];
-  const bool use_tc = tc_decoder_supported(d, *hp);
+  const bool use_tc = tc_decoder_supported(d, *hp) && !(hp->flags & 16);
   for (int k = 0; k < NB - 1; ++k) block_forward(c, 1, k, z, true);
   block_forward(c, 1, NB - 1, z, false);  // statistics of the last BatchNorm only
   prof::mark(2, st);

@@ -214,7 +214,8 @@ void tc_block_forward(const TcBlockArgs& a, cudaStream_t st) {
   note_launch();
   const float* As[3] = {s.a_lo, s.a_hi, s.a_hi};
   const float* Bs[3] = {s.w_hi, s.w_lo, s.w_hi};
-  int rc = tc::gemm_tf32_multi(3, As, Bs, a.din, false, a.din, false, a.V, a.dout, a.B, a.dout, a.din, 0, false, a.bias, st);
+  int rc = tc::gemm_tf32_multi(3, As, Bs, a.din, false, a.din, false, a.V, a.dout, a.B, a.dout, a.din, 0, false, a.bias, st,
+                               /*max_chain_kb=*/32);
   if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
 }
 

@@ -244,7 +244,7 @@ static int n_sm_tc() {
 // first when stream-K splits a tile over several CTAs).  max_ctas <= 0: one CTA per SM.
 int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs, int lda, bool a_mn, int ldb, bool b_mn,
                     float* C, int ldc, int M, int N, int K, int max_ctas, bool accumulate, const float* bias,
-                    cudaStream_t st) {
+                    cudaStream_t st, int max_chain_kb) {
   if (n_pairs < 1 || n_pairs > 3) return -3;
   CUtensorMap ta[3], tb[3];
   const int nq = b_mn ? 32 : 16;  // an MN-major B is staged in 32-column boxes
@@ -277,6 +277,10 @@ int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs,
       if (best < 0 || cost < best) { best = cost; splits = sp; }
     }
   }
+  // Precision knob: the TMEM accumulator is updated with truncation, a bias that grows with the
+  // length of the accumulation chain (measured ~5e-9 relative per MMA step).  GEMMs that feed a
+  // BatchNorm -> ReLU directly cap the chain; the partial tiles are combined by fp32 red.add (RN).
+  if (max_chain_kb > 0 && (kb_total + splits - 1) / splits > max_chain_kb) splits = (kb_total + max_chain_kb - 1) / max_chain_kb;
   const long long chunks = tiles * splits;
   int grid = (int)(chunks < sms ? chunks : sms);
   const bool split = splits > 1;
@@ -300,7 +304,7 @@ int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs,
 
 int gemm_tf32(const float* A, int lda, bool a_mn, const float* Bm, int ldb, bool b_mn, float* C, int ldc, int M, int N,
               int K, int max_ctas, bool accumulate, cudaStream_t st) {
-  return gemm_tf32_multi(1, &A, &Bm, lda, a_mn, ldb, b_mn, C, ldc, M, N, K, max_ctas, accumulate, nullptr, st);
+  return gemm_tf32_multi(1, &A, &Bm, lda, a_mn, ldb, b_mn, C, ldc, M, N, K, max_ctas, accumulate, nullptr, st, 0);
 }
 
 }  // namespace tc

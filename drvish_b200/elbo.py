@@ -37,7 +37,7 @@ class FusedTraceELBO:
 
     def __init__(self, num_particles: int = 1, seed: int = 0, data_parallel: Optional[bool] = None,
                  process_group=None, include_guide_factor: bool = True, force_simt: bool = False,
-                 update_bn_stats: bool = True, **_ignored):
+                 update_bn_stats: bool = True, extra_flags: int = 0, **_ignored):
         if num_particles != 1:
             raise NotImplementedError("the fused ELBO evaluates one particle (the reference notebook's setting)")
         self.seed = int(seed)
@@ -45,7 +45,8 @@ class FusedTraceELBO:
         self.data_parallel = data_parallel
         self.process_group = process_group
         self.include_guide_factor = include_guide_factor
-        self.flags = (_lib.DRV_FLAG_FORCE_SIMT if force_simt else 0) | (0 if update_bn_stats else _lib.DRV_FLAG_NO_BN_UPDATE)
+        self.flags = ((_lib.DRV_FLAG_FORCE_SIMT if force_simt else 0) | (0 if update_bn_stats else _lib.DRV_FLAG_NO_BN_UPDATE)
+                      | int(extra_flags))
         self._explicit_noise = None
         self._noise_bufs = {}
         self.last_status = 0

@@ -3,6 +3,7 @@ and the ctypes calls into the C ABI.  PyTorch is used for device memory and stre
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -96,7 +97,7 @@ class ModelRuntime:
         hp.bn_eps = float(bn0.eps)
         hp.bn_momentum = float(bn0.momentum)
         hp.include_guide_factor = 1 if include_guide_factor else 0
-        hp.flags = int(flags)
+        hp.flags = int(flags) | int(os.environ.get("DRVISH_B200_DEBUG_FLAGS", "0"))
         return hp
 
     # ------------------------------------------------------------------------------------

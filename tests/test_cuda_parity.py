@@ -138,3 +138,74 @@ def test_noise_generators_are_standard():
     assert torch.equal(a, out)  # counter-based: reproducible
     _lib.check(lib.drv_fill_laplace(C.c_void_p(out.data_ptr()), n, C.c_uint64(7), C.c_uint64(4 * n), st), "fill")
     assert abs(float(out.mean())) < 5e-3 and abs(float(out.var()) - 2) < 3e-2
+
+
+# ---- full benchmark sizes (BASELINE.json configs 2 and 3: one 4096-cell minibatch) -------------
+FULL = {
+    "cfg2_full": dict(n_input=2000, n_latent=10, layers=[128, 128], batch=4096, drugs=0),
+    "cfg3_full": dict(n_input=5000, n_latent=10, layers=[256, 256], batch=4096, drugs=8, doses=8, classes=8),
+}
+
+
+@pytest.mark.parametrize("name", list(FULL))
+def test_full_size_step_matches_oracle(name):
+    """The tensor-core path at the sizes bench.py times, against the fp64 oracle (a few seconds of CPU)."""
+    case = P.make_case(FULL[name], data_seed=1234)
+    rep = P.compare_step(case)
+    print(_report(rep))
+    assert rep["loss_rel"] <= ELBO_TOL, _report(rep)
+    assert rep["worst_grad_rel"] <= GRAD_TOL, _report(rep)
+    assert rep["bn_worst_rel"] <= 1e-5, _report(rep)
+
+
+def test_tensor_core_and_cuda_core_paths_agree():
+    """A/B on the device: tcgen05 path vs the fp32 CUDA-core path on the same inputs."""
+    case = P.make_case(FULL["cfg2_full"], data_seed=7)
+    l_tc, g_tc, _ = P.cuda_step(case, force_simt=False)
+    l_cc, g_cc, _ = P.cuda_step(case, force_simt=True)
+    assert abs(l_tc - l_cc) <= 2e-5 * abs(l_cc)
+    zero = P.zero_grad_biases(2)
+    for k in g_tc:
+        if k in zero:
+            continue
+        assert P.rel_err(g_tc[k], g_cc[k]) <= GRAD_TOL, (k, P.rel_err(g_tc[k], g_cc[k]))
+
+
+def test_size_independent_properties():
+    """(i) the plate terms scale linearly with scale_factor; (ii) permuting the cells of the
+    minibatch (with their noise) leaves the loss and the gradients unchanged."""
+    import drvish_b200 as D
+
+    cfg = dict(n_input=512, n_latent=8, layers=[64, 64], batch=1024, drugs=0)
+    case = P.make_case(cfg, data_seed=3)
+    loss1, g1, model = P.cuda_step(case)
+    model2 = P.build_cuda_model(case, "cuda:0")
+    model2.scale_factor = 0.25
+    loss2, g2, _ = P.cuda_step(case, model=model2)
+    assert abs(loss2 - 0.25 * loss1) <= 1e-5 * abs(loss1)
+    k = "decoder.fc.8.weight"
+    assert P.rel_err(g2[k], 0.25 * g1[k]) <= 1e-4
+    perm = torch.randperm(cfg["batch"], generator=torch.Generator().manual_seed(0))
+    case_p = dict(case, x=case["x"][perm], noise={k2: v[perm] for k2, v in case["noise"].items()})
+    loss3, g3, _ = P.cuda_step(case_p)
+    assert abs(loss3 - loss1) <= 1e-5 * abs(loss1)
+    assert P.rel_err(g3[k], g1[k]) <= 1e-4
+
+
+def test_production_noise_path_runs_and_is_seeded():
+    """Philox draws inside the step: same seed -> same loss, different step index -> different draws."""
+    import drvish_b200 as D
+
+    cfg = dict(n_input=256, n_latent=6, layers=[64, 64], batch=256, drugs=2, doses=4, classes=4)
+    case = P.make_case(cfg)
+    args = [case["x"].cuda(), case["labels"].cuda(), [t.cuda() for t in case["y"]]]
+    losses = []
+    for seed in (5, 5, 6):
+        model = P.build_cuda_model(case, "cuda:0")
+        elbo = D.FusedTraceELBO(seed=seed, data_parallel=False, update_bn_stats=False)
+        losses.append([elbo.loss_and_grads(model.model, model.guide, *args) for _ in range(2)])
+    # same seed -> same draws (reductions use atomics: equal up to summation order)
+    assert all(abs(a - b) <= 1e-7 * abs(a) for a, b in zip(losses[0], losses[1]))
+    assert abs(losses[0][0] - losses[0][1]) > 1e-5 * abs(losses[0][0])
+    assert abs(losses[0][0] - losses[2][0]) > 1e-5 * abs(losses[0][0])
+    assert all(torch.isfinite(torch.tensor(l)).all() for l in losses)
