@@ -22,6 +22,29 @@ inline void note_launch() {
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Side stream for work that is off the critical chain of a step (weight-gradient GEMMs, the
+// dose-response head): forked from / joined to the caller's stream with events, so the whole step
+// still looks like one stream to the caller (and is CUDA-graph capturable).
+struct SideStream {
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool used = false;
+  // work enqueued on `side` after this call sees everything enqueued on `main` so far
+  void fork(cudaStream_t main) {
+    cudaEventRecord(ev_fork, main);
+    cudaStreamWaitEvent(side, ev_fork, 0);
+    used = true;
+  }
+  // work enqueued on `main` after this call sees everything enqueued on `side` so far
+  void join(cudaStream_t main) {
+    if (!used) return;
+    cudaEventRecord(ev_join, side);
+    cudaStreamWaitEvent(main, ev_join, 0);
+    used = false;
+  }
+};
+SideStream* side_stream();  // per-thread, created on first use (nullptr if creation failed)
+
 // BatchNorm -> ReLU applied to one element (modules.py:19-20).  Explicit fma so that the
 // forward value and the recomputed ReLU gate of the backward are bit-identical.
 struct BnParams {

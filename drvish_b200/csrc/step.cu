@@ -26,6 +26,21 @@ inline void mark(int i, cudaStream_t st) {
 }
 }  // namespace prof
 
+SideStream* side_stream() {
+  static thread_local SideStream ss;
+  static thread_local bool tried = false;
+  if (!tried) {
+    tried = true;
+    if (cudaStreamCreateWithFlags(&ss.side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ss.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ss.ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      ss.side = nullptr;
+      cudaGetLastError();
+    }
+  }
+  return ss.side ? &ss : nullptr;
+}
+
 namespace {
 
 constexpr int64_t ALIGN_F = 32;  // tensors start on 128-byte boundaries inside the flat buffers
@@ -177,6 +192,7 @@ struct Ctx {
   float* grads;
   float* bnbuf;
   cudaStream_t st;
+  SideStream* side;  // may be null: everything then runs on st
   template <class T> T* at(size_t off) const { return reinterpret_cast<T*>(ws + off); }
   BnParams bn(int s, int k) const {
     const Block& b = s == 0 ? n.enc[k] : n.dec[k];
@@ -226,10 +242,13 @@ void block_backward(const Ctx& c, int s, int k, const float* U0, const float* dV
       TcBlockArgs a{};
       a.U = U; a.sqrt_in = sq; a.bn = c.bn(s, k); a.W = c.params + b.W; a.B = B; a.din = b.din; a.dout = b.dout;
       a.scratch = c.ws + c.p.tcb[s][k]; a.dV = dV; a.dW = c.grads + b.W; a.db = c.grads + b.bias;
-      a.dY = sq ? nullptr : c.at<float>(c.p.Gb[s][k]); a.gacc = gacc;
+      a.dY = sq ? nullptr : c.at<float>(c.p.Gb[s][k]); a.gacc = gacc; a.side = c.side;
       tc_block_backward(a, c.st);
     } else {
-      simt_linear_wgrad(dV, B, b.dout, U, b.din, pro, c.bn(s, k), c.grads + b.W, c.grads + b.bias, c.st);
+      // the weight gradient is off the critical chain: side stream
+      cudaStream_t ws = c.st;
+      if (c.side) { c.side->fork(c.st); ws = c.side->side; }
+      simt_linear_wgrad(dV, B, b.dout, U, b.din, pro, c.bn(s, k), c.grads + b.W, c.grads + b.bias, ws);
       if (sq)
         simt_linear_dgrad_bngrad(dV, B, b.dout, c.params + b.W, b.din, U, pro, c.bn(s, k), gacc, c.st);
       else
@@ -328,7 +347,8 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
   Plan p = make_plan(d, n);
   if (workspace_bytes < p.total) return DRV_ENOSPC;
   cudaStream_t st = (cudaStream_t)stream;
-  Ctx c{d, *hp, n, p, (char*)workspace, params, grads, bn_running, st};
+  SideStream* side = (hp->flags & 64) ? nullptr : side_stream();
+  Ctx c{d, *hp, n, p, (char*)workspace, params, grads, bn_running, st, side};
   const int B = d.n_cells, G = d.n_genes, L = d.n_latent;
   const bool bwd = grads != nullptr;
 
@@ -345,6 +365,26 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
   float* l = c.at<float>(p.l);
   sample_forward(O, eps_z, eps_l, B, L, *hp, z, l, out, st);
   prof::mark(1, st);
+
+  // ---- dose-response head (drnbvae.py:110-116, 131-132): needs only z, runs on the side stream
+  // concurrently with the decoder; joined before the sampling backward consumes dz_drs
+  DrShape ds{B, L, d.n_drugs, d.n_classes, d.n_doses_total};
+  if (d.n_drugs > 0) {
+    cudaStream_t dst = st;
+    if (side) { side->fork(st); dst = side->side; }
+    dr_project(z, w_prior, ds, c.at<float>(p.u), dst);
+    dr_means(c.at<float>(p.u), b_prior, labels, dose_offsets, ds, y, hp->sigma_scale, c.at<float>(p.m),
+             c.at<float>(p.gfac), out, status, dst);
+    if (bwd) {
+      // weight_loc / weight_scale never enter the loss (SURVEY 3.2): their gradient is zero
+      cudaMemsetAsync(grads + n.w_loc, 0, sizeof(float) * (size_t)(n.b_loc - n.w_loc), dst);
+    }
+    dr_prior_factor(w_prior, b_prior, eps_bias, params + n.b_loc, params + n.b_scale, dose_offsets, ds, *hp,
+                    bwd ? grads + n.b_loc : nullptr, bwd ? grads + n.b_scale : nullptr, out, dst);
+    if (bwd)
+      dr_backward(c.at<float>(p.u), b_prior, w_prior, labels, dose_offsets, c.at<float>(p.gfac), ds,
+                  c.at<float>(p.du), c.at<float>(p.dz_drs), dst);
+  }
 
   // ---- model: decoder trunk (nbvae.py:70 -> modules.py:93) ------------------------------------
   const Block& last = n.dec[NB - 1];
@@ -372,31 +412,18 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
   }
   prof::mark(3, st);
 
-  // ---- dose-response head (drnbvae.py:110-116, 131-132) ---------------------------------------
-  DrShape ds{B, L, d.n_drugs, d.n_classes, d.n_doses_total};
-  if (d.n_drugs > 0) {
-    dr_project(z, w_prior, ds, c.at<float>(p.u), st);
-    dr_means(c.at<float>(p.u), b_prior, labels, dose_offsets, ds, y, hp->sigma_scale, c.at<float>(p.m),
-             c.at<float>(p.gfac), out, status, st);
-    if (bwd) {
-      // weight_loc / weight_scale never enter the loss (SURVEY 3.2): their gradient is zero
-      cudaMemsetAsync(grads + n.w_loc, 0, sizeof(float) * (size_t)(n.b_loc - n.w_loc), st);
-    }
-    dr_prior_factor(w_prior, b_prior, eps_bias, params + n.b_loc, params + n.b_scale, dose_offsets, ds, *hp,
-                    bwd ? grads + n.b_loc : nullptr, bwd ? grads + n.b_scale : nullptr, out, st);
-    if (bwd)
-      dr_backward(c.at<float>(p.u), b_prior, w_prior, labels, dose_offsets, c.at<float>(p.gfac), ds,
-                  c.at<float>(p.du), c.at<float>(p.dz_drs), st);
-  }
   prof::mark(4, st);
 
   if (bwd) {
     // ---- backward of the last decoder Linear ---------------------------------------------------
     if (use_tc) {
+      ta.side = side;
       tc_decoder_backward(ta, st);
     } else {
+      cudaStream_t ws = st;
+      if (side) { side->fork(st); ws = side->side; }
       simt_linear_wgrad(dlogits, B, last.dout, c.at<float>(p.V[1][NB - 2]), last.din, 1, c.bn(1, NB - 1),
-                        grads + last.W, grads + last.bias, st);
+                        grads + last.W, grads + last.bias, ws);
       simt_linear_dgrad_gate(dlogits, B, last.dout, params + last.W, last.din, c.at<float>(p.V[1][NB - 2]), 1,
                              c.bn(1, NB - 1), c.at<float>(p.Gb[1][NB - 1]), st);
     }
@@ -404,6 +431,7 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
     // ---- decoder trunk backward, sampling backward ---------------------------------------------
     block_backward(c, 1, NB - 1, z, nullptr, true);
     for (int k = NB - 2; k >= 0; --k) block_backward(c, 1, k, z, c.at<float>(p.Gb[1][k + 1]), false);
+    if (side && d.n_drugs > 0) side->join(st);  // dz_drs (later side work re-forks)
     sample_backward(O, eps_z, eps_l, z, l, c.at<float>(p.Gb[1][0]), d.n_drugs > 0 ? c.at<float>(p.dz_drs) : nullptr,
                     c.at<float>(p.asum), B, L, *hp, c.at<float>(p.dO), st);
     prof::mark(6, st);
@@ -412,6 +440,7 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
       block_backward(c, 0, k, x, k == NB - 1 ? c.at<float>(p.dO) : c.at<float>(p.Gb[0][k + 1]), false);
     prof::mark(7, st);
   }
+  if (side) side->join(st);
   if (bn_batches && !(hp->flags & DRV_FLAG_NO_BN_UPDATE)) bump_counters(bn_batches, n.n_bn, st);
   // fold the status word into the result record
   {
@@ -465,7 +494,7 @@ int drv_encoder_forward(const drv_dims* dims, const drv_hparams* hp, const float
   Plan p = make_plan(*dims, n);
   if (workspace_bytes < p.total) return DRV_ENOSPC;
   cudaStream_t st = (cudaStream_t)stream;
-  Ctx c{*dims, *hp, n, p, (char*)workspace, params, nullptr, bn_running, st};
+  Ctx c{*dims, *hp, n, p, (char*)workspace, params, nullptr, bn_running, st, nullptr};
   cudaMemsetAsync(c.ws + p.zero_begin, 0, p.zero_bytes, st);
   for (int k = 0; k < n.n_blocks; ++k) block_forward(c, 0, k, x, true);
   encoder_outputs(c.at<float>(p.V[0][n.n_blocks - 1]), dims->n_cells, dims->n_latent, z_loc, z_scale, l_loc, l_scale, st);
@@ -483,7 +512,7 @@ int drv_decoder_forward(const drv_dims* dims, const drv_hparams* hp, const float
   Plan p = make_plan(*dims, n);
   if (workspace_bytes < p.total) return DRV_ENOSPC;
   cudaStream_t st = (cudaStream_t)stream;
-  Ctx c{*dims, *hp, n, p, (char*)workspace, params, nullptr, bn_running, st};
+  Ctx c{*dims, *hp, n, p, (char*)workspace, params, nullptr, bn_running, st, nullptr};
   cudaMemsetAsync(c.ws + p.zero_begin, 0, p.zero_bytes, st);
   for (int k = 0; k < n.n_blocks; ++k) block_forward(c, 1, k, z, true);
   nb_decoder_outputs(c.at<float>(p.V[1][n.n_blocks - 1]), library, dims->n_cells, dims->n_genes, log_r, logit, st);

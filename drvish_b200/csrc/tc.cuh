@@ -21,6 +21,7 @@ struct TcDecoderArgs {
   bool bwd;
   float *dW, *db;     // [2G][h], [2G]
   float* dY;          // [B][h]: d loss / d (BN output), already gated by the ReLU mask
+  SideStream* side;   // optional: weight-gradient GEMM runs there
 };
 
 size_t tc_workspace_bytes(const drv_dims& d);
@@ -55,6 +56,7 @@ struct TcBlockArgs {
   float *dW, *db;     // [dout][din], [dout]
   float* dY;          // [B][din]: d loss / d (BN output), ReLU-gated; NULL -> reduce to gacc instead
   double* gacc;       // [2][din]: sum_b dY, sum_b dY*xhat  (-> d beta, d gamma), used when dY == NULL
+  SideStream* side;   // optional: weight-gradient GEMM runs there
 };
 size_t tc_block_workspace_bytes(int B, int din, int dout);
 bool tc_block_forward_supported(int B, int din, int dout, const drv_hparams& hp);

@@ -236,7 +236,9 @@ void tc_block_backward(const TcBlockArgs& a, cudaStream_t st) {
     note_launch();
   }
   // dW[j][i] = sum_b dV[b][j] A[b][i]: both operands MN-major (K = cells)
-  int rc = tc::gemm_tf32(s.dh_r, a.dout, true, s.a_hi, a.din, true, a.dW, a.din, a.dout, a.din, a.B, 0, false, st);
+  cudaStream_t ws = st;
+  if (a.side) { a.side->fork(st); ws = a.side->side; }  // off the critical chain
+  int rc = tc::gemm_tf32(s.dh_r, a.dout, true, s.a_hi, a.din, true, a.dW, a.din, a.dout, a.din, a.B, 0, false, ws);
   // dA[b][i] = sum_j dV[b][j] W[j][i]: A K-major, B MN-major (K = dout)
   float* dA = a.dY ? a.dY : s.a_lo;  // the first encoder block reuses the A_lo buffer
   if (rc == 0) rc = tc::gemm_tf32(s.dh_r, a.dout, false, s.w_hi, a.din, true, dA, a.din, a.B, a.din, a.dout, 0, false, st);

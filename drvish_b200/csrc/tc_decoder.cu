@@ -542,7 +542,9 @@ void tc_decoder_backward(const TcDecoderArgs& a, cudaStream_t st) {
   const int n_ct = (a.B + BM - 1) / BM, n_gt = (a.G + 63) / 64;
   launch_dec(k_dec<3, true>, n_ct * n_gt, tAct, tW3, tX, p, st);
   // dW[j][i] = sum_b dlogits[b][j] act[b][i]   (both operands MN-major, K = cells)
-  int rc = gemm_tf32(a.dlogits, 2 * a.G, true, s.act, a.h, true, a.dW, a.h, 2 * a.G, a.h, a.B, 0, false, st);
+  cudaStream_t ws = st;
+  if (a.side) { a.side->fork(st); ws = a.side->side; }  // off the critical chain
+  int rc = gemm_tf32(a.dlogits, 2 * a.G, true, s.act, a.h, true, a.dW, a.h, 2 * a.G, a.h, a.B, 0, false, ws);
   // dAct[b][i] = sum_j dlogits[b][j] W[j][i]   (A K-major, B MN-major, K = 2G)
   if (rc == 0) rc = gemm_tf32(a.dlogits, 2 * a.G, false, s.Wr, a.h, true, a.dY, a.h, a.B, a.h, 2 * a.G, 0, false, st);
   if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
