@@ -235,7 +235,6 @@ def run_native(args, cfg):
         device_step(i)
     launches_per_step = rt.last_launches + (5 if cfg["drugs"] else 2)  # + noise fills
     barrier()
-    lib.drv_profile_enable(1)
     sampler = ClockSampler(local)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -246,10 +245,6 @@ def run_native(args, cfg):
     barrier()
     clocks = sampler.finish()
     ms_total = ev0.elapsed_time(ev1)
-    sec = (C.c_float * 7)()
-    nprof = C.c_int()
-    lib.drv_profile_read(sec, C.byref(nprof))
-    lib.drv_profile_enable(0)
     loss_last, status = rt.read_out()
     t = torch.tensor([ms_total], device=device, dtype=torch.float64)
     if world > 1:
@@ -257,6 +252,26 @@ def run_native(args, cfg):
     ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- live kernel timing for the roofline: CUDA events recorded by the library on the step's
+    # own stream, around the sections and around the single kernels of the fused decoder path.
+    # The side stream is switched off here (flag 64) so that a section contains ALL of its work.
+    n_prof = min(args.steps, 32)
+    os.environ["DRVISH_B200_DEBUG_FLAGS"] = "64"
+    for i in range(3):
+        device_step(i)
+    torch.cuda.synchronize()
+    lib.drv_profile_enable(1)
+    for i in range(n_prof):
+        device_step(i)
+    torch.cuda.synchronize()
+    sec = (C.c_float * 7)()
+    kms = (C.c_float * 5)()
+    nprof = C.c_int()
+    lib.drv_profile_read(sec, C.byref(nprof))
+    lib.drv_profile_read_kernels(kms)
+    lib.drv_profile_enable(0)
+    os.environ["DRVISH_B200_DEBUG_FLAGS"] = "0"
 
     # ---- end-to-end through the public API, host minibatches --------------------------------
     # every step's inputs start in pinned HOST memory; PinnedBatchPrefetcher issues the H2D copy of
@@ -292,8 +307,9 @@ def run_native(args, cfg):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the fused decoder-last-layer + NB-likelihood section ----------------------
+    # ---- roofline of the fused decoder-last-layer + NB-likelihood step ----------------
     peaks = load_peaks()
+    Bf, Gf, hf = float(B), float(G), float(cfg["layers"][0])
     bytes_alg, flops_alg = decoder_algorithmic(cfg)
     t_dec_ms = sec[2] + sec[4]
     t_hbm = bytes_alg / (peaks["hbm"] * 1e9)
@@ -304,12 +320,43 @@ def run_native(args, cfg):
     else:
         roof = {"bound": "hbm", "achieved": bytes_alg / (t_dec_ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s"}
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof["traffic"] = None
-    roof["kernel"] = "decoder last Linear + gene-softmax + NB likelihood, fwd+bwd (sections DEC_NB_FWD + DEC_NB_BWD)"
-    roof["peak_source"] = peaks["which"] + (" bf16 sustained; tf32 operands: nominal tensor peak is half" if roof["bound"] == "tensor" else "")
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(f"cfg{args.config}", {})
+    roof["traffic"] = traffic.get("decoder_step_bytes")
+    roof["kernel"] = ("fused decoder step = k_dec<1> (logsumexp) + k_dec<2> (NB likelihood + NB part of dlogits) + "
+                      "k_dec<3> (softmax coupling) + dAct and dW tcgen05 GEMMs (sections DEC_NB_FWD + DEC_NB_BWD, "
+                      "side stream off)")
+    roof["algorithmic"] = {"bytes": bytes_alg, "flops": flops_alg, "formula": "8BG+8Bh+16Gh bytes, 12BGh flops (SURVEY 8d)"}
+    roof["peak_source"] = peaks["which"] + " (bf16 sustained cuBLAS; the kernels use kind::tf32 whose nominal peak is half)"
     roof["section_ms"] = {k: round(float(sec[i]), 4) for i, k in enumerate(
         ["enc_fwd", "dec_trunk_fwd", "dec_nb_fwd", "dose_response", "dec_nb_bwd", "dec_trunk_bwd", "enc_bwd"])}
     roof["profiled_steps"] = int(nprof.value)
+    # per-kernel entries: algorithmic work of that launch / its own event-timed duration
+    kdefs = [
+        ("k_dec<1> logsumexp", 4 * Gf * hf + 4 * Bf * hf, 2 * Bf * Gf * hf),
+        ("k_dec<2> NB likelihood (+ NB part of dlogits)", 4 * Bf * Gf + 8 * Bf * Gf + 8 * Gf * hf + 4 * Bf * hf, 4 * Bf * Gf * hf),
+        ("k_dec<3> softmax coupling", 8 * Bf * Gf + 4 * Gf * hf + 4 * Bf * hf, 2 * Bf * Gf * hf),
+        ("dAct GEMM", 8 * Bf * Gf + 8 * Gf * hf + 4 * Bf * hf, 4 * Bf * Gf * hf),
+        ("dW GEMM", 8 * Bf * Gf + 8 * Gf * hf + 4 * Bf * hf, 4 * Bf * Gf * hf),
+    ]
+    rk = []
+    for i, (name, kb, kf) in enumerate(kdefs):
+        ms = float(kms[i])
+        if ms <= 0:
+            continue
+        th, tt = kb / (peaks["hbm"] * 1e9), kf / (peaks["tensor"] * 1e12)
+        ent = {"kernel": name, "ms": round(ms, 4), "bound": "hbm" if th >= tt else "tensor"}
+        if th >= tt:
+            ent.update(achieved=kb / (ms * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s")
+        else:
+            ent.update(achieved=kf / (ms * 1e-3) / 1e12, peak=peaks["tensor"], unit="TFLOP/s")
+        ent["frac"] = ent["achieved"] / ent["peak"]
+        ent["traffic"] = traffic.get(name.split(" ")[0])
+        rk.append(ent)
+    roof["kernels"] = rk
 
     # ---- CPU baseline on the host cores (bounded sample) ---------------------------------------
     cpu = None

@@ -68,6 +68,7 @@ SYMBOLS = {
     "drv_logit_mean_sigmoid": (C.c_int, [C.POINTER(Dims)] + [_P] * 8 + [C.c_size_t, _P]),
     "drv_profile_enable": (C.c_int, [C.c_int]),
     "drv_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "drv_profile_read_kernels": (C.c_int, [C.POINTER(C.c_float)]),
     "drv_fill_normal": (C.c_int, [_P, C.c_int64, C.c_uint64, C.c_uint64, _P]),
     "drv_fill_laplace": (C.c_int, [_P, C.c_int64, C.c_uint64, C.c_uint64, _P]),
 }

@@ -35,6 +35,14 @@ struct SideStream {
     cudaStreamWaitEvent(side, ev_fork, 0);
     used = true;
   }
+  // split form: mark the fork point now, keep submitting critical-path work to `main`, and attach
+  // the side stream later - kernels that become ready together are dispatched in submission order,
+  // so the critical-path kernel gets the SMs first
+  void mark(cudaStream_t main) { cudaEventRecord(ev_fork, main); }
+  void attach() {
+    cudaStreamWaitEvent(side, ev_fork, 0);
+    used = true;
+  }
   // work enqueued on `main` after this call sees everything enqueued on `side` so far
   void join(cudaStream_t main) {
     if (!used) return;

@@ -20,9 +20,13 @@ constexpr int MAX_STEPS = 64;
 bool enabled = false;
 int n_steps = 0;
 cudaEvent_t ev[MAX_STEPS][DRV_N_SECTIONS + 1];
+cudaEvent_t kev[MAX_STEPS][DRV_N_PROFILED_KERNELS][2];  // start/stop pairs around single kernels
 bool created = false;
 inline void mark(int i, cudaStream_t st) {
   if (enabled && n_steps < MAX_STEPS) cudaEventRecord(ev[n_steps][i], st);
+}
+inline void kmark(int k, int which, cudaStream_t st) {
+  if (enabled && n_steps < MAX_STEPS) cudaEventRecord(kev[n_steps][k][which], st);
 }
 }  // namespace prof
 
@@ -459,6 +463,10 @@ int drv_profile_enable(int on) {
     for (int i = 0; i < prof::MAX_STEPS; ++i)
       for (int j = 0; j <= DRV_N_SECTIONS; ++j)
         if (cudaEventCreate(&prof::ev[i][j]) != cudaSuccess) return (int)cudaGetLastError();
+    for (int i = 0; i < prof::MAX_STEPS; ++i)
+      for (int j = 0; j < DRV_N_PROFILED_KERNELS; ++j)
+        for (int w = 0; w < 2; ++w)
+          if (cudaEventCreate(&prof::kev[i][j][w]) != cudaSuccess) return (int)cudaGetLastError();
     prof::created = true;
   }
   prof::enabled = on != 0;
@@ -483,6 +491,23 @@ int drv_profile_read(float* h_ms_per_section, int* h_n_steps) {
   if (h_n_steps) *h_n_steps = ns;
   return 0;
 }
+
+int drv_profile_read_kernels(float* h_ms_per_kernel) {
+  if (!prof::created) return DRV_EINVAL;
+  int ns = prof::n_steps;
+  for (int j = 0; j < DRV_N_PROFILED_KERNELS; ++j) h_ms_per_kernel[j] = 0.f;
+  for (int i = 0; i < ns; ++i)
+    for (int j = 0; j < DRV_N_PROFILED_KERNELS; ++j) {
+      float ms = 0.f;
+      cudaError_t e = cudaEventSynchronize(prof::kev[i][j][1]);
+      if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, prof::kev[i][j][0], prof::kev[i][j][1]);
+      if (e != cudaSuccess) { cudaGetLastError(); ms = 0.f; }  // kernel not launched on this path
+      h_ms_per_kernel[j] += ms / ns;
+    }
+  return 0;
+}
+
+void drv_internal_kmark(int k, int which, void* stream) { prof::kmark(k, which, (cudaStream_t)stream); }
 
 int drv_encoder_forward(const drv_dims* dims, const drv_hparams* hp, const float* x, const float* params,
                         float* bn_running, int64_t* bn_batches, float* z_loc, float* z_scale, float* l_loc,

@@ -236,12 +236,14 @@ void tc_block_backward(const TcBlockArgs& a, cudaStream_t st) {
     note_launch();
   }
   // dW[j][i] = sum_b dV[b][j] A[b][i]: both operands MN-major (K = cells)
-  cudaStream_t ws = st;
-  if (a.side) { a.side->fork(st); ws = a.side->side; }  // off the critical chain
-  int rc = tc::gemm_tf32(s.dh_r, a.dout, true, s.a_hi, a.din, true, a.dW, a.din, a.dout, a.din, a.B, 0, false, ws);
-  // dA[b][i] = sum_j dV[b][j] W[j][i]: A K-major, B MN-major (K = dout)
+  if (a.side) a.side->mark(st);
+  // dA[b][i] = sum_j dV[b][j] W[j][i]: A K-major, B MN-major (K = dout): critical path, submitted first
   float* dA = a.dY ? a.dY : s.a_lo;  // the first encoder block reuses the A_lo buffer
-  if (rc == 0) rc = tc::gemm_tf32(s.dh_r, a.dout, false, s.w_hi, a.din, true, dA, a.din, a.B, a.din, a.dout, 0, false, st);
+  int rc = tc::gemm_tf32(s.dh_r, a.dout, false, s.w_hi, a.din, true, dA, a.din, a.B, a.din, a.dout, 0, false, st);
+  // dW[j][i] = sum_b dV[b][j] A[b][i]: both operands MN-major (K = cells): off the critical chain
+  cudaStream_t ws = st;
+  if (a.side) { a.side->attach(); ws = a.side->side; }
+  if (rc == 0) rc = tc::gemm_tf32(s.dh_r, a.dout, true, s.a_hi, a.din, true, a.dW, a.din, a.dout, a.din, a.B, 0, false, ws);
   if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
   if (a.dY) {
     size_t n = (size_t)a.B * a.din;

@@ -18,6 +18,8 @@
 #include "tc.cuh"
 #include "tc_common.cuh"
 
+extern "C" void drv_internal_kmark(int k, int which, void* stream);
+
 namespace drv {
 
 using namespace tc;
@@ -61,6 +63,29 @@ struct DecParams {
   float* db;          // [2G] (atomic accumulation, zeroed)
 };
 
+// Column sums of 4 values over the 32 lanes of a warp by a transposing butterfly (6 shuffles instead
+// of 20): afterwards w[0] of every lane with (lane & 7) == 0 holds the sum of column
+// 2*bit4(lane) + bit3(lane); returns that column index or -1.
+__device__ __forceinline__ int butterfly4(float (&w)[4], int lane) {
+  const bool hi16 = lane & 16;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = hi16 ? w[i] : w[i + 2];
+    const float keep = hi16 ? w[i + 2] : w[i];
+    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  const bool hi8 = lane & 8;
+  {
+    const float send = hi8 ? w[0] : w[1];
+    const float keep = hi8 ? w[1] : w[0];
+    w[0] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  w[0] += __shfl_xor_sync(0xffffffffu, w[0], 4);
+  w[0] += __shfl_xor_sync(0xffffffffu, w[0], 2);
+  w[0] += __shfl_xor_sync(0xffffffffu, w[0], 1);
+  return (lane & 7) == 0 ? ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1) : -1;
+}
+
 template <int PHASE, bool WITH_A>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtensorMap tmW,
@@ -78,7 +103,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
   float* lgtab = (float*)(tmem_slot + 4);
   load_lgamma_table(lgtab, threadIdx.x);
 
-  constexpr int TN = PHASE == 1 ? 128 : 64;  // genes per tile
+  constexpr int TN = PHASE == 2 ? 64 : 128;  // genes per tile (phases 1 and 3 cover the scale half only)
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int n_gt = (p.G + TN - 1) / TN;
   const int n_ct = (p.B + BM - 1) / BM;
@@ -90,7 +115,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
   if (warp == N_EPI_WARPS && lane == 0) {
     tma_prefetch_desc(&tmAct);
     tma_prefetch_desc(&tmW);
-    if (PHASE != 1) tma_prefetch_desc(&tmX);
+    if (PHASE == 2) tma_prefetch_desc(&tmX);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -116,7 +141,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
       for (int t = t0, it = 0; t < t1; ++t, ++it) {
         const int ct = t / n_gt, gt = t % n_gt;
         const int b0 = ct * BM, g0 = gt * TN;
-        if (PHASE != 1) {
+        if (PHASE == 2) {
           const int xs = it & 1, xph = (it >> 1) & 1;
           mbar_wait(&x_empty[xs], xph ^ 1);
           mbar_expect_tx(&x_full[xs], X_BYTES);
@@ -129,7 +154,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
           uint8_t* sa = smem + s * STAGE_BYTES;
           mbar_expect_tx(&full[s], STAGE_BYTES);
           tma_load_2d(sa, &tmAct, &full[s], kb * BK, b0);
-          if (PHASE == 1) tma_load_2d(sa + A_BYTES, &tmW, &full[s], kb * BK, g0);
+          if (PHASE != 2) tma_load_2d(sa + A_BYTES, &tmW, &full[s], kb * BK, g0);
           else tma_load_3d(sa + A_BYTES, &tmW, &full[s], kb * BK, g0, 0);
         }
       }
@@ -197,6 +222,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
           lse_b = p.lse[b];
           if (PHASE == 3) asum_b = p.asum[b];
         }
+        if (PHASE == 3 && !row_ok) asum_b = 0.f;
       }
       const int g0 = gt * TN;
       mbar_wait(&acc_full[as], aph);
@@ -230,10 +256,74 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
           s_run = s_run * __expf(m_run - M) + s * __expf(m - M);
           m_run = M;
         }
+      } else if (PHASE == 3) {
+        // backward, light phase: the NB part of d loss/d logits was written by phase 2; only the
+        // softmax coupling is missing:  ds = ds' + c A[b] softmax(s)  (ds = a - p A).
+        // This warp owns 32 genes of the 128-gene (scale half) tile, in 8 groups of 4 columns.
+        const int gbase = g0 + cg * 32;
+        const float cA = p.c * asum_b;
+        float* drow = p.dlogits + (size_t)b * 2 * p.G + gbase;
+        const bool vec_all = gbase + 32 <= p.G;
+        // all 8 x 16-byte loads of this thread's ds' row segment are issued up front (the loop
+        // would otherwise expose one DRAM/L2 latency per group: measured stall_long_sb 60 %)
+        float4 dpre[8];
+#pragma unroll
+        for (int g4 = 0; g4 < 8; ++g4) {
+          dpre[g4] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row_ok) {
+            if (vec_all) {
+              dpre[g4] = __ldcs(reinterpret_cast<const float4*>(drow + 4 * g4));
+            } else {
+              const int gq = gbase + 4 * g4;
+              if (gq < p.G) dpre[g4].x = drow[4 * g4];
+              if (gq + 1 < p.G) dpre[g4].y = drow[4 * g4 + 1];
+              if (gq + 2 < p.G) dpre[g4].z = drow[4 * g4 + 2];
+              if (gq + 3 < p.G) dpre[g4].w = drow[4 * g4 + 3];
+            }
+          }
+        }
+#pragma unroll
+        for (int g4 = 0; g4 < 8; ++g4) {
+          float sv[4], bs[4], ds[4];
+          tmem_ld4(tbase + cg * 32 + g4 * 4, sv);
+          const int gq = gbase + 4 * g4;
+          const bool vec = gq + 4 <= p.G;
+          float* d0 = drow + 4 * g4;
+          if (vec) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(p.bias + gq));
+            bs[0] = f.x; bs[1] = f.y; bs[2] = f.z; bs[3] = f.w;
+          } else {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) bs[v] = (gq + v < p.G) ? __ldg(&p.bias[gq + v]) : 0.f;
+          }
+          const float dsp[4] = {dpre[g4].x, dpre[g4].y, dpre[g4].z, dpre[g4].w};
+          tmem_ld_wait();
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const bool ok = row_ok && (gq + v < p.G);
+            const float pr = ex2_approx((sv[v] + bs[v] - lse_b) * 1.4426950408889634f);
+            ds[v] = ok ? rna_tf32(__fmaf_rn(cA, pr, dsp[v])) : 0.f;
+          }
+          if (row_ok) {
+            if (vec) *reinterpret_cast<float4*>(d0) = make_float4(ds[0], ds[1], ds[2], ds[3]);
+            else {
+#pragma unroll
+              for (int v = 0; v < 4; ++v)
+                if (gq + v < p.G) d0[v] = ds[v];
+            }
+          }
+          const int col = butterfly4(ds, lane);
+          if (col >= 0 && gq + col < p.G) atomicAdd(&p.db[gq + col], ds[0]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[as]);
       } else {
-        // phases 2/3: this warp owns 16 genes of the 64-gene tile, processed as a ROLLED loop
-        // over 4 groups of 4 columns (compact code: the fully unrolled epilogue thrashed the
-        // instruction cache); nb_elems<.,4> provides the instruction-level parallelism.
+        // phase 2: this warp owns 16 genes of the 64-gene tile, processed as a ROLLED loop over 4
+        // groups of 4 columns (compact code: the fully unrolled epilogue thrashed the instruction
+        // cache); nb_elems<.,4> provides the instruction-level parallelism.  In training mode
+        // (WITH_A) the same pass also emits the NB part of d loss/d logits, so the transcendental
+        // work is done once:  ds' = -c a (fp32, completed by phase 3),  drho = -c dLL/drho (final).
         const int xs = it & 1, xph = (it >> 1) & 1;
         mbar_wait(&x_full[xs], xph);
         const int gbase = g0 + cg * 16;
@@ -266,79 +356,46 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
             }
           }
           tmem_ld_wait();
-          float a_lsl[4], a_rho[4], a_x[4], ls[4];
+          float a_lsl[4], a_rho[4], a_x[4];
           bool ok[4];
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
             ok[v] = row_ok && (gq + v < p.G);
-            ls[v] = ok[v] ? sv[v] + bs[v] - lse_b : 0.f;
-            a_lsl[v] = PHASE == 2 ? (ok[v] ? lml + sv[v] + bs[v] : 0.f) : lib_b + ls[v];
+            a_lsl[v] = ok[v] ? lml + sv[v] + bs[v] : 0.f;
             a_rho[v] = ok[v] ? rv[v] + br[v] : 0.f;
             a_x[v] = ok[v] ? xv[v] : 0.f;
           }
           NbElem e[4];
-          nb_elems<(PHASE == 3) || WITH_A, 4>(a_lsl, a_rho, a_x, p.eps, lgtab, e);
-          if (PHASE == 2) {
+          nb_elems<WITH_A, 4>(a_lsl, a_rho, a_x, p.eps, lgtab, e);
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              if (ok[v]) {
-                ll_acc += e[v].ll;
-                if (WITH_A) a_acc += e[v].a;
-              }
+          for (int v = 0; v < 4; ++v) {
+            if (ok[v]) {
+              ll_acc += e[v].ll;
+              if (WITH_A) a_acc += e[v].a;
             }
-          } else {
-            // backward: ds = -c (a - p A), drho = -c dLL/drho (rounded to tf32: MMA operands)
-            float ds[4], dr[4];
+          }
+          if (WITH_A) {
+            float dsp[4], dr[4];
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
-              ds[v] = ok[v] ? rna_tf32(-p.c * (e[v].a - ex2_approx(ls[v] * 1.4426950408889634f) * asum_b)) : 0.f;
-              dr[v] = ok[v] ? rna_tf32(-p.c * e[v].drho) : 0.f;
+              dsp[v] = ok[v] ? -p.c * e[v].a : 0.f;
+              dr[v] = ok[v] ? rna_tf32(-p.c * e[v].drho) : 0.f;  // tf32 MMA operand of dW / dAct
             }
             if (row_ok) {
               float* d0 = p.dlogits + (size_t)b * 2 * p.G + gq;
               float* d1 = d0 + p.G;
               if (gq + 4 <= p.G) {
-                *reinterpret_cast<float4*>(d0) = make_float4(ds[0], ds[1], ds[2], ds[3]);
+                *reinterpret_cast<float4*>(d0) = make_float4(dsp[0], dsp[1], dsp[2], dsp[3]);
                 *reinterpret_cast<float4*>(d1) = make_float4(dr[0], dr[1], dr[2], dr[3]);
               } else {
 #pragma unroll
                 for (int v = 0; v < 4; ++v)
-                  if (gq + v < p.G) { d0[v] = ds[v]; d1[v] = dr[v]; }
+                  if (gq + v < p.G) { d0[v] = dsp[v]; d1[v] = dr[v]; }
               }
             }
-            // bias gradient: column sums over the 32 rows of this warp by a transposing butterfly
-            // (8 values x 32 lanes -> 8 sums in 9 shuffles), then one atomic per column
-            float w8[8] = {ds[0], ds[1], ds[2], ds[3], dr[0], dr[1], dr[2], dr[3]};
-            {
-              const bool hi16 = lane & 16;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float send = hi16 ? w8[i] : w8[i + 4];
-                float keep = hi16 ? w8[i + 4] : w8[i];
-                w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-              }
-              const bool hi8 = lane & 8;
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                float send = hi8 ? w8[i] : w8[i + 2];
-                float keep = hi8 ? w8[i + 2] : w8[i];
-                w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-              }
-              const bool hi4 = lane & 4;
-              {
-                float send = hi4 ? w8[0] : w8[1];
-                float keep = hi4 ? w8[1] : w8[0];
-                w8[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-              }
-              w8[0] += __shfl_xor_sync(0xffffffffu, w8[0], 2);
-              w8[0] += __shfl_xor_sync(0xffffffffu, w8[0], 1);
-              // lane holds column index: bit4 -> +4 (dr half), bit3 -> +2, bit2 -> +1
-              if ((lane & 3) == 0) {
-                const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-                const int col = idx & 3;
-                if (gq + col < p.G) atomicAdd(&p.db[(idx >> 2) * p.G + gq + col], w8[0]);
-              }
-            }
+            // bias gradient of the log_r half: column sums over the 32 rows of this warp
+            const int col = butterfly4(dr, lane);
+            if (col >= 0 && gq + col < p.G) atomicAdd(&p.db[p.G + gq + col], dr[0]);
           }
         }
         tc_fence_before();
@@ -511,7 +568,9 @@ void tc_decoder_forward(const TcDecoderArgs& a, cudaStream_t st) {
   const int n_ct = (a.B + BM - 1) / BM;
   // phase 1: logsumexp over genes
   const int n_gt1 = (a.G + 127) / 128;
+  drv_internal_kmark(0, 0, st);
   launch_dec(k_dec<1, false>, n_ct * n_gt1, tAct, tW1, tX, p, st);
+  drv_internal_kmark(0, 1, st);
   {
     const int n_tiles1 = n_ct * n_gt1;
     const int grid1 = n_tiles1 < sm_count() ? n_tiles1 : sm_count();
@@ -521,9 +580,12 @@ void tc_decoder_forward(const TcDecoderArgs& a, cudaStream_t st) {
   // phase 2: NB log-likelihood row sums
   cudaMemsetAsync(a.ll, 0, sizeof(float) * a.B, st);
   cudaMemsetAsync(a.asum, 0, sizeof(float) * a.B, st);
+  if (a.bwd) cudaMemsetAsync(a.db, 0, sizeof(float) * 2 * a.G, st);  // bias gradient: phases 2 (log_r) + 3 (scale)
   const int n_gt = (a.G + 63) / 64;
+  drv_internal_kmark(1, 0, st);
   if (a.bwd) launch_dec(k_dec<2, true>, n_ct * n_gt, tAct, tW3, tX, p, st);
   else launch_dec(k_dec<2, false>, n_ct * n_gt, tAct, tW3, tX, p, st);
+  drv_internal_kmark(1, 1, st);
   k_loss_from_ll<<<8, 256, 0, st>>>(a.ll, a.B, a.c, a.out);
   note_launch();
 }
@@ -538,15 +600,22 @@ void tc_decoder_backward(const TcDecoderArgs& a, cudaStream_t st) {
   DecParams p{};
   p.B = a.B; p.G = a.G; p.h = a.h; p.bias = a.bias; p.lib = a.lib; p.eps = a.eps; p.c = a.c;
   p.lse = a.lse; p.ll = a.ll; p.asum = a.asum; p.dlogits = a.dlogits; p.db = a.db;
-  cudaMemsetAsync(a.db, 0, sizeof(float) * 2 * a.G, st);
-  const int n_ct = (a.B + BM - 1) / BM, n_gt = (a.G + 63) / 64;
-  launch_dec(k_dec<3, true>, n_ct * n_gt, tAct, tW3, tX, p, st);
+  const int n_ct = (a.B + BM - 1) / BM, n_gt1 = (a.G + 127) / 128;
+  drv_internal_kmark(2, 0, st);
+  launch_dec(k_dec<3, true>, n_ct * n_gt1, tAct, tW1, tX, p, st);
+  drv_internal_kmark(2, 1, st);
   // dW[j][i] = sum_b dlogits[b][j] act[b][i]   (both operands MN-major, K = cells)
+  if (a.side) a.side->mark(st);
+  // dAct[b][i] = sum_j dlogits[b][j] W[j][i]   (A K-major, B MN-major, K = 2G): critical path, submitted first
+  drv_internal_kmark(3, 0, st);
+  int rc = gemm_tf32(a.dlogits, 2 * a.G, false, s.Wr, a.h, true, a.dY, a.h, a.B, a.h, 2 * a.G, 0, false, st);
+  drv_internal_kmark(3, 1, st);
+  // dW[j][i] = sum_b dlogits[b][j] act[b][i]   (both operands MN-major, K = cells): off the critical chain
   cudaStream_t ws = st;
-  if (a.side) { a.side->fork(st); ws = a.side->side; }  // off the critical chain
-  int rc = gemm_tf32(a.dlogits, 2 * a.G, true, s.act, a.h, true, a.dW, a.h, 2 * a.G, a.h, a.B, 0, false, ws);
-  // dAct[b][i] = sum_j dlogits[b][j] W[j][i]   (A K-major, B MN-major, K = 2G)
-  if (rc == 0) rc = gemm_tf32(a.dlogits, 2 * a.G, false, s.Wr, a.h, true, a.dY, a.h, a.B, a.h, 2 * a.G, 0, false, st);
+  if (a.side) { a.side->attach(); ws = a.side->side; }
+  drv_internal_kmark(4, 0, ws);
+  if (rc == 0) rc = gemm_tf32(a.dlogits, 2 * a.G, true, s.act, a.h, true, a.dW, a.h, 2 * a.G, a.h, a.B, 0, false, ws);
+  drv_internal_kmark(4, 1, ws);
   if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
   int blocks = (int)(((size_t)a.B * a.h + 255) / 256);
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;

@@ -147,6 +147,11 @@ int drv_fill_laplace(float* out, int64_t n, uint64_t seed, uint64_t offset, void
 #define DRV_SEC_ENC_BWD 6        /* encoder backward */
 int drv_profile_enable(int on);
 int drv_profile_read(float* h_ms_per_section, int* h_n_steps);
+/* Event pairs around single kernels of the fused decoder path (mean milliseconds per launch):
+ * 0 = phase 1 (logsumexp), 1 = phase 2 (NB likelihood [+ NB part of dlogits]), 2 = phase 3 (softmax
+ * coupling), 3 = dAct GEMM, 4 = dW GEMM.  0 when the kernel did not run. */
+#define DRV_N_PROFILED_KERNELS 5
+int drv_profile_read_kernels(float* h_ms_per_kernel);
 
 /* Number of kernels the last drv_* call on this thread enqueued (for bench.py's gpu_launches). */
 int drv_last_launch_count(void);
