@@ -90,12 +90,16 @@ template <int PHASE, bool WITH_A>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtensorMap tmW,
       const __grid_constant__ CUtensorMap tmX, DecParams p) {
+  // phase 3 stages a 128 x 128 ds' tile (4 boxes, 64 KB) instead of the 128 x 64 count tile and
+  // makes room for it with a 2-deep operand ring (its MMA is far from critical)
+  constexpr int NST = PHASE == 3 ? 2 : STAGES;
+  constexpr int XB = PHASE == 3 ? 2 * X_BYTES : X_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* xbuf = smem + STAGES * STAGE_BYTES;
-  uint64_t* full = (uint64_t*)(xbuf + 2 * X_BYTES);
-  uint64_t* empty = full + STAGES;
-  uint64_t* acc_full = empty + STAGES;    // [2]
+  uint8_t* xbuf = smem + NST * STAGE_BYTES;
+  uint64_t* full = (uint64_t*)(xbuf + 2 * XB);
+  uint64_t* empty = full + NST;
+  uint64_t* acc_full = empty + NST;       // [2]
   uint64_t* acc_empty = acc_full + 2;     // [2]
   uint64_t* x_full = acc_empty + 2;       // [2]
   uint64_t* x_empty = x_full + 2;         // [2]
@@ -115,8 +119,8 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
   if (warp == N_EPI_WARPS && lane == 0) {
     tma_prefetch_desc(&tmAct);
     tma_prefetch_desc(&tmW);
-    if (PHASE == 2) tma_prefetch_desc(&tmX);
-    for (int s = 0; s < STAGES; ++s) {
+    if (PHASE != 1) tma_prefetch_desc(&tmX);
+    for (int s = 0; s < NST; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
@@ -141,15 +145,16 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
       for (int t = t0, it = 0; t < t1; ++t, ++it) {
         const int ct = t / n_gt, gt = t % n_gt;
         const int b0 = ct * BM, g0 = gt * TN;
-        if (PHASE == 2) {
+        if (PHASE != 1) {
           const int xs = it & 1, xph = (it >> 1) & 1;
           mbar_wait(&x_empty[xs], xph ^ 1);
-          mbar_expect_tx(&x_full[xs], X_BYTES);
-          tma_load_2d(xbuf + xs * X_BYTES, &tmX, &x_full[xs], g0, b0);
-          tma_load_2d(xbuf + xs * X_BYTES + X_BYTES / 2, &tmX, &x_full[xs], g0 + 32, b0);
+          mbar_expect_tx(&x_full[xs], XB);
+#pragma unroll
+          for (int j = 0; j < XB / (BM * 128); ++j)
+            tma_load_2d(xbuf + xs * XB + j * (BM * 128), &tmX, &x_full[xs], g0 + 32 * j, b0);
         }
         for (int kb = 0; kb < nkb; ++kb, ++kit) {
-          const int s = kit % STAGES, ph = (kit / STAGES) & 1;
+          const int s = kit % NST, ph = (kit / NST) & 1;
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* sa = smem + s * STAGE_BYTES;
           mbar_expect_tx(&full[s], STAGE_BYTES);
@@ -170,7 +175,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * 128);
         for (int kb = 0; kb < nkb; ++kb, ++kit) {
-          const int s = kit % STAGES, ph = (kit / STAGES) & 1;
+          const int s = kit % NST, ph = (kit / NST) & 1;
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
@@ -263,25 +268,11 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
         const int gbase = g0 + cg * 32;
         const float cA = p.c * asum_b;
         float* drow = p.dlogits + (size_t)b * 2 * p.G + gbase;
-        const bool vec_all = gbase + 32 <= p.G;
-        // all 8 x 16-byte loads of this thread's ds' row segment are issued up front (the loop
-        // would otherwise expose one DRAM/L2 latency per group: measured stall_long_sb 60 %)
-        float4 dpre[8];
-#pragma unroll
-        for (int g4 = 0; g4 < 8; ++g4) {
-          dpre[g4] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row_ok) {
-            if (vec_all) {
-              dpre[g4] = __ldcs(reinterpret_cast<const float4*>(drow + 4 * g4));
-            } else {
-              const int gq = gbase + 4 * g4;
-              if (gq < p.G) dpre[g4].x = drow[4 * g4];
-              if (gq + 1 < p.G) dpre[g4].y = drow[4 * g4 + 1];
-              if (gq + 2 < p.G) dpre[g4].z = drow[4 * g4 + 2];
-              if (gq + 3 < p.G) dpre[g4].w = drow[4 * g4 + 3];
-            }
-          }
-        }
+        // ds' tile: TMA-staged a tile ahead by the producer warp (box cg = this warp's 32 genes,
+        // row r, 16-byte chunk g4 XOR-swizzled with r % 8)
+        const int xs = it & 1, xph = (it >> 1) & 1;
+        mbar_wait(&x_full[xs], xph);
+        const uint8_t* drow_s = xbuf + xs * XB + cg * (BM * 128) + r * 128;
 #pragma unroll
         for (int g4 = 0; g4 < 8; ++g4) {
           float sv[4], bs[4], ds[4];
@@ -296,7 +287,8 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
 #pragma unroll
             for (int v = 0; v < 4; ++v) bs[v] = (gq + v < p.G) ? __ldg(&p.bias[gq + v]) : 0.f;
           }
-          const float dsp[4] = {dpre[g4].x, dpre[g4].y, dpre[g4].z, dpre[g4].w};
+          const float4 dld = *reinterpret_cast<const float4*>(drow_s + ((g4 ^ (r & 7)) * 16));
+          const float dsp[4] = {dld.x, dld.y, dld.z, dld.w};
           tmem_ld_wait();
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
@@ -317,7 +309,10 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[as]);
+        if (lane == 0) {
+          mbar_arrive(&acc_empty[as]);
+          mbar_arrive(&x_empty[xs]);
+        }
       } else {
         // phase 2: this warp owns 16 genes of the 64-gene tile, processed as a ROLLED loop over 4
         // groups of 4 columns (compact code: the fully unrolled epilogue thrashed the instruction
@@ -328,7 +323,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
         mbar_wait(&x_full[xs], xph);
         const int gbase = g0 + cg * 16;
         const float lml = lib_b - lse_b;
-        const uint8_t* xrow = xbuf + xs * X_BYTES + (cg >> 1) * (X_BYTES / 2) + r * 128;
+        const uint8_t* xrow = xbuf + xs * XB + (cg >> 1) * (BM * 128) + r * 128;
         const bool full_cols = gbase + 16 <= p.G;
 #pragma unroll 1
         for (int g4 = 0; g4 < 4; ++g4) {
@@ -601,8 +596,13 @@ void tc_decoder_backward(const TcDecoderArgs& a, cudaStream_t st) {
   p.B = a.B; p.G = a.G; p.h = a.h; p.bias = a.bias; p.lib = a.lib; p.eps = a.eps; p.c = a.c;
   p.lse = a.lse; p.ll = a.ll; p.asum = a.asum; p.dlogits = a.dlogits; p.db = a.db;
   const int n_ct = (a.B + BM - 1) / BM, n_gt1 = (a.G + 127) / 128;
+  CUtensorMap tD;  // scale half of dlogits: [B][G] with row stride 2G
+  if (!tmap_2d(&tD, a.dlogits, a.B, a.G, 2 * (uint64_t)a.G, BM, 32)) {
+    if (g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
+    return;
+  }
   drv_internal_kmark(2, 0, st);
-  launch_dec(k_dec<3, true>, n_ct * n_gt1, tAct, tW1, tX, p, st);
+  launch_dec(k_dec<3, true>, n_ct * n_gt1, tAct, tW1, tD, p, st);
   drv_internal_kmark(2, 1, st);
   // dW[j][i] = sum_b dlogits[b][j] act[b][i]   (both operands MN-major, K = cells)
   if (a.side) a.side->mark(st);
