@@ -21,9 +21,48 @@ inline int row_splits(int B, int D) {
   return s < 1 ? 1 : s;
 }
 
+// Finalisation folded into the statistics kernel: the last CTA to finish (ticket counter) turns the
+// fp64 sums into mean / rstd and updates the running buffers (momentum, unbiased variance) - one
+// launch less per BatchNorm.
+struct StatFinal {
+  unsigned int* ticket;  // zeroed counter
+  int B;
+  float eps, momentum;
+  float *mean, *rstd, *rmean, *rvar;  // rmean/rvar may be null
+};
+
+__device__ __forceinline__ void stat_finalize_if_last(const StatFinal& f, const double* acc, int D) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (tid == 0) {
+    const unsigned int total = gridDim.x * gridDim.y;
+    is_last = atomicAdd(f.ticket, 1u) == total - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int nthr = blockDim.x * blockDim.y;
+  for (int i = tid; i < D; i += nthr) {
+    const double m = __ldcg(&acc[i]) / f.B;
+    double var = __ldcg(&acc[D + i]) / f.B - m * m;
+    if (var < 0.0) var = 0.0;
+    f.mean[i] = (float)m;
+    // the fp64 part ends here (sum of squares minus squared mean); sqrt / divide in fp32 keep the
+    // single finalising CTA short
+    f.rstd[i] = 1.0f / sqrtf((float)(var + (double)f.eps));
+    if (f.rmean) {
+      const float unbiased = (float)var * ((float)f.B / (float)(f.B - 1));
+      f.rmean[i] = (1.0f - f.momentum) * f.rmean[i] + f.momentum * (float)m;
+      f.rvar[i] = (1.0f - f.momentum) * f.rvar[i] + f.momentum * unbiased;
+    }
+  }
+}
+
 template <bool SQRT>
 __global__ void __launch_bounds__(CW* RY) k_colstats(const float* __restrict__ U, int B, int D, int rows_per_cta,
-                                                      double* __restrict__ acc) {
+                                                      double* __restrict__ acc, StatFinal fin) {
   int col = blockIdx.x * CW + threadIdx.x;
   int r0 = blockIdx.y * rows_per_cta;
   int r1 = min(B, r0 + rows_per_cta);
@@ -54,13 +93,14 @@ __global__ void __launch_bounds__(CW* RY) k_colstats(const float* __restrict__ U
     for (int i = 0; i < RY; ++i) t += sh[threadIdx.y][i][threadIdx.x];
     atomicAdd(&acc[(size_t)threadIdx.y * D + col], t);
   }
+  stat_finalize_if_last(fin, acc, D);
 }
 
 // Wide version (D % 4 == 0): 128-bit loads, 4 columns per thread, 2 rows in flight per thread.
 // fp32 partial sums over <= 32 rows are folded into fp64 accumulators.
 template <bool SQRT>
 __global__ void __launch_bounds__(CW* RY) k_colstats4(const float* __restrict__ U, int B, int D, int rows_per_cta,
-                                                       double* __restrict__ acc) {
+                                                       double* __restrict__ acc, StatFinal fin) {
   const int col = (blockIdx.x * CW + threadIdx.x) * 4;
   const int r0 = blockIdx.y * rows_per_cta;
   const int r1 = min(B, r0 + rows_per_cta);
@@ -114,6 +154,7 @@ __global__ void __launch_bounds__(CW* RY) k_colstats4(const float* __restrict__ 
     for (int i = 0; i < RY; ++i) t += sh[which][i][c];
     atomicAdd(&acc[(size_t)which * D + gcol], t);
   }
+  stat_finalize_if_last(fin, acc, D);
 }
 
 __global__ void k_colstats_finalize(const double* __restrict__ acc, int B, int D, float eps, float momentum,
@@ -133,6 +174,9 @@ __global__ void k_colstats_finalize(const double* __restrict__ acc, int B, int D
   }
 }
 
+// GATE: dY holds the UNGATED gradient w.r.t. the ReLU output; the gate [bn(U) > 0] is recomputed here
+// (same fused-multiply-add sequence as the forward), saving a separate gating pass.
+template <bool GATE>
 __global__ void __launch_bounds__(CW* RY) k_bn_bwd_reduce(const float* __restrict__ dY, const float* __restrict__ U, int B,
                                                            int D, int rows_per_cta, BnParams bn,
                                                            double* __restrict__ acc) {
@@ -141,10 +185,11 @@ __global__ void __launch_bounds__(CW* RY) k_bn_bwd_reduce(const float* __restric
   int r1 = min(B, r0 + rows_per_cta);
   double s1 = 0.0, s2 = 0.0;
   if (col < D) {
-    float mean = bn.mean[col], rstd = bn.rstd[col];
+    float mean = bn.mean[col], rstd = bn.rstd[col], gam = bn.gamma[col], bet = bn.beta[col];
     for (int r = r0 + threadIdx.y; r < r1; r += RY) {
       float g = dY[(size_t)r * D + col];
       float xh = bn_xhat(U[(size_t)r * D + col], mean, rstd);
+      if (GATE && !(bn_y(xh, gam, bet) > 0.f)) g = 0.f;
       s1 += g;
       s2 += (double)g * xh;
     }
@@ -161,6 +206,7 @@ __global__ void __launch_bounds__(CW* RY) k_bn_bwd_reduce(const float* __restric
   }
 }
 
+template <bool GATE>
 __global__ void k_bn_bwd_apply(float* __restrict__ dY, const float* __restrict__ U, int B, int D, BnParams bn,
                                const double* __restrict__ acc, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   size_t n = (size_t)B * D;
@@ -169,7 +215,9 @@ __global__ void k_bn_bwd_apply(float* __restrict__ dY, const float* __restrict__
     float s1 = (float)(acc[col] / B), s2 = (float)(acc[D + col] / B);
     float rstd = bn.rstd[col];
     float xh = bn_xhat(U[idx], bn.mean[col], rstd);
-    dY[idx] = bn.gamma[col] * rstd * (dY[idx] - s1 - xh * s2);
+    float g = dY[idx];
+    if (GATE && !(bn_y(xh, bn.gamma[col], bn.beta[col]) > 0.f)) g = 0.f;
+    dY[idx] = bn.gamma[col] * rstd * (g - s1 - xh * s2);
     if (idx < (size_t)D) {
       dbeta[col] = (float)acc[col];
       dgamma[col] = (float)acc[D + col];
@@ -196,7 +244,9 @@ __global__ void k_finalize_status(drv_step_out* out) {
 
 }  // namespace
 
-void colstats_accumulate(const float* U, int B, int D, bool sqrt_in, double* acc, cudaStream_t st) {
+void colstats(const float* U, int B, int D, bool sqrt_in, double* acc, unsigned int* ticket, float eps, float momentum,
+              float* mean, float* rstd, float* running_mean, float* running_var, cudaStream_t st) {
+  StatFinal fin{ticket, B, eps, momentum, mean, rstd, running_mean, running_var};
   if (D % 4 == 0 && D >= 512 && ((uintptr_t)U % 16) == 0) {
     int col_blocks = cdiv(D, CW * 4);
     int S = cdiv(148 * 8, col_blocks);
@@ -206,8 +256,8 @@ void colstats_accumulate(const float* U, int B, int D, bool sqrt_in, double* acc
     int rows = cdiv(cdiv(B, S), RY) * RY;
     S = cdiv(B, rows);
     dim3 grid(col_blocks, S), block(CW, RY);
-    if (sqrt_in) k_colstats4<true><<<grid, block, 0, st>>>(U, B, D, rows, acc);
-    else k_colstats4<false><<<grid, block, 0, st>>>(U, B, D, rows, acc);
+    if (sqrt_in) k_colstats4<true><<<grid, block, 0, st>>>(U, B, D, rows, acc, fin);
+    else k_colstats4<false><<<grid, block, 0, st>>>(U, B, D, rows, acc, fin);
     note_launch();
     return;
   }
@@ -216,33 +266,29 @@ void colstats_accumulate(const float* U, int B, int D, bool sqrt_in, double* acc
   rows = cdiv(rows, RY) * RY;
   S = cdiv(B, rows);
   dim3 grid(cdiv(D, CW), S), block(CW, RY);
-  if (sqrt_in) k_colstats<true><<<grid, block, 0, st>>>(U, B, D, rows, acc);
-  else k_colstats<false><<<grid, block, 0, st>>>(U, B, D, rows, acc);
+  if (sqrt_in) k_colstats<true><<<grid, block, 0, st>>>(U, B, D, rows, acc, fin);
+  else k_colstats<false><<<grid, block, 0, st>>>(U, B, D, rows, acc, fin);
   note_launch();
 }
 
-void colstats_finalize(const double* acc, int B, int D, float eps, float momentum, float* mean, float* rstd,
-                       float* running_mean, float* running_var, cudaStream_t st) {
-  k_colstats_finalize<<<cdiv(D, 256), 256, 0, st>>>(acc, B, D, eps, momentum, mean, rstd, running_mean, running_var);
-  note_launch();
-}
-
-void bn_bwd_reduce(const float* dY, const float* U, int B, int D, BnParams bn, double* acc, cudaStream_t st) {
+void bn_bwd_reduce(const float* dY, const float* U, int B, int D, BnParams bn, double* acc, bool gate, cudaStream_t st) {
   int S = row_splits(B, D);
   int rows = cdiv(B, S);
   rows = cdiv(rows, RY) * RY;
   S = cdiv(B, rows);
   dim3 grid(cdiv(D, CW), S), block(CW, RY);
-  k_bn_bwd_reduce<<<grid, block, 0, st>>>(dY, U, B, D, rows, bn, acc);
+  if (gate) k_bn_bwd_reduce<true><<<grid, block, 0, st>>>(dY, U, B, D, rows, bn, acc);
+  else k_bn_bwd_reduce<false><<<grid, block, 0, st>>>(dY, U, B, D, rows, bn, acc);
   note_launch();
 }
 
 void bn_bwd_apply(float* dY_dU, const float* U, int B, int D, BnParams bn, const double* acc, float* dgamma,
-                  float* dbeta, cudaStream_t st) {
+                  float* dbeta, bool gate, cudaStream_t st) {
   size_t n = (size_t)B * D;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  k_bn_bwd_apply<<<blocks, 256, 0, st>>>(dY_dU, U, B, D, bn, acc, dgamma, dbeta);
+  if (gate) k_bn_bwd_apply<true><<<blocks, 256, 0, st>>>(dY_dU, U, B, D, bn, acc, dgamma, dbeta);
+  else k_bn_bwd_apply<false><<<blocks, 256, 0, st>>>(dY_dU, U, B, D, bn, acc, dgamma, dbeta);
   note_launch();
 }
 

@@ -6,16 +6,16 @@
 namespace drv {
 
 // ---- k_stats.cu: BatchNorm statistics and their backward ------------------------------------
-// acc: [2][D] doubles, zero on entry.  sum / sum of squares of (sqrt?)U over the batch.
-void colstats_accumulate(const float* U, int B, int D, bool sqrt_in, double* acc, cudaStream_t st);
-// mean / rstd from acc; running buffers updated like torch BatchNorm1d in training mode.
-void colstats_finalize(const double* acc, int B, int D, float eps, float momentum, float* mean, float* rstd,
-                       float* running_mean, float* running_var, cudaStream_t st);
-// acc[0][i] += sum_b dY, acc[1][i] += sum_b dY * xhat
-void bn_bwd_reduce(const float* dY, const float* U, int B, int D, BnParams bn, double* acc, cudaStream_t st);
+// acc: [2][D] doubles and *ticket, all zero on entry.  Sum / sum of squares of (sqrt?)U over the
+// batch; the last CTA turns them into mean / rstd and updates the running buffers like torch
+// BatchNorm1d in training mode.
+void colstats(const float* U, int B, int D, bool sqrt_in, double* acc, unsigned int* ticket, float eps, float momentum,
+              float* mean, float* rstd, float* running_mean, float* running_var, cudaStream_t st);
+// acc[0][i] += sum_b dY, acc[1][i] += sum_b dY * xhat   (gate: dY is ungated, apply [bn(U) > 0] here)
+void bn_bwd_reduce(const float* dY, const float* U, int B, int D, BnParams bn, double* acc, bool gate, cudaStream_t st);
 // dU = gamma rstd (dY - s1/B - xhat s2/B) in place over dY; also dgamma = s2, dbeta = s1.
 void bn_bwd_apply(float* dY_dU, const float* U, int B, int D, BnParams bn, const double* acc, float* dgamma,
-                  float* dbeta, cudaStream_t st);
+                  float* dbeta, bool gate, cudaStream_t st);
 void bn_grad_finalize(const double* acc, int D, float* dgamma, float* dbeta, cudaStream_t st);
 void bump_counters(int64_t* counters, int n, cudaStream_t st);
 

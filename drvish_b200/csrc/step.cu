@@ -122,6 +122,7 @@ struct Plan {
   size_t stat_acc[2][DRV_MAX_LAYERS + 1];   // [enc/dec][block]: double[2*din] forward statistics
   size_t grad_acc[2][DRV_MAX_LAYERS + 1];   // double[2*din] backward sums
   size_t status;                             // uint32
+  size_t ticket[2][DRV_MAX_LAYERS + 1];      // uint32 'last CTA' counters of the statistics kernels
   size_t mean[2][DRV_MAX_LAYERS + 1], rstd[2][DRV_MAX_LAYERS + 1];
   size_t V[2][DRV_MAX_LAYERS + 1];          // Linear outputs (B x dout); dec last = logits B x 2G
   size_t Gb[2][DRV_MAX_LAYERS + 1];         // dY / dU of each block input (B x din), block 0 of enc unused
@@ -143,6 +144,7 @@ Plan make_plan(const drv_dims& d, const Net& n) {
       const Block& b = s == 0 ? n.enc[k] : n.dec[k];
       p.stat_acc[s][k] = take(sizeof(double) * 2 * b.din);
       p.grad_acc[s][k] = take(sizeof(double) * 2 * b.din);
+      p.ticket[s][k] = take(256);
     }
   p.status = take(256);
   p.zero_bytes = o - p.zero_begin;
@@ -213,10 +215,9 @@ void block_forward(const Ctx& c, int s, int k, const float* U0, bool do_linear) 
   const float* U = k == 0 ? U0 : c.at<float>(c.p.V[s][k - 1]);
   const bool sq = (s == 0 && k == 0);
   double* acc = c.at<double>(c.p.stat_acc[s][k]);
-  colstats_accumulate(U, B, b.din, sq, acc, c.st);
-  colstats_finalize(acc, B, b.din, c.hp.bn_eps, c.hp.bn_momentum, c.at<float>(c.p.mean[s][k]),
-                    c.at<float>(c.p.rstd[s][k]), update ? c.bnbuf + b.rmean : nullptr,
-                    update ? c.bnbuf + b.rvar : nullptr, c.st);
+  colstats(U, B, b.din, sq, acc, c.at<unsigned int>(c.p.ticket[s][k]), c.hp.bn_eps, c.hp.bn_momentum,
+           c.at<float>(c.p.mean[s][k]), c.at<float>(c.p.rstd[s][k]), update ? c.bnbuf + b.rmean : nullptr,
+           update ? c.bnbuf + b.rvar : nullptr, c.st);
   if (!do_linear) return;
   if (c.p.tcb[s][k] && tc_block_forward_supported(B, b.din, b.dout, c.hp) && (sq ? !(c.hp.flags & 32) : !(c.hp.flags & 8))) {
     TcBlockArgs a{};
@@ -234,6 +235,7 @@ void block_forward(const Ctx& c, int s, int k, const float* U0, bool do_linear) 
 // produced (fused tcgen05 path).  The first encoder block needs no dU (x is data): its dY is
 // reduced to d gamma / d beta on the fly.
 void block_backward(const Ctx& c, int s, int k, const float* U0, const float* dV, bool linear_done) {
+  bool gated = true;  // false: Gb holds the ungated dAct and the BatchNorm backward applies the ReLU gate
   const int B = c.d.n_cells;
   const Block& b = s == 0 ? c.n.enc[k] : c.n.dec[k];
   const float* U = k == 0 ? U0 : c.at<float>(c.p.V[s][k - 1]);
@@ -248,6 +250,7 @@ void block_backward(const Ctx& c, int s, int k, const float* U0, const float* dV
       a.scratch = c.ws + c.p.tcb[s][k]; a.dV = dV; a.dW = c.grads + b.W; a.db = c.grads + b.bias;
       a.dY = sq ? nullptr : c.at<float>(c.p.Gb[s][k]); a.gacc = gacc; a.side = c.side;
       tc_block_backward(a, c.st);
+      gated = false;
     } else {
       // the weight gradient is off the critical chain: side stream
       cudaStream_t ws = c.st;
@@ -263,8 +266,9 @@ void block_backward(const Ctx& c, int s, int k, const float* U0, const float* dV
     bn_grad_finalize(gacc, b.din, c.grads + b.gamma, c.grads + b.beta, c.st);
   } else {
     float* dY = c.at<float>(c.p.Gb[s][k]);
-    bn_bwd_reduce(dY, U, B, b.din, c.bn(s, k), gacc, c.st);
-    bn_bwd_apply(dY, U, B, b.din, c.bn(s, k), gacc, c.grads + b.gamma, c.grads + b.beta, c.st);
+    if (linear_done) gated = false;  // fused decoder path: dAct arrives ungated
+    bn_bwd_reduce(dY, U, B, b.din, c.bn(s, k), gacc, !gated, c.st);
+    bn_bwd_apply(dY, U, B, b.din, c.bn(s, k), gacc, c.grads + b.gamma, c.grads + b.beta, !gated, c.st);
   }
 }
 

@@ -57,6 +57,27 @@ __global__ void k_round_rows(const float* __restrict__ src, size_t n, float* __r
     dst[i] = rna_tf32(src[i]);
 }
 
+__global__ void k_round_colsum(const float* __restrict__ V, int B, int D, int rows_per_cta, float* __restrict__ Vr,
+                               float* __restrict__ out) {
+  int col = blockIdx.x * 32 + threadIdx.x;
+  int r0 = blockIdx.y * rows_per_cta, r1 = min(B, r0 + rows_per_cta);
+  float s = 0.f;
+  if (col < D)
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      const float v = V[(size_t)r * D + col];
+      Vr[(size_t)r * D + col] = rna_tf32(v);
+      s += v;
+    }
+  __shared__ float sh[8][32];
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < D) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+    atomicAdd(&out[col], t);
+  }
+}
+
 __global__ void k_colsum_small(const float* __restrict__ V, int B, int D, int rows_per_cta, float* __restrict__ out) {
   // 32 columns x 8 row lanes per CTA, the batch split over gridDim.y; out must be zeroed
   int col = blockIdx.x * 32 + threadIdx.x;
@@ -225,14 +246,14 @@ void tc_block_backward(const TcBlockArgs& a, cudaStream_t st) {
   size_t nd = (size_t)a.B * a.dout;
   int rb = (int)((nd + 255) / 256);
   if (rb > n_sm() * 2) rb = n_sm() * 2;
-  k_round_rows<<<rb, 256, 0, st>>>(a.dV, nd, s.dh_r);
-  note_launch();
+  (void)rb;
   {
+    // one pass over dV: tf32-rounded copy (MMA operand) + column sums (bias gradient)
     dim3 cb(32, 8);
     int rows = 64;
     dim3 cgrid((a.dout + 31) / 32, (a.B + rows - 1) / rows);
     cudaMemsetAsync(a.db, 0, sizeof(float) * a.dout, st);
-    k_colsum_small<<<cgrid, cb, 0, st>>>(a.dV, a.B, a.dout, rows, a.db);
+    k_round_colsum<<<cgrid, cb, 0, st>>>(a.dV, a.B, a.dout, rows, s.dh_r, a.db);
     note_launch();
   }
   // dW[j][i] = sum_b dV[b][j] A[b][i]: both operands MN-major (K = cells)
@@ -245,14 +266,7 @@ void tc_block_backward(const TcBlockArgs& a, cudaStream_t st) {
   if (a.side) { a.side->attach(); ws = a.side->side; }
   if (rc == 0) rc = tc::gemm_tf32(s.dh_r, a.dout, true, s.a_hi, a.din, true, a.dW, a.din, a.dout, a.din, a.B, 0, false, ws);
   if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
-  if (a.dY) {
-    size_t n = (size_t)a.B * a.din;
-    int blocks = (int)((n + 255) / 256);
-    if (blocks > n_sm() * 8) blocks = n_sm() * 8;
-    k_gate_block<<<blocks, 256, 0, st>>>(a.dY, a.U, n, a.din, a.bn);
-    note_launch();
-    return;
-  }
+  if (a.dY) return;  // the ReLU gate is applied by the BatchNorm backward kernels
   // reduce dA to the input-BatchNorm gradients (gate and xhat recomputed from sqrt(x))
   int col_blocks = (a.din + CW * 4 - 1) / (CW * 4);
   int S = (n_sm() * 8 + col_blocks - 1) / col_blocks;

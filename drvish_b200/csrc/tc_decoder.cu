@@ -617,10 +617,7 @@ void tc_decoder_backward(const TcDecoderArgs& a, cudaStream_t st) {
   if (rc == 0) rc = gemm_tf32(a.dlogits, 2 * a.G, true, s.act, a.h, true, a.dW, a.h, 2 * a.G, a.h, a.B, 0, false, ws);
   drv_internal_kmark(4, 1, ws);
   if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
-  int blocks = (int)(((size_t)a.B * a.h + 255) / 256);
-  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  k_gate<<<blocks, 256, 0, st>>>(a.dY, a.U, a.B, a.h, a.bn);
-  note_launch();
+  // the ReLU gate of dAct is applied by the BatchNorm backward kernels (block_backward)
 }
 
 }  // namespace drv
