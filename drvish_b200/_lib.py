@@ -69,8 +69,9 @@ SYMBOLS = {
     "drv_profile_enable": (C.c_int, [C.c_int]),
     "drv_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "drv_profile_read_kernels": (C.c_int, [C.POINTER(C.c_float)]),
-    "drv_fill_normal": (C.c_int, [_P, C.c_int64, C.c_uint64, C.c_uint64, _P]),
-    "drv_fill_laplace": (C.c_int, [_P, C.c_int64, C.c_uint64, C.c_uint64, _P]),
+    "drv_fill_normal": (C.c_int, [_P, C.c_int64, C.c_uint64, C.c_uint64, _P, C.c_uint64, _P]),
+    "drv_fill_laplace": (C.c_int, [_P, C.c_int64, C.c_uint64, C.c_uint64, _P, C.c_uint64, _P]),
+    "drv_counter_add": (C.c_int, [_P, C.c_uint64, _P]),
 }
 
 _lib = None

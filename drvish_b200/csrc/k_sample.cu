@@ -108,10 +108,14 @@ __device__ __forceinline__ void philox4(uint64_t seed, uint64_t ctr, uint32_t (&
 
 __device__ __forceinline__ float u01(uint32_t v) { return ((float)(v >> 8) + 0.5f) * (1.0f / 16777216.0f); }  // (0,1)
 
+// The Philox counter is offset + step_counter[0] * stride: the step counter lives in device memory
+// so that a captured CUDA graph draws fresh noise on every replay.
 template <bool LAPLACE>
-__global__ void k_fill(float* __restrict__ out, int64_t n, uint64_t seed, uint64_t offset) {
+__global__ void k_fill(float* __restrict__ out, int64_t n, uint64_t seed, uint64_t offset,
+                       const unsigned long long* __restrict__ step_counter, uint64_t stride) {
   int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // quad index
   if (q * 4 >= n) return;
+  if (step_counter) offset += (uint64_t)(*step_counter) * stride;
   uint32_t r[4];
   philox4(seed, offset / 4 + (uint64_t)q, r);
   float v[4];
@@ -159,14 +163,22 @@ void encoder_outputs(const float* O, int B, int L, float* z_loc, float* z_scale,
   note_launch();
 }
 
-void fill_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, cudaStream_t st) {
+void fill_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, const unsigned long long* ctr, uint64_t stride,
+                 cudaStream_t st) {
   if (n <= 0) return;
-  k_fill<false><<<cdiv(cdiv(n, 4), 256), 256, 0, st>>>(out, n, seed, offset);
+  k_fill<false><<<cdiv(cdiv(n, 4), 256), 256, 0, st>>>(out, n, seed, offset, ctr, stride);
   note_launch();
 }
-void fill_laplace(float* out, int64_t n, uint64_t seed, uint64_t offset, cudaStream_t st) {
+void fill_laplace(float* out, int64_t n, uint64_t seed, uint64_t offset, const unsigned long long* ctr, uint64_t stride,
+                  cudaStream_t st) {
   if (n <= 0) return;
-  k_fill<true><<<cdiv(cdiv(n, 4), 256), 256, 0, st>>>(out, n, seed, offset);
+  k_fill<true><<<cdiv(cdiv(n, 4), 256), 256, 0, st>>>(out, n, seed, offset, ctr, stride);
+  note_launch();
+}
+
+__global__ void k_counter_add(unsigned long long* c, unsigned long long v) { *c += v; }
+void counter_add(unsigned long long* ctr, unsigned long long v, cudaStream_t st) {
+  k_counter_add<<<1, 1, 0, st>>>(ctr, v);
   note_launch();
 }
 

@@ -44,8 +44,11 @@ void sample_backward(const float* O, const float* eps_z, const float* eps_l, con
                      float* dO, cudaStream_t st);
 void encoder_outputs(const float* O, int B, int L, float* z_loc, float* z_scale, float* l_loc, float* l_scale,
                      cudaStream_t st);
-void fill_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, cudaStream_t st);
-void fill_laplace(float* out, int64_t n, uint64_t seed, uint64_t offset, cudaStream_t st);
+void fill_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, const unsigned long long* ctr, uint64_t stride,
+                 cudaStream_t st);
+void fill_laplace(float* out, int64_t n, uint64_t seed, uint64_t offset, const unsigned long long* ctr, uint64_t stride,
+                  cudaStream_t st);
+void counter_add(unsigned long long* ctr, unsigned long long v, cudaStream_t st);
 
 // ---- k_dr.cu: dose-response head ----------------------------------------------------------------
 struct DrShape {

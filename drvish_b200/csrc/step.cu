@@ -565,19 +565,29 @@ int drv_logit_mean_sigmoid(const drv_dims* dims, const float* z, const float* w,
   return finish();
 }
 
-int drv_fill_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
+int drv_fill_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, const uint64_t* step_counter, uint64_t stride,
+                    void* stream) {
   g_launches = 0;
   g_err = cudaSuccess;
   if (!out || n < 0) return DRV_EINVAL;
-  fill_normal(out, n, seed, offset, (cudaStream_t)stream);
+  fill_normal(out, n, seed, offset, (const unsigned long long*)step_counter, stride, (cudaStream_t)stream);
   return finish();
 }
 
-int drv_fill_laplace(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
+int drv_fill_laplace(float* out, int64_t n, uint64_t seed, uint64_t offset, const uint64_t* step_counter, uint64_t stride,
+                     void* stream) {
   g_launches = 0;
   g_err = cudaSuccess;
   if (!out || n < 0) return DRV_EINVAL;
-  fill_laplace(out, n, seed, offset, (cudaStream_t)stream);
+  fill_laplace(out, n, seed, offset, (const unsigned long long*)step_counter, stride, (cudaStream_t)stream);
+  return finish();
+}
+
+int drv_counter_add(uint64_t* counter, uint64_t v, void* stream) {
+  g_launches = 0;
+  g_err = cudaSuccess;
+  if (!counter) return DRV_EINVAL;
+  counter_add((unsigned long long*)counter, v, (cudaStream_t)stream);
   return finish();
 }
 

@@ -37,7 +37,8 @@ class FusedTraceELBO:
 
     def __init__(self, num_particles: int = 1, seed: int = 0, data_parallel: Optional[bool] = None,
                  process_group=None, include_guide_factor: bool = True, force_simt: bool = False,
-                 update_bn_stats: bool = True, extra_flags: int = 0, **_ignored):
+                 update_bn_stats: bool = True, extra_flags: int = 0, use_cuda_graph: bool = True,
+                 **_ignored):
         if num_particles != 1:
             raise NotImplementedError("the fused ELBO evaluates one particle (the reference notebook's setting)")
         self.seed = int(seed)
@@ -50,6 +51,10 @@ class FusedTraceELBO:
         self._explicit_noise = None
         self._noise_bufs = {}
         self.last_status = 0
+        self.use_cuda_graph = bool(use_cuda_graph)
+        self._graphs = {}
+        self._graph_seen = {}
+        self._step_ctr = None  # device uint64: steps taken (drives the Philox counters)
 
     # -- noise ------------------------------------------------------------------------------
     def set_noise(self, noise: Optional[dict]) -> None:
@@ -76,28 +81,34 @@ class FusedTraceELBO:
                 bufs.update(w_prior=torch.empty(D * L, device=dev), b_prior=torch.empty(T, device=dev),
                             eps_bias=torch.empty(T, device=dev))
             self._noise_bufs[key] = bufs
-        # production mode: Philox counters (seed, running offset); the draw order follows the
-        # reference (latent, library, then per-drug guide / prior draws - SURVEY 8b)
+        # production mode: Philox counters keyed by (seed, step, rank); the step index is read from a
+        # DEVICE counter so that a captured CUDA graph draws fresh noise on every replay.  The draw
+        # order follows the reference (latent, library, then per-drug guide / prior draws - SURVEY 8b)
         import ctypes as C
         from .runtime import _ptr, _stream
 
         lib, st = rt.lib, _stream(dev)
+        if self._step_ctr is None or self._step_ctr.device != dev:
+            self._step_ctr = torch.full((1,), self.step_index, dtype=torch.int64, device=dev)
+        ctr = _ptr(self._step_ctr)
         per_step = 4 * ((B * L + 3) // 4 + (B + 3) // 4 + (D * L + 3) // 4 + 2 * ((T + 3) // 4))
         rank = torch.distributed.get_rank() if self._dp_enabled() else 0
-        off = (self.step_index * 4096 + rank) * per_step
+        stride = C.c_uint64(4096 * per_step)
+        off = rank * per_step
         seed = C.c_uint64(self.seed)
-        _lib.check(lib.drv_fill_normal(_ptr(bufs["eps_z"]), B * L, seed, C.c_uint64(off), st), "drv_fill_normal")
+        _lib.check(lib.drv_fill_normal(_ptr(bufs["eps_z"]), B * L, seed, C.c_uint64(off), ctr, stride, st), "drv_fill_normal")
         off += 4 * ((B * L + 3) // 4)
-        _lib.check(lib.drv_fill_normal(_ptr(bufs["eps_l"]), B, seed, C.c_uint64(off), st), "drv_fill_normal")
+        _lib.check(lib.drv_fill_normal(_ptr(bufs["eps_l"]), B, seed, C.c_uint64(off), ctr, stride, st), "drv_fill_normal")
         off += 4 * ((B + 3) // 4)
         if D:
-            _lib.check(lib.drv_fill_laplace(_ptr(bufs["w_prior"]), D * L, seed, C.c_uint64(off), st), "drv_fill_laplace")
+            _lib.check(lib.drv_fill_laplace(_ptr(bufs["w_prior"]), D * L, seed, C.c_uint64(off), ctr, stride, st), "drv_fill_laplace")
             off += 4 * ((D * L + 3) // 4)
-            _lib.check(lib.drv_fill_normal(_ptr(bufs["b_prior"]), T, seed, C.c_uint64(off), st), "drv_fill_normal")
+            _lib.check(lib.drv_fill_normal(_ptr(bufs["b_prior"]), T, seed, C.c_uint64(off), ctr, stride, st), "drv_fill_normal")
             off += 4 * ((T + 3) // 4)
-            _lib.check(lib.drv_fill_normal(_ptr(bufs["eps_bias"]), T, seed, C.c_uint64(off), st), "drv_fill_normal")
+            _lib.check(lib.drv_fill_normal(_ptr(bufs["eps_bias"]), T, seed, C.c_uint64(off), ctr, stride, st), "drv_fill_normal")
             bufs["w_prior"].mul_(rt.lmbs[0].lam_scale)
             bufs["b_prior"].mul_(rt.lmbs[0].prior_bias_scale)
+        _lib.check(lib.drv_counter_add(ctr, C.c_uint64(1), st), "drv_counter_add")
         return bufs
 
     # -- helpers ----------------------------------------------------------------------------
@@ -119,12 +130,23 @@ class FusedTraceELBO:
             return model
         raise TypeError("FusedTraceELBO expects the bound model/guide methods of a drvish_b200 NBVAE or DRNBVAE")
 
-    @staticmethod
-    def _flatten_y(rt, y, dev):
+    def _flatten_y(self, rt, y, dev):
         if not rt.n_drugs:
             return None
         if torch.is_tensor(y):  # stacked (D, K, C, 1)
             y = list(y)
+        # the bulk dose-response target is the same object every batch (reference data/target.py:31-34):
+        # cache its flattened device copy (also keeps its address stable for CUDA-graph replay)
+        sig = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in y)
+        cached = getattr(self, "_y_cache", None)
+        if cached is not None and cached[0] == sig:
+            return cached[1]
+        flat = self._flatten_y_uncached(rt, y, dev)
+        self._y_cache = (sig, flat)
+        return flat
+
+    @staticmethod
+    def _flatten_y_uncached(rt, y, dev):
         K = rt.n_classes
         parts = []
         for i, t in enumerate(y):
@@ -142,8 +164,7 @@ class FusedTraceELBO:
         x = args[0]
         labels = args[1] if len(args) > 1 else None
         y = self._flatten_y(rt, args[2] if len(args) > 2 else None, rt.device)
-        noise = self._noise(rt, x.shape[0])
-        rt.elbo_step(x, labels, y, noise, want_grads, self.flags, self.include_guide_factor)
+        self._enqueue(rt, x, labels, y, want_grads)
         self.step_index += 1
         if want_grads and self._dp_enabled():
             # one all-reduce: gradients + the loss in the tail slot
@@ -158,6 +179,45 @@ class FusedTraceELBO:
         if want_grads:
             rt.attach_grads()
         return loss
+
+    def _enqueue(self, rt, x, labels, y, want_grads: bool) -> None:
+        """Noise draws + drv_elbo_step, either launched directly or replayed from a CUDA graph.
+
+        A graph is keyed by the device pointers it bakes in (x, labels, y, mode, batch size); it is
+        captured the second time a key is seen (the first call runs eagerly and warms up every
+        kernel variant), so a training loop that cycles through a few staging buffers - e.g.
+        PinnedBatchPrefetcher's two - replays ~70 kernel launches with one cudaGraphLaunch."""
+        def eager():
+            noise = self._noise(rt, x.shape[0])
+            rt.elbo_step(x, labels, y, noise, want_grads, self.flags, self.include_guide_factor)
+
+        if not self.use_cuda_graph or self._explicit_noise is not None or not x.is_cuda:
+            return eager()
+        key = (x.data_ptr(), tuple(x.shape), 0 if labels is None else labels.data_ptr(), 0 if y is None else y.data_ptr(),
+               want_grads, rt.flat_params.data_ptr())
+        g = self._graphs.get(key)
+        if g is not None:
+            g.replay()
+            return
+        seen = self._graph_seen.get(key, 0)
+        self._graph_seen[key] = seen + 1
+        if seen < 1 or len(self._graphs) >= 64:
+            if len(self._graph_seen) > 4096:
+                self._graph_seen.clear()
+            return eager()
+        torch.cuda.current_stream(rt.device).synchronize()
+        g = torch.cuda.CUDAGraph()
+        try:
+            with torch.cuda.graph(g):
+                eager()
+        except Exception:
+            self.use_cuda_graph = False  # capture unsupported here: stay on direct launches
+            torch.cuda.synchronize()
+            return eager()
+        # the graph bakes in raw pointers only; whatever tensor later lives at the same address with
+        # the same shape is what a replay reads, so no tensor needs to be kept alive here
+        self._graphs[key] = g
+        g.replay()
 
     # -- the two methods pyro.infer.SVI calls -----------------------------------------------------
     def loss(self, model, guide, *args, **kwargs) -> float:

@@ -130,9 +130,14 @@ int drv_logit_mean_sigmoid(const drv_dims* dims, const float* z, const float* w,
                            float* out, uint32_t* status,
                            void* workspace, size_t workspace_bytes, void* stream);
 
-/* Counter-based (Philox4x32-10) noise: out[i] ~ N(0,1) / Laplace(0,1), keyed by (seed, offset+i). */
-int drv_fill_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
-int drv_fill_laplace(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+/* Counter-based (Philox4x32-10) noise: out[i] ~ N(0,1) / Laplace(0,1), keyed by
+ * (seed, offset + step_counter[0]*stride + i).  step_counter (device, may be NULL) lets a captured
+ * CUDA graph draw fresh noise on every replay; drv_counter_add advances it on the stream. */
+int drv_fill_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, const uint64_t* step_counter, uint64_t stride,
+                    void* stream);
+int drv_fill_laplace(float* out, int64_t n, uint64_t seed, uint64_t offset, const uint64_t* step_counter, uint64_t stride,
+                     void* stream);
+int drv_counter_add(uint64_t* counter, uint64_t v, void* stream);
 
 /* Section timing with CUDA events recorded on the step's stream (bench.py's live roofline
  * measurement).  drv_profile_enable(1) arms it (up to 64 steps are kept); drv_profile_read

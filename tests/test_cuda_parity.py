@@ -130,13 +130,13 @@ def test_noise_generators_are_standard():
     n = 1 << 20
     out = torch.empty(n, device="cuda")
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    _lib.check(lib.drv_fill_normal(C.c_void_p(out.data_ptr()), n, C.c_uint64(7), C.c_uint64(0), st), "fill")
+    _lib.check(lib.drv_fill_normal(C.c_void_p(out.data_ptr()), n, C.c_uint64(7), C.c_uint64(0), None, C.c_uint64(0), st), "fill")
     assert abs(float(out.mean())) < 5e-3 and abs(float(out.var()) - 1) < 1e-2
     assert abs(float((out ** 4).mean()) - 3) < 0.1
     a = out.clone()
-    _lib.check(lib.drv_fill_normal(C.c_void_p(out.data_ptr()), n, C.c_uint64(7), C.c_uint64(0), st), "fill")
+    _lib.check(lib.drv_fill_normal(C.c_void_p(out.data_ptr()), n, C.c_uint64(7), C.c_uint64(0), None, C.c_uint64(0), st), "fill")
     assert torch.equal(a, out)  # counter-based: reproducible
-    _lib.check(lib.drv_fill_laplace(C.c_void_p(out.data_ptr()), n, C.c_uint64(7), C.c_uint64(4 * n), st), "fill")
+    _lib.check(lib.drv_fill_laplace(C.c_void_p(out.data_ptr()), n, C.c_uint64(7), C.c_uint64(4 * n), None, C.c_uint64(0), st), "fill")
     assert abs(float(out.mean())) < 5e-3 and abs(float(out.var()) - 2) < 3e-2
 
 
@@ -209,3 +209,25 @@ def test_production_noise_path_runs_and_is_seeded():
     assert abs(losses[0][0] - losses[0][1]) > 1e-5 * abs(losses[0][0])
     assert abs(losses[0][0] - losses[2][0]) > 1e-5 * abs(losses[0][0])
     assert all(torch.isfinite(torch.tensor(l)).all() for l in losses)
+
+
+def test_cuda_graph_replay_matches_direct_launches():
+    """The graph path (captured on the second use of a batch buffer, replayed afterwards) must give the
+    same losses and gradients as direct launches: the Philox step counter lives in device memory."""
+    import drvish_b200 as D
+
+    cfg = dict(n_input=256, n_latent=6, layers=[64, 64], batch=256, drugs=2, doses=4, classes=4)
+    case = P.make_case(cfg)
+    args = [case["x"].cuda(), case["labels"].cuda(), [t.cuda() for t in case["y"]]]
+    runs = {}
+    for graph in (False, True):
+        model = P.build_cuda_model(case, "cuda:0")
+        elbo = D.FusedTraceELBO(seed=11, data_parallel=False, use_cuda_graph=graph)
+        losses = [elbo.loss_and_grads(model.model, model.guide, *args) for _ in range(5)]
+        grad = model.decoder.fc[8].weight.grad.detach().clone()
+        runs[graph] = (losses, grad, len(elbo._graphs))
+    assert runs[True][2] == 1 and runs[False][2] == 0
+    for a, b in zip(runs[False][0], runs[True][0]):
+        assert abs(a - b) <= 1e-6 * abs(a), (runs[False][0], runs[True][0])
+    assert len(set(round(v, 3) for v in runs[True][0])) == 5  # fresh noise on every replay
+    assert P.rel_err(runs[True][1], runs[False][1]) <= 1e-5
