@@ -360,11 +360,23 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
   const int B = d.n_cells, G = d.n_genes, L = d.n_latent;
   const bool bwd = grads != nullptr;
 
+  uint32_t* status = c.at<uint32_t>(p.status);
+  const int NB = n.n_blocks;
+  // Two-part execution for data parallel (DRV_FLAG_STOP_AFTER_DECODER / DRV_FLAG_ENCODER_BACKWARD_ONLY):
+  // the caller starts the all-reduce of the decoder + dose-response gradient slice between the
+  // parts, so that it overlaps the encoder backward.
+  const bool part2_only = bwd && (hp->flags & DRV_FLAG_ENCODER_BACKWARD_ONLY);
+  const bool stop_after_decoder = bwd && (hp->flags & DRV_FLAG_STOP_AFTER_DECODER);
+  if (part2_only) {
+    for (int k = NB - 1; k >= 0; --k)
+      block_backward(c, 0, k, x, k == NB - 1 ? c.at<float>(p.dO) : c.at<float>(p.Gb[0][k + 1]), false);
+    if (side) side->join(st);
+    if (bn_batches && !(hp->flags & DRV_FLAG_NO_BN_UPDATE)) bump_counters(bn_batches, n.n_bn, st);
+    return finish();
+  }
+
   cudaMemsetAsync(c.ws + p.zero_begin, 0, p.zero_bytes, st);
   cudaMemsetAsync(out, 0, sizeof(drv_step_out), st);
-  uint32_t* status = c.at<uint32_t>(p.status);
-
-  const int NB = n.n_blocks;
   prof::mark(0, st);
   // ---- guide: encoder + reparameterised draws (nbvae.py:81-90) --------------------------------
   for (int k = 0; k < NB; ++k) block_forward(c, 0, k, x, true);
@@ -443,6 +455,13 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
     sample_backward(O, eps_z, eps_l, z, l, c.at<float>(p.Gb[1][0]), d.n_drugs > 0 ? c.at<float>(p.dz_drs) : nullptr,
                     c.at<float>(p.asum), B, L, *hp, c.at<float>(p.dO), st);
     prof::mark(6, st);
+    if (stop_after_decoder) {
+      // decoder / dose-response gradients and the loss are final: hand back to the caller
+      if (side) side->join(st);
+      cudaMemcpyAsync(&out->status, status, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
+      finalize_status(out, st);
+      return finish();
+    }
     // ---- encoder backward ----------------------------------------------------------------------
     for (int k = NB - 1; k >= 0; --k)
       block_backward(c, 0, k, x, k == NB - 1 ? c.at<float>(p.dO) : c.at<float>(p.Gb[0][k + 1]), false);

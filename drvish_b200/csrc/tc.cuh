@@ -37,7 +37,7 @@ int gemm_tf32(const float* A, int lda, bool a_mn, const float* Bm, int ldb, bool
               int K, int max_ctas, bool accumulate, cudaStream_t st);
 int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs, int lda, bool a_mn, int ldb, bool b_mn,
                     float* C, int ldc, int M, int N, int K, int max_ctas, bool accumulate, const float* bias,
-                    cudaStream_t st, int max_chain_kb = 0);
+                    cudaStream_t st, int max_chain_kb = 0, float* partials = nullptr, int max_parts = 0);
 }
 
 // One BatchNorm -> ReLU -> Linear block (reference modules.py:19-21) on the tensor cores: 3xTF32

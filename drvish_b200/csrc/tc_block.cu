@@ -171,8 +171,10 @@ __global__ void k_gate_block(float* __restrict__ dact, const float* __restrict__
   }
 }
 
+constexpr int kMaxParts = 16;
+
 struct Scratch {
-  float *a_hi, *a_lo, *w_hi, *w_lo, *dh_r;
+  float *a_hi, *a_lo, *w_hi, *w_lo, *dh_r, *parts;
   size_t total;
 };
 
@@ -182,6 +184,7 @@ Scratch carve(void* base, int B, int G, int h) {
   auto take = [&](size_t bytes) { size_t r = o; o = (o + bytes + 255) / 256 * 256; return r; };
   size_t ah = take(4 * (size_t)B * G), al = take(4 * (size_t)B * G);
   size_t wh = take(4 * (size_t)h * G), wl = take(4 * (size_t)h * G), dh = take(4 * (size_t)B * h);
+  size_t pt = take(4 * (size_t)B * h * kMaxParts);  // per-k-part slabs of the deterministic forward GEMM
   s.total = o;
   if (base) {
     char* c = (char*)base;
@@ -190,6 +193,7 @@ Scratch carve(void* base, int B, int G, int h) {
     s.w_hi = (float*)(c + wh);
     s.w_lo = (float*)(c + wl);
     s.dh_r = (float*)(c + dh);
+    s.parts = (float*)(c + pt);
   }
   return s;
 }
@@ -236,7 +240,7 @@ void tc_block_forward(const TcBlockArgs& a, cudaStream_t st) {
   const float* As[3] = {s.a_lo, s.a_hi, s.a_hi};
   const float* Bs[3] = {s.w_hi, s.w_lo, s.w_hi};
   int rc = tc::gemm_tf32_multi(3, As, Bs, a.din, false, a.din, false, a.V, a.dout, a.B, a.dout, a.din, 0, false, a.bias, st,
-                               /*max_chain_kb=*/32);
+                               /*max_chain_kb=*/32, s.parts, kMaxParts);
   if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
 }
 

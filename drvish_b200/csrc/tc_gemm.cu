@@ -68,7 +68,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
           const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, int n_pairs,
           float* __restrict__ C, int ldc, int M, int N, int K, int n_tile, int splits, int force_atomic,
-          const float* __restrict__ bias, int mn_lbo, int mn_sbo, int mn_kstep) {
+          const float* __restrict__ bias, long long part_stride, int mn_lbo, int mn_sbo, int mn_kstep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
@@ -176,7 +176,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const int tile = ch / splits, part = ch % splits;
       const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * n_tile;
       const bool whole = !force_atomic;
-      const bool add_bias = bias != nullptr && part == 0;
+      const bool add_bias = bias != nullptr && part == 0 && part_stride == 0;
       const int as = seg & 1, aph = (seg >> 1) & 1;
       const int m = m0 + q * 32 + lane;
       mbar_wait(&acc_full[as], aph);
@@ -187,7 +187,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         tmem_ld16(tb + (uint32_t)c, v);
         tmem_ld_wait();
         if (m < M) {
-          float* dst = C + (size_t)m * ldc + n0 + c;
+          // part_stride != 0: deterministic split - every k-part stores into its own slab
+          float* dst = C + (size_t)part * part_stride + (size_t)m * ldc + n0 + c;
           if (add_bias) {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
@@ -226,6 +227,31 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
 }  // namespace
 
+// C[m][n] = bias[n] + sum_p partials[p][m][n], parts added in index order (deterministic)
+__global__ void k_reduce_parts(const float* __restrict__ parts, int n_parts, size_t mn, int N, const float* __restrict__ bias,
+                               float* __restrict__ C, int ldc) {
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < mn; i += (size_t)gridDim.x * blockDim.x * 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool vec = (N % 4 == 0) && (i + 4 <= mn);
+    for (int p = 0; p < n_parts; ++p) {
+      const float* src = parts + (size_t)p * mn + i;
+      if (vec) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(src));
+        acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+      } else {
+        for (int j = 0; j < 4; ++j)
+          if (i + j < mn) acc[j] += src[j];
+      }
+    }
+    for (int j = 0; j < 4; ++j) {
+      const size_t e = i + j;
+      if (e >= mn) break;
+      const size_t m = e / N, n = e % N;
+      C[m * ldc + n] = acc[j] + (bias ? bias[n] : 0.f);
+    }
+  }
+}
+
 static int n_sm_tc() {
   static int n = 0;
   if (!n) {
@@ -244,7 +270,7 @@ static int n_sm_tc() {
 // first when stream-K splits a tile over several CTAs).  max_ctas <= 0: one CTA per SM.
 int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs, int lda, bool a_mn, int ldb, bool b_mn,
                     float* C, int ldc, int M, int N, int K, int max_ctas, bool accumulate, const float* bias,
-                    cudaStream_t st, int max_chain_kb) {
+                    cudaStream_t st, int max_chain_kb, float* partials, int max_parts) {
   if (n_pairs < 1 || n_pairs > 3) return -3;
   CUtensorMap ta[3], tb[3];
   const int nq = b_mn ? 32 : 16;  // an MN-major B is staged in 32-column boxes
@@ -281,9 +307,33 @@ int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs,
   // length of the accumulation chain (measured ~5e-9 relative per MMA step).  GEMMs that feed a
   // BatchNorm -> ReLU directly cap the chain; the partial tiles are combined by fp32 red.add (RN).
   if (max_chain_kb > 0 && (kb_total + splits - 1) / splits > max_chain_kb) splits = (kb_total + max_chain_kb - 1) / max_chain_kb;
+  // Deterministic mode (forward GEMMs: their results decide ReLU gates, so they must not depend on
+  // the order of atomics): every k-part is stored to its own slab of `partials` and the slabs are
+  // summed in a fixed order by k_reduce_parts.
+  const bool deterministic = partials != nullptr && !accumulate;
+  if (deterministic && splits > max_parts) splits = max_parts;
   const long long chunks = tiles * splits;
   int grid = (int)(chunks < sms ? chunks : sms);
   const bool split = splits > 1;
+  if (deterministic && split) {
+    auto launch = [&](auto kern) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+      kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(ta[0], tb[0], ta[1], tb[1], ta[2], tb[2], n_pairs, partials, N, M, N, K,
+                                               n_tile, splits, 0, nullptr, (long long)M * N, g_mn_lbo, g_mn_sbo,
+                                               g_mn_kstep);
+    };
+    if (a_mn && b_mn) launch(k_tc_gemm<true, true>);
+    else if (a_mn) launch(k_tc_gemm<true, false>);
+    else if (b_mn) launch(k_tc_gemm<false, true>);
+    else launch(k_tc_gemm<false, false>);
+    note_launch();
+    const size_t n4 = ((size_t)M * N + 3) / 4;
+    int blocks = (int)((n4 + 255) / 256);
+    if (blocks > n_sm_tc() * 8) blocks = n_sm_tc() * 8;
+    k_reduce_parts<<<blocks, 256, 0, st>>>(partials, splits, (size_t)M * N, N, bias, C, ldc);
+    note_launch();
+    return 0;
+  }
   if (split && !accumulate) {
     if (ldc == N) cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st);
     else cudaMemset2DAsync(C, sizeof(float) * (size_t)ldc, 0, sizeof(float) * (size_t)N, (size_t)M, st);
@@ -292,7 +342,7 @@ int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs,
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(ta[0], tb[0], ta[1], tb[1], ta[2], tb[2], n_pairs, C, ldc, M, N, K, n_tile,
-                                             splits, force_atomic, bias, g_mn_lbo, g_mn_sbo, g_mn_kstep);
+                                             splits, force_atomic, bias, 0LL, g_mn_lbo, g_mn_sbo, g_mn_kstep);
   };
   if (a_mn && b_mn) launch(k_tc_gemm<true, true>);
   else if (a_mn) launch(k_tc_gemm<true, false>);
@@ -304,7 +354,8 @@ int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs,
 
 int gemm_tf32(const float* A, int lda, bool a_mn, const float* Bm, int ldb, bool b_mn, float* C, int ldc, int M, int N,
               int K, int max_ctas, bool accumulate, cudaStream_t st) {
-  return gemm_tf32_multi(1, &A, &Bm, lda, a_mn, ldb, b_mn, C, ldc, M, N, K, max_ctas, accumulate, nullptr, st, 0);
+  return gemm_tf32_multi(1, &A, &Bm, lda, a_mn, ldb, b_mn, C, ldc, M, N, K, max_ctas, accumulate, nullptr, st, 0, nullptr,
+                         0);
 }
 
 }  // namespace tc

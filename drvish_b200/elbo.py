@@ -62,7 +62,7 @@ class FusedTraceELBO:
         lists ``w_prior`` (L,1), ``b_prior`` (C_i,1), ``eps_bias`` (C_i,1)) instead of drawing."""
         self._explicit_noise = noise
 
-    def _noise(self, rt, B: int) -> dict:
+    def _noise(self, rt, B: int, draw: bool = True) -> dict:
         dev = rt.device
         if self._explicit_noise is not None:
             n = self._explicit_noise
@@ -81,6 +81,8 @@ class FusedTraceELBO:
                 bufs.update(w_prior=torch.empty(D * L, device=dev), b_prior=torch.empty(T, device=dev),
                             eps_bias=torch.empty(T, device=dev))
             self._noise_bufs[key] = bufs
+        if not draw:
+            return bufs  # second part of a two-part step: same draws
         # production mode: Philox counters keyed by (seed, step, rank); the step index is read from a
         # DEVICE counter so that a captured CUDA graph draws fresh noise on every replay.  The draw
         # order follows the reference (latent, library, then per-drug guide / prior draws - SURVEY 8b)
@@ -164,11 +166,23 @@ class FusedTraceELBO:
         x = args[0]
         labels = args[1] if len(args) > 1 else None
         y = self._flatten_y(rt, args[2] if len(args) > 2 else None, rt.device)
-        self._enqueue(rt, x, labels, y, want_grads)
-        self.step_index += 1
         if want_grads and self._dp_enabled():
-            # one all-reduce: gradients + the loss in the tail slot
-            allreduce_grads_and_loss(rt.flat_grads, rt.n_param_floats, rt._out[0], self.process_group)
+            # two-part step: the all-reduce of the decoder + dose-response slice (incl. the loss in the
+            # tail slot) runs on NCCL's stream while the encoder backward is still computing
+            self._enqueue(rt, x, labels, y, True, part=1)
+            rt.flat_grads[rt.n_param_floats] = rt._out[0].to(torch.float32)
+            tail = rt.flat_grads[rt.decoder_offset:]
+            w1 = torch.distributed.all_reduce(tail, op=torch.distributed.ReduceOp.SUM, group=self.process_group,
+                                              async_op=True)
+            self._enqueue(rt, x, labels, y, True, part=2)
+            head = rt.flat_grads[:rt.decoder_offset]
+            w2 = torch.distributed.all_reduce(head, op=torch.distributed.ReduceOp.SUM, group=self.process_group,
+                                              async_op=True)
+            w1.wait()
+            w2.wait()
+        else:
+            self._enqueue(rt, x, labels, y, want_grads)
+        self.step_index += 1
         loss, status = rt.read_out()
         self.last_status = status
         if status & (_lib.DRV_STATUS_MISSING_CLASS | _lib.DRV_STATUS_BAD_LABEL):
@@ -180,21 +194,24 @@ class FusedTraceELBO:
             rt.attach_grads()
         return loss
 
-    def _enqueue(self, rt, x, labels, y, want_grads: bool) -> None:
+    def _enqueue(self, rt, x, labels, y, want_grads: bool, part: int = 0) -> None:
         """Noise draws + drv_elbo_step, either launched directly or replayed from a CUDA graph.
 
         A graph is keyed by the device pointers it bakes in (x, labels, y, mode, batch size); it is
         captured the second time a key is seen (the first call runs eagerly and warms up every
         kernel variant), so a training loop that cycles through a few staging buffers - e.g.
         PinnedBatchPrefetcher's two - replays ~70 kernel launches with one cudaGraphLaunch."""
+        pflags = {0: 0, 1: _lib.DRV_FLAG_STOP_AFTER_DECODER, 2: _lib.DRV_FLAG_ENCODER_BACKWARD_ONLY}[part]
+
         def eager():
-            noise = self._noise(rt, x.shape[0])
-            rt.elbo_step(x, labels, y, noise, want_grads, self.flags, self.include_guide_factor)
+            # part 2 continues the step of part 1: same noise buffers, no new draws
+            noise = self._noise(rt, x.shape[0], draw=(part != 2))
+            rt.elbo_step(x, labels, y, noise, want_grads, self.flags | pflags, self.include_guide_factor)
 
         if not self.use_cuda_graph or self._explicit_noise is not None or not x.is_cuda:
             return eager()
         key = (x.data_ptr(), tuple(x.shape), 0 if labels is None else labels.data_ptr(), 0 if y is None else y.data_ptr(),
-               want_grads, rt.flat_params.data_ptr())
+               want_grads, rt.flat_params.data_ptr(), part)
         g = self._graphs.get(key)
         if g is not None:
             g.replay()

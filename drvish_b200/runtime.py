@@ -156,6 +156,9 @@ class ModelRuntime:
                 off += k
         self.flat_params, self.flat_grads = flat, gflat
         self.n_param_floats = total.value
+        # float offset of the first decoder tensor: [decoder_offset:] is the slice whose gradients are
+        # final before the encoder backward starts (decoder + dose-response head + loss slot)
+        self.decoder_offset = int(offs[4 * (len(self.layers) + 1)])
         # BatchNorm buffers
         bns = self._bn_modules()
         nb = 2 * len(bns)

@@ -72,6 +72,11 @@ typedef struct drv_hparams {
 
 #define DRV_FLAG_FORCE_SIMT 1   /* never take the tcgen05/TMA kernels (debug / A-B parity) */
 #define DRV_FLAG_NO_BN_UPDATE 2 /* do not touch running_mean/var (gradient checks) */
+/* bits 4..64 are debug switches (force single kernels onto the CUDA-core path, no side stream) */
+#define DRV_FLAG_STOP_AFTER_DECODER 128     /* part 1 of 2: return once the decoder, dose-response and latent
+                                               gradients and the loss are final (data-parallel overlap) */
+#define DRV_FLAG_ENCODER_BACKWARD_ONLY 256  /* part 2 of 2: encoder backward of the step started by part 1
+                                               (same arguments, same workspace) */
 
 /* Results of one step: one 16-byte device record, read back with a single D2H copy. */
 typedef struct drv_step_out {

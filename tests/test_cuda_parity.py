@@ -231,3 +231,47 @@ def test_cuda_graph_replay_matches_direct_launches():
         assert abs(a - b) <= 1e-6 * abs(a), (runs[False][0], runs[True][0])
     assert len(set(round(v, 3) for v in runs[True][0])) == 5  # fresh noise on every replay
     assert P.rel_err(runs[True][1], runs[False][1]) <= 1e-5
+
+
+def test_two_part_step_equals_single_call():
+    """DRV_FLAG_STOP_AFTER_DECODER + DRV_FLAG_ENCODER_BACKWARD_ONLY (used to overlap the data-parallel
+    all-reduce with the encoder backward) give the same loss and gradients as one call."""
+    import drvish_b200 as D
+
+    cfg = dict(n_input=512, n_latent=8, layers=[64, 64], batch=512, drugs=2, doses=4, classes=4)
+    case = P.make_case(cfg)
+    loss_ref, g_ref, _ = P.cuda_step(case)
+    model = P.build_cuda_model(case, "cuda:0")
+    elbo = D.FusedTraceELBO(data_parallel=False)
+    elbo.set_noise(case["noise"])
+    rt = model._runtime()
+    rt.ensure_flat()
+    x, labels = case["x"].cuda(), case["labels"].cuda()
+    y = elbo._flatten_y(rt, [t.cuda() for t in case["y"]], rt.device)
+    elbo._enqueue(rt, x, labels, y, True, part=1)
+    loss1, status = rt.read_out()
+    dec = rt.flat_grads[rt.decoder_offset:rt.n_param_floats].clone()
+    elbo._enqueue(rt, x, labels, y, True, part=2)
+    torch.cuda.synchronize()
+    rt.attach_grads()
+    assert abs(loss1 - loss_ref) <= 1e-6 * abs(loss_ref) and status == 0
+    # the decoder slice was already final after part 1
+    assert torch.equal(dec, rt.flat_grads[rt.decoder_offset:rt.n_param_floats])
+    zero = P.zero_grad_biases(2)
+    for n, p in model.named_parameters():
+        if n in zero or g_ref[n] is None or float(g_ref[n].norm()) == 0:
+            continue
+        assert P.rel_err(p.grad.double().cpu(), g_ref[n]) <= GRAD_TOL, n  # two runs: atomics order differs
+
+
+def test_forward_is_run_to_run_deterministic():
+    """Forward GEMMs reduce their k-parts in a fixed order (no atomics): a repeated step must not flip
+    ReLU gates, i.e. loss and gradients repeat to rounding-of-atomic-sums accuracy."""
+    cfg = dict(n_input=512, n_latent=8, layers=[64, 64], batch=512, drugs=2, doses=4, classes=4)
+    case = P.make_case(cfg)
+    l1, g1, _ = P.cuda_step(case)
+    for _ in range(3):
+        l2, g2, _ = P.cuda_step(case)
+        assert abs(l1 - l2) <= 1e-7 * abs(l1)
+        for k in ("decoder.fc.3.bias", "decoder.fc.2.weight", "encoder.fc.0.weight", "encoder.fc.3.weight"):
+            assert P.rel_err(g2[k], g1[k]) <= 2e-5, (k, P.rel_err(g2[k], g1[k]))
