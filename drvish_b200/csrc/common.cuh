@@ -62,6 +62,15 @@ struct BnParams {
   const float* beta;   // BatchNorm bias
 };
 
+// sqrt of a count (encoder input transform, modules.py:56).  MUFU.SQRT (<= 1 ulp): the IEEE sqrtf
+// takes a slow fix-up path for x = 0 - about half of all scRNA counts - which ncu showed to dominate
+// otherwise memory-bound kernels.  Used everywhere so that forward values and recomputed gates agree.
+__device__ __forceinline__ float sqrt_count(float v) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+
 __device__ __forceinline__ float bn_xhat(float u, float mean, float rstd) { return (u - mean) * rstd; }
 __device__ __forceinline__ float bn_y(float xhat, float gamma, float beta) { return __fmaf_rn(xhat, gamma, beta); }
 __device__ __forceinline__ float bn_relu(float u, float mean, float rstd, float gamma, float beta) {

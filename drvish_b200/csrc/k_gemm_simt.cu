@@ -22,7 +22,7 @@ struct Prologue {
 
 __device__ __forceinline__ float apply_pro(const Prologue& p, float u, int col) {
   if (p.mode == 0) return u;
-  if (p.mode == 2) u = sqrtf(u);
+  if (p.mode == 2) u = sqrt_count(u);
   return bn_relu(u, p.bn.mean[col], p.bn.rstd[col], p.bn.gamma[col], p.bn.beta[col]);
 }
 
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(NT) k_gemm(const float* __restrict__ A, int ld
           int gm = m0 + ty * 4 + i;
           if (gm < M) {
             float u = ep.U[(size_t)gm * ep.ldu + gn];
-            if (ep.gate.mode == 2) u = sqrtf(u);
+            if (ep.gate.mode == 2) u = sqrt_count(u);
             float xh = bn_xhat(u, mean, rstd);
             if (bn_y(xh, g, be) > 0.f) {
               s1 += acc[i][j];
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(NT) k_gemm(const float* __restrict__ A, int ld
         else *dst = v;
       } else if (EPI == EPI_GATE) {
         float u = ep.U[(size_t)gm * ep.ldu + gn];
-        if (ep.gate.mode == 2) u = sqrtf(u);
+        if (ep.gate.mode == 2) u = sqrt_count(u);
         float y = bn_y(bn_xhat(u, ep.gate.bn.mean[gn], ep.gate.bn.rstd[gn]), ep.gate.bn.gamma[gn], ep.gate.bn.beta[gn]);
         C[(size_t)gm * ldc + gn] = y > 0.f ? v : 0.f;
       }

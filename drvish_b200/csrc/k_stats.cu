@@ -72,13 +72,13 @@ __global__ void __launch_bounds__(CW* RY) k_colstats(const float* __restrict__ U
     for (; r + 3 * RY < r1; r += 4 * RY) {
       float v0 = U[(size_t)r * D + col], v1 = U[(size_t)(r + RY) * D + col];
       float v2 = U[(size_t)(r + 2 * RY) * D + col], v3 = U[(size_t)(r + 3 * RY) * D + col];
-      if (SQRT) { v0 = sqrtf(v0); v1 = sqrtf(v1); v2 = sqrtf(v2); v3 = sqrtf(v3); }
+      if (SQRT) { v0 = sqrt_count(v0); v1 = sqrt_count(v1); v2 = sqrt_count(v2); v3 = sqrt_count(v3); }
       s += (double)v0 + (double)v1 + (double)v2 + (double)v3;
       ss += (double)v0 * v0 + (double)v1 * v1 + (double)v2 * v2 + (double)v3 * v3;
     }
     for (; r < r1; r += RY) {
       float v = U[(size_t)r * D + col];
-      if (SQRT) v = sqrtf(v);
+      if (SQRT) v = sqrt_count(v);
       s += v;
       ss += (double)v * v;
     }
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(CW* RY) k_colstats4(const float* __restrict__ 
         float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          if (SQRT) v[j] = sqrtf(v[j]);
+          if (SQRT) v[j] = sqrt_count(v[j]);
           ps[j & 3] += v[j];
           pss[j & 3] = __fmaf_rn(v[j], v[j], pss[j & 3]);
         }
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(CW* RY) k_colstats4(const float* __restrict__ 
         float v[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          if (SQRT) v[j] = sqrtf(v[j]);
+          if (SQRT) v[j] = sqrt_count(v[j]);
           ps[j] += v[j];
           pss[j] = __fmaf_rn(v[j], v[j], pss[j]);
         }

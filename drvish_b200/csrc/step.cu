@@ -223,6 +223,7 @@ void block_forward(const Ctx& c, int s, int k, const float* U0, bool do_linear) 
     TcBlockArgs a{};
     a.U = U; a.sqrt_in = sq; a.bn = c.bn(s, k); a.W = c.params + b.W; a.bias = c.params + b.bias;
     a.B = B; a.din = b.din; a.dout = b.dout; a.V = c.at<float>(c.p.V[s][k]); a.scratch = c.ws + c.p.tcb[s][k];
+    a.no_fused_prologue = (c.hp.flags & 512) != 0;
     tc_block_forward(a, c.st);
   } else {
     simt_linear_forward(U, B, b.din, sq ? 2 : 1, c.bn(s, k), c.params + b.W, c.params + b.bias, b.dout,

@@ -35,6 +35,11 @@ namespace drv {
 namespace tc {
 int gemm_tf32(const float* A, int lda, bool a_mn, const float* Bm, int ldb, bool b_mn, float* C, int ldc, int M, int N,
               int K, int max_ctas, bool accumulate, cudaStream_t st);
+void reduce_parts(const float* parts, int n_parts, int M, int N, const float* bias, float* C, int ldc, cudaStream_t st);
+// Encoder-input Linear forward with the sqrt / BatchNorm / ReLU / hi-lo split prologue fused into the
+// GEMM (tc_encfwd.cu).  Writes V = relu(bn(sqrt(x))) W^T + b and the tf32 'hi' part of the activations.
+int encfwd_fused(const float* x, int B, int G, BnParams bn, const float* w_hi, const float* w_lo, int h,
+                 const float* bias, float* V, float* a_hi, float* partials, int max_parts, cudaStream_t st);
 int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs, int lda, bool a_mn, int ldb, bool b_mn,
                     float* C, int ldc, int M, int N, int K, int max_ctas, bool accumulate, const float* bias,
                     cudaStream_t st, int max_chain_kb = 0, float* partials = nullptr, int max_parts = 0);
@@ -46,6 +51,7 @@ int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs,
 struct TcBlockArgs {
   const float* U;     // [B][din] block input (x for the first encoder block)
   bool sqrt_in;       // apply sqrt before the BatchNorm (encoder input, modules.py:56)
+  bool no_fused_prologue;  // debug: materialise A_hi / A_lo instead of the fused-prologue kernel
   BnParams bn;        // statistics / affine of the block's BatchNorm
   const float* W;     // [dout][din]
   const float* bias;  // [dout]

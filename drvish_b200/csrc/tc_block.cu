@@ -34,7 +34,7 @@ __global__ void k_enc_prep(const float* __restrict__ x, size_t n, int G, BnParam
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int c = col + j;
-      float a = bn_relu(SQRT ? sqrtf(in[j]) : in[j], bn.mean[c], bn.rstd[c], bn.gamma[c], bn.beta[c]);
+      float a = bn_relu(SQRT ? sqrt_count(in[j]) : in[j], bn.mean[c], bn.rstd[c], bn.gamma[c], bn.beta[c]);
       h[j] = rna_tf32(a);
       l[j] = rna_tf32(a - h[j]);
     }
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(CW* RY) k_bn0_grad(const float* __restrict__ d
       for (int u = 0; u < 2; ++u)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float xh = bn_xhat(sqrtf(xs[u][j]), mv[j], rv[j]);
+          const float xh = bn_xhat(sqrt_count(xs[u][j]), mv[j], rv[j]);
           if (bn_y(xh, gv[j], bv[j]) > 0.f) {
             s1[j] += ds[u][j];
             s2[j] = __fmaf_rn(ds[u][j], xh, s2[j]);
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(CW* RY) k_bn0_grad(const float* __restrict__ d
       const float xs[4] = {xa.x, xa.y, xa.z, xa.w}, ds[4] = {da.x, da.y, da.z, da.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float xh = bn_xhat(sqrtf(xs[j]), mv[j], rv[j]);
+        const float xh = bn_xhat(sqrt_count(xs[j]), mv[j], rv[j]);
         if (bn_y(xh, gv[j], bv[j]) > 0.f) {
           s1[j] += ds[j];
           s2[j] = __fmaf_rn(ds[j], xh, s2[j]);
@@ -227,15 +227,21 @@ bool tc_block_backward_supported(int B, int din, int dout, const drv_hparams& hp
 void tc_block_forward(const TcBlockArgs& a, cudaStream_t st) {
   Scratch s = carve(a.scratch, a.B, a.din, a.dout);
   const size_t n = (size_t)a.B * a.din;
-  int blocks = (int)((n / 4 + 255) / 256);
-  if (blocks > n_sm() * 8) blocks = n_sm() * 8;
-  if (a.sqrt_in) k_enc_prep<true><<<blocks, 256, 0, st>>>(a.U, n, a.din, a.bn, s.a_hi, s.a_lo);
-  else k_enc_prep<false><<<blocks, 256, 0, st>>>(a.U, n, a.din, a.bn, s.a_hi, s.a_lo);
-  note_launch();
   size_t nw = (size_t)a.dout * a.din;
   int wb = (int)((nw + 255) / 256);
   if (wb > n_sm() * 4) wb = n_sm() * 4;
   k_split_tf32<<<wb, 256, 0, st>>>(a.W, nw, s.w_hi, s.w_lo);
+  note_launch();
+  if (a.sqrt_in && !a.no_fused_prologue) {
+    // encoder input layer: sqrt / BatchNorm / ReLU / hi-lo split fused into the GEMM's producer side
+    int rc = tc::encfwd_fused(a.U, a.B, a.din, a.bn, s.w_hi, s.w_lo, a.dout, a.bias, a.V, s.a_hi, s.parts, kMaxParts, st);
+    if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
+    return;
+  }
+  int blocks = (int)((n / 4 + 255) / 256);
+  if (blocks > n_sm() * 8) blocks = n_sm() * 8;
+  if (a.sqrt_in) k_enc_prep<true><<<blocks, 256, 0, st>>>(a.U, n, a.din, a.bn, s.a_hi, s.a_lo);
+  else k_enc_prep<false><<<blocks, 256, 0, st>>>(a.U, n, a.din, a.bn, s.a_hi, s.a_lo);
   note_launch();
   const float* As[3] = {s.a_lo, s.a_hi, s.a_hi};
   const float* Bs[3] = {s.w_hi, s.w_lo, s.w_hi};

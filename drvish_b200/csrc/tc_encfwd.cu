@@ -1,0 +1,309 @@
+// Encoder input layer forward with the prologue fused into the tensor-core GEMM:
+//   V = relu(bn(sqrt(x))) W^T + b        (reference Encoder.forward modules.py:56, make_fc :19-21)
+// The count tile is TMA-loaded ONCE, transformed in shared memory by 4 "transform" warps (sqrt,
+// BatchNorm, ReLU, split into tf32 hi + lo parts at the very same swizzled offsets, so no layout
+// knowledge is needed), and consumed by three MMAs per k-step (3xTF32: A_lo W_hi + A_hi W_lo +
+// A_hi W_hi).  The hi tile is also written back to HBM by a TMA store: it is
+// the B operand of the weight-gradient GEMM in the backward.  Compared with materialising A_hi /
+// A_lo first (prep kernel + 3 operand passes) this removes 2/3 of the HBM traffic of the layer.
+//
+// Warp roles (10 warps): 0 TMA producer, 1 TMEM alloc + MMA issuer, 2-5 transform, 6-9 epilogue.
+// Pipeline barriers per stage: full (TMA landed) -> ready (tile transformed, async-proxy fenced)
+// -> empty (MMAs retired AND the hi-tile store has finished reading the stage).
+// Work = (cell tile, k-part) chunks; every k-part is stored to its own slab and the slabs are
+// summed in fixed order (deterministic; accumulation chains <= 32 k-blocks).
+#include "kernels.cuh"
+#include "tc.cuh"
+#include "tc_common.cuh"
+
+namespace drv {
+namespace tc {
+
+namespace {
+
+constexpr int BM = 128, BK = 32, BN = 256;
+constexpr int NST = 2;
+constexpr int X_BYTES = BM * BK * 4;        // 16 KB count tile -> becomes the hi tile in place
+constexpr int W_BYTES = BN * BK * 4;        // 32 KB
+constexpr int STAGE = 2 * X_BYTES + 2 * W_BYTES;  // x/hi, lo, W_hi, W_lo = 96 KB
+constexpr int SMEM_BYTES = NST * STAGE + 1024 + 256;
+constexpr int NTHREADS = 320;
+constexpr int TMEM_COLS = 512;
+
+__device__ __forceinline__ float rna_tf32_(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWhi,
+         const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CUtensorMap tmAhi, BnParams bn, int B, int G,
+         int h, int n_tile, int splits, float* __restrict__ out, long long part_stride, const float* __restrict__ bias) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + NST * STAGE);
+  uint64_t* ready = full + NST;
+  uint64_t* empty = ready + NST;
+  uint64_t* acc_full = empty + NST;   // [2]
+  uint64_t* acc_empty = acc_full + 2; // [2]
+  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int kb_total = (G + BK - 1) / BK;
+  const int m_tiles = (B + BM - 1) / BM, n_tiles = (h + n_tile - 1) / n_tile;
+  const long long chunks = (long long)m_tiles * n_tiles * splits;
+  const int c0 = (int)(chunks * blockIdx.x / gridDim.x);
+  const int c1 = (int)(chunks * (blockIdx.x + 1) / gridDim.x);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmWhi);
+    tma_prefetch_desc(&tmWlo);
+    tma_prefetch_desc(&tmAhi);
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&ready[s], 4);   // one arrival per transform warp
+      mbar_init(&empty[s], 2);   // tcgen05.commit + hi-tile store drained
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto chunk_range = [&](int ch, int& tile, int& part, int& kb_b, int& kb_e) {
+    tile = ch / splits;
+    part = ch % splits;
+    kb_b = (int)((long long)kb_total * part / splits);
+    kb_e = (int)((long long)kb_total * (part + 1) / splits);
+  };
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int i = 0;
+      for (int ch = c0; ch < c1; ++ch) {
+        int tile, part, kb_b, kb_e;
+        chunk_range(ch, tile, part, kb_b, kb_e);
+        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * n_tile;
+        for (int kb = kb_b; kb < kb_e; ++kb, ++i) {
+          const int s = i % NST, ph = (i / NST) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* st = smem + s * STAGE;
+          mbar_expect_tx(&full[s], X_BYTES + 2 * (uint32_t)n_tile * BK * 4);
+          tma_load_2d(st, &tmX, &full[s], kb * BK, m0);
+          tma_load_2d(st + 2 * X_BYTES, &tmWhi, &full[s], kb * BK, n0);
+          tma_load_2d(st + 2 * X_BYTES + W_BYTES, &tmWlo, &full[s], kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(BM, n_tile, 0, 0);
+      int i = 0, seg = 0;
+      for (int ch = c0; ch < c1; ++ch, ++seg) {
+        int tile, part, kb_b, kb_e;
+        chunk_range(ch, tile, part, kb_b, kb_e);
+        const int as = seg & 1, aph = (seg >> 1) & 1;
+        mbar_wait(&acc_empty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = kb_b; kb < kb_e; ++kb, ++i) {
+          const int s = i % NST, ph = (i / NST) & 1;
+          mbar_wait(&ready[s], ph);
+          tc_fence_after();
+          const uint32_t hi = smem_u32(smem + s * STAGE), lo = hi + X_BYTES;
+          const uint32_t whi = hi + 2 * X_BYTES, wlo = whi + W_BYTES;
+#pragma unroll
+          for (int pair = 0; pair < 3; ++pair) {
+            const uint32_t sa = pair == 0 ? lo : hi;
+            const uint32_t sb = pair == 1 ? wlo : whi;
+#pragma unroll
+            for (int kk = 0; kk < BK / 8; ++kk)
+              umma_tf32(d_tmem, smem_desc(sa + kk * 32, 16, 1024), smem_desc(sb + kk * 32, 16, 1024), idesc,
+                        (kb != kb_b) || (pair | kk) != 0);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[as]);
+      }
+    }
+  } else if (warp < 6) {
+    // ===== transform warps: x tile -> (hi, lo) of relu(bn(sqrt(x))) in place =====
+    const int t = (warp - 2) * 32 + lane;  // row of the tile
+    int i = 0;
+    int pending_store_stage = -1;
+    for (int ch = c0; ch < c1; ++ch) {
+      int tile, part, kb_b, kb_e;
+      chunk_range(ch, tile, part, kb_b, kb_e);
+      const int m0 = (tile / n_tiles) * BM;
+      const bool store_hi = (tile % n_tiles) == 0;
+      for (int kb = kb_b; kb < kb_e; ++kb, ++i) {
+        const int s = i % NST, ph = (i / NST) & 1;
+        if (t == 0 && pending_store_stage >= 0) {
+          // the previous hi-tile store has finished reading its stage: release it
+          tma_store_wait_read0();
+          mbar_arrive(&empty[pending_store_stage]);
+          pending_store_stage = -1;
+        }
+        mbar_wait(&full[s], ph);
+        uint8_t* xt = smem + s * STAGE;
+        uint8_t* lt = xt + X_BYTES;
+        const int k0 = kb * BK;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          // logical 16-byte chunk c of row t lives at physical chunk c ^ (t % 8) (128-byte swizzle):
+          // the 8 threads of a quarter-warp phase touch 8 different chunks -> conflict-free
+          const int off = t * 128 + ((c ^ (t & 7)) << 4);
+          const float4 xv = *reinterpret_cast<const float4*>(xt + off);
+          const float in[4] = {xv.x, xv.y, xv.z, xv.w};
+          float hv[4], lv[4];
+          const int col = k0 + c * 4;
+          if (col + 4 <= G) {
+            const float4 mean = __ldg(reinterpret_cast<const float4*>(bn.mean + col));
+            const float4 rstd = __ldg(reinterpret_cast<const float4*>(bn.rstd + col));
+            const float4 gam = __ldg(reinterpret_cast<const float4*>(bn.gamma + col));
+            const float4 bet = __ldg(reinterpret_cast<const float4*>(bn.beta + col));
+            const float mv[4] = {mean.x, mean.y, mean.z, mean.w}, rv[4] = {rstd.x, rstd.y, rstd.z, rstd.w};
+            const float gv[4] = {gam.x, gam.y, gam.z, gam.w}, bv[4] = {bet.x, bet.y, bet.z, bet.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float a = bn_relu(sqrt_count(in[j]), mv[j], rv[j], gv[j], bv[j]);
+              hv[j] = rna_tf32_(a);
+              lv[j] = rna_tf32_(a - hv[j]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float a = 0.f;
+              if (col + j < G) a = bn_relu(sqrt_count(in[j]), bn.mean[col + j], bn.rstd[col + j], bn.gamma[col + j], bn.beta[col + j]);
+              hv[j] = rna_tf32_(a);
+              lv[j] = rna_tf32_(a - hv[j]);
+            }
+          }
+          *reinterpret_cast<float4*>(xt + off) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+          *reinterpret_cast<float4*>(lt + off) = make_float4(lv[0], lv[1], lv[2], lv[3]);
+        }
+        fence_proxy_async();        // generic-proxy writes -> visible to tcgen05.mma / TMA store
+        named_bar_sync(1, 128);     // the whole tile is transformed
+        if (t == 0) {
+          if (store_hi) {
+            tma_store_2d(&tmAhi, xt, k0, m0);
+            tma_store_commit();
+            pending_store_stage = s;
+          } else {
+            mbar_arrive(&empty[s]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready[s]);
+      }
+    }
+    if (t == 0) {
+      if (pending_store_stage >= 0) {
+        tma_store_wait_read0();
+        mbar_arrive(&empty[pending_store_stage]);
+      }
+      tma_store_wait_all();  // global writes of the hi tiles complete before the kernel ends
+    }
+  } else {
+    // ===== epilogue: TMEM -> slab of this k-part =====
+    const int q = warp % 4;
+    int seg = 0;
+    for (int ch = c0; ch < c1; ++ch, ++seg) {
+      int tile, part, kb_b, kb_e;
+      chunk_range(ch, tile, part, kb_b, kb_e);
+      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * n_tile;
+      const int as = seg & 1, aph = (seg >> 1) & 1;
+      const int m = m0 + q * 32 + lane;
+      mbar_wait(&acc_full[as], aph);
+      tc_fence_after();
+      const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      for (int c = 0; c < n_tile; c += 16) {
+        float v[16];
+        tmem_ld16(tb + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (m < B) {
+          float* dst = out + (size_t)part * part_stride + (size_t)m * h + n0 + c;
+          if (part_stride == 0 && bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (n0 + c + j < h) v[j] += __ldg(&bias[n0 + c + j]);
+          }
+          if (n0 + c + 16 <= h && ((((uintptr_t)dst) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (n0 + c + j < h) dst[j] = v[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+int sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace
+
+int encfwd_fused(const float* x, int B, int G, BnParams bn, const float* w_hi, const float* w_lo, int h,
+                 const float* bias, float* V, float* a_hi, float* partials, int max_parts, cudaStream_t st) {
+  CUtensorMap tX, tWh, tWl, tA;
+  const int n_tile = h >= BN ? BN : ((h + 15) / 16) * 16;
+  if (!tmap_2d(&tX, x, B, G, G, BM, BK)) return -3;
+  if (!tmap_2d(&tWh, w_hi, h, G, G, (uint32_t)n_tile, BK)) return -3;
+  if (!tmap_2d(&tWl, w_lo, h, G, G, (uint32_t)n_tile, BK)) return -3;
+  if (!tmap_2d(&tA, a_hi, B, G, G, BM, BK)) return -3;
+  const int kb_total = (G + BK - 1) / BK;
+  const long long tiles = (long long)((B + BM - 1) / BM) * ((h + n_tile - 1) / n_tile);
+  // k-parts: fill the SMs, keep accumulation chains <= 32 k-blocks (3 MMAs each), <= max_parts slabs
+  int splits = (int)((sms() + tiles - 1) / tiles);
+  if ((kb_total + splits - 1) / splits > 11) splits = (kb_total + 10) / 11;  // 12 MMA steps per k-block
+  if (splits > max_parts) splits = max_parts;
+  if (splits > kb_total) splits = kb_total;
+  if (splits < 1) splits = 1;
+  const long long chunks = tiles * splits;
+  const int grid = (int)(chunks < sms() ? chunks : sms());
+  cudaFuncSetAttribute(k_encfwd, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (splits > 1) {
+    k_encfwd<<<grid, NTHREADS, SMEM_BYTES, st>>>(tX, tWh, tWl, tA, bn, B, G, h, n_tile, splits, partials,
+                                                 (long long)B * h, nullptr);
+    note_launch();
+    reduce_parts(partials, splits, B, h, bias, V, h, st);
+  } else {
+    k_encfwd<<<grid, NTHREADS, SMEM_BYTES, st>>>(tX, tWh, tWl, tA, bn, B, G, h, n_tile, 1, V, 0LL, bias);
+    note_launch();
+  }
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace drv

@@ -352,6 +352,14 @@ int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs,
   return 0;
 }
 
+void reduce_parts(const float* parts, int n_parts, int M, int N, const float* bias, float* C, int ldc, cudaStream_t st) {
+  const size_t n4 = ((size_t)M * N + 3) / 4;
+  int blocks = (int)((n4 + 255) / 256);
+  if (blocks > n_sm_tc() * 8) blocks = n_sm_tc() * 8;
+  k_reduce_parts<<<blocks, 256, 0, st>>>(parts, n_parts, (size_t)M * N, N, bias, C, ldc);
+  note_launch();
+}
+
 int gemm_tf32(const float* A, int lda, bool a_mn, const float* Bm, int ldb, bool b_mn, float* C, int ldc, int M, int N,
               int K, int max_ctas, bool accumulate, cudaStream_t st) {
   return gemm_tf32_multi(1, &A, &Bm, lda, a_mn, ldb, b_mn, C, ldc, M, N, K, max_ctas, accumulate, nullptr, st, 0, nullptr,
