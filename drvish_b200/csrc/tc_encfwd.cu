@@ -22,12 +22,16 @@ namespace tc {
 namespace {
 
 constexpr int BM = 128, BK = 32, BN = 256;
-constexpr int NST = 2;
+// Two independent rings: the count tiles need a transform pass (3 stages of hi + lo = 32 KB), the
+// weight tiles go straight from TMA to the MMA (2 stages of W_hi + W_lo = 64 KB) and have their own
+// producer thread, so a full weight ring never delays the count loads (and vice versa).
+constexpr int XST = 3, WST = 2;
 constexpr int X_BYTES = BM * BK * 4;        // 16 KB count tile -> becomes the hi tile in place
 constexpr int W_BYTES = BN * BK * 4;        // 32 KB
-constexpr int STAGE = 2 * X_BYTES + 2 * W_BYTES;  // x/hi, lo, W_hi, W_lo = 96 KB
-constexpr int SMEM_BYTES = NST * STAGE + 1024 + 256;
-constexpr int NTHREADS = 320;
+constexpr int XSTAGE = 2 * X_BYTES;         // x/hi, lo
+constexpr int WSTAGE = 2 * W_BYTES;         // W_hi, W_lo
+constexpr int SMEM_BYTES = XST * XSTAGE + WST * WSTAGE + 1024 + 256;
+constexpr int NTHREADS = 352;
 constexpr int TMEM_COLS = 512;
 
 __device__ __forceinline__ float rna_tf32_(float v) {
@@ -42,10 +46,14 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
          int h, int n_tile, int splits, float* __restrict__ out, long long part_stride, const float* __restrict__ bias) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = (uint64_t*)(smem + NST * STAGE);
-  uint64_t* ready = full + NST;
-  uint64_t* empty = ready + NST;
-  uint64_t* acc_full = empty + NST;   // [2]
+  uint8_t* xring = smem;
+  uint8_t* wring = smem + XST * XSTAGE;
+  uint64_t* full = (uint64_t*)(wring + WST * WSTAGE);  // [XST] count tile landed
+  uint64_t* ready = full + XST;                        // [XST] tile transformed
+  uint64_t* empty = ready + XST;                       // [XST] MMAs retired + hi-tile store drained
+  uint64_t* wfull = empty + XST;                       // [WST]
+  uint64_t* wempty = wfull + WST;                      // [WST]
+  uint64_t* acc_full = wempty + WST;  // [2]
   uint64_t* acc_empty = acc_full + 2; // [2]
   uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
 
@@ -61,10 +69,14 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
     tma_prefetch_desc(&tmWhi);
     tma_prefetch_desc(&tmWlo);
     tma_prefetch_desc(&tmAhi);
-    for (int s = 0; s < NST; ++s) {
+    for (int s = 0; s < XST; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&ready[s], 4);   // one arrival per transform warp
       mbar_init(&empty[s], 2);   // tcgen05.commit + hi-tile store drained
+    }
+    for (int s = 0; s < WST; ++s) {
+      mbar_init(&wfull[s], 1);
+      mbar_init(&wempty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
@@ -86,21 +98,35 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
   };
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer: count tiles =====
     if (lane == 0) {
       int i = 0;
       for (int ch = c0; ch < c1; ++ch) {
         int tile, part, kb_b, kb_e;
         chunk_range(ch, tile, part, kb_b, kb_e);
-        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * n_tile;
+        const int m0 = (tile / n_tiles) * BM;
         for (int kb = kb_b; kb < kb_e; ++kb, ++i) {
-          const int s = i % NST, ph = (i / NST) & 1;
+          const int s = i % XST, ph = (i / XST) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          uint8_t* st = smem + s * STAGE;
-          mbar_expect_tx(&full[s], X_BYTES + 2 * (uint32_t)n_tile * BK * 4);
-          tma_load_2d(st, &tmX, &full[s], kb * BK, m0);
-          tma_load_2d(st + 2 * X_BYTES, &tmWhi, &full[s], kb * BK, n0);
-          tma_load_2d(st + 2 * X_BYTES + W_BYTES, &tmWlo, &full[s], kb * BK, n0);
+          mbar_expect_tx(&full[s], X_BYTES);
+          tma_load_2d(xring + s * XSTAGE, &tmX, &full[s], kb * BK, m0);
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ===== TMA producer: weight tiles =====
+    if (lane == 0) {
+      int i = 0;
+      for (int ch = c0; ch < c1; ++ch) {
+        int tile, part, kb_b, kb_e;
+        chunk_range(ch, tile, part, kb_b, kb_e);
+        const int n0 = (tile % n_tiles) * n_tile;
+        for (int kb = kb_b; kb < kb_e; ++kb, ++i) {
+          const int s = i % WST, ph = (i / WST) & 1;
+          mbar_wait(&wempty[s], ph ^ 1);
+          mbar_expect_tx(&wfull[s], 2 * (uint32_t)n_tile * BK * 4);
+          tma_load_2d(wring + s * WSTAGE, &tmWhi, &wfull[s], kb * BK, n0);
+          tma_load_2d(wring + s * WSTAGE + W_BYTES, &tmWlo, &wfull[s], kb * BK, n0);
         }
       }
     }
@@ -112,31 +138,41 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
       for (int ch = c0; ch < c1; ++ch, ++seg) {
         int tile, part, kb_b, kb_e;
         chunk_range(ch, tile, part, kb_b, kb_e);
-        const int as = seg & 1, aph = (seg >> 1) & 1;
-        mbar_wait(&acc_empty[as], aph ^ 1);
+        // Two TMEM accumulators per chunk, added by the epilogue in fp32 (round-to-nearest): the main
+        // products A_hi W_hi and the small correction products A_lo W_hi + A_hi W_lo.  The tcgen05
+        // accumulator is updated with truncation - about half an ulp OF THE ACCUMULATOR per MMA step -
+        // so adding the 2^-12-sized corrections into the big sum tripled the bias (measured: worst
+        // gradient error 2.8e-4 -> 9e-4); kept apart, the corrections meet a tiny ulp and the main sum
+        // sees only a third of the steps.  (Cost: no accumulator double-buffering across chunks,
+        // ~10 % of this kernel, the chunks are long.)
+        const int aph = seg & 1;
+        mbar_wait(&acc_empty[0], aph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
         for (int kb = kb_b; kb < kb_e; ++kb, ++i) {
-          const int s = i % NST, ph = (i / NST) & 1;
+          const int s = i % XST, ph = (i / XST) & 1;
+          const int ws = i % WST, wph = (i / WST) & 1;
           mbar_wait(&ready[s], ph);
+          mbar_wait(&wfull[ws], wph);
           tc_fence_after();
-          const uint32_t hi = smem_u32(smem + s * STAGE), lo = hi + X_BYTES;
-          const uint32_t whi = hi + 2 * X_BYTES, wlo = whi + W_BYTES;
+          const uint32_t hi = smem_u32(xring + s * XSTAGE), lo = hi + X_BYTES;
+          const uint32_t whi = smem_u32(wring + ws * WSTAGE), wlo = whi + W_BYTES;
 #pragma unroll
           for (int pair = 0; pair < 3; ++pair) {
             const uint32_t sa = pair == 0 ? lo : hi;
             const uint32_t sb = pair == 1 ? wlo : whi;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(pair == 2 ? 0 : BN);
 #pragma unroll
             for (int kk = 0; kk < BK / 8; ++kk)
               umma_tf32(d_tmem, smem_desc(sa + kk * 32, 16, 1024), smem_desc(sb + kk * 32, 16, 1024), idesc,
-                        (kb != kb_b) || (pair | kk) != 0);
+                        (kb != kb_b) || kk != 0 || pair == 1);
           }
           umma_commit(&empty[s]);
+          umma_commit(&wempty[ws]);
         }
-        umma_commit(&acc_full[as]);
+        umma_commit(&acc_full[0]);
       }
     }
-  } else if (warp < 6) {
+  } else if (warp >= 2 && warp < 6) {
     // ===== transform warps: x tile -> (hi, lo) of relu(bn(sqrt(x))) in place =====
     const int t = (warp - 2) * 32 + lane;  // row of the tile
     int i = 0;
@@ -147,7 +183,7 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
       const int m0 = (tile / n_tiles) * BM;
       const bool store_hi = (tile % n_tiles) == 0;
       for (int kb = kb_b; kb < kb_e; ++kb, ++i) {
-        const int s = i % NST, ph = (i / NST) & 1;
+        const int s = i % XST, ph = (i / XST) & 1;
         if (t == 0 && pending_store_stage >= 0) {
           // the previous hi-tile store has finished reading its stage: release it
           tma_store_wait_read0();
@@ -155,7 +191,7 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
           pending_store_stage = -1;
         }
         mbar_wait(&full[s], ph);
-        uint8_t* xt = smem + s * STAGE;
+        uint8_t* xt = xring + s * XSTAGE;
         uint8_t* lt = xt + X_BYTES;
         const int k0 = kb * BK;
 #pragma unroll
@@ -214,7 +250,7 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
       }
       tma_store_wait_all();  // global writes of the hi tiles complete before the kernel ends
     }
-  } else {
+  } else if (warp >= 6 && warp < 10) {
     // ===== epilogue: TMEM -> slab of this k-part =====
     const int q = warp % 4;
     int seg = 0;
@@ -222,15 +258,24 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
       int tile, part, kb_b, kb_e;
       chunk_range(ch, tile, part, kb_b, kb_e);
       const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * n_tile;
-      const int as = seg & 1, aph = (seg >> 1) & 1;
+      const int aph = seg & 1;
       const int m = m0 + q * 32 + lane;
-      mbar_wait(&acc_full[as], aph);
+      const bool two = true;  // main + correction accumulators
+      mbar_wait(&acc_full[0], aph);
       tc_fence_after();
-      const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16);
       for (int c = 0; c < n_tile; c += 16) {
         float v[16];
         tmem_ld16(tb + (uint32_t)c, v);
-        tmem_ld_wait();
+        if (two) {
+          float v2[16];
+          tmem_ld16(tb + (uint32_t)(BN + c), v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += v2[j];
+        } else {
+          tmem_ld_wait();
+        }
         if (m < B) {
           float* dst = out + (size_t)part * part_stride + (size_t)m * h + n0 + c;
           if (part_stride == 0 && bias != nullptr) {
@@ -250,7 +295,7 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      if (lane == 0) mbar_arrive(&acc_empty[0]);
     }
   }
   tc_fence_before();
@@ -284,12 +329,20 @@ int encfwd_fused(const float* x, int B, int G, BnParams bn, const float* w_hi, c
   if (!tmap_2d(&tA, a_hi, B, G, G, BM, BK)) return -3;
   const int kb_total = (G + BK - 1) / BK;
   const long long tiles = (long long)((B + BM - 1) / BM) * ((h + n_tile - 1) / n_tile);
-  // k-parts: fill the SMs, keep accumulation chains <= 32 k-blocks (3 MMAs each), <= max_parts slabs
-  int splits = (int)((sms() + tiles - 1) / tiles);
-  if ((kb_total + splits - 1) / splits > 11) splits = (kb_total + 10) / 11;  // 12 MMA steps per k-block
-  if (splits > max_parts) splits = max_parts;
-  if (splits > kb_total) splits = kb_total;
-  if (splits < 1) splits = 1;
+  // k-parts: minimise waves x k-blocks per chunk (chunks beyond a multiple of the SM count cost a
+  // whole extra wave), with accumulation chains <= 20 k-blocks (240 MMA steps, bias ~1e-6, see
+  // DESIGN.md) and at most max_parts slabs
+  int splits = 1;
+  {
+    long long best = -1;
+    for (int sp = 1; sp <= max_parts && sp <= kb_total; ++sp) {
+      const int per = (kb_total + sp - 1) / sp;
+      if (per > 20 && sp < max_parts) continue;
+      const long long waves = (tiles * sp + sms() - 1) / sms();
+      const long long cost = waves * (per + 2);
+      if (best < 0 || cost < best) { best = cost; splits = sp; }
+    }
+  }
   const long long chunks = tiles * splits;
   const int grid = (int)(chunks < sms() ? chunks : sms());
   cudaFuncSetAttribute(k_encfwd, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);

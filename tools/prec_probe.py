@@ -1,12 +1,12 @@
-import sys, torch
+import os, sys, torch
 sys.path.insert(0, '.')
 from tests import parity as P
 import drvish_b200 as D
 cfg = dict(n_input=5000, n_latent=10, layers=[256, 256], batch=4096, drugs=8, doses=8, classes=8)
-for seed in (1234,):
+for seed in [int(v) for v in os.environ.get('SEEDS', '1234').split(',')]:
     case = P.make_case(cfg, data_seed=seed)
     loss64, g64, _, _ = P.oracle_step(case, torch.float64)
-    for flags in (0, 16, 32, 12, 16+32+12):
+    for flags in [int(v) for v in os.environ.get('FLAGS', '0').split(',')]:
         model = P.build_cuda_model(case, 'cuda:0')
         elbo = D.FusedTraceELBO(data_parallel=False, extra_flags=flags)
         elbo.set_noise(case['noise'])
