@@ -7,6 +7,7 @@
 //   dW   = dlogits^T act   : A = dlogits [B][2G] MN-major, B = act [B][h] MN-major, K = cells
 //   dAct = dlogits  W      : A = dlogits [B][2G] K-major,  B = W [2G][h]  MN-major, K = 2G
 // Split-K partial tiles are combined with red.global.add.f32 into a zeroed C.
+#include <stdlib.h>
 #include "tc.cuh"
 #include "tc_common.cuh"
 
@@ -41,6 +42,7 @@ bool make_tensor_map(CUtensorMap* map, const void* base, int rank, const uint64_
 
 // debug overrides for the MN-major descriptor fields (bytes); 0 = defaults
 static int g_mn_lbo = 4096, g_mn_sbo = 512, g_mn_kstep = 1024;
+static int g_force_mt = getenv("DRV_MT") ? atoi(getenv("DRV_MT")) : 0;  // debug: 1 / 2 forces the M sub-tile count
 
 namespace {
 
@@ -62,18 +64,27 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 // SM); a CTA walks its contiguous unit range as <= a few (tile, k-range) segments.  A segment that
 // covers a whole tile stores it, partial segments are combined with red.global.add into a zeroed C.
 // Two TMEM accumulator stages overlap the epilogue of a segment with the MMAs of the next one.
-template <bool A_MN, bool B_MN>
+// MT = number of 128-row M sub-tiles a CTA computes against ONE staged B tile.  MT = 2 (256 x 256 output
+// tile, two TMEM accumulators, 3 stages of 64 KB) moves 1.5x fewer operand bytes from L2 per MMA
+// than MT = 1 (4 stages of 48 KB, accumulator double-buffered across chunks): the large GEMMs are
+// bound by L2 -> shared-memory bandwidth (ncu: tensor pipe 25-44 %, ~7 TB/s of TMA traffic).
+template <bool A_MN, bool B_MN, int MT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
           const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, int n_pairs,
           float* __restrict__ C, int ldc, int M, int N, int K, int n_tile, int splits, int force_atomic,
           const float* __restrict__ bias, long long part_stride, int mn_lbo, int mn_sbo, int mn_kstep) {
+  constexpr int TBM = MT * BM;                       // rows of the CTA tile
+  constexpr int NSTG = MT == 1 ? STAGES : 3;
+  constexpr int SA_BYTES = MT * A_BYTES;
+  constexpr int STG_BYTES = SA_BYTES + B_BYTES;
+  constexpr int NACC = MT == 1 ? 2 : 1;              // accumulator stages (MT = 2 uses all 512 TMEM columns)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
-  uint64_t* empty = full + STAGES;
-  uint64_t* acc_full = empty + STAGES;   // [2]
+  uint64_t* full = (uint64_t*)(smem + NSTG * STG_BYTES);
+  uint64_t* empty = full + NSTG;
+  uint64_t* acc_full = empty + NSTG;     // [2]
   uint64_t* acc_empty = acc_full + 2;    // [2]
   uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
 
@@ -81,7 +92,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   // the operand pairs are concatenated along a virtual K axis: sum_p A_p B_p^T accumulates in TMEM
   const int kb_pair = (K + BK - 1) / BK;
   const int kb_total = kb_pair * n_pairs;
-  const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + n_tile - 1) / n_tile;
+  const int m_tiles = (M + TBM - 1) / TBM, n_tiles = (N + n_tile - 1) / n_tile;
   // work = (tile, k-part) chunks: every tile's k range is cut into `splits` parts; CTA c owns the
   // contiguous chunk range [c0, c1)
   const long long chunks = (long long)m_tiles * n_tiles * splits;
@@ -91,7 +102,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < NSTG; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
@@ -110,26 +121,26 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      const uint32_t tx = A_BYTES + (uint32_t)n_tile * BK * 4;
+      const uint32_t tx = SA_BYTES + (uint32_t)n_tile * BK * 4;
       int i = 0;
       for (int ch = c0; ch < c1; ++ch) {
         const int tile = ch / splits, part = ch % splits;
         const int kb_b = (int)((long long)kb_total * part / splits), kb_e = (int)((long long)kb_total * (part + 1) / splits);
-        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * n_tile;
+        const int m0 = (tile / n_tiles) * TBM, n0 = (tile % n_tiles) * n_tile;
         for (int kb = kb_b; kb < kb_e; ++kb, ++i) {
-          const int s = i % STAGES, ph = (i / STAGES) & 1;
+          const int s = i % NSTG, ph = (i / NSTG) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          uint8_t* sa = smem + s * STAGE_BYTES;
-          uint8_t* sb = sa + A_BYTES;
+          uint8_t* sa = smem + s * STG_BYTES;
+          uint8_t* sb = sa + SA_BYTES;
           mbar_expect_tx(&full[s], tx);
           const int pair = kb / kb_pair;
           const int k0 = (kb - pair * kb_pair) * BK;
           const CUtensorMap* ma = pair == 0 ? &tmA : (pair == 1 ? &tmA1 : &tmA2);
           const CUtensorMap* mb = pair == 0 ? &tmB : (pair == 1 ? &tmB1 : &tmB2);
           if (A_MN) {
-            for (int j = 0; j < BM / 32; ++j) tma_load_2d(sa + j * 4096, ma, &full[s], m0 + 32 * j, k0);
+            for (int j = 0; j < TBM / 32; ++j) tma_load_2d(sa + j * 4096, ma, &full[s], m0 + 32 * j, k0);
           } else {
-            tma_load_2d(sa, ma, &full[s], k0, m0);
+            for (int j = 0; j < MT; ++j) tma_load_2d(sa + j * A_BYTES, ma, &full[s], k0, m0 + j * BM);
           }
           if (B_MN) {
             for (int j = 0; j < n_tile / 32; ++j) tma_load_2d(sb + j * 4096, mb, &full[s], n0 + 32 * j, k0);
@@ -147,21 +158,25 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       for (int ch = c0; ch < c1; ++ch, ++seg) {
         const int part = ch % splits;
         const int kb_b = (int)((long long)kb_total * part / splits), kb_e = (int)((long long)kb_total * (part + 1) / splits);
-        const int as = seg & 1, aph = (seg >> 1) & 1;
+        const int as = seg % NACC, aph = (seg / NACC) & 1;
         mbar_wait(&acc_empty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * MAXN);
         for (int kb = kb_b; kb < kb_e; ++kb, ++i) {
-          const int s = i % STAGES, ph = (i / STAGES) & 1;
+          const int s = i % NSTG, ph = (i / NSTG) & 1;
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
+          const uint32_t sa = smem_u32(smem + s * STG_BYTES);
+          const uint32_t sb = sa + SA_BYTES;
 #pragma unroll
           for (int kk = 0; kk < BK / 8; ++kk) {
-            const uint64_t da = A_MN ? smem_desc(sa + kk * mn_kstep, mn_lbo, mn_sbo, 1) : smem_desc(sa + kk * 32, 16, 1024);
             const uint64_t db = B_MN ? smem_desc(sb + kk * mn_kstep, mn_lbo, mn_sbo, 1) : smem_desc(sb + kk * 32, 16, 1024);
-            umma_tf32(d_tmem, da, db, idesc, (kb != kb_b) || (kk != 0));
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint32_t sam = sa + mt * A_BYTES;  // sub-tile mt: its own 128 rows (4 MN-major boxes)
+              const uint64_t da = A_MN ? smem_desc(sam + kk * mn_kstep, mn_lbo, mn_sbo, 1) : smem_desc(sam + kk * 32, 16, 1024);
+              umma_tf32(d_tmem + (uint32_t)(mt * MAXN), da, db, idesc, (kb != kb_b) || (kk != 0));
+            }
           }
           umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
         }
@@ -174,14 +189,16 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     int seg = 0;
     for (int ch = c0; ch < c1; ++ch, ++seg) {
       const int tile = ch / splits, part = ch % splits;
-      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * n_tile;
+      const int m0 = (tile / n_tiles) * TBM, n0 = (tile % n_tiles) * n_tile;
       const bool whole = !force_atomic;
       const bool add_bias = bias != nullptr && part == 0 && part_stride == 0;
-      const int as = seg & 1, aph = (seg >> 1) & 1;
-      const int m = m0 + q * 32 + lane;
+      const int as = seg % NACC, aph = (seg / NACC) & 1;
       mbar_wait(&acc_full[as], aph);
       tc_fence_after();
-      const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * MAXN);
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+      const int m = m0 + mt * BM + q * 32 + lane;
+      const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * MAXN + mt * MAXN);
       for (int c = 0; c < n_tile; c += 16) {
         float v[16];
         tmem_ld16(tb + (uint32_t)c, v);
@@ -211,6 +228,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
           }
         }
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -286,21 +304,33 @@ int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs,
     if (!ok) return -3;
   }
   const int kb_total = ((K + BK - 1) / BK) * n_pairs;
-  const long long tiles = (long long)((M + BM - 1) / BM) * ((N + n_tile - 1) / n_tile);
   const int sms = max_ctas > 0 && max_ctas < n_sm_tc() ? max_ctas : n_sm_tc();
-  // split every tile's k range into `splits` parts so that the (tile, part) chunks fill the SMs:
-  // minimise ceil(chunks / SMs) * (k-blocks per chunk + epilogue cost), epilogue ~6 k-blocks for a
-  // plain store, ~12 for the red.add combine of split tiles
-  int splits = 1;
+  // Candidate schedules: MT = 1 (128-row tiles) or MT = 2 (256-row tiles, 1.5x fewer operand bytes
+  // per MMA but no accumulator double-buffering, so only for long k ranges), each with the k range
+  // of every tile split into `splits` parts so that the (tile, part) chunks fill the SMs.  Cost
+  // model per schedule: waves x (k-blocks per chunk x relative k-block time + epilogue), where a
+  // k-block costs MT x 1.0 MMA units but only (MT + 2) / 3 of the L2 traffic time of MT = 1; the
+  // epilogue is ~6 k-blocks (store) or ~12 (red.add of split tiles) per 128 rows.
+  int splits = 1, mt_sel = 1;
   {
     const int cand[] = {1, 2, 3, 4, 6, 8, 12, 16};
-    long long best = -1;
-    for (int ci = 0; ci < 8; ++ci) {
-      int sp = cand[ci];
-      if (sp > 1 && kb_total / sp < 8) break;
-      long long waves = (tiles * sp + sms - 1) / sms;
-      long long cost = waves * ((kb_total + sp - 1) / sp + (sp > 1 ? 12 : 6));
-      if (best < 0 || cost < best) { best = cost; splits = sp; }
+    double best = -1;
+    for (int mt = 1; mt <= 2; ++mt) {
+      if (mt == 2 && (M <= BM || g_force_mt == 1)) continue;
+      if (mt == 1 && g_force_mt == 2 && M > BM) continue;
+      const long long tiles = (long long)((M + mt * BM - 1) / (mt * BM)) * ((N + n_tile - 1) / n_tile);
+      for (int ci = 0; ci < 8; ++ci) {
+        const int sp = cand[ci];
+        if (sp > 1 && kb_total / sp < 8) break;
+        const long long waves = (tiles * sp + sms - 1) / sms;
+        const double per = (double)((kb_total + sp - 1) / sp);
+        // time per k-block relative to MT = 1: bound by max(MMA time, L2 traffic time); with the
+        // measured ~40 % tensor utilisation of MT = 1 the traffic term dominates
+        const double kb_cost = mt == 1 ? 1.0 : 1.35;
+        const double epi = (sp > 1 ? 12.0 : 6.0) * mt * (mt == 2 ? 1.5 : 1.0);
+        const double cost = (double)waves * (per * kb_cost + epi);
+        if (best < 0 || cost < best) { best = cost; splits = sp; mt_sel = mt; }
+      }
     }
   }
   // Precision knob: the TMEM accumulator is updated with truncation, a bias that grows with the
@@ -312,43 +342,44 @@ int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs,
   // summed in a fixed order by k_reduce_parts.
   const bool deterministic = partials != nullptr && !accumulate;
   if (deterministic && splits > max_parts) splits = max_parts;
+  const long long tiles = (long long)((M + mt_sel * BM - 1) / (mt_sel * BM)) * ((N + n_tile - 1) / n_tile);
   const long long chunks = tiles * splits;
   int grid = (int)(chunks < sms ? chunks : sms);
   const bool split = splits > 1;
+  float* outp = C;
+  int out_ld = ldc, force_atomic = (split || accumulate) ? 1 : 0;
+  long long part_stride = 0;
+  const float* kbias = bias;
   if (deterministic && split) {
-    auto launch = [&](auto kern) {
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-      kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(ta[0], tb[0], ta[1], tb[1], ta[2], tb[2], n_pairs, partials, N, M, N, K,
-                                               n_tile, splits, 0, nullptr, (long long)M * N, g_mn_lbo, g_mn_sbo,
-                                               g_mn_kstep);
-    };
-    if (a_mn && b_mn) launch(k_tc_gemm<true, true>);
-    else if (a_mn) launch(k_tc_gemm<true, false>);
-    else if (b_mn) launch(k_tc_gemm<false, true>);
-    else launch(k_tc_gemm<false, false>);
-    note_launch();
+    outp = partials; out_ld = N; force_atomic = 0; part_stride = (long long)M * N; kbias = nullptr;
+  } else if (split && !accumulate) {
+    if (ldc == N) cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st);
+    else cudaMemset2DAsync(C, sizeof(float) * (size_t)ldc, 0, sizeof(float) * (size_t)N, (size_t)M, st);
+  }
+  auto launch = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(ta[0], tb[0], ta[1], tb[1], ta[2], tb[2], n_pairs, outp, out_ld, M, N, K, n_tile,
+                                             splits, force_atomic, kbias, part_stride, g_mn_lbo, g_mn_sbo, g_mn_kstep);
+  };
+  if (mt_sel == 1) {
+    if (a_mn && b_mn) launch(k_tc_gemm<true, true, 1>);
+    else if (a_mn) launch(k_tc_gemm<true, false, 1>);
+    else if (b_mn) launch(k_tc_gemm<false, true, 1>);
+    else launch(k_tc_gemm<false, false, 1>);
+  } else {
+    if (a_mn && b_mn) launch(k_tc_gemm<true, true, 2>);
+    else if (a_mn) launch(k_tc_gemm<true, false, 2>);
+    else if (b_mn) launch(k_tc_gemm<false, true, 2>);
+    else launch(k_tc_gemm<false, false, 2>);
+  }
+  note_launch();
+  if (deterministic && split) {
     const size_t n4 = ((size_t)M * N + 3) / 4;
     int blocks = (int)((n4 + 255) / 256);
     if (blocks > n_sm_tc() * 8) blocks = n_sm_tc() * 8;
     k_reduce_parts<<<blocks, 256, 0, st>>>(partials, splits, (size_t)M * N, N, bias, C, ldc);
     note_launch();
-    return 0;
   }
-  if (split && !accumulate) {
-    if (ldc == N) cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st);
-    else cudaMemset2DAsync(C, sizeof(float) * (size_t)ldc, 0, sizeof(float) * (size_t)N, (size_t)M, st);
-  }
-  const int force_atomic = (split || accumulate) ? 1 : 0;
-  auto launch = [&](auto kern) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(ta[0], tb[0], ta[1], tb[1], ta[2], tb[2], n_pairs, C, ldc, M, N, K, n_tile,
-                                             splits, force_atomic, bias, 0LL, g_mn_lbo, g_mn_sbo, g_mn_kstep);
-  };
-  if (a_mn && b_mn) launch(k_tc_gemm<true, true>);
-  else if (a_mn) launch(k_tc_gemm<true, false>);
-  else if (b_mn) launch(k_tc_gemm<false, true>);
-  else launch(k_tc_gemm<false, false>);
-  note_launch();
   return 0;
 }
 
