@@ -212,7 +212,8 @@ __global__ void k_bn_bwd_apply(float* __restrict__ dY, const float* __restrict__
   size_t n = (size_t)B * D;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
     int col = (int)(idx % D);
-    float s1 = (float)(acc[col] / B), s2 = (float)(acc[D + col] / B);
+    const float invB = 1.0f / (float)B;
+    float s1 = (float)acc[col] * invB, s2 = (float)acc[D + col] * invB;
     float rstd = bn.rstd[col];
     float xh = bn_xhat(U[idx], bn.mean[col], rstd);
     float g = dY[idx];

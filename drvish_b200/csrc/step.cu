@@ -129,6 +129,7 @@ struct Plan {
   size_t z, l, lse, ll, asum, dO;
   size_t u, m, gfac, du, dz_drs;
   size_t tc;                                 // scratch of the fused tcgen05 decoder path
+  size_t p_hi, p_lo;                         // tf32 hi / lo split of the whole flat parameter buffer
   size_t tcb[2][DRV_MAX_LAYERS + 1];         // scratch of the tensor-core blocks (0 = block runs on CUDA cores)
   size_t total;
 };
@@ -169,6 +170,8 @@ Plan make_plan(const drv_dims& d, const Net& n) {
     p.m = take(4 * (size_t)d.n_classes * d.n_doses_total);
     p.gfac = take(4 * (size_t)d.n_classes * d.n_doses_total);
   }
+  p.p_hi = take(4 * (size_t)n.n_param_floats);
+  p.p_lo = take(4 * (size_t)n.n_param_floats);
   p.tc = o;
   o += tc_workspace_bytes(d);
   o = (o + 255) / 256 * 256;
@@ -222,6 +225,7 @@ void block_forward(const Ctx& c, int s, int k, const float* U0, bool do_linear) 
   if (c.p.tcb[s][k] && tc_block_forward_supported(B, b.din, b.dout, c.hp) && (sq ? !(c.hp.flags & 32) : !(c.hp.flags & 8))) {
     TcBlockArgs a{};
     a.U = U; a.sqrt_in = sq; a.bn = c.bn(s, k); a.W = c.params + b.W; a.bias = c.params + b.bias;
+    a.W_hi = c.at<float>(c.p.p_hi) + b.W; a.W_lo = c.at<float>(c.p.p_lo) + b.W;
     a.B = B; a.din = b.din; a.dout = b.dout; a.V = c.at<float>(c.p.V[s][k]); a.scratch = c.ws + c.p.tcb[s][k];
     a.no_fused_prologue = (c.hp.flags & 512) != 0;
     tc_block_forward(a, c.st);
@@ -248,6 +252,7 @@ void block_backward(const Ctx& c, int s, int k, const float* U0, const float* dV
       // the forward of this block ran on the tensor cores too: its A_hi / W_hi operands are reused
       TcBlockArgs a{};
       a.U = U; a.sqrt_in = sq; a.bn = c.bn(s, k); a.W = c.params + b.W; a.B = B; a.din = b.din; a.dout = b.dout;
+      a.W_hi = c.at<float>(c.p.p_hi) + b.W; a.W_lo = c.at<float>(c.p.p_lo) + b.W;
       a.scratch = c.ws + c.p.tcb[s][k]; a.dV = dV; a.dW = c.grads + b.W; a.db = c.grads + b.bias;
       a.dY = sq ? nullptr : c.at<float>(c.p.Gb[s][k]); a.gacc = gacc; a.side = c.side;
       tc_block_backward(a, c.st);
@@ -379,6 +384,10 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
   cudaMemsetAsync(c.ws + p.zero_begin, 0, p.zero_bytes, st);
   cudaMemsetAsync(out, 0, sizeof(drv_step_out), st);
   prof::mark(0, st);
+  // tf32 hi / lo parts of every weight, one pass over the flat parameter buffer (the tensor-core
+  // kernels take pre-rounded operands: kind::tf32 truncates)
+  if (!(hp->flags & DRV_FLAG_FORCE_SIMT))
+    split_params_tf32(params, (size_t)n.n_param_floats, c.at<float>(p.p_hi), c.at<float>(p.p_lo), st);
   // ---- guide: encoder + reparameterised draws (nbvae.py:81-90) --------------------------------
   for (int k = 0; k < NB; ++k) block_forward(c, 0, k, x, true);
   const float* O = c.at<float>(p.V[0][NB - 1]);
@@ -418,7 +427,7 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
   float* dlogits = c.at<float>(p.V[1][NB - 1]);
   TcDecoderArgs ta{};
   if (use_tc) {
-    ta.U = c.at<float>(p.V[1][NB - 2]); ta.bn = c.bn(1, NB - 1); ta.W = params + last.W; ta.bias = params + last.bias;
+    ta.U = c.at<float>(p.V[1][NB - 2]); ta.bn = c.bn(1, NB - 1); ta.W = params + last.W; ta.W_hi = c.at<float>(p.p_hi) + last.W; ta.bias = params + last.bias;
     ta.x = x; ta.lib = l; ta.B = B; ta.G = G; ta.h = last.din; ta.eps = hp->epsilon; ta.c = hp->scale_factor;
     ta.lse = c.at<float>(p.lse); ta.ll = c.at<float>(p.ll); ta.asum = c.at<float>(p.asum); ta.out = out;
     ta.scratch = c.ws + p.tc; ta.dlogits = dlogits; ta.bwd = bwd;
@@ -545,6 +554,8 @@ int drv_encoder_forward(const drv_dims* dims, const drv_hparams* hp, const float
   cudaStream_t st = (cudaStream_t)stream;
   Ctx c{*dims, *hp, n, p, (char*)workspace, params, nullptr, bn_running, st, nullptr};
   cudaMemsetAsync(c.ws + p.zero_begin, 0, p.zero_bytes, st);
+  if (!(hp->flags & DRV_FLAG_FORCE_SIMT))
+    split_params_tf32(params, (size_t)n.n_param_floats, c.at<float>(p.p_hi), c.at<float>(p.p_lo), st);
   for (int k = 0; k < n.n_blocks; ++k) block_forward(c, 0, k, x, true);
   encoder_outputs(c.at<float>(p.V[0][n.n_blocks - 1]), dims->n_cells, dims->n_latent, z_loc, z_scale, l_loc, l_scale, st);
   if (bn_batches && !(hp->flags & DRV_FLAG_NO_BN_UPDATE)) bump_counters(bn_batches, n.n_blocks, st);
@@ -563,6 +574,8 @@ int drv_decoder_forward(const drv_dims* dims, const drv_hparams* hp, const float
   cudaStream_t st = (cudaStream_t)stream;
   Ctx c{*dims, *hp, n, p, (char*)workspace, params, nullptr, bn_running, st, nullptr};
   cudaMemsetAsync(c.ws + p.zero_begin, 0, p.zero_bytes, st);
+  if (!(hp->flags & DRV_FLAG_FORCE_SIMT))
+    split_params_tf32(params, (size_t)n.n_param_floats, c.at<float>(p.p_hi), c.at<float>(p.p_lo), st);
   for (int k = 0; k < n.n_blocks; ++k) block_forward(c, 1, k, z, true);
   nb_decoder_outputs(c.at<float>(p.V[1][n.n_blocks - 1]), library, dims->n_cells, dims->n_genes, log_r, logit, st);
   if (bn_batches && !(hp->flags & DRV_FLAG_NO_BN_UPDATE)) bump_counters(bn_batches + n.n_blocks, n.n_blocks, st);

@@ -9,6 +9,7 @@ struct TcDecoderArgs {
   const float* U;     // [B][h] input of the last decoder block (output of the previous Linear)
   BnParams bn;        // statistics / affine of the last decoder BatchNorm
   const float* W;     // [2G][h]
+  const float* W_hi;  // [2G][h] tf32-rounded copy (split once per step for all layers)
   const float* bias;  // [2G]
   const float* x;     // [B][G]
   const float* lib;   // [B]
@@ -54,6 +55,7 @@ struct TcBlockArgs {
   bool no_fused_prologue;  // debug: materialise A_hi / A_lo instead of the fused-prologue kernel
   BnParams bn;        // statistics / affine of the block's BatchNorm
   const float* W;     // [dout][din]
+  const float *W_hi, *W_lo;  // tf32 hi / lo parts of W (split once per step for all layers)
   const float* bias;  // [dout]
   int B, din, dout;
   float* V;           // [B][dout] output of the Linear
@@ -69,4 +71,6 @@ bool tc_block_forward_supported(int B, int din, int dout, const drv_hparams& hp)
 bool tc_block_backward_supported(int B, int din, int dout, const drv_hparams& hp);
 void tc_block_forward(const TcBlockArgs& a, cudaStream_t st);
 void tc_block_backward(const TcBlockArgs& a, cudaStream_t st);
+// hi = rna_tf32(src), lo = rna_tf32(src - hi) over the whole flat parameter buffer
+void split_params_tf32(const float* src, size_t n, float* hi, float* lo, cudaStream_t st);
 }  // namespace drv

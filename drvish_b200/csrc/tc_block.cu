@@ -227,14 +227,9 @@ bool tc_block_backward_supported(int B, int din, int dout, const drv_hparams& hp
 void tc_block_forward(const TcBlockArgs& a, cudaStream_t st) {
   Scratch s = carve(a.scratch, a.B, a.din, a.dout);
   const size_t n = (size_t)a.B * a.din;
-  size_t nw = (size_t)a.dout * a.din;
-  int wb = (int)((nw + 255) / 256);
-  if (wb > n_sm() * 4) wb = n_sm() * 4;
-  k_split_tf32<<<wb, 256, 0, st>>>(a.W, nw, s.w_hi, s.w_lo);
-  note_launch();
   if (a.sqrt_in && !a.no_fused_prologue) {
     // encoder input layer: sqrt / BatchNorm / ReLU / hi-lo split fused into the GEMM's producer side
-    int rc = tc::encfwd_fused(a.U, a.B, a.din, a.bn, s.w_hi, s.w_lo, a.dout, a.bias, a.V, s.a_hi, s.parts, kMaxParts, st);
+    int rc = tc::encfwd_fused(a.U, a.B, a.din, a.bn, a.W_hi, a.W_lo, a.dout, a.bias, a.V, s.a_hi, s.parts, kMaxParts, st);
     if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
     return;
   }
@@ -244,7 +239,7 @@ void tc_block_forward(const TcBlockArgs& a, cudaStream_t st) {
   else k_enc_prep<false><<<blocks, 256, 0, st>>>(a.U, n, a.din, a.bn, s.a_hi, s.a_lo);
   note_launch();
   const float* As[3] = {s.a_lo, s.a_hi, s.a_hi};
-  const float* Bs[3] = {s.w_hi, s.w_lo, s.w_hi};
+  const float* Bs[3] = {a.W_hi, a.W_lo, a.W_hi};
   int rc = tc::gemm_tf32_multi(3, As, Bs, a.din, false, a.din, false, a.V, a.dout, a.B, a.dout, a.din, 0, false, a.bias, st,
                                /*max_chain_kb=*/32, s.parts, kMaxParts);
   if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
@@ -270,7 +265,7 @@ void tc_block_backward(const TcBlockArgs& a, cudaStream_t st) {
   if (a.side) a.side->mark(st);
   // dA[b][i] = sum_j dV[b][j] W[j][i]: A K-major, B MN-major (K = dout): critical path, submitted first
   float* dA = a.dY ? a.dY : s.a_lo;  // the first encoder block reuses the A_lo buffer
-  int rc = tc::gemm_tf32(s.dh_r, a.dout, false, s.w_hi, a.din, true, dA, a.din, a.B, a.din, a.dout, 0, false, st);
+  int rc = tc::gemm_tf32(s.dh_r, a.dout, false, a.W_hi, a.din, true, dA, a.din, a.B, a.din, a.dout, 0, false, st);
   // dW[j][i] = sum_b dV[b][j] A[b][i]: both operands MN-major (K = cells): off the critical chain
   cudaStream_t ws = st;
   if (a.side) { a.side->attach(); ws = a.side->side; }
@@ -287,6 +282,13 @@ void tc_block_backward(const TcBlockArgs& a, cudaStream_t st) {
   S = (a.B + rows - 1) / rows;
   dim3 grid(col_blocks, S), block(CW, RY);
   k_bn0_grad<<<grid, block, 0, st>>>(dA, a.U, a.B, a.din, rows, a.bn, a.gacc);
+  note_launch();
+}
+
+void split_params_tf32(const float* src, size_t n, float* hi, float* lo, cudaStream_t st) {
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > n_sm() * 8) blocks = n_sm() * 8;
+  k_split_tf32<<<blocks, 256, 0, st>>>(src, n, hi, lo);
   note_launch();
 }
 

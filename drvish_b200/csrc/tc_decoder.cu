@@ -509,12 +509,12 @@ int sm_count() {
 
 bool make_maps(const TcDecoderArgs& a, const Scratch& s, CUtensorMap* act, CUtensorMap* w1, CUtensorMap* w3, CUtensorMap* x) {
   if (!tmap_2d(act, s.act, a.B, a.h, a.h, BM, BK)) return false;
-  if (!tmap_2d(w1, s.Wr, a.G, a.h, a.h, 128, BK)) return false;
+  if (!tmap_2d(w1, a.W_hi, a.G, a.h, a.h, 128, BK)) return false;
   {
     uint64_t dims[3] = {(uint64_t)a.h, (uint64_t)a.G, 2};
     uint64_t strides[2] = {(uint64_t)a.h * 4, (uint64_t)a.G * a.h * 4};
     uint32_t box[3] = {BK, 64, 2};
-    if (!make_tensor_map(w3, s.Wr, 3, dims, strides, box, 1)) return false;
+    if (!make_tensor_map(w3, a.W_hi, 3, dims, strides, box, 1)) return false;
   }
   if (!tmap_2d(x, a.x, a.B, a.G, a.G, BM, 32)) return false;
   return true;
@@ -553,8 +553,6 @@ void tc_decoder_forward(const TcDecoderArgs& a, cudaStream_t st) {
   int blocks = (int)(((size_t)a.B * a.h + 255) / 256);
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
   k_act<<<blocks, 256, 0, st>>>(a.U, a.B, a.h, a.bn, s.act);
-  note_launch();
-  k_round_tf32<<<sm_count() * 4, 256, 0, st>>>(a.W, (size_t)2 * a.G * a.h, s.Wr);
   note_launch();
   DecParams p{};
   p.B = a.B; p.G = a.G; p.h = a.h; p.bias = a.bias; p.lib = a.lib; p.eps = a.eps; p.c = a.c;
@@ -608,7 +606,7 @@ void tc_decoder_backward(const TcDecoderArgs& a, cudaStream_t st) {
   if (a.side) a.side->mark(st);
   // dAct[b][i] = sum_j dlogits[b][j] W[j][i]   (A K-major, B MN-major, K = 2G): critical path, submitted first
   drv_internal_kmark(3, 0, st);
-  int rc = gemm_tf32(a.dlogits, 2 * a.G, false, s.Wr, a.h, true, a.dY, a.h, a.B, a.h, 2 * a.G, 0, false, st);
+  int rc = gemm_tf32(a.dlogits, 2 * a.G, false, a.W_hi, a.h, true, a.dY, a.h, a.B, a.h, 2 * a.G, 0, false, st);
   drv_internal_kmark(3, 1, st);
   // dW[j][i] = sum_b dlogits[b][j] act[b][i]   (both operands MN-major, K = cells): off the critical chain
   cudaStream_t ws = st;
