@@ -255,6 +255,7 @@ void block_backward(const Ctx& c, int s, int k, const float* U0, const float* dV
       a.W_hi = c.at<float>(c.p.p_hi) + b.W; a.W_lo = c.at<float>(c.p.p_lo) + b.W;
       a.scratch = c.ws + c.p.tcb[s][k]; a.dV = dV; a.dW = c.grads + b.W; a.db = c.grads + b.bias;
       a.dY = sq ? nullptr : c.at<float>(c.p.Gb[s][k]); a.gacc = gacc; a.side = c.side;
+      a.no_fused_prologue = (c.hp.flags & 512) != 0;
       tc_block_backward(a, c.st);
       gated = false;
     } else {

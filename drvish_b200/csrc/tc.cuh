@@ -41,6 +41,9 @@ void reduce_parts(const float* parts, int n_parts, int M, int N, const float* bi
 // GEMM (tc_encfwd.cu).  Writes V = relu(bn(sqrt(x))) W^T + b and the tf32 'hi' part of the activations.
 int encfwd_fused(const float* x, int B, int G, BnParams bn, const float* w_hi, const float* w_lo, int h,
                  const float* bias, float* V, float* a_hi, float* partials, int max_parts, cudaStream_t st);
+// d gamma / d beta sums of the encoder's input BatchNorm from dH and W without materialising dA (tc_bn0grad.cu)
+int bn0grad_fused(const float* dH_r, const float* W_hi, const float* x, int B, int G, int h, BnParams bn, double* gacc,
+                  cudaStream_t st);
 int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs, int lda, bool a_mn, int ldb, bool b_mn,
                     float* C, int ldc, int M, int N, int K, int max_ctas, bool accumulate, const float* bias,
                     cudaStream_t st, int max_chain_kb = 0, float* partials = nullptr, int max_parts = 0);

@@ -265,13 +265,21 @@ void tc_block_backward(const TcBlockArgs& a, cudaStream_t st) {
   if (a.side) a.side->mark(st);
   // dA[b][i] = sum_j dV[b][j] W[j][i]: A K-major, B MN-major (K = dout): critical path, submitted first
   float* dA = a.dY ? a.dY : s.a_lo;  // the first encoder block reuses the A_lo buffer
-  int rc = tc::gemm_tf32(s.dh_r, a.dout, false, a.W_hi, a.din, true, dA, a.din, a.B, a.din, a.dout, 0, false, st);
+  int rc = 0;
+  const bool fused_bn0 = !a.dY && a.sqrt_in && !a.no_fused_prologue && a.din % 4 == 0 && a.dout % 4 == 0;
+  if (fused_bn0) {
+    // encoder input layer: dA is never stored - transposed GEMM with the reduction over the batch
+    // inside the epilogue threads
+    rc = tc::bn0grad_fused(s.dh_r, a.W_hi, a.U, a.B, a.din, a.dout, a.bn, a.gacc, st);
+  } else {
+    rc = tc::gemm_tf32(s.dh_r, a.dout, false, a.W_hi, a.din, true, dA, a.din, a.B, a.din, a.dout, 0, false, st);
+  }
   // dW[j][i] = sum_b dV[b][j] A[b][i]: both operands MN-major (K = cells): off the critical chain
   cudaStream_t ws = st;
   if (a.side) { a.side->attach(); ws = a.side->side; }
   if (rc == 0) rc = tc::gemm_tf32(s.dh_r, a.dout, true, s.a_hi, a.din, true, a.dW, a.din, a.dout, a.din, a.B, 0, false, ws);
   if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
-  if (a.dY) return;  // the ReLU gate is applied by the BatchNorm backward kernels
+  if (a.dY || fused_bn0) return;  // (the ReLU gate is applied by the BatchNorm backward kernels)
   // reduce dA to the input-BatchNorm gradients (gate and xhat recomputed from sqrt(x))
   int col_blocks = (a.din + CW * 4 - 1) / (CW * 4);
   int S = (n_sm() * 8 + col_blocks - 1) / col_blocks;
