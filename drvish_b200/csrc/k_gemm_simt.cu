@@ -26,7 +26,7 @@ __device__ __forceinline__ float apply_pro(const Prologue& p, float u, int col) 
   return bn_relu(u, p.bn.mean[col], p.bn.rstd[col], p.bn.gamma[col], p.bn.beta[col]);
 }
 
-enum { EPI_BIAS = 0, EPI_DW = 1, EPI_GATE = 2, EPI_BNGRAD = 3 };
+enum { EPI_BIAS = 0, EPI_DW = 1, EPI_GATE = 2, EPI_BNGRAD = 3, EPI_PLAIN = 4 };
 
 struct Epilogue {
   const float* bias;  // EPI_BIAS
@@ -177,6 +177,8 @@ __global__ void __launch_bounds__(NT) k_gemm(const float* __restrict__ A, int ld
         float* dst = (ONES && gn == N - 1) ? &ep.db[gm] : &C[(size_t)gm * ldc + gn];
         if (gridDim.z > 1) atomicAdd(dst, v);
         else *dst = v;
+      } else if (EPI == EPI_PLAIN) {
+        C[(size_t)gm * ldc + gn] = v;
       } else if (EPI == EPI_GATE) {
         float u = ep.U[(size_t)gm * ep.ldu + gn];
         if (ep.gate.mode == 2) u = sqrt_count(u);
@@ -225,15 +227,14 @@ void simt_linear_wgrad(const float* dV, int B, int dout, const float* U, int din
   note_launch();
 }
 
+// dA = dV W (ungated): the ReLU gate is applied by the BatchNorm backward kernels
 void simt_linear_dgrad_gate(const float* dV, int B, int dout, const float* W, int din, const float* U, int pro_mode,
                             BnParams bn, float* dY, cudaStream_t st) {
+  (void)U; (void)pro_mode; (void)bn;
   Prologue none{0, {}};
   Epilogue ep{};
-  ep.U = U;
-  ep.ldu = din;
-  ep.gate = Prologue{pro_mode, bn};
-  k_gemm<true, false, false, EPI_GATE><<<grid_for(B, din), NT, 0, st>>>(dV, dout, W, din, dY, din, B, din, dout, none,
-                                                                        none, ep);
+  k_gemm<true, false, false, EPI_PLAIN><<<grid_for(B, din), NT, 0, st>>>(dV, dout, W, din, dY, din, B, din, dout, none,
+                                                                         none, ep);
   note_launch();
 }
 

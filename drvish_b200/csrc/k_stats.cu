@@ -31,20 +31,20 @@ struct StatFinal {
   float *mean, *rstd, *rmean, *rvar;  // rmean/rvar may be null
 };
 
-__device__ __forceinline__ void stat_finalize_if_last(const StatFinal& f, const double* acc, int D) {
+// One ticket per column block (blockIdx.x): the last of its gridDim.y row-split CTAs finalises the
+// block's own columns [col0, col0 + ncols), so the finalisation is spread over gridDim.x CTAs.
+__device__ __forceinline__ void stat_finalize_if_last(const StatFinal& f, const double* acc, int D, int col0, int ncols) {
   __shared__ bool is_last;
   __threadfence();
   __syncthreads();
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  if (tid == 0) {
-    const unsigned int total = gridDim.x * gridDim.y;
-    is_last = atomicAdd(f.ticket, 1u) == total - 1;
-  }
+  if (tid == 0) is_last = atomicAdd(f.ticket + blockIdx.x, 1u) == gridDim.y - 1;
   __syncthreads();
   if (!is_last) return;
   __threadfence();
   const int nthr = blockDim.x * blockDim.y;
-  for (int i = tid; i < D; i += nthr) {
+  const int cend = min(D, col0 + ncols);
+  for (int i = col0 + tid; i < cend; i += nthr) {
     const double m = __ldcg(&acc[i]) / f.B;
     double var = __ldcg(&acc[D + i]) / f.B - m * m;
     if (var < 0.0) var = 0.0;
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(CW* RY) k_colstats(const float* __restrict__ U
     for (int i = 0; i < RY; ++i) t += sh[threadIdx.y][i][threadIdx.x];
     atomicAdd(&acc[(size_t)threadIdx.y * D + col], t);
   }
-  stat_finalize_if_last(fin, acc, D);
+  stat_finalize_if_last(fin, acc, D, blockIdx.x * CW, CW);
 }
 
 // Wide version (D % 4 == 0): 128-bit loads, 4 columns per thread, 2 rows in flight per thread.
@@ -110,12 +110,14 @@ __global__ void __launch_bounds__(CW* RY) k_colstats4(const float* __restrict__ 
     while (r < r1) {
       float ps[4] = {0.f, 0.f, 0.f, 0.f}, pss[4] = {0.f, 0.f, 0.f, 0.f};
       int chunk_end = min(r1, r + 32 * RY);
-      for (; r + RY < chunk_end; r += 2 * RY) {
+      for (; r + 3 * RY < chunk_end; r += 4 * RY) {
         const float4 a = __ldcs(reinterpret_cast<const float4*>(U + (size_t)r * D + col));
         const float4 b = __ldcs(reinterpret_cast<const float4*>(U + (size_t)(r + RY) * D + col));
-        float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        const float4 c = __ldcs(reinterpret_cast<const float4*>(U + (size_t)(r + 2 * RY) * D + col));
+        const float4 d = __ldcs(reinterpret_cast<const float4*>(U + (size_t)(r + 3 * RY) * D + col));
+        float v[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 16; ++j) {
           if (SQRT) v[j] = sqrt_count(v[j]);
           ps[j & 3] += v[j];
           pss[j & 3] = __fmaf_rn(v[j], v[j], pss[j & 3]);
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(CW* RY) k_colstats4(const float* __restrict__ 
     for (int i = 0; i < RY; ++i) t += sh[which][i][c];
     atomicAdd(&acc[(size_t)which * D + gcol], t);
   }
-  stat_finalize_if_last(fin, acc, D);
+  stat_finalize_if_last(fin, acc, D, blockIdx.x * CW * 4, CW * 4);
 }
 
 __global__ void k_colstats_finalize(const double* __restrict__ acc, int B, int D, float eps, float momentum,
@@ -250,8 +252,8 @@ void colstats(const float* U, int B, int D, bool sqrt_in, double* acc, unsigned 
   StatFinal fin{ticket, B, eps, momentum, mean, rstd, running_mean, running_var};
   if (D % 4 == 0 && D >= 512 && ((uintptr_t)U % 16) == 0) {
     int col_blocks = cdiv(D, CW * 4);
-    int S = cdiv(148 * 8, col_blocks);
-    int max_split = cdiv(B, RY * 4);
+    int S = cdiv(148 * 4, col_blocks);
+    int max_split = cdiv(B, RY * 32);
     if (S > max_split) S = max_split;
     if (S < 1) S = 1;
     int rows = cdiv(cdiv(B, S), RY) * RY;

@@ -145,7 +145,7 @@ Plan make_plan(const drv_dims& d, const Net& n) {
       const Block& b = s == 0 ? n.enc[k] : n.dec[k];
       p.stat_acc[s][k] = take(sizeof(double) * 2 * b.din);
       p.grad_acc[s][k] = take(sizeof(double) * 2 * b.din);
-      p.ticket[s][k] = take(256);
+      p.ticket[s][k] = take(4 * (size_t)(b.din / 32 + 2));  // one counter per column block of the statistics kernels
     }
   p.status = take(256);
   p.zero_bytes = o - p.zero_begin;
@@ -240,7 +240,7 @@ void block_forward(const Ctx& c, int s, int k, const float* U0, bool do_linear) 
 // produced (fused tcgen05 path).  The first encoder block needs no dU (x is data): its dY is
 // reduced to d gamma / d beta on the fly.
 void block_backward(const Ctx& c, int s, int k, const float* U0, const float* dV, bool linear_done) {
-  bool gated = true;  // false: Gb holds the ungated dAct and the BatchNorm backward applies the ReLU gate
+  bool gated = false;  // Gb holds the ungated dAct: the BatchNorm backward kernels apply the ReLU gate
   const int B = c.d.n_cells;
   const Block& b = s == 0 ? c.n.enc[k] : c.n.dec[k];
   const float* U = k == 0 ? U0 : c.at<float>(c.p.V[s][k - 1]);
