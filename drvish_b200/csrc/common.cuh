@@ -53,6 +53,52 @@ struct SideStream {
 };
 SideStream* side_stream();  // per-thread, created on first use (nullptr if creation failed)
 
+// Finalisation folded into the statistics kernel: the last CTA to finish (ticket counter) turns the
+// fp64 sums into mean / rstd and updates the running buffers (momentum, unbiased variance) - one
+// launch less per BatchNorm.
+struct StatFinal {
+  unsigned int* ticket;  // zeroed counter
+  int B;
+  float eps, momentum;
+  float *mean, *rstd, *rmean, *rvar;  // rmean/rvar may be null
+};
+
+// One ticket per column block (blockIdx.x): the last of its gridDim.y row-split CTAs finalises the
+// block's own columns [col0, col0 + ncols), so the finalisation is spread over gridDim.x CTAs.
+__device__ __forceinline__ void stat_finalize_if_last(const StatFinal& f, const double* acc, int D, int col0, int ncols) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (tid == 0) is_last = atomicAdd(f.ticket + blockIdx.x, 1u) == gridDim.y - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int nthr = blockDim.x * blockDim.y;
+  const int cend = min(D, col0 + ncols);
+  for (int i = col0 + tid; i < cend; i += nthr) {
+    const double m = __ldcg(&acc[i]) / f.B;
+    double var = __ldcg(&acc[D + i]) / f.B - m * m;
+    if (var < 0.0) var = 0.0;
+    f.mean[i] = (float)m;
+    // the fp64 part ends here (sum of squares minus squared mean); sqrt / divide in fp32 keep the
+    // single finalising CTA short
+    f.rstd[i] = 1.0f / sqrtf((float)(var + (double)f.eps));
+    if (f.rmean) {
+      const float unbiased = (float)var * ((float)f.B / (float)(f.B - 1));
+      f.rmean[i] = (1.0f - f.momentum) * f.rmean[i] + f.momentum * (float)m;
+      f.rvar[i] = (1.0f - f.momentum) * f.rvar[i] + f.momentum * unbiased;
+    }
+  }
+}
+
+// Where a producer kernel (the split-K reduction of a Linear) leaves the BatchNorm statistics of
+// its OUTPUT for the next block: acc = [2][D] zeroed fp64 sums.
+struct ColStatsOut {
+  double* acc;
+  StatFinal fin;
+};
+
 // BatchNorm -> ReLU applied to one element (modules.py:19-20).  Explicit fma so that the
 // forward value and the recomputed ReLU gate of the backward are bit-identical.
 struct BnParams {

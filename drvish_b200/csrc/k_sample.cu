@@ -141,7 +141,92 @@ __global__ void k_fill(float* __restrict__ out, int64_t n, uint64_t seed, uint64
     if (q * 4 + i < n) out[q * 4 + i] = v[i];
 }
 
+// All noise draws of one ELBO step in ONE launch (the five drv_fill_* calls + the prior scalings +
+// the counter bump).  Segment i covers blocks [blk0[i], blk0[i+1]); its values are exactly those of
+// the per-buffer generators at the same Philox offsets.  The last CTA to finish advances the step
+// counter (every CTA has read it before taking its ticket) and re-arms the ticket.
+struct NoiseSegs {
+  float* out[5];
+  long long n[5];
+  unsigned long long off[5];
+  float scale[5];
+  int laplace[5];
+  int blk0[6];
+};
+
+__device__ __forceinline__ void draw4(bool laplace, uint64_t seed, uint64_t ctr, float (&v)[4]) {
+  uint32_t r[4];
+  philox4(seed, ctr, r);
+  if (laplace) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float u = 2.f * u01(r[i]) - 1.f;
+      v[i] = -copysignf(1.f, u) * log1pf(-fabsf(u));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float rad = sqrtf(-2.f * logf(u01(r[2 * i])));
+      float s, co;
+      sincospif(2.f * u01(r[2 * i + 1]), &s, &co);
+      v[2 * i] = rad * co;
+      v[2 * i + 1] = rad * s;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_draw_step_noise(NoiseSegs sg, uint64_t seed, unsigned long long* state,
+                                                         uint64_t stride) {
+  int seg = 0;
+#pragma unroll
+  for (int i = 1; i < 5; ++i)
+    if ((int)blockIdx.x >= sg.blk0[i]) seg = i;
+  const unsigned long long step = *(volatile unsigned long long*)state;
+  int64_t q = (int64_t)(blockIdx.x - sg.blk0[seg]) * blockDim.x + threadIdx.x;
+  int64_t n = sg.n[seg];
+  if (q * 4 < n) {
+    float v[4];
+    draw4(sg.laplace[seg] != 0, seed, (sg.off[seg] + step * stride) / 4 + (uint64_t)q, v);
+    float* out = sg.out[seg];
+    float sc = sg.scale[seg];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (q * 4 + i < n) out[q * 4 + i] = v[i] * sc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(state + 1);
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+      *ticket = 0u;
+      *state = step + 1;
+    }
+  }
+}
+
 }  // namespace
+
+void draw_step_noise(float* const* outs, const int64_t* ns, const int* laplace, const float* scales, uint64_t seed,
+                     uint64_t offset, unsigned long long* state, uint64_t stride, cudaStream_t st) {
+  NoiseSegs sg{};
+  int blk = 0;
+  uint64_t off = offset;
+  for (int i = 0; i < 5; ++i) {
+    int64_t n = outs[i] ? ns[i] : 0;
+    sg.out[i] = outs[i];
+    sg.n[i] = n;
+    sg.off[i] = off;
+    sg.scale[i] = scales[i];
+    sg.laplace[i] = laplace[i];
+    sg.blk0[i] = blk;
+    blk += (int)cdiv(cdiv(n, 4), 256);
+    off += 4 * (uint64_t)cdiv(n, 4);
+  }
+  sg.blk0[5] = blk;
+  if (blk == 0) blk = 1;
+  k_draw_step_noise<<<blk, 256, 0, st>>>(sg, seed, state, stride);
+  note_launch();
+}
 
 void sample_forward(const float* O, const float* eps_z, const float* eps_l, int B, int L, const drv_hparams& hp,
                     float* z, float* l, drv_step_out* out, cudaStream_t st) {

@@ -49,6 +49,9 @@ void fill_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, const un
 void fill_laplace(float* out, int64_t n, uint64_t seed, uint64_t offset, const unsigned long long* ctr, uint64_t stride,
                   cudaStream_t st);
 void counter_add(unsigned long long* ctr, unsigned long long v, cudaStream_t st);
+// all five noise buffers of one step in one launch; state = {step counter, ticket}
+void draw_step_noise(float* const* outs, const int64_t* ns, const int* laplace, const float* scales, uint64_t seed,
+                     uint64_t offset, unsigned long long* state, uint64_t stride, cudaStream_t st);
 
 // ---- k_dr.cu: dose-response head ----------------------------------------------------------------
 struct DrShape {

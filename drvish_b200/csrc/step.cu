@@ -211,28 +211,42 @@ struct Ctx {
 
 // One BatchNorm1d -> ReLU -> Linear block, forward: batch statistics (+ running buffers), then
 // optionally the Linear with the BN/ReLU (and sqrt for the encoder input) applied in its prologue.
-void block_forward(const Ctx& c, int s, int k, const float* U0, bool do_linear) {
+// stats_done: the previous block's Linear already left this block's BatchNorm statistics (fused into
+// its split-K reduction).  Returns whether THIS block's Linear did the same for block k + 1.
+bool block_forward(const Ctx& c, int s, int k, const float* U0, bool do_linear, bool stats_done = false) {
   const int B = c.d.n_cells;
   const bool update = !(c.hp.flags & DRV_FLAG_NO_BN_UPDATE) && c.bnbuf;
   const Block& b = s == 0 ? c.n.enc[k] : c.n.dec[k];
   const float* U = k == 0 ? U0 : c.at<float>(c.p.V[s][k - 1]);
   const bool sq = (s == 0 && k == 0);
   double* acc = c.at<double>(c.p.stat_acc[s][k]);
-  colstats(U, B, b.din, sq, acc, c.at<unsigned int>(c.p.ticket[s][k]), c.hp.bn_eps, c.hp.bn_momentum,
-           c.at<float>(c.p.mean[s][k]), c.at<float>(c.p.rstd[s][k]), update ? c.bnbuf + b.rmean : nullptr,
-           update ? c.bnbuf + b.rvar : nullptr, c.st);
-  if (!do_linear) return;
+  if (!stats_done)
+    colstats(U, B, b.din, sq, acc, c.at<unsigned int>(c.p.ticket[s][k]), c.hp.bn_eps, c.hp.bn_momentum,
+             c.at<float>(c.p.mean[s][k]), c.at<float>(c.p.rstd[s][k]), update ? c.bnbuf + b.rmean : nullptr,
+             update ? c.bnbuf + b.rvar : nullptr, c.st);
+  if (!do_linear) return false;
   if (c.p.tcb[s][k] && tc_block_forward_supported(B, b.din, b.dout, c.hp) && (sq ? !(c.hp.flags & 32) : !(c.hp.flags & 8))) {
     TcBlockArgs a{};
     a.U = U; a.sqrt_in = sq; a.bn = c.bn(s, k); a.W = c.params + b.W; a.bias = c.params + b.bias;
     a.W_hi = c.at<float>(c.p.p_hi) + b.W; a.W_lo = c.at<float>(c.p.p_lo) + b.W;
     a.B = B; a.din = b.din; a.dout = b.dout; a.V = c.at<float>(c.p.V[s][k]); a.scratch = c.ws + c.p.tcb[s][k];
     a.no_fused_prologue = (c.hp.flags & 512) != 0;
-    tc_block_forward(a, c.st);
+    ColStatsOut ns{};
+    const int n_blocks = c.n.n_blocks;
+    if (k + 1 < n_blocks && !(c.hp.flags & 1024)) {  // 1024 (debug): separate statistics kernels
+      const Block& nb = s == 0 ? c.n.enc[k + 1] : c.n.dec[k + 1];
+      ns.acc = c.at<double>(c.p.stat_acc[s][k + 1]);
+      ns.fin = StatFinal{c.at<unsigned int>(c.p.ticket[s][k + 1]), B, c.hp.bn_eps, c.hp.bn_momentum,
+                         c.at<float>(c.p.mean[s][k + 1]), c.at<float>(c.p.rstd[s][k + 1]),
+                         update ? c.bnbuf + nb.rmean : nullptr, update ? c.bnbuf + nb.rvar : nullptr};
+      a.next_stats = &ns;
+    }
+    return tc_block_forward(a, c.st);
   } else {
     simt_linear_forward(U, B, b.din, sq ? 2 : 1, c.bn(s, k), c.params + b.W, c.params + b.bias, b.dout,
                         c.at<float>(c.p.V[s][k]), c.st);
   }
+  return false;
 }
 
 // Backward of block k given dV of its Linear: dW, db, then dY = (dV W) * relu-gate, then the
@@ -387,10 +401,21 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
   prof::mark(0, st);
   // tf32 hi / lo parts of every weight, one pass over the flat parameter buffer (the tensor-core
   // kernels take pre-rounded operands: kind::tf32 truncates)
-  if (!(hp->flags & DRV_FLAG_FORCE_SIMT))
-    split_params_tf32(params, (size_t)n.n_param_floats, c.at<float>(p.p_hi), c.at<float>(p.p_lo), st);
+  bool enc_sd = false;
+  if (!(hp->flags & DRV_FLAG_FORCE_SIMT)) {
+    if (side) {
+      // the parameter split and the statistics of x are independent: run them side by side
+      side->fork(st);
+      split_params_tf32(params, (size_t)n.n_param_floats, c.at<float>(p.p_hi), c.at<float>(p.p_lo), side->side);
+      block_forward(c, 0, 0, x, false);
+      enc_sd = true;
+      side->join(st);
+    } else {
+      split_params_tf32(params, (size_t)n.n_param_floats, c.at<float>(p.p_hi), c.at<float>(p.p_lo), st);
+    }
+  }
   // ---- guide: encoder + reparameterised draws (nbvae.py:81-90) --------------------------------
-  for (int k = 0; k < NB; ++k) block_forward(c, 0, k, x, true);
+  for (int k = 0; k < NB; ++k) enc_sd = block_forward(c, 0, k, x, true, enc_sd);
   const float* O = c.at<float>(p.V[0][NB - 1]);
   float* z = c.at<float>(p.z);
   float* l = c.at<float>(p.l);
@@ -420,8 +445,9 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
   // ---- model: decoder trunk (nbvae.py:70 -> modules.py:93) ------------------------------------
   const Block& last = n.dec[NB - 1];
   const bool use_tc = tc_decoder_supported(d, *hp) && !(hp->flags & 16);
-  for (int k = 0; k < NB - 1; ++k) block_forward(c, 1, k, z, true);
-  block_forward(c, 1, NB - 1, z, false);  // statistics of the last BatchNorm only
+  bool dec_sd = false;
+  for (int k = 0; k < NB - 1; ++k) dec_sd = block_forward(c, 1, k, z, true, dec_sd);
+  block_forward(c, 1, NB - 1, z, false, dec_sd);  // statistics of the last BatchNorm only
   prof::mark(2, st);
 
   // ---- last Linear + gene softmax + NB likelihood (modules.py:93-96, nbvae.py:72-78) ----------
@@ -557,7 +583,7 @@ int drv_encoder_forward(const drv_dims* dims, const drv_hparams* hp, const float
   cudaMemsetAsync(c.ws + p.zero_begin, 0, p.zero_bytes, st);
   if (!(hp->flags & DRV_FLAG_FORCE_SIMT))
     split_params_tf32(params, (size_t)n.n_param_floats, c.at<float>(p.p_hi), c.at<float>(p.p_lo), st);
-  for (int k = 0; k < n.n_blocks; ++k) block_forward(c, 0, k, x, true);
+  for (int k = 0, sd = 0; k < n.n_blocks; ++k) sd = block_forward(c, 0, k, x, true, sd);
   encoder_outputs(c.at<float>(p.V[0][n.n_blocks - 1]), dims->n_cells, dims->n_latent, z_loc, z_scale, l_loc, l_scale, st);
   if (bn_batches && !(hp->flags & DRV_FLAG_NO_BN_UPDATE)) bump_counters(bn_batches, n.n_blocks, st);
   return finish();
@@ -577,7 +603,7 @@ int drv_decoder_forward(const drv_dims* dims, const drv_hparams* hp, const float
   cudaMemsetAsync(c.ws + p.zero_begin, 0, p.zero_bytes, st);
   if (!(hp->flags & DRV_FLAG_FORCE_SIMT))
     split_params_tf32(params, (size_t)n.n_param_floats, c.at<float>(p.p_hi), c.at<float>(p.p_lo), st);
-  for (int k = 0; k < n.n_blocks; ++k) block_forward(c, 1, k, z, true);
+  for (int k = 0, sd = 0; k < n.n_blocks; ++k) sd = block_forward(c, 1, k, z, true, sd);
   nb_decoder_outputs(c.at<float>(p.V[1][n.n_blocks - 1]), library, dims->n_cells, dims->n_genes, log_r, logit, st);
   if (bn_batches && !(hp->flags & DRV_FLAG_NO_BN_UPDATE)) bump_counters(bn_batches + n.n_blocks, n.n_blocks, st);
   return finish();
@@ -605,6 +631,23 @@ int drv_fill_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, const
   g_err = cudaSuccess;
   if (!out || n < 0) return DRV_EINVAL;
   fill_normal(out, n, seed, offset, (const unsigned long long*)step_counter, stride, (cudaStream_t)stream);
+  return finish();
+}
+
+int drv_draw_step_noise(const drv_dims* dims, const drv_hparams* hp, uint64_t seed, uint64_t offset, uint64_t* state,
+                        uint64_t stride, float* eps_z, float* eps_l, float* w_prior, float* b_prior, float* eps_bias,
+                        void* stream) {
+  g_launches = 0;
+  g_err = cudaSuccess;
+  if (!dims || !hp || !state || !eps_z || !eps_l) return DRV_EINVAL;
+  const bool dr = dims->n_drugs > 0;
+  if (dr && (!w_prior || !b_prior || !eps_bias)) return DRV_EINVAL;
+  float* outs[5] = {eps_z, eps_l, dr ? w_prior : nullptr, dr ? b_prior : nullptr, dr ? eps_bias : nullptr};
+  int64_t ns[5] = {(int64_t)dims->n_cells * dims->n_latent, dims->n_cells, (int64_t)dims->n_drugs * dims->n_latent,
+                   dims->n_doses_total, dims->n_doses_total};
+  int lap[5] = {0, 0, 1, 0, 0};
+  float sc[5] = {1.f, 1.f, hp->lam_scale, hp->bias_scale, 1.f};
+  draw_step_noise(outs, ns, lap, sc, seed, offset, (unsigned long long*)state, stride, (cudaStream_t)stream);
   return finish();
 }
 

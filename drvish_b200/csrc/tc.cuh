@@ -23,6 +23,7 @@ struct TcDecoderArgs {
   float *dW, *db;     // [2G][h], [2G]
   float* dY;          // [B][h]: d loss / d (BN output), already gated by the ReLU mask
   SideStream* side;   // optional: weight-gradient GEMM runs there
+  const ColStatsOut* next_stats;  // optional: BatchNorm statistics of V for the next block
 };
 
 size_t tc_workspace_bytes(const drv_dims& d);
@@ -36,17 +37,23 @@ namespace drv {
 namespace tc {
 int gemm_tf32(const float* A, int lda, bool a_mn, const float* Bm, int ldb, bool b_mn, float* C, int ldc, int M, int N,
               int K, int max_ctas, bool accumulate, cudaStream_t st);
-void reduce_parts(const float* parts, int n_parts, int M, int N, const float* bias, float* C, int ldc, cudaStream_t st);
+// C = bias + sum of the k-part slabs in index order; with `stats` also the column sums / sums of squares
+// of C and (last CTA) mean / rstd / running buffers of the BatchNorm that consumes C.  Returns true
+// when the statistics were produced.
+bool reduce_parts(const float* parts, int n_parts, int M, int N, const float* bias, float* C, int ldc, cudaStream_t st,
+                  const ColStatsOut* stats = nullptr);
 // Encoder-input Linear forward with the sqrt / BatchNorm / ReLU / hi-lo split prologue fused into the
 // GEMM (tc_encfwd.cu).  Writes V = relu(bn(sqrt(x))) W^T + b and the tf32 'hi' part of the activations.
 int encfwd_fused(const float* x, int B, int G, BnParams bn, const float* w_hi, const float* w_lo, int h,
-                 const float* bias, float* V, float* a_hi, float* partials, int max_parts, cudaStream_t st);
+                 const float* bias, float* V, float* a_hi, float* partials, int max_parts, cudaStream_t st,
+                 const ColStatsOut* stats = nullptr);  // returns 1 when `stats` were produced
 // d gamma / d beta sums of the encoder's input BatchNorm from dH and W without materialising dA (tc_bn0grad.cu)
 int bn0grad_fused(const float* dH_r, const float* W_hi, const float* x, int B, int G, int h, BnParams bn, double* gacc,
                   cudaStream_t st);
 int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs, int lda, bool a_mn, int ldb, bool b_mn,
                     float* C, int ldc, int M, int N, int K, int max_ctas, bool accumulate, const float* bias,
-                    cudaStream_t st, int max_chain_kb = 0, float* partials = nullptr, int max_parts = 0);
+                    cudaStream_t st, int max_chain_kb = 0, float* partials = nullptr, int max_parts = 0,
+                    const ColStatsOut* stats = nullptr);  // returns 1 when `stats` were produced
 }
 
 // One BatchNorm -> ReLU -> Linear block (reference modules.py:19-21) on the tensor cores: 3xTF32
@@ -68,11 +75,12 @@ struct TcBlockArgs {
   float* dY;          // [B][din]: d loss / d (BN output), ReLU-gated; NULL -> reduce to gacc instead
   double* gacc;       // [2][din]: sum_b dY, sum_b dY*xhat  (-> d beta, d gamma), used when dY == NULL
   SideStream* side;   // optional: weight-gradient GEMM runs there
+  const ColStatsOut* next_stats;  // optional: BatchNorm statistics of V for the next block
 };
 size_t tc_block_workspace_bytes(int B, int din, int dout);
 bool tc_block_forward_supported(int B, int din, int dout, const drv_hparams& hp);
 bool tc_block_backward_supported(int B, int din, int dout, const drv_hparams& hp);
-void tc_block_forward(const TcBlockArgs& a, cudaStream_t st);
+bool tc_block_forward(const TcBlockArgs& a, cudaStream_t st);  // true: next_stats were produced
 void tc_block_backward(const TcBlockArgs& a, cudaStream_t st);
 // hi = rna_tf32(src), lo = rna_tf32(src - hi) over the whole flat parameter buffer
 void split_params_tf32(const float* src, size_t n, float* hi, float* lo, cudaStream_t st);

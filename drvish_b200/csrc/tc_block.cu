@@ -224,14 +224,15 @@ bool tc_block_backward_supported(int B, int din, int dout, const drv_hparams& hp
   return tc_block_forward_supported(B, din, dout, hp) && dout % 4 == 0;
 }
 
-void tc_block_forward(const TcBlockArgs& a, cudaStream_t st) {
+bool tc_block_forward(const TcBlockArgs& a, cudaStream_t st) {
   Scratch s = carve(a.scratch, a.B, a.din, a.dout);
   const size_t n = (size_t)a.B * a.din;
   if (a.sqrt_in && !a.no_fused_prologue) {
     // encoder input layer: sqrt / BatchNorm / ReLU / hi-lo split fused into the GEMM's producer side
-    int rc = tc::encfwd_fused(a.U, a.B, a.din, a.bn, a.W_hi, a.W_lo, a.dout, a.bias, a.V, s.a_hi, s.parts, kMaxParts, st);
-    if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
-    return;
+    int rc = tc::encfwd_fused(a.U, a.B, a.din, a.bn, a.W_hi, a.W_lo, a.dout, a.bias, a.V, s.a_hi, s.parts, kMaxParts, st,
+                              a.next_stats);
+    if (rc < 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
+    return rc == 1;
   }
   int blocks = (int)((n / 4 + 255) / 256);
   if (blocks > n_sm() * 8) blocks = n_sm() * 8;
@@ -241,8 +242,9 @@ void tc_block_forward(const TcBlockArgs& a, cudaStream_t st) {
   const float* As[3] = {s.a_lo, s.a_hi, s.a_hi};
   const float* Bs[3] = {a.W_hi, a.W_lo, a.W_hi};
   int rc = tc::gemm_tf32_multi(3, As, Bs, a.din, false, a.din, false, a.V, a.dout, a.B, a.dout, a.din, 0, false, a.bias, st,
-                               /*max_chain_kb=*/32, s.parts, kMaxParts);
-  if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
+                               /*max_chain_kb=*/32, s.parts, kMaxParts, a.next_stats);
+  if (rc < 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
+  return rc == 1;
 }
 
 void tc_block_backward(const TcBlockArgs& a, cudaStream_t st) {

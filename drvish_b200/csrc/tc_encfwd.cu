@@ -320,7 +320,8 @@ int sms() {
 }  // namespace
 
 int encfwd_fused(const float* x, int B, int G, BnParams bn, const float* w_hi, const float* w_lo, int h,
-                 const float* bias, float* V, float* a_hi, float* partials, int max_parts, cudaStream_t st) {
+                 const float* bias, float* V, float* a_hi, float* partials, int max_parts, cudaStream_t st,
+                 const ColStatsOut* stats) {
   CUtensorMap tX, tWh, tWl, tA;
   const int n_tile = h >= BN ? BN : ((h + 15) / 16) * 16;
   if (!tmap_2d(&tX, x, B, G, G, BM, BK)) return -3;
@@ -350,7 +351,7 @@ int encfwd_fused(const float* x, int B, int G, BnParams bn, const float* w_hi, c
     k_encfwd<<<grid, NTHREADS, SMEM_BYTES, st>>>(tX, tWh, tWl, tA, bn, B, G, h, n_tile, splits, partials,
                                                  (long long)B * h, nullptr);
     note_launch();
-    reduce_parts(partials, splits, B, h, bias, V, h, st);
+    return reduce_parts(partials, splits, B, h, bias, V, h, st, stats) ? 1 : 0;
   } else {
     k_encfwd<<<grid, NTHREADS, SMEM_BYTES, st>>>(tX, tWh, tWl, tA, bn, B, G, h, n_tile, 1, V, 0LL, bias);
     note_launch();

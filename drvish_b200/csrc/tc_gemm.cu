@@ -270,6 +270,61 @@ __global__ void k_reduce_parts(const float* __restrict__ parts, int n_parts, siz
   }
 }
 
+// Same sums (same part order, so C is bit-identical to k_reduce_parts) + BatchNorm statistics of C:
+// block (64 column quads, 4 row lanes), grid (1, row splits); each thread folds <= 32 rows in fp32,
+// the CTA folds its row lanes in fp64 and issues one double atomic per column and moment; the last
+// CTA finalises mean / rstd / running buffers (stat_finalize_if_last).  Requires N % 4 == 0, ldc % 4 == 0.
+__global__ void __launch_bounds__(256) k_reduce_parts_stats(const float* __restrict__ parts, int n_parts, int M, int N,
+                                                            const float* __restrict__ bias, float* __restrict__ C, int ldc,
+                                                            int rows_per_cta, double* __restrict__ acc, StatFinal fin) {
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  const size_t mn = (size_t)M * N;
+  __shared__ float sh[2][4][256];
+  for (int cq0 = 0; cq0 < N / 4; cq0 += 64) {
+    const int cq = cq0 + tx;
+    float ps[4] = {0.f, 0.f, 0.f, 0.f}, pss[4] = {0.f, 0.f, 0.f, 0.f};
+    if (cq < N / 4) {
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias) bv = *reinterpret_cast<const float4*>(bias + cq * 4);
+      for (int m = r0 + ty; m < r1; m += 4) {
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* src = parts + (size_t)m * N + cq * 4;
+        for (int p = 0; p < n_parts; ++p) {
+          const float4 v = __ldcs(reinterpret_cast<const float4*>(src + (size_t)p * mn));
+          a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
+        }
+        a[0] += bv.x; a[1] += bv.y; a[2] += bv.z; a[3] += bv.w;
+        *reinterpret_cast<float4*>(C + (size_t)m * ldc + cq * 4) = make_float4(a[0], a[1], a[2], a[3]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ps[j] += a[j];
+          pss[j] = __fmaf_rn(a[j], a[j], pss[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sh[0][ty][tx * 4 + j] = ps[j];
+      sh[1][ty][tx * 4 + j] = pss[j];
+    }
+    __syncthreads();
+    const int tid = ty * 64 + tx;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const int col = cq0 * 4 + tid;
+      if (col < N) {
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t += (double)sh[which][i][tid];
+        atomicAdd(&acc[(size_t)which * N + col], t);
+      }
+    }
+    __syncthreads();
+  }
+  stat_finalize_if_last(fin, acc, N, 0, N);
+}
+
 static int n_sm_tc() {
   static int n = 0;
   if (!n) {
@@ -288,7 +343,7 @@ static int n_sm_tc() {
 // first when stream-K splits a tile over several CTAs).  max_ctas <= 0: one CTA per SM.
 int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs, int lda, bool a_mn, int ldb, bool b_mn,
                     float* C, int ldc, int M, int N, int K, int max_ctas, bool accumulate, const float* bias,
-                    cudaStream_t st, int max_chain_kb, float* partials, int max_parts) {
+                    cudaStream_t st, int max_chain_kb, float* partials, int max_parts, const ColStatsOut* stats) {
   if (n_pairs < 1 || n_pairs > 3) return -3;
   CUtensorMap ta[3], tb[3];
   const int nq = b_mn ? 32 : 16;  // an MN-major B is staged in 32-column boxes
@@ -373,28 +428,35 @@ int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs,
     else launch(k_tc_gemm<false, false, 2>);
   }
   note_launch();
-  if (deterministic && split) {
-    const size_t n4 = ((size_t)M * N + 3) / 4;
-    int blocks = (int)((n4 + 255) / 256);
-    if (blocks > n_sm_tc() * 8) blocks = n_sm_tc() * 8;
-    k_reduce_parts<<<blocks, 256, 0, st>>>(partials, splits, (size_t)M * N, N, bias, C, ldc);
-    note_launch();
-  }
+  if (deterministic && split) return reduce_parts(partials, splits, M, N, bias, C, ldc, st, stats) ? 1 : 0;
   return 0;
 }
 
-void reduce_parts(const float* parts, int n_parts, int M, int N, const float* bias, float* C, int ldc, cudaStream_t st) {
+bool reduce_parts(const float* parts, int n_parts, int M, int N, const float* bias, float* C, int ldc, cudaStream_t st,
+                  const ColStatsOut* stats) {
+  if (stats && N % 4 == 0 && ldc % 4 == 0 && M > 1) {
+    int R = (M + 15) / 16;
+    if (R > n_sm_tc() * 4) R = n_sm_tc() * 4;
+    if (R < (M + 127) / 128) R = (M + 127) / 128;  // <= 32 rows per thread in the fp32 partial sums
+    const int rows_per_cta = (M + R - 1) / R;
+    R = (M + rows_per_cta - 1) / rows_per_cta;
+    k_reduce_parts_stats<<<dim3(1, R), dim3(64, 4), 0, st>>>(parts, n_parts, M, N, bias, C, ldc, rows_per_cta, stats->acc,
+                                                             stats->fin);
+    note_launch();
+    return true;
+  }
   const size_t n4 = ((size_t)M * N + 3) / 4;
   int blocks = (int)((n4 + 255) / 256);
   if (blocks > n_sm_tc() * 8) blocks = n_sm_tc() * 8;
   k_reduce_parts<<<blocks, 256, 0, st>>>(parts, n_parts, (size_t)M * N, N, bias, C, ldc);
   note_launch();
+  return false;
 }
 
 int gemm_tf32(const float* A, int lda, bool a_mn, const float* Bm, int ldb, bool b_mn, float* C, int ldc, int M, int N,
               int K, int max_ctas, bool accumulate, cudaStream_t st) {
   return gemm_tf32_multi(1, &A, &Bm, lda, a_mn, ldb, b_mn, C, ldc, M, N, K, max_ctas, accumulate, nullptr, st, 0, nullptr,
-                         0);
+                         0, nullptr);
 }
 
 }  // namespace tc

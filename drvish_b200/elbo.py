@@ -91,26 +91,16 @@ class FusedTraceELBO:
 
         lib, st = rt.lib, _stream(dev)
         if self._step_ctr is None or self._step_ctr.device != dev:
-            self._step_ctr = torch.full((1,), self.step_index, dtype=torch.int64, device=dev)
-        ctr = _ptr(self._step_ctr)
+            # {step counter, launch ticket}; the draw kernel advances the counter itself
+            self._step_ctr = torch.tensor([self.step_index, 0], dtype=torch.int64, device=dev)
         per_step = 4 * ((B * L + 3) // 4 + (B + 3) // 4 + (D * L + 3) // 4 + 2 * ((T + 3) // 4))
         rank = torch.distributed.get_rank() if self._dp_enabled() else 0
-        stride = C.c_uint64(4096 * per_step)
-        off = rank * per_step
-        seed = C.c_uint64(self.seed)
-        _lib.check(lib.drv_fill_normal(_ptr(bufs["eps_z"]), B * L, seed, C.c_uint64(off), ctr, stride, st), "drv_fill_normal")
-        off += 4 * ((B * L + 3) // 4)
-        _lib.check(lib.drv_fill_normal(_ptr(bufs["eps_l"]), B, seed, C.c_uint64(off), ctr, stride, st), "drv_fill_normal")
-        off += 4 * ((B + 3) // 4)
-        if D:
-            _lib.check(lib.drv_fill_laplace(_ptr(bufs["w_prior"]), D * L, seed, C.c_uint64(off), ctr, stride, st), "drv_fill_laplace")
-            off += 4 * ((D * L + 3) // 4)
-            _lib.check(lib.drv_fill_normal(_ptr(bufs["b_prior"]), T, seed, C.c_uint64(off), ctr, stride, st), "drv_fill_normal")
-            off += 4 * ((T + 3) // 4)
-            _lib.check(lib.drv_fill_normal(_ptr(bufs["eps_bias"]), T, seed, C.c_uint64(off), ctr, stride, st), "drv_fill_normal")
-            bufs["w_prior"].mul_(rt.lmbs[0].lam_scale)
-            bufs["b_prior"].mul_(rt.lmbs[0].prior_bias_scale)
-        _lib.check(lib.drv_counter_add(ctr, C.c_uint64(1), st), "drv_counter_add")
+        dims, hp = rt.dims(B), rt.hparams()
+        _lib.check(lib.drv_draw_step_noise(C.byref(dims), C.byref(hp), C.c_uint64(self.seed), C.c_uint64(rank * per_step),
+                                           _ptr(self._step_ctr), C.c_uint64(4096 * per_step), _ptr(bufs["eps_z"]),
+                                           _ptr(bufs["eps_l"]), _ptr(bufs["w_prior"]) if D else None,
+                                           _ptr(bufs["b_prior"]) if D else None, _ptr(bufs["eps_bias"]) if D else None,
+                                           st), "drv_draw_step_noise")
         return bufs
 
     # -- helpers ----------------------------------------------------------------------------

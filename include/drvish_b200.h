@@ -144,6 +144,17 @@ int drv_fill_laplace(float* out, int64_t n, uint64_t seed, uint64_t offset, cons
                      void* stream);
 int drv_counter_add(uint64_t* counter, uint64_t v, void* stream);
 
+/* All noise draws of one ELBO step in a single launch, in the reference's draw order (latent,
+ * library - nbvae.py:89-90; then weight_p ~ Laplace(0, lam_scale), bias_p ~ Normal(0, bias_scale),
+ * and the unit-normal of the guide's bias - modules.py:130-135,152-157).  Buffer k starts at Philox
+ * offset `offset` + sum of the 4-rounded sizes before it, so the values equal those of
+ * drv_fill_normal / drv_fill_laplace at the same offsets (times the prior scale).  state is a
+ * device uint64[2] = {step counter, 0}: the step counter is advanced by one when the launch
+ * completes.  The three dose-response buffers may be NULL when dims->n_drugs == 0. */
+int drv_draw_step_noise(const drv_dims* dims, const drv_hparams* hp, uint64_t seed, uint64_t offset, uint64_t* state,
+                        uint64_t stride, float* eps_z, float* eps_l, float* w_prior, float* b_prior, float* eps_bias,
+                        void* stream);
+
 /* Section timing with CUDA events recorded on the step's stream (bench.py's live roofline
  * measurement).  drv_profile_enable(1) arms it (up to 64 steps are kept); drv_profile_read
  * synchronises on the recorded events and returns the mean milliseconds per section. */

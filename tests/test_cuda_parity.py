@@ -211,6 +211,41 @@ def test_production_noise_path_runs_and_is_seeded():
     assert all(torch.isfinite(torch.tensor(l)).all() for l in losses)
 
 
+def test_fused_noise_draw_equals_the_per_buffer_generators():
+    """drv_draw_step_noise = the five drv_fill_* calls at consecutive Philox offsets, the prior scalings
+    and the counter bump, in one launch."""
+    import ctypes as C
+
+    from drvish_b200 import _lib
+    from drvish_b200.runtime import make_dims
+
+    lib = _lib.load()
+    B, L, D, T = 300, 6, 3, 13
+    dims = make_dims(B, 64, L, [32], D, 4, T)
+    hp = _lib.HParams()
+    hp.lam_scale, hp.bias_scale = 0.37, 2.5
+    sizes = [B * L, B, D * L, T, T]
+    per_step = sum(4 * ((n + 3) // 4) for n in sizes)
+    state = torch.tensor([3, 0], dtype=torch.int64, device="cuda")
+    fused = [torch.empty(n, device="cuda") for n in sizes]
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+    for rep in range(2):
+        step = 3 + rep
+        _lib.check(lib.drv_draw_step_noise(C.byref(dims), C.byref(hp), C.c_uint64(9), C.c_uint64(2 * per_step), ptr(state),
+                                           C.c_uint64(4096 * per_step), *[ptr(t) for t in fused], st), "draw")
+        ctr = torch.tensor([step], dtype=torch.int64, device="cuda")
+        off = 2 * per_step
+        for k, n in enumerate(sizes):
+            ref = torch.empty(n, device="cuda")
+            fn = lib.drv_fill_laplace if k == 2 else lib.drv_fill_normal
+            _lib.check(fn(ptr(ref), n, C.c_uint64(9), C.c_uint64(off), ptr(ctr), C.c_uint64(4096 * per_step), st), "fill")
+            off += 4 * ((n + 3) // 4)
+            scale = {2: 0.37, 3: 2.5}.get(k, 1.0)
+            assert torch.equal(fused[k], ref * scale), (rep, k)
+        assert state.tolist() == [step + 1, 0]
+
+
 def test_cuda_graph_replay_matches_direct_launches():
     """The graph path (captured on the second use of a batch buffer, replayed afterwards) must give the
     same losses and gradients as direct launches: the Philox step counter lives in device memory."""
