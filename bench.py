@@ -289,31 +289,39 @@ def run_native(args, cfg):
     # ---- end-to-end through the public API, host minibatches --------------------------------
     # every step's inputs start in pinned HOST memory; PinnedBatchPrefetcher issues the H2D copy of
     # batch i+1 on a side stream while step i runs; loss_and_grads reads the loss back (D2H) each step
-    from drvish_b200.data import PinnedBatchPrefetcher
+    from drvish_b200.data import PinnedBatchPrefetcher, pack_batches
 
     host_x = [xs[i].cpu().pin_memory() for i in range(min(4, n_batches))]
     e2e_steps = max(10, args.steps // 2)
+    tail = [labels, y] if cfg["drugs"] else []
+    fp32_set = [[hx] + tail for hx in host_x]
+    # the same minibatches packed once to 16 bits (dataset-build-time work, lossless: data.PackedCounts)
+    u16_set = pack_batches(fp32_set)
 
-    def host_batches(n):
-        for i in range(n):
-            yield [host_x[i % len(host_x)]] + ([labels, y] if cfg["drugs"] else [])
-
-    def run_e2e(n):
+    def run_e2e(pf, dataset, n):
+        pf.batches = (dataset[i % len(dataset)] for i in range(n))
         last = None
-        for batch in PinnedBatchPrefetcher(host_batches(n), device):
+        for batch in pf:
             last = elbo.loss_and_grads(model.model, model.guide, *batch)
         return last
 
-    run_e2e(8)  # untimed: both staging buffers get their CUDA graph
-    barrier()
-    t0 = time.perf_counter()
-    run_e2e(e2e_steps)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * e2e_steps / float(t.item())
+    def time_e2e(dataset, on_the_fly=False):
+        pf = PinnedBatchPrefetcher(None, device, pack_on_the_fly=on_the_fly)
+        run_e2e(pf, dataset, 3 * pf.SLOTS)  # untimed: every staging slot gets its CUDA graph
+        barrier()
+        pf.h2d_bytes = 0
+        t0 = time.perf_counter()
+        run_e2e(pf, dataset, e2e_steps)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return world * B * e2e_steps / float(t.item()), pf.h2d_bytes // e2e_steps
+
+    e2e_value, e2e_h2d = time_e2e(fp32_set)
+    e2e_u16, e2e_u16_h2d = time_e2e(u16_set)
+    e2e_fly, e2e_fly_h2d = time_e2e(fp32_set, on_the_fly=True)
 
     if rank != 0:
         if world > 1:
@@ -388,9 +396,14 @@ def run_native(args, cfg):
                    "parallelism": f"dp{world}", "l2": f"inputs rotate over {n_batches} resident minibatches "
                    f"({n_batches * B * G * 4 / 1e9:.2f} GB > 126 MB L2), no flush", "optimizer": "excluded",
                    "noise": "Philox in-kernel draws each step", "cuda_graph": not args.no_graph},
-        "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": B * G * 4, "d2h_bytes_per_step": 16,
+        "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": e2e_h2d, "d2h_bytes_per_step": 16,
                 "steps": e2e_steps, "api": "FusedTraceELBO.loss_and_grads(model.model, model.guide, *batch) fed by PinnedBatchPrefetcher "
-                       "(pinned host fp32 minibatches, H2D of batch i+1 overlapped with step i)"},
+                       "(pinned host fp32 minibatches, H2D of the batches ahead overlapped with the running step)",
+                "bound": "PCIe: %.1f GB/s host->device" % (e2e_h2d * e2e_value / (world * B) / 1e9),
+                # same API, minibatches packed ONCE to lossless uint16 when the dataset is built
+                "packed_u16_dataset": {"value": e2e_u16, "unit": "cells/s", "h2d_bytes_per_step": e2e_u16_h2d},
+                # same API, fp32 host minibatches packed by the prefetcher's worker thread every step
+                "packed_u16_on_the_fly": {"value": e2e_fly, "unit": "cells/s", "h2d_bytes_per_step": e2e_fly_h2d}},
         "gpu_launches": launches_per_step * args.steps,
         "launches_per_step": launches_per_step,
         "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "loss_last": loss_last, "status": status,

@@ -22,6 +22,34 @@ inline void note_launch() {
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Programmatic dependent launch: every kernel of the step is launched with the "programmatic stream
+// serialization" attribute and starts with pdl_prologue().  launch_dependents lets the NEXT kernel of
+// the stream be scheduled as soon as all CTAs of this one are resident (its launch latency and CTA
+// start-up overlap this kernel's execution); griddepcontrol.wait then blocks until the PREVIOUS
+// kernel has completed and flushed its memory, so data dependencies are exactly those of plain
+// stream order.  The step is a chain of ~60 short kernels: this removes most of the per-boundary
+// bubble.  DRV_PDL=0 in the environment turns the attribute off (the instructions are then no-ops).
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<Args&&>(args)...);
+}
+
 // Side stream for work that is off the critical chain of a step (weight-gradient GEMMs, the
 // dose-response head): forked from / joined to the caller's stream with events, so the whole step
 // still looks like one stream to the caller (and is CUDA-graph capturable).

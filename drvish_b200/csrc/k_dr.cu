@@ -24,6 +24,7 @@ __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-
 
 __global__ void k_dr_project(const float* __restrict__ z, const float* __restrict__ w, int B, int L, int D,
                              float* __restrict__ u) {
+  pdl_prologue();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * D) return;
   int b = idx / D, i = idx % D;
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(256) k_dr_means(const float* __restrict__ u, c
                                                   DrShape s, const float* __restrict__ y, float sigma,
                                                   float* __restrict__ m_out, float* __restrict__ gfac,
                                                   drv_step_out* out, uint32_t* status) {
+  pdl_prologue();
   extern __shared__ float sh[];  // [K] sums, [K] counts
   float* acc = sh;
   float* cnt = sh + s.K;
@@ -83,6 +85,7 @@ __global__ void __launch_bounds__(256) k_dr_means(const float* __restrict__ u, c
 __global__ void k_dr_du(const float* __restrict__ u, const float* __restrict__ bias, const int64_t* __restrict__ labels,
                         const int32_t* __restrict__ off, const float* __restrict__ gfac, DrShape s,
                         float* __restrict__ du) {
+  pdl_prologue();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= s.B * s.D) return;
   int b = idx / s.D, i = idx % s.D;
@@ -100,6 +103,7 @@ __global__ void k_dr_du(const float* __restrict__ u, const float* __restrict__ b
 
 __global__ void k_dr_dz(const float* __restrict__ du, const float* __restrict__ w, int B, int L, int D,
                         float* __restrict__ dz) {
+  pdl_prologue();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * L) return;
   int b = idx / L, d = idx % L;
@@ -115,6 +119,7 @@ __global__ void __launch_bounds__(256) k_dr_prior_factor(const float* __restrict
                                                          const int32_t* __restrict__ off, DrShape s, float lam, float bsc,
                                                          float alpha, int include_factor, float* __restrict__ d_bias_loc,
                                                          float* __restrict__ d_bias_scale_unc, drv_step_out* out) {
+  pdl_prologue();
   double t = 0.0;  // contribution to the LOSS (= -ELBO)
   for (int j = threadIdx.x; j < s.D * s.L; j += blockDim.x)
     t -= (double)(-logf(2.f * lam) - fabsf(w_prior[j]) / lam);  // Laplace(0, lam).log_prob
@@ -161,28 +166,28 @@ __global__ void __launch_bounds__(256) k_dr_prior_factor(const float* __restrict
 }  // namespace
 
 void dr_project(const float* z, const float* w, DrShape s, float* u, cudaStream_t st) {
-  k_dr_project<<<cdiv((int64_t)s.B * s.D, 256), 256, 0, st>>>(z, w, s.B, s.L, s.D, u);
+  launch_k(k_dr_project, cdiv((int64_t)s.B * s.D, 256), 256, 0, st, z, w, s.B, s.L, s.D, u);
   note_launch();
 }
 
 void dr_means(const float* u, const float* bias, const int64_t* labels, const int32_t* dose_off, DrShape s,
               const float* y, float sigma, float* m, float* gfac, drv_step_out* out, uint32_t* status, cudaStream_t st) {
-  k_dr_means<<<s.T, 256, 2 * s.K * sizeof(float), st>>>(u, bias, labels, dose_off, s, y, sigma, m, gfac, out, status);
+  launch_k(k_dr_means, s.T, 256, 2 * s.K * sizeof(float), st, u, bias, labels, dose_off, s, y, sigma, m, gfac, out, status);
   note_launch();
 }
 
 void dr_backward(const float* u, const float* bias, const float* w, const int64_t* labels, const int32_t* dose_off,
                  const float* gfac, DrShape s, float* du, float* dz, cudaStream_t st) {
-  k_dr_du<<<cdiv((int64_t)s.B * s.D, 256), 256, 0, st>>>(u, bias, labels, dose_off, gfac, s, du);
+  launch_k(k_dr_du, cdiv((int64_t)s.B * s.D, 256), 256, 0, st, u, bias, labels, dose_off, gfac, s, du);
   note_launch();
-  k_dr_dz<<<cdiv((int64_t)s.B * s.L, 256), 256, 0, st>>>(du, w, s.B, s.L, s.D, dz);
+  launch_k(k_dr_dz, cdiv((int64_t)s.B * s.L, 256), 256, 0, st, du, w, s.B, s.L, s.D, dz);
   note_launch();
 }
 
 void dr_prior_factor(const float* w_prior, const float* b_prior, const float* eps_bias, const float* bias_loc,
                      const float* bias_scale_unc, const int32_t* dose_off, DrShape s, const drv_hparams& hp,
                      float* d_bias_loc, float* d_bias_scale_unc, drv_step_out* out, cudaStream_t st) {
-  k_dr_prior_factor<<<1, 256, 0, st>>>(w_prior, b_prior, eps_bias, bias_loc, bias_scale_unc, dose_off, s, hp.lam_scale,
+  launch_k(k_dr_prior_factor, 1, 256, 0, st, w_prior, b_prior, eps_bias, bias_loc, bias_scale_unc, dose_off, s, hp.lam_scale,
                                        hp.bias_scale, hp.alpha, hp.include_guide_factor, d_bias_loc, d_bias_scale_unc,
                                        out);
   note_launch();

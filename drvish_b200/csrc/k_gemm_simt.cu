@@ -44,6 +44,7 @@ template <bool AK, bool BKC, bool ONES, int EPI>
 __global__ void __launch_bounds__(NT) k_gemm(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
                                             float* __restrict__ C, int ldc, int M, int N, int K, Prologue proA,
                                             Prologue proB, Epilogue ep) {
+  pdl_prologue();
   __shared__ __align__(16) float As[BK][BM + PAD];
   __shared__ __align__(16) float Bs[BK][BN + PAD];
   const int tid = threadIdx.x;
@@ -198,7 +199,7 @@ void simt_linear_forward(const float* U, int B, int din, int pro_mode, BnParams 
   Prologue pa{pro_mode, bn}, pb{0, {}};
   Epilogue ep{};
   ep.bias = bias;
-  k_gemm<true, true, false, EPI_BIAS><<<grid_for(B, dout), NT, 0, st>>>(U, din, W, din, V, dout, B, dout, din, pa, pb, ep);
+  launch_k(k_gemm<true, true, false, EPI_BIAS>, grid_for(B, dout), NT, 0, st, U, din, W, din, V, dout, B, dout, din, pa, pb, ep);
   note_launch();
 }
 
@@ -223,7 +224,7 @@ void simt_linear_wgrad(const float* dV, int B, int dout, const float* U, int din
     cudaMemsetAsync(db, 0, sizeof(float) * (size_t)dout, st);
     grid.z = splits;
   }
-  k_gemm<false, false, true, EPI_DW><<<grid, NT, 0, st>>>(dV, dout, U, din, dW, din, dout, din + 1, B, pa, pb, ep);
+  launch_k(k_gemm<false, false, true, EPI_DW>, grid, NT, 0, st, dV, dout, U, din, dW, din, dout, din + 1, B, pa, pb, ep);
   note_launch();
 }
 
@@ -233,7 +234,7 @@ void simt_linear_dgrad_gate(const float* dV, int B, int dout, const float* W, in
   (void)U; (void)pro_mode; (void)bn;
   Prologue none{0, {}};
   Epilogue ep{};
-  k_gemm<true, false, false, EPI_PLAIN><<<grid_for(B, din), NT, 0, st>>>(dV, dout, W, din, dY, din, B, din, dout, none,
+  launch_k(k_gemm<true, false, false, EPI_PLAIN>, grid_for(B, din), NT, 0, st, dV, dout, W, din, dY, din, B, din, dout, none,
                                                                          none, ep);
   note_launch();
 }
@@ -246,7 +247,7 @@ void simt_linear_dgrad_bngrad(const float* dV, int B, int dout, const float* W, 
   ep.ldu = din;
   ep.gate = Prologue{pro_mode, bn};
   ep.acc = acc;
-  k_gemm<true, false, false, EPI_BNGRAD><<<grid_for(B, din), NT, 0, st>>>(dV, dout, W, din, nullptr, 0, B, din, dout,
+  launch_k(k_gemm<true, false, false, EPI_BNGRAD>, grid_for(B, din), NT, 0, st, dV, dout, W, din, nullptr, 0, B, din, dout,
                                                                           none, none, ep);
   note_launch();
 }

@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(NBT) k_nb_rows(float* __restrict__ logits, con
                                                  const float* __restrict__ lib, int G, float eps, float c,
                                                  float* __restrict__ lse_out, float* __restrict__ ll_out,
                                                  float* __restrict__ asum_out, drv_step_out* out) {
+  pdl_prologue();
   __shared__ float sh[NBT / 32];
   __shared__ float lgtab[32];
   load_lgamma_table(lgtab, threadIdx.x);
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(NBT) k_nb_rows(float* __restrict__ logits, con
 
 __global__ void k_nb_decoder_outputs(const float* __restrict__ logits, const float* __restrict__ lib, int G,
                                      float* __restrict__ log_r, float* __restrict__ logit) {
+  pdl_prologue();
   __shared__ float sh[NBT / 32];
   const int b = blockIdx.x;
   const float* s = logits + (size_t)b * 2 * G;
@@ -145,13 +147,13 @@ __global__ void k_nb_decoder_outputs(const float* __restrict__ logits, const flo
 
 void nb_rows(float* logits, const float* x, const float* lib, int B, int G, float eps, float scale_factor, bool bwd,
              float* lse, float* ll, float* asum, drv_step_out* out, cudaStream_t st) {
-  if (bwd) k_nb_rows<true><<<B, NBT, 0, st>>>(logits, x, lib, G, eps, scale_factor, lse, ll, asum, out);
-  else k_nb_rows<false><<<B, NBT, 0, st>>>(logits, x, lib, G, eps, scale_factor, lse, ll, asum, out);
+  if (bwd) launch_k(k_nb_rows<true>, B, NBT, 0, st, logits, x, lib, G, eps, scale_factor, lse, ll, asum, out);
+  else launch_k(k_nb_rows<false>, B, NBT, 0, st, logits, x, lib, G, eps, scale_factor, lse, ll, asum, out);
   note_launch();
 }
 
 void nb_decoder_outputs(const float* logits, const float* lib, int B, int G, float* log_r, float* logit, cudaStream_t st) {
-  k_nb_decoder_outputs<<<B, NBT, 0, st>>>(logits, lib, G, log_r, logit);
+  launch_k(k_nb_decoder_outputs, B, NBT, 0, st, logits, lib, G, log_r, logit);
   note_launch();
 }
 

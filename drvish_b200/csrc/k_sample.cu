@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(ST) k_sample_fwd(const float* __restrict__ O, 
                                                    const float* __restrict__ eps_l, int B, int L, float c,
                                                    float lib_loc, float lib_scale, float* __restrict__ z,
                                                    float* __restrict__ l, drv_step_out* out) {
+  pdl_prologue();
   int b = blockIdx.x * ST + threadIdx.x;
   const int P = 2 * L + 2;
   float t = 0.f;  // log p - log q of this cell
@@ -51,6 +52,7 @@ __global__ void __launch_bounds__(ST) k_sample_bwd(const float* __restrict__ O, 
                                                    const float* __restrict__ dz_drs, const float* __restrict__ asum,
                                                    int B, int L, float c, float lib_loc, float lib_scale,
                                                    float* __restrict__ dO) {
+  pdl_prologue();
   int b = blockIdx.x * ST + threadIdx.x;
   if (b >= B) return;
   const int P = 2 * L + 2;
@@ -74,6 +76,7 @@ __global__ void __launch_bounds__(ST) k_sample_bwd(const float* __restrict__ O, 
 
 __global__ void k_encoder_outputs(const float* __restrict__ O, int B, int L, float* __restrict__ z_loc,
                                   float* __restrict__ z_scale, float* __restrict__ l_loc, float* __restrict__ l_scale) {
+  pdl_prologue();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * (L + 1)) return;
   int b = idx / (L + 1), d = idx % (L + 1);
@@ -113,6 +116,7 @@ __device__ __forceinline__ float u01(uint32_t v) { return ((float)(v >> 8) + 0.5
 template <bool LAPLACE>
 __global__ void k_fill(float* __restrict__ out, int64_t n, uint64_t seed, uint64_t offset,
                        const unsigned long long* __restrict__ step_counter, uint64_t stride) {
+  pdl_prologue();
   int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // quad index
   if (q * 4 >= n) return;
   if (step_counter) offset += (uint64_t)(*step_counter) * stride;
@@ -177,6 +181,7 @@ __device__ __forceinline__ void draw4(bool laplace, uint64_t seed, uint64_t ctr,
 
 __global__ void __launch_bounds__(256) k_draw_step_noise(NoiseSegs sg, uint64_t seed, unsigned long long* state,
                                                          uint64_t stride) {
+  pdl_prologue();
   int seg = 0;
 #pragma unroll
   for (int i = 1; i < 5; ++i)
@@ -224,46 +229,47 @@ void draw_step_noise(float* const* outs, const int64_t* ns, const int* laplace, 
   }
   sg.blk0[5] = blk;
   if (blk == 0) blk = 1;
-  k_draw_step_noise<<<blk, 256, 0, st>>>(sg, seed, state, stride);
+  launch_k(k_draw_step_noise, blk, 256, 0, st, sg, seed, state, stride);
   note_launch();
 }
 
 void sample_forward(const float* O, const float* eps_z, const float* eps_l, int B, int L, const drv_hparams& hp,
                     float* z, float* l, drv_step_out* out, cudaStream_t st) {
-  k_sample_fwd<<<cdiv(B, ST), ST, 0, st>>>(O, eps_z, eps_l, B, L, hp.scale_factor, hp.lib_loc, hp.lib_scale, z, l, out);
+  launch_k(k_sample_fwd, cdiv(B, ST), ST, 0, st, O, eps_z, eps_l, B, L, hp.scale_factor, hp.lib_loc, hp.lib_scale, z, l, out);
   note_launch();
 }
 
 void sample_backward(const float* O, const float* eps_z, const float* eps_l, const float* z, const float* l,
                      const float* dz_dec, const float* dz_drs, const float* asum, int B, int L, const drv_hparams& hp,
                      float* dO, cudaStream_t st) {
-  k_sample_bwd<<<cdiv(B, ST), ST, 0, st>>>(O, eps_z, eps_l, z, l, dz_dec, dz_drs, asum, B, L, hp.scale_factor,
+  launch_k(k_sample_bwd, cdiv(B, ST), ST, 0, st, O, eps_z, eps_l, z, l, dz_dec, dz_drs, asum, B, L, hp.scale_factor,
                                            hp.lib_loc, hp.lib_scale, dO);
   note_launch();
 }
 
 void encoder_outputs(const float* O, int B, int L, float* z_loc, float* z_scale, float* l_loc, float* l_scale,
                      cudaStream_t st) {
-  k_encoder_outputs<<<cdiv((int64_t)B * (L + 1), 256), 256, 0, st>>>(O, B, L, z_loc, z_scale, l_loc, l_scale);
+  launch_k(k_encoder_outputs, cdiv((int64_t)B * (L + 1), 256), 256, 0, st, O, B, L, z_loc, z_scale, l_loc, l_scale);
   note_launch();
 }
 
 void fill_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, const unsigned long long* ctr, uint64_t stride,
                  cudaStream_t st) {
   if (n <= 0) return;
-  k_fill<false><<<cdiv(cdiv(n, 4), 256), 256, 0, st>>>(out, n, seed, offset, ctr, stride);
+  launch_k(k_fill<false>, cdiv(cdiv(n, 4), 256), 256, 0, st, out, n, seed, offset, ctr, stride);
   note_launch();
 }
 void fill_laplace(float* out, int64_t n, uint64_t seed, uint64_t offset, const unsigned long long* ctr, uint64_t stride,
                   cudaStream_t st) {
   if (n <= 0) return;
-  k_fill<true><<<cdiv(cdiv(n, 4), 256), 256, 0, st>>>(out, n, seed, offset, ctr, stride);
+  launch_k(k_fill<true>, cdiv(cdiv(n, 4), 256), 256, 0, st, out, n, seed, offset, ctr, stride);
   note_launch();
 }
 
-__global__ void k_counter_add(unsigned long long* c, unsigned long long v) { *c += v; }
+__global__ void k_counter_add(unsigned long long* c, unsigned long long v) {
+  pdl_prologue(); *c += v; }
 void counter_add(unsigned long long* ctr, unsigned long long v, cudaStream_t st) {
-  k_counter_add<<<1, 1, 0, st>>>(ctr, v);
+  launch_k(k_counter_add, 1, 1, 0, st, ctr, v);
   note_launch();
 }
 

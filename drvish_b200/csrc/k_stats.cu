@@ -24,6 +24,7 @@ inline int row_splits(int B, int D) {
 template <bool SQRT>
 __global__ void __launch_bounds__(CW* RY) k_colstats(const float* __restrict__ U, int B, int D, int rows_per_cta,
                                                       double* __restrict__ acc, StatFinal fin) {
+  pdl_prologue();
   int col = blockIdx.x * CW + threadIdx.x;
   int r0 = blockIdx.y * rows_per_cta;
   int r1 = min(B, r0 + rows_per_cta);
@@ -62,6 +63,7 @@ __global__ void __launch_bounds__(CW* RY) k_colstats(const float* __restrict__ U
 template <bool SQRT>
 __global__ void __launch_bounds__(CW* RY) k_colstats4(const float* __restrict__ U, int B, int D, int rows_per_cta,
                                                        double* __restrict__ acc, StatFinal fin) {
+  pdl_prologue();
   const int col = (blockIdx.x * CW + threadIdx.x) * 4;
   const int r0 = blockIdx.y * rows_per_cta;
   const int r1 = min(B, r0 + rows_per_cta);
@@ -123,6 +125,7 @@ __global__ void __launch_bounds__(CW* RY) k_colstats4(const float* __restrict__ 
 __global__ void k_colstats_finalize(const double* __restrict__ acc, int B, int D, float eps, float momentum,
                                     float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ rmean,
                                     float* __restrict__ rvar) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= D) return;
   double m = acc[i] / B;
@@ -143,6 +146,7 @@ template <bool GATE>
 __global__ void __launch_bounds__(CW* RY) k_bn_bwd_reduce(const float* __restrict__ dY, const float* __restrict__ U, int B,
                                                            int D, int rows_per_cta, BnParams bn,
                                                            double* __restrict__ acc) {
+  pdl_prologue();
   int col = blockIdx.x * CW + threadIdx.x;
   int r0 = blockIdx.y * rows_per_cta;
   int r1 = min(B, r0 + rows_per_cta);
@@ -172,6 +176,7 @@ __global__ void __launch_bounds__(CW* RY) k_bn_bwd_reduce(const float* __restric
 template <bool GATE>
 __global__ void k_bn_bwd_apply(float* __restrict__ dY, const float* __restrict__ U, int B, int D, BnParams bn,
                                const double* __restrict__ acc, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_prologue();
   size_t n = (size_t)B * D;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
     int col = (int)(idx % D);
@@ -191,6 +196,7 @@ __global__ void k_bn_bwd_apply(float* __restrict__ dY, const float* __restrict__
 
 __global__ void k_bn_grad_finalize(const double* __restrict__ acc, int D, float* __restrict__ dgamma,
                                    float* __restrict__ dbeta) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= D) return;
   dbeta[i] = (float)acc[i];
@@ -198,11 +204,13 @@ __global__ void k_bn_grad_finalize(const double* __restrict__ acc, int D, float*
 }
 
 __global__ void k_bump(int64_t* c, int n) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) c[i] += 1;
 }
 
 __global__ void k_finalize_status(drv_step_out* out) {
+  pdl_prologue();
   if (isnan(out->loss)) out->status |= DRV_STATUS_NAN_LOSS;
 }
 
@@ -220,8 +228,8 @@ void colstats(const float* U, int B, int D, bool sqrt_in, double* acc, unsigned 
     int rows = cdiv(cdiv(B, S), RY) * RY;
     S = cdiv(B, rows);
     dim3 grid(col_blocks, S), block(CW, RY);
-    if (sqrt_in) k_colstats4<true><<<grid, block, 0, st>>>(U, B, D, rows, acc, fin);
-    else k_colstats4<false><<<grid, block, 0, st>>>(U, B, D, rows, acc, fin);
+    if (sqrt_in) launch_k(k_colstats4<true>, grid, block, 0, st, U, B, D, rows, acc, fin);
+    else launch_k(k_colstats4<false>, grid, block, 0, st, U, B, D, rows, acc, fin);
     note_launch();
     return;
   }
@@ -230,8 +238,8 @@ void colstats(const float* U, int B, int D, bool sqrt_in, double* acc, unsigned 
   rows = cdiv(rows, RY) * RY;
   S = cdiv(B, rows);
   dim3 grid(cdiv(D, CW), S), block(CW, RY);
-  if (sqrt_in) k_colstats<true><<<grid, block, 0, st>>>(U, B, D, rows, acc, fin);
-  else k_colstats<false><<<grid, block, 0, st>>>(U, B, D, rows, acc, fin);
+  if (sqrt_in) launch_k(k_colstats<true>, grid, block, 0, st, U, B, D, rows, acc, fin);
+  else launch_k(k_colstats<false>, grid, block, 0, st, U, B, D, rows, acc, fin);
   note_launch();
 }
 
@@ -241,8 +249,8 @@ void bn_bwd_reduce(const float* dY, const float* U, int B, int D, BnParams bn, d
   rows = cdiv(rows, RY) * RY;
   S = cdiv(B, rows);
   dim3 grid(cdiv(D, CW), S), block(CW, RY);
-  if (gate) k_bn_bwd_reduce<true><<<grid, block, 0, st>>>(dY, U, B, D, rows, bn, acc);
-  else k_bn_bwd_reduce<false><<<grid, block, 0, st>>>(dY, U, B, D, rows, bn, acc);
+  if (gate) launch_k(k_bn_bwd_reduce<true>, grid, block, 0, st, dY, U, B, D, rows, bn, acc);
+  else launch_k(k_bn_bwd_reduce<false>, grid, block, 0, st, dY, U, B, D, rows, bn, acc);
   note_launch();
 }
 
@@ -251,23 +259,23 @@ void bn_bwd_apply(float* dY_dU, const float* U, int B, int D, BnParams bn, const
   size_t n = (size_t)B * D;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  if (gate) k_bn_bwd_apply<true><<<blocks, 256, 0, st>>>(dY_dU, U, B, D, bn, acc, dgamma, dbeta);
-  else k_bn_bwd_apply<false><<<blocks, 256, 0, st>>>(dY_dU, U, B, D, bn, acc, dgamma, dbeta);
+  if (gate) launch_k(k_bn_bwd_apply<true>, blocks, 256, 0, st, dY_dU, U, B, D, bn, acc, dgamma, dbeta);
+  else launch_k(k_bn_bwd_apply<false>, blocks, 256, 0, st, dY_dU, U, B, D, bn, acc, dgamma, dbeta);
   note_launch();
 }
 
 void bn_grad_finalize(const double* acc, int D, float* dgamma, float* dbeta, cudaStream_t st) {
-  k_bn_grad_finalize<<<cdiv(D, 256), 256, 0, st>>>(acc, D, dgamma, dbeta);
+  launch_k(k_bn_grad_finalize, cdiv(D, 256), 256, 0, st, acc, D, dgamma, dbeta);
   note_launch();
 }
 
 void bump_counters(int64_t* counters, int n, cudaStream_t st) {
-  k_bump<<<cdiv(n, 64), 64, 0, st>>>(counters, n);
+  launch_k(k_bump, cdiv(n, 64), 64, 0, st, counters, n);
   note_launch();
 }
 
 void finalize_status(drv_step_out* out, cudaStream_t st) {
-  k_finalize_status<<<1, 1, 0, st>>>(out);
+  launch_k(k_finalize_status, 1, 1, 0, st, out);
   note_launch();
 }
 

@@ -5,6 +5,8 @@
 // Everything is enqueued on the caller's stream; no allocation, no host synchronisation.
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "kernels.cuh"
 #include "tc.cuh"
 
@@ -29,6 +31,15 @@ inline void kmark(int k, int which, cudaStream_t st) {
   if (enabled && n_steps < MAX_STEPS) cudaEventRecord(kev[n_steps][k][which], st);
 }
 }  // namespace prof
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("DRV_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
 
 SideStream* side_stream() {
   static thread_local SideStream ss;

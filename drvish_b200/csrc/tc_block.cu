@@ -27,6 +27,7 @@ __device__ __forceinline__ float rna_tf32(float v) {
 template <bool SQRT>
 __global__ void k_enc_prep(const float* __restrict__ x, size_t n, int G, BnParams bn, float* __restrict__ hi,
                            float* __restrict__ lo) {
+  pdl_prologue();
   for (size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i4 < n; i4 += (size_t)gridDim.x * blockDim.x * 4) {
     float4 xv = *reinterpret_cast<const float4*>(x + i4);
     int col = (int)(i4 % G);  // G % 4 == 0: the four elements share a row
@@ -44,6 +45,7 @@ __global__ void k_enc_prep(const float* __restrict__ x, size_t n, int G, BnParam
 }
 
 __global__ void k_split_tf32(const float* __restrict__ src, size_t n, float* __restrict__ hi, float* __restrict__ lo) {
+  pdl_prologue();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float v = src[i];
     float h = rna_tf32(v);
@@ -53,12 +55,14 @@ __global__ void k_split_tf32(const float* __restrict__ src, size_t n, float* __r
 }
 
 __global__ void k_round_rows(const float* __restrict__ src, size_t n, float* __restrict__ dst) {
+  pdl_prologue();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     dst[i] = rna_tf32(src[i]);
 }
 
 __global__ void k_round_colsum(const float* __restrict__ V, int B, int D, int rows_per_cta, float* __restrict__ Vr,
                                float* __restrict__ out) {
+  pdl_prologue();
   int col = blockIdx.x * 32 + threadIdx.x;
   int r0 = blockIdx.y * rows_per_cta, r1 = min(B, r0 + rows_per_cta);
   float s = 0.f;
@@ -79,6 +83,7 @@ __global__ void k_round_colsum(const float* __restrict__ V, int B, int D, int ro
 }
 
 __global__ void k_colsum_small(const float* __restrict__ V, int B, int D, int rows_per_cta, float* __restrict__ out) {
+  pdl_prologue();
   // 32 columns x 8 row lanes per CTA, the batch split over gridDim.y; out must be zeroed
   int col = blockIdx.x * 32 + threadIdx.x;
   int r0 = blockIdx.y * rows_per_cta, r1 = min(B, r0 + rows_per_cta);
@@ -100,6 +105,7 @@ __global__ void k_colsum_small(const float* __restrict__ V, int B, int D, int ro
 constexpr int CW = 32, RY = 8;
 __global__ void __launch_bounds__(CW* RY) k_bn0_grad(const float* __restrict__ dA, const float* __restrict__ x, int B,
                                                       int G, int rows_per_cta, BnParams bn, double* __restrict__ acc) {
+  pdl_prologue();
   const int col = (blockIdx.x * CW + threadIdx.x) * 4;
   const int r0 = blockIdx.y * rows_per_cta;
   const int r1 = min(B, r0 + rows_per_cta);
@@ -164,6 +170,7 @@ __global__ void __launch_bounds__(CW* RY) k_bn0_grad(const float* __restrict__ d
 
 // dY = dA * [bn(U) > 0] in place (same fused-multiply-add sequence as the forward)
 __global__ void k_gate_block(float* __restrict__ dact, const float* __restrict__ U, size_t n, int D, BnParams bn) {
+  pdl_prologue();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     int col = (int)(i % D);
     float y = bn_y(bn_xhat(U[i], bn.mean[col], bn.rstd[col]), bn.gamma[col], bn.beta[col]);
@@ -236,8 +243,8 @@ bool tc_block_forward(const TcBlockArgs& a, cudaStream_t st) {
   }
   int blocks = (int)((n / 4 + 255) / 256);
   if (blocks > n_sm() * 8) blocks = n_sm() * 8;
-  if (a.sqrt_in) k_enc_prep<true><<<blocks, 256, 0, st>>>(a.U, n, a.din, a.bn, s.a_hi, s.a_lo);
-  else k_enc_prep<false><<<blocks, 256, 0, st>>>(a.U, n, a.din, a.bn, s.a_hi, s.a_lo);
+  if (a.sqrt_in) launch_k(k_enc_prep<true>, blocks, 256, 0, st, a.U, n, a.din, a.bn, s.a_hi, s.a_lo);
+  else launch_k(k_enc_prep<false>, blocks, 256, 0, st, a.U, n, a.din, a.bn, s.a_hi, s.a_lo);
   note_launch();
   const float* As[3] = {s.a_lo, s.a_hi, s.a_hi};
   const float* Bs[3] = {a.W_hi, a.W_lo, a.W_hi};
@@ -260,7 +267,7 @@ void tc_block_backward(const TcBlockArgs& a, cudaStream_t st) {
     int rows = 64;
     dim3 cgrid((a.dout + 31) / 32, (a.B + rows - 1) / rows);
     cudaMemsetAsync(a.db, 0, sizeof(float) * a.dout, st);
-    k_round_colsum<<<cgrid, cb, 0, st>>>(a.dV, a.B, a.dout, rows, s.dh_r, a.db);
+    launch_k(k_round_colsum, cgrid, cb, 0, st, a.dV, a.B, a.dout, rows, s.dh_r, a.db);
     note_launch();
   }
   // dW[j][i] = sum_b dV[b][j] A[b][i]: both operands MN-major (K = cells)
@@ -291,14 +298,14 @@ void tc_block_backward(const TcBlockArgs& a, cudaStream_t st) {
   int rows = ((a.B + S - 1) / S + RY - 1) / RY * RY;
   S = (a.B + rows - 1) / rows;
   dim3 grid(col_blocks, S), block(CW, RY);
-  k_bn0_grad<<<grid, block, 0, st>>>(dA, a.U, a.B, a.din, rows, a.bn, a.gacc);
+  launch_k(k_bn0_grad, grid, block, 0, st, dA, a.U, a.B, a.din, rows, a.bn, a.gacc);
   note_launch();
 }
 
 void split_params_tf32(const float* src, size_t n, float* hi, float* lo, cudaStream_t st) {
   int blocks = (int)((n + 255) / 256);
   if (blocks > n_sm() * 8) blocks = n_sm() * 8;
-  k_split_tf32<<<blocks, 256, 0, st>>>(src, n, hi, lo);
+  launch_k(k_split_tf32, blocks, 256, 0, st, src, n, hi, lo);
   note_launch();
 }
 

@@ -33,6 +33,7 @@ constexpr int NTHREADS = 192;
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_bn0grad(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH,
           const __grid_constant__ CUtensorMap tmX, BnParams bn, int B, int G, int h, double* __restrict__ gacc) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* xbuf = smem + NST * STAGE;
@@ -211,7 +212,7 @@ int bn0grad_fused(const float* dH_r, const float* W_hi, const float* x, int B, i
   const int n_tiles = ((G + BG - 1) / BG) * ((B + BC - 1) / BC);
   const int grid = n_tiles < sms() ? n_tiles : sms();
   cudaFuncSetAttribute(k_bn0grad, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  k_bn0grad<<<grid, NTHREADS, SMEM_BYTES, st>>>(tW, tH, tX, bn, B, G, h, gacc);
+  launch_k(k_bn0grad, grid, NTHREADS, SMEM_BYTES, st, tW, tH, tX, bn, B, G, h, gacc);
   note_launch();
   return 0;
 }

@@ -90,6 +90,7 @@ template <int PHASE, bool WITH_A>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtensorMap tmW,
       const __grid_constant__ CUtensorMap tmX, DecParams p) {
+  pdl_prologue();
   // phase 3 stages a 128 x 128 ds' tile (4 boxes, 64 KB) instead of the 128 x 64 count tile and
   // makes room for it with a 2-deep operand ring (its MMA is far from critical)
   constexpr int NST = PHASE == 3 ? 2 : STAGES;
@@ -417,6 +418,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
 
 // act = relu(bn(U)) materialised once (B x h fp32, L2 resident) as the TMA-fed A operand
 __global__ void k_act(const float* __restrict__ U, int B, int h, BnParams bn, float* __restrict__ act) {
+  pdl_prologue();
   size_t n = (size_t)B * h;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     int col = (int)(i % h);
@@ -425,12 +427,14 @@ __global__ void k_act(const float* __restrict__ U, int B, int h, BnParams bn, fl
 }
 
 __global__ void k_round_tf32(const float* __restrict__ src, size_t n, float* __restrict__ dst) {
+  pdl_prologue();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     dst[i] = rna_tf32(src[i]);
 }
 
 __global__ void k_lse_combine(const float* __restrict__ pm, const float* __restrict__ ps, int n_gt, int n_tiles, int grid,
                               int B, float* __restrict__ lse) {
+  pdl_prologue();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int ct = b / BM;
@@ -448,6 +452,7 @@ __global__ void k_lse_combine(const float* __restrict__ pm, const float* __restr
 }
 
 __global__ void k_loss_from_ll(const float* __restrict__ ll, int B, float c, drv_step_out* out) {
+  pdl_prologue();
   double t = 0.0;
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) t += (double)ll[b];
   t = warp_sum(t);
@@ -462,6 +467,7 @@ __global__ void k_loss_from_ll(const float* __restrict__ ll, int B, float c, drv
 }
 
 __global__ void k_gate(float* __restrict__ dact, const float* __restrict__ U, int B, int h, BnParams bn) {
+  pdl_prologue();
   size_t n = (size_t)B * h;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     int col = (int)(i % h);
@@ -525,7 +531,7 @@ void launch_dec(K kern, int n_tiles, const CUtensorMap& act, const CUtensorMap& 
                 const DecParams& p, cudaStream_t st) {
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-  kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(act, w, x, p);
+  launch_k(kern, grid, NTHREADS, SMEM_BYTES, st, act, w, x, p);
   note_launch();
 }
 
@@ -552,7 +558,7 @@ void tc_decoder_forward(const TcDecoderArgs& a, cudaStream_t st) {
   }
   int blocks = (int)(((size_t)a.B * a.h + 255) / 256);
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  k_act<<<blocks, 256, 0, st>>>(a.U, a.B, a.h, a.bn, s.act);
+  launch_k(k_act, blocks, 256, 0, st, a.U, a.B, a.h, a.bn, s.act);
   note_launch();
   DecParams p{};
   p.B = a.B; p.G = a.G; p.h = a.h; p.bias = a.bias; p.lib = a.lib; p.eps = a.eps; p.c = a.c;
@@ -567,7 +573,7 @@ void tc_decoder_forward(const TcDecoderArgs& a, cudaStream_t st) {
   {
     const int n_tiles1 = n_ct * n_gt1;
     const int grid1 = n_tiles1 < sm_count() ? n_tiles1 : sm_count();
-    k_lse_combine<<<(a.B + 63) / 64, 64, 0, st>>>(s.part_m, s.part_s, n_gt1, n_tiles1, grid1, a.B, a.lse);
+    launch_k(k_lse_combine, (a.B + 63) / 64, 64, 0, st, s.part_m, s.part_s, n_gt1, n_tiles1, grid1, a.B, a.lse);
   }
   note_launch();
   // phase 2: NB log-likelihood row sums
@@ -579,7 +585,7 @@ void tc_decoder_forward(const TcDecoderArgs& a, cudaStream_t st) {
   if (a.bwd) launch_dec(k_dec<2, true>, n_ct * n_gt, tAct, tW3, tX, p, st);
   else launch_dec(k_dec<2, false>, n_ct * n_gt, tAct, tW3, tX, p, st);
   drv_internal_kmark(1, 1, st);
-  k_loss_from_ll<<<8, 256, 0, st>>>(a.ll, a.B, a.c, a.out);
+  launch_k(k_loss_from_ll, 8, 256, 0, st, a.ll, a.B, a.c, a.out);
   note_launch();
 }
 

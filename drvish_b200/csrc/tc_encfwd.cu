@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWhi,
          const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CUtensorMap tmAhi, BnParams bn, int B, int G,
          int h, int n_tile, int splits, float* __restrict__ out, long long part_stride, const float* __restrict__ bias) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* xring = smem;
@@ -348,12 +349,12 @@ int encfwd_fused(const float* x, int B, int G, BnParams bn, const float* w_hi, c
   const int grid = (int)(chunks < sms() ? chunks : sms());
   cudaFuncSetAttribute(k_encfwd, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (splits > 1) {
-    k_encfwd<<<grid, NTHREADS, SMEM_BYTES, st>>>(tX, tWh, tWl, tA, bn, B, G, h, n_tile, splits, partials,
+    launch_k(k_encfwd, grid, NTHREADS, SMEM_BYTES, st, tX, tWh, tWl, tA, bn, B, G, h, n_tile, splits, partials,
                                                  (long long)B * h, nullptr);
     note_launch();
     return reduce_parts(partials, splits, B, h, bias, V, h, st, stats) ? 1 : 0;
   } else {
-    k_encfwd<<<grid, NTHREADS, SMEM_BYTES, st>>>(tX, tWh, tWl, tA, bn, B, G, h, n_tile, 1, V, 0LL, bias);
+    launch_k(k_encfwd, grid, NTHREADS, SMEM_BYTES, st, tX, tWh, tWl, tA, bn, B, G, h, n_tile, 1, V, 0LL, bias);
     note_launch();
   }
   return 0;

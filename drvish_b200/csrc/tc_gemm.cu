@@ -75,6 +75,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, int n_pairs,
           float* __restrict__ C, int ldc, int M, int N, int K, int n_tile, int splits, int force_atomic,
           const float* __restrict__ bias, long long part_stride, int mn_lbo, int mn_sbo, int mn_kstep) {
+  pdl_prologue();
   constexpr int TBM = MT * BM;                       // rows of the CTA tile
   constexpr int NSTG = MT == 1 ? STAGES : 3;
   constexpr int SA_BYTES = MT * A_BYTES;
@@ -248,6 +249,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 // C[m][n] = bias[n] + sum_p partials[p][m][n], parts added in index order (deterministic)
 __global__ void k_reduce_parts(const float* __restrict__ parts, int n_parts, size_t mn, int N, const float* __restrict__ bias,
                                float* __restrict__ C, int ldc) {
+  pdl_prologue();
   for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < mn; i += (size_t)gridDim.x * blockDim.x * 4) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     const bool vec = (N % 4 == 0) && (i + 4 <= mn);
@@ -277,6 +279,7 @@ __global__ void k_reduce_parts(const float* __restrict__ parts, int n_parts, siz
 __global__ void __launch_bounds__(256) k_reduce_parts_stats(const float* __restrict__ parts, int n_parts, int M, int N,
                                                             const float* __restrict__ bias, float* __restrict__ C, int ldc,
                                                             int rows_per_cta, double* __restrict__ acc, StatFinal fin) {
+  pdl_prologue();
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
   const size_t mn = (size_t)M * N;
@@ -413,7 +416,7 @@ int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs,
   }
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(ta[0], tb[0], ta[1], tb[1], ta[2], tb[2], n_pairs, outp, out_ld, M, N, K, n_tile,
+    launch_k(kern, grid, NTHREADS, SMEM_BYTES, st, ta[0], tb[0], ta[1], tb[1], ta[2], tb[2], n_pairs, outp, out_ld, M, N, K, n_tile,
                                              splits, force_atomic, kbias, part_stride, g_mn_lbo, g_mn_sbo, g_mn_kstep);
   };
   if (mt_sel == 1) {
@@ -440,7 +443,7 @@ bool reduce_parts(const float* parts, int n_parts, int M, int N, const float* bi
     if (R < (M + 127) / 128) R = (M + 127) / 128;  // <= 32 rows per thread in the fp32 partial sums
     const int rows_per_cta = (M + R - 1) / R;
     R = (M + rows_per_cta - 1) / rows_per_cta;
-    k_reduce_parts_stats<<<dim3(1, R), dim3(64, 4), 0, st>>>(parts, n_parts, M, N, bias, C, ldc, rows_per_cta, stats->acc,
+    launch_k(k_reduce_parts_stats, dim3(1, R), dim3(64, 4), 0, st, parts, n_parts, M, N, bias, C, ldc, rows_per_cta, stats->acc,
                                                              stats->fin);
     note_launch();
     return true;
@@ -448,7 +451,7 @@ bool reduce_parts(const float* parts, int n_parts, int M, int N, const float* bi
   const size_t n4 = ((size_t)M * N + 3) / 4;
   int blocks = (int)((n4 + 255) / 256);
   if (blocks > n_sm_tc() * 8) blocks = n_sm_tc() * 8;
-  k_reduce_parts<<<blocks, 256, 0, st>>>(parts, n_parts, (size_t)M * N, N, bias, C, ldc);
+  launch_k(k_reduce_parts, blocks, 256, 0, st, parts, n_parts, (size_t)M * N, N, bias, C, ldc);
   note_launch();
   return false;
 }

@@ -2,51 +2,171 @@
 
 The reference moves every minibatch synchronously (`xs = (x.cuda() for x in xs)`,
 src/drvish/train/__init__.py:42-43), so the copy of the 4096 x G fp32 count tile (82 MB at
-config 3) serialises with the step.  ``PinnedBatchPrefetcher`` wraps any iterable of
-``(x, labels, y)``-style batches, stages the large count tensor through pinned memory and issues
-the copy of batch i+1 on a side stream while step i runs (two device buffers)."""
+config 3) serialises with the step - and at PCIe Gen5 rates that copy alone (1.5 ms) is longer
+than the whole ELBO step on a B200.  Two pieces:
+
+``PinnedBatchPrefetcher`` wraps any iterable of ``(x, labels, y)``-style batches; a worker thread
+stages the count tensor of the batches ahead through pinned memory on a copy stream (three device
+slots) while the current step runs.
+
+``PackedCounts`` is a lossless 16-bit host representation of a count tile (scRNA counts are
+non-negative integers): packed ONCE when the dataset is built (``pack_batches``), it halves the
+bytes every epoch moves over PCIe; the device widens it back to the fp32 tile the step reads,
+bit-exactly (``drv_unpack_counts_u16``).  A tile with a non-integer / negative / > 65535 entry is
+left as fp32."""
 from __future__ import annotations
 
-from typing import Iterable, Iterator, Sequence
+import ctypes as C
+import os
+import queue
+import threading
+from typing import Iterable, Iterator, List, Optional, Sequence
 
 import torch
 
+from . import _lib
+
+
+class PackedCounts:
+    """uint16 copy (stored in a pinned int16 tensor) of an integer-valued fp32 count tile."""
+
+    __slots__ = ("data", "shape")
+
+    def __init__(self, data: torch.Tensor, shape):
+        self.data, self.shape = data, tuple(shape)
+
+    @staticmethod
+    def pack(x: torch.Tensor, n_threads: Optional[int] = None, out: Optional[torch.Tensor] = None) -> Optional["PackedCounts"]:
+        """None when ``x`` is not representable (the caller keeps the fp32 tile)."""
+        if x.is_cuda or x.dtype != torch.float32:
+            raise TypeError("PackedCounts.pack expects a host fp32 tensor")
+        x = x.contiguous()
+        n = x.numel()
+        if out is None:
+            out = torch.empty(n, dtype=torch.int16)
+            if torch.cuda.is_available():
+                out = out.pin_memory()
+        lib = _lib.load()
+        nt = n_threads or min(16, os.cpu_count() or 1)
+        ok = lib.drv_host_pack_counts_u16(C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), n, nt)
+        if ok != n:
+            return None
+        return PackedCounts(out, x.shape)
+
+    def unpack_host(self) -> torch.Tensor:
+        """fp32 tile on the host (tests)."""
+        import numpy as np
+
+        return torch.from_numpy(self.data.numpy().view(np.uint16).astype(np.float32)).reshape(self.shape)
+
+
+def pack_batches(batches: Iterable[Sequence]) -> List[list]:
+    """Dataset-build-time packing: the count tile of every batch becomes ``PackedCounts`` where it is
+    representable (otherwise the fp32 tensor is kept, pinned)."""
+    out = []
+    for b in batches:
+        x = b[0]
+        p = PackedCounts.pack(x) if (torch.is_tensor(x) and not x.is_cuda and x.dtype == torch.float32) else None
+        if p is None and torch.is_tensor(x) and not x.is_cuda and not x.is_pinned() and torch.cuda.is_available():
+            x = x.pin_memory()
+        out.append([p if p is not None else x] + list(b[1:]))
+    return out
+
 
 class PinnedBatchPrefetcher:
-    def __init__(self, batches: Iterable[Sequence], device: torch.device):
+    """Iterate ``batches`` with the host->device copy of the next ones already in flight.
+
+    pack_on_the_fly: also pack fp32 host tiles to 16 bits in the worker thread before the copy (only
+    pays when the host packs faster than the bus moves the saved bytes; off by default)."""
+
+    SLOTS = 3
+
+    def __init__(self, batches: Iterable[Sequence], device: torch.device, pack_on_the_fly: bool = False):
         self.batches = batches
         self.device = torch.device(device)
+        self.pack_on_the_fly = pack_on_the_fly
         self.stream = torch.cuda.Stream(device=self.device)
-        self._bufs = [None, None]
-        self._events = [torch.cuda.Event(), torch.cuda.Event()]
+        self._x = [None] * self.SLOTS          # fp32 device tiles handed to the step
+        self._staged = [None] * self.SLOTS     # uint16 device staging
+        self._host16 = [None] * self.SLOTS     # pinned uint16 staging for on-the-fly packing
+        self._ready = [torch.cuda.Event() for _ in range(self.SLOTS)]
+        self._consumed = [None] * self.SLOTS   # recorded on the consumer's stream when a slot is handed back
+        self.h2d_bytes = 0
 
-    def _issue(self, slot: int, batch: Sequence):
+    # -- worker side --------------------------------------------------------------------------
+    def _stage(self, slot: int, batch: Sequence) -> list:
         x = batch[0]
-        if self._bufs[slot] is None or self._bufs[slot].shape != x.shape or self._bufs[slot].dtype != x.dtype:
-            self._bufs[slot] = torch.empty(x.shape, dtype=x.dtype, device=self.device)
-        if not x.is_cuda and not x.is_pinned():
-            x = x.pin_memory()
+        lib = _lib.load()
         with torch.cuda.stream(self.stream):
-            self._bufs[slot].copy_(x, non_blocking=True)
+            if self._consumed[slot] is not None:
+                self.stream.wait_event(self._consumed[slot])
+            packed = x if isinstance(x, PackedCounts) else None
+            if packed is None and self.pack_on_the_fly and torch.is_tensor(x) and not x.is_cuda and x.dtype == torch.float32:
+                n = x.numel()
+                if self._host16[slot] is None or self._host16[slot].numel() != n:
+                    self._host16[slot] = torch.empty(n, dtype=torch.int16).pin_memory()
+                packed = PackedCounts.pack(x, out=self._host16[slot])
+            shape = packed.shape if packed is not None else tuple(x.shape)
+            if self._x[slot] is None or tuple(self._x[slot].shape) != shape:
+                self._x[slot] = torch.empty(shape, dtype=torch.float32, device=self.device)
+            if packed is not None:
+                n = packed.data.numel()
+                if self._staged[slot] is None or self._staged[slot].numel() != n:
+                    self._staged[slot] = torch.empty(n, dtype=torch.int16, device=self.device)
+                self._staged[slot].copy_(packed.data, non_blocking=True)
+                _lib.check(lib.drv_unpack_counts_u16(C.c_void_p(self._staged[slot].data_ptr()),
+                                                     C.c_void_p(self._x[slot].data_ptr()), n,
+                                                     C.c_void_p(self.stream.cuda_stream)), "drv_unpack_counts_u16")
+                self.h2d_bytes += 2 * n
+            else:
+                if not x.is_cuda and not x.is_pinned():
+                    x = x.pin_memory()
+                self._x[slot].copy_(x, non_blocking=True)
+                self.h2d_bytes += 0 if x.is_cuda else 4 * x.numel()
             rest = [t.to(self.device, non_blocking=True) if torch.is_tensor(t) and not t.is_cuda else t for t in batch[1:]]
-            self._events[slot].record(self.stream)
-        return [self._bufs[slot]] + rest
+            self._ready[slot].record(self.stream)
+        return [self._x[slot]] + rest
 
-    def __iter__(self) -> Iterator[list]:
-        it = iter(self.batches)
+    def _worker(self, free: threading.Semaphore, out_q: "queue.Queue"):
         try:
-            nxt = self._issue(0, next(it))
-        except StopIteration:
-            return
-        slot = 0
-        while nxt is not None:
-            cur, cur_slot = nxt, slot
-            try:
-                # the buffer of `slot ^ 1` was consumed by the step before last, which has completed
-                # (SVI.step returns the Python float loss, i.e. it synchronises)
-                slot ^= 1
-                nxt = self._issue(slot, next(it))
-            except StopIteration:
-                nxt = None
-            torch.cuda.current_stream(self.device).wait_event(self._events[cur_slot])
-            yield cur
+            torch.cuda.set_device(self.device)
+            for k, batch in enumerate(self.batches):
+                free.acquire()
+                if self._stop:
+                    break
+                slot = k % self.SLOTS
+                out_q.put((slot, self._stage(slot, batch)))
+            out_q.put(None)
+        except BaseException as e:  # surfaced on the consumer side
+            out_q.put(e)
+
+    # -- consumer side ------------------------------------------------------------------------
+    def __iter__(self) -> Iterator[list]:
+        free = threading.Semaphore(self.SLOTS - 1)  # the slot being consumed is never restaged
+        out_q: "queue.Queue" = queue.Queue()
+        self._stop = False
+        th = threading.Thread(target=self._worker, args=(free, out_q), daemon=True)
+        th.start()
+        prev = None
+        try:
+            while True:
+                item = out_q.get()
+                if item is None:
+                    break
+                if isinstance(item, BaseException):
+                    raise item
+                slot, batch = item
+                cur = torch.cuda.current_stream(self.device)
+                if prev is not None:
+                    # the consumer is done with the previous batch once everything it enqueued so far has run
+                    ev = torch.cuda.Event()
+                    ev.record(cur)
+                    self._consumed[prev] = ev
+                    free.release()
+                cur.wait_event(self._ready[slot])
+                prev = slot
+                yield batch
+        finally:
+            self._stop = True
+            free.release()
+            th.join(timeout=5.0)

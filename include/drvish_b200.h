@@ -155,6 +155,15 @@ int drv_draw_step_noise(const drv_dims* dims, const drv_hparams* hp, uint64_t se
                         uint64_t stride, float* eps_z, float* eps_l, float* w_prior, float* b_prior, float* eps_bias,
                         void* stream);
 
+/* Lossless 16-bit staging of count tiles for the host->device copy (the reference ships dense fp32
+ * minibatches: train/__init__.py:42-43).  drv_host_pack_counts_u16 (HOST pointers, n_threads worker
+ * threads) writes h_dst[i] = (uint16)h_src[i] and returns n when every entry is an integer in
+ * [0, 65535], else the index of the first entry that is not (the tile must then travel as fp32);
+ * -1 for invalid arguments.  drv_unpack_counts_u16 widens a device uint16 tile back to fp32
+ * (bit-exact inverse); src and dst must be 16-byte aligned. */
+int64_t drv_host_pack_counts_u16(const float* h_src, uint16_t* h_dst, int64_t n, int n_threads);
+int drv_unpack_counts_u16(const uint16_t* src, float* dst, int64_t n, void* stream);
+
 /* Section timing with CUDA events recorded on the step's stream (bench.py's live roofline
  * measurement).  drv_profile_enable(1) arms it (up to 64 steps are kept); drv_profile_read
  * synchronises on the recorded events and returns the mean milliseconds per section. */

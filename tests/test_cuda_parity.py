@@ -310,3 +310,30 @@ def test_forward_is_run_to_run_deterministic():
         assert abs(l1 - l2) <= 1e-7 * abs(l1)
         for k in ("decoder.fc.3.bias", "decoder.fc.2.weight", "encoder.fc.0.weight", "encoder.fc.3.weight"):
             assert P.rel_err(g2[k], g1[k]) <= 2e-4, (k, P.rel_err(g2[k], g1[k]))  # gate flips showed up as 1.4e-3
+
+
+def test_prefetcher_delivers_exact_tiles_fp32_packed_and_on_the_fly():
+    """PinnedBatchPrefetcher: fp32 host tiles, PackedCounts (uint16 over the bus, drv_unpack_counts_u16 on
+    the device) and on-the-fly packing all hand the step the same fp32 tile, bit for bit; a tile that is
+    not representable in 16 bits travels as fp32."""
+    from drvish_b200.data import PackedCounts, PinnedBatchPrefetcher, pack_batches
+
+    g = torch.Generator().manual_seed(5)
+    tiles = [torch.poisson(torch.full((97, 131), 2.0 + i), generator=g) for i in range(7)]
+    tiles[3][4, 5] = 1.5  # not an integer: stays fp32
+    tiles[6][0, 0] = 65535.0
+    labels = torch.arange(97)
+    fp32 = [[t, labels] for t in tiles]
+    packed = pack_batches(fp32)
+    assert [isinstance(b[0], PackedCounts) for b in packed] == [True, True, True, False, True, True, True]
+    for dataset, fly in ((fp32, False), (packed, False), (fp32, True)):
+        pf = PinnedBatchPrefetcher(dataset, "cuda:0", pack_on_the_fly=fly)
+        for epoch in range(2):
+            got = []
+            for x, lab in pf:
+                assert x.is_cuda and lab.is_cuda and x.dtype == torch.float32
+                got.append(x.clone())
+            assert len(got) == len(tiles)
+            for a, b in zip(got, tiles):
+                assert torch.equal(a.cpu(), b)
+    assert pf.h2d_bytes > 0

@@ -112,3 +112,34 @@ def test_data_parallel_allreduce_is_sum_over_shards(tmp_path):
     n = r0["n"]
     torch.testing.assert_close(r0["flat"][:n], tot, rtol=1e-12, atol=1e-12)
     assert abs(float(r0["flat"][n]) - tot_loss) <= 1e-9 * abs(tot_loss)
+
+
+def test_packed_counts_round_trip_and_rejection():
+    """Lossless 16-bit host staging (drv_host_pack_counts_u16): exact for integer counts in [0, 65535],
+    refused (first offending index found) otherwise."""
+    import ctypes as C
+
+    from drvish_b200 import _lib
+    from drvish_b200.data import PackedCounts, pack_batches
+
+    g = torch.Generator().manual_seed(3)
+    x = torch.poisson(torch.full((333, 257), 3.0), generator=g)
+    x[0, 0], x[5, 7] = 65535.0, 0.0
+    for nt in (1, 3, 8):
+        p = PackedCounts.pack(x, n_threads=nt)
+        assert p is not None and p.shape == (333, 257)
+        assert torch.equal(p.unpack_host(), x)
+    lib = _lib.load()
+    out = torch.empty(x.numel(), dtype=torch.int16)
+    for bad in (0.5, -1.0, 65536.0, float("nan"), float("inf")):
+        y = x.clone()
+        y[200, 100] = bad
+        assert PackedCounts.pack(y) is None
+        idx = lib.drv_host_pack_counts_u16(C.c_void_p(y.data_ptr()), C.c_void_p(out.data_ptr()), y.numel(), 4)
+        assert idx == 200 * 257 + 100
+    big = torch.zeros(1 << 20)
+    big[70000], big[900000] = 0.25, 0.25
+    out = torch.empty(big.numel(), dtype=torch.int16)
+    assert lib.drv_host_pack_counts_u16(C.c_void_p(big.data_ptr()), C.c_void_p(out.data_ptr()), big.numel(), 8) == 70000
+    sets = pack_batches([[x, "labels"], [x + 0.5, "labels"]])
+    assert isinstance(sets[0][0], PackedCounts) and torch.is_tensor(sets[1][0]) and sets[0][1] == "labels"
