@@ -55,7 +55,7 @@ inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
 // still looks like one stream to the caller (and is CUDA-graph capturable).
 struct SideStream {
   cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_aux = nullptr;
   bool used = false;
   // work enqueued on `side` after this call sees everything enqueued on `main` so far
   void fork(cudaStream_t main) {
@@ -71,6 +71,10 @@ struct SideStream {
     cudaStreamWaitEvent(side, ev_fork, 0);
     used = true;
   }
+  // a second, named join point: `main` waits for the side-stream work submitted before record_aux()
+  // only (join() would also wait for whatever was queued on the side stream afterwards)
+  void record_aux() { cudaEventRecord(ev_aux, side); }
+  void wait_aux(cudaStream_t main) { cudaStreamWaitEvent(main, ev_aux, 0); }
   // work enqueued on `main` after this call sees everything enqueued on `side` so far
   void join(cudaStream_t main) {
     if (!used) return;

@@ -219,11 +219,7 @@ void simt_linear_wgrad(const float* dV, int B, int dout, const float* U, int din
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
   }
-  if (splits > 1) {
-    cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)dout * din, st);
-    cudaMemsetAsync(db, 0, sizeof(float) * (size_t)dout, st);
-    grid.z = splits;
-  }
+  if (splits > 1) grid.z = splits;  // split-K accumulation: dW / db were cleared at the start of the step
   launch_k(k_gemm<false, false, true, EPI_DW>, grid, NT, 0, st, dV, dout, U, din, dW, din, dout, din + 1, B, pa, pb, ep);
   note_launch();
 }

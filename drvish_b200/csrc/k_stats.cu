@@ -214,6 +214,17 @@ __global__ void k_finalize_status(drv_step_out* out) {
   if (isnan(out->loss)) out->status |= DRV_STATUS_NAN_LOSS;
 }
 
+__global__ void k_finalize_step(drv_step_out* out, const uint32_t* status, int64_t* c, int n) {
+  pdl_prologue();
+  const int i = threadIdx.x;
+  if (c && i < n) c[i] += 1;
+  if (i == 0) {
+    uint32_t s = *status;
+    if (isnan(out->loss)) s |= DRV_STATUS_NAN_LOSS;
+    out->status = s;
+  }
+}
+
 }  // namespace
 
 void colstats(const float* U, int B, int D, bool sqrt_in, double* acc, unsigned int* ticket, float eps, float momentum,
@@ -271,6 +282,11 @@ void bn_grad_finalize(const double* acc, int D, float* dgamma, float* dbeta, cud
 
 void bump_counters(int64_t* counters, int n, cudaStream_t st) {
   launch_k(k_bump, cdiv(n, 64), 64, 0, st, counters, n);
+  note_launch();
+}
+
+void finalize_step(drv_step_out* out, const uint32_t* status, int64_t* counters, int n, cudaStream_t st) {
+  launch_k(k_finalize_step, 1, 64, 0, st, out, status, counters, n);
   note_launch();
 }
 

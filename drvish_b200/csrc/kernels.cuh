@@ -72,5 +72,7 @@ void dr_prior_factor(const float* w_prior, const float* b_prior, const float* ep
                      float* d_bias_loc, float* d_bias_scale_unc, drv_step_out* out, cudaStream_t st);
 
 void finalize_status(drv_step_out* out, cudaStream_t st);
+// counters[i] += 1 (BatchNorm num_batches_tracked; may be null), out->status = *status | NaN flag
+void finalize_step(drv_step_out* out, const uint32_t* status, int64_t* counters, int n, cudaStream_t st);
 
 }  // namespace drv

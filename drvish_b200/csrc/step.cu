@@ -48,7 +48,8 @@ SideStream* side_stream() {
     tried = true;
     if (cudaStreamCreateWithFlags(&ss.side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ss.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ss.ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&ss.ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ss.ev_aux, cudaEventDisableTiming) != cudaSuccess) {
       ss.side = nullptr;
       cudaGetLastError();
     }
@@ -158,6 +159,8 @@ Plan make_plan(const drv_dims& d, const Net& n) {
       p.grad_acc[s][k] = take(sizeof(double) * 2 * b.din);
       p.ticket[s][k] = take(4 * (size_t)(b.din / 32 + 2));  // one counter per column block of the statistics kernels
     }
+  p.ll = take(4 * B);    // per-cell log-likelihood / dLL/dl sums: atomic accumulation
+  p.asum = take(4 * B);
   p.status = take(256);
   p.zero_bytes = o - p.zero_begin;
   for (int s = 0; s < 2; ++s)
@@ -171,8 +174,6 @@ Plan make_plan(const drv_dims& d, const Net& n) {
   p.z = take(4 * B * d.n_latent);
   p.l = take(4 * B);
   p.lse = take(4 * B);
-  p.ll = take(4 * B);
-  p.asum = take(4 * B);
   p.dO = take(4 * B * (2 * d.n_latent + 2));
   if (d.n_drugs > 0) {
     p.u = take(4 * B * d.n_drugs);
@@ -408,22 +409,30 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
   }
 
   cudaMemsetAsync(c.ws + p.zero_begin, 0, p.zero_bytes, st);
-  cudaMemsetAsync(out, 0, sizeof(drv_step_out), st);
   prof::mark(0, st);
-  // tf32 hi / lo parts of every weight, one pass over the flat parameter buffer (the tensor-core
-  // kernels take pre-rounded operands: kind::tf32 truncates)
-  bool enc_sd = false;
-  if (!(hp->flags & DRV_FLAG_FORCE_SIMT)) {
-    if (side) {
-      // the parameter split and the statistics of x are independent: run them side by side
-      side->fork(st);
-      split_params_tf32(params, (size_t)n.n_param_floats, c.at<float>(p.p_hi), c.at<float>(p.p_lo), side->side);
-      block_forward(c, 0, 0, x, false);
-      enc_sd = true;
-      side->join(st);
-    } else {
-      split_params_tf32(params, (size_t)n.n_param_floats, c.at<float>(p.p_hi), c.at<float>(p.p_lo), st);
+  // Start-of-step work that is off the critical chain runs on the side stream, next to the
+  // statistics of x: the result record and the whole gradient buffer are cleared ONCE (every
+  // gradient kernel then accumulates - no memset nodes inside the backward chain), and the tf32
+  // hi / lo parts of every weight are produced in one pass over the flat parameter buffer (the
+  // tensor-core kernels take pre-rounded operands: kind::tf32 truncates).
+  const bool tc_any = !(hp->flags & DRV_FLAG_FORCE_SIMT);
+  const bool dec_tc = tc_decoder_supported(d, *hp) && !(hp->flags & 16);
+  {
+    cudaStream_t ss = st;
+    if (side) { side->fork(st); ss = side->side; }
+    cudaMemsetAsync(out, 0, sizeof(drv_step_out), ss);
+    if (tc_any) split_params_tf32(params, (size_t)n.n_param_floats, c.at<float>(p.p_hi), c.at<float>(p.p_lo), ss);
+    if (bwd) {
+      cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)n.n_param_floats, ss);
+      // d loss / d (last decoder activation): split-K accumulation target of the fused decoder backward
+      if (dec_tc) cudaMemsetAsync(c.at<float>(p.Gb[1][NB - 1]), 0, sizeof(float) * (size_t)B * n.dec[NB - 1].din, ss);
     }
+  }
+  bool enc_sd = false;
+  if (side) {
+    block_forward(c, 0, 0, x, false);  // statistics of x (main stream) overlap the side-stream work
+    enc_sd = true;
+    side->join(st);
   }
   // ---- guide: encoder + reparameterised draws (nbvae.py:81-90) --------------------------------
   for (int k = 0; k < NB; ++k) enc_sd = block_forward(c, 0, k, x, true, enc_sd);
@@ -443,14 +452,14 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
     dr_means(c.at<float>(p.u), b_prior, labels, dose_offsets, ds, y, hp->sigma_scale, c.at<float>(p.m),
              c.at<float>(p.gfac), out, status, dst);
     if (bwd) {
-      // weight_loc / weight_scale never enter the loss: their gradient is zero
-      cudaMemsetAsync(grads + n.w_loc, 0, sizeof(float) * (size_t)(n.b_loc - n.w_loc), dst);
+      // weight_loc / weight_scale never enter the loss: their gradient stays zero
     }
     dr_prior_factor(w_prior, b_prior, eps_bias, params + n.b_loc, params + n.b_scale, dose_offsets, ds, *hp,
                     bwd ? grads + n.b_loc : nullptr, bwd ? grads + n.b_scale : nullptr, out, dst);
     if (bwd)
       dr_backward(c.at<float>(p.u), b_prior, w_prior, labels, dose_offsets, c.at<float>(p.gfac), ds,
                   c.at<float>(p.du), c.at<float>(p.dz_drs), dst);
+    if (side) side->record_aux();  // the sampling backward waits for exactly this point of the side stream
   }
 
   // ---- model: decoder trunk (nbvae.py:70 -> modules.py:93) ------------------------------------
@@ -499,15 +508,14 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
     // ---- decoder trunk backward, sampling backward ---------------------------------------------
     block_backward(c, 1, NB - 1, z, nullptr, true);
     for (int k = NB - 2; k >= 0; --k) block_backward(c, 1, k, z, c.at<float>(p.Gb[1][k + 1]), false);
-    if (side && d.n_drugs > 0) side->join(st);  // dz_drs (later side work re-forks)
+    if (side && d.n_drugs > 0) side->wait_aux(st);  // dz_drs is ready; weight-gradient GEMMs queued behind it are not waited for
     sample_backward(O, eps_z, eps_l, z, l, c.at<float>(p.Gb[1][0]), d.n_drugs > 0 ? c.at<float>(p.dz_drs) : nullptr,
                     c.at<float>(p.asum), B, L, *hp, c.at<float>(p.dO), st);
     prof::mark(6, st);
     if (stop_after_decoder) {
       // decoder / dose-response gradients and the loss are final: hand back to the caller
       if (side) side->join(st);
-      cudaMemcpyAsync(&out->status, status, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
-      finalize_status(out, st);
+      finalize_step(out, status, nullptr, 0, st);
       return finish();
     }
     // ---- encoder backward ----------------------------------------------------------------------
@@ -516,12 +524,8 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
     prof::mark(7, st);
   }
   if (side) side->join(st);
-  if (bn_batches && !(hp->flags & DRV_FLAG_NO_BN_UPDATE)) bump_counters(bn_batches, n.n_bn, st);
-  // fold the status word into the result record
-  {
-    cudaMemcpyAsync(&out->status, status, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
-    finalize_status(out, st);
-  }
+  // BatchNorm batch counters + status word folded into the result record: one launch
+  finalize_step(out, status, (bn_batches && !(hp->flags & DRV_FLAG_NO_BN_UPDATE)) ? bn_batches : nullptr, n.n_bn, st);
   if (prof::enabled && prof::n_steps < prof::MAX_STEPS) {
     if (!bwd) for (int i = 5; i <= DRV_N_SECTIONS; ++i) prof::mark(i, st);
     ++prof::n_steps;

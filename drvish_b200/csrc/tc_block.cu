@@ -266,7 +266,6 @@ void tc_block_backward(const TcBlockArgs& a, cudaStream_t st) {
     dim3 cb(32, 8);
     int rows = 64;
     dim3 cgrid((a.dout + 31) / 32, (a.B + rows - 1) / rows);
-    cudaMemsetAsync(a.db, 0, sizeof(float) * a.dout, st);
     launch_k(k_round_colsum, cgrid, cb, 0, st, a.dV, a.B, a.dout, rows, s.dh_r, a.db);
     note_launch();
   }
@@ -286,7 +285,7 @@ void tc_block_backward(const TcBlockArgs& a, cudaStream_t st) {
   // dW[j][i] = sum_b dV[b][j] A[b][i]: both operands MN-major (K = cells): off the critical chain
   cudaStream_t ws = st;
   if (a.side) { a.side->attach(); ws = a.side->side; }
-  if (rc == 0) rc = tc::gemm_tf32(s.dh_r, a.dout, true, s.a_hi, a.din, true, a.dW, a.din, a.dout, a.din, a.B, 0, false, ws);
+  if (rc == 0) rc = tc::gemm_tf32(s.dh_r, a.dout, true, s.a_hi, a.din, true, a.dW, a.din, a.dout, a.din, a.B, 0, /*accumulate (cleared at step start)=*/true, ws);
   if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
   if (a.dY || fused_bn0) return;  // (the ReLU gate is applied by the BatchNorm backward kernels)
   // reduce dA to the input-BatchNorm gradients (gate and xhat recomputed from sqrt(x))

@@ -55,8 +55,8 @@ struct DecParams {
   // phase 1
   float* part_m;      // [n_slots][B]
   float* part_s;
-  // phase 2/3
-  const float* lse;   // [B]
+  // phase 2/3: lse[b] is combined from the phase-1 partials when a CTA enters a cell tile
+  int lse_n_gt, lse_n_tiles, lse_grid;  // phase 1's gene tiles per cell tile, tile count and grid
   float* ll;          // [B] (atomic accumulation, zeroed)
   float* asum;        // [B]
   float* dlogits;     // [B][2G]
@@ -84,6 +84,21 @@ __device__ __forceinline__ int butterfly4(float (&w)[4], int lane) {
   w[0] += __shfl_xor_sync(0xffffffffu, w[0], 2);
   w[0] += __shfl_xor_sync(0xffffffffu, w[0], 1);
   return (lane & 7) == 0 ? ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1) : -1;
+}
+
+// logsumexp of row b from the (max, sum exp) partials phase 1 left per (CTA, column group) slot
+__device__ __forceinline__ float combine_lse(const DecParams& p, int ct, int b) {
+  const int first_cta = (int)((((long long)ct * p.lse_n_gt + 1) * p.lse_grid - 1) / p.lse_n_tiles);
+  const int last_cta = (int)((((long long)ct * p.lse_n_gt + p.lse_n_gt) * p.lse_grid - 1) / p.lse_n_tiles);
+  const int n_slots = (last_cta - first_cta + 1) * 4;
+  float m = -INFINITY;
+  for (int s = 0; s < n_slots; ++s) m = fmaxf(m, __ldcg(&p.part_m[(size_t)s * p.B + b]));
+  float acc = 0.f;
+  for (int s = 0; s < n_slots; ++s) {
+    const float pmv = __ldcg(&p.part_m[(size_t)s * p.B + b]);
+    if (pmv > -INFINITY) acc += __ldcg(&p.part_s[(size_t)s * p.B + b]) * __expf(pmv - m);
+  }
+  return m + logf(acc);
 }
 
 template <int PHASE, bool WITH_A>
@@ -225,7 +240,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
         row_ok = b < p.B;
         if (PHASE != 1 && row_ok) {
           lib_b = p.lib[b];
-          lse_b = p.lse[b];
+          lse_b = combine_lse(p, ct, b);
           if (PHASE == 3) asum_b = p.asum[b];
         }
         if (PHASE == 3 && !row_ok) asum_b = 0.f;
@@ -274,10 +289,15 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
         const int xs = it & 1, xph = (it >> 1) & 1;
         mbar_wait(&x_full[xs], xph);
         const uint8_t* drow_s = xbuf + xs * XB + cg * (BM * 128) + r * 128;
+        float sv_n[4];
+        tmem_ld4(tbase + cg * 32, sv_n);
+        tmem_ld_wait();
 #pragma unroll
         for (int g4 = 0; g4 < 8; ++g4) {
           float sv[4], bs[4], ds[4];
-          tmem_ld4(tbase + cg * 32 + g4 * 4, sv);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) sv[v] = sv_n[v];
+          if (g4 + 1 < 8) tmem_ld4(tbase + cg * 32 + (g4 + 1) * 4, sv_n);  // next group, in flight during this one
           const int gq = gbase + 4 * g4;
           const bool vec = gq + 4 <= p.G;
           float* d0 = drow + 4 * g4;
@@ -290,7 +310,6 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
           }
           const float4 dld = *reinterpret_cast<const float4*>(drow_s + ((g4 ^ (r & 7)) * 16));
           const float dsp[4] = {dld.x, dld.y, dld.z, dld.w};
-          tmem_ld_wait();
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
             const bool ok = row_ok && (gq + v < p.G);
@@ -307,6 +326,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
           }
           const int col = butterfly4(ds, lane);
           if (col >= 0 && gq + col < p.G) atomicAdd(&p.db[gq + col], ds[0]);
+          tmem_ld_wait();
         }
         tc_fence_before();
         __syncwarp();
@@ -326,11 +346,21 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
         const float lml = lib_b - lse_b;
         const uint8_t* xrow = xbuf + xs * XB + (cg >> 1) * (BM * 128) + r * 128;
         const bool full_cols = gbase + 16 <= p.G;
+        float sv_n[4], rv_n[4];
+        tmem_ld4(tbase + cg * 16, sv_n);
+        tmem_ld4(tbase + 64 + cg * 16, rv_n);
+        tmem_ld_wait();
 #pragma unroll 1
         for (int g4 = 0; g4 < 4; ++g4) {
           float sv[4], rv[4], xv[4], bs[4], br[4];
-          tmem_ld4(tbase + cg * 16 + g4 * 4, sv);
-          tmem_ld4(tbase + 64 + cg * 16 + g4 * 4, rv);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) { sv[v] = sv_n[v]; rv[v] = rv_n[v]; }
+          {
+            // next group's logits: in flight while this group's NB terms are evaluated
+            const int gn = g4 + 1 < 4 ? g4 + 1 : g4;
+            tmem_ld4(tbase + cg * 16 + gn * 4, sv_n);
+            tmem_ld4(tbase + 64 + cg * 16 + gn * 4, rv_n);
+          }
           {
             // count tile: box (cg/2), row r, 16-byte chunk (cg%2)*4 + g4, XOR-swizzled with r%8
             const int chunk = ((cg & 1) * 4 + g4) ^ (r & 7);
@@ -351,7 +381,6 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
               br[v] = okg ? __ldg(&p.bias[p.G + gq + v]) : 0.f;
             }
           }
-          tmem_ld_wait();
           float a_lsl[4], a_rho[4], a_x[4];
           bool ok[4];
 #pragma unroll
@@ -393,6 +422,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
             const int col = butterfly4(dr, lane);
             if (col >= 0 && gq + col < p.G) atomicAdd(&p.db[p.G + gq + col], dr[0]);
           }
+          tmem_ld_wait();
         }
         tc_fence_before();
         __syncwarp();
@@ -430,25 +460,6 @@ __global__ void k_round_tf32(const float* __restrict__ src, size_t n, float* __r
   pdl_prologue();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     dst[i] = rna_tf32(src[i]);
-}
-
-__global__ void k_lse_combine(const float* __restrict__ pm, const float* __restrict__ ps, int n_gt, int n_tiles, int grid,
-                              int B, float* __restrict__ lse) {
-  pdl_prologue();
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const int ct = b / BM;
-  const int first_cta = (int)((((long long)ct * n_gt + 1) * grid - 1) / n_tiles);
-  const int last_cta = (int)((((long long)ct * n_gt + n_gt) * grid - 1) / n_tiles);
-  const int n_slots = (last_cta - first_cta + 1) * 4;
-  float m = -INFINITY;
-  for (int s = 0; s < n_slots; ++s) m = fmaxf(m, pm[(size_t)s * B + b]);
-  float acc = 0.f;
-  for (int s = 0; s < n_slots; ++s) {
-    float pmv = pm[(size_t)s * B + b];
-    if (pmv > -INFINITY) acc += ps[(size_t)s * B + b] * __expf(pmv - m);
-  }
-  lse[b] = m + logf(acc);
 }
 
 __global__ void k_loss_from_ll(const float* __restrict__ ll, int B, float c, drv_step_out* out) {
@@ -549,6 +560,12 @@ bool tc_decoder_supported(const drv_dims& d, const drv_hparams& hp) {
   return d.n_genes % 4 == 0 && d.n_genes >= 64 && h % 32 == 0 && h >= 32 && h <= 512 && d.n_cells >= 32;
 }
 
+static void set_lse_layout(DecParams& p, int n_ct, int n_gt1) {
+  p.lse_n_gt = n_gt1;
+  p.lse_n_tiles = n_ct * n_gt1;
+  p.lse_grid = p.lse_n_tiles < sm_count() ? p.lse_n_tiles : sm_count();
+}
+
 void tc_decoder_forward(const TcDecoderArgs& a, cudaStream_t st) {
   Scratch s = carve(a.scratch, a.B, a.G, a.h);
   CUtensorMap tAct, tW1, tW3, tX;
@@ -562,24 +579,16 @@ void tc_decoder_forward(const TcDecoderArgs& a, cudaStream_t st) {
   note_launch();
   DecParams p{};
   p.B = a.B; p.G = a.G; p.h = a.h; p.bias = a.bias; p.lib = a.lib; p.eps = a.eps; p.c = a.c;
-  p.part_m = s.part_m; p.part_s = s.part_s; p.lse = a.lse; p.ll = a.ll; p.asum = a.asum;
+  p.part_m = s.part_m; p.part_s = s.part_s; p.ll = a.ll; p.asum = a.asum;
   p.dlogits = a.dlogits; p.db = a.db;
   const int n_ct = (a.B + BM - 1) / BM;
   // phase 1: logsumexp over genes
   const int n_gt1 = (a.G + 127) / 128;
+  set_lse_layout(p, n_ct, n_gt1);
   drv_internal_kmark(0, 0, st);
   launch_dec(k_dec<1, false>, n_ct * n_gt1, tAct, tW1, tX, p, st);
   drv_internal_kmark(0, 1, st);
-  {
-    const int n_tiles1 = n_ct * n_gt1;
-    const int grid1 = n_tiles1 < sm_count() ? n_tiles1 : sm_count();
-    launch_k(k_lse_combine, (a.B + 63) / 64, 64, 0, st, s.part_m, s.part_s, n_gt1, n_tiles1, grid1, a.B, a.lse);
-  }
-  note_launch();
-  // phase 2: NB log-likelihood row sums
-  cudaMemsetAsync(a.ll, 0, sizeof(float) * a.B, st);
-  cudaMemsetAsync(a.asum, 0, sizeof(float) * a.B, st);
-  if (a.bwd) cudaMemsetAsync(a.db, 0, sizeof(float) * 2 * a.G, st);  // bias gradient: phases 2 (log_r) + 3 (scale)
+  // phase 2: NB log-likelihood row sums (ll / asum / db were zeroed at the start of the step)
   const int n_gt = (a.G + 63) / 64;
   drv_internal_kmark(1, 0, st);
   if (a.bwd) launch_dec(k_dec<2, true>, n_ct * n_gt, tAct, tW3, tX, p, st);
@@ -598,8 +607,9 @@ void tc_decoder_backward(const TcDecoderArgs& a, cudaStream_t st) {
   }
   DecParams p{};
   p.B = a.B; p.G = a.G; p.h = a.h; p.bias = a.bias; p.lib = a.lib; p.eps = a.eps; p.c = a.c;
-  p.lse = a.lse; p.ll = a.ll; p.asum = a.asum; p.dlogits = a.dlogits; p.db = a.db;
+  p.part_m = s.part_m; p.part_s = s.part_s; p.ll = a.ll; p.asum = a.asum; p.dlogits = a.dlogits; p.db = a.db;
   const int n_ct = (a.B + BM - 1) / BM, n_gt1 = (a.G + 127) / 128;
+  set_lse_layout(p, n_ct, n_gt1);
   CUtensorMap tD;  // scale half of dlogits: [B][G] with row stride 2G
   if (!tmap_2d(&tD, a.dlogits, a.B, a.G, 2 * (uint64_t)a.G, BM, 32)) {
     if (g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
@@ -612,13 +622,13 @@ void tc_decoder_backward(const TcDecoderArgs& a, cudaStream_t st) {
   if (a.side) a.side->mark(st);
   // dAct[b][i] = sum_j dlogits[b][j] W[j][i]   (A K-major, B MN-major, K = 2G): critical path, submitted first
   drv_internal_kmark(3, 0, st);
-  int rc = gemm_tf32(a.dlogits, 2 * a.G, false, a.W_hi, a.h, true, a.dY, a.h, a.B, a.h, 2 * a.G, 0, false, st);
+  int rc = gemm_tf32(a.dlogits, 2 * a.G, false, a.W_hi, a.h, true, a.dY, a.h, a.B, a.h, 2 * a.G, 0, /*accumulate (cleared at step start)=*/true, st);
   drv_internal_kmark(3, 1, st);
   // dW[j][i] = sum_b dlogits[b][j] act[b][i]   (both operands MN-major, K = cells): off the critical chain
   cudaStream_t ws = st;
   if (a.side) { a.side->attach(); ws = a.side->side; }
   drv_internal_kmark(4, 0, ws);
-  if (rc == 0) rc = gemm_tf32(a.dlogits, 2 * a.G, true, s.act, a.h, true, a.dW, a.h, 2 * a.G, a.h, a.B, 0, false, ws);
+  if (rc == 0) rc = gemm_tf32(a.dlogits, 2 * a.G, true, s.act, a.h, true, a.dW, a.h, 2 * a.G, a.h, a.B, 0, true, ws);
   drv_internal_kmark(4, 1, ws);
   if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
   // the ReLU gate of dAct is applied by the BatchNorm backward kernels (block_backward)
