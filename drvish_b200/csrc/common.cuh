@@ -36,6 +36,25 @@ __device__ __forceinline__ void pdl_prologue() {
 bool pdl_enabled();
 
 template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args);
+
+// Plain stream-ordered launch.  For persistent kernels that fill an SM's shared memory: launched as
+// a programmatic dependent such a kernel becomes RESIDENT while it waits for its predecessor and
+// blocks the SMs for the kernels of the other stream (seen in the graph timeline: a 32-CTA weight-
+// gradient GEMM idling on 32 SMs for 48 us behind the previous side-stream GEMM).
+template <typename... KArgs, typename... Args>
+inline void launch_k_plain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.attrs = nullptr;
+  cfg.numAttrs = 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<Args&&>(args)...);
+}
+
+template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;

@@ -224,10 +224,56 @@ void simt_linear_wgrad(const float* dV, int B, int dout, const float* U, int din
   note_launch();
 }
 
+// dA = dV W for a narrow input (din <= 32, e.g. the decoder's first Linear, latent -> hidden): the
+// generic tile kernel would run 64 CTAs with most of each tile empty.  One warp per row: the lanes
+// split the dout-long dot products (coalesced reads of the dV row, W^T staged in shared memory with
+// the dout index contiguous -> conflict-free), then a butterfly leaves column i's sum in every lane.
+template <int DIN_MAX>
+__global__ void __launch_bounds__(256) k_dgrad_skinny(const float* __restrict__ dV, int B, int dout,
+                                                      const float* __restrict__ W, int din, float* __restrict__ dA) {
+  pdl_prologue();
+  extern __shared__ float sk_sh[];  // W^T: [din][dout]
+  for (int i = threadIdx.x; i < dout * din; i += blockDim.x) {
+    const int j = i / din, c = i % din;
+    sk_sh[c * dout + j] = W[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+  for (int r = blockIdx.x * 8 + warp; r < B; r += gridDim.x * 8) {
+    float acc[DIN_MAX];
+#pragma unroll
+    for (int i = 0; i < DIN_MAX; ++i) acc[i] = 0.f;
+    const float* row = dV + (size_t)r * dout;
+    for (int j = lane; j < dout; j += 32) {
+      const float v = row[j];
+#pragma unroll
+      for (int i = 0; i < DIN_MAX; ++i)
+        if (i < din) acc[i] = __fmaf_rn(v, sk_sh[i * dout + j], acc[i]);
+    }
+    float mine = 0.f;
+#pragma unroll
+    for (int i = 0; i < DIN_MAX; ++i) {
+      if (i < din) {
+        const float t = warp_sum(acc[i]);
+        if (lane == i) mine = t;
+      }
+    }
+    if (lane < din) dA[(size_t)r * din + lane] = mine;
+  }
+}
+
 // dA = dV W (ungated): the ReLU gate is applied by the BatchNorm backward kernels
 void simt_linear_dgrad_gate(const float* dV, int B, int dout, const float* W, int din, const float* U, int pro_mode,
                             BnParams bn, float* dY, cudaStream_t st) {
   (void)U; (void)pro_mode; (void)bn;
+  const size_t sk_bytes = sizeof(float) * (size_t)dout * din;
+  if (din <= 32 && sk_bytes <= 48 * 1024) {
+    const int grid = cdiv(B, 8) < 148 * 4 ? cdiv(B, 8) : 148 * 4;
+    if (din <= 16) launch_k(k_dgrad_skinny<16>, grid, 256, sk_bytes, st, dV, B, dout, W, din, dY);
+    else launch_k(k_dgrad_skinny<32>, grid, 256, sk_bytes, st, dV, B, dout, W, din, dY);
+    note_launch();
+    return;
+  }
   Prologue none{0, {}};
   Epilogue ep{};
   launch_k(k_gemm<true, false, false, EPI_PLAIN>, grid_for(B, din), NT, 0, st, dV, dout, W, din, dY, din, B, din, dout, none,

@@ -194,6 +194,50 @@ __global__ void k_bn_bwd_apply(float* __restrict__ dY, const float* __restrict__
   }
 }
 
+// BatchNorm backward apply fused with the preparation of the NEXT Linear's backward operands: dU is
+// written once, tf32-rounded (the MMA operand of both the dA and the dW GEMM of the block below),
+// and its unrounded column sums are accumulated into that block's bias gradient.
+template <bool GATE>
+__global__ void __launch_bounds__(256) k_bn_bwd_apply_round(const float* __restrict__ dY, const float* __restrict__ U, int B,
+                                                            int D, int rows_per_cta, BnParams bn,
+                                                            const double* __restrict__ acc, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, float* __restrict__ dU_r,
+                                                            float* __restrict__ db_next) {
+  pdl_prologue();
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(B, r0 + rows_per_cta);
+  float s = 0.f;
+  if (col < D) {
+    const float invB = 1.0f / (float)B;
+    const float s1 = (float)acc[col] * invB, s2 = (float)acc[D + col] * invB;
+    const float rstd = bn.rstd[col], mean = bn.mean[col], gamma = bn.gamma[col], beta = bn.beta[col];
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      const size_t idx = (size_t)r * D + col;
+      const float xh = bn_xhat(U[idx], mean, rstd);
+      float g = dY[idx];
+      if (GATE && !(bn_y(xh, gamma, beta) > 0.f)) g = 0.f;
+      const float du = gamma * rstd * (g - s1 - xh * s2);
+      uint32_t rr;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rr) : "f"(du));
+      dU_r[idx] = __uint_as_float(rr);
+      s += du;
+    }
+    if (blockIdx.y == 0 && threadIdx.y == 0) {
+      dbeta[col] = (float)acc[col];
+      dgamma[col] = (float)acc[D + col];
+    }
+  }
+  __shared__ float sh[8][32];
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < D) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+    atomicAdd(&db_next[col], t);
+  }
+}
+
 __global__ void k_bn_grad_finalize(const double* __restrict__ acc, int D, float* __restrict__ dgamma,
                                    float* __restrict__ dbeta) {
   pdl_prologue();
@@ -272,6 +316,15 @@ void bn_bwd_apply(float* dY_dU, const float* U, int B, int D, BnParams bn, const
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (gate) launch_k(k_bn_bwd_apply<true>, blocks, 256, 0, st, dY_dU, U, B, D, bn, acc, dgamma, dbeta);
   else launch_k(k_bn_bwd_apply<false>, blocks, 256, 0, st, dY_dU, U, B, D, bn, acc, dgamma, dbeta);
+  note_launch();
+}
+
+void bn_bwd_apply_round(const float* dY, const float* U, int B, int D, BnParams bn, const double* acc, float* dgamma,
+                        float* dbeta, bool gate, float* dU_r, float* db_next, cudaStream_t st) {
+  const int rows = 64;
+  dim3 grid(cdiv(D, 32), cdiv(B, rows)), block(32, 8);
+  if (gate) launch_k(k_bn_bwd_apply_round<true>, grid, block, 0, st, dY, U, B, D, rows, bn, acc, dgamma, dbeta, dU_r, db_next);
+  else launch_k(k_bn_bwd_apply_round<false>, grid, block, 0, st, dY, U, B, D, rows, bn, acc, dgamma, dbeta, dU_r, db_next);
   note_launch();
 }
 

@@ -16,6 +16,9 @@ void bn_bwd_reduce(const float* dY, const float* U, int B, int D, BnParams bn, d
 // dU = gamma rstd (dY - s1/B - xhat s2/B) in place over dY; also dgamma = s2, dbeta = s1.
 void bn_bwd_apply(float* dY_dU, const float* U, int B, int D, BnParams bn, const double* acc, float* dgamma,
                   float* dbeta, bool gate, cudaStream_t st);
+// same, but dU is written tf32-rounded to dU_r (not in place) and its column sums are added to db_next
+void bn_bwd_apply_round(const float* dY, const float* U, int B, int D, BnParams bn, const double* acc, float* dgamma,
+                        float* dbeta, bool gate, float* dU_r, float* db_next, cudaStream_t st);
 void bn_grad_finalize(const double* acc, int D, float* dgamma, float* dbeta, cudaStream_t st);
 void bump_counters(int64_t* counters, int n, cudaStream_t st);
 

@@ -265,7 +265,10 @@ bool block_forward(const Ctx& c, int s, int k, const float* U0, bool do_linear, 
 // BatchNorm backward (d gamma, d beta, dU in place).  `linear_done`: dW/db/dY were already
 // produced (fused tcgen05 path).  The first encoder block needs no dU (x is data): its dY is
 // reduced to d gamma / d beta on the fly.
-void block_backward(const Ctx& c, int s, int k, const float* U0, const float* dV, bool linear_done) {
+// dv_prepared: the block above already left this block's tf32-rounded dV and bias gradient
+// (bn_bwd_apply_round).  Returns whether this block did the same for block k - 1.
+bool block_backward(const Ctx& c, int s, int k, const float* U0, const float* dV, bool linear_done,
+                    bool dv_prepared = false) {
   bool gated = false;  // Gb holds the ungated dAct: the BatchNorm backward kernels apply the ReLU gate
   const int B = c.d.n_cells;
   const Block& b = s == 0 ? c.n.enc[k] : c.n.dec[k];
@@ -282,6 +285,7 @@ void block_backward(const Ctx& c, int s, int k, const float* U0, const float* dV
       a.scratch = c.ws + c.p.tcb[s][k]; a.dV = dV; a.dW = c.grads + b.W; a.db = c.grads + b.bias;
       a.dY = sq ? nullptr : c.at<float>(c.p.Gb[s][k]); a.gacc = gacc; a.side = c.side;
       a.no_fused_prologue = (c.hp.flags & 512) != 0;
+      a.dv_prepared = dv_prepared;
       tc_block_backward(a, c.st);
       gated = false;
     } else {
@@ -297,12 +301,23 @@ void block_backward(const Ctx& c, int s, int k, const float* U0, const float* dV
   }
   if (sq) {
     bn_grad_finalize(gacc, b.din, c.grads + b.gamma, c.grads + b.beta, c.st);
-  } else {
-    float* dY = c.at<float>(c.p.Gb[s][k]);
-    if (linear_done) gated = false;  // fused decoder path: dAct arrives ungated
-    bn_bwd_reduce(dY, U, B, b.din, c.bn(s, k), gacc, !gated, c.st);
-    bn_bwd_apply(dY, U, B, b.din, c.bn(s, k), gacc, c.grads + b.gamma, c.grads + b.beta, !gated, c.st);
+    return false;
   }
+  float* dY = c.at<float>(c.p.Gb[s][k]);
+  if (linear_done) gated = false;  // fused decoder path: dAct arrives ungated
+  bn_bwd_reduce(dY, U, B, b.din, c.bn(s, k), gacc, !gated, c.st);
+  if (k >= 1 && !(c.hp.flags & 2048)) {  // 2048 (debug): separate round / column-sum kernel
+    const Block& nb = s == 0 ? c.n.enc[k - 1] : c.n.dec[k - 1];
+    const bool nsq = (s == 0 && k - 1 == 0);
+    if (c.p.tcb[s][k - 1] && tc_block_backward_supported(B, nb.din, nb.dout, c.hp) &&
+        (nsq ? !(c.hp.flags & 32) : !(c.hp.flags & 4))) {
+      bn_bwd_apply_round(dY, U, B, b.din, c.bn(s, k), gacc, c.grads + b.gamma, c.grads + b.beta, !gated,
+                         tc_block_rounded_dv(c.ws + c.p.tcb[s][k - 1], B, nb.din, nb.dout), c.grads + nb.bias, c.st);
+      return true;
+    }
+  }
+  bn_bwd_apply(dY, U, B, b.din, c.bn(s, k), gacc, c.grads + b.gamma, c.grads + b.beta, !gated, c.st);
+  return false;
 }
 
 int finish() {
@@ -401,8 +416,8 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
   const bool part2_only = bwd && (hp->flags & DRV_FLAG_ENCODER_BACKWARD_ONLY);
   const bool stop_after_decoder = bwd && (hp->flags & DRV_FLAG_STOP_AFTER_DECODER);
   if (part2_only) {
-    for (int k = NB - 1; k >= 0; --k)
-      block_backward(c, 0, k, x, k == NB - 1 ? c.at<float>(p.dO) : c.at<float>(p.Gb[0][k + 1]), false);
+    for (int k = NB - 1, prep = 0; k >= 0; --k)
+      prep = block_backward(c, 0, k, x, k == NB - 1 ? c.at<float>(p.dO) : c.at<float>(p.Gb[0][k + 1]), false, prep);
     if (side) side->join(st);
     if (bn_batches && !(hp->flags & DRV_FLAG_NO_BN_UPDATE)) bump_counters(bn_batches, n.n_bn, st);
     return finish();
@@ -417,23 +432,32 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
   // tensor-core kernels take pre-rounded operands: kind::tf32 truncates).
   const bool tc_any = !(hp->flags & DRV_FLAG_FORCE_SIMT);
   const bool dec_tc = tc_decoder_supported(d, *hp) && !(hp->flags & 16);
+  bool enc_sd0 = false;
   {
     cudaStream_t ss = st;
     if (side) { side->fork(st); ss = side->side; }
     cudaMemsetAsync(out, 0, sizeof(drv_step_out), ss);
-    if (tc_any) split_params_tf32(params, (size_t)n.n_param_floats, c.at<float>(p.p_hi), c.at<float>(p.p_lo), ss);
+    // encoder weights first: they are all the encoder forward waits for
+    const size_t enc_floats = (size_t)n.dec[0].gamma;
+    if (tc_any) split_params_tf32(params, enc_floats, c.at<float>(p.p_hi), c.at<float>(p.p_lo), ss);
+    bool enc_sd_ = false;
+    if (side) {
+      block_forward(c, 0, 0, x, false);  // statistics of x (main stream) overlap the side-stream work
+      enc_sd_ = true;
+      side->join(st);
+      side->used = true;  // the rest of the start-up work stays behind on the side stream (joined after the sampling)
+    }
+    if (tc_any)
+      split_params_tf32(params + enc_floats, (size_t)n.n_param_floats - enc_floats, c.at<float>(p.p_hi) + enc_floats,
+                        c.at<float>(p.p_lo) + enc_floats, ss);
     if (bwd) {
       cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)n.n_param_floats, ss);
       // d loss / d (last decoder activation): split-K accumulation target of the fused decoder backward
       if (dec_tc) cudaMemsetAsync(c.at<float>(p.Gb[1][NB - 1]), 0, sizeof(float) * (size_t)B * n.dec[NB - 1].din, ss);
     }
+    enc_sd0 = enc_sd_;
   }
-  bool enc_sd = false;
-  if (side) {
-    block_forward(c, 0, 0, x, false);  // statistics of x (main stream) overlap the side-stream work
-    enc_sd = true;
-    side->join(st);
-  }
+  bool enc_sd = enc_sd0;
   // ---- guide: encoder + reparameterised draws (nbvae.py:81-90) --------------------------------
   for (int k = 0; k < NB; ++k) enc_sd = block_forward(c, 0, k, x, true, enc_sd);
   const float* O = c.at<float>(p.V[0][NB - 1]);
@@ -442,9 +466,11 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
   sample_forward(O, eps_z, eps_l, B, L, *hp, z, l, out, st);
   prof::mark(1, st);
 
+  if (side) side->join(st);  // decoder weights' tf32 parts, cleared gradients
   // ---- dose-response head (drnbvae.py:110-116, 131-132): needs only z, runs on the side stream
   // concurrently with the decoder; joined before the sampling backward consumes dz_drs
   DrShape ds{B, L, d.n_drugs, d.n_classes, d.n_doses_total};
+  auto dose_response_head = [&]() {
   if (d.n_drugs > 0) {
     cudaStream_t dst = st;
     if (side) { side->fork(st); dst = side->side; }
@@ -461,6 +487,11 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
                   c.at<float>(p.du), c.at<float>(p.dz_drs), dst);
     if (side) side->record_aux();  // the sampling backward waits for exactly this point of the side stream
   }
+  };
+  // forward-only calls and stream-less calls run it here; in training it is deferred to the decoder
+  // backward, where it overlaps the bandwidth-bound GEMMs instead of the latency-bound trunk
+  const bool dr_late = bwd && side != nullptr && dec_tc;
+  if (!dr_late) dose_response_head();
 
   // ---- model: decoder trunk (nbvae.py:70 -> modules.py:93) ------------------------------------
   const Block& last = n.dec[NB - 1];
@@ -495,6 +526,7 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
     // ---- backward of the last decoder Linear ---------------------------------------------------
     if (use_tc) {
       ta.side = side;
+      if (dr_late) dose_response_head();  // side stream: overlaps phase 3 / the dAct GEMM, ahead of the dW GEMM
       tc_decoder_backward(ta, st);
     } else {
       cudaStream_t ws = st;
@@ -506,8 +538,8 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
     }
     prof::mark(5, st);
     // ---- decoder trunk backward, sampling backward ---------------------------------------------
-    block_backward(c, 1, NB - 1, z, nullptr, true);
-    for (int k = NB - 2; k >= 0; --k) block_backward(c, 1, k, z, c.at<float>(p.Gb[1][k + 1]), false);
+    bool prep = block_backward(c, 1, NB - 1, z, nullptr, true);
+    for (int k = NB - 2; k >= 0; --k) prep = block_backward(c, 1, k, z, c.at<float>(p.Gb[1][k + 1]), false, prep);
     if (side && d.n_drugs > 0) side->wait_aux(st);  // dz_drs is ready; weight-gradient GEMMs queued behind it are not waited for
     sample_backward(O, eps_z, eps_l, z, l, c.at<float>(p.Gb[1][0]), d.n_drugs > 0 ? c.at<float>(p.dz_drs) : nullptr,
                     c.at<float>(p.asum), B, L, *hp, c.at<float>(p.dO), st);
@@ -519,8 +551,8 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
       return finish();
     }
     // ---- encoder backward ----------------------------------------------------------------------
-    for (int k = NB - 1; k >= 0; --k)
-      block_backward(c, 0, k, x, k == NB - 1 ? c.at<float>(p.dO) : c.at<float>(p.Gb[0][k + 1]), false);
+    for (int k = NB - 1, eprep = 0; k >= 0; --k)
+      eprep = block_backward(c, 0, k, x, k == NB - 1 ? c.at<float>(p.dO) : c.at<float>(p.Gb[0][k + 1]), false, eprep);
     prof::mark(7, st);
   }
   if (side) side->join(st);

@@ -24,7 +24,10 @@ struct TcDecoderArgs {
   float* dY;          // [B][h]: d loss / d (BN output), already gated by the ReLU mask
   SideStream* side;   // optional: weight-gradient GEMM runs there
   const ColStatsOut* next_stats;  // optional: BatchNorm statistics of V for the next block
+  bool dv_prepared;   // backward: the tf32-rounded dV and the bias gradient were already produced (bn_bwd_apply_round)
 };
+// where tc_block_backward expects the tf32-rounded dV of a block ([B][dout])
+float* tc_block_rounded_dv(void* scratch, int B, int din, int dout);
 
 size_t tc_workspace_bytes(const drv_dims& d);
 bool tc_decoder_supported(const drv_dims& d, const drv_hparams& hp);
@@ -76,7 +79,10 @@ struct TcBlockArgs {
   double* gacc;       // [2][din]: sum_b dY, sum_b dY*xhat  (-> d beta, d gamma), used when dY == NULL
   SideStream* side;   // optional: weight-gradient GEMM runs there
   const ColStatsOut* next_stats;  // optional: BatchNorm statistics of V for the next block
+  bool dv_prepared;   // backward: the tf32-rounded dV and the bias gradient were already produced (bn_bwd_apply_round)
 };
+// where tc_block_backward expects the tf32-rounded dV of a block ([B][dout])
+float* tc_block_rounded_dv(void* scratch, int B, int din, int dout);
 size_t tc_block_workspace_bytes(int B, int din, int dout);
 bool tc_block_forward_supported(int B, int din, int dout, const drv_hparams& hp);
 bool tc_block_backward_supported(int B, int din, int dout, const drv_hparams& hp);

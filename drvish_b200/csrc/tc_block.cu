@@ -261,7 +261,7 @@ void tc_block_backward(const TcBlockArgs& a, cudaStream_t st) {
   int rb = (int)((nd + 255) / 256);
   if (rb > n_sm() * 2) rb = n_sm() * 2;
   (void)rb;
-  {
+  if (!a.dv_prepared) {
     // one pass over dV: tf32-rounded copy (MMA operand) + column sums (bias gradient)
     dim3 cb(32, 8);
     int rows = 64;
@@ -300,6 +300,8 @@ void tc_block_backward(const TcBlockArgs& a, cudaStream_t st) {
   launch_k(k_bn0_grad, grid, block, 0, st, dA, a.U, a.B, a.din, rows, a.bn, a.gacc);
   note_launch();
 }
+
+float* tc_block_rounded_dv(void* scratch, int B, int din, int dout) { return carve(scratch, B, din, dout).dh_r; }
 
 void split_params_tf32(const float* src, size_t n, float* hi, float* lo, cudaStream_t st) {
   int blocks = (int)((n + 255) / 256);

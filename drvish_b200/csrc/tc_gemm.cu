@@ -416,7 +416,7 @@ int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs,
   }
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    launch_k(kern, grid, NTHREADS, SMEM_BYTES, st, ta[0], tb[0], ta[1], tb[1], ta[2], tb[2], n_pairs, outp, out_ld, M, N, K, n_tile,
+    launch_k_plain(kern, grid, NTHREADS, SMEM_BYTES, st, ta[0], tb[0], ta[1], tb[1], ta[2], tb[2], n_pairs, outp, out_ld, M, N, K, n_tile,
                                              splits, force_atomic, kbias, part_stride, g_mn_lbo, g_mn_sbo, g_mn_kstep);
   };
   if (mt_sel == 1) {
