@@ -50,12 +50,41 @@ __global__ void __launch_bounds__(256) k_dr_means(const float* __restrict__ u, c
   __syncthreads();
   const float bi = bias[slot];
   bool bad = false;
-  for (int b = threadIdx.x; b < s.B; b += blockDim.x) {
-    int64_t lab = labels[b];
-    if (lab < 0 || lab >= s.K) { bad = true; continue; }
-    float r = sigmoidf_(u[(size_t)b * s.D + i] + bi);
-    atomicAdd(&acc[lab], r);
-    atomicAdd(&cnt[lab], 1.f);
+  if (s.K <= 16) {
+    // few classes: per-thread sums selected by label (no dynamic indexing), one warp reduction per
+    // class, one shared-memory atomic per warp and class - instead of 256 threads contending for K words
+    float ra[16], ca[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) ra[k] = ca[k] = 0.f;
+    for (int b = threadIdx.x; b < s.B; b += blockDim.x) {
+      const int64_t lab = labels[b];
+      if (lab < 0 || lab >= s.K) { bad = true; continue; }
+      const float r = sigmoidf_(u[(size_t)b * s.D + i] + bi);
+      const int li = (int)lab;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        ra[k] += li == k ? r : 0.f;
+        ca[k] += li == k ? 1.f : 0.f;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      if (k < s.K) {
+        const float tr = warp_sum(ra[k]), tc = warp_sum(ca[k]);
+        if (threadIdx.x % 32 == 0) {
+          atomicAdd(&acc[k], tr);
+          atomicAdd(&cnt[k], tc);
+        }
+      }
+    }
+  } else {
+    for (int b = threadIdx.x; b < s.B; b += blockDim.x) {
+      int64_t lab = labels[b];
+      if (lab < 0 || lab >= s.K) { bad = true; continue; }
+      float r = sigmoidf_(u[(size_t)b * s.D + i] + bi);
+      atomicAdd(&acc[lab], r);
+      atomicAdd(&cnt[lab], 1.f);
+    }
   }
   if (bad) atomicOr(status, DRV_STATUS_BAD_LABEL);
   __syncthreads();

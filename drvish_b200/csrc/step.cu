@@ -490,7 +490,8 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
   };
   // forward-only calls and stream-less calls run it here; in training it is deferred to the decoder
   // backward, where it overlaps the bandwidth-bound GEMMs instead of the latency-bound trunk
-  const bool dr_late = bwd && side != nullptr && dec_tc;
+  static const bool dr_late_env = getenv("DRV_DR_LATE") != nullptr;
+  const bool dr_late = dr_late_env && bwd && side != nullptr && dec_tc;
   if (!dr_late) dose_response_head();
 
   // ---- model: decoder trunk (nbvae.py:70 -> modules.py:93) ------------------------------------

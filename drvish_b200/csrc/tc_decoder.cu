@@ -34,8 +34,13 @@ constexpr int B_BYTES = 128 * BK * 4;      // 16 KB (128 weight rows)
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int X_BYTES = 2 * BM * 32 * 4;   // one count tile: two 128x32 boxes = 32 KB
 constexpr int N_EPI_WARPS = 16;
-constexpr int NTHREADS = (N_EPI_WARPS + 2) * 32;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * X_BYTES + 1024 + 512;
+constexpr int NTHREADS = (N_EPI_WARPS + 3) * 32;  // + TMA producer, MMA issuer, TMA store warp
+// phase 2 (training): 3 operand stages + 2 count tiles (overwritten in place by ds') + 2 drho tiles
+constexpr int SMEM_BYTES = 3 * STAGE_BYTES + 4 * X_BYTES + 1024 + 512;
+// phases 1, 2 (forward only) and 3 need less: leave room for the small kernels of the other stream
+constexpr int SMEM_SMALL = STAGES * STAGE_BYTES + 2 * X_BYTES + 1024 + 512;
+static_assert(SMEM_SMALL >= 2 * STAGE_BYTES + 4 * X_BYTES + 1024 + 512, "phase 3 layout");
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
 constexpr int TMEM_COLS = 256;
 
 // tcgen05 kind::tf32 TRUNCATES the low 13 mantissa bits of its fp32 operands, which biases every
@@ -104,22 +109,31 @@ __device__ __forceinline__ float combine_lse(const DecParams& p, int ct, int b) 
 template <int PHASE, bool WITH_A>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtensorMap tmW,
-      const __grid_constant__ CUtensorMap tmX, DecParams p) {
+      const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD,
+      const __grid_constant__ CUtensorMap tmR, DecParams p) {
   pdl_prologue();
-  // phase 3 stages a 128 x 128 ds' tile (4 boxes, 64 KB) instead of the 128 x 64 count tile and
-  // makes room for it with a 2-deep operand ring (its MMA is far from critical)
-  constexpr int NST = PHASE == 3 ? 2 : STAGES;
+  // The gradient tiles leave through shared memory and TMA stores (TSTORE): a warp-wide 128-bit store
+  // from the TMEM register layout touches 32 different rows - 32 half-filled sectors per instruction -
+  // and phase 2 turned out to be bound by exactly those stores (a third store stream cost +50%).
+  //   phase 2 (training): ds' overwrites the count tile in place, drho has its own two buffers; the
+  //     operand ring shrinks to 3 stages to make room (the MMA is far from critical here)
+  //   phase 3: stages a 128 x 128 ds' tile (4 boxes, 64 KB), 2-deep operand ring, ds written in place
+  constexpr bool TSTORE = (PHASE == 2 && WITH_A) || PHASE == 3;
+  constexpr int NST = PHASE == 3 ? 2 : (TSTORE ? 3 : STAGES);
   constexpr int XB = PHASE == 3 ? 2 * X_BYTES : X_BYTES;
+  constexpr int RB = (PHASE == 2 && WITH_A) ? X_BYTES : 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* xbuf = smem + NST * STAGE_BYTES;
-  uint64_t* full = (uint64_t*)(xbuf + 2 * XB);
+  uint8_t* rbuf = xbuf + 2 * XB;  // [2][RB]
+  uint64_t* full = (uint64_t*)(rbuf + 2 * RB);
   uint64_t* empty = full + NST;
   uint64_t* acc_full = empty + NST;       // [2]
   uint64_t* acc_empty = acc_full + 2;     // [2]
   uint64_t* x_full = acc_empty + 2;       // [2]
   uint64_t* x_empty = x_full + 2;         // [2]
-  uint32_t* tmem_slot = (uint32_t*)(x_empty + 2);
+  uint64_t* o_full = x_empty + 2;         // [2] output tile complete in shared memory (TSTORE)
+  uint32_t* tmem_slot = (uint32_t*)(o_full + 2);
   float* lgtab = (float*)(tmem_slot + 4);
   load_lgamma_table(lgtab, threadIdx.x);
 
@@ -144,7 +158,8 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], N_EPI_WARPS);
       mbar_init(&x_full[s], 1);
-      mbar_init(&x_empty[s], N_EPI_WARPS);
+      mbar_init(&x_empty[s], TSTORE ? 1 : N_EPI_WARPS);  // TSTORE: released by the store warp
+      mbar_init(&o_full[s], N_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -204,6 +219,28 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
         }
         umma_commit(&acc_full[as]);
       }
+    }
+  } else if (warp == N_EPI_WARPS + 2) {
+    // ===== TMA store warp: finished gradient tiles, shared memory -> global =====
+    if (TSTORE && lane == 0) {
+      for (int t = t0, it = 0; t < t1; ++t, ++it) {
+        const int ct = t / n_gt, gt = t % n_gt;
+        const int b0 = ct * BM, g0 = gt * TN;
+        const int xs = it & 1, ph = (it >> 1) & 1;
+        mbar_wait(&o_full[xs], ph);  // the writers fenced their generic-proxy stores (fence.proxy.async)
+#pragma unroll
+        for (int j = 0; j < XB / (BM * 128); ++j)
+          tma_store_2d(&tmD, xbuf + xs * XB + j * (BM * 128), g0 + 32 * j, b0);
+        if (PHASE == 2) {
+#pragma unroll
+          for (int j = 0; j < RB / (BM * 128); ++j)
+            tma_store_2d(&tmR, rbuf + xs * RB + j * (BM * 128), g0 + 32 * j, b0);
+        }
+        tma_store_commit();
+        tma_store_wait_read0();      // shared memory may be refilled; the global writes complete asynchronously
+        mbar_arrive(&x_empty[xs]);
+      }
+      tma_store_wait_all();
     }
   } else {
     // ===== epilogue warps =====
@@ -283,12 +320,11 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
         // This warp owns 32 genes of the 128-gene (scale half) tile, in 8 groups of 4 columns.
         const int gbase = g0 + cg * 32;
         const float cA = p.c * asum_b;
-        float* drow = p.dlogits + (size_t)b * 2 * p.G + gbase;
         // ds' tile: TMA-staged a tile ahead by the producer warp (box cg = this warp's 32 genes,
         // row r, 16-byte chunk g4 XOR-swizzled with r % 8)
         const int xs = it & 1, xph = (it >> 1) & 1;
         mbar_wait(&x_full[xs], xph);
-        const uint8_t* drow_s = xbuf + xs * XB + cg * (BM * 128) + r * 128;
+        uint8_t* drow_s = xbuf + xs * XB + cg * (BM * 128) + r * 128;
         float sv_n[4];
         tmem_ld4(tbase + cg * 32, sv_n);
         tmem_ld_wait();
@@ -300,7 +336,6 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
           if (g4 + 1 < 8) tmem_ld4(tbase + cg * 32 + (g4 + 1) * 4, sv_n);  // next group, in flight during this one
           const int gq = gbase + 4 * g4;
           const bool vec = gq + 4 <= p.G;
-          float* d0 = drow + 4 * g4;
           if (vec) {
             const float4 f = __ldg(reinterpret_cast<const float4*>(p.bias + gq));
             bs[0] = f.x; bs[1] = f.y; bs[2] = f.z; bs[3] = f.w;
@@ -316,23 +351,18 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
             const float pr = ex2_approx((sv[v] + bs[v] - lse_b) * 1.4426950408889634f);
             ds[v] = ok ? rna_tf32(__fmaf_rn(cA, pr, dsp[v])) : 0.f;
           }
-          if (row_ok) {
-            if (vec) *reinterpret_cast<float4*>(d0) = make_float4(ds[0], ds[1], ds[2], ds[3]);
-            else {
-#pragma unroll
-              for (int v = 0; v < 4; ++v)
-                if (gq + v < p.G) d0[v] = ds[v];
-            }
-          }
+          // in place over the staged ds' chunk; the store warp ships the tile (TMA clips rows >= B, genes >= G)
+          *reinterpret_cast<float4*>(drow_s + ((g4 ^ (r & 7)) * 16)) = make_float4(ds[0], ds[1], ds[2], ds[3]);
           const int col = butterfly4(ds, lane);
           if (col >= 0 && gq + col < p.G) atomicAdd(&p.db[gq + col], ds[0]);
           tmem_ld_wait();
         }
+        fence_proxy_async();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(&acc_empty[as]);
-          mbar_arrive(&x_empty[xs]);
+          mbar_arrive(&o_full[xs]);
         }
       } else {
         // phase 2: this warp owns 16 genes of the 64-gene tile, processed as a ROLLED loop over 4
@@ -344,7 +374,8 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
         mbar_wait(&x_full[xs], xph);
         const int gbase = g0 + cg * 16;
         const float lml = lib_b - lse_b;
-        const uint8_t* xrow = xbuf + xs * XB + (cg >> 1) * (BM * 128) + r * 128;
+        uint8_t* xrow = xbuf + xs * XB + (cg >> 1) * (BM * 128) + r * 128;
+        uint8_t* rrow = rbuf + xs * RB + (cg >> 1) * (BM * 128) + r * 128;
         const bool full_cols = gbase + 16 <= p.G;
         float sv_n[4], rv_n[4];
         tmem_ld4(tbase + cg * 16, sv_n);
@@ -361,9 +392,9 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
             tmem_ld4(tbase + cg * 16 + gn * 4, sv_n);
             tmem_ld4(tbase + 64 + cg * 16 + gn * 4, rv_n);
           }
+          // count tile: box (cg/2), row r, 16-byte chunk (cg%2)*4 + g4, XOR-swizzled with r%8
+          const int chunk = ((cg & 1) * 4 + g4) ^ (r & 7);
           {
-            // count tile: box (cg/2), row r, 16-byte chunk (cg%2)*4 + g4, XOR-swizzled with r%8
-            const int chunk = ((cg & 1) * 4 + g4) ^ (r & 7);
             const float4 f = *reinterpret_cast<const float4*>(xrow + chunk * 16);
             xv[0] = f.x; xv[1] = f.y; xv[2] = f.z; xv[3] = f.w;
           }
@@ -406,29 +437,22 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
               dsp[v] = ok[v] ? -p.c * e[v].a : 0.f;
               dr[v] = ok[v] ? rna_tf32(-p.c * e[v].drho) : 0.f;  // tf32 MMA operand of dW / dAct
             }
-            if (row_ok) {
-              float* d0 = p.dlogits + (size_t)b * 2 * p.G + gq;
-              float* d1 = d0 + p.G;
-              if (gq + 4 <= p.G) {
-                *reinterpret_cast<float4*>(d0) = make_float4(dsp[0], dsp[1], dsp[2], dsp[3]);
-                *reinterpret_cast<float4*>(d1) = make_float4(dr[0], dr[1], dr[2], dr[3]);
-              } else {
-#pragma unroll
-                for (int v = 0; v < 4; ++v)
-                  if (gq + v < p.G) { d0[v] = dsp[v]; d1[v] = dr[v]; }
-              }
-            }
+            // ds' overwrites the counts it was computed from (same swizzled chunk), drho goes to its own
+            // tile; the store warp ships both (TMA clips rows >= B and genes >= G)
+            *reinterpret_cast<float4*>(xrow + chunk * 16) = make_float4(dsp[0], dsp[1], dsp[2], dsp[3]);
+            *reinterpret_cast<float4*>(rrow + chunk * 16) = make_float4(dr[0], dr[1], dr[2], dr[3]);
             // bias gradient of the log_r half: column sums over the 32 rows of this warp
             const int col = butterfly4(dr, lane);
             if (col >= 0 && gq + col < p.G) atomicAdd(&p.db[p.G + gq + col], dr[0]);
           }
           tmem_ld_wait();
         }
+        if (TSTORE) fence_proxy_async();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(&acc_empty[as]);
-          mbar_arrive(&x_empty[xs]);
+          mbar_arrive(TSTORE ? &o_full[xs] : &x_empty[xs]);
         }
       }
     }
@@ -537,12 +561,14 @@ bool make_maps(const TcDecoderArgs& a, const Scratch& s, CUtensorMap* act, CUten
   return true;
 }
 
+// d / r: tensor maps of the scale / log_r halves of dlogits for the TMA stores (any valid map where unused)
 template <class K>
 void launch_dec(K kern, int n_tiles, const CUtensorMap& act, const CUtensorMap& w, const CUtensorMap& x,
-                const DecParams& p, cudaStream_t st) {
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+                const CUtensorMap& d, const CUtensorMap& r, const DecParams& p, cudaStream_t st,
+                int smem_bytes = SMEM_SMALL) {
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   int grid = n_tiles < sm_count() ? n_tiles : sm_count();
-  launch_k(kern, grid, NTHREADS, SMEM_BYTES, st, act, w, x, p);
+  launch_k_plain(kern, grid, NTHREADS, smem_bytes, st, act, w, x, d, r, p);
   note_launch();
 }
 
@@ -586,13 +612,23 @@ void tc_decoder_forward(const TcDecoderArgs& a, cudaStream_t st) {
   const int n_gt1 = (a.G + 127) / 128;
   set_lse_layout(p, n_ct, n_gt1);
   drv_internal_kmark(0, 0, st);
-  launch_dec(k_dec<1, false>, n_ct * n_gt1, tAct, tW1, tX, p, st);
+  launch_dec(k_dec<1, false>, n_ct * n_gt1, tAct, tW1, tX, tX, tX, p, st);
   drv_internal_kmark(0, 1, st);
   // phase 2: NB log-likelihood row sums (ll / asum / db were zeroed at the start of the step)
   const int n_gt = (a.G + 63) / 64;
   drv_internal_kmark(1, 0, st);
-  if (a.bwd) launch_dec(k_dec<2, true>, n_ct * n_gt, tAct, tW3, tX, p, st);
-  else launch_dec(k_dec<2, false>, n_ct * n_gt, tAct, tW3, tX, p, st);
+  if (a.bwd) {
+    // scale / log_r halves of dlogits: [B][G] each, row stride 2G
+    CUtensorMap tD, tR;
+    if (!tmap_2d(&tD, a.dlogits, a.B, a.G, 2 * (uint64_t)a.G, BM, 32) ||
+        !tmap_2d(&tR, a.dlogits + a.G, a.B, a.G, 2 * (uint64_t)a.G, BM, 32)) {
+      if (g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
+      return;
+    }
+    launch_dec(k_dec<2, true>, n_ct * n_gt, tAct, tW3, tX, tD, tR, p, st, SMEM_BYTES);
+  } else {
+    launch_dec(k_dec<2, false>, n_ct * n_gt, tAct, tW3, tX, tX, tX, p, st);
+  }
   drv_internal_kmark(1, 1, st);
   launch_k(k_loss_from_ll, 8, 256, 0, st, a.ll, a.B, a.c, a.out);
   note_launch();
@@ -616,7 +652,7 @@ void tc_decoder_backward(const TcDecoderArgs& a, cudaStream_t st) {
     return;
   }
   drv_internal_kmark(2, 0, st);
-  launch_dec(k_dec<3, true>, n_ct * n_gt1, tAct, tW1, tD, p, st);
+  launch_dec(k_dec<3, true>, n_ct * n_gt1, tAct, tW1, tD, tD, tD, p, st);
   drv_internal_kmark(2, 1, st);
   // dW[j][i] = sum_b dlogits[b][j] act[b][i]   (both operands MN-major, K = cells)
   if (a.side) a.side->mark(st);
