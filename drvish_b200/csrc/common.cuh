@@ -205,16 +205,41 @@ __device__ __forceinline__ float digamma_pos(float y) {
   return acc + logf(y) - 0.5f * inv - series;
 }
 
-// lgamma(1 + x) for a count x >= 0.  Integer counts below 32 come from a table.
-static __constant__ float c_lgamma1p[32] = {
-    0.f, 0.f, 0.69314718055994531f, 1.79175946922805500f, 3.17805383034794562f, 4.78749174278204599f,
-    6.57925121201010100f, 8.52516136106541430f, 10.6046029027452502f, 12.8018274800814696f,
-    15.1044125730755153f, 17.5023078458738858f, 19.9872144956618861f, 22.5521638531234229f,
-    25.1912211827386815f, 27.8992713838408916f, 30.6718601060806728f, 33.5050734501368889f,
-    36.3954452080330536f, 39.3398841871994940f, 42.3356164607534850f, 45.3801388984769080f,
-    48.4711813518352239f, 51.6066755677643736f, 54.7847293981123192f, 58.0036052229805199f,
-    61.2617017610020020f, 64.5575386270063311f, 67.8897431371815350f, 71.2570389671680090f,
-    74.6582363488301644f, 78.0922235533153106f};
+// lgamma(1 + x) for a count x >= 0.  Integer counts below LGTAB_N come from a table.
+constexpr int LGTAB_N = 128;
+static __constant__ float c_lgamma1p[LGTAB_N] = {
+    0.f, 0.f, 0.69314718055994495f, 1.7917594692280554f,
+    3.1780538303479449f, 4.7874917427820467f, 6.5792512120101021f, 8.5251613610654147f,
+    10.604602902745249f, 12.801827480081467f, 15.104412573075514f, 17.502307845873887f,
+    19.987214495661885f, 22.552163853123421f, 25.191221182738683f, 27.89927138384089f,
+    30.671860106080672f, 33.505073450136891f, 36.395445208033053f, 39.339884187199495f,
+    42.335616460753485f, 45.380138898476908f, 48.47118135183522f, 51.606675567764377f,
+    54.784729398112319f, 58.003605222980518f, 61.261701761002008f, 64.557538627006338f,
+    67.889743137181526f, 71.257038967168f, 74.658236348830172f, 78.092223553315307f,
+    81.557959456115029f, 85.054467017581516f, 88.580827542197682f, 92.136175603687093f,
+    95.719694542143202f, 99.330612454787428f, 102.96819861451381f, 106.63176026064346f,
+    110.32063971475738f, 114.03421178146169f, 117.77188139974507f, 121.53308151543864f,
+    125.3172711493569f, 129.12393363912722f, 132.95257503561632f, 136.80272263732635f,
+    140.67392364823425f, 144.5657439463449f, 148.47776695177305f, 152.40959258449732f,
+    156.3608363030788f, 160.3311282166309f, 164.32011226319514f, 168.32744544842765f,
+    172.35279713916282f, 176.39584840699737f, 180.45629141754375f, 184.53382886144948f,
+    188.62817342367163f, 192.7390472878449f, 196.86618167288998f, 201.00931639928152f,
+    205.16819948264123f, 209.34258675253685f, 213.53224149456327f, 217.73693411395419f,
+    221.95644181913036f, 226.1905483237276f, 230.43904356577693f, 234.70172344281826f,
+    238.97838956183432f, 243.26884900298276f, 247.57291409618691f, 251.89040220972316f,
+    256.22113555000954f, 260.56494097186322f, 264.92164979855283f, 269.29109765101981f,
+    273.67312428569369f, 278.06757344036612f, 282.47429268763034f, 286.89313329542699f,
+    291.32395009427034f, 295.7666013507606f, 300.22094864701415f, 304.68685676566867f,
+    309.16419358014696f, 313.65282994987905f, 318.15263962020936f, 322.66349912672626f,
+    327.1852877037752f, 331.71788719692847f, 336.26118197919851f, 340.81505887079896f,
+    345.37940706226686f, 349.95411804077025f, 354.53908551944085f, 359.1342053695754f,
+    363.73937555556347f, 368.35449607240474f, 372.97946888568902f, 377.61419787391861f,
+    382.25858877306007f, 386.91254912321756f, 391.57598821732967f, 396.24881705179149f,
+    400.93094827891576f, 405.62229616114485f, 410.32277652693728f, 415.03230672824964f,
+    419.75080559954478f, 424.47819341825709f, 429.21439186665162f, 433.95932399501481f,
+    438.71291418612117f, 443.47508812091894f, 448.24577274538456f, 453.02489623849618f,
+    457.81238798127811f, 462.60817852687495f, 467.41219957160814f, 472.22438392698058f,
+    477.04466549258569f, 481.87297922988796f, 486.70926113683942f, 491.55344822329801f};
 
 // Result of one (cell, gene) element of the NB block.
 struct NbElem {
@@ -223,6 +248,12 @@ struct NbElem {
   float drho;  // dLL/d rho = e^rho (log sigmoid(-ell) + psi(r+x) - psi(r)) - a
 };
 
+// MUFU.RCP alone: __fdividef(1, y) wraps it in range fix-ups (6 instructions) that the NB terms never need
+__device__ __forceinline__ float rcp_approx(float v) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
 __device__ __forceinline__ float ex2_approx(float v) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
@@ -234,13 +265,13 @@ __device__ __forceinline__ float lg2_approx(float v) {
   return r;
 }
 
-// Copies log(x!) for x < 32 into a 32-float shared-memory table (one bank per entry: divergent
-// count lookups are conflict-free, unlike a constant-memory lookup).
+// Copies log(x!) for x < LGTAB_N into a shared-memory table (divergent count lookups are cheap there,
+// unlike a constant-memory lookup).  Needs >= LGTAB_N threads.
 __device__ __forceinline__ void load_lgamma_table(float* tab_smem, int tid) {
-  if (tid < 32) tab_smem[tid] = c_lgamma1p[tid];
+  if (tid < LGTAB_N) tab_smem[tid] = c_lgamma1p[tid];
 }
 
-// Rare path (non-integer count, count >= 32 or r >= 1e4): generic lgamma / digamma.  Kept out of
+// Rare path (non-integer count, count >= LGTAB_N or r >= 1e4): generic lgamma / digamma.  Kept out of
 // line so that the hot epilogue loop stays small enough for the instruction cache.
 static __device__ __noinline__ float2 nb_count_slow(float r, float x, bool bwd) {
   float2 o;
@@ -275,23 +306,23 @@ __device__ __forceinline__ void nb_elems(const float (&lsl)[NV], const float (&r
     const float t = 1.f + e;
     const float sp = __fmaf_rn(lg2_approx(t), LN2, fmaxf(ell, 0.f));  // softplus(ell)
     const float xr = x[v] + MAGIC;                                     // integer test without F2I/I2F
-    const bool fast = ((xr - MAGIC) == x[v]) && (x[v] < 32.f) && (r < 1.0e8f);
+    const bool fast = ((xr - MAGIC) == x[v]) && (x[v] < (float)LGTAB_N) && (r < 1.0e8f);
     // shifted Stirling at y0 = r + 4 and y1 = r + x + 4
     const float rx = r + x[v];
     const float y0 = r + 4.f, y1 = rx + 4.f;
     const float u0 = r * (r + 3.f), w0 = u0 + 2.f, q0 = u0 * w0;      // r(r+1)(r+2)(r+3)
     const float u1 = rx * (rx + 3.f), w1 = u1 + 2.f, q1 = u1 * w1;
-    const float i0 = __fdividef(1.f, y0), i1 = __fdividef(1.f, y1);
+    const float i0 = rcp_approx(y0), i1 = rcp_approx(y1);
     const float l0 = lg2_approx(y0) * LN2, l1 = lg2_approx(y1) * LN2;
     const float i0s = i0 * i0, i1s = i1 * i1;
-    const float iq0 = __fdividef(1.f, q0);
+    const float iq0 = rcp_approx(q0);
     const float c0 = i0 * __fmaf_rn(i0s, -2.7777777778e-3f, 8.3333333333e-2f);
     const float c1 = i1 * __fmaf_rn(i1s, -2.7777777778e-3f, 8.3333333333e-2f);
     float lgd = __fmaf_rn(y1 - 0.5f, l1, -(y0 - 0.5f) * l0) - x[v] + (c1 - c0) - lg2_approx(q1 * iq0) * LN2;
-    float cnt = lgd - lgtab[__float_as_int(xr) & 31];
+    float cnt = lgd - lgtab[__float_as_int(xr) & (LGTAB_N - 1)];
     float psd = 0.f;
     if (BWD) {
-      const float iq1 = __fdividef(1.f, q1);
+      const float iq1 = rcp_approx(q1);
       const float g0 = l0 - 0.5f * i0 - i0s * __fmaf_rn(i0s, -8.3333333333e-3f, 8.3333333333e-2f);
       const float g1 = l1 - 0.5f * i1 - i1s * __fmaf_rn(i1s, -8.3333333333e-3f, 8.3333333333e-2f);
       const float qd0 = (u0 + w0) * __fmaf_rn(2.f, r, 3.f);          // Q'(r)
@@ -309,7 +340,7 @@ __device__ __forceinline__ void nb_elems(const float (&lsl)[NV], const float (&r
     }
     o[v].ll = __fmaf_rn(x[v], ell, cnt) - rx * sp;
     if (BWD) {
-      const float inv = __fdividef(1.f, t);
+      const float inv = rcp_approx(t);
       const float sig = ell >= 0.f ? inv : e * inv;
       o[v].a = x[v] - rx * sig;
       o[v].drho = rexp * (psd - sp) - o[v].a;

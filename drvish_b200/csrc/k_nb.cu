@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(NBT) k_nb_rows(float* __restrict__ logits, con
                                                  float* __restrict__ asum_out, drv_step_out* out) {
   pdl_prologue();
   __shared__ float sh[NBT / 32];
-  __shared__ float lgtab[32];
+  __shared__ float lgtab[LGTAB_N];
   load_lgamma_table(lgtab, threadIdx.x);
   __syncthreads();
   const int b = blockIdx.x;

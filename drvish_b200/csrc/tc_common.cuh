@@ -61,6 +61,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// for the service warps of an epilogue-bound kernel: a spinning try_wait loop issues an instruction
+// every few cycles and takes issue slots from the warps doing the work
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned ns) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
+
 // TMA loads (tile mode), completion on an mbarrier
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(

@@ -14,6 +14,8 @@
 // Persistent CTAs (one per SM), 18 warps: 16 epilogue warps (4 per TMEM lane quarter, each a
 // 16-gene column slice), 1 TMA producer warp, 1 MMA-issuer warp.  Tiles: 128 cells x 64 genes
 // (x 2 halves = 128 accumulator columns), double-buffered in TMEM (256 columns).
+#include <type_traits>
+
 #include "kernels.cuh"
 #include "tc.cuh"
 #include "tc_common.cuh"
@@ -36,10 +38,10 @@ constexpr int X_BYTES = 2 * BM * 32 * 4;   // one count tile: two 128x32 boxes =
 constexpr int N_EPI_WARPS = 16;
 constexpr int NTHREADS = (N_EPI_WARPS + 3) * 32;  // + TMA producer, MMA issuer, TMA store warp
 // phase 2 (training): 3 operand stages + 2 count tiles (overwritten in place by ds') + 2 drho tiles
-constexpr int SMEM_BYTES = 3 * STAGE_BYTES + 4 * X_BYTES + 1024 + 512;
+constexpr int SMEM_BYTES = 3 * STAGE_BYTES + 4 * X_BYTES + 1024 + 1024;
 // phases 1, 2 (forward only) and 3 need less: leave room for the small kernels of the other stream
-constexpr int SMEM_SMALL = STAGES * STAGE_BYTES + 2 * X_BYTES + 1024 + 512;
-static_assert(SMEM_SMALL >= 2 * STAGE_BYTES + 4 * X_BYTES + 1024 + 512, "phase 3 layout");
+constexpr int SMEM_SMALL = STAGES * STAGE_BYTES + 2 * X_BYTES + 1024 + 1024;
+static_assert(SMEM_SMALL >= 2 * STAGE_BYTES + 4 * X_BYTES + 1024 + 1024, "phase 3 layout");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
 constexpr int TMEM_COLS = 256;
 
@@ -169,6 +171,11 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // phase 2 is bound by its epilogue warps: the service warps back off between barrier polls
+  auto swait = [](uint64_t* bar, uint32_t parity) {
+    if (PHASE == 2) mbar_wait_relaxed(bar, parity, 100);
+    else mbar_wait(bar, parity);
+  };
   if (warp == N_EPI_WARPS) {
     // ===== TMA producer =====
     if (lane == 0) {
@@ -178,7 +185,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
         const int b0 = ct * BM, g0 = gt * TN;
         if (PHASE != 1) {
           const int xs = it & 1, xph = (it >> 1) & 1;
-          mbar_wait(&x_empty[xs], xph ^ 1);
+          swait(&x_empty[xs], xph ^ 1);
           mbar_expect_tx(&x_full[xs], XB);
 #pragma unroll
           for (int j = 0; j < XB / (BM * 128); ++j)
@@ -186,7 +193,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
         }
         for (int kb = 0; kb < nkb; ++kb, ++kit) {
           const int s = kit % NST, ph = (kit / NST) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
+          swait(&empty[s], ph ^ 1);
           uint8_t* sa = smem + s * STAGE_BYTES;
           mbar_expect_tx(&full[s], STAGE_BYTES);
           tma_load_2d(sa, &tmAct, &full[s], kb * BK, b0);
@@ -202,12 +209,12 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
       int kit = 0;
       for (int t = t0, it = 0; t < t1; ++t, ++it) {
         const int as = it & 1, aph = (it >> 1) & 1;
-        mbar_wait(&acc_empty[as], aph ^ 1);
+        swait(&acc_empty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * 128);
         for (int kb = 0; kb < nkb; ++kb, ++kit) {
           const int s = kit % NST, ph = (kit / NST) & 1;
-          mbar_wait(&full[s], ph);
+          swait(&full[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
@@ -227,7 +234,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
         const int ct = t / n_gt, gt = t % n_gt;
         const int b0 = ct * BM, g0 = gt * TN;
         const int xs = it & 1, ph = (it >> 1) & 1;
-        mbar_wait(&o_full[xs], ph);  // the writers fenced their generic-proxy stores (fence.proxy.async)
+        swait(&o_full[xs], ph);  // the writers fenced their generic-proxy stores (fence.proxy.async)
 #pragma unroll
         for (int j = 0; j < XB / (BM * 128); ++j)
           tma_store_2d(&tmD, xbuf + xs * XB + j * (BM * 128), g0 + 32 * j, b0);
@@ -381,6 +388,10 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
         tmem_ld4(tbase + cg * 16, sv_n);
         tmem_ld4(tbase + 64 + cg * 16, rv_n);
         tmem_ld_wait();
+        // interior tiles (all 128 cells and 64 genes valid) take a copy of the loop without the validity
+        // selects; TMA zero-fills / clips the edges, so only the edge tiles need masking for the sums
+        auto tile_loop = [&](auto masked_tag) {
+        constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll 1
         for (int g4 = 0; g4 < 4; ++g4) {
           float sv[4], rv[4], xv[4], bs[4], br[4];
@@ -399,7 +410,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
             xv[0] = f.x; xv[1] = f.y; xv[2] = f.z; xv[3] = f.w;
           }
           const int gq = gbase + 4 * g4;
-          if (full_cols) {  // warp-uniform addresses -> broadcast loads
+          if (!MASKED || full_cols) {  // warp-uniform addresses -> broadcast loads
             const float4 f = __ldg(reinterpret_cast<const float4*>(p.bias + gq));
             const float4 h2 = __ldg(reinterpret_cast<const float4*>(p.bias + p.G + gq));
             bs[0] = f.x; bs[1] = f.y; bs[2] = f.z; bs[3] = f.w;
@@ -416,7 +427,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
           bool ok[4];
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
-            ok[v] = row_ok && (gq + v < p.G);
+            ok[v] = !MASKED || (row_ok && (gq + v < p.G));
             a_lsl[v] = ok[v] ? lml + sv[v] + bs[v] : 0.f;
             a_rho[v] = ok[v] ? rv[v] + br[v] : 0.f;
             a_x[v] = ok[v] ? xv[v] : 0.f;
@@ -443,10 +454,13 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
             *reinterpret_cast<float4*>(rrow + chunk * 16) = make_float4(dr[0], dr[1], dr[2], dr[3]);
             // bias gradient of the log_r half: column sums over the 32 rows of this warp
             const int col = butterfly4(dr, lane);
-            if (col >= 0 && gq + col < p.G) atomicAdd(&p.db[p.G + gq + col], dr[0]);
+            if (col >= 0 && (!MASKED || gq + col < p.G)) atomicAdd(&p.db[p.G + gq + col], dr[0]);
           }
           tmem_ld_wait();
         }
+        };
+        if (ct * BM + BM <= p.B && g0 + TN <= p.G) tile_loop(std::false_type{});
+        else tile_loop(std::true_type{});
         if (TSTORE) fence_proxy_async();
         tc_fence_before();
         __syncwarp();
