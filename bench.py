@@ -244,7 +244,7 @@ def run_native(args, cfg):
             device_step(i)
     for i in range(args.warmup):
         device_step(i)
-    launches_per_step = rt.last_launches + (5 if cfg["drugs"] else 2)  # + noise fills
+    launches_per_step = rt.last_launches + 1  # + the noise draw (one launch)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()

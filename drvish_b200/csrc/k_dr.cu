@@ -56,15 +56,27 @@ __global__ void __launch_bounds__(256) k_dr_means(const float* __restrict__ u, c
     float ra[16], ca[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) ra[k] = ca[k] = 0.f;
-    for (int b = threadIdx.x; b < s.B; b += blockDim.x) {
-      const int64_t lab = labels[b];
-      if (lab < 0 || lab >= s.K) { bad = true; continue; }
-      const float r = sigmoidf_(u[(size_t)b * s.D + i] + bi);
-      const int li = (int)lab;
+    for (int b0 = threadIdx.x; b0 < s.B; b0 += 4 * blockDim.x) {
+      // four cells per trip: the eight loads are issued before any of them is used
+      int64_t lab[4];
+      float uv[4];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        ra[k] += li == k ? r : 0.f;
-        ca[k] += li == k ? 1.f : 0.f;
+      for (int j = 0; j < 4; ++j) {
+        const int b = b0 + j * blockDim.x;
+        lab[j] = b < s.B ? labels[b] : 0;
+        uv[j] = b < s.B ? u[(size_t)b * s.D + i] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (b0 + j * (int)blockDim.x >= s.B) continue;
+        if (lab[j] < 0 || lab[j] >= s.K) { bad = true; continue; }
+        const float r = sigmoidf_(uv[j] + bi);
+        const int li = (int)lab[j];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          ra[k] += li == k ? r : 0.f;
+          ca[k] += li == k ? 1.f : 0.f;
+        }
       }
     }
 #pragma unroll

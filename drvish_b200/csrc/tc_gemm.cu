@@ -293,9 +293,18 @@ __global__ void __launch_bounds__(256) k_reduce_parts_stats(const float* __restr
       for (int m = r0 + ty; m < r1; m += 4) {
         float a[4] = {0.f, 0.f, 0.f, 0.f};
         const float* src = parts + (size_t)m * N + cq * 4;
-        for (int p = 0; p < n_parts; ++p) {
-          const float4 v = __ldcs(reinterpret_cast<const float4*>(src + (size_t)p * mn));
-          a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
+        // the slabs come from DRAM: keep 8 independent 16-byte loads in flight per thread (the kernel
+        // is latency-bound otherwise); the sums still run in part order
+        for (int p0 = 0; p0 < n_parts; p0 += 8) {
+          float4 v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            v[j] = (p0 + j < n_parts) ? __ldcs(reinterpret_cast<const float4*>(src + (size_t)(p0 + j) * mn))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (p0 + j < n_parts) { a[0] += v[j].x; a[1] += v[j].y; a[2] += v[j].z; a[3] += v[j].w; }
+          }
         }
         a[0] += bv.x; a[1] += bv.y; a[2] += bv.z; a[3] += bv.w;
         *reinterpret_cast<float4*>(C + (size_t)m * ldc + cq * 4) = make_float4(a[0], a[1], a[2], a[3]);
@@ -438,7 +447,7 @@ int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs,
 bool reduce_parts(const float* parts, int n_parts, int M, int N, const float* bias, float* C, int ldc, cudaStream_t st,
                   const ColStatsOut* stats) {
   if (stats && N % 4 == 0 && ldc % 4 == 0 && M > 1) {
-    int R = (M + 15) / 16;
+    int R = (M + 7) / 8;
     if (R > n_sm_tc() * 4) R = n_sm_tc() * 4;
     if (R < (M + 127) / 128) R = (M + 127) / 128;  // <= 32 rows per thread in the fp32 partial sums
     const int rows_per_cta = (M + R - 1) / R;

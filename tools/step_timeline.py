@@ -3,7 +3,7 @@ fn=sys.argv[1]
 with open(fn) as f: lines=[l for l in f if not l.startswith('==')]
 rows=[r for r in csv.DictReader(lines) if r.get('Metric Name')=='gpu__time_duration.sum']
 names=[r['Kernel Name'] for r in rows]
-idx=[i for i,n in enumerate(names) if 'k_finalize_status' in n]
+idx=[i for i,n in enumerate(names) if 'k_finalize_st' in n]
 a,b=idx[-2]+1, idx[-1]+1
 tot=0
 for r in rows[a:b]:
