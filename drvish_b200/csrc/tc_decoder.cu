@@ -305,16 +305,34 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
         if (lane == 0) mbar_arrive(&acc_empty[as]);
         const int gbase = g0 + cg * 32;
         float m = -INFINITY;
+        if (gbase + 32 <= p.G) {  // interior: vector bias loads (warp-uniform addresses), no bounds selects
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          v0[j] = (gbase + j < p.G) ? v0[j] + __ldg(&p.bias[min(gbase + j, p.G - 1)]) : -INFINITY;
-          v1[j] = (gbase + 16 + j < p.G) ? v1[j] + __ldg(&p.bias[min(gbase + 16 + j, p.G - 1)]) : -INFINITY;
-          m = fmaxf(m, fmaxf(v0[j], v1[j]));
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 f0 = __ldg(reinterpret_cast<const float4*>(p.bias + gbase + 4 * j4));
+            const float4 f1 = __ldg(reinterpret_cast<const float4*>(p.bias + gbase + 16 + 4 * j4));
+            v0[4 * j4] += f0.x; v0[4 * j4 + 1] += f0.y; v0[4 * j4 + 2] += f0.z; v0[4 * j4 + 3] += f0.w;
+            v1[4 * j4] += f1.x; v1[4 * j4 + 1] += f1.y; v1[4 * j4 + 2] += f1.z; v1[4 * j4 + 3] += f1.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) m = fmaxf(m, fmaxf(v0[j], v1[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            v0[j] = (gbase + j < p.G) ? v0[j] + __ldg(&p.bias[min(gbase + j, p.G - 1)]) : -INFINITY;
+            v1[j] = (gbase + 16 + j < p.G) ? v1[j] + __ldg(&p.bias[min(gbase + 16 + j, p.G - 1)]) : -INFINITY;
+            m = fmaxf(m, fmaxf(v0[j], v1[j]));
+          }
         }
         float s = 0.f;
         if (m > -INFINITY) {
+          const float L2E = 1.4426950408889634f, mm = m * L2E;  // exp(v - m) = 2^(v log2e - m log2e): one FFMA + MUFU
+          float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) s += __expf(v0[j] - m) + __expf(v1[j] - m);
+          for (int j = 0; j < 16; ++j) {
+            s0 += ex2_approx(__fmaf_rn(v0[j], L2E, -mm));
+            s1 += ex2_approx(__fmaf_rn(v1[j], L2E, -mm));
+          }
+          s = s0 + s1;
         }
         if (m > -INFINITY) {
           const float M = fmaxf(m_run, m);

@@ -22,6 +22,10 @@ CASES = {
     "drugs_ragged": dict(n_input=150, n_latent=7, layers=[64, 48], batch=96, drugs=3, doses=5, classes=3,
                          lam_scale=1.0, bias_scale=1.0),
     "mid": dict(n_input=1000, n_latent=10, layers=[128, 128], batch=512, drugs=0),
+    # tensor-core path with ragged edges: 3 cell tiles (the last one partial), a partial gene tile,
+    # hidden widths that are not powers of two, dose-response head on
+    "tc_ragged": dict(n_input=1100, n_latent=9, layers=[96, 160], batch=300, drugs=2, doses=3, classes=4,
+                      lam_scale=1.0, bias_scale=1.0),
 }
 
 
@@ -73,6 +77,24 @@ def test_step_matches_committed_golden(golden_dir, fixture, cfg):
     for k, v in g.items():
         if k.startswith("after.") and "running" in k:
             assert P.rel_err(sd[k[6:]].cpu(), torch.from_numpy(v)) <= 1e-5, k
+
+
+def test_heavy_tailed_counts_take_the_generic_lgamma_path():
+    """Counts far beyond the log-factorial table (x up to ~5000) go through the out-of-line lgamma /
+    digamma path of the NB kernels; zeros stay exact.  (Non-integer counts are rejected by the
+    reference's NegativeBinomial support check, so they are not a valid input.)"""
+    cfg = dict(n_input=512, n_latent=6, layers=[64, 64], batch=256, drugs=0)
+    case = P.make_case(cfg, data_seed=7)
+    g = torch.Generator().manual_seed(11)
+    x = case["x"].clone()
+    big = torch.rand(x.shape, generator=g) < 0.05
+    x[big] = torch.floor(torch.rand(int(big.sum()), generator=g) * 5000.0)
+    case["x"] = x
+    for force_simt in (True, False):
+        rep = P.compare_step(case, force_simt=force_simt)
+        print(_report(rep))
+        assert rep["loss_rel"] <= ELBO_TOL, _report(rep)
+        assert rep["worst_grad_rel"] <= GRAD_TOL, _report(rep)
 
 
 def test_evaluate_loss_is_forward_only():
