@@ -258,14 +258,28 @@ __global__ void k_finalize_status(drv_step_out* out) {
   if (isnan(out->loss)) out->status |= DRV_STATUS_NAN_LOSS;
 }
 
-__global__ void k_finalize_step(drv_step_out* out, const uint32_t* status, int64_t* c, int n) {
+// Last launch of a step: BatchNorm batch counters, the decoder's log-likelihood sum folded into the
+// loss (ll may be null: the CUDA-core NB kernel adds it itself), status word + NaN flag.
+__global__ void __launch_bounds__(256) k_finalize_step(drv_step_out* out, const uint32_t* status, int64_t* c, int n,
+                                                       const float* __restrict__ ll, int B, float scale) {
   pdl_prologue();
   const int i = threadIdx.x;
   if (c && i < n) c[i] += 1;
+  double t = 0.0;
+  if (ll)
+    for (int b = i; b < B; b += blockDim.x) t += (double)ll[b];
+  t = warp_sum(t);
+  __shared__ double sh[8];
+  if (i % 32 == 0) sh[i / 32] = t;
+  __syncthreads();
   if (i == 0) {
-    uint32_t s = *status;
-    if (isnan(out->loss)) s |= DRV_STATUS_NAN_LOSS;
-    out->status = s;
+    double s = 0.0;
+    for (int w = 0; w < (int)blockDim.x / 32; ++w) s += sh[w];
+    const double loss = out->loss - (double)scale * s;
+    out->loss = loss;
+    uint32_t st = *status;
+    if (isnan(loss)) st |= DRV_STATUS_NAN_LOSS;
+    out->status = st;
   }
 }
 
@@ -338,8 +352,9 @@ void bump_counters(int64_t* counters, int n, cudaStream_t st) {
   note_launch();
 }
 
-void finalize_step(drv_step_out* out, const uint32_t* status, int64_t* counters, int n, cudaStream_t st) {
-  launch_k(k_finalize_step, 1, 64, 0, st, out, status, counters, n);
+void finalize_step(drv_step_out* out, const uint32_t* status, int64_t* counters, int n, const float* ll, int B,
+                   float scale, cudaStream_t st) {
+  launch_k(k_finalize_step, 1, 256, 0, st, out, status, counters, n, ll, B, scale);
   note_launch();
 }
 

@@ -76,6 +76,8 @@ void dr_prior_factor(const float* w_prior, const float* b_prior, const float* ep
 
 void finalize_status(drv_step_out* out, cudaStream_t st);
 // counters[i] += 1 (BatchNorm num_batches_tracked; may be null), out->status = *status | NaN flag
-void finalize_step(drv_step_out* out, const uint32_t* status, int64_t* counters, int n, cudaStream_t st);
+// ... and out->loss -= scale * sum_b ll[b] (ll may be null)
+void finalize_step(drv_step_out* out, const uint32_t* status, int64_t* counters, int n, const float* ll, int B,
+                   float scale, cudaStream_t st);
 
 }  // namespace drv

@@ -548,7 +548,7 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
     if (stop_after_decoder) {
       // decoder / dose-response gradients and the loss are final: hand back to the caller
       if (side) side->join(st);
-      finalize_step(out, status, nullptr, 0, st);
+      finalize_step(out, status, nullptr, 0, use_tc ? c.at<float>(p.ll) : nullptr, B, hp->scale_factor, st);
       return finish();
     }
     // ---- encoder backward ----------------------------------------------------------------------
@@ -558,7 +558,8 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
   }
   if (side) side->join(st);
   // BatchNorm batch counters + status word folded into the result record: one launch
-  finalize_step(out, status, (bn_batches && !(hp->flags & DRV_FLAG_NO_BN_UPDATE)) ? bn_batches : nullptr, n.n_bn, st);
+  finalize_step(out, status, (bn_batches && !(hp->flags & DRV_FLAG_NO_BN_UPDATE)) ? bn_batches : nullptr, n.n_bn,
+                use_tc ? c.at<float>(p.ll) : nullptr, B, hp->scale_factor, st);
   if (prof::enabled && prof::n_steps < prof::MAX_STEPS) {
     if (!bwd) for (int i = 5; i <= DRV_N_SECTIONS; ++i) prof::mark(i, st);
     ++prof::n_steps;

@@ -121,12 +121,15 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
   //     operand ring shrinks to 3 stages to make room (the MMA is far from critical here)
   //   phase 3: stages a 128 x 128 ds' tile (4 boxes, 64 KB), 2-deep operand ring, ds written in place
   constexpr bool TSTORE = (PHASE == 2 && WITH_A) || PHASE == 3;
-  constexpr int NST = PHASE == 3 ? 2 : (TSTORE ? 3 : STAGES);
-  constexpr int XB = PHASE == 3 ? 2 * X_BYTES : X_BYTES;
+  // phase 1 moves TWO 32-float k-blocks per ring stage: the producer / MMA-thread hand-shake per stage,
+  // not bytes or MMA time, is what bounds it (profiles/r01_notes.md), so fewer, fatter stages win
+  constexpr int KG = PHASE == 1 ? 2 : 1;
+  constexpr int NST = PHASE == 3 ? 2 : (TSTORE ? 3 : (PHASE == 1 ? 3 : STAGES));
+  constexpr int XB = PHASE == 3 ? 2 * X_BYTES : (PHASE == 1 ? 0 : X_BYTES);  // phase 1 stages no count tile
   constexpr int RB = (PHASE == 2 && WITH_A) ? X_BYTES : 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* xbuf = smem + NST * STAGE_BYTES;
+  uint8_t* xbuf = smem + NST * KG * STAGE_BYTES;
   uint8_t* rbuf = xbuf + 2 * XB;  // [2][RB]
   uint64_t* full = (uint64_t*)(rbuf + 2 * RB);
   uint64_t* empty = full + NST;
@@ -191,14 +194,17 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
           for (int j = 0; j < XB / (BM * 128); ++j)
             tma_load_2d(xbuf + xs * XB + j * (BM * 128), &tmX, &x_full[xs], g0 + 32 * j, b0);
         }
-        for (int kb = 0; kb < nkb; ++kb, ++kit) {
+        for (int kb = 0; kb < nkb; kb += KG, ++kit) {
           const int s = kit % NST, ph = (kit / NST) & 1;
           swait(&empty[s], ph ^ 1);
-          uint8_t* sa = smem + s * STAGE_BYTES;
-          mbar_expect_tx(&full[s], STAGE_BYTES);
-          tma_load_2d(sa, &tmAct, &full[s], kb * BK, b0);
-          if (PHASE != 2) tma_load_2d(sa + A_BYTES, &tmW, &full[s], kb * BK, g0);
-          else tma_load_3d(sa + A_BYTES, &tmW, &full[s], kb * BK, g0, 0);
+          const int ng = min(KG, nkb - kb);
+          mbar_expect_tx(&full[s], ng * STAGE_BYTES);
+          for (int j = 0; j < ng; ++j) {
+            uint8_t* sa = smem + (s * KG + j) * STAGE_BYTES;
+            tma_load_2d(sa, &tmAct, &full[s], (kb + j) * BK, b0);
+            if (PHASE != 2) tma_load_2d(sa + A_BYTES, &tmW, &full[s], (kb + j) * BK, g0);
+            else tma_load_3d(sa + A_BYTES, &tmW, &full[s], (kb + j) * BK, g0, 0);
+          }
         }
       }
     }
@@ -212,16 +218,19 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
         swait(&acc_empty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * 128);
-        for (int kb = 0; kb < nkb; ++kb, ++kit) {
+        for (int kb = 0; kb < nkb; kb += KG, ++kit) {
           const int s = kit % NST, ph = (kit / NST) & 1;
           swait(&full[s], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
+          const int ng = min(KG, nkb - kb);
+          for (int j = 0; j < ng; ++j) {
+            const uint32_t sa = smem_u32(smem + (s * KG + j) * STAGE_BYTES);
+            const uint32_t sb = sa + A_BYTES;
 #pragma unroll
-          for (int kk = 0; kk < BK / 8; ++kk)
-            umma_tf32(d_tmem, smem_desc(sa + kk * 32, 16, 1024), smem_desc(sb + kk * 32, 16, 1024), idesc,
-                      (kb | kk) != 0);
+            for (int kk = 0; kk < BK / 8; ++kk)
+              umma_tf32(d_tmem, smem_desc(sa + kk * 32, 16, 1024), smem_desc(sb + kk * 32, 16, 1024), idesc,
+                        (kb | j | kk) != 0);
+          }
           umma_commit(&empty[s]);
         }
         umma_commit(&acc_full[as]);
@@ -518,21 +527,6 @@ __global__ void k_round_tf32(const float* __restrict__ src, size_t n, float* __r
     dst[i] = rna_tf32(src[i]);
 }
 
-__global__ void k_loss_from_ll(const float* __restrict__ ll, int B, float c, drv_step_out* out) {
-  pdl_prologue();
-  double t = 0.0;
-  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) t += (double)ll[b];
-  t = warp_sum(t);
-  __shared__ double sh[8];
-  if (threadIdx.x % 32 == 0) sh[threadIdx.x / 32] = t;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int i = 0; i < (int)blockDim.x / 32; ++i) s += sh[i];
-    atomicAdd(&out->loss, -(double)c * s);
-  }
-}
-
 __global__ void k_gate(float* __restrict__ dact, const float* __restrict__ U, int B, int h, BnParams bn) {
   pdl_prologue();
   size_t n = (size_t)B * h;
@@ -662,8 +656,7 @@ void tc_decoder_forward(const TcDecoderArgs& a, cudaStream_t st) {
     launch_dec(k_dec<2, false>, n_ct * n_gt, tAct, tW3, tX, tX, tX, p, st);
   }
   drv_internal_kmark(1, 1, st);
-  launch_k(k_loss_from_ll, 8, 256, 0, st, a.ll, a.B, a.c, a.out);
-  note_launch();
+  // the row sums LL[b] are folded into the loss by the step's last launch (finalize_step)
 }
 
 void tc_decoder_backward(const TcDecoderArgs& a, cudaStream_t st) {
