@@ -68,7 +68,11 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 // tile, two TMEM accumulators, 3 stages of 64 KB) moves 1.5x fewer operand bytes from L2 per MMA
 // than MT = 1 (4 stages of 48 KB, accumulator double-buffered across chunks): the large GEMMs are
 // bound by L2 -> shared-memory bandwidth (ncu: tensor pipe 25-44 %, ~7 TB/s of TMA traffic).
-template <bool A_MN, bool B_MN, int MT>
+// CL = 2: thread-block clusters of two CTAs take two M tiles of the same (N tile, k-part); each CTA
+// loads HALF of every staged B tile and multicasts it into both CTAs' rings, so B is read from L2
+// once per pair.  The large backward GEMMs are bound by exactly that traffic (dAct: 39 k-blocks x
+// 64 KB per CTA x 128 CTAs = 320 MB through L2 in ~45 us; half of it is the shared B operand).
+template <bool A_MN, bool B_MN, int MT, int CL = 1>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
@@ -94,18 +98,21 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int kb_pair = (K + BK - 1) / BK;
   const int kb_total = kb_pair * n_pairs;
   const int m_tiles = (M + TBM - 1) / TBM, n_tiles = (N + n_tile - 1) / n_tile;
-  // work = (tile, k-part) chunks: every tile's k range is cut into `splits` parts; CTA c owns the
-  // contiguous chunk range [c0, c1)
-  const long long chunks = (long long)m_tiles * n_tiles * splits;
-  const int c0 = (int)(chunks * blockIdx.x / gridDim.x);
-  const int c1 = (int)(chunks * (blockIdx.x + 1) / gridDim.x);
+  // work = (group of CL M tiles, N tile, k-part) chunks: every tile's k range is cut into `splits`
+  // parts; cluster w owns the contiguous chunk range [c0, c1) and its CTA `rank` the M tile
+  // CL * group + rank of every chunk
+  const int rank = CL == 1 ? 0 : (int)cluster_ctarank();
+  const int n_wk = (int)gridDim.x / CL, wk = (int)blockIdx.x / CL;
+  const long long chunks = (long long)((m_tiles + CL - 1) / CL) * n_tiles * splits;
+  const int c0 = (int)(chunks * wk / n_wk);
+  const int c1 = (int)(chunks * (wk + 1) / n_wk);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < NSTG; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], CL);  // a stage is refilled (by both CTAs of a pair) once every CTA has consumed it
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
@@ -116,6 +123,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (warp == 1) tmem_alloc<2 * MAXN>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -127,7 +135,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       for (int ch = c0; ch < c1; ++ch) {
         const int tile = ch / splits, part = ch % splits;
         const int kb_b = (int)((long long)kb_total * part / splits), kb_e = (int)((long long)kb_total * (part + 1) / splits);
-        const int m0 = (tile / n_tiles) * TBM, n0 = (tile % n_tiles) * n_tile;
+        const int m0 = (CL * (tile / n_tiles) + rank) * TBM, n0 = (tile % n_tiles) * n_tile;
         for (int kb = kb_b; kb < kb_e; ++kb, ++i) {
           const int s = i % NSTG, ph = (i / NSTG) & 1;
           mbar_wait(&empty[s], ph ^ 1);
@@ -143,7 +151,17 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           } else {
             for (int j = 0; j < MT; ++j) tma_load_2d(sa + j * A_BYTES, ma, &full[s], k0, m0 + j * BM);
           }
-          if (B_MN) {
+          if (CL == 2) {
+            // my half of the B tile, delivered to both CTAs of the pair (tmB's box is half a tile here)
+            if (B_MN) {
+              const int nb = n_tile / 64;
+              for (int j = rank * nb; j < (rank + 1) * nb; ++j)
+                tma_load_2d_mc(sb + j * 4096, mb, &full[s], n0 + 32 * j, k0, (uint16_t)0x3);
+            } else {
+              const int half = n_tile / 2;
+              tma_load_2d_mc(sb + rank * half * BK * 4, mb, &full[s], k0, n0 + rank * half, (uint16_t)0x3);
+            }
+          } else if (B_MN) {
             for (int j = 0; j < n_tile / 32; ++j) tma_load_2d(sb + j * 4096, mb, &full[s], n0 + 32 * j, k0);
           } else {
             tma_load_2d(sb, mb, &full[s], k0, n0);
@@ -179,7 +197,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               umma_tf32(d_tmem + (uint32_t)(mt * MAXN), da, db, idesc, (kb != kb_b) || (kk != 0));
             }
           }
-          umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+          if (CL == 2) umma_commit_mc(&empty[s], (uint16_t)0x3);  // ... in both CTAs: the peer multicasts into this stage too
+          else umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
         }
         umma_commit(&acc_full[as]);
       }
@@ -190,7 +209,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     int seg = 0;
     for (int ch = c0; ch < c1; ++ch, ++seg) {
       const int tile = ch / splits, part = ch % splits;
-      const int m0 = (tile / n_tiles) * TBM, n0 = (tile % n_tiles) * n_tile;
+      const int m0 = (CL * (tile / n_tiles) + rank) * TBM, n0 = (tile % n_tiles) * n_tile;
       const bool whole = !force_atomic;
       const bool add_bias = bias != nullptr && part == 0 && part_stride == 0;
       const int as = seg % NACC, aph = (seg / NACC) & 1;
@@ -238,6 +257,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<2 * MAXN>(tmem_base);
@@ -428,6 +448,43 @@ int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs,
     launch_k_plain(kern, grid, NTHREADS, SMEM_BYTES, st, ta[0], tb[0], ta[1], tb[1], ta[2], tb[2], n_pairs, outp, out_ld, M, N, K, n_tile,
                                              splits, force_atomic, kbias, part_stride, g_mn_lbo, g_mn_sbo, g_mn_kstep);
   };
+  // Cluster-of-2 schedule for the large accumulate-mode GEMMs (256-row tiles, one operand pair): the
+  // B tile is multicast across two M tiles.
+  // Measured (profiles/r01_notes.md): neutral at cluster size 2 - dW 55.7 -> 51.7 us, dAct 55.8 -> 57.7 us -
+  // consistent with the L2's own de-duplication of near-simultaneous unicast requests; opt-in until a
+  // larger cluster / 2-CTA MMA variant exists.  DRV_CLUSTER_GEMM=1 enables it (parity-tested).
+  static const bool no_cluster = getenv("DRV_CLUSTER_GEMM") == nullptr;
+  const int m_tiles2 = (M + 2 * BM - 1) / (2 * BM);
+  if (!no_cluster && mt_sel == 2 && n_pairs == 1 && !deterministic && n_tile % 64 == 0 && m_tiles2 >= 2 && sms >= 2) {
+    if (!b_mn) {  // K-major B: the pair's halves are two boxes of n_tile / 2 rows
+      if (!tmap_2d(&tb[0], Bs[0], (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)(n_tile / 2), BK)) return -3;
+    }
+    const long long units = (long long)((m_tiles2 + 1) / 2) * ((N + n_tile - 1) / n_tile) * splits;
+    const int n_cl = (int)(units < sms / 2 ? units : sms / 2);
+    auto launch_cl = [&](auto kern) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(2 * n_cl);
+      cfg.blockDim = dim3(NTHREADS);
+      cfg.dynamicSmemBytes = SMEM_BYTES;
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      cudaLaunchKernelEx(&cfg, kern, ta[0], tb[0], ta[1], tb[1], ta[2], tb[2], n_pairs, outp, out_ld, M, N, K, n_tile, splits,
+                         force_atomic, kbias, part_stride, g_mn_lbo, g_mn_sbo, g_mn_kstep);
+    };
+    if (a_mn && b_mn) launch_cl(k_tc_gemm<true, true, 2, 2>);
+    else if (a_mn) launch_cl(k_tc_gemm<true, false, 2, 2>);
+    else if (b_mn) launch_cl(k_tc_gemm<false, true, 2, 2>);
+    else launch_cl(k_tc_gemm<false, false, 2, 2>);
+    note_launch();
+    return 0;
+  }
   if (mt_sel == 1) {
     if (a_mn && b_mn) launch(k_tc_gemm<true, true, 1>);
     else if (a_mn) launch(k_tc_gemm<true, false, 1>);
