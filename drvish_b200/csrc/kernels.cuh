@@ -80,4 +80,11 @@ void finalize_status(drv_step_out* out, cudaStream_t st);
 void finalize_step(drv_step_out* out, const uint32_t* status, int64_t* counters, int n, const float* ll, int B,
                    float scale, cudaStream_t st);
 
+// ---- k_optim.cu ------------------------------------------------------------------------------------
+int aggmo_step(const long long* offs, const long long* lens, int n_tensors, const drv_aggmo& hp, float* params,
+               const float* grads, float* momentum, long long mom_stride, double* norms, cudaStream_t st);
+
+void aggmo_step_dose_response(const long long* bases, int L, int n_drugs, const int32_t* dose_off, const drv_aggmo& hp,
+                              float* params, const float* grads, float* momentum, long long mom_stride, cudaStream_t st);
+
 }  // namespace drv

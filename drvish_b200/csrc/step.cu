@@ -567,6 +567,39 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
   return finish();
 }
 
+int drv_aggmo_step(const drv_dims* dims, const drv_aggmo* hp, float* params, const float* grads, float* momentum,
+                   const int32_t* dose_offsets, void* scratch, void* stream) {
+  g_launches = 0;
+  g_err = cudaSuccess;
+  if (!valid(dims) || !hp || !params || !grads || !momentum || !scratch) return DRV_EINVAL;
+  if (dims->n_drugs > 0 && !dose_offsets) return DRV_EINVAL;
+  if (hp->n_betas < 1 || hp->n_betas > DRV_MAX_BETAS) return DRV_EINVAL;
+  Net n = make_net(*dims);
+  long long offs[DRV_MAX_TENSORS], lens[DRV_MAX_TENSORS];
+  int nt = 0;
+  auto add = [&](int64_t off, int64_t len) {
+    if (len > 0 && nt < DRV_MAX_TENSORS) { offs[nt] = off; lens[nt] = len; ++nt; }
+  };
+  for (int s = 0; s < 2; ++s)
+    for (int k = 0; k < n.n_blocks; ++k) {
+      const Block& b = s == 0 ? n.enc[k] : n.dec[k];
+      add(b.gamma, b.din);
+      add(b.beta, b.din);
+      add(b.W, (int64_t)b.dout * b.din);
+      add(b.bias, b.dout);
+    }
+  int rc = aggmo_step(offs, lens, nt, *hp, params, grads, momentum, (long long)n.n_param_floats, (double*)scratch,
+                      (cudaStream_t)stream);
+  if (rc != 0) return rc;
+  if (dims->n_drugs > 0) {
+    // per-drug tensors of the dose-response head (each one its own pyro.param in the reference)
+    const long long bases[4] = {n.w_loc, n.w_scale, n.b_loc, n.b_scale};
+    aggmo_step_dose_response(bases, dims->n_latent, dims->n_drugs, dose_offsets, *hp, params, grads, momentum,
+                             (long long)n.n_param_floats, (cudaStream_t)stream);
+  }
+  return finish();
+}
+
 int drv_profile_enable(int on) {
   if (on && !prof::created) {
     for (int i = 0; i < prof::MAX_STEPS; ++i)

@@ -164,6 +164,29 @@ int drv_draw_step_noise(const drv_dims* dims, const drv_hparams* hp, uint64_t se
 int64_t drv_host_pack_counts_u16(const float* h_src, uint16_t* h_dst, int64_t n, int n_threads);
 int drv_unpack_counts_u16(const uint16_t* src, float* dst, int64_t n, void* stream);
 
+/* Fused optimizer step over the flat buffers: AggMo.step (reference
+ * src/drvish/train/aggmo.py:42-79) applied to every parameter tensor, preceded by Pyro's per-tensor
+ * gradient clipping (PyroOptim clip_args {"clip_norm": c} = torch.nn.utils.clip_grad_norm_ on each
+ * parameter separately; clip_norm <= 0 disables it).  lr is the EFFECTIVE rate, i.e. already divided
+ * by n_betas as the reference does at construction (aggmo.py:22).  momentum: n_betas consecutive
+ * copies of the flat layout (zero-initialised by the caller before the first step); scratch: at
+ * least DRV_MAX_TENSORS doubles; dose_offsets: device int32[n_drugs + 1] as for drv_elbo_step (NULL
+ * without drugs) - every drug's weight_loc / weight_scale / bias_loc / bias_scale is its own tensor.
+ * Two launches for the networks (one without clipping) + one for the dose-response head; gradients
+ * are not modified. */
+#define DRV_MAX_BETAS 4
+#define DRV_MAX_TENSORS 96
+typedef struct drv_aggmo {
+  float lr;
+  float weight_decay;
+  float clip_norm;
+  int32_t nesterov;
+  int32_t n_betas;
+  float betas[DRV_MAX_BETAS];
+} drv_aggmo;
+int drv_aggmo_step(const drv_dims* dims, const drv_aggmo* hp, float* params, const float* grads, float* momentum,
+                   const int32_t* dose_offsets, void* scratch, void* stream);
+
 /* Section timing with CUDA events recorded on the step's stream (bench.py's live roofline
  * measurement).  drv_profile_enable(1) arms it (up to 64 steps are kept); drv_profile_read
  * synchronises on the recorded events and returns the mean milliseconds per section. */

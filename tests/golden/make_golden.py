@@ -109,8 +109,48 @@ def oracle_step(name, cfg, seed_data):
                         **{k: (v.detach().cpu().numpy() if torch.is_tensor(v) else v) for k, v in out.items()})
 
 
+def ref_aggmo():
+    """ref_aggmo.npz: the reference's OWN optimizer (src/drvish/train/aggmo.py, loaded by file path) run
+    for 4 steps on three ragged tensors, each step preceded by the per-parameter
+    torch.nn.utils.clip_grad_norm_ that Pyro's PyroOptim applies (clip_args={"clip_norm": c}); the four
+    variants cover nesterov on/off, weight decay and clipping that does / does not bite.  Pins SURVEY 8f-1."""
+    import importlib.util
+
+    path = "/root/reference/src/drvish/train/aggmo.py"
+    spec = importlib.util.spec_from_file_location("ref_aggmo", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    shapes = [(37, 19), (53,), (8, 5, 3)]
+    variants = {
+        "nesterov_clip": dict(lr=5e-4, betas=[0.0, 0.9, 0.99], nesterov=True, weight_decay=0.0, clip=20.0),
+        "plain_clip": dict(lr=1e-2, betas=[0.0, 0.9, 0.99], nesterov=False, weight_decay=0.0, clip=0.5),
+        "wd_noclip": dict(lr=3e-3, betas=[0.0, 0.9], nesterov=True, weight_decay=0.01, clip=None),
+        "one_beta": dict(lr=1e-3, betas=[0.5], nesterov=False, weight_decay=0.0, clip=100.0),
+    }
+    out = {}
+    for name, v in variants.items():
+        g = torch.Generator().manual_seed(99)
+        params = [torch.nn.Parameter(torch.randn(s, generator=g)) for s in shapes]
+        # one optimizer PER parameter, like PyroOptim
+        opts = [mod.AggMo([p], lr=v["lr"], betas=v["betas"], weight_decay=v["weight_decay"], nesterov=v["nesterov"])
+                for p in params]
+        for i, p in enumerate(params):
+            out[f"{name}.p0.{i}"] = p.detach().clone().numpy()
+        for step in range(4):
+            for i, (p, o) in enumerate(zip(params, opts)):
+                scale = 40.0 if step == 1 else 1.0  # step 1: norms well above the clip threshold
+                p.grad = torch.randn(p.shape, generator=g) * scale
+                out[f"{name}.g{step}.{i}"] = p.grad.clone().numpy()
+                if v["clip"] is not None:
+                    torch.nn.utils.clip_grad_norm_(p, v["clip"])
+                o.step()
+                out[f"{name}.p{step + 1}.{i}"] = p.detach().clone().numpy()
+    np.savez_compressed(os.path.join(HERE, "ref_aggmo.npz"), **out)
+
+
 if __name__ == "__main__":
     ref_modules_small()
+    ref_aggmo()
     oracle_step("oracle_step_cfg1.npz", O.CONFIGS[1], seed_data=1235)
     oracle_step("oracle_step_tiny.npz",
                 dict(n_input=203, n_latent=3, layers=[24, 40], batch=77, drugs=0), seed_data=5)
