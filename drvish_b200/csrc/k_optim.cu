@@ -17,17 +17,27 @@ constexpr int OPT_PER_CTA = 4096;     // floats per CTA (4 float4 per thread)
 
 struct TensorTable {
   int n;
+  int blk0[DRV_MAX_TENSORS + 1];  // first CTA of every tensor (prefix sum of its chunk count)
   long long off[DRV_MAX_TENSORS];
   long long len[DRV_MAX_TENSORS];
 };
 
+// CTA -> (tensor, chunk): binary search in the block prefix (n <= 96)
+__device__ __forceinline__ int tensor_of_block(const TensorTable& tb, int blk) {
+  int lo = 0, hi = tb.n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tb.blk0[mid] <= blk) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
 // norms[t] += sum of squares of tensor t's gradient (fp64 accumulation)
 __global__ void __launch_bounds__(OPT_T) k_grad_sqnorm(const float* __restrict__ g, TensorTable tb, double* __restrict__ norms) {
   pdl_prologue();
-  const int t = blockIdx.y;
+  const int t = tensor_of_block(tb, blockIdx.x);
   const long long len = tb.len[t];
-  const long long c0 = (long long)blockIdx.x * OPT_PER_CTA;
-  if (c0 >= len) return;
+  const long long c0 = (long long)(blockIdx.x - tb.blk0[t]) * OPT_PER_CTA;
   const float* gp = g + tb.off[t];
   double s = 0.0;
   const long long c1 = c0 + OPT_PER_CTA < len ? c0 + OPT_PER_CTA : len;
@@ -71,10 +81,9 @@ __global__ void __launch_bounds__(OPT_T) k_aggmo(float* __restrict__ params, con
                                                  float* __restrict__ mom, long long mom_stride, TensorTable tb,
                                                  const double* __restrict__ norms, drv_aggmo hp) {
   pdl_prologue();
-  const int t = blockIdx.y;
+  const int t = tensor_of_block(tb, blockIdx.x);
   const long long len = tb.len[t];
-  const long long c0 = (long long)blockIdx.x * OPT_PER_CTA;
-  if (c0 >= len) return;
+  const long long c0 = (long long)(blockIdx.x - tb.blk0[t]) * OPT_PER_CTA;
   const long long base = tb.off[t];
   float coef = 1.f;
   if (hp.clip_norm > 0.f) {
@@ -90,10 +99,37 @@ __global__ void __launch_bounds__(OPT_T) k_aggmo(float* __restrict__ params, con
     betas[b] = hp.betas[b];
   }
   const long long c1 = c0 + OPT_PER_CTA < len ? c0 + OPT_PER_CTA : len;
-  for (long long i = c0 + threadIdx.x; i < c1; i += OPT_T) {
-    // scalar, coalesced (consecutive lanes, consecutive floats): the pass is HBM-bound either way
-    params[base + i] = aggmo_elem(params[base + i], grads[base + i], coef, hp.weight_decay, hp.lr, hp.n_betas, betas,
-                                  hp.nesterov != 0, bufs, i);
+  const bool nest = hp.nesterov != 0;
+  for (long long i = c0 + threadIdx.x * 4; i < c1; i += OPT_T * 4) {
+    if (i + 4 <= c1) {  // tensors start on 128-byte boundaries: 128-bit accesses throughout
+      float4 p = *reinterpret_cast<float4*>(params + base + i);
+      const float4 g = *reinterpret_cast<const float4*>(grads + base + i);
+      float pv[4] = {p.x, p.y, p.z, p.w};
+      float d[4] = {g.x * coef, g.y * coef, g.z * coef, g.w * coef};
+      if (hp.weight_decay != 0.f) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d[j] = __fmaf_rn(hp.weight_decay, pv[j], d[j]);
+      }
+#pragma unroll
+      for (int b = 0; b < DRV_MAX_BETAS; ++b) {
+        if (b < hp.n_betas) {
+          float4 m = *reinterpret_cast<float4*>(bufs[b] + i);
+          float mv[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            mv[j] = __fmaf_rn(betas[b], mv[j], d[j]);
+            const float upd = nest ? __fmaf_rn(betas[b], mv[j], d[j]) : mv[j];
+            pv[j] = __fmaf_rn(-hp.lr, upd, pv[j]);
+          }
+          *reinterpret_cast<float4*>(bufs[b] + i) = make_float4(mv[0], mv[1], mv[2], mv[3]);
+        }
+      }
+      *reinterpret_cast<float4*>(params + base + i) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+    } else {
+      for (long long j = i; j < c1; ++j)
+        params[base + j] = aggmo_elem(params[base + j], grads[base + j], coef, hp.weight_decay, hp.lr, hp.n_betas, betas,
+                                      nest, bufs, j);
+    }
   }
 }
 
@@ -152,13 +188,15 @@ int aggmo_step(const long long* offs, const long long* lens, int n_tensors, cons
   if (n_tensors < 1 || n_tensors > DRV_MAX_TENSORS) return DRV_EINVAL;
   TensorTable tb{};
   tb.n = n_tensors;
-  long long max_len = 0;
+  int blocks = 0;
   for (int i = 0; i < n_tensors; ++i) {
     tb.off[i] = offs[i];
     tb.len[i] = lens[i];
-    if (lens[i] > max_len) max_len = lens[i];
+    tb.blk0[i] = blocks;
+    blocks += cdiv(lens[i], OPT_PER_CTA);
   }
-  dim3 grid((unsigned)cdiv(max_len, OPT_PER_CTA), (unsigned)n_tensors);
+  tb.blk0[n_tensors] = blocks;
+  dim3 grid((unsigned)blocks);
   if (hp.clip_norm > 0.f) {
     cudaMemsetAsync(norms, 0, sizeof(double) * n_tensors, st);
     launch_k(k_grad_sqnorm, grid, OPT_T, 0, st, grads, tb, norms);
