@@ -294,12 +294,15 @@ static __device__ __noinline__ float2 nb_count_slow(float r, float x, bool bwd) 
 // non-integer take the generic lgamma / digamma route.  No int<->float conversions (they share
 // the SFU pipe with the transcendentals).
 template <bool BWD, int NV>
+// rshift_l2e: log2(e) times the per-cell shift added to log_r for the COUNT parameter only
+// (r = exp(rho + shift) + eps; ell keeps the unshifted rho) - MCVNBVAE's data-split adjustment,
+// mcv_nbvae.py:78-79; 0 for NBVAE / DRNBVAE.  It rides in the FFMA that feeds ex2: no extra instruction.
 __device__ __forceinline__ void nb_elems(const float (&lsl)[NV], const float (&rho)[NV], const float (&x)[NV], float eps,
-                                         const float* __restrict__ lgtab, NbElem (&o)[NV]) {
+                                         const float* __restrict__ lgtab, NbElem (&o)[NV], float rshift_l2e = 0.f) {
   const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f, MAGIC = 8388608.f;
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
-    const float rexp = ex2_approx(rho[v] * LOG2E);
+    const float rexp = ex2_approx(__fmaf_rn(rho[v], LOG2E, rshift_l2e));
     const float r = rexp + eps;
     const float ell = lsl[v] - rho[v];
     const float e = ex2_approx(-fabsf(ell) * LOG2E);

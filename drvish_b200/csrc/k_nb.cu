@@ -38,9 +38,10 @@ __device__ __forceinline__ float block_max(float v, float* sh) {
 
 template <bool BWD>
 __global__ void __launch_bounds__(NBT) k_nb_rows(float* __restrict__ logits, const float* __restrict__ x,
-                                                 const float* __restrict__ lib, int G, float eps, float c,
-                                                 float* __restrict__ lse_out, float* __restrict__ ll_out,
-                                                 float* __restrict__ asum_out, drv_step_out* out) {
+                                                 const float* __restrict__ lib, const float* __restrict__ rshift, int G,
+                                                 float eps, float c, float* __restrict__ lse_out,
+                                                 float* __restrict__ ll_out, float* __restrict__ asum_out,
+                                                 drv_step_out* out) {
   pdl_prologue();
   __shared__ float sh[NBT / 32];
   __shared__ float lgtab[LGTAB_N];
@@ -51,6 +52,7 @@ __global__ void __launch_bounds__(NBT) k_nb_rows(float* __restrict__ logits, con
   float* rho = s + G;
   const float* xr = x + (size_t)b * G;
   const float l = lib[b];
+  const float rs = rshift ? rshift[b] * 1.4426950408889634f : 0.f;  // MCV: shift of log_r for the count parameter
 
   // pass 1: logsumexp over the scale half
   float mx = -INFINITY;
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(NBT) k_nb_rows(float* __restrict__ logits, con
       a_x[v] = ok[v] ? xr[g] : 0.f;
     }
     NbElem e[4];
-    nb_elems<BWD, 4>(a_lsl, a_rho, a_x, eps, lgtab, e);
+    nb_elems<BWD, 4>(a_lsl, a_rho, a_x, eps, lgtab, e, rs);
 #pragma unroll
     for (int v = 0; v < 4; ++v)
       if (ok[v]) {
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(NBT) k_nb_rows(float* __restrict__ logits, con
       a_x[v] = ok[v] ? xr[g] : 0.f;
     }
     NbElem e[4];
-    nb_elems<true, 4>(a_lsl, a_rho, a_x, eps, lgtab, e);
+    nb_elems<true, 4>(a_lsl, a_rho, a_x, eps, lgtab, e, rs);
 #pragma unroll
     for (int v = 0; v < 4; ++v)
       if (ok[v]) {
@@ -145,10 +147,10 @@ __global__ void k_nb_decoder_outputs(const float* __restrict__ logits, const flo
 
 }  // namespace
 
-void nb_rows(float* logits, const float* x, const float* lib, int B, int G, float eps, float scale_factor, bool bwd,
-             float* lse, float* ll, float* asum, drv_step_out* out, cudaStream_t st) {
-  if (bwd) launch_k(k_nb_rows<true>, B, NBT, 0, st, logits, x, lib, G, eps, scale_factor, lse, ll, asum, out);
-  else launch_k(k_nb_rows<false>, B, NBT, 0, st, logits, x, lib, G, eps, scale_factor, lse, ll, asum, out);
+void nb_rows(float* logits, const float* x, const float* lib, const float* rshift, int B, int G, float eps,
+             float scale_factor, bool bwd, float* lse, float* ll, float* asum, drv_step_out* out, cudaStream_t st) {
+  if (bwd) launch_k(k_nb_rows<true>, B, NBT, 0, st, logits, x, lib, rshift, G, eps, scale_factor, lse, ll, asum, out);
+  else launch_k(k_nb_rows<false>, B, NBT, 0, st, logits, x, lib, rshift, G, eps, scale_factor, lse, ll, asum, out);
   note_launch();
 }
 

@@ -266,6 +266,17 @@ void fill_laplace(float* out, int64_t n, uint64_t seed, uint64_t offset, const u
   note_launch();
 }
 
+__global__ void k_axpby(const float* __restrict__ a, const float* __restrict__ b, float ca, float cb, int n,
+                        float* __restrict__ out) {
+  pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = ca * a[i] + cb * b[i];
+}
+void axpby(const float* a, const float* b, float ca, float cb, int n, float* out, cudaStream_t st) {
+  launch_k(k_axpby, cdiv(n, 256), 256, 0, st, a, b, ca, cb, n, out);
+  note_launch();
+}
+
 __global__ void k_counter_add(unsigned long long* c, unsigned long long v) {
   pdl_prologue(); *c += v; }
 void counter_add(unsigned long long* ctr, unsigned long long v, cudaStream_t st) {

@@ -34,8 +34,9 @@ void simt_linear_dgrad_bngrad(const float* dV, int B, int dout, const float* W, 
 
 // ---- k_nb.cu: gene-softmax + library scaling + NB log-likelihood on materialised logits -------
 // logits [B][2G] = [scale | log_r]; bwd: overwritten with d loss / d logits.
-void nb_rows(float* logits, const float* x, const float* lib, int B, int G, float eps, float scale_factor, bool bwd,
-             float* lse, float* ll, float* asum, drv_step_out* out, cudaStream_t st);
+// rshift (may be null): per-cell shift of log_r for the count parameter (MCVNBVAE, mcv_nbvae.py:78-79)
+void nb_rows(float* logits, const float* x, const float* lib, const float* rshift, int B, int G, float eps,
+             float scale_factor, bool bwd, float* lse, float* ll, float* asum, drv_step_out* out, cudaStream_t st);
 // NBDecoder.forward outputs from materialised logits
 void nb_decoder_outputs(const float* logits, const float* lib, int B, int G, float* log_r, float* logit, cudaStream_t st);
 
@@ -52,6 +53,7 @@ void fill_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, const un
 void fill_laplace(float* out, int64_t n, uint64_t seed, uint64_t offset, const unsigned long long* ctr, uint64_t stride,
                   cudaStream_t st);
 void counter_add(unsigned long long* ctr, unsigned long long v, cudaStream_t st);
+void axpby(const float* a, const float* b, float ca, float cb, int n, float* out, cudaStream_t st);  // out = ca a + cb b
 // all five noise buffers of one step in one launch; state = {step counter, ticket}
 void draw_step_noise(float* const* outs, const int64_t* ns, const int* laplace, const float* scales, uint64_t seed,
                      uint64_t offset, unsigned long long* state, uint64_t stride, cudaStream_t st);

@@ -138,7 +138,7 @@ struct Plan {
   size_t mean[2][DRV_MAX_LAYERS + 1], rstd[2][DRV_MAX_LAYERS + 1];
   size_t V[2][DRV_MAX_LAYERS + 1];          // Linear outputs (B x dout); dec last = logits B x 2G
   size_t Gb[2][DRV_MAX_LAYERS + 1];         // dY / dU of each block input (B x din), block 0 of enc unused
-  size_t z, l, lse, ll, asum, dO;
+  size_t z, l, lse, ll, asum, dO, rshift;
   size_t u, m, gfac, du, dz_drs;
   size_t tc;                                 // scratch of the fused tcgen05 decoder path
   size_t p_hi, p_lo;                         // tf32 hi / lo split of the whole flat parameter buffer
@@ -174,6 +174,7 @@ Plan make_plan(const drv_dims& d, const Net& n) {
   p.z = take(4 * B * d.n_latent);
   p.l = take(4 * B);
   p.lse = take(4 * B);
+  p.rshift = take(4 * B);  // MCVNBVAE: log_split_complement - log_split per cell
   p.dO = take(4 * B * (2 * d.n_latent + 2));
   if (d.n_drugs > 0) {
     p.u = take(4 * B * d.n_drugs);
@@ -389,14 +390,19 @@ size_t drv_workspace_bytes(const drv_dims* dims) {
   return make_plan(*dims, n).total;
 }
 
-int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, const int64_t* labels, const float* y,
-                  const float* eps_z, const float* eps_l, const float* w_prior, const float* b_prior,
-                  const float* eps_bias, const int32_t* dose_offsets, const float* params, float* grads,
-                  float* bn_running, int64_t* bn_batches, drv_step_out* out, void* workspace, size_t workspace_bytes,
-                  void* stream) {
+// x feeds the encoder, x_lik is scored by the likelihood (the same tile except for MCVNBVAE: x0 / x1);
+// log_split / log_split_c (both or neither): per-cell data-split terms of MCVNBVAE, log_r += lsc - ls
+// for the NB count parameter (mcv_nbvae.py:78-79).
+static int elbo_step_impl(const drv_dims* dims, const drv_hparams* hp, const float* x, const float* x_lik,
+                          const float* log_split, const float* log_split_c, const int64_t* labels, const float* y,
+                          const float* eps_z, const float* eps_l, const float* w_prior, const float* b_prior,
+                          const float* eps_bias, const int32_t* dose_offsets, const float* params, float* grads,
+                          float* bn_running, int64_t* bn_batches, drv_step_out* out, void* workspace,
+                          size_t workspace_bytes, void* stream) {
   g_launches = 0;
   g_err = cudaSuccess;
-  if (!valid(dims) || !hp || !x || !eps_z || !eps_l || !params || !out || !workspace) return DRV_EINVAL;
+  if (!valid(dims) || !hp || !x || !x_lik || !eps_z || !eps_l || !params || !out || !workspace) return DRV_EINVAL;
+  if ((log_split == nullptr) != (log_split_c == nullptr)) return DRV_EINVAL;
   const drv_dims& d = *dims;
   if (d.n_drugs > 0 && (!labels || !y || !w_prior || !b_prior || !eps_bias || !dose_offsets)) return DRV_EINVAL;
   Net n = make_net(d);
@@ -502,12 +508,19 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
   block_forward(c, 1, NB - 1, z, false, dec_sd);  // statistics of the last BatchNorm only
   prof::mark(2, st);
 
+  // MCVNBVAE: per-cell shift of log_r (count parameter only), mcv_nbvae.py:78-79
+  const float* rshift = nullptr;
+  if (log_split) {
+    float* rs = c.at<float>(p.rshift);
+    axpby(log_split_c, log_split, 1.f, -1.f, B, rs, st);
+    rshift = rs;
+  }
   // ---- last Linear + gene softmax + NB likelihood (modules.py:93-96, nbvae.py:72-78) ----------
   float* dlogits = c.at<float>(p.V[1][NB - 1]);
   TcDecoderArgs ta{};
   if (use_tc) {
     ta.U = c.at<float>(p.V[1][NB - 2]); ta.bn = c.bn(1, NB - 1); ta.W = params + last.W; ta.W_hi = c.at<float>(p.p_hi) + last.W; ta.bias = params + last.bias;
-    ta.x = x; ta.lib = l; ta.B = B; ta.G = G; ta.h = last.din; ta.eps = hp->epsilon; ta.c = hp->scale_factor;
+    ta.x = x_lik; ta.rshift = rshift; ta.lib = l; ta.B = B; ta.G = G; ta.h = last.din; ta.eps = hp->epsilon; ta.c = hp->scale_factor;
     ta.lse = c.at<float>(p.lse); ta.ll = c.at<float>(p.ll); ta.asum = c.at<float>(p.asum); ta.out = out;
     ta.scratch = c.ws + p.tc; ta.dlogits = dlogits; ta.bwd = bwd;
     ta.dW = bwd ? grads + last.W : nullptr; ta.db = bwd ? grads + last.bias : nullptr;
@@ -516,7 +529,7 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
   } else {
     simt_linear_forward(c.at<float>(p.V[1][NB - 2]), B, last.din, 1, c.bn(1, NB - 1), params + last.W,
                         params + last.bias, last.dout, dlogits, st);
-    nb_rows(dlogits, x, l, B, G, hp->epsilon, hp->scale_factor, bwd, c.at<float>(p.lse), c.at<float>(p.ll),
+    nb_rows(dlogits, x_lik, l, rshift, B, G, hp->epsilon, hp->scale_factor, bwd, c.at<float>(p.lse), c.at<float>(p.ll),
             c.at<float>(p.asum), out, st);
   }
   prof::mark(3, st);
@@ -565,6 +578,25 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, c
     ++prof::n_steps;
   }
   return finish();
+}
+
+int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp, const float* x, const int64_t* labels, const float* y,
+                  const float* eps_z, const float* eps_l, const float* w_prior, const float* b_prior,
+                  const float* eps_bias, const int32_t* dose_offsets, const float* params, float* grads,
+                  float* bn_running, int64_t* bn_batches, drv_step_out* out, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+  return elbo_step_impl(dims, hp, x, x, nullptr, nullptr, labels, y, eps_z, eps_l, w_prior, b_prior, eps_bias,
+                        dose_offsets, params, grads, bn_running, bn_batches, out, workspace, workspace_bytes, stream);
+}
+
+int drv_elbo_step_mcv(const drv_dims* dims, const drv_hparams* hp, const float* x0, const float* x1,
+                      const float* log_split, const float* log_split_complement, const float* eps_z,
+                      const float* eps_l, const float* params, float* grads, float* bn_running, int64_t* bn_batches,
+                      drv_step_out* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!dims || dims->n_drugs != 0 || !log_split || !log_split_complement) return DRV_EINVAL;
+  return elbo_step_impl(dims, hp, x0, x1, log_split, log_split_complement, nullptr, nullptr, eps_z, eps_l, nullptr,
+                        nullptr, nullptr, nullptr, params, grads, bn_running, bn_batches, out, workspace,
+                        workspace_bytes, stream);
 }
 
 int drv_aggmo_step(const drv_dims* dims, const drv_aggmo* hp, float* params, const float* grads, float* momentum,

@@ -11,7 +11,8 @@ struct TcDecoderArgs {
   const float* W;     // [2G][h]
   const float* W_hi;  // [2G][h] tf32-rounded copy (split once per step for all layers)
   const float* bias;  // [2G]
-  const float* x;     // [B][G]
+  const float* x;     // [B][G] counts scored by the likelihood
+  const float* rshift;  // [B] or NULL: shift of log_r for the NB count parameter (MCVNBVAE)
   const float* lib;   // [B]
   int B, G, h;
   float eps, c;

@@ -58,6 +58,7 @@ struct DecParams {
   int B, G, h;
   const float* bias;  // [2G]
   const float* lib;   // [B]
+  const float* rshift;  // [B] or NULL (MCVNBVAE data-split shift of log_r, count parameter only)
   float eps, c;
   // phase 1
   float* part_m;      // [n_slots][B]
@@ -273,7 +274,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
       p.part_s[slot] = s_run;
     };
     int cur_ct = -1;
-    float lib_b = 0.f, lse_b = 0.f, asum_b = 0.f;
+    float lib_b = 0.f, lse_b = 0.f, asum_b = 0.f, rs_b = 0.f;
     int b = 0;
     bool row_ok = false;
     for (int t = t0, it = 0; t < t1; ++t, ++it) {
@@ -294,6 +295,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
         if (PHASE != 1 && row_ok) {
           lib_b = p.lib[b];
           lse_b = combine_lse(p, ct, b);
+          if (PHASE == 2) rs_b = p.rshift ? p.rshift[b] * 1.4426950408889634f : 0.f;
           if (PHASE == 3) asum_b = p.asum[b];
         }
         if (PHASE == 3 && !row_ok) asum_b = 0.f;
@@ -460,7 +462,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
             a_x[v] = ok[v] ? xv[v] : 0.f;
           }
           NbElem e[4];
-          nb_elems<WITH_A, 4>(a_lsl, a_rho, a_x, p.eps, lgtab, e);
+          nb_elems<WITH_A, 4>(a_lsl, a_rho, a_x, p.eps, lgtab, e, rs_b);
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
             if (ok[v]) {
@@ -630,7 +632,7 @@ void tc_decoder_forward(const TcDecoderArgs& a, cudaStream_t st) {
   launch_k(k_act, blocks, 256, 0, st, a.U, a.B, a.h, a.bn, s.act);
   note_launch();
   DecParams p{};
-  p.B = a.B; p.G = a.G; p.h = a.h; p.bias = a.bias; p.lib = a.lib; p.eps = a.eps; p.c = a.c;
+  p.B = a.B; p.G = a.G; p.h = a.h; p.bias = a.bias; p.lib = a.lib; p.rshift = a.rshift; p.eps = a.eps; p.c = a.c;
   p.part_m = s.part_m; p.part_s = s.part_s; p.ll = a.ll; p.asum = a.asum;
   p.dlogits = a.dlogits; p.db = a.db;
   const int n_ct = (a.B + BM - 1) / BM;

@@ -154,24 +154,38 @@ class FusedTraceELBO:
         rt = module._runtime()
         rt.ensure_flat()
         x = args[0]
-        labels = args[1] if len(args) > 1 else None
-        y = self._flatten_y(rt, args[2] if len(args) > 2 else None, rt.device)
+        mcv = None
+        if getattr(module, "is_mcv", False):
+            # (x0, x1, log_data_split, log_data_split_complement), mcv_nbvae.py:57-63
+            if len(args) != 4:
+                raise TypeError("MCVNBVAE batches are (x0, x1, log_data_split, log_data_split_complement)")
+            B = x.shape[0]
+            per_cell = lambda t: torch.as_tensor(t, dtype=torch.float32, device=x.device).reshape(-1).expand(B).contiguous() \
+                if torch.as_tensor(t).numel() in (1, B) else None
+            ls, lsc = per_cell(args[2]), per_cell(args[3])
+            if ls is None or lsc is None:
+                raise RuntimeError("drvish_b200: the data-split terms must be scalars or one value per cell")
+            mcv = (args[1], ls, lsc)
+            labels, y = None, None
+        else:
+            labels = args[1] if len(args) > 1 else None
+            y = self._flatten_y(rt, args[2] if len(args) > 2 else None, rt.device)
         if want_grads and self._dp_enabled():
             # two-part step: the all-reduce of the decoder + dose-response slice (incl. the loss in the
             # tail slot) runs on NCCL's stream while the encoder backward is still computing
-            self._enqueue(rt, x, labels, y, True, part=1)
+            self._enqueue(rt, x, labels, y, True, part=1, mcv=mcv)
             rt.flat_grads[rt.n_param_floats] = rt._out[0].to(torch.float32)
             tail = rt.flat_grads[rt.decoder_offset:]
             w1 = torch.distributed.all_reduce(tail, op=torch.distributed.ReduceOp.SUM, group=self.process_group,
                                               async_op=True)
-            self._enqueue(rt, x, labels, y, True, part=2)
+            self._enqueue(rt, x, labels, y, True, part=2, mcv=mcv)
             head = rt.flat_grads[:rt.decoder_offset]
             w2 = torch.distributed.all_reduce(head, op=torch.distributed.ReduceOp.SUM, group=self.process_group,
                                               async_op=True)
             w1.wait()
             w2.wait()
         else:
-            self._enqueue(rt, x, labels, y, want_grads)
+            self._enqueue(rt, x, labels, y, want_grads, mcv=mcv)
         self.step_index += 1
         loss, status = rt.read_out()
         self.last_status = status
@@ -184,7 +198,7 @@ class FusedTraceELBO:
             rt.attach_grads()
         return loss
 
-    def _enqueue(self, rt, x, labels, y, want_grads: bool, part: int = 0) -> None:
+    def _enqueue(self, rt, x, labels, y, want_grads: bool, part: int = 0, mcv=None) -> None:
         """Noise draws + drv_elbo_step, either launched directly or replayed from a CUDA graph.
 
         A graph is keyed by the device pointers it bakes in (x, labels, y, mode, batch size); it is
@@ -196,12 +210,13 @@ class FusedTraceELBO:
         def eager():
             # part 2 continues the step of part 1: same noise buffers, no new draws
             noise = self._noise(rt, x.shape[0], draw=(part != 2))
-            rt.elbo_step(x, labels, y, noise, want_grads, self.flags | pflags, self.include_guide_factor)
+            rt.elbo_step(x, labels, y, noise, want_grads, self.flags | pflags, self.include_guide_factor, mcv=mcv)
 
         if not self.use_cuda_graph or self._explicit_noise is not None or not x.is_cuda:
             return eager()
         key = (x.data_ptr(), tuple(x.shape), 0 if labels is None else labels.data_ptr(), 0 if y is None else y.data_ptr(),
-               want_grads, rt.flat_params.data_ptr(), part)
+               want_grads, rt.flat_params.data_ptr(), part,
+               None if mcv is None else tuple(t.data_ptr() for t in mcv))
         g = self._graphs.get(key)
         if g is not None:
             g.replay()

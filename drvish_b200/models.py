@@ -95,6 +95,38 @@ class NBVAE(nn.Module):
             pyro.sample("library", dist.Normal(l_loc, l_scale).to_event(1))
 
 
+class MCVNBVAE(NBVAE):
+    r"""Molecular-cross-validation variant (reference src/drvish/models/mcv_nbvae.py:14-105): the guide
+    encodes one half of the molecules (``x0``), the model scores the other half (``x1``) with ``log_r``
+    shifted by ``log_data_split_complement - log_data_split`` (:78-79).  Same constructor as ``NBVAE``;
+    batches are ``(x0, x1, log_data_split, log_data_split_complement)`` as produced by the reference's
+    ``MCVDataLoader.split_molecules`` (train/mcv_train.py:20-40)."""
+
+    pyro_name = "mcv_nbvae"
+    is_mcv = True
+
+    def model(self, x0: torch.Tensor, x1: torch.Tensor, log_data_split: torch.Tensor,
+              log_data_split_complement: torch.Tensor):
+        _need_pyro()
+        pyro.module(self.pyro_name, self)
+        with pyro.plate("data", len(x0)), poutine.scale(scale=self.scale_factor):
+            z = pyro.sample("latent", dist.Normal(0, x0.new_ones(self.n_latent)).to_event(1))
+            l = pyro.sample("library", dist.Normal(self.l_loc, self.l_scale).to_event(1))
+            log_r, logit = self.decoder(z, l)
+            log_r = log_r + (log_data_split_complement - log_data_split)  # adjust for data split
+            pyro.sample("obs", dist.NegativeBinomial(total_count=torch.exp(log_r) + self.epsilon,
+                                                     logits=logit).to_event(1), obs=x1)
+
+    def guide(self, x0: torch.Tensor, x1: torch.Tensor, log_data_split: torch.Tensor,
+              log_data_split_complement: torch.Tensor):
+        _need_pyro()
+        pyro.module(self.pyro_name, self)
+        with pyro.plate("data", len(x0)), poutine.scale(scale=self.scale_factor):
+            z_loc, z_scale, l_loc, l_scale = self.encoder(x0)
+            pyro.sample("latent", dist.Normal(z_loc, z_scale).to_event(1))
+            pyro.sample("library", dist.Normal(l_loc, l_scale).to_event(1))
+
+
 class DRNBVAE(NBVAE):
     r"""NB-VAE with a per-drug dose-response likelihood (reference drnbvae.py:16-132).
 

@@ -203,8 +203,9 @@ class ModelRuntime:
 
     # ------------------------------------------------------------------------------------
     def elbo_step(self, x, labels, y_flat, noise: dict, want_grads: bool, flags: int = 0,
-                  include_guide_factor: bool = True):
-        """Enqueue one drv_elbo_step.  Returns nothing; read the result with read_out()."""
+                  include_guide_factor: bool = True, mcv=None):
+        """Enqueue one drv_elbo_step (or drv_elbo_step_mcv when ``mcv = (x1, log_split, log_split_complement)``,
+        each of the last two a contiguous fp32 [B] device tensor).  Returns nothing; read the result with read_out()."""
         self.ensure_flat()
         x = _f32c(x, "x")
         if x.dim() != 2 or x.shape[1] != self.n_genes:
@@ -220,6 +221,18 @@ class ModelRuntime:
             if labels.dtype != torch.int64:
                 labels = labels.long()
             labels = labels.contiguous()
+        if mcv is not None:
+            x1, ls, lsc = mcv
+            x1 = _f32c(x1, "x1")
+            if x1.shape != x.shape or ls.numel() != B or lsc.numel() != B:
+                raise RuntimeError("drvish_b200: MCV step needs x1 of x0's shape and one data-split term per cell")
+            code = self.lib.drv_elbo_step_mcv(
+                C.byref(d), C.byref(hp), _ptr(x), _ptr(x1), _ptr(ls), _ptr(lsc), _ptr(noise["eps_z"]), _ptr(noise["eps_l"]),
+                _ptr(self.flat_params), _ptr(self.flat_grads) if want_grads else None, _ptr(self.flat_bn),
+                _ptr(self.bn_counters), _ptr(self._out), _ptr(ws), ws.numel(), _stream(self.device))
+            _lib.check(code, "drv_elbo_step_mcv")
+            self.last_launches = self.lib.drv_last_launch_count()
+            return
         code = self.lib.drv_elbo_step(
             C.byref(d), C.byref(hp), _ptr(x), _ptr(labels) if self.n_drugs else None,
             _ptr(y_flat) if self.n_drugs else None, _ptr(noise["eps_z"]), _ptr(noise["eps_l"]),

@@ -116,6 +116,16 @@ int drv_elbo_step(const drv_dims* dims, const drv_hparams* hp,
                   drv_step_out* out,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same step for the molecular-cross-validation variant MCVNBVAE (reference
+ * src/drvish/models/mcv_nbvae.py:57-105): the guide encodes x0, the model scores x1,
+ * and log_r is shifted by log_split_complement - log_split (per cell, [B] each) for the NB count
+ * parameter only - the logits the decoder returned are NOT recomputed (:78-79).  dims->n_drugs must
+ * be 0.  Same kernels: the shift rides in the FFMA that feeds exp2 in the NB epilogue. */
+int drv_elbo_step_mcv(const drv_dims* dims, const drv_hparams* hp, const float* x0, const float* x1,
+                      const float* log_split, const float* log_split_complement, const float* eps_z,
+                      const float* eps_l, const float* params, float* grads, float* bn_running, int64_t* bn_batches,
+                      drv_step_out* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Encoder.forward (modules.py:46-60): writes z_loc [B][L], z_scale [B][L], l_loc [B], l_scale [B]. */
 int drv_encoder_forward(const drv_dims* dims, const drv_hparams* hp, const float* x,
                         const float* params, float* bn_running, int64_t* bn_batches,

@@ -186,6 +186,25 @@ def nbvae_loss(model: OracleNBVAE, x, eps_z, eps_l) -> Tuple[torch.Tensor, Dict[
     return -elbo, {"z": z, "l": l, "ll": ll, "log_p": log_p, "log_q": log_q}
 
 
+def mcv_nbvae_loss(model: OracleNBVAE, x0, x1, log_split, log_split_complement, eps_z, eps_l):
+    """MCVNBVAE step (reference mcv_nbvae.py:57-105): the guide encodes x0 (:98), the model scores x1
+    (:81-87) with ``log_r += log_data_split_complement - log_data_split`` (:78-79) - the logits the
+    decoder returned are NOT recomputed after the shift.  Same ELBO assembly as nbvae_loss."""
+    one = x0.new_ones(())
+    z_loc, z_scale, l_loc, l_scale = model.encoder(x0)
+    z = z_loc + eps_z * z_scale
+    l = l_loc + eps_l * l_scale
+    log_q = Normal(z_loc, z_scale).log_prob(z).sum(-1) + Normal(l_loc, l_scale).log_prob(l).sum(-1)
+    log_p = Normal(0 * one, x0.new_ones(model.n_latent)).log_prob(z).sum(-1)
+    log_p = log_p + Normal(model.lib_loc * one, model.lib_scale * x0.new_ones(1)).log_prob(l).sum(-1)
+    log_r, logit = model.decoder(z, l)
+    log_r = log_r + (log_split_complement - log_split)
+    nb = NegativeBinomial(total_count=torch.exp(log_r) + model.epsilon, logits=logit)
+    ll = nb.log_prob(x1).sum(-1)
+    elbo = model.scale_factor * (log_p + ll - log_q).sum()
+    return -elbo, {"z": z, "l": l, "ll": ll, "log_p": log_p, "log_q": log_q}
+
+
 def drnbvae_loss(model: OracleDRNBVAE, x, labels, y: Sequence[torch.Tensor], eps_z, eps_l,
                  w_prior: Sequence[torch.Tensor], b_prior: Sequence[torch.Tensor],
                  eps_bias: Sequence[torch.Tensor], include_guide_factor: bool = True):
