@@ -342,6 +342,32 @@ def run_native(args, cfg):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return world * B * e2e_steps / float(t.item()), pf.h2d_bytes // e2e_steps
 
+    # ---- the reference's GPU-resident sparse loader (data/cupy.py): CSR dataset on the device, every
+    # batch densified by drv_csr_gather_rows, no host copy of counts (an extra: NOT an e2e number in the
+    # contract's sense, its inputs never cross the bus)
+    from drvish_b200.data import CsrCountMatrix
+
+    n_csr = min(4, n_batches)
+    csr = CsrCountMatrix.from_torch(torch.cat([xs[i] for i in range(n_csr)]).to_sparse_csr(), device=device)
+    csr_idx = [torch.arange(i * B, (i + 1) * B, device=device) for i in range(n_csr)]
+
+    def run_csr(n):
+        last = None
+        for i in range(n):
+            last = elbo.loss_and_grads(model.model, model.guide, csr.dense_rows(csr_idx[i % n_csr]), *tail)
+        return last
+
+    run_csr(9)
+    barrier()
+    t0 = time.perf_counter()
+    run_csr(e2e_steps)
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    csr_value = world * B * e2e_steps / float(t.item())
+    csr_nnz = int(csr.data.numel() // n_csr)
+
     e2e_value, e2e_h2d = time_e2e(fp32_set)
     e2e_u16, e2e_u16_h2d = time_e2e(u16_set)
     e2e_fly, e2e_fly_h2d = time_e2e(fp32_set, on_the_fly=True)
@@ -426,7 +452,10 @@ def run_native(args, cfg):
                 # same API, minibatches packed ONCE to lossless uint16 when the dataset is built
                 "packed_u16_dataset": {"value": e2e_u16, "unit": "cells/s", "h2d_bytes_per_step": e2e_u16_h2d},
                 # same API, fp32 host minibatches packed by the prefetcher's worker thread every step
-                "packed_u16_on_the_fly": {"value": e2e_fly, "unit": "cells/s", "h2d_bytes_per_step": e2e_fly_h2d}},
+                "packed_u16_on_the_fly": {"value": e2e_fly, "unit": "cells/s", "h2d_bytes_per_step": e2e_fly_h2d},
+                # same API, dataset resident on the device as CSR (reference data/cupy.py), tiles densified per step
+                "csr_resident_dataset": {"value": csr_value, "unit": "cells/s", "h2d_bytes_per_step": 0,
+                                         "nnz_per_step": csr_nnz}},
         "with_optimizer": with_opt,
         "gpu_launches": launches_per_step * args.steps,
         "launches_per_step": launches_per_step,

@@ -51,8 +51,55 @@ __global__ void __launch_bounds__(256) k_unpack_u16(const uint16_t* __restrict__
   if (blockIdx.x == 0 && threadIdx.x < (int)(n - n8 * 8)) dst[n8 * 8 + threadIdx.x] = (float)src[n8 * 8 + threadIdx.x];
 }
 
+// Dense minibatch tile from a device-resident CSR count matrix (reference CupySparseDataLoader,
+// src/drvish/data/cupy.py:36-43: `t[indices].todense()` per batch).  One warp per output row: the
+// row is cleared with 128-bit stores, then its nonzeros are scattered.  HBM-bound on the dense
+// write (B x G x 4 bytes); the CSR side reads 8 bytes per nonzero.
+template <typename IdxT>
+__global__ void __launch_bounds__(256) k_csr_gather(const IdxT* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                                    const float* __restrict__ data, const int64_t* __restrict__ rows,
+                                                    int B, int G, float* __restrict__ out) {
+  pdl_prologue();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+  if (warp >= B) return;
+  float* o = out + (size_t)warp * G;
+  if ((G & 3) == 0) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = lane; i < G / 4; i += 32) reinterpret_cast<float4*>(o)[i] = z;
+  } else {
+    for (int i = lane; i < G; i += 32) o[i] = 0.f;
+  }
+  __syncwarp();
+  const int64_t r = rows ? rows[warp] : warp;
+  const long long a = (long long)indptr[r], b = (long long)indptr[r + 1];
+  for (long long k = a + lane; k < b; k += 32) {
+    const int c = indices[k];
+    if (c >= 0 && c < G) o[c] = data[k];
+  }
+}
+
 }  // namespace
 }  // namespace drv
+
+extern "C" int drv_csr_gather_rows(const void* indptr, int indptr_is_int64, const int32_t* indices, const float* data,
+                                   const int64_t* rows, int n_rows, int n_genes, float* out, void* stream) {
+  using namespace drv;
+  g_launches = 0;
+  g_err = cudaSuccess;
+  if (!indptr || !indices || !data || !out || n_rows < 0 || n_genes < 1) return DRV_EINVAL;
+  if (n_rows == 0) return 0;
+  const unsigned blocks = (unsigned)((n_rows * 32 + 255) / 256);
+  if (indptr_is_int64)
+    launch_k(k_csr_gather<long long>, blocks, 256, 0, (cudaStream_t)stream, (const long long*)indptr, indices, data, rows, n_rows,
+             n_genes, out);
+  else
+    launch_k(k_csr_gather<int>, blocks, 256, 0, (cudaStream_t)stream, (const int*)indptr, indices, data, rows, n_rows, n_genes,
+             out);
+  note_launch();
+  cudaError_t e = g_err;
+  g_err = cudaSuccess;
+  return (int)e;
+}
 
 extern "C" int64_t drv_host_pack_counts_u16(const float* h_src, uint16_t* h_dst, int64_t n, int n_threads) {
   if (!h_src || !h_dst || n < 0) return -1;

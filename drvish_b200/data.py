@@ -73,6 +73,72 @@ def pack_batches(batches: Iterable[Sequence]) -> List[list]:
     return out
 
 
+class CsrCountMatrix:
+    """Device-resident CSR count matrix + dense minibatch gather (reference ``CupySparseDataset`` /
+    ``CupySparseDataLoader``, src/drvish/data/cupy.py:10-43: datasets that only fit in GPU memory in
+    sparse form; every batch is densified on the device, no host round trip).
+
+    Build it from a ``torch.sparse_csr`` tensor, a scipy ``csr_matrix`` or the three CSR arrays.
+    ``dense_rows(idx)`` returns the fp32 [len(idx)][G] tile the step reads; tiles rotate over ``slots``
+    buffers so that the CUDA-graph keys of ``FusedTraceELBO`` stay stable."""
+
+    def __init__(self, indptr, indices, data, shape, device="cuda", slots: int = 3):
+        dev = torch.device(device)
+        ip = torch.as_tensor(indptr)
+        self.indptr = ip.to(dev, torch.int64 if ip.dtype == torch.int64 else torch.int32).contiguous()
+        self.indices = torch.as_tensor(indices).to(dev, torch.int32).contiguous()
+        self.data = torch.as_tensor(data).to(dev, torch.float32).contiguous()
+        self.shape = (int(shape[0]), int(shape[1]))
+        if self.indptr.numel() != self.shape[0] + 1 or self.indices.numel() != self.data.numel():
+            raise ValueError("inconsistent CSR arrays")
+        self.device = dev
+        self._slots = [None] * slots
+        self._k = 0
+
+    @classmethod
+    def from_scipy(cls, m, device="cuda", slots: int = 3):
+        m = m.tocsr()
+        return cls(m.indptr, m.indices, m.data, m.shape, device, slots)
+
+    @classmethod
+    def from_torch(cls, t: torch.Tensor, device="cuda", slots: int = 3):
+        t = t.to_sparse_csr() if t.layout != torch.sparse_csr else t
+        return cls(t.crow_indices(), t.col_indices(), t.values(), t.shape, device, slots)
+
+    def __len__(self) -> int:
+        return self.shape[0]
+
+    def dense_rows(self, rows: Optional[torch.Tensor] = None, n_rows: Optional[int] = None) -> torch.Tensor:
+        if rows is not None:
+            rows = torch.as_tensor(rows).to(self.device, torch.int64).contiguous()
+            n = rows.numel()
+        else:
+            n = int(n_rows if n_rows is not None else self.shape[0])
+        slot = self._k % len(self._slots)
+        self._k += 1
+        buf = self._slots[slot]
+        if buf is None or buf.shape[0] != n:
+            buf = self._slots[slot] = torch.empty(n, self.shape[1], dtype=torch.float32, device=self.device)
+        lib = _lib.load()
+        _lib.check(lib.drv_csr_gather_rows(C.c_void_p(self.indptr.data_ptr()), int(self.indptr.dtype == torch.int64),
+                                           C.c_void_p(self.indices.data_ptr()), C.c_void_p(self.data.data_ptr()),
+                                           None if rows is None else C.c_void_p(rows.data_ptr()), n, self.shape[1],
+                                           C.c_void_p(buf.data_ptr()),
+                                           C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
+                   "drv_csr_gather_rows")
+        return buf
+
+    def batches(self, batch_size: int, *extra, shuffle: bool = False, generator=None):
+        """Iterate dense tiles like ``CupySparseDataLoader``: yields ``[x_tile, *extra_i[idx]]``."""
+        n = self.shape[0]
+        order = torch.randperm(n, generator=generator) if shuffle else torch.arange(n)
+        for a in range(0, n, batch_size):
+            idx = order[a:a + batch_size]
+            dev_idx = idx.to(self.device)
+            yield [self.dense_rows(dev_idx)] + [(e[dev_idx] if e.is_cuda else e[idx]) if torch.is_tensor(e) and e.shape[:1] == (n,)
+                                                else e for e in extra]
+
+
 class PinnedBatchPrefetcher:
     """Iterate ``batches`` with the host->device copy of the next ones already in flight.
 

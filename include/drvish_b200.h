@@ -197,6 +197,14 @@ typedef struct drv_aggmo {
 int drv_aggmo_step(const drv_dims* dims, const drv_aggmo* hp, float* params, const float* grads, float* momentum,
                    const int32_t* dose_offsets, void* scratch, void* stream);
 
+/* Dense [n_rows][n_genes] fp32 minibatch tile from a DEVICE-resident CSR count matrix (SURVEY 8f row
+ * 2; reference CupySparseDataLoader, src/drvish/data/cupy.py:36-43: `t[indices].todense()`).  indptr:
+ * int32 or int64 (indptr_is_int64) [n_total_rows + 1]; indices int32; data fp32; rows: int64 [n_rows]
+ * row ids of the minibatch (NULL = rows 0..n_rows-1).  Duplicate column entries keep the last one
+ * written (canonical CSR has none). */
+int drv_csr_gather_rows(const void* indptr, int indptr_is_int64, const int32_t* indices, const float* data,
+                        const int64_t* rows, int n_rows, int n_genes, float* out, void* stream);
+
 /* Section timing with CUDA events recorded on the step's stream (bench.py's live roofline
  * measurement).  drv_profile_enable(1) arms it (up to 64 steps are kept); drv_profile_read
  * synchronises on the recorded events and returns the mean milliseconds per section. */

@@ -400,3 +400,23 @@ def test_mcv_step_matches_oracle(force_simt):
     e2 = D.FusedTraceELBO(data_parallel=False, force_simt=force_simt, update_bn_stats=False)
     e2.set_noise(n)
     assert abs(e2.loss_and_grads(plain.model, plain.guide, x0.cuda()) - loss) > 1e-3 * abs(loss)
+
+
+def test_csr_dense_gather_matches_todense():
+    """drv_csr_gather_rows / CsrCountMatrix (reference data/cupy.py:36-43): the dense tile
+    of any row subset equals `m[idx].todense()`, bit for bit; int32 and int64 indptr; ragged gene counts."""
+    from drvish_b200.data import CsrCountMatrix
+
+    g = torch.Generator().manual_seed(8)
+    for n_genes in (203, 1000):
+        dense = torch.poisson(torch.full((301, n_genes), 0.3), generator=g)
+        dense[17] = 0  # an empty row
+        sp = dense.to_sparse_csr()
+        for dtype in (torch.int32, torch.int64):
+            m = CsrCountMatrix(sp.crow_indices().to(dtype), sp.col_indices(), sp.values(), dense.shape)
+            idx = torch.randperm(301, generator=g)[:97]
+            assert torch.equal(m.dense_rows(idx).cpu(), dense[idx])
+            assert torch.equal(m.dense_rows(n_rows=301).cpu(), dense)
+        batches = list(CsrCountMatrix.from_torch(sp).batches(128, torch.arange(301)))
+        assert [b[0].shape[0] for b in batches] == [128, 128, 45] and torch.equal(batches[2][1].cpu(), torch.arange(256, 301))
+        assert torch.equal(batches[1][0].cpu(), dense[128:256])
