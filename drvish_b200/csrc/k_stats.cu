@@ -122,24 +122,6 @@ __global__ void __launch_bounds__(CW* RY) k_colstats4(const float* __restrict__ 
   stat_finalize_if_last(fin, acc, D, blockIdx.x * CW * 4, CW * 4);
 }
 
-__global__ void k_colstats_finalize(const double* __restrict__ acc, int B, int D, float eps, float momentum,
-                                    float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ rmean,
-                                    float* __restrict__ rvar) {
-  pdl_prologue();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= D) return;
-  double m = acc[i] / B;
-  double var = acc[D + i] / B - m * m;
-  if (var < 0.0) var = 0.0;
-  mean[i] = (float)m;
-  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
-  if (rmean) {
-    double unbiased = var * ((double)B / (double)(B - 1));
-    rmean[i] = (float)((1.0 - momentum) * rmean[i] + momentum * m);
-    rvar[i] = (float)((1.0 - momentum) * rvar[i] + momentum * unbiased);
-  }
-}
-
 // GATE: dY holds the UNGATED gradient w.r.t. the ReLU output; the gate [bn(U) > 0] is recomputed here
 // (same fused-multiply-add sequence as the forward), saving a separate gating pass.
 template <bool GATE>
@@ -253,11 +235,6 @@ __global__ void k_bump(int64_t* c, int n) {
   if (i < n) c[i] += 1;
 }
 
-__global__ void k_finalize_status(drv_step_out* out) {
-  pdl_prologue();
-  if (isnan(out->loss)) out->status |= DRV_STATUS_NAN_LOSS;
-}
-
 // Last launch of a step: BatchNorm batch counters, the decoder's log-likelihood sum folded into the
 // loss (ll may be null: the CUDA-core NB kernel adds it itself), status word + NaN flag.
 __global__ void __launch_bounds__(256) k_finalize_step(drv_step_out* out, const uint32_t* status, int64_t* c, int n,
@@ -355,11 +332,6 @@ void bump_counters(int64_t* counters, int n, cudaStream_t st) {
 void finalize_step(drv_step_out* out, const uint32_t* status, int64_t* counters, int n, const float* ll, int B,
                    float scale, cudaStream_t st) {
   launch_k(k_finalize_step, 1, 256, 0, st, out, status, counters, n, ll, B, scale);
-  note_launch();
-}
-
-void finalize_status(drv_step_out* out, cudaStream_t st) {
-  launch_k(k_finalize_status, 1, 1, 0, st, out);
   note_launch();
 }
 

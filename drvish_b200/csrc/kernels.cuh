@@ -76,7 +76,6 @@ void dr_prior_factor(const float* w_prior, const float* b_prior, const float* ep
                      const float* bias_scale_unc, const int32_t* dose_off, DrShape s, const drv_hparams& hp,
                      float* d_bias_loc, float* d_bias_scale_unc, drv_step_out* out, cudaStream_t st);
 
-void finalize_status(drv_step_out* out, cudaStream_t st);
 // counters[i] += 1 (BatchNorm num_batches_tracked; may be null), out->status = *status | NaN flag
 // ... and out->loss -= scale * sum_b ll[b] (ll may be null)
 void finalize_step(drv_step_out* out, const uint32_t* status, int64_t* counters, int n, const float* ll, int B,

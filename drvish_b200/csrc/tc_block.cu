@@ -54,12 +54,6 @@ __global__ void k_split_tf32(const float* __restrict__ src, size_t n, float* __r
   }
 }
 
-__global__ void k_round_rows(const float* __restrict__ src, size_t n, float* __restrict__ dst) {
-  pdl_prologue();
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    dst[i] = rna_tf32(src[i]);
-}
-
 __global__ void k_round_colsum(const float* __restrict__ V, int B, int D, int rows_per_cta, float* __restrict__ Vr,
                                float* __restrict__ out) {
   pdl_prologue();
@@ -72,24 +66,6 @@ __global__ void k_round_colsum(const float* __restrict__ V, int B, int D, int ro
       Vr[(size_t)r * D + col] = rna_tf32(v);
       s += v;
     }
-  __shared__ float sh[8][32];
-  sh[threadIdx.y][threadIdx.x] = s;
-  __syncthreads();
-  if (threadIdx.y == 0 && col < D) {
-    float t = 0.f;
-    for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
-    atomicAdd(&out[col], t);
-  }
-}
-
-__global__ void k_colsum_small(const float* __restrict__ V, int B, int D, int rows_per_cta, float* __restrict__ out) {
-  pdl_prologue();
-  // 32 columns x 8 row lanes per CTA, the batch split over gridDim.y; out must be zeroed
-  int col = blockIdx.x * 32 + threadIdx.x;
-  int r0 = blockIdx.y * rows_per_cta, r1 = min(B, r0 + rows_per_cta);
-  float s = 0.f;
-  if (col < D)
-    for (int r = r0 + threadIdx.y; r < r1; r += 8) s += V[(size_t)r * D + col];
   __shared__ float sh[8][32];
   sh[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
@@ -165,16 +141,6 @@ __global__ void __launch_bounds__(CW* RY) k_bn0_grad(const float* __restrict__ d
 #pragma unroll
     for (int i = 0; i < RY; ++i) t += (double)sh[which][i][c];
     atomicAdd(&acc[(size_t)which * G + gcol], t);
-  }
-}
-
-// dY = dA * [bn(U) > 0] in place (same fused-multiply-add sequence as the forward)
-__global__ void k_gate_block(float* __restrict__ dact, const float* __restrict__ U, size_t n, int D, BnParams bn) {
-  pdl_prologue();
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    int col = (int)(i % D);
-    float y = bn_y(bn_xhat(U[i], bn.mean[col], bn.rstd[col]), bn.gamma[col], bn.beta[col]);
-    if (!(y > 0.f)) dact[i] = 0.f;
   }
 }
 

@@ -523,22 +523,6 @@ __global__ void k_act(const float* __restrict__ U, int B, int h, BnParams bn, fl
   }
 }
 
-__global__ void k_round_tf32(const float* __restrict__ src, size_t n, float* __restrict__ dst) {
-  pdl_prologue();
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    dst[i] = rna_tf32(src[i]);
-}
-
-__global__ void k_gate(float* __restrict__ dact, const float* __restrict__ U, int B, int h, BnParams bn) {
-  pdl_prologue();
-  size_t n = (size_t)B * h;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    int col = (int)(i % h);
-    float y = bn_y(bn_xhat(U[i], bn.mean[col], bn.rstd[col]), bn.gamma[col], bn.beta[col]);
-    if (!(y > 0.f)) dact[i] = 0.f;
-  }
-}
-
 struct Scratch {
   float* act;      // [B][h]  relu(bn(U)) rounded to tf32
   float* Wr;       // [2G][h] last-layer weight rounded to tf32
