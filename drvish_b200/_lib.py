@@ -78,6 +78,7 @@ SYMBOLS = {
     "drv_unpack_counts_u16": (C.c_int, [_P, _P, C.c_int64, _P]),
     "drv_elbo_step_mcv": (C.c_int, [_P] * 14 + [C.c_size_t, _P]),
     "drv_csr_gather_rows": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
+    "drv_split_molecules": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P]),
     "drv_aggmo_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "drv_draw_step_noise": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P, C.c_uint64, _P, _P, _P, _P, _P, _P]),
 }

@@ -23,6 +23,7 @@ import threading
 from typing import Iterable, Iterator, List, Optional, Sequence
 
 import torch
+import torch.utils.data
 
 from . import _lib
 
@@ -137,6 +138,79 @@ class CsrCountMatrix:
             dev_idx = idx.to(self.device)
             yield [self.dense_rows(dev_idx)] + [(e[dev_idx] if e.is_cuda else e[idx]) if torch.is_tensor(e) and e.shape[:1] == (n,)
                                                 else e for e in extra]
+
+
+def split_molecules(umis: torch.Tensor, data_split: torch.Tensor, data_split_complement: torch.Tensor,
+                    overlap_factor: torch.Tensor, *args, seed: Optional[int] = None, call_index: Optional[int] = None,
+                    out: Optional[Sequence[torch.Tensor]] = None):
+    """Device version of the reference's ``MCVDataLoader.split_molecules`` (train/mcv_train.py:20-40):
+    ``(x_data + overlap, y_data + overlap, log data_split, log data_split_complement, *args)`` from ONE
+    kernel launch (``drv_split_molecules``) on the tile's device.  ``umis`` [B][G] fp32 CUDA tensor, the
+    three split tensors one value per row ([B] or [B, 1], as indexed out of the ``TensorDataset``).
+
+    seed / call_index key the Philox draws; by default the seed is ``torch.initial_seed()`` and a
+    process-wide counter supplies a fresh call index per call (a new split every iteration, as in the
+    reference).  There is no CPU path."""
+    if not umis.is_cuda:
+        raise RuntimeError("drvish_b200.split_molecules needs CUDA tensors (no CPU fallback)")
+    if umis.dtype != torch.float32 or umis.dim() != 2:
+        raise TypeError("umis must be a 2-d fp32 tensor of counts")
+    B, G = umis.shape
+    umis = umis.contiguous()
+
+    def row(t, name):
+        t = torch.as_tensor(t, dtype=torch.float32, device=umis.device)
+        if t.numel() == 1:
+            t = t.reshape(1).expand(B)
+        if t.numel() != B:
+            raise ValueError(f"{name}: expected one value per row ({B}), got shape {tuple(t.shape)}")
+        return t.reshape(B).contiguous()
+
+    shape = tuple(data_split.shape) if torch.is_tensor(data_split) and data_split.numel() == B else (B, 1)
+    ds, dc, ov = row(data_split, "data_split"), row(data_split_complement, "data_split_complement"), row(overlap_factor, "overlap_factor")
+    if out is None:
+        x0, x1 = torch.empty_like(umis), torch.empty_like(umis)
+        ls, lc = torch.empty(B, device=umis.device), torch.empty(B, device=umis.device)
+    else:
+        x0, x1, ls, lc = out
+    if seed is None:
+        seed = torch.initial_seed()
+    if call_index is None:
+        call_index = split_molecules._calls
+        split_molecules._calls += 1
+    lib = _lib.load()
+    _lib.check(lib.drv_split_molecules(*(C.c_void_p(t.data_ptr()) for t in (umis, ds, dc, ov)), B, G,
+                                       int(seed) & (2**64 - 1), int(call_index) & (2**64 - 1),
+                                       *(C.c_void_p(t.data_ptr()) for t in (x0, x1, ls, lc)),
+                                       C.c_void_p(torch.cuda.current_stream(umis.device).cuda_stream)),
+               "drv_split_molecules")
+    return (x0, x1, ls.reshape(shape), lc.reshape(shape), *args)
+
+
+split_molecules._calls = 0
+
+
+class MCVDataLoader(torch.utils.data.DataLoader):
+    """Drop-in for the reference's ``MCVDataLoader`` (train/mcv_train.py:6-40): a ``DataLoader`` over a
+    ``TensorDataset`` of ``(umis, data_split, data_split_complement, overlap_factor, *extra)`` that
+    yields a NEW molecule split ``(x0, x1, log_split, log_split_complement, *extra)`` every time it is
+    iterated.  The indexed minibatch is moved to ``device`` (default: current CUDA device) and split
+    there by one kernel; with a device-resident dataset nothing crosses the bus."""
+
+    def __init__(self, dataset, device=None, seed: Optional[int] = None, **kwargs):
+        super().__init__(dataset=dataset, **kwargs)
+        self.device = torch.device("cuda" if device is None else device)
+        self.seed = seed
+
+    def __iter__(self):
+        for indices in iter(self.batch_sampler):
+            batch = []
+            for d in self.dataset.tensors:
+                idx = torch.as_tensor(indices, device=d.device)
+                batch.append(d[idx].to(self.device, non_blocking=True))
+            yield self.split_molecules(*batch, seed=self.seed)
+
+    split_molecules = staticmethod(split_molecules)
 
 
 class PinnedBatchPrefetcher:

@@ -205,6 +205,21 @@ int drv_aggmo_step(const drv_dims* dims, const drv_aggmo* hp, float* params, con
 int drv_csr_gather_rows(const void* indptr, int indptr_is_int64, const int32_t* indices, const float* data,
                         const int64_t* rows, int n_rows, int n_genes, float* out, void* stream);
 
+/* Molecular-cross-validation split of a UMI count tile (reference
+ * MCVDataLoader.split_molecules, src/drvish/train/mcv_train.py:20-40), one launch per minibatch:
+ *   x_data ~ Binomial(umis, data_split - overlap_factor)
+ *   y_data ~ Binomial(umis - x_data, (1 - data_split) / (1 - data_split + overlap_factor))
+ *   overlap = umis - x_data - y_data
+ *   x0 = x_data + overlap, x1 = y_data + overlap, log_split = log data_split,
+ *   log_split_complement = log data_split_complement
+ * umis, x0, x1: [n_rows][n_genes] fp32 (non-negative integer counts); data_split,
+ * data_split_complement, overlap_factor, log_split, log_split_complement: one float per row.  Draws
+ * are Philox4x32-10 keyed by (seed, call_index, element, draw): the same arguments reproduce the same
+ * split whatever the launch shape; advance call_index once per minibatch. */
+int drv_split_molecules(const float* umis, const float* data_split, const float* data_split_complement,
+                        const float* overlap_factor, int n_rows, int n_genes, uint64_t seed, uint64_t call_index,
+                        float* x0, float* x1, float* log_split, float* log_split_complement, void* stream);
+
 /* Section timing with CUDA events recorded on the step's stream (bench.py's live roofline
  * measurement).  drv_profile_enable(1) arms it (up to 64 steps are kept); drv_profile_read
  * synchronises on the recorded events and returns the mean milliseconds per section. */

@@ -205,6 +205,20 @@ def mcv_nbvae_loss(model: OracleNBVAE, x0, x1, log_split, log_split_complement, 
     return -elbo, {"z": z, "l": l, "ll": ll, "log_p": log_p, "log_q": log_q}
 
 
+def split_molecules(umis, data_split, data_split_complement, overlap_factor):
+    """Restatement of the reference's ``MCVDataLoader.split_molecules`` (train/mcv_train.py:20-40):
+    two dependent binomial thinnings and the overlap bookkeeping, with torch.distributions on the CPU.
+    PINNED: bit-identical to the reference's own function under the same ``torch.manual_seed``
+    (tests/golden/ref_split_molecules.npz, generated by executing the reference file).  The CUDA kernel
+    draws from Philox instead, so it is compared with this function in DISTRIBUTION (pmf chi-square,
+    moments) and through the exact invariants x0 = n - y_data, x1 = n - x_data."""
+    x_data = torch.distributions.Binomial(umis, probs=data_split - overlap_factor).sample()
+    y_data = torch.distributions.Binomial(
+        umis - x_data, probs=(1 - data_split) / (1 - data_split + overlap_factor)).sample()
+    overlap = umis - x_data - y_data
+    return x_data + overlap, y_data + overlap, torch.log(data_split), torch.log(data_split_complement)
+
+
 def drnbvae_loss(model: OracleDRNBVAE, x, labels, y: Sequence[torch.Tensor], eps_z, eps_l,
                  w_prior: Sequence[torch.Tensor], b_prior: Sequence[torch.Tensor],
                  eps_bias: Sequence[torch.Tensor], include_guide_factor: bool = True):

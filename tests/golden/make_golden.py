@@ -148,9 +148,28 @@ def ref_aggmo():
     np.savez_compressed(os.path.join(HERE, "ref_aggmo.npz"), **out)
 
 
+def ref_split_molecules():
+    """ref_split_molecules.npz: the reference's OWN MCVDataLoader.split_molecules
+    (src/drvish/train/mcv_train.py, loaded by file path) under torch.manual_seed(5).  Pins SURVEY 8f-3's
+    loader restatement (oracle.split_molecules)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ref_mcv_train", "/root/reference/src/drvish/train/mcv_train.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    from tests.parity import split_case
+
+    umis, split, comp, overlap = split_case()
+    torch.manual_seed(5)
+    x0, x1, ls, lc = mod.MCVDataLoader.split_molecules(umis, split, comp, overlap)
+    np.savez_compressed(os.path.join(HERE, "ref_split_molecules.npz"), x0=x0.numpy(), x1=x1.numpy(), log_split=ls.numpy(),
+                        log_split_complement=lc.numpy())
+
+
 if __name__ == "__main__":
     ref_modules_small()
     ref_aggmo()
+    ref_split_molecules()
     oracle_step("oracle_step_cfg1.npz", O.CONFIGS[1], seed_data=1235)
     oracle_step("oracle_step_tiny.npz",
                 dict(n_input=203, n_latent=3, layers=[24, 40], batch=77, drugs=0), seed_data=5)

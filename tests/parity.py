@@ -120,3 +120,13 @@ def compare_step(case, device="cuda:0", force_simt=False):
             assert int(sd[k]) == int(v), k
     rep["bn_worst_rel"] = bn_worst
     return rep
+
+
+def split_case():
+    """Inputs of the molecule-split golden vector (tests/golden/make_golden.py, tests/test_oracle.py)."""
+    g = torch.Generator().manual_seed(77)
+    umis = torch.poisson(torch.rand(23, 41, generator=g) * 6.0, generator=g)
+    umis[3, 5] = 900.0  # a large count
+    split = 0.5 + 0.4 * torch.rand(23, 1, generator=g)
+    overlap = 0.1 * torch.rand(23, 1, generator=g)
+    return umis, split, 1 - split, overlap

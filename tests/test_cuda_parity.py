@@ -420,3 +420,98 @@ def test_csr_dense_gather_matches_todense():
         batches = list(CsrCountMatrix.from_torch(sp).batches(128, torch.arange(301)))
         assert [b[0].shape[0] for b in batches] == [128, 128, 45] and torch.equal(batches[2][1].cpu(), torch.arange(256, 301))
         assert torch.equal(batches[1][0].cpu(), dense[128:256])
+
+
+def test_split_molecules_kernel_matches_binomial_law():
+    """drv_split_molecules (reference MCVDataLoader.split_molecules, mcv_train.py:20-40).
+    The kernel draws from Philox, the reference from torch's CPU generator, so parity is distributional:
+    exact invariants on every element, pmf chi-square of both thinnings against scipy's binomial for small
+    and chunked (n > 64) counts, marginal laws x0 ~ Bin(n, split), x1 ~ Bin(n, 1 - split + overlap), and
+    moments against the oracle restatement's own samples."""
+    from scipy import stats
+
+    from drvish_b200.data import split_molecules
+
+    dev = "cuda:0"
+    split, ov = 0.8, 0.05
+    p1, p2 = split - ov, (1 - split) / (1 - split + ov)
+    for n, rows in ((1, 4000), (7, 4000), (40, 2000), (300, 1000), (5000, 250)):
+        G = 64
+        umis = torch.full((rows, G), float(n), device=dev)
+        s = torch.full((rows, 1), split, device=dev)
+        o = torch.full((rows, 1), ov, device=dev)
+        x0, x1, ls, lc = split_molecules(umis, s, 1 - s, o, seed=11, call_index=n)
+        assert ls.shape == (rows, 1) and torch.allclose(ls.cpu(), torch.log(s).cpu()) and torch.allclose(lc.cpu(), torch.log(1 - s).cpu())
+        x_data, y_data = (umis - x1).cpu().numpy().ravel(), (umis - x0).cpu().numpy().ravel()
+        assert (x_data == np.round(x_data)).all() and (x_data >= 0).all() and (x_data <= n).all()
+        assert (y_data >= 0).all() and (x_data + y_data <= n).all()
+        N = x_data.size
+        for draws, p in ((x_data, p1), (n - y_data, split)):  # x_data ~ Bin(n,p1); x0 = n - y_data ~ Bin(n, split)
+            mean, var = n * p, n * p * (1 - p)
+            assert abs(draws.mean() - mean) < 5 * np.sqrt(var / N) + 1e-9, (n, draws.mean(), mean)
+            assert abs(draws.var() - var) < 0.05 * var + 1e-9, (n, draws.var(), var)
+            if n <= 300:  # pmf chi-square over bins with expected count >= 20
+                obs = np.bincount(draws.astype(np.int64), minlength=n + 1).astype(np.float64)
+                exp = stats.binom.pmf(np.arange(n + 1), n, p) * N
+                keep = exp >= 20
+                o_k, e_k = np.append(obs[keep], obs[~keep].sum()), np.append(exp[keep], exp[~keep].sum())
+                if e_k[-1] < 20:
+                    o_k, e_k = o_k[:-1], e_k[:-1] * (o_k[:-1].sum() / e_k[:-1].sum())
+                chi2 = ((o_k - e_k) ** 2 / e_k).sum()
+                assert stats.chi2.sf(chi2, len(e_k) - 1) > 1e-4, (n, p, chi2, len(e_k))
+        # y_data | x_data ~ Bin(n - x_data, p2): conditional mean through the regression on the remainder
+        rem = n - x_data
+        if rem.sum() > 0:
+            assert abs(y_data.sum() / rem.sum() - p2) < 5 * np.sqrt(p2 * (1 - p2) / rem.sum())
+
+    # realistic tile: per-row splits, ragged gene count (scalar path) and a 16-byte-aligned one (vector path),
+    # against the oracle's samples of the same law; determinism in (seed, call_index)
+    for G in (203, 512):
+        case_g = torch.Generator().manual_seed(3)
+        umis = torch.poisson(torch.rand(300, G, generator=case_g) * 8.0, generator=case_g)
+        s = 0.5 + 0.4 * torch.rand(300, 1, generator=case_g)
+        o = 0.1 * torch.rand(300, 1, generator=case_g)
+        torch.manual_seed(0)
+        r0, r1, _, _ = O.split_molecules(umis, s, 1 - s, o)
+        a = split_molecules(umis.to(dev), s.to(dev), (1 - s).to(dev), o.to(dev), seed=5, call_index=0)
+        b = split_molecules(umis.to(dev), s.to(dev), (1 - s).to(dev), o.to(dev), seed=5, call_index=0)
+        c = split_molecules(umis.to(dev), s.to(dev), (1 - s).to(dev), o.to(dev), seed=5, call_index=1)
+        x0, x1 = a[0].cpu(), a[1].cpu()
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and not torch.equal(a[0], c[0])
+        assert bool((x0 + x1 >= umis).all()) and bool((x0 <= umis).all()) and bool((x1 <= umis).all())
+        assert bool((x0[umis == 0] == 0).all()) and bool((x1[umis == 0] == 0).all())
+        tot = umis.sum().item()
+        for mine, ref in ((x0, r0), (x1, r1)):
+            assert abs(mine.sum().item() - ref.sum().item()) < 6 * np.sqrt(tot * 0.25) , (mine.sum(), ref.sum())
+        # overlap_factor = 0: an exact partition of the molecules
+        z = torch.zeros_like(o)
+        p0, p1_, _, _ = split_molecules(umis.to(dev), s.to(dev), (1 - s).to(dev), z.to(dev), seed=5, call_index=2)
+        assert torch.equal((p0 + p1_).cpu(), umis)
+
+
+def test_mcv_dataloader_feeds_the_mcv_step():
+    """MCVDataLoader mirror: a TensorDataset of (umis, split, complement, overlap) -> batches the MCVNBVAE step takes."""
+    import drvish_b200 as D
+    from drvish_b200.data import MCVDataLoader
+
+    g = torch.Generator().manual_seed(2)
+    n, G = 300, 256
+    umis = torch.poisson(torch.rand(n, G, generator=g) * 5.0, generator=g)
+    split = torch.full((n, 1), 0.9)
+    ds = torch.utils.data.TensorDataset(umis, split, 1 - split, torch.zeros(n, 1))
+    dl = MCVDataLoader(ds, batch_size=128, shuffle=False, seed=3)
+    model = D.MCVNBVAE(n_input=G, n_latent=4, layers=[32, 32]).cuda()
+    elbo = D.FusedTraceELBO(data_parallel=False)
+    sizes, first = [], []
+    for epoch in range(2):
+        for k, batch in enumerate(dl):
+            x0, x1, ls, lc = batch
+            assert x0.is_cuda and ls.shape == (x0.shape[0], 1)
+            if k == 0:
+                first.append(x0.clone())
+                assert torch.equal((x0 + x1).cpu(), umis[:128])
+            sizes.append(x0.shape[0])
+            loss = elbo.loss_and_grads(model.model, model.guide, *batch)
+            assert np.isfinite(loss)
+    assert sizes == [128, 128, 44] * 2
+    assert not torch.equal(first[0], first[1])  # a new split every iteration

@@ -174,3 +174,18 @@ def test_drnbvae_oracle_runs_and_guide_factor_sign():
                                      include_guide_factor=False)
     # factor (<=0) sits in the guide: ELBO -= factor, loss += factor
     assert loss <= loss_nf + 1e-4
+
+
+def test_split_molecules_matches_reference_golden(golden_dir):
+    """SURVEY 8f-3 loader: the restated binomial thinning is bit-identical to the reference's own
+    MCVDataLoader.split_molecules (train/mcv_train.py:20-40) under the same torch seed."""
+    from tests.parity import split_case
+
+    g = _load(golden_dir, "ref_split_molecules.npz")
+    umis, split, comp, overlap = split_case()
+    torch.manual_seed(5)
+    x0, x1, ls, lc = O.split_molecules(umis, split, comp, overlap)
+    assert np.array_equal(x0.numpy(), g["x0"]) and np.array_equal(x1.numpy(), g["x1"])
+    assert np.array_equal(ls.numpy(), g["log_split"]) and np.array_equal(lc.numpy(), g["log_split_complement"])
+    # invariants the CUDA kernel is tested on as well
+    assert bool(((x0 + x1) >= umis).all()) and bool((x0 <= umis).all()) and bool((x1 <= umis).all())
