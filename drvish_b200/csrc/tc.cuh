@@ -41,6 +41,9 @@ namespace drv {
 namespace tc {
 int gemm_tf32(const float* A, int lda, bool a_mn, const float* Bm, int ldb, bool b_mn, float* C, int ldc, int M, int N,
               int K, int max_ctas, bool accumulate, cudaStream_t st);
+// fp16 operands (kind::f16; same mantissa as tf32, half the bytes): C (+)= alpha A B^T
+int gemm_f16(const void* A, int lda, bool a_mn, const void* Bm, int ldb, bool b_mn, float* C, int ldc, int M, int N, int K,
+             int max_ctas, bool accumulate, float alpha, cudaStream_t st);
 // C = bias + sum of the k-part slabs in index order; with `stats` also the column sums / sums of squares
 // of C and (last CTA) mean / rstd / running buffers of the BatchNorm that consumes C.  Returns true
 // when the statistics were produced.

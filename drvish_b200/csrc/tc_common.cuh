@@ -13,7 +13,8 @@ namespace tc {
 // ---- host: tensor maps --------------------------------------------------------------------------
 // Encoded through the driver entry point obtained from the runtime (no link against libcuda).
 bool make_tensor_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                     const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box, int swizzle /* 0 none, 1 128B, 2 128B_ATOM_32B */);
+                     const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box, int swizzle /* 0 none, 1 128B, 2 128B_ATOM_32B */,
+                     bool f16 = false);
 
 // 2-D fp32 tensor [rows][cols] (cols contiguous), box = box_rows x box_cols, 128-byte swizzle.
 inline bool tmap_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
@@ -22,6 +23,15 @@ inline bool tmap_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t c
   uint64_t strides[1] = {ld_elems * sizeof(float)};
   uint32_t box[2] = {box_cols, box_rows};
   return make_tensor_map(m, base, 2, dims, strides, box, swizzle);
+}
+
+// 2-D fp16 tensor [rows][cols] (cols contiguous), 128-byte swizzle (rows of the box = 64 halfs = 128 B).
+inline bool tmap_2d_h(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows,
+                      uint32_t box_cols) {
+  uint64_t dims[2] = {cols, rows};
+  uint64_t strides[1] = {ld_elems * 2};
+  uint32_t box[2] = {box_cols, box_rows};
+  return make_tensor_map(m, base, 2, dims, strides, box, 1, true);
 }
 
 #ifdef __CUDACC__
@@ -126,6 +136,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// same with fp16 operands (kind::f16: 10-bit mantissa like tf32, half the bytes, twice the MMA rate)
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  uint32_t acc = accumulate ? 1u : 0u;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
 // arrive on an mbarrier once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -204,6 +223,17 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn, int b_mn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// fp16 A and B (format 0), fp32 accumulate
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+// two floats -> packed fp16 pair (lo = a, hi = b), round to nearest, saturating (no infinities)
+__device__ __forceinline__ uint32_t pack_h2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
 #endif  // __CUDACC__
 

@@ -17,7 +17,7 @@ namespace drv {
 namespace tc {
 
 bool make_tensor_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                     const uint32_t* box, int swizzle) {
+                     const uint32_t* box, int swizzle, bool f16) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -32,7 +32,7 @@ bool make_tensor_map(CUtensorMap* map, const void* base, int rank, const uint64_
   });
   if (!fn) return false;
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base),
+  CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base),
                   (const cuuint64_t*)dims, (const cuuint64_t*)strides_bytes, (const cuuint32_t*)box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
                   swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -72,14 +72,22 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 // loads HALF of every staged B tile and multicasts it into both CTAs' rings, so B is read from L2
 // once per pair.  The large backward GEMMs are bound by exactly that traffic (dAct: 39 k-blocks x
 // 64 KB per CTA x 128 CTAs = 320 MB through L2 in ~45 us; half of it is the shared B operand).
-template <bool A_MN, bool B_MN, int MT, int CL = 1>
+// H16: fp16 operands (kind::f16, same 10-bit mantissa as tf32): a k-block is 64 elements (still one
+// 128-byte swizzle row), an MN-major box 64 elements wide, UMMA_K = 16 - half the bytes and half the
+// pipeline hand-shakes per unit of K, twice the MMA rate.  alpha scales the result (exact power-of-two
+// rescaling of fp16 operands that were stored pre-scaled).
+template <bool A_MN, bool B_MN, int MT, int CL = 1, bool H16 = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
           const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, int n_pairs,
           float* __restrict__ C, int ldc, int M, int N, int K, int n_tile, int splits, int force_atomic,
-          const float* __restrict__ bias, long long part_stride, int mn_lbo, int mn_sbo, int mn_kstep) {
+          const float* __restrict__ bias, long long part_stride, int mn_lbo, int mn_sbo, int mn_kstep, float alpha) {
   pdl_prologue();
+  constexpr int BKE = H16 ? 64 : 32;                 // elements per k-block
+  constexpr int MNB = H16 ? 64 : 32;                 // M/N elements per MN-major box (128 bytes)
+  constexpr int MNBB = BKE * 128;                    // bytes of one MN-major box
+  constexpr uint32_t MN_LAYOUT = H16 ? 2 : 1;        // SWIZZLE_128B / SWIZZLE_128B with 32-byte atoms
   constexpr int TBM = MT * BM;                       // rows of the CTA tile
   constexpr int NSTG = MT == 1 ? STAGES : 3;
   constexpr int SA_BYTES = MT * A_BYTES;
@@ -95,7 +103,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   // the operand pairs are concatenated along a virtual K axis: sum_p A_p B_p^T accumulates in TMEM
-  const int kb_pair = (K + BK - 1) / BK;
+  const int kb_pair = (K + BKE - 1) / BKE;
   const int kb_total = kb_pair * n_pairs;
   const int m_tiles = (M + TBM - 1) / TBM, n_tiles = (N + n_tile - 1) / n_tile;
   // work = (group of CL M tiles, N tile, k-part) chunks: every tile's k range is cut into `splits`
@@ -130,7 +138,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      const uint32_t tx = SA_BYTES + (uint32_t)n_tile * BK * 4;
+      const uint32_t tx = SA_BYTES + (uint32_t)n_tile * 128;
       int i = 0;
       for (int ch = c0; ch < c1; ++ch) {
         const int tile = ch / splits, part = ch % splits;
@@ -143,26 +151,26 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           uint8_t* sb = sa + SA_BYTES;
           mbar_expect_tx(&full[s], tx);
           const int pair = kb / kb_pair;
-          const int k0 = (kb - pair * kb_pair) * BK;
+          const int k0 = (kb - pair * kb_pair) * BKE;
           const CUtensorMap* ma = pair == 0 ? &tmA : (pair == 1 ? &tmA1 : &tmA2);
           const CUtensorMap* mb = pair == 0 ? &tmB : (pair == 1 ? &tmB1 : &tmB2);
           if (A_MN) {
-            for (int j = 0; j < TBM / 32; ++j) tma_load_2d(sa + j * 4096, ma, &full[s], m0 + 32 * j, k0);
+            for (int j = 0; j < TBM / MNB; ++j) tma_load_2d(sa + j * MNBB, ma, &full[s], m0 + MNB * j, k0);
           } else {
             for (int j = 0; j < MT; ++j) tma_load_2d(sa + j * A_BYTES, ma, &full[s], k0, m0 + j * BM);
           }
           if (CL == 2) {
             // my half of the B tile, delivered to both CTAs of the pair (tmB's box is half a tile here)
             if (B_MN) {
-              const int nb = n_tile / 64;
+              const int nb = n_tile / (2 * MNB);
               for (int j = rank * nb; j < (rank + 1) * nb; ++j)
-                tma_load_2d_mc(sb + j * 4096, mb, &full[s], n0 + 32 * j, k0, (uint16_t)0x3);
+                tma_load_2d_mc(sb + j * MNBB, mb, &full[s], n0 + MNB * j, k0, (uint16_t)0x3);
             } else {
               const int half = n_tile / 2;
-              tma_load_2d_mc(sb + rank * half * BK * 4, mb, &full[s], k0, n0 + rank * half, (uint16_t)0x3);
+              tma_load_2d_mc(sb + rank * half * 128, mb, &full[s], k0, n0 + rank * half, (uint16_t)0x3);
             }
           } else if (B_MN) {
-            for (int j = 0; j < n_tile / 32; ++j) tma_load_2d(sb + j * 4096, mb, &full[s], n0 + 32 * j, k0);
+            for (int j = 0; j < n_tile / MNB; ++j) tma_load_2d(sb + j * MNBB, mb, &full[s], n0 + MNB * j, k0);
           } else {
             tma_load_2d(sb, mb, &full[s], k0, n0);
           }
@@ -172,7 +180,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
-      const uint32_t idesc = idesc_tf32(BM, n_tile, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      const uint32_t idesc = H16 ? idesc_f16(BM, n_tile, A_MN ? 1 : 0, B_MN ? 1 : 0) : idesc_tf32(BM, n_tile, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int i = 0, seg = 0;
       for (int ch = c0; ch < c1; ++ch, ++seg) {
         const int part = ch % splits;
@@ -189,12 +197,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           const uint32_t sb = sa + SA_BYTES;
 #pragma unroll
           for (int kk = 0; kk < BK / 8; ++kk) {
-            const uint64_t db = B_MN ? smem_desc(sb + kk * mn_kstep, mn_lbo, mn_sbo, 1) : smem_desc(sb + kk * 32, 16, 1024);
+            const uint64_t db = B_MN ? smem_desc(sb + kk * mn_kstep, mn_lbo, mn_sbo, MN_LAYOUT) : smem_desc(sb + kk * 32, 16, 1024);
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
               const uint32_t sam = sa + mt * A_BYTES;  // sub-tile mt: its own 128 rows (4 MN-major boxes)
-              const uint64_t da = A_MN ? smem_desc(sam + kk * mn_kstep, mn_lbo, mn_sbo, 1) : smem_desc(sam + kk * 32, 16, 1024);
-              umma_tf32(d_tmem + (uint32_t)(mt * MAXN), da, db, idesc, (kb != kb_b) || (kk != 0));
+              const uint64_t da = A_MN ? smem_desc(sam + kk * mn_kstep, mn_lbo, mn_sbo, MN_LAYOUT) : smem_desc(sam + kk * 32, 16, 1024);
+              if (H16) umma_f16(d_tmem + (uint32_t)(mt * MAXN), da, db, idesc, (kb != kb_b) || (kk != 0));
+              else umma_tf32(d_tmem + (uint32_t)(mt * MAXN), da, db, idesc, (kb != kb_b) || (kk != 0));
             }
           }
           if (CL == 2) umma_commit_mc(&empty[s], (uint16_t)0x3);  // ... in both CTAs: the peer multicasts into this stage too
@@ -223,6 +232,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         float v[16];
         tmem_ld16(tb + (uint32_t)c, v);
         tmem_ld_wait();
+        if (H16) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= alpha;
+        }
         if (m < M) {
           // part_stride != 0: deterministic split - every k-part stores into its own slab
           float* dst = C + (size_t)part * part_stride + (size_t)m * ldc + n0 + c;
@@ -373,24 +386,38 @@ static int n_sm_tc() {
 // (32 for an MN-major B).  n_pairs operand pairs (same shapes/strides) are summed: C = sum_p A_p B_p^T.
 // accumulate: add into the existing contents of C; otherwise C is overwritten (it is zeroed here
 // first when stream-K splits a tile over several CTAs).  max_ctas <= 0: one CTA per SM.
-int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs, int lda, bool a_mn, int ldb, bool b_mn,
-                    float* C, int ldc, int M, int N, int K, int max_ctas, bool accumulate, const float* bias,
-                    cudaStream_t st, int max_chain_kb, float* partials, int max_parts, const ColStatsOut* stats) {
+static int gemm_impl(bool h16, float alpha, int n_pairs, const void* const* As, const void* const* Bs, int lda, bool a_mn,
+                     int ldb, bool b_mn, float* C, int ldc, int M, int N, int K, int max_ctas, bool accumulate,
+                     const float* bias, cudaStream_t st, int max_chain_kb, float* partials, int max_parts,
+                     const ColStatsOut* stats) {
   if (n_pairs < 1 || n_pairs > 3) return -3;
   CUtensorMap ta[3], tb[3];
-  const int nq = b_mn ? 32 : 16;  // an MN-major B is staged in 32-column boxes
+  const int bke = h16 ? 64 : 32;   // elements per k-block
+  const int mnb = h16 ? 64 : 32;   // an MN-major operand is staged in boxes of 128 bytes of M/N elements
+  const int nq = b_mn ? mnb : 16;
   int n_tile = N >= MAXN ? MAXN : ((N + nq - 1) / nq) * nq;
   for (int p = 0; p < 3; ++p) {
     int q = p < n_pairs ? p : 0;
     bool ok;
-    if (a_mn) ok = tmap_2d(&ta[p], As[q], (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, 32, 2);
-    else ok = tmap_2d(&ta[p], As[q], (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK);
+    if (h16) {
+      if (a_mn) ok = tmap_2d_h(&ta[p], As[q], (uint64_t)K, (uint64_t)M, (uint64_t)lda, bke, mnb);
+      else ok = tmap_2d_h(&ta[p], As[q], (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, bke);
+      if (!ok) return -3;
+      if (b_mn) ok = tmap_2d_h(&tb[p], Bs[q], (uint64_t)K, (uint64_t)N, (uint64_t)ldb, bke, mnb);
+      else ok = tmap_2d_h(&tb[p], Bs[q], (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)n_tile, bke);
+      if (!ok) return -3;
+      continue;
+    }
+    if (a_mn) ok = tmap_2d(&ta[p], (const float*)As[q], (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, 32, 2);
+    else ok = tmap_2d(&ta[p], (const float*)As[q], (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK);
     if (!ok) return -3;
-    if (b_mn) ok = tmap_2d(&tb[p], Bs[q], (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, 32, 2);
-    else ok = tmap_2d(&tb[p], Bs[q], (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)n_tile, BK);
+    if (b_mn) ok = tmap_2d(&tb[p], (const float*)Bs[q], (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, 32, 2);
+    else ok = tmap_2d(&tb[p], (const float*)Bs[q], (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)n_tile, BK);
     if (!ok) return -3;
   }
-  const int kb_total = ((K + BK - 1) / BK) * n_pairs;
+  const int kb_total = ((K + bke - 1) / bke) * n_pairs;
+  // MN-major descriptor fields (bytes): stride between M/N boxes, between 8-row k groups, per UMMA_K
+  const int mn_lbo = h16 ? 8192 : g_mn_lbo, mn_sbo = h16 ? 1024 : g_mn_sbo, mn_kstep = h16 ? 2048 : g_mn_kstep;
   const int sms = max_ctas > 0 && max_ctas < n_sm_tc() ? max_ctas : n_sm_tc();
   // Candidate schedules: MT = 1 (128-row tiles) or MT = 2 (256-row tiles, 1.5x fewer operand bytes
   // per MMA but no accumulator double-buffering, so only for long k ranges), each with the k range
@@ -446,7 +473,7 @@ int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs,
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     launch_k_plain(kern, grid, NTHREADS, SMEM_BYTES, st, ta[0], tb[0], ta[1], tb[1], ta[2], tb[2], n_pairs, outp, out_ld, M, N, K, n_tile,
-                                             splits, force_atomic, kbias, part_stride, g_mn_lbo, g_mn_sbo, g_mn_kstep);
+                                             splits, force_atomic, kbias, part_stride, mn_lbo, mn_sbo, mn_kstep, alpha);
   };
   // Cluster-of-2 schedule for the large accumulate-mode GEMMs (256-row tiles, one operand pair): the
   // B tile is multicast across two M tiles.
@@ -455,9 +482,9 @@ int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs,
   // larger cluster / 2-CTA MMA variant exists.  DRV_CLUSTER_GEMM=1 enables it (parity-tested).
   static const bool no_cluster = getenv("DRV_CLUSTER_GEMM") == nullptr;
   const int m_tiles2 = (M + 2 * BM - 1) / (2 * BM);
-  if (!no_cluster && mt_sel == 2 && n_pairs == 1 && !deterministic && n_tile % 64 == 0 && m_tiles2 >= 2 && sms >= 2) {
+  if (!h16 && !no_cluster && mt_sel == 2 && n_pairs == 1 && !deterministic && n_tile % 64 == 0 && m_tiles2 >= 2 && sms >= 2) {
     if (!b_mn) {  // K-major B: the pair's halves are two boxes of n_tile / 2 rows
-      if (!tmap_2d(&tb[0], Bs[0], (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)(n_tile / 2), BK)) return -3;
+      if (!tmap_2d(&tb[0], (const float*)Bs[0], (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)(n_tile / 2), BK)) return -3;
     }
     const long long units = (long long)((m_tiles2 + 1) / 2) * ((N + n_tile - 1) / n_tile) * splits;
     const int n_cl = (int)(units < sms / 2 ? units : sms / 2);
@@ -476,7 +503,7 @@ int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs,
       cfg.attrs = at;
       cfg.numAttrs = 1;
       cudaLaunchKernelEx(&cfg, kern, ta[0], tb[0], ta[1], tb[1], ta[2], tb[2], n_pairs, outp, out_ld, M, N, K, n_tile, splits,
-                         force_atomic, kbias, part_stride, g_mn_lbo, g_mn_sbo, g_mn_kstep);
+                         force_atomic, kbias, part_stride, mn_lbo, mn_sbo, mn_kstep, alpha);
     };
     if (a_mn && b_mn) launch_cl(k_tc_gemm<true, true, 2, 2>);
     else if (a_mn) launch_cl(k_tc_gemm<true, false, 2, 2>);
@@ -485,7 +512,19 @@ int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs,
     note_launch();
     return 0;
   }
-  if (mt_sel == 1) {
+  if (h16) {
+    if (mt_sel == 1) {
+      if (a_mn && b_mn) launch(k_tc_gemm<true, true, 1, 1, true>);
+      else if (a_mn) launch(k_tc_gemm<true, false, 1, 1, true>);
+      else if (b_mn) launch(k_tc_gemm<false, true, 1, 1, true>);
+      else launch(k_tc_gemm<false, false, 1, 1, true>);
+    } else {
+      if (a_mn && b_mn) launch(k_tc_gemm<true, true, 2, 1, true>);
+      else if (a_mn) launch(k_tc_gemm<true, false, 2, 1, true>);
+      else if (b_mn) launch(k_tc_gemm<false, true, 2, 1, true>);
+      else launch(k_tc_gemm<false, false, 2, 1, true>);
+    }
+  } else if (mt_sel == 1) {
     if (a_mn && b_mn) launch(k_tc_gemm<true, true, 1>);
     else if (a_mn) launch(k_tc_gemm<true, false, 1>);
     else if (b_mn) launch(k_tc_gemm<false, true, 1>);
@@ -499,6 +538,22 @@ int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs,
   note_launch();
   if (deterministic && split) return reduce_parts(partials, splits, M, N, bias, C, ldc, st, stats) ? 1 : 0;
   return 0;
+}
+
+int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs, int lda, bool a_mn, int ldb, bool b_mn,
+                    float* C, int ldc, int M, int N, int K, int max_ctas, bool accumulate, const float* bias,
+                    cudaStream_t st, int max_chain_kb, float* partials, int max_parts, const ColStatsOut* stats) {
+  const void* a[3] = {As[0], n_pairs > 1 ? As[1] : nullptr, n_pairs > 2 ? As[2] : nullptr};
+  const void* b[3] = {Bs[0], n_pairs > 1 ? Bs[1] : nullptr, n_pairs > 2 ? Bs[2] : nullptr};
+  return gemm_impl(false, 1.f, n_pairs, a, b, lda, a_mn, ldb, b_mn, C, ldc, M, N, K, max_ctas, accumulate, bias, st,
+                   max_chain_kb, partials, max_parts, stats);
+}
+
+// fp16 operands (raw 16-bit storage; lda / ldb in elements, row strides multiples of 8), C += or = alpha A B^T
+int gemm_f16(const void* A, int lda, bool a_mn, const void* Bm, int ldb, bool b_mn, float* C, int ldc, int M, int N, int K,
+             int max_ctas, bool accumulate, float alpha, cudaStream_t st) {
+  return gemm_impl(true, alpha, 1, &A, &Bm, lda, a_mn, ldb, b_mn, C, ldc, M, N, K, max_ctas, accumulate, nullptr, st, 0,
+                   nullptr, 0, nullptr);
 }
 
 bool reduce_parts(const float* parts, int n_parts, int M, int N, const float* bias, float* C, int ldc, cudaStream_t st,
@@ -542,6 +597,18 @@ extern "C" int drv_test_tc_gemm(const float* A, int lda, int a_mn, const float* 
   drv::g_launches = 0;
   drv::g_err = cudaSuccess;
   int r = drv::tc::gemm_tf32(A, lda, a_mn != 0, B, ldb, b_mn != 0, C, ldc, M, N, K, splits, false, (cudaStream_t)stream);
+  if (r) return r;
+  cudaError_t e = drv::g_err;
+  drv::g_err = cudaSuccess;
+  return (int)e;
+}
+
+// Test hook: same with fp16 operands (tests/test_tc_gemm.py)
+extern "C" int drv_test_tc_gemm_h(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, float* C, int ldc,
+                                  int M, int N, int K, int splits, float alpha, void* stream) {
+  drv::g_launches = 0;
+  drv::g_err = cudaSuccess;
+  int r = drv::tc::gemm_f16(A, lda, a_mn != 0, B, ldb, b_mn != 0, C, ldc, M, N, K, splits, false, alpha, (cudaStream_t)stream);
   if (r) return r;
   cudaError_t e = drv::g_err;
   drv::g_err = cudaSuccess;
