@@ -14,6 +14,8 @@
 // Persistent CTAs (one per SM), 18 warps: 16 epilogue warps (4 per TMEM lane quarter, each a
 // 16-gene column slice), 1 TMA producer warp, 1 MMA-issuer warp.  Tiles: 128 cells x 64 genes
 // (x 2 halves = 128 accumulator columns), double-buffered in TMEM (256 columns).
+#include <cuda_fp16.h>
+#include <stdlib.h>
 #include <type_traits>
 
 #include "kernels.cuh"
@@ -44,6 +46,13 @@ constexpr int SMEM_SMALL = STAGES * STAGE_BYTES + 2 * X_BYTES + 1024 + 1024;
 static_assert(SMEM_SMALL >= 2 * STAGE_BYTES + 4 * X_BYTES + 1024 + 1024, "phase 3 layout");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
 constexpr int TMEM_COLS = 256;
+// fp16-operand variant (H16): act, W and d loss/d logits are stored as fp16 - the same 10-bit mantissa
+// as the tf32 operands they replace, half the bytes through HBM / L2 / shared memory, 64-element
+// k-blocks (half the pipeline hand-shakes) and twice the MMA rate.  d logits is stored divided by the
+// plate scale c and multiplied by DL_SCALE, so that its magnitude is that of the per-element count
+// residual whatever scale_factor is (fp16 range: |x - mu| up to 1e6 representable, values below 1e-3
+// keep 9.5e-7 absolute resolution); the backward GEMMs multiply by c / DL_SCALE (exact powers of two).
+constexpr float DL_SCALE = 0.0625f;
 
 // tcgen05 kind::tf32 TRUNCATES the low 13 mantissa bits of its fp32 operands, which biases every
 // product by ~2^-11; rounding the operands to nearest when they are produced keeps the error
@@ -109,7 +118,17 @@ __device__ __forceinline__ float combine_lse(const DecParams& p, int ct, int b) 
   return m + logf(acc);
 }
 
-template <int PHASE, bool WITH_A>
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int PHASE, bool WITH_A, bool H16>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtensorMap tmW,
       const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD,
@@ -125,9 +144,14 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
   // phase 1 moves TWO 32-float k-blocks per ring stage: the producer / MMA-thread hand-shake per stage,
   // not bytes or MMA time, is what bounds it (profiles/r01_notes.md), so fewer, fatter stages win
   constexpr int KG = PHASE == 1 ? 2 : 1;
-  constexpr int NST = PHASE == 3 ? 2 : (TSTORE ? 3 : (PHASE == 1 ? 3 : STAGES));
-  constexpr int XB = PHASE == 3 ? 2 * X_BYTES : (PHASE == 1 ? 0 : X_BYTES);  // phase 1 stages no count tile
+  // H16 phase 3: the staged ds' tile is fp16 (32 KB), which leaves room for a 4-deep operand ring
+  constexpr int NST = PHASE == 3 ? (H16 ? 4 : 2) : (TSTORE ? 3 : (PHASE == 1 ? 3 : STAGES));
+  constexpr int XB = PHASE == 3 ? (H16 ? X_BYTES : 2 * X_BYTES) : (PHASE == 1 ? 0 : X_BYTES);  // phase 1 stages no count tile
   constexpr int RB = (PHASE == 2 && WITH_A) ? X_BYTES : 0;
+  // H16 phase 2 (training): the fp16 ds' / drho tiles (16 KB each) have their own double buffer (rbuf); the
+  // count tile is released by the epilogue warps, the output buffer by the store warp (o_empty)
+  constexpr bool X_BY_STORE = TSTORE && !(H16 && PHASE == 2);
+  constexpr int BKE = H16 ? 64 : BK;  // operand elements per k-block (one 128-byte swizzle row)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* xbuf = smem + NST * KG * STAGE_BYTES;
@@ -139,7 +163,8 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
   uint64_t* x_full = acc_empty + 2;       // [2]
   uint64_t* x_empty = x_full + 2;         // [2]
   uint64_t* o_full = x_empty + 2;         // [2] output tile complete in shared memory (TSTORE)
-  uint32_t* tmem_slot = (uint32_t*)(o_full + 2);
+  uint64_t* o_empty = o_full + 2;         // [2] output tile read by the TMA store (H16 phase 2)
+  uint32_t* tmem_slot = (uint32_t*)(o_empty + 2);
   float* lgtab = (float*)(tmem_slot + 4);
   load_lgamma_table(lgtab, threadIdx.x);
 
@@ -150,7 +175,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
   const int n_tiles = n_gt * n_ct;
   const int t0 = (int)((long long)n_tiles * blockIdx.x / gridDim.x);
   const int t1 = (int)((long long)n_tiles * (blockIdx.x + 1) / gridDim.x);
-  const int nkb = p.h / BK;
+  const int nkb = (p.h + BKE - 1) / BKE;  // TMA zero-fills a partial last k-block
 
   if (warp == N_EPI_WARPS && lane == 0) {
     tma_prefetch_desc(&tmAct);
@@ -164,8 +189,9 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], N_EPI_WARPS);
       mbar_init(&x_full[s], 1);
-      mbar_init(&x_empty[s], TSTORE ? 1 : N_EPI_WARPS);  // TSTORE: released by the store warp
+      mbar_init(&x_empty[s], X_BY_STORE ? 1 : N_EPI_WARPS);  // released by the store warp / the epilogue warps
       mbar_init(&o_full[s], N_EPI_WARPS);
+      mbar_init(&o_empty[s], 1);
     }
     fence_barrier_init();
   }
@@ -191,9 +217,10 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
           const int xs = it & 1, xph = (it >> 1) & 1;
           swait(&x_empty[xs], xph ^ 1);
           mbar_expect_tx(&x_full[xs], XB);
+          constexpr int XW = (H16 && PHASE == 3) ? 64 : 32;  // elements per 128-byte box row
 #pragma unroll
           for (int j = 0; j < XB / (BM * 128); ++j)
-            tma_load_2d(xbuf + xs * XB + j * (BM * 128), &tmX, &x_full[xs], g0 + 32 * j, b0);
+            tma_load_2d(xbuf + xs * XB + j * (BM * 128), &tmX, &x_full[xs], g0 + XW * j, b0);
         }
         for (int kb = 0; kb < nkb; kb += KG, ++kit) {
           const int s = kit % NST, ph = (kit / NST) & 1;
@@ -202,9 +229,9 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
           mbar_expect_tx(&full[s], ng * STAGE_BYTES);
           for (int j = 0; j < ng; ++j) {
             uint8_t* sa = smem + (s * KG + j) * STAGE_BYTES;
-            tma_load_2d(sa, &tmAct, &full[s], (kb + j) * BK, b0);
-            if (PHASE != 2) tma_load_2d(sa + A_BYTES, &tmW, &full[s], (kb + j) * BK, g0);
-            else tma_load_3d(sa + A_BYTES, &tmW, &full[s], (kb + j) * BK, g0, 0);
+            tma_load_2d(sa, &tmAct, &full[s], (kb + j) * BKE, b0);
+            if (PHASE != 2) tma_load_2d(sa + A_BYTES, &tmW, &full[s], (kb + j) * BKE, g0);
+            else tma_load_3d(sa + A_BYTES, &tmW, &full[s], (kb + j) * BKE, g0, 0);
           }
         }
       }
@@ -212,7 +239,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
   } else if (warp == N_EPI_WARPS + 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = idesc_tf32(BM, 128, 0, 0);
+      const uint32_t idesc = H16 ? idesc_f16(BM, 128, 0, 0) : idesc_tf32(BM, 128, 0, 0);
       int kit = 0;
       for (int t = t0, it = 0; t < t1; ++t, ++it) {
         const int as = it & 1, aph = (it >> 1) & 1;
@@ -228,9 +255,12 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
             const uint32_t sa = smem_u32(smem + (s * KG + j) * STAGE_BYTES);
             const uint32_t sb = sa + A_BYTES;
 #pragma unroll
-            for (int kk = 0; kk < BK / 8; ++kk)
-              umma_tf32(d_tmem, smem_desc(sa + kk * 32, 16, 1024), smem_desc(sb + kk * 32, 16, 1024), idesc,
-                        (kb | j | kk) != 0);
+            for (int kk = 0; kk < BK / 8; ++kk) {  // 4 MMAs of 32 bytes of K per row (8 tf32 / 16 fp16 elements)
+              if (H16) umma_f16(d_tmem, smem_desc(sa + kk * 32, 16, 1024), smem_desc(sb + kk * 32, 16, 1024), idesc,
+                                (kb | j | kk) != 0);
+              else umma_tf32(d_tmem, smem_desc(sa + kk * 32, 16, 1024), smem_desc(sb + kk * 32, 16, 1024), idesc,
+                             (kb | j | kk) != 0);
+            }
           }
           umma_commit(&empty[s]);
         }
@@ -245,17 +275,24 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
         const int b0 = ct * BM, g0 = gt * TN;
         const int xs = it & 1, ph = (it >> 1) & 1;
         swait(&o_full[xs], ph);  // the writers fenced their generic-proxy stores (fence.proxy.async)
+        if (H16 && PHASE == 2) {
+          // one 128 x 64 fp16 box each: ds' (first 16 KB of the slot), drho (second 16 KB)
+          tma_store_2d(&tmD, rbuf + xs * RB, g0, b0);
+          tma_store_2d(&tmR, rbuf + xs * RB + BM * 128, g0, b0);
+        } else {
+          constexpr int XW = H16 ? 64 : 32;
 #pragma unroll
-        for (int j = 0; j < XB / (BM * 128); ++j)
-          tma_store_2d(&tmD, xbuf + xs * XB + j * (BM * 128), g0 + 32 * j, b0);
-        if (PHASE == 2) {
+          for (int j = 0; j < XB / (BM * 128); ++j)
+            tma_store_2d(&tmD, xbuf + xs * XB + j * (BM * 128), g0 + XW * j, b0);
+          if (PHASE == 2) {
 #pragma unroll
-          for (int j = 0; j < RB / (BM * 128); ++j)
-            tma_store_2d(&tmR, rbuf + xs * RB + j * (BM * 128), g0 + 32 * j, b0);
+            for (int j = 0; j < RB / (BM * 128); ++j)
+              tma_store_2d(&tmR, rbuf + xs * RB + j * (BM * 128), g0 + 32 * j, b0);
+          }
         }
         tma_store_commit();
         tma_store_wait_read0();      // shared memory may be refilled; the global writes complete asynchronously
-        mbar_arrive(&x_empty[xs]);
+        mbar_arrive(X_BY_STORE ? &x_empty[xs] : &o_empty[xs]);
       }
       tma_store_wait_all();
     }
@@ -360,6 +397,65 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
         // row r, 16-byte chunk g4 XOR-swizzled with r % 8)
         const int xs = it & 1, xph = (it >> 1) & 1;
         mbar_wait(&x_full[xs], xph);
+        if (H16) {
+          // staged ds' tile: fp16, pre-scaled by DL_SCALE / c; two boxes of 64 genes, this warp's 32 genes
+          // are the 16-byte chunks (cg & 1) * 4 + j of box cg / 2.  ds = ds' + DL_SCALE A[b] softmax(s), in place.
+          const float SA = DL_SCALE * asum_b, unscale = p.c * (1.f / DL_SCALE);
+          uint8_t* drow_h = xbuf + xs * XB + (cg >> 1) * (BM * 128) + r * 128;
+          float sv8_n[8];
+          tmem_ld8(tbase + cg * 32, sv8_n);
+          tmem_ld_wait();
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            float sv[8], bs[8], ds[8];
+#pragma unroll
+            for (int v = 0; v < 8; ++v) sv[v] = sv8_n[v];
+            if (j + 1 < 4) tmem_ld8(tbase + cg * 32 + (j + 1) * 8, sv8_n);
+            const int gq = gbase + 8 * j;  // G % 8 == 0 on this path: a group of 8 genes is all-valid or all-out
+            const bool gok = gq < p.G;
+            if (gok) {
+              const float4 f0 = __ldg(reinterpret_cast<const float4*>(p.bias + gq));
+              const float4 f1 = __ldg(reinterpret_cast<const float4*>(p.bias + gq + 4));
+              bs[0] = f0.x; bs[1] = f0.y; bs[2] = f0.z; bs[3] = f0.w; bs[4] = f1.x; bs[5] = f1.y; bs[6] = f1.z; bs[7] = f1.w;
+            } else {
+#pragma unroll
+              for (int v = 0; v < 8; ++v) bs[v] = 0.f;
+            }
+            uint4* cell = reinterpret_cast<uint4*>(drow_h + ((((cg & 1) * 4 + j) ^ (r & 7)) * 16));
+            const uint4 raw = *cell;
+            const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+            const bool ok = row_ok && gok;
+            uint32_t ow[4];
+#pragma unroll
+            for (int v2 = 0; v2 < 4; ++v2) {
+              const float2 d2 = __half22float2(*reinterpret_cast<const __half2*>(&rw[v2]));
+              const float p0 = ex2_approx((sv[2 * v2] + bs[2 * v2] - lse_b) * 1.4426950408889634f);
+              const float p1 = ex2_approx((sv[2 * v2 + 1] + bs[2 * v2 + 1] - lse_b) * 1.4426950408889634f);
+              ds[2 * v2] = ok ? __fmaf_rn(SA, p0, d2.x) : 0.f;
+              ds[2 * v2 + 1] = ok ? __fmaf_rn(SA, p1, d2.y) : 0.f;
+              ow[v2] = pack_h2_sat(ds[2 * v2], ds[2 * v2 + 1]);
+            }
+            *cell = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            {
+              float w0[4] = {ds[0], ds[1], ds[2], ds[3]}, w1[4] = {ds[4], ds[5], ds[6], ds[7]};
+              const int col = butterfly4(w0, lane);
+              butterfly4(w1, lane);
+              if (col >= 0 && gok) {
+                atomicAdd(&p.db[gq + col], w0[0] * unscale);
+                atomicAdd(&p.db[gq + 4 + col], w1[0] * unscale);
+              }
+            }
+            tmem_ld_wait();
+          }
+          fence_proxy_async();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&acc_empty[as]);
+            mbar_arrive(&o_full[xs]);
+          }
+          continue;
+        }
         uint8_t* drow_s = xbuf + xs * XB + cg * (BM * 128) + r * 128;
         float sv_n[4];
         tmem_ld4(tbase + cg * 32, sv_n);
@@ -408,6 +504,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
         // work is done once:  ds' = -c a (fp32, completed by phase 3),  drho = -c dLL/drho (final).
         const int xs = it & 1, xph = (it >> 1) & 1;
         mbar_wait(&x_full[xs], xph);
+        if (H16 && WITH_A) mbar_wait(&o_empty[xs], xph ^ 1);  // the TMA store of this slot's previous tile has read it
         const int gbase = g0 + cg * 16;
         const float lml = lib_b - lse_b;
         uint8_t* xrow = xbuf + xs * XB + (cg >> 1) * (BM * 128) + r * 128;
@@ -470,7 +567,21 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
               if (WITH_A) a_acc += e[v].a;
             }
           }
-          if (WITH_A) {
+          if (WITH_A && H16) {
+            // fp16 tiles, pre-scaled by DL_SCALE / c: 4 genes = 8 bytes of chunk 2 cg + g4 / 2 of this row
+            float dsp[4], drs[4], dr[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              dsp[v] = ok[v] ? -DL_SCALE * e[v].a : 0.f;
+              drs[v] = ok[v] ? -DL_SCALE * e[v].drho : 0.f;
+              dr[v] = ok[v] ? -p.c * e[v].drho : 0.f;
+            }
+            uint8_t* ocell = rbuf + xs * RB + r * 128 + (((2 * cg + (g4 >> 1)) ^ (r & 7)) * 16) + (g4 & 1) * 8;
+            *reinterpret_cast<uint2*>(ocell) = make_uint2(pack_h2_sat(dsp[0], dsp[1]), pack_h2_sat(dsp[2], dsp[3]));
+            *reinterpret_cast<uint2*>(ocell + BM * 128) = make_uint2(pack_h2_sat(drs[0], drs[1]), pack_h2_sat(drs[2], drs[3]));
+            const int col = butterfly4(dr, lane);
+            if (col >= 0 && (!MASKED || gq + col < p.G)) atomicAdd(&p.db[p.G + gq + col], dr[0]);
+          } else if (WITH_A) {
             float dsp[4], dr[4];
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
@@ -495,7 +606,8 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(&acc_empty[as]);
-          mbar_arrive(TSTORE ? &o_full[xs] : &x_empty[xs]);
+          if (TSTORE) mbar_arrive(&o_full[xs]);
+          if (!X_BY_STORE) mbar_arrive(&x_empty[xs]);
         }
       }
     }
@@ -514,12 +626,25 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
 }
 
 // act = relu(bn(U)) materialised once (B x h fp32, L2 resident) as the TMA-fed A operand
-__global__ void k_act(const float* __restrict__ U, int B, int h, BnParams bn, float* __restrict__ act) {
+__global__ void k_act(const float* __restrict__ U, int B, int h, BnParams bn, float* __restrict__ act,
+                      __half* __restrict__ act_h) {
   pdl_prologue();
   size_t n = (size_t)B * h;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     int col = (int)(i % h);
-    act[i] = rna_tf32(bn_relu(U[i], bn.mean[col], bn.rstd[col], bn.gamma[col], bn.beta[col]));
+    const float v = bn_relu(U[i], bn.mean[col], bn.rstd[col], bn.gamma[col], bn.beta[col]);
+    if (act_h) act_h[i] = __float2half_rn(v);
+    else act[i] = rna_tf32(v);
+  }
+}
+
+// fp16 copy of the last-layer weight (the MMA operand of the logits GEMM and of dAct)
+__global__ void k_to_half(const float* __restrict__ src, size_t n4, __half2* __restrict__ dst) {
+  pdl_prologue();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+    dst[2 * i] = __floats2half2_rn(v.x, v.y);
+    dst[2 * i + 1] = __floats2half2_rn(v.z, v.w);
   }
 }
 
@@ -528,6 +653,8 @@ struct Scratch {
   float* Wr;       // [2G][h] last-layer weight rounded to tf32
   float* part_m;   // [slots][B]
   float* part_s;
+  __half* act_h;   // [B][h]  fp16 operand copies (H16 path)
+  __half* W_h;     // [2G][h]
   size_t total;
 };
 
@@ -538,6 +665,7 @@ Scratch carve(void* base, int B, int G, int h) {
   size_t slots = (size_t)((G + 127) / 128) * 4;
   size_t a = take(4 * (size_t)B * h), pm = take(4 * slots * B), ps = take(4 * slots * B);
   size_t wr = take(4 * (size_t)2 * G * h);
+  size_t ah = take(2 * (size_t)B * h), wh = take(2 * (size_t)2 * G * h);
   s.total = o;
   if (base) {
     char* c = (char*)base;
@@ -545,6 +673,8 @@ Scratch carve(void* base, int B, int G, int h) {
     s.part_m = (float*)(c + pm);
     s.part_s = (float*)(c + ps);
     s.Wr = (float*)(c + wr);
+    s.act_h = (__half*)(c + ah);
+    s.W_h = (__half*)(c + wh);
   }
   return s;
 }
@@ -560,7 +690,22 @@ int sm_count() {
   return n;
 }
 
+// fp16 operands need 16-byte-aligned halves of d logits (G % 8) and a full 64-element k-block
+bool use_h16(const TcDecoderArgs& a) {
+  static const bool off = getenv("DRV_DEC_TF32") != nullptr;  // debug / A-B: the tf32-operand decoder
+  return !off && a.G % 8 == 0 && a.h >= 64;
+}
+
 bool make_maps(const TcDecoderArgs& a, const Scratch& s, CUtensorMap* act, CUtensorMap* w1, CUtensorMap* w3, CUtensorMap* x) {
+  if (use_h16(a)) {
+    if (!tmap_2d_h(act, s.act_h, a.B, a.h, a.h, BM, 64)) return false;
+    if (!tmap_2d_h(w1, s.W_h, a.G, a.h, a.h, 128, 64)) return false;
+    uint64_t dims[3] = {(uint64_t)a.h, (uint64_t)a.G, 2};
+    uint64_t strides[2] = {(uint64_t)a.h * 2, (uint64_t)a.G * a.h * 2};
+    uint32_t box[3] = {64, 64, 2};
+    if (!make_tensor_map(w3, s.W_h, 3, dims, strides, box, 1, true)) return false;
+    return tmap_2d(x, a.x, a.B, a.G, a.G, BM, 32);
+  }
   if (!tmap_2d(act, s.act, a.B, a.h, a.h, BM, BK)) return false;
   if (!tmap_2d(w1, a.W_hi, a.G, a.h, a.h, 128, BK)) return false;
   {
@@ -611,10 +756,18 @@ void tc_decoder_forward(const TcDecoderArgs& a, cudaStream_t st) {
     if (g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
     return;
   }
+  const bool h16 = use_h16(a);
   int blocks = (int)(((size_t)a.B * a.h + 255) / 256);
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  launch_k(k_act, blocks, 256, 0, st, a.U, a.B, a.h, a.bn, s.act);
+  launch_k(k_act, blocks, 256, 0, st, a.U, a.B, a.h, a.bn, s.act, h16 ? s.act_h : (__half*)nullptr);
   note_launch();
+  if (h16) {
+    const size_t n4 = (size_t)2 * a.G * a.h / 4;
+    int wb = (int)((n4 + 255) / 256);
+    if (wb > sm_count() * 8) wb = sm_count() * 8;
+    launch_k(k_to_half, wb, 256, 0, st, a.W, n4, reinterpret_cast<__half2*>(s.W_h));
+    note_launch();
+  }
   DecParams p{};
   p.B = a.B; p.G = a.G; p.h = a.h; p.bias = a.bias; p.lib = a.lib; p.rshift = a.rshift; p.eps = a.eps; p.c = a.c;
   p.part_m = s.part_m; p.part_s = s.part_s; p.ll = a.ll; p.asum = a.asum;
@@ -624,22 +777,32 @@ void tc_decoder_forward(const TcDecoderArgs& a, cudaStream_t st) {
   const int n_gt1 = (a.G + 127) / 128;
   set_lse_layout(p, n_ct, n_gt1);
   drv_internal_kmark(0, 0, st);
-  launch_dec(k_dec<1, false>, n_ct * n_gt1, tAct, tW1, tX, tX, tX, p, st);
+  if (h16) launch_dec(k_dec<1, false, true>, n_ct * n_gt1, tAct, tW1, tX, tX, tX, p, st);
+  else launch_dec(k_dec<1, false, false>, n_ct * n_gt1, tAct, tW1, tX, tX, tX, p, st);
   drv_internal_kmark(0, 1, st);
   // phase 2: NB log-likelihood row sums (ll / asum / db were zeroed at the start of the step)
   const int n_gt = (a.G + 63) / 64;
   drv_internal_kmark(1, 0, st);
   if (a.bwd) {
-    // scale / log_r halves of dlogits: [B][G] each, row stride 2G
+    // scale / log_r halves of dlogits: [B][G] each, row stride 2G (fp16 on the H16 path, same buffer)
     CUtensorMap tD, tR;
-    if (!tmap_2d(&tD, a.dlogits, a.B, a.G, 2 * (uint64_t)a.G, BM, 32) ||
-        !tmap_2d(&tR, a.dlogits + a.G, a.B, a.G, 2 * (uint64_t)a.G, BM, 32)) {
+    bool ok;
+    if (h16) {
+      const __half* dl = reinterpret_cast<const __half*>(a.dlogits);
+      ok = tmap_2d_h(&tD, dl, a.B, a.G, 2 * (uint64_t)a.G, BM, 64) && tmap_2d_h(&tR, dl + a.G, a.B, a.G, 2 * (uint64_t)a.G, BM, 64);
+    } else {
+      ok = tmap_2d(&tD, a.dlogits, a.B, a.G, 2 * (uint64_t)a.G, BM, 32) &&
+           tmap_2d(&tR, a.dlogits + a.G, a.B, a.G, 2 * (uint64_t)a.G, BM, 32);
+    }
+    if (!ok) {
       if (g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
       return;
     }
-    launch_dec(k_dec<2, true>, n_ct * n_gt, tAct, tW3, tX, tD, tR, p, st, SMEM_BYTES);
+    if (h16) launch_dec(k_dec<2, true, true>, n_ct * n_gt, tAct, tW3, tX, tD, tR, p, st, SMEM_BYTES);
+    else launch_dec(k_dec<2, true, false>, n_ct * n_gt, tAct, tW3, tX, tD, tR, p, st, SMEM_BYTES);
   } else {
-    launch_dec(k_dec<2, false>, n_ct * n_gt, tAct, tW3, tX, tX, tX, p, st);
+    if (h16) launch_dec(k_dec<2, false, true>, n_ct * n_gt, tAct, tW3, tX, tX, tX, p, st);
+    else launch_dec(k_dec<2, false, false>, n_ct * n_gt, tAct, tW3, tX, tX, tX, p, st);
   }
   drv_internal_kmark(1, 1, st);
   // the row sums LL[b] are folded into the loss by the step's last launch (finalize_step)
@@ -657,25 +820,32 @@ void tc_decoder_backward(const TcDecoderArgs& a, cudaStream_t st) {
   p.part_m = s.part_m; p.part_s = s.part_s; p.ll = a.ll; p.asum = a.asum; p.dlogits = a.dlogits; p.db = a.db;
   const int n_ct = (a.B + BM - 1) / BM, n_gt1 = (a.G + 127) / 128;
   set_lse_layout(p, n_ct, n_gt1);
+  const bool h16 = use_h16(a);
   CUtensorMap tD;  // scale half of dlogits: [B][G] with row stride 2G
-  if (!tmap_2d(&tD, a.dlogits, a.B, a.G, 2 * (uint64_t)a.G, BM, 32)) {
+  if (!(h16 ? tmap_2d_h(&tD, a.dlogits, a.B, a.G, 2 * (uint64_t)a.G, BM, 64)
+            : tmap_2d(&tD, a.dlogits, a.B, a.G, 2 * (uint64_t)a.G, BM, 32))) {
     if (g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
     return;
   }
   drv_internal_kmark(2, 0, st);
-  launch_dec(k_dec<3, true>, n_ct * n_gt1, tAct, tW1, tD, tD, tD, p, st);
+  if (h16) launch_dec(k_dec<3, true, true>, n_ct * n_gt1, tAct, tW1, tD, tD, tD, p, st);
+  else launch_dec(k_dec<3, true, false>, n_ct * n_gt1, tAct, tW1, tD, tD, tD, p, st);
   drv_internal_kmark(2, 1, st);
   // dW[j][i] = sum_b dlogits[b][j] act[b][i]   (both operands MN-major, K = cells)
   if (a.side) a.side->mark(st);
   // dAct[b][i] = sum_j dlogits[b][j] W[j][i]   (A K-major, B MN-major, K = 2G): critical path, submitted first
   drv_internal_kmark(3, 0, st);
-  int rc = gemm_tf32(a.dlogits, 2 * a.G, false, a.W_hi, a.h, true, a.dY, a.h, a.B, a.h, 2 * a.G, 0, /*accumulate (cleared at step start)=*/true, st);
+  const float alpha = a.c * (1.f / DL_SCALE);  // d logits is stored as DL_SCALE / c times its value
+  int rc = h16 ? gemm_f16(a.dlogits, 2 * a.G, false, s.W_h, a.h, true, a.dY, a.h, a.B, a.h, 2 * a.G, 0, true, alpha, st)
+               : gemm_tf32(a.dlogits, 2 * a.G, false, a.W_hi, a.h, true, a.dY, a.h, a.B, a.h, 2 * a.G, 0, /*accumulate (cleared at step start)=*/true, st);
   drv_internal_kmark(3, 1, st);
   // dW[j][i] = sum_b dlogits[b][j] act[b][i]   (both operands MN-major, K = cells): off the critical chain
   cudaStream_t ws = st;
   if (a.side) { a.side->attach(); ws = a.side->side; }
   drv_internal_kmark(4, 0, ws);
-  if (rc == 0) rc = gemm_tf32(a.dlogits, 2 * a.G, true, s.act, a.h, true, a.dW, a.h, 2 * a.G, a.h, a.B, 0, true, ws);
+  if (rc == 0)
+    rc = h16 ? gemm_f16(a.dlogits, 2 * a.G, true, s.act_h, a.h, true, a.dW, a.h, 2 * a.G, a.h, a.B, 0, true, alpha, ws)
+             : gemm_tf32(a.dlogits, 2 * a.G, true, s.act, a.h, true, a.dW, a.h, 2 * a.G, a.h, a.B, 0, true, ws);
   drv_internal_kmark(4, 1, ws);
   if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
   // the ReLU gate of dAct is applied by the BatchNorm backward kernels (block_backward)
