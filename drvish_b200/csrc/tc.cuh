@@ -42,8 +42,9 @@ namespace tc {
 int gemm_tf32(const float* A, int lda, bool a_mn, const float* Bm, int ldb, bool b_mn, float* C, int ldc, int M, int N,
               int K, int max_ctas, bool accumulate, cudaStream_t st);
 // fp16 operands (kind::f16; same mantissa as tf32, half the bytes): C (+)= alpha A B^T
+// alpha_dev: optional device float multiplied into alpha (dynamic operand scaling)
 int gemm_f16(const void* A, int lda, bool a_mn, const void* Bm, int ldb, bool b_mn, float* C, int ldc, int M, int N, int K,
-             int max_ctas, bool accumulate, float alpha, cudaStream_t st);
+             int max_ctas, bool accumulate, float alpha, cudaStream_t st, const float* alpha_dev = nullptr);
 // C = bias + sum of the k-part slabs in index order; with `stats` also the column sums / sums of squares
 // of C and (last CTA) mean / rstd / running buffers of the BatchNorm that consumes C.  Returns true
 // when the statistics were produced.
@@ -51,9 +52,13 @@ bool reduce_parts(const float* parts, int n_parts, int M, int N, const float* bi
                   const ColStatsOut* stats = nullptr);
 // Encoder-input Linear forward with the sqrt / BatchNorm / ReLU / hi-lo split prologue fused into the
 // GEMM (tc_encfwd.cu).  Writes V = relu(bn(sqrt(x))) W^T + b and the tf32 'hi' part of the activations.
+// h16: fp16 operands - w_hi / w_lo are the fp16 hi / scaled-lo parts from encfwd_split_weight_h16 and a_hi
+// receives the fp16 hi part of the activations.
 int encfwd_fused(const float* x, int B, int G, BnParams bn, const float* w_hi, const float* w_lo, int h,
                  const float* bias, float* V, float* a_hi, float* partials, int max_parts, cudaStream_t st,
-                 const ColStatsOut* stats = nullptr);  // returns 1 when `stats` were produced
+                 const ColStatsOut* stats = nullptr, bool h16 = false);  // returns 1 when `stats` were produced
+bool encfwd_h16_supported(int G, int h);
+void encfwd_split_weight_h16(const float* W, int h, int G, void* w_hi_h, void* w_lo_h, cudaStream_t st);
 // d gamma / d beta sums of the encoder's input BatchNorm from dH and W without materialising dA (tc_bn0grad.cu)
 int bn0grad_fused(const float* dH_r, const float* W_hi, const float* x, int B, int G, int h, BnParams bn, double* gacc,
                   cudaStream_t st);

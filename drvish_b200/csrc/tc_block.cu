@@ -9,6 +9,8 @@
 // accumulator (fp32) - error ~2^-22 per product, i.e. fp32-class.  The backward GEMMs
 // (dW = dH^T A, dA = dH W) tolerate single-pass tf32 and reuse A_hi / W_hi; dA is reduced to
 // the BatchNorm gradients (the input x is data, so no dX is needed).
+#include <cuda_fp16.h>
+
 #include "kernels.cuh"
 #include "tc.cuh"
 #include "tc_common.cuh"
@@ -51,6 +53,38 @@ __global__ void k_split_tf32(const float* __restrict__ src, size_t n, float* __r
     float h = rna_tf32(v);
     hi[i] = h;
     lo[i] = rna_tf32(v - h);
+  }
+}
+
+// fp16 copy of a gradient matrix whose magnitude is not known in advance (it scales with scale_factor):
+// k_absmax finds max |v| (bit pattern of a non-negative float orders like an unsigned integer),
+// k_to_half4_scaled multiplies by the power of two that brings the maximum into [2^10, 2^11) - exact, far
+// from fp16's overflow, the small entries well inside its normal range - and leaves the inverse for the
+// GEMM epilogue in scale_out[1].
+__global__ void k_absmax(const float* __restrict__ src, size_t n4, unsigned* __restrict__ amax_bits) {
+  pdl_prologue();
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = *(reinterpret_cast<const float4*>(src) + i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f && m < INFINITY) atomicMax(amax_bits, __float_as_uint(m));
+}
+
+__global__ void k_to_half4_scaled(const float* __restrict__ src, size_t n4, const unsigned* __restrict__ amax_bits,
+                                  __half2* __restrict__ dst, float* __restrict__ scale_out) {
+  pdl_prologue();
+  const unsigned bits = *amax_bits;
+  // 2^(10 - floor(log2(amax))): exponent field arithmetic, no rounding anywhere
+  const int e = (int)(bits >> 23) - 127;
+  const float scale = bits == 0u ? 1.f : __uint_as_float((unsigned)(127 + 10 - max(-100, min(100, e))) << 23);
+  if (blockIdx.x == 0 && threadIdx.x == 0) scale_out[1] = 1.f / scale;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = *(reinterpret_cast<const float4*>(src) + i);
+    dst[2 * i] = __floats2half2_rn(v.x * scale, v.y * scale);
+    dst[2 * i + 1] = __floats2half2_rn(v.z * scale, v.w * scale);
   }
 }
 
@@ -202,8 +236,16 @@ bool tc_block_forward(const TcBlockArgs& a, cudaStream_t st) {
   const size_t n = (size_t)a.B * a.din;
   if (a.sqrt_in && !a.no_fused_prologue) {
     // encoder input layer: sqrt / BatchNorm / ReLU / hi-lo split fused into the GEMM's producer side
-    int rc = tc::encfwd_fused(a.U, a.B, a.din, a.bn, a.W_hi, a.W_lo, a.dout, a.bias, a.V, s.a_hi, s.parts, kMaxParts, st,
-                              a.next_stats);
+    int rc;
+    if (tc::encfwd_h16_supported(a.din, a.dout)) {
+      // fp16 operands: the weight's fp16 hi / lo parts live in the (otherwise unused) w_hi / w_lo scratch
+      tc::encfwd_split_weight_h16(a.W, a.dout, a.din, s.w_hi, s.w_lo, st);
+      rc = tc::encfwd_fused(a.U, a.B, a.din, a.bn, s.w_hi, s.w_lo, a.dout, a.bias, a.V, s.a_hi, s.parts, kMaxParts, st,
+                            a.next_stats, true);
+    } else {
+      rc = tc::encfwd_fused(a.U, a.B, a.din, a.bn, a.W_hi, a.W_lo, a.dout, a.bias, a.V, s.a_hi, s.parts, kMaxParts, st,
+                            a.next_stats);
+    }
     if (rc < 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
     return rc == 1;
   }
@@ -251,7 +293,27 @@ void tc_block_backward(const TcBlockArgs& a, cudaStream_t st) {
   // dW[j][i] = sum_b dV[b][j] A[b][i]: both operands MN-major (K = cells): off the critical chain
   cudaStream_t ws = st;
   if (a.side) { a.side->attach(); ws = a.side->side; }
-  if (rc == 0) rc = tc::gemm_tf32(s.dh_r, a.dout, true, s.a_hi, a.din, true, a.dW, a.din, a.dout, a.din, a.B, 0, /*accumulate (cleared at step start)=*/true, ws);
+  if (rc == 0) {
+    if (a.sqrt_in && !a.no_fused_prologue && tc::encfwd_h16_supported(a.din, a.dout)) {
+      // the forward left the fp16 hi part of the activations in a_hi: dynamically scaled fp16 copy of dV
+      // (the a_lo scratch is free: [scale words | fp16 dV]), fp16 GEMM with the inverse scale as alpha
+      unsigned* amax = reinterpret_cast<unsigned*>(s.a_lo);
+      __half* dh_h = reinterpret_cast<__half*>(reinterpret_cast<char*>(s.a_lo) + 256);
+      const size_t n4 = nd / 4;  // dout % 8 == 0
+      int hb = (int)((n4 + 255) / 256);
+      if (hb > n_sm() * 4) hb = n_sm() * 4;
+      cudaMemsetAsync(amax, 0, 8, ws);
+      launch_k(k_absmax, hb, 256, 0, ws, s.dh_r, n4, amax);
+      note_launch();
+      launch_k(k_to_half4_scaled, hb, 256, 0, ws, s.dh_r, n4, amax, reinterpret_cast<__half2*>(dh_h),
+               reinterpret_cast<float*>(amax));
+      note_launch();
+      rc = tc::gemm_f16(dh_h, a.dout, true, s.a_hi, a.din, true, a.dW, a.din, a.dout, a.din, a.B, 0, true, 1.f, ws,
+                        reinterpret_cast<const float*>(amax) + 1);
+    } else {
+      rc = tc::gemm_tf32(s.dh_r, a.dout, true, s.a_hi, a.din, true, a.dW, a.din, a.dout, a.din, a.B, 0, /*accumulate (cleared at step start)=*/true, ws);
+    }
+  }
   if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
   if (a.dY || fused_bn0) return;  // (the ReLU gate is applied by the BatchNorm backward kernels)
   // reduce dA to the input-BatchNorm gradients (gate and xhat recomputed from sqrt(x))

@@ -12,6 +12,9 @@
 // -> empty (MMAs retired AND the hi-tile store has finished reading the stage).
 // Work = (cell tile, k-part) chunks; every k-part is stored to its own slab and the slabs are
 // summed in fixed order (deterministic; accumulation chains <= 32 k-blocks).
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
 #include "kernels.cuh"
 #include "tc.cuh"
 #include "tc_common.cuh"
@@ -40,6 +43,15 @@ __device__ __forceinline__ float rna_tf32_(float v) {
   return __uint_as_float(r);
 }
 
+// H16: the same 3-term split on fp16 operands (kind::f16).  hi = fp16(a), lo = fp16((a - hi) * 2^11): the
+// pair carries the 22 mantissa bits of the tf32 split, the 2^11 keeps the low part in fp16's normal range
+// and is taken out of the correction accumulator by the epilogue.  A k-block is 64 genes: two raw fp32
+// count boxes (32 KB) become the fp16 hi tile (over box 0) and lo tile (over box 1), W_hi / W_lo tiles are
+// 256 x 64 fp16 - half the operand bytes and ring hand-shakes per unit of K, twice the MMA rate; the hi
+// tile written back for the weight gradient is fp16 too (half the HBM bytes both ways).
+constexpr float LO_SCALE = 2048.f;
+
+template <bool H16>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWhi,
          const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CUtensorMap tmAhi, BnParams bn, int B, int G,
@@ -58,8 +70,9 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
   uint64_t* acc_empty = acc_full + 2; // [2]
   uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
 
+  constexpr int BKE = H16 ? 64 : BK;  // genes per k-block
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int kb_total = (G + BK - 1) / BK;
+  const int kb_total = (G + BKE - 1) / BKE;
   const int m_tiles = (B + BM - 1) / BM, n_tiles = (h + n_tile - 1) / n_tile;
   const long long chunks = (long long)m_tiles * n_tiles * splits;
   const int c0 = (int)(chunks * blockIdx.x / gridDim.x);
@@ -109,8 +122,9 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
         for (int kb = kb_b; kb < kb_e; ++kb, ++i) {
           const int s = i % XST, ph = (i / XST) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], X_BYTES);
-          tma_load_2d(xring + s * XSTAGE, &tmX, &full[s], kb * BK, m0);
+          mbar_expect_tx(&full[s], H16 ? 2 * X_BYTES : X_BYTES);
+          tma_load_2d(xring + s * XSTAGE, &tmX, &full[s], kb * BKE, m0);
+          if (H16) tma_load_2d(xring + s * XSTAGE + X_BYTES, &tmX, &full[s], kb * BKE + 32, m0);
         }
       }
     }
@@ -125,16 +139,16 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
         for (int kb = kb_b; kb < kb_e; ++kb, ++i) {
           const int s = i % WST, ph = (i / WST) & 1;
           mbar_wait(&wempty[s], ph ^ 1);
-          mbar_expect_tx(&wfull[s], 2 * (uint32_t)n_tile * BK * 4);
-          tma_load_2d(wring + s * WSTAGE, &tmWhi, &wfull[s], kb * BK, n0);
-          tma_load_2d(wring + s * WSTAGE + W_BYTES, &tmWlo, &wfull[s], kb * BK, n0);
+          mbar_expect_tx(&wfull[s], 2 * (uint32_t)n_tile * 128);
+          tma_load_2d(wring + s * WSTAGE, &tmWhi, &wfull[s], kb * BKE, n0);
+          tma_load_2d(wring + s * WSTAGE + W_BYTES, &tmWlo, &wfull[s], kb * BKE, n0);
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = idesc_tf32(BM, n_tile, 0, 0);
+      const uint32_t idesc = H16 ? idesc_f16(BM, n_tile, 0, 0) : idesc_tf32(BM, n_tile, 0, 0);
       int i = 0, seg = 0;
       for (int ch = c0; ch < c1; ++ch, ++seg) {
         int tile, part, kb_b, kb_e;
@@ -163,9 +177,12 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
             const uint32_t sb = pair == 1 ? wlo : whi;
             const uint32_t d_tmem = tmem_base + (uint32_t)(pair == 2 ? 0 : BN);
 #pragma unroll
-            for (int kk = 0; kk < BK / 8; ++kk)
-              umma_tf32(d_tmem, smem_desc(sa + kk * 32, 16, 1024), smem_desc(sb + kk * 32, 16, 1024), idesc,
-                        (kb != kb_b) || kk != 0 || pair == 1);
+            for (int kk = 0; kk < BK / 8; ++kk) {  // 4 steps of 32 bytes of K per row
+              if (H16) umma_f16(d_tmem, smem_desc(sa + kk * 32, 16, 1024), smem_desc(sb + kk * 32, 16, 1024), idesc,
+                                (kb != kb_b) || kk != 0 || pair == 1);
+              else umma_tf32(d_tmem, smem_desc(sa + kk * 32, 16, 1024), smem_desc(sb + kk * 32, 16, 1024), idesc,
+                             (kb != kb_b) || kk != 0 || pair == 1);
+            }
           }
           umma_commit(&empty[s]);
           umma_commit(&wempty[ws]);
@@ -194,9 +211,72 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
         mbar_wait(&full[s], ph);
         uint8_t* xt = xring + s * XSTAGE;
         uint8_t* lt = xt + X_BYTES;
-        const int k0 = kb * BK;
+        const int k0 = kb * BKE;
+        if (H16) {
+          // row t of both raw boxes (2 x 32 genes) -> fp16 hi row over box 0, fp16 lo row over box 1.  A
+          // thread owns its row in both boxes; box 1's raw row is read before the lo values of box 0's
+          // genes are written over it.
+          uint32_t lo_keep[16];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+          for (int half = 0; half < 2; ++half) {
+            float a[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 xv = *reinterpret_cast<const float4*>(xt + half * X_BYTES + t * 128 + ((c ^ (t & 7)) << 4));
+              a[4 * c] = xv.x; a[4 * c + 1] = xv.y; a[4 * c + 2] = xv.z; a[4 * c + 3] = xv.w;
+            }
+            if (half == 1) {
+              // box 1's row is in registers: the lo parts of genes 0..31 take its chunks 0..3
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(lt + t * 128 + ((j ^ (t & 7)) << 4)) =
+                    make_uint4(lo_keep[4 * j], lo_keep[4 * j + 1], lo_keep[4 * j + 2], lo_keep[4 * j + 3]);
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const int col = k0 + half * 32 + c * 4;
+              if (col + 4 <= G) {
+                const float4 mean = __ldg(reinterpret_cast<const float4*>(bn.mean + col));
+                const float4 rstd = __ldg(reinterpret_cast<const float4*>(bn.rstd + col));
+                const float4 gam = __ldg(reinterpret_cast<const float4*>(bn.gamma + col));
+                const float4 bet = __ldg(reinterpret_cast<const float4*>(bn.beta + col));
+                a[4 * c] = bn_relu(sqrt_count(a[4 * c]), mean.x, rstd.x, gam.x, bet.x);
+                a[4 * c + 1] = bn_relu(sqrt_count(a[4 * c + 1]), mean.y, rstd.y, gam.y, bet.y);
+                a[4 * c + 2] = bn_relu(sqrt_count(a[4 * c + 2]), mean.z, rstd.z, gam.z, bet.z);
+                a[4 * c + 3] = bn_relu(sqrt_count(a[4 * c + 3]), mean.w, rstd.w, gam.w, bet.w);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  a[4 * c + j] = (col + j < G) ? bn_relu(sqrt_count(a[4 * c + j]), bn.mean[col + j], bn.rstd[col + j],
+                                                         bn.gamma[col + j], bn.beta[col + j])
+                                               : 0.f;
+              }
+            }
+            // 8 genes -> one 16-byte chunk of hi and of lo
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int v = 0; v < 4; ++v) {
+                const float a0 = a[8 * j + 2 * v], a1 = a[8 * j + 2 * v + 1];
+                const __half2 hh = __floats2half2_rn(a0, a1);
+                const float2 hf = __half22float2(hh);
+                hw[v] = *reinterpret_cast<const uint32_t*>(&hh);
+                const __half2 ll = __floats2half2_rn((a0 - hf.x) * LO_SCALE, (a1 - hf.y) * LO_SCALE);
+                lw[v] = *reinterpret_cast<const uint32_t*>(&ll);
+              }
+              const int lc = half * 4 + j;  // logical 16-byte chunk of the 64-gene fp16 row
+              *reinterpret_cast<uint4*>(xt + t * 128 + ((lc ^ (t & 7)) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              if (half == 0) {
+                lo_keep[4 * j] = lw[0]; lo_keep[4 * j + 1] = lw[1]; lo_keep[4 * j + 2] = lw[2]; lo_keep[4 * j + 3] = lw[3];
+              } else {
+                *reinterpret_cast<uint4*>(lt + t * 128 + ((lc ^ (t & 7)) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < (H16 ? 0 : 8); ++c) {
           // logical 16-byte chunk c of row t lives at physical chunk c ^ (t % 8) (128-byte swizzle):
           // the 8 threads of a quarter-warp phase touch 8 different chunks -> conflict-free
           const int off = t * 128 + ((c ^ (t & 7)) << 4);
@@ -273,7 +353,7 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
           tmem_ld16(tb + (uint32_t)(BN + c), v2);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += v2[j];
+          for (int j = 0; j < 16; ++j) v[j] = H16 ? __fmaf_rn(v2[j], 1.f / LO_SCALE, v[j]) : v[j] + v2[j];
         } else {
           tmem_ld_wait();
         }
@@ -320,16 +400,48 @@ int sms() {
 
 }  // namespace
 
+// fp16 hi / scaled-lo split of the first Linear's weight ([h][G], once per step)
+__global__ void k_split_h16(const float* __restrict__ src, size_t n2, __half2* __restrict__ hi, __half2* __restrict__ lo) {
+  pdl_prologue();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(src) + i);
+    const __half2 hh = __floats2half2_rn(v.x, v.y);
+    const float2 hf = __half22float2(hh);
+    hi[i] = hh;
+    lo[i] = __floats2half2_rn((v.x - hf.x) * LO_SCALE, (v.y - hf.y) * LO_SCALE);
+  }
+}
+
+bool encfwd_h16_supported(int G, int h) {
+  static const bool off = getenv("DRV_ENC_TF32") != nullptr;  // debug / A-B: the tf32-operand kernel
+  return !off && G % 8 == 0 && G >= 64 && h % 8 == 0;
+}
+
+void encfwd_split_weight_h16(const float* W, int h, int G, void* w_hi_h, void* w_lo_h, cudaStream_t st) {
+  const size_t n2 = (size_t)h * G / 2;
+  int blocks = (int)((n2 + 255) / 256);
+  if (blocks > sms() * 8) blocks = sms() * 8;
+  launch_k(k_split_h16, blocks, 256, 0, st, W, n2, reinterpret_cast<__half2*>(w_hi_h), reinterpret_cast<__half2*>(w_lo_h));
+  note_launch();
+}
+
 int encfwd_fused(const float* x, int B, int G, BnParams bn, const float* w_hi, const float* w_lo, int h,
                  const float* bias, float* V, float* a_hi, float* partials, int max_parts, cudaStream_t st,
-                 const ColStatsOut* stats) {
+                 const ColStatsOut* stats, bool h16) {
   CUtensorMap tX, tWh, tWl, tA;
   const int n_tile = h >= BN ? BN : ((h + 15) / 16) * 16;
+  const int bke = h16 ? 64 : BK;
   if (!tmap_2d(&tX, x, B, G, G, BM, BK)) return -3;
-  if (!tmap_2d(&tWh, w_hi, h, G, G, (uint32_t)n_tile, BK)) return -3;
-  if (!tmap_2d(&tWl, w_lo, h, G, G, (uint32_t)n_tile, BK)) return -3;
-  if (!tmap_2d(&tA, a_hi, B, G, G, BM, BK)) return -3;
-  const int kb_total = (G + BK - 1) / BK;
+  if (h16) {  // w_hi / w_lo / a_hi are fp16 buffers
+    if (!tmap_2d_h(&tWh, w_hi, h, G, G, (uint32_t)n_tile, 64)) return -3;
+    if (!tmap_2d_h(&tWl, w_lo, h, G, G, (uint32_t)n_tile, 64)) return -3;
+    if (!tmap_2d_h(&tA, a_hi, B, G, G, BM, 64)) return -3;
+  } else {
+    if (!tmap_2d(&tWh, w_hi, h, G, G, (uint32_t)n_tile, BK)) return -3;
+    if (!tmap_2d(&tWl, w_lo, h, G, G, (uint32_t)n_tile, BK)) return -3;
+    if (!tmap_2d(&tA, a_hi, B, G, G, BM, BK)) return -3;
+  }
+  const int kb_total = (G + bke - 1) / bke;
   const long long tiles = (long long)((B + BM - 1) / BM) * ((h + n_tile - 1) / n_tile);
   // k-parts: minimise waves x k-blocks per chunk (chunks beyond a multiple of the SM count cost a
   // whole extra wave), with accumulation chains <= 20 k-blocks (240 MMA steps, bias ~1e-6, see
@@ -347,14 +459,15 @@ int encfwd_fused(const float* x, int B, int G, BnParams bn, const float* w_hi, c
   }
   const long long chunks = tiles * splits;
   const int grid = (int)(chunks < sms() ? chunks : sms());
-  cudaFuncSetAttribute(k_encfwd, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  auto kern = h16 ? k_encfwd<true> : k_encfwd<false>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (splits > 1) {
-    launch_k(k_encfwd, grid, NTHREADS, SMEM_BYTES, st, tX, tWh, tWl, tA, bn, B, G, h, n_tile, splits, partials,
-                                                 (long long)B * h, nullptr);
+    launch_k(kern, grid, NTHREADS, SMEM_BYTES, st, tX, tWh, tWl, tA, bn, B, G, h, n_tile, splits, partials,
+                                             (long long)B * h, (const float*)nullptr);
     note_launch();
     return reduce_parts(partials, splits, B, h, bias, V, h, st, stats) ? 1 : 0;
   } else {
-    launch_k(k_encfwd, grid, NTHREADS, SMEM_BYTES, st, tX, tWh, tWl, tA, bn, B, G, h, n_tile, 1, V, 0LL, bias);
+    launch_k(kern, grid, NTHREADS, SMEM_BYTES, st, tX, tWh, tWl, tA, bn, B, G, h, n_tile, 1, V, 0LL, bias);
     note_launch();
   }
   return 0;

@@ -82,7 +82,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
           const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, int n_pairs,
           float* __restrict__ C, int ldc, int M, int N, int K, int n_tile, int splits, int force_atomic,
-          const float* __restrict__ bias, long long part_stride, int mn_lbo, int mn_sbo, int mn_kstep, float alpha) {
+          const float* __restrict__ bias, long long part_stride, int mn_lbo, int mn_sbo, int mn_kstep, float alpha,
+          const float* __restrict__ alpha_dev) {
   pdl_prologue();
   constexpr int BKE = H16 ? 64 : 32;                 // elements per k-block
   constexpr int MNB = H16 ? 64 : 32;                 // M/N elements per MN-major box (128 bytes)
@@ -216,6 +217,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // ===== epilogue: TMEM -> registers -> global =====
     const int q = warp % 4;  // TMEM lane quarter this warp may access
     int seg = 0;
+    if (H16 && alpha_dev) alpha *= __ldcg(alpha_dev);  // written by an earlier kernel of the stream
     for (int ch = c0; ch < c1; ++ch, ++seg) {
       const int tile = ch / splits, part = ch % splits;
       const int m0 = (CL * (tile / n_tiles) + rank) * TBM, n0 = (tile % n_tiles) * n_tile;
@@ -386,7 +388,7 @@ static int n_sm_tc() {
 // (32 for an MN-major B).  n_pairs operand pairs (same shapes/strides) are summed: C = sum_p A_p B_p^T.
 // accumulate: add into the existing contents of C; otherwise C is overwritten (it is zeroed here
 // first when stream-K splits a tile over several CTAs).  max_ctas <= 0: one CTA per SM.
-static int gemm_impl(bool h16, float alpha, int n_pairs, const void* const* As, const void* const* Bs, int lda, bool a_mn,
+static int gemm_impl(bool h16, float alpha, const float* alpha_dev, int n_pairs, const void* const* As, const void* const* Bs, int lda, bool a_mn,
                      int ldb, bool b_mn, float* C, int ldc, int M, int N, int K, int max_ctas, bool accumulate,
                      const float* bias, cudaStream_t st, int max_chain_kb, float* partials, int max_parts,
                      const ColStatsOut* stats) {
@@ -473,7 +475,7 @@ static int gemm_impl(bool h16, float alpha, int n_pairs, const void* const* As, 
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     launch_k_plain(kern, grid, NTHREADS, SMEM_BYTES, st, ta[0], tb[0], ta[1], tb[1], ta[2], tb[2], n_pairs, outp, out_ld, M, N, K, n_tile,
-                                             splits, force_atomic, kbias, part_stride, mn_lbo, mn_sbo, mn_kstep, alpha);
+                                             splits, force_atomic, kbias, part_stride, mn_lbo, mn_sbo, mn_kstep, alpha, alpha_dev);
   };
   // Cluster-of-2 schedule for the large accumulate-mode GEMMs (256-row tiles, one operand pair): the
   // B tile is multicast across two M tiles.
@@ -503,7 +505,7 @@ static int gemm_impl(bool h16, float alpha, int n_pairs, const void* const* As, 
       cfg.attrs = at;
       cfg.numAttrs = 1;
       cudaLaunchKernelEx(&cfg, kern, ta[0], tb[0], ta[1], tb[1], ta[2], tb[2], n_pairs, outp, out_ld, M, N, K, n_tile, splits,
-                         force_atomic, kbias, part_stride, mn_lbo, mn_sbo, mn_kstep, alpha);
+                         force_atomic, kbias, part_stride, mn_lbo, mn_sbo, mn_kstep, alpha, alpha_dev);
     };
     if (a_mn && b_mn) launch_cl(k_tc_gemm<true, true, 2, 2>);
     else if (a_mn) launch_cl(k_tc_gemm<true, false, 2, 2>);
@@ -545,14 +547,14 @@ int gemm_tf32_multi(int n_pairs, const float* const* As, const float* const* Bs,
                     cudaStream_t st, int max_chain_kb, float* partials, int max_parts, const ColStatsOut* stats) {
   const void* a[3] = {As[0], n_pairs > 1 ? As[1] : nullptr, n_pairs > 2 ? As[2] : nullptr};
   const void* b[3] = {Bs[0], n_pairs > 1 ? Bs[1] : nullptr, n_pairs > 2 ? Bs[2] : nullptr};
-  return gemm_impl(false, 1.f, n_pairs, a, b, lda, a_mn, ldb, b_mn, C, ldc, M, N, K, max_ctas, accumulate, bias, st,
+  return gemm_impl(false, 1.f, nullptr, n_pairs, a, b, lda, a_mn, ldb, b_mn, C, ldc, M, N, K, max_ctas, accumulate, bias, st,
                    max_chain_kb, partials, max_parts, stats);
 }
 
 // fp16 operands (raw 16-bit storage; lda / ldb in elements, row strides multiples of 8), C += or = alpha A B^T
 int gemm_f16(const void* A, int lda, bool a_mn, const void* Bm, int ldb, bool b_mn, float* C, int ldc, int M, int N, int K,
-             int max_ctas, bool accumulate, float alpha, cudaStream_t st) {
-  return gemm_impl(true, alpha, 1, &A, &Bm, lda, a_mn, ldb, b_mn, C, ldc, M, N, K, max_ctas, accumulate, nullptr, st, 0,
+             int max_ctas, bool accumulate, float alpha, cudaStream_t st, const float* alpha_dev) {
+  return gemm_impl(true, alpha, alpha_dev, 1, &A, &Bm, lda, a_mn, ldb, b_mn, C, ldc, M, N, K, max_ctas, accumulate, nullptr, st, 0,
                    nullptr, 0, nullptr);
 }
 
