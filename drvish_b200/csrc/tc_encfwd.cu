@@ -7,7 +7,8 @@
 // the B operand of the weight-gradient GEMM in the backward.  Compared with materialising A_hi /
 // A_lo first (prep kernel + 3 operand passes) this removes 2/3 of the HBM traffic of the layer.
 //
-// Warp roles (10 warps): 0 TMA producer, 1 TMEM alloc + MMA issuer, 2-5 transform, 6-9 epilogue.
+// Warp roles: 0 TMA producer, 1 TMEM alloc + MMA issuer, 2-9 transform (tf32 variant: 2-5), 10-13 epilogue,
+// 14 weight-tile TMA producer.
 // Pipeline barriers per stage: full (TMA landed) -> ready (tile transformed, async-proxy fenced)
 // -> empty (MMAs retired AND the hi-tile store has finished reading the stage).
 // Work = (cell tile, k-part) chunks; every k-part is stored to its own slab and the slabs are
@@ -34,7 +35,11 @@ constexpr int W_BYTES = BN * BK * 4;        // 32 KB
 constexpr int XSTAGE = 2 * X_BYTES;         // x/hi, lo
 constexpr int WSTAGE = 2 * W_BYTES;         // W_hi, W_lo
 constexpr int SMEM_BYTES = XST * XSTAGE + WST * WSTAGE + 1024 + 256;
-constexpr int NTHREADS = 352;
+// H16: TG thread groups of 128 threads share a tile row (64 / TG genes each): the transform pass, not the
+// MMA or the loads, bounded the kernel with 4 warps (86 us), 8 warps gave 66 us
+constexpr int TG = 4;
+constexpr int TW = 4 * TG;               // transform warps (H16); the tf32 variant uses the first 4
+constexpr int NTHREADS = (TW + 7) * 32;  // warps: 0 x-TMA, 1 MMA, 2..2+TW-1 transform, then 4 epilogue, 1 W-TMA
 constexpr int TMEM_COLS = 512;
 
 __device__ __forceinline__ float rna_tf32_(float v) {
@@ -85,7 +90,7 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
     tma_prefetch_desc(&tmAhi);
     for (int s = 0; s < XST; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&ready[s], 4);   // one arrival per transform warp
+      mbar_init(&ready[s], H16 ? TW : 4);   // one arrival per transform warp
       mbar_init(&empty[s], 2);   // tcgen05.commit + hi-tile store drained
     }
     for (int s = 0; s < WST; ++s) {
@@ -128,7 +133,7 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
         }
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == TW + 6) {
     // ===== TMA producer: weight tiles =====
     if (lane == 0) {
       int i = 0;
@@ -190,9 +195,13 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
         umma_commit(&acc_full[0]);
       }
     }
-  } else if (warp >= 2 && warp < 6) {
+  } else if (warp >= 2 && warp < (H16 ? 2 + TW : 6)) {
     // ===== transform warps: x tile -> (hi, lo) of relu(bn(sqrt(x))) in place =====
-    const int t = (warp - 2) * 32 + lane;  // row of the tile
+    const int tid = (warp - 2) * 32 + lane;
+    const int t = tid % 128;      // row of the tile
+    const int tg = tid / 128;     // H16: which 64 / TG genes of the row this thread converts
+    constexpr int NTR = H16 ? 128 * TG : 128;
+    constexpr int GPT = 64 / TG;  // genes per thread
     int i = 0;
     int pending_store_stage = -1;
     for (int ch = c0; ch < c1; ++ch) {
@@ -202,7 +211,7 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
       const bool store_hi = (tile % n_tiles) == 0;
       for (int kb = kb_b; kb < kb_e; ++kb, ++i) {
         const int s = i % XST, ph = (i / XST) & 1;
-        if (t == 0 && pending_store_stage >= 0) {
+        if (tid == 0 && pending_store_stage >= 0) {
           // the previous hi-tile store has finished reading its stage: release it
           tma_store_wait_read0();
           mbar_arrive(&empty[pending_store_stage]);
@@ -213,66 +222,53 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
         uint8_t* lt = xt + X_BYTES;
         const int k0 = kb * BKE;
         if (H16) {
-          // row t of both raw boxes (2 x 32 genes) -> fp16 hi row over box 0, fp16 lo row over box 1.  A
-          // thread owns its row in both boxes; box 1's raw row is read before the lo values of box 0's
-          // genes are written over it.
-          uint32_t lo_keep[16];
+          // thread (tg, t): GPT genes of row t -> GPT / 8 chunks of the fp16 hi row (tile over raw box 0) and of
+          // the fp16 lo row (tile over raw box 1).  Outputs land where other threads' raw values live, so
+          // every raw value is in registers (barrier) before anything is written.
+          float a[GPT];
+          const int box = (tg * GPT) / 32, rc0 = ((tg * GPT) % 32) / 4;  // raw box, first raw 16-byte chunk
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            float a[32];
+          for (int c = 0; c < GPT / 4; ++c) {
+            const float4 xv = *reinterpret_cast<const float4*>(xt + box * X_BYTES + t * 128 + (((rc0 + c) ^ (t & 7)) << 4));
+            a[4 * c] = xv.x; a[4 * c + 1] = xv.y; a[4 * c + 2] = xv.z; a[4 * c + 3] = xv.w;
+          }
+          named_bar_sync(2, NTR);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float4 xv = *reinterpret_cast<const float4*>(xt + half * X_BYTES + t * 128 + ((c ^ (t & 7)) << 4));
-              a[4 * c] = xv.x; a[4 * c + 1] = xv.y; a[4 * c + 2] = xv.z; a[4 * c + 3] = xv.w;
-            }
-            if (half == 1) {
-              // box 1's row is in registers: the lo parts of genes 0..31 take its chunks 0..3
+          for (int c = 0; c < GPT / 4; ++c) {
+            const int col = k0 + tg * GPT + c * 4;
+            if (col + 4 <= G) {
+              const float4 mean = __ldg(reinterpret_cast<const float4*>(bn.mean + col));
+              const float4 rstd = __ldg(reinterpret_cast<const float4*>(bn.rstd + col));
+              const float4 gam = __ldg(reinterpret_cast<const float4*>(bn.gamma + col));
+              const float4 bet = __ldg(reinterpret_cast<const float4*>(bn.beta + col));
+              a[4 * c] = bn_relu(sqrt_count(a[4 * c]), mean.x, rstd.x, gam.x, bet.x);
+              a[4 * c + 1] = bn_relu(sqrt_count(a[4 * c + 1]), mean.y, rstd.y, gam.y, bet.y);
+              a[4 * c + 2] = bn_relu(sqrt_count(a[4 * c + 2]), mean.z, rstd.z, gam.z, bet.z);
+              a[4 * c + 3] = bn_relu(sqrt_count(a[4 * c + 3]), mean.w, rstd.w, gam.w, bet.w);
+            } else {
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<uint4*>(lt + t * 128 + ((j ^ (t & 7)) << 4)) =
-                    make_uint4(lo_keep[4 * j], lo_keep[4 * j + 1], lo_keep[4 * j + 2], lo_keep[4 * j + 3]);
+                a[4 * c + j] = (col + j < G) ? bn_relu(sqrt_count(a[4 * c + j]), bn.mean[col + j], bn.rstd[col + j],
+                                                       bn.gamma[col + j], bn.beta[col + j])
+                                             : 0.f;
             }
+          }
+          // 8 genes -> one 16-byte chunk of hi and of lo
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const int col = k0 + half * 32 + c * 4;
-              if (col + 4 <= G) {
-                const float4 mean = __ldg(reinterpret_cast<const float4*>(bn.mean + col));
-                const float4 rstd = __ldg(reinterpret_cast<const float4*>(bn.rstd + col));
-                const float4 gam = __ldg(reinterpret_cast<const float4*>(bn.gamma + col));
-                const float4 bet = __ldg(reinterpret_cast<const float4*>(bn.beta + col));
-                a[4 * c] = bn_relu(sqrt_count(a[4 * c]), mean.x, rstd.x, gam.x, bet.x);
-                a[4 * c + 1] = bn_relu(sqrt_count(a[4 * c + 1]), mean.y, rstd.y, gam.y, bet.y);
-                a[4 * c + 2] = bn_relu(sqrt_count(a[4 * c + 2]), mean.z, rstd.z, gam.z, bet.z);
-                a[4 * c + 3] = bn_relu(sqrt_count(a[4 * c + 3]), mean.w, rstd.w, gam.w, bet.w);
-              } else {
+          for (int j = 0; j < GPT / 8; ++j) {
+            uint32_t hw[4], lw[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  a[4 * c + j] = (col + j < G) ? bn_relu(sqrt_count(a[4 * c + j]), bn.mean[col + j], bn.rstd[col + j],
-                                                         bn.gamma[col + j], bn.beta[col + j])
-                                               : 0.f;
-              }
+            for (int v = 0; v < 4; ++v) {
+              const float a0 = a[8 * j + 2 * v], a1 = a[8 * j + 2 * v + 1];
+              const __half2 hh = __floats2half2_rn(a0, a1);
+              const float2 hf = __half22float2(hh);
+              hw[v] = *reinterpret_cast<const uint32_t*>(&hh);
+              const __half2 ll = __floats2half2_rn((a0 - hf.x) * LO_SCALE, (a1 - hf.y) * LO_SCALE);
+              lw[v] = *reinterpret_cast<const uint32_t*>(&ll);
             }
-            // 8 genes -> one 16-byte chunk of hi and of lo
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint32_t hw[4], lw[4];
-#pragma unroll
-              for (int v = 0; v < 4; ++v) {
-                const float a0 = a[8 * j + 2 * v], a1 = a[8 * j + 2 * v + 1];
-                const __half2 hh = __floats2half2_rn(a0, a1);
-                const float2 hf = __half22float2(hh);
-                hw[v] = *reinterpret_cast<const uint32_t*>(&hh);
-                const __half2 ll = __floats2half2_rn((a0 - hf.x) * LO_SCALE, (a1 - hf.y) * LO_SCALE);
-                lw[v] = *reinterpret_cast<const uint32_t*>(&ll);
-              }
-              const int lc = half * 4 + j;  // logical 16-byte chunk of the 64-gene fp16 row
-              *reinterpret_cast<uint4*>(xt + t * 128 + ((lc ^ (t & 7)) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-              if (half == 0) {
-                lo_keep[4 * j] = lw[0]; lo_keep[4 * j + 1] = lw[1]; lo_keep[4 * j + 2] = lw[2]; lo_keep[4 * j + 3] = lw[3];
-              } else {
-                *reinterpret_cast<uint4*>(lt + t * 128 + ((lc ^ (t & 7)) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-              }
-            }
+            const int lc = tg * (GPT / 8) + j;  // logical 16-byte chunk of the 64-gene fp16 row
+            *reinterpret_cast<uint4*>(xt + t * 128 + ((lc ^ (t & 7)) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(lt + t * 128 + ((lc ^ (t & 7)) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
           }
         }
 #pragma unroll
@@ -310,8 +306,8 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
           *reinterpret_cast<float4*>(lt + off) = make_float4(lv[0], lv[1], lv[2], lv[3]);
         }
         fence_proxy_async();        // generic-proxy writes -> visible to tcgen05.mma / TMA store
-        named_bar_sync(1, 128);     // the whole tile is transformed
-        if (t == 0) {
+        named_bar_sync(1, NTR);     // the whole tile is transformed
+        if (tid == 0) {
           if (store_hi) {
             tma_store_2d(&tmAhi, xt, k0, m0);
             tma_store_commit();
@@ -324,14 +320,14 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
         if (lane == 0) mbar_arrive(&ready[s]);
       }
     }
-    if (t == 0) {
+    if (tid == 0) {
       if (pending_store_stage >= 0) {
         tma_store_wait_read0();
         mbar_arrive(&empty[pending_store_stage]);
       }
       tma_store_wait_all();  // global writes of the hi tiles complete before the kernel ends
     }
-  } else if (warp >= 6 && warp < 10) {
+  } else if (warp >= TW + 2 && warp < TW + 6) {
     // ===== epilogue: TMEM -> slab of this k-part =====
     const int q = warp % 4;
     int seg = 0;
