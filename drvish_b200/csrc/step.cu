@@ -215,6 +215,7 @@ struct Ctx {
   float* bnbuf;
   cudaStream_t st;
   SideStream* side;  // may be null: everything then runs on st
+  bool enc0_w_prepared = false;  // fp16 weight parts of the encoder input block were produced at the start of the step
   template <class T> T* at(size_t off) const { return reinterpret_cast<T*>(ws + off); }
   BnParams bn(int s, int k) const {
     const Block& b = s == 0 ? n.enc[k] : n.dec[k];
@@ -244,6 +245,7 @@ bool block_forward(const Ctx& c, int s, int k, const float* U0, bool do_linear, 
     a.W_hi = c.at<float>(c.p.p_hi) + b.W; a.W_lo = c.at<float>(c.p.p_lo) + b.W;
     a.B = B; a.din = b.din; a.dout = b.dout; a.V = c.at<float>(c.p.V[s][k]); a.scratch = c.ws + c.p.tcb[s][k];
     a.no_fused_prologue = (c.hp.flags & 512) != 0;
+    a.w_prepared = sq && c.enc0_w_prepared;
     ColStatsOut ns{};
     const int n_blocks = c.n.n_blocks;
     if (k + 1 < n_blocks && !(c.hp.flags & 1024)) {  // 1024 (debug): separate statistics kernels
@@ -438,7 +440,7 @@ static int elbo_step_impl(const drv_dims* dims, const drv_hparams* hp, const flo
   // tensor-core kernels take pre-rounded operands: kind::tf32 truncates).
   const bool tc_any = !(hp->flags & DRV_FLAG_FORCE_SIMT);
   const bool dec_tc = tc_decoder_supported(d, *hp) && !(hp->flags & 16);
-  bool enc_sd0 = false;
+  bool enc_sd0 = false, dec_w_prepared = false;
   {
     cudaStream_t ss = st;
     if (side) { side->fork(st); ss = side->side; }
@@ -446,6 +448,12 @@ static int elbo_step_impl(const drv_dims* dims, const drv_hparams* hp, const flo
     // encoder weights first: they are all the encoder forward waits for
     const size_t enc_floats = (size_t)n.dec[0].gamma;
     if (tc_any) split_params_tf32(params, enc_floats, c.at<float>(p.p_hi), c.at<float>(p.p_lo), ss);
+    if (side && p.tcb[0][0] && tc_block_forward_supported(B, n.enc[0].din, n.enc[0].dout, *hp) && !(hp->flags & 32)) {
+      TcBlockArgs a{};  // fp16 hi / lo parts of the encoder input weight, next to the tf32 split
+      a.sqrt_in = true; a.no_fused_prologue = (hp->flags & 512) != 0; a.W = params + n.enc[0].W;
+      a.B = B; a.din = n.enc[0].din; a.dout = n.enc[0].dout; a.scratch = c.ws + p.tcb[0][0];
+      c.enc0_w_prepared = tc_block_prepare(a, ss);
+    }
     bool enc_sd_ = false;
     if (side) {
       block_forward(c, 0, 0, x, false);  // statistics of x (main stream) overlap the side-stream work
@@ -456,6 +464,11 @@ static int elbo_step_impl(const drv_dims* dims, const drv_hparams* hp, const flo
     if (tc_any)
       split_params_tf32(params + enc_floats, (size_t)n.n_param_floats - enc_floats, c.at<float>(p.p_hi) + enc_floats,
                         c.at<float>(p.p_lo) + enc_floats, ss);
+    if (side && dec_tc) {
+      TcDecoderArgs a{};  // fp16 copy of the last decoder weight (joined before the decoder starts)
+      a.W = params + n.dec[NB - 1].W; a.B = B; a.G = G; a.h = n.dec[NB - 1].din; a.scratch = c.ws + p.tc;
+      dec_w_prepared = tc_decoder_prepare(a, ss);
+    }
     if (bwd) {
       cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)n.n_param_floats, ss);
       // d loss / d (last decoder activation): split-K accumulation target of the fused decoder backward
@@ -522,7 +535,7 @@ static int elbo_step_impl(const drv_dims* dims, const drv_hparams* hp, const flo
     ta.U = c.at<float>(p.V[1][NB - 2]); ta.bn = c.bn(1, NB - 1); ta.W = params + last.W; ta.W_hi = c.at<float>(p.p_hi) + last.W; ta.bias = params + last.bias;
     ta.x = x_lik; ta.rshift = rshift; ta.lib = l; ta.B = B; ta.G = G; ta.h = last.din; ta.eps = hp->epsilon; ta.c = hp->scale_factor;
     ta.lse = c.at<float>(p.lse); ta.ll = c.at<float>(p.ll); ta.asum = c.at<float>(p.asum); ta.out = out;
-    ta.scratch = c.ws + p.tc; ta.dlogits = dlogits; ta.bwd = bwd;
+    ta.scratch = c.ws + p.tc; ta.dlogits = dlogits; ta.bwd = bwd; ta.w_prepared = dec_w_prepared;
     ta.dW = bwd ? grads + last.W : nullptr; ta.db = bwd ? grads + last.bias : nullptr;
     ta.dY = c.at<float>(p.Gb[1][NB - 1]);
     tc_decoder_forward(ta, st);

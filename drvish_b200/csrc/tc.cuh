@@ -26,11 +26,15 @@ struct TcDecoderArgs {
   SideStream* side;   // optional: weight-gradient GEMM runs there
   const ColStatsOut* next_stats;  // optional: BatchNorm statistics of V for the next block
   bool dv_prepared;   // backward: the tf32-rounded dV and the bias gradient were already produced (bn_bwd_apply_round)
+  bool w_prepared;    // tc_decoder_prepare already left the fp16 copy of W in the scratch
 };
 // where tc_block_backward expects the tf32-rounded dV of a block ([B][dout])
 float* tc_block_rounded_dv(void* scratch, int B, int din, int dout);
 
 size_t tc_workspace_bytes(const drv_dims& d);
+// Start-of-step work that only depends on the parameters (fp16 copy of W; needs W, G, h, scratch): may run on
+// another stream ahead of tc_decoder_forward.  Returns whether anything was prepared.
+bool tc_decoder_prepare(const TcDecoderArgs& a, cudaStream_t st);
 bool tc_decoder_supported(const drv_dims& d, const drv_hparams& hp);
 void tc_decoder_forward(const TcDecoderArgs& a, cudaStream_t st);   // lse, ll, asum, loss
 void tc_decoder_backward(const TcDecoderArgs& a, cudaStream_t st);  // dW, db, dY
@@ -89,9 +93,13 @@ struct TcBlockArgs {
   SideStream* side;   // optional: weight-gradient GEMM runs there
   const ColStatsOut* next_stats;  // optional: BatchNorm statistics of V for the next block
   bool dv_prepared;   // backward: the tf32-rounded dV and the bias gradient were already produced (bn_bwd_apply_round)
+  bool w_prepared;    // tc_block_prepare already left the fp16 hi / lo parts of W in the scratch
 };
 // where tc_block_backward expects the tf32-rounded dV of a block ([B][dout])
 float* tc_block_rounded_dv(void* scratch, int B, int din, int dout);
+// Start-of-step work of the encoder input block that only depends on the parameters (fp16 hi / lo split of W;
+// needs W, B, din, dout, sqrt_in, no_fused_prologue, scratch).  Returns whether anything was prepared.
+bool tc_block_prepare(const TcBlockArgs& a, cudaStream_t st);
 size_t tc_block_workspace_bytes(int B, int din, int dout);
 bool tc_block_forward_supported(int B, int din, int dout, const drv_hparams& hp);
 bool tc_block_backward_supported(int B, int din, int dout, const drv_hparams& hp);

@@ -231,6 +231,13 @@ bool tc_block_backward_supported(int B, int din, int dout, const drv_hparams& hp
   return tc_block_forward_supported(B, din, dout, hp) && dout % 4 == 0;
 }
 
+bool tc_block_prepare(const TcBlockArgs& a, cudaStream_t st) {
+  if (!(a.sqrt_in && !a.no_fused_prologue && tc::encfwd_h16_supported(a.din, a.dout))) return false;
+  Scratch s = carve(a.scratch, a.B, a.din, a.dout);
+  tc::encfwd_split_weight_h16(a.W, a.dout, a.din, s.w_hi, s.w_lo, st);
+  return true;
+}
+
 bool tc_block_forward(const TcBlockArgs& a, cudaStream_t st) {
   Scratch s = carve(a.scratch, a.B, a.din, a.dout);
   const size_t n = (size_t)a.B * a.din;
@@ -239,7 +246,7 @@ bool tc_block_forward(const TcBlockArgs& a, cudaStream_t st) {
     int rc;
     if (tc::encfwd_h16_supported(a.din, a.dout)) {
       // fp16 operands: the weight's fp16 hi / lo parts live in the (otherwise unused) w_hi / w_lo scratch
-      tc::encfwd_split_weight_h16(a.W, a.dout, a.din, s.w_hi, s.w_lo, st);
+      if (!a.w_prepared) tc::encfwd_split_weight_h16(a.W, a.dout, a.din, s.w_hi, s.w_lo, st);
       rc = tc::encfwd_fused(a.U, a.B, a.din, a.bn, s.w_hi, s.w_lo, a.dout, a.bias, a.V, s.a_hi, s.parts, kMaxParts, st,
                             a.next_stats, true);
     } else {

@@ -7,8 +7,8 @@
 // no dX is needed.)
 //
 // A = W_hi^T: MN-major (genes contiguous, 128-byte swizzle with 32-byte atoms), B = dH (tf32-rounded)
-// K-major, tile = 128 genes x 128 cells, K = h.  Persistent CTAs, 6 warps: TMA producer, MMA issuer,
-// 4 epilogue warps; two TMEM accumulator stages and two count-tile buffers overlap the epilogue of a
+// K-major, tile = 128 genes x 128 cells, K = h.  Persistent CTAs, 10 warps: TMA producer, MMA issuer,
+// 8 epilogue warps; two TMEM accumulator stages and two count-tile buffers overlap the epilogue of a
 // tile with the loads / MMAs of the next.
 #include "kernels.cuh"
 #include "tc.cuh"
@@ -28,7 +28,11 @@ constexpr int B_BYTES = BC * BK * 4;    // 16 KB
 constexpr int STAGE = A_BYTES + B_BYTES;
 constexpr int X_BYTES = 4 * BC * 32 * 4;  // count tile: 4 boxes of 128 cells x 32 genes = 64 KB
 constexpr int SMEM_BYTES = NST * STAGE + 2 * X_BYTES + 1024 + 256;
-constexpr int NTHREADS = 192;
+// 8 epilogue warps: two per TMEM lane quarter, each taking half of the tile's cell columns.  With one warp
+// per scheduler the epilogue's dependent instruction stream was the bound (ncu: issue slots 35 % busy with
+// ~1 eligible warp per scheduler, tensor pipe 26 %).
+constexpr int N_EPI = 8;
+constexpr int NTHREADS = (2 + N_EPI) * 32;
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_bn0grad(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH,
@@ -64,9 +68,9 @@ k_bn0grad(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUten
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);
+      mbar_init(&acc_empty[s], N_EPI);
       mbar_init(&x_full[s], 1);
-      mbar_init(&x_empty[s], 4);
+      mbar_init(&x_empty[s], N_EPI);
     }
     fence_barrier_init();
   }
@@ -125,6 +129,7 @@ k_bn0grad(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUten
   } else {
     // ===== epilogue: thread = gene, sums over the cells of the tile =====
     const int q = warp % 4;
+    const int ch = (warp - 2) / 4;  // which half of the tile's cells
     const int r = q * 32 + lane;  // gene within the tile
     float s1 = 0.f, s2 = 0.f;
     int cur_gt = -1, g = 0;
@@ -153,7 +158,7 @@ k_bn0grad(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUten
       const uint8_t* xq = xbuf + as * X_BYTES + q * (BC * 128);
       const int chunk = lane >> 2, within = (lane & 3) * 4;
 #pragma unroll 1
-      for (int c = 0; c < BC; c += 16) {
+      for (int c = ch * (BC / 2); c < (ch + 1) * (BC / 2); c += 16) {
         float v[16];
         tmem_ld16(tb + (uint32_t)c, v);
         float xv[16];

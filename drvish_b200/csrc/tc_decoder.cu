@@ -749,6 +749,17 @@ static void set_lse_layout(DecParams& p, int n_ct, int n_gt1) {
   p.lse_grid = p.lse_n_tiles < sm_count() ? p.lse_n_tiles : sm_count();
 }
 
+bool tc_decoder_prepare(const TcDecoderArgs& a, cudaStream_t st) {
+  if (!use_h16(a)) return false;
+  Scratch s = carve(a.scratch, a.B, a.G, a.h);
+  const size_t n4 = (size_t)2 * a.G * a.h / 4;
+  int wb = (int)((n4 + 255) / 256);
+  if (wb > sm_count() * 8) wb = sm_count() * 8;
+  launch_k(k_to_half, wb, 256, 0, st, a.W, n4, reinterpret_cast<__half2*>(s.W_h));
+  note_launch();
+  return true;
+}
+
 void tc_decoder_forward(const TcDecoderArgs& a, cudaStream_t st) {
   Scratch s = carve(a.scratch, a.B, a.G, a.h);
   CUtensorMap tAct, tW1, tW3, tX;
@@ -761,13 +772,7 @@ void tc_decoder_forward(const TcDecoderArgs& a, cudaStream_t st) {
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
   launch_k(k_act, blocks, 256, 0, st, a.U, a.B, a.h, a.bn, s.act, h16 ? s.act_h : (__half*)nullptr);
   note_launch();
-  if (h16) {
-    const size_t n4 = (size_t)2 * a.G * a.h / 4;
-    int wb = (int)((n4 + 255) / 256);
-    if (wb > sm_count() * 8) wb = sm_count() * 8;
-    launch_k(k_to_half, wb, 256, 0, st, a.W, n4, reinterpret_cast<__half2*>(s.W_h));
-    note_launch();
-  }
+  if (h16 && !a.w_prepared) tc_decoder_prepare(a, st);
   DecParams p{};
   p.B = a.B; p.G = a.G; p.h = a.h; p.bias = a.bias; p.lib = a.lib; p.rshift = a.rshift; p.eps = a.eps; p.c = a.c;
   p.part_m = s.part_m; p.part_s = s.part_s; p.ll = a.ll; p.asum = a.asum;
