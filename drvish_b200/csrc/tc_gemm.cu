@@ -561,7 +561,8 @@ int gemm_f16(const void* A, int lda, bool a_mn, const void* Bm, int ldb, bool b_
 bool reduce_parts(const float* parts, int n_parts, int M, int N, const float* bias, float* C, int ldc, cudaStream_t st,
                   const ColStatsOut* stats) {
   if (stats && N % 4 == 0 && ldc % 4 == 0 && M > 1) {
-    int R = (M + 7) / 8;
+    static const int rows_env = getenv("DRV_RP_ROWS") ? atoi(getenv("DRV_RP_ROWS")) : 16;
+    int R = (M + rows_env - 1) / rows_env;
     if (R > n_sm_tc() * 4) R = n_sm_tc() * 4;
     if (R < (M + 127) / 128) R = (M + 127) / 128;  // <= 32 rows per thread in the fp32 partial sums
     const int rows_per_cta = (M + R - 1) / R;
