@@ -227,9 +227,11 @@ def run_native(args, cfg):
     def device_step(i, single_call=False):
         # exactly what FusedTraceELBO.loss_and_grads enqueues, minus the per-step loss read-back
         xb = xs[i % n_batches]
-        if world > 1 and not single_call:
+        if world > 1 and not single_call and not elbo.dp_overlap:
+            elbo._enqueue(rt, xb, labels, yflat, True, part=3)
+            dist.all_reduce(rt.flat_grads[:rt.n_param_floats + 1], op=dist.ReduceOp.SUM)
+        elif world > 1 and not single_call:
             elbo._enqueue(rt, xb, labels, yflat, True, part=1)
-            rt.flat_grads[rt.n_param_floats] = rt._out[0].to(torch.float32)
             w1 = dist.all_reduce(rt.flat_grads[rt.decoder_offset:], op=dist.ReduceOp.SUM, async_op=True)
             elbo._enqueue(rt, xb, labels, yflat, True, part=2)
             w2 = dist.all_reduce(rt.flat_grads[:rt.decoder_offset], op=dist.ReduceOp.SUM, async_op=True)
@@ -400,7 +402,7 @@ def run_native(args, cfg):
                       "k_dec<3> (softmax coupling) + dAct and dW tcgen05 GEMMs (sections DEC_NB_FWD + DEC_NB_BWD, "
                       "side stream off)")
     roof["algorithmic"] = {"bytes": bytes_alg, "flops": flops_alg, "formula": "8BG+8Bh+16Gh bytes, 12BGh flops (SURVEY 8d)"}
-    roof["peak_source"] = peaks["which"] + " (bf16 sustained cuBLAS; the kernels use kind::tf32 whose nominal peak is half)"
+    roof["peak_source"] = peaks["which"] + " (bf16 sustained cuBLAS; the decoder kernels use kind::f16 - fp16 operands, fp32 accumulate - whose nominal peak is the bf16 one)"
     roof["section_ms"] = {k: round(float(sec[i]), 4) for i, k in enumerate(
         ["enc_fwd", "dec_trunk_fwd", "dec_nb_fwd", "dose_response", "dec_nb_bwd", "dec_trunk_bwd", "enc_bwd"])}
     roof["profiled_steps"] = int(nprof.value)
@@ -439,7 +441,7 @@ def run_native(args, cfg):
     line = {
         "metric": "cells/sec per SVI step (ELBO fwd+bwd)", "value": value, "unit": "cells/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (tf32 tensor-core operands where stated in DESIGN.md)",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp16 / tf32 tensor-core operands with fp32 accumulation where stated in DESIGN.md)",
         "data": "synthetic",
         "config": {"workload": cfg["name"], "minibatch_per_gpu": B, "global_batch": B * world,
                    "parallelism": f"dp{world}", "l2": f"inputs rotate over {n_batches} resident minibatches "

@@ -14,6 +14,7 @@ DRV_FLAG_FORCE_SIMT = 1
 DRV_FLAG_NO_BN_UPDATE = 2
 DRV_FLAG_STOP_AFTER_DECODER = 128
 DRV_FLAG_ENCODER_BACKWARD_ONLY = 256
+DRV_FLAG_LOSS_IN_GRADS = 2048
 DRV_STATUS_NAN_LOSS = 1
 DRV_STATUS_MISSING_CLASS = 2
 DRV_STATUS_BAD_LABEL = 4

@@ -238,7 +238,8 @@ __global__ void k_bump(int64_t* c, int n) {
 // Last launch of a step: BatchNorm batch counters, the decoder's log-likelihood sum folded into the
 // loss (ll may be null: the CUDA-core NB kernel adds it itself), status word + NaN flag.
 __global__ void __launch_bounds__(256) k_finalize_step(drv_step_out* out, const uint32_t* status, int64_t* c, int n,
-                                                       const float* __restrict__ ll, int B, float scale) {
+                                                       const float* __restrict__ ll, int B, float scale,
+                                                       float* __restrict__ loss_slot) {
   pdl_prologue();
   const int i = threadIdx.x;
   if (c && i < n) c[i] += 1;
@@ -254,6 +255,7 @@ __global__ void __launch_bounds__(256) k_finalize_step(drv_step_out* out, const 
     for (int w = 0; w < (int)blockDim.x / 32; ++w) s += sh[w];
     const double loss = out->loss - (double)scale * s;
     out->loss = loss;
+    if (loss_slot) *loss_slot = (float)loss;  // data parallel: the loss rides in the gradient buffer's tail slot
     uint32_t st = *status;
     if (isnan(loss)) st |= DRV_STATUS_NAN_LOSS;
     out->status = st;
@@ -330,8 +332,8 @@ void bump_counters(int64_t* counters, int n, cudaStream_t st) {
 }
 
 void finalize_step(drv_step_out* out, const uint32_t* status, int64_t* counters, int n, const float* ll, int B,
-                   float scale, cudaStream_t st) {
-  launch_k(k_finalize_step, 1, 256, 0, st, out, status, counters, n, ll, B, scale);
+                   float scale, cudaStream_t st, float* loss_slot) {
+  launch_k(k_finalize_step, 1, 256, 0, st, out, status, counters, n, ll, B, scale, loss_slot);
   note_launch();
 }
 

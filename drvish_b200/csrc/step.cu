@@ -574,7 +574,8 @@ static int elbo_step_impl(const drv_dims* dims, const drv_hparams* hp, const flo
     if (stop_after_decoder) {
       // decoder / dose-response gradients and the loss are final: hand back to the caller
       if (side) side->join(st);
-      finalize_step(out, status, nullptr, 0, use_tc ? c.at<float>(p.ll) : nullptr, B, hp->scale_factor, st);
+      finalize_step(out, status, nullptr, 0, use_tc ? c.at<float>(p.ll) : nullptr, B, hp->scale_factor, st,
+                    grads + n.n_param_floats);  // loss -> tail slot of the gradient buffer (one collective carries both)
       return finish();
     }
     // ---- encoder backward ----------------------------------------------------------------------
@@ -585,7 +586,8 @@ static int elbo_step_impl(const drv_dims* dims, const drv_hparams* hp, const flo
   if (side) side->join(st);
   // BatchNorm batch counters + status word folded into the result record: one launch
   finalize_step(out, status, (bn_batches && !(hp->flags & DRV_FLAG_NO_BN_UPDATE)) ? bn_batches : nullptr, n.n_bn,
-                use_tc ? c.at<float>(p.ll) : nullptr, B, hp->scale_factor, st);
+                use_tc ? c.at<float>(p.ll) : nullptr, B, hp->scale_factor, st,
+                (bwd && (hp->flags & DRV_FLAG_LOSS_IN_GRADS)) ? grads + n.n_param_floats : nullptr);
   if (prof::enabled && prof::n_steps < prof::MAX_STEPS) {
     if (!bwd) for (int i = 5; i <= DRV_N_SECTIONS; ++i) prof::mark(i, st);
     ++prof::n_steps;

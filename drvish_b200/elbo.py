@@ -14,6 +14,7 @@ the tail slot of the same buffer.  The R-rank result is sum_r reference(shard_r)
 """
 from __future__ import annotations
 
+import os
 import warnings
 from typing import Optional
 
@@ -52,6 +53,9 @@ class FusedTraceELBO:
         self._noise_bufs = {}
         self.last_status = 0
         self.use_cuda_graph = bool(use_cuda_graph)
+        # data parallel: True = two-part step, the all-reduce of the decoder slice overlaps the encoder backward;
+        # False = one graph + one all-reduce after it (see DESIGN.md section 5 for the measurements)
+        self.dp_overlap = os.environ.get("DRV_DP_OVERLAP", "0") == "1"
         self._graphs = {}
         self._graph_seen = {}
         self._step_ctr = None  # device uint64: steps taken (drives the Philox counters)
@@ -170,11 +174,15 @@ class FusedTraceELBO:
         else:
             labels = args[1] if len(args) > 1 else None
             y = self._flatten_y(rt, args[2] if len(args) > 2 else None, rt.device)
-        if want_grads and self._dp_enabled():
+        if want_grads and self._dp_enabled() and not self.dp_overlap:
+            # whole step, then ONE all-reduce of the flat gradient buffer (loss in its tail slot)
+            self._enqueue(rt, x, labels, y, True, part=3, mcv=mcv)
+            torch.distributed.all_reduce(rt.flat_grads[:rt.n_param_floats + 1], op=torch.distributed.ReduceOp.SUM,
+                                         group=self.process_group)
+        elif want_grads and self._dp_enabled():
             # two-part step: the all-reduce of the decoder + dose-response slice (incl. the loss in the
             # tail slot) runs on NCCL's stream while the encoder backward is still computing
-            self._enqueue(rt, x, labels, y, True, part=1, mcv=mcv)
-            rt.flat_grads[rt.n_param_floats] = rt._out[0].to(torch.float32)
+            self._enqueue(rt, x, labels, y, True, part=1, mcv=mcv)  # leaves the loss in flat_grads[n_param_floats]
             tail = rt.flat_grads[rt.decoder_offset:]
             w1 = torch.distributed.all_reduce(tail, op=torch.distributed.ReduceOp.SUM, group=self.process_group,
                                               async_op=True)
@@ -205,7 +213,8 @@ class FusedTraceELBO:
         captured the second time a key is seen (the first call runs eagerly and warms up every
         kernel variant), so a training loop that cycles through a few staging buffers - e.g.
         PinnedBatchPrefetcher's two - replays ~70 kernel launches with one cudaGraphLaunch."""
-        pflags = {0: 0, 1: _lib.DRV_FLAG_STOP_AFTER_DECODER, 2: _lib.DRV_FLAG_ENCODER_BACKWARD_ONLY}[part]
+        pflags = {0: 0, 1: _lib.DRV_FLAG_STOP_AFTER_DECODER, 2: _lib.DRV_FLAG_ENCODER_BACKWARD_ONLY,
+                  3: _lib.DRV_FLAG_LOSS_IN_GRADS}[part]
 
         def eager():
             # part 2 continues the step of part 1: same noise buffers, no new draws

@@ -74,7 +74,11 @@ typedef struct drv_hparams {
 #define DRV_FLAG_NO_BN_UPDATE 2 /* do not touch running_mean/var (gradient checks) */
 /* bits 4..64 are debug switches (force single kernels onto the CUDA-core path, no side stream) */
 #define DRV_FLAG_STOP_AFTER_DECODER 128     /* part 1 of 2: return once the decoder, dose-response and latent
-                                               gradients and the loss are final (data-parallel overlap) */
+                                               gradients and the loss are final (data-parallel overlap); the
+                                               loss is also written as a float to grads[total floats of
+                                               drv_param_offsets], so grads needs that one extra slot */
+#define DRV_FLAG_LOSS_IN_GRADS 2048         /* whole step in one call, loss also written to grads[total floats]
+                                               (data parallel with ONE all-reduce after the step) */
 #define DRV_FLAG_ENCODER_BACKWARD_ONLY 256  /* part 2 of 2: encoder backward of the step started by part 1
                                                (same arguments, same workspace) */
 

@@ -21,7 +21,6 @@ rt.ensure_flat()
 def step(i):
     xb = xs[i % 4]
     elbo._enqueue(rt, xb, labels, yflat, True, part=1)
-    rt.flat_grads[rt.n_param_floats] = rt._out[0].to(torch.float32)
     w1 = dist.all_reduce(rt.flat_grads[rt.decoder_offset:], op=dist.ReduceOp.SUM, async_op=True)
     elbo._enqueue(rt, xb, labels, yflat, True, part=2)
     w2 = dist.all_reduce(rt.flat_grads[:rt.decoder_offset], op=dist.ReduceOp.SUM, async_op=True)
