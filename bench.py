@@ -223,13 +223,15 @@ def run_native(args, cfg):
     # same code path as loss_and_grads minus the per-step loss read-back (one sync at the end)
     yflat = elbo._flatten_y(rt, y, device) if cfg["drugs"] else None
     rt.ensure_flat()
+    if world > 1 and not elbo.dp_overlap:
+        elbo.dp_prepare(rt)  # peer-mapped gradient buffer (before any graph is captured)
 
     def device_step(i, single_call=False):
         # exactly what FusedTraceELBO.loss_and_grads enqueues, minus the per-step loss read-back
         xb = xs[i % n_batches]
         if world > 1 and not single_call and not elbo.dp_overlap:
             elbo._enqueue(rt, xb, labels, yflat, True, part=3)
-            dist.all_reduce(rt.flat_grads[:rt.n_param_floats + 1], op=dist.ReduceOp.SUM)
+            elbo.dp_all_reduce(rt)
         elif world > 1 and not single_call:
             elbo._enqueue(rt, xb, labels, yflat, True, part=1)
             w1 = dist.all_reduce(rt.flat_grads[rt.decoder_offset:], op=dist.ReduceOp.SUM, async_op=True)

@@ -80,6 +80,12 @@ SYMBOLS = {
     "drv_elbo_step_mcv": (C.c_int, [_P] * 14 + [C.c_size_t, _P]),
     "drv_csr_gather_rows": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "drv_split_molecules": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P]),
+    "drv_comm_header_bytes": (C.c_size_t, []),
+    "drv_comm_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), _P]),
+    "drv_comm_open": (C.c_int, [_P, C.POINTER(C.c_void_p)]),
+    "drv_comm_close": (C.c_int, [_P]),
+    "drv_comm_free": (C.c_int, [_P]),
+    "drv_peer_allreduce": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int64, _P]),
     "drv_aggmo_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "drv_draw_step_noise": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P, C.c_uint64, _P, _P, _P, _P, _P, _P]),
 }

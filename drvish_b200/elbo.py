@@ -22,7 +22,7 @@ import torch
 
 from . import _lib
 from .models import HAVE_PYRO, NBVAE
-from .parallel import allreduce_grads_and_loss
+from .parallel import PeerAllReduce, allreduce_grads_and_loss
 
 if HAVE_PYRO:  # pragma: no cover
     import pyro
@@ -58,6 +58,7 @@ class FusedTraceELBO:
         self.dp_overlap = os.environ.get("DRV_DP_OVERLAP", "0") == "1"
         self._graphs = {}
         self._graph_seen = {}
+        self._peer = {}  # id(runtime) -> PeerAllReduce or None (NCCL)
         self._step_ctr = None  # device uint64: steps taken (drives the Philox counters)
 
     # -- noise ------------------------------------------------------------------------------
@@ -108,6 +109,28 @@ class FusedTraceELBO:
         return bufs
 
     # -- helpers ----------------------------------------------------------------------------
+    def dp_all_reduce(self, rt) -> None:
+        """Sum the flat gradient buffer (+ loss slot) over the ranks: one peer-memory kernel over NVLink when the
+        group is a single node of 2 / 4 / 8 GPUs (``parallel.PeerAllReduce``), else one NCCL all-reduce."""
+        self.dp_prepare(rt)
+        peer = self._peer[id(rt)]
+        if peer is not None:
+            peer.all_reduce()
+        else:
+            torch.distributed.all_reduce(rt.flat_grads[:rt.n_param_floats + 1], op=torch.distributed.ReduceOp.SUM,
+                                         group=self.process_group)
+
+    def dp_prepare(self, rt) -> None:
+        """Set up the peer-memory all-reduce (collective call: every rank, before its first step)."""
+        if id(rt) in self._peer:
+            return
+        peer = PeerAllReduce.create(rt.flat_grads.numel(), rt.device, self.process_group)
+        if peer is not None:
+            rt.rebase_grads(peer.data)
+            self._graphs.clear()
+            self._graph_seen.clear()
+        self._peer[id(rt)] = peer
+
     def _dp_enabled(self) -> bool:
         if self.data_parallel is False:
             return False
@@ -176,9 +199,10 @@ class FusedTraceELBO:
             y = self._flatten_y(rt, args[2] if len(args) > 2 else None, rt.device)
         if want_grads and self._dp_enabled() and not self.dp_overlap:
             # whole step, then ONE all-reduce of the flat gradient buffer (loss in its tail slot)
+            if id(rt) not in self._peer:
+                self.dp_prepare(rt)
             self._enqueue(rt, x, labels, y, True, part=3, mcv=mcv)
-            torch.distributed.all_reduce(rt.flat_grads[:rt.n_param_floats + 1], op=torch.distributed.ReduceOp.SUM,
-                                         group=self.process_group)
+            self.dp_all_reduce(rt)
         elif want_grads and self._dp_enabled():
             # two-part step: the all-reduce of the decoder + dose-response slice (incl. the loss in the
             # tail slot) runs on NCCL's stream while the encoder backward is still computing

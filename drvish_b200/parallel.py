@@ -7,10 +7,15 @@ normalises with ITS shard's BatchNorm statistics and class means, exactly like R
 reference steps whose gradients are added."""
 from __future__ import annotations
 
+import ctypes as C
+import os
+import warnings
 from typing import Optional
 
 import torch
 import torch.distributed as dist
+
+from . import _lib
 
 
 def dp_world_size(group=None) -> int:
@@ -37,3 +42,68 @@ def shard_rows(n_rows: int, rank: int, world: int) -> slice:
     """Rank r takes rows [r*B, (r+1)*B) of a global minibatch of R*B cells."""
     per = n_rows // world
     return slice(rank * per, (rank + 1) * per)
+
+
+class _RawCuda:
+    """Zero-copy view of raw device memory for torch.as_tensor (CUDA array interface)."""
+
+    def __init__(self, ptr: int, n_floats: int):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class PeerAllReduce:
+    """The step's gradient all-reduce as ONE kernel over NVLink peer memory (``drv_peer_allreduce``).
+
+    Allocates this rank's buffer of ``n_floats`` floats through the C ABI, exchanges CUDA IPC handles over the
+    process group and maps every other rank's buffer.  ``self.data`` is the local buffer as a torch tensor (the
+    runtime re-bases its flat gradient buffer onto it); ``all_reduce()`` sums it in place over the ranks, on the
+    current stream.  Single-node groups of 2, 4 or 8 ranks; ``create`` returns None (caller keeps NCCL) otherwise
+    or when the IPC set-up fails."""
+
+    def __init__(self, n_floats: int, device: torch.device, group=None):
+        self.lib = _lib.load()
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.n_floats = int(n_floats)
+        self.device = torch.device(device)
+        header = self.lib.drv_comm_header_bytes()
+        base = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.drv_comm_alloc(4 * ((self.n_floats + 3) // 4 * 4), C.byref(base), handle), "drv_comm_alloc")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, (bytes(handle), os.uname().nodename), group=group)
+            if len({h[1] for h in handles}) != 1:
+                self.lib.drv_comm_free(base)
+                raise RuntimeError("ranks on different nodes")
+            self._own = base.value
+            bases = []
+            for j, (h, _) in enumerate(handles):
+                if j == self.rank:
+                    bases.append(base.value)
+                    continue
+                peer = C.c_void_p()
+                buf = (C.c_ubyte * 64).from_buffer_copy(h)
+                _lib.check(self.lib.drv_comm_open(buf, C.byref(peer)), "drv_comm_open")
+                bases.append(peer.value)
+        self._bases = (C.c_void_p * self.world)(*bases)
+        self.data = torch.as_tensor(_RawCuda(base.value + header, self.n_floats), device=self.device)
+        dist.barrier(group=group)  # every rank has mapped every buffer before the first kernel touches them
+
+    @classmethod
+    def create(cls, n_floats: int, device, group=None) -> Optional["PeerAllReduce"]:
+        if os.environ.get("DRV_PEER_ALLREDUCE", "1") == "0":
+            return None
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_backend(group) != "nccl":
+            return None
+        if dist.get_world_size(group) not in (2, 4, 8):
+            return None
+        try:
+            return cls(n_floats, device, group)
+        except Exception as e:  # IPC not permitted, ranks on several nodes, ...: NCCL does the job
+            warnings.warn(f"drvish_b200: peer-memory all-reduce unavailable ({e}); using NCCL")
+            return None
+
+    def all_reduce(self) -> None:
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.drv_peer_allreduce(self._bases, self.rank, self.world, self.n_floats, C.c_void_p(st)),
+                   "drv_peer_allreduce")

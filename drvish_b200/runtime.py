@@ -195,6 +195,17 @@ class ModelRuntime:
             self._workspaces[n_cells] = ws
         return ws
 
+    def rebase_grads(self, new_flat: torch.Tensor) -> None:
+        """Move the flat gradient buffer (and every ``param.grad`` view) onto ``new_flat`` - e.g. the peer-mapped
+        buffer of ``parallel.PeerAllReduce``.  Same layout; graphs captured earlier must be dropped by the caller."""
+        if new_flat.numel() < self.flat_grads.numel() or new_flat.dtype != torch.float32 or new_flat.device != self.flat_grads.device:
+            raise ValueError("rebase_grads: incompatible buffer")
+        new_flat[:self.flat_grads.numel()].copy_(self.flat_grads)
+        base = self.flat_grads.data_ptr()
+        self._grad_views = [new_flat[(v.data_ptr() - base) // 4:(v.data_ptr() - base) // 4 + v.numel()].view(v.shape)
+                            for v in self._grad_views]
+        self.flat_grads = new_flat
+
     def attach_grads(self) -> None:
         """Point every ``param.grad`` at its slice of the flat gradient buffer (what Pyro's
         ``loss.backward()`` leaves behind)."""

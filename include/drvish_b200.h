@@ -224,6 +224,21 @@ int drv_split_molecules(const float* umis, const float* data_split, const float*
                         const float* overlap_factor, int n_rows, int n_genes, uint64_t seed, uint64_t call_index,
                         float* x0, float* x1, float* log_split, float* log_split_complement, void* stream);
 
+/* Gradient all-reduce over NVLink peer memory ("a single gradient all-reduce per step"; the
+ * reference itself is single-device, src/drvish/train/__init__.py:42-46).  Every rank of the node allocates its flat
+ * gradient buffer with drv_comm_alloc (cudaMalloc + a 64-byte CUDA IPC handle, HOST pointer h_handle64),
+ * exchanges the handles out of band (torch.distributed), maps the others with drv_comm_open, and passes
+ * the `world` base pointers (HOST array indexed by rank; its own entry is its allocation) to
+ * drv_peer_allreduce: one kernel that sums the n_floats floats found drv_comm_header_bytes() behind every
+ * base (rank order, bit-identical result on all ranks) in place.  world must be 2, 4 or 8; all ranks must
+ * call it the same number of times.  Data pointer of a region = base + drv_comm_header_bytes(). */
+size_t drv_comm_header_bytes(void);
+int drv_comm_alloc(size_t data_bytes, void** base_out, void* h_handle64);
+int drv_comm_open(const void* h_handle64, void** base_out);
+int drv_comm_close(void* base);
+int drv_comm_free(void* base);
+int drv_peer_allreduce(void* const* h_bases, int rank, int world, int64_t n_floats, void* stream);
+
 /* Section timing with CUDA events recorded on the step's stream (bench.py's live roofline
  * measurement).  drv_profile_enable(1) arms it (up to 64 steps are kept); drv_profile_read
  * synchronises on the recorded events and returns the mean milliseconds per section. */
