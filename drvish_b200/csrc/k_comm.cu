@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(512) k_peer_allreduce(Peers p, int rank, long 
   for (int j = 0; j < WORLD; ++j) data[j] = reinterpret_cast<float4*>(reinterpret_cast<char*>(p.base[j]) + COMM_HEADER_BYTES);
   // U independent elements per thread and trip: U x WORLD 16-byte loads in flight (the loop is bound by the
   // NVLink round trip, not by bytes, when only one remote load per thread is outstanding)
-  constexpr int U = 8 / WORLD;
+  constexpr int U = WORLD >= 8 ? 2 : 8 / WORLD;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = c0 + (long long)blockIdx.x * blockDim.x + t; i < c1; i += U * stride) {
     float4 v[U][WORLD];

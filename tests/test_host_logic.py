@@ -87,6 +87,10 @@ def _dp_worker(rank, world, port, out_dir):
     flat = torch.zeros(n + 32, dtype=torch.float64)
     flat[:n] = torch.cat([grads[k].reshape(-1) for k in names])
     allreduce_grads_and_loss(flat, n, torch.tensor(loss, dtype=torch.float64))
+    # the peer-memory all-reduce is NVLink/CUDA-IPC only: under gloo the step keeps the collective above
+    from drvish_b200.parallel import PeerAllReduce
+
+    assert PeerAllReduce.create(n + 32, "cpu") is None
     torch.save({"flat": flat, "n": n, "names": names}, os.path.join(out_dir, f"r{rank}.pt"))
     dist.destroy_process_group()
 
@@ -143,3 +147,23 @@ def test_packed_counts_round_trip_and_rejection():
     assert lib.drv_host_pack_counts_u16(C.c_void_p(big.data_ptr()), C.c_void_p(out.data_ptr()), big.numel(), 8) == 70000
     sets = pack_batches([[x, "labels"], [x + 0.5, "labels"]])
     assert isinstance(sets[0][0], PackedCounts) and torch.is_tensor(sets[1][0]) and sets[0][1] == "labels"
+
+
+def test_loaders_have_no_cpu_path():
+    """The device loaders (molecule split, CSR gather) raise on host tensors instead of falling back."""
+    from drvish_b200.data import MCVDataLoader, split_molecules
+
+    umis = torch.ones(4, 8)
+    s = torch.full((4, 1), 0.9)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        split_molecules(umis, s, 1 - s, torch.zeros(4, 1))
+    # same constructor surface as the reference's DataLoader subclass (train/mcv_train.py:13-14)
+    ds = torch.utils.data.TensorDataset(umis, s, 1 - s, torch.zeros(4, 1))
+    dl = MCVDataLoader(ds, batch_size=2, shuffle=False)
+    assert len(dl) == 2 and callable(MCVDataLoader.split_molecules)
+
+
+def test_peer_allreduce_needs_an_nccl_group():
+    from drvish_b200.parallel import PeerAllReduce
+
+    assert PeerAllReduce.create(1024, "cpu") is None  # torch.distributed not initialised: NCCL / single rank path
