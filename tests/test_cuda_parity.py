@@ -24,6 +24,8 @@ CASES = {
     "mid": dict(n_input=1000, n_latent=10, layers=[128, 128], batch=512, drugs=0),
     # tensor-core path with ragged edges: 3 cell tiles (the last one partial), a partial gene tile,
     # hidden widths that are not powers of two, dose-response head on
+    # configs 4 / 5: hidden width 512 (two N tiles in the encoder GEMM, 8 fp16 k-blocks in the decoder), latent 32
+    "wide_hidden": dict(n_input=1024, n_latent=32, layers=[512, 512], batch=384, drugs=0),
     # config 5's head and latent width (96 drugs x 10 doses, K=8, latent 64) on a small gene panel
     "cfg5_head": dict(n_input=384, n_latent=64, layers=[128, 96], batch=256, drugs=96, doses=10, classes=8),
     "tc_ragged": dict(n_input=1100, n_latent=9, layers=[96, 160], batch=300, drugs=2, doses=3, classes=4,
