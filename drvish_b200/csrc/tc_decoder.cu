@@ -1,19 +1,23 @@
 // Fused decoder-last-layer GEMM + gene softmax + library scaling + NB likelihood on the sm_100a
-// tensor cores (tcgen05.mma.kind::tf32, TMEM accumulators, TMA-fed 128-byte-swizzled operands).
+// tensor cores (tcgen05.mma, TMEM accumulators, TMA-fed 128-byte-swizzled operands; kind::f16 with fp16
+// operands by default - see DL_SCALE below - or kind::tf32 with fp32 containers, template flag H16).
 // The (cells x 2*genes) logits / mean matrix never touches HBM in the forward pass:
 //
 //   phase 1  logits(scale half) tile in TMEM -> per-row online (max, sum exp) partials  -> lse[b]
 //   phase 2  logits(both halves) tile in TMEM + TMA-staged count tile -> NB log-prob row sums
 //            LL[b], A[b] = sum_g dLL/d ell  (= dLL/d library)                 [evaluate_loss stops here]
-//   phase 3  recompute the tile, form d loss/d logits in registers, write it
-//            once (fp32) and reduce the bias gradient; dW = dlogits^T act and dAct = dlogits W then
-//            run as tf32 tcgen05 GEMMs that read dlogits / act / W in the layouts they already have
-//            (MN-major descriptors, tc_gemm.cu).
+//            training: the NB part of d loss/d logits (ds', drho) leaves in the same pass through
+//            shared-memory tiles and TMA stores
+//   phase 3  recompute the scale-half tile, add the softmax coupling ds = ds' + A[b] softmax(s) in place
+//            to the TMA-staged ds' tile, TMA store, bias gradient; dW = dlogits^T act
+//            and dAct = dlogits W then run as tcgen05 GEMMs that read dlogits / act / W in the layouts
+//            they already have (MN-major descriptors, tc_gemm.cu).
 //
 // Reference arithmetic: NBDecoder.forward modules.py:93-96, "obs" site nbvae.py:72-78.
-// Persistent CTAs (one per SM), 18 warps: 16 epilogue warps (4 per TMEM lane quarter, each a
-// 16-gene column slice), 1 TMA producer warp, 1 MMA-issuer warp.  Tiles: 128 cells x 64 genes
-// (x 2 halves = 128 accumulator columns), double-buffered in TMEM (256 columns).
+// Persistent CTAs (one per SM), 19 warps: 16 epilogue warps (4 per TMEM lane quarter, each a
+// 16-gene column slice), a TMA producer warp, an MMA-issuer warp and a TMA store warp.  Tiles: 128 cells x
+// 64 genes x 2 halves (phase 2) or 128 x 128 genes (phases 1, 3) = 128 accumulator columns,
+// double-buffered in TMEM (256 columns).
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include <type_traits>

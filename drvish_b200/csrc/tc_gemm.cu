@@ -1,7 +1,7 @@
-// Generic tf32 tensor-core GEMM for sm_100a:  C[M][N] (+)= sum_k A(m,k) * B(n,k)
-// tcgen05.mma.kind::tf32 (fp32 operands straight from memory, fp32 accumulate in TMEM), operands
-// staged by TMA with the 128-byte swizzle through a 4-stage mbarrier ring, warp-specialised:
-// warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+// Generic tensor-core GEMM for sm_100a:  C[M][N] (+)= alpha * sum_k A(m,k) * B(n,k)
+// tcgen05.mma.kind::tf32 (fp32 operands straight from memory) or kind::f16 (fp16 operands, template flag
+// H16), fp32 accumulate in TMEM, operands staged by TMA with the 128-byte swizzle through an mbarrier ring,
+// warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
 // Each operand may be K-major ([rows][K], K contiguous) or MN-major ([K][rows], rows contiguous),
 // so that d logits / activations / weights are consumed in the layout they already have:
 //   dW   = dlogits^T act   : A = dlogits [B][2G] MN-major, B = act [B][h] MN-major, K = cells
