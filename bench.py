@@ -448,7 +448,11 @@ def run_native(args, cfg):
         "config": {"workload": cfg["name"], "minibatch_per_gpu": B, "global_batch": B * world,
                    "parallelism": f"dp{world}", "l2": f"inputs rotate over {n_batches} resident minibatches "
                    f"({n_batches * B * G * 4 / 1e9:.2f} GB > 126 MB L2), no flush", "optimizer": "excluded from value/e2e (see with_optimizer)",
-                   "noise": "Philox in-kernel draws each step", "cuda_graph": not args.no_graph},
+                   "noise": "Philox in-kernel draws each step", "cuda_graph": not args.no_graph,
+                   "all_reduce": ("none (1 GPU)" if world == 1 else
+                                  "two-part step, NCCL all-reduces overlapping the encoder backward" if elbo.dp_overlap else
+                                  "one drv_peer_allreduce kernel over NVLink peer memory per step" if elbo._peer.get(id(rt)) is not None
+                                  else "one NCCL all-reduce per step")},
         "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": e2e_h2d, "d2h_bytes_per_step": 16,
                 "steps": e2e_steps, "api": "FusedTraceELBO.loss_and_grads(model.model, model.guide, *batch) fed by PinnedBatchPrefetcher "
                        "(pinned host fp32 minibatches, H2D of the batches ahead overlapped with the running step)",
