@@ -68,26 +68,43 @@ class PeerAllReduce:
         header = self.lib.drv_comm_header_bytes()
         base = C.c_void_p()
         handle = (C.c_ubyte * 64)()
+        opened, bases, err = [], [], None
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.drv_comm_alloc(4 * ((self.n_floats + 3) // 4 * 4), C.byref(base), handle), "drv_comm_alloc")
+            # Every step below is collective: a rank that fails keeps taking part and reports the failure, so that
+            # ALL ranks fall back to NCCL together (a rank in ncclAllReduce next to ranks in the peer kernel hangs).
+            rc = self.lib.drv_comm_alloc(4 * ((self.n_floats + 3) // 4 * 4), C.byref(base), handle)
+            if rc != 0:
+                err = f"drv_comm_alloc failed ({rc})"
             handles = [None] * self.world
-            dist.all_gather_object(handles, (bytes(handle), os.uname().nodename), group=group)
-            if len({h[1] for h in handles}) != 1:
-                self.lib.drv_comm_free(base)
-                raise RuntimeError("ranks on different nodes")
-            self._own = base.value
-            bases = []
-            for j, (h, _) in enumerate(handles):
-                if j == self.rank:
-                    bases.append(base.value)
-                    continue
-                peer = C.c_void_p()
-                buf = (C.c_ubyte * 64).from_buffer_copy(h)
-                _lib.check(self.lib.drv_comm_open(buf, C.byref(peer)), "drv_comm_open")
-                bases.append(peer.value)
+            dist.all_gather_object(handles, (bytes(handle) if err is None else None, os.uname().nodename), group=group)
+            if err is None and any(h[0] is None for h in handles):
+                err = "a rank could not allocate its buffer"
+            if err is None and len({h[1] for h in handles}) != 1:
+                err = "ranks on different nodes"
+            if err is None:
+                for j, (h, _) in enumerate(handles):
+                    if j == self.rank:
+                        bases.append(base.value)
+                        continue
+                    peer = C.c_void_p()
+                    rc = self.lib.drv_comm_open((C.c_ubyte * 64).from_buffer_copy(h), C.byref(peer))
+                    if rc != 0:
+                        err = f"drv_comm_open failed ({rc})"
+                        break
+                    opened.append(peer.value)
+                    bases.append(peer.value)
+            # agreement + barrier: every rank has mapped every buffer before the first kernel touches them
+            ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                for p in opened:
+                    self.lib.drv_comm_close(C.c_void_p(p))
+                if base.value:
+                    self.lib.drv_comm_free(base)
+                raise RuntimeError(err or "another rank could not set up the peer buffers")
+        self._own = base.value
         self._bases = (C.c_void_p * self.world)(*bases)
         self.data = torch.as_tensor(_RawCuda(base.value + header, self.n_floats), device=self.device)
-        dist.barrier(group=group)  # every rank has mapped every buffer before the first kernel touches them
 
     @classmethod
     def create(cls, n_floats: int, device, group=None) -> Optional["PeerAllReduce"]:
