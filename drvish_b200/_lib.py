@@ -18,6 +18,7 @@ DRV_FLAG_LOSS_IN_GRADS = 2048
 DRV_STATUS_NAN_LOSS = 1
 DRV_STATUS_MISSING_CLASS = 2
 DRV_STATUS_BAD_LABEL = 4
+DRV_GRAD_TAIL_FLOATS = 4  # loss + one float per status bit in the tail of the gradient buffer (data parallel)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdrvish_b200.so")

@@ -241,13 +241,6 @@ static __constant__ float c_lgamma1p[LGTAB_N] = {
     457.81238798127811f, 462.60817852687495f, 467.41219957160814f, 472.22438392698058f,
     477.04466549258569f, 481.87297922988796f, 486.70926113683942f, 491.55344822329801f};
 
-// Result of one (cell, gene) element of the NB block.
-struct NbElem {
-  float ll;    // log NB(x | r, logits=ell)
-  float a;     // dLL/d ell = x - (x + r) sigmoid(ell)
-  float drho;  // dLL/d rho = e^rho (log sigmoid(-ell) + psi(r+x) - psi(r)) - a
-};
-
 // MUFU.RCP alone: __fdividef(1, y) wraps it in range fix-ups (6 instructions) that the NB terms never need
 __device__ __forceinline__ float rcp_approx(float v) {
   float r;
@@ -271,95 +264,232 @@ __device__ __forceinline__ void load_lgamma_table(float* tab_smem, int tid) {
   if (tid < LGTAB_N) tab_smem[tid] = c_lgamma1p[tid];
 }
 
-// Rare path (non-integer count, count >= LGTAB_N or r >= 1e4): generic lgamma / digamma.  Kept out of
-// line so that the hot epilogue loop stays small enough for the instruction cache.
-static __device__ __noinline__ float2 nb_count_slow(float r, float x, bool bwd) {
-  float2 o;
-  o.x = lgammaf(r + x) - lgammaf(r) - lgammaf(1.f + x);
-  o.y = bwd ? digamma_pos(r + x) - digamma_pos(r) : 0.f;
-  return o;
+// ---------------------------------------------------------------------------------------------
+// packed fp32 pairs: sm_100 has FFMA2 / FMUL2 / FADD2 (PTX fma/mul/add/sub .f32x2 on 64-bit
+// registers).  One issue slot does the same operation on two elements: the NB epilogue is bound by
+// instruction issue, so its arithmetic runs on element PAIRS.
+// ---------------------------------------------------------------------------------------------
+struct f2 {
+  unsigned long long v;
+};
+__device__ __forceinline__ f2 mk2(float a, float b) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ f2 bc2(float a) { return mk2(a, a); }
+__device__ __forceinline__ void un2(f2 p, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p.v)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  f2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  f2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+  f2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
 }
 
-// NV elements of the NB block per thread (straight-line code; the NV independent elements give
-// the instruction-level parallelism).
+// The fast route of the NB element math covers integer counts 0 <= x < LGTAB_N and r < NB_R_BIG; everything
+// else (a warp-rare event with real data) goes through nb_elem_generic.  NB_R_BIG is where the fast route's
+// error takes off: it forms (r + 7/2) log((r+x+4) / (r+4)) from two MUFU.LG2 results whose relative error
+// (2^-22) is multiplied by r log2 r - ~5e-3 absolute per element at r = 2048, twice that at 4096
+// (tools/nb_math_probe.py; the reference's own fp32 arithmetic, lgamma(r+x) - lgamma(r), loses as much there).
+// The generic route uses log1p / the Stirling difference in a form without large cancelling terms.
+constexpr float NB_R_BIG = 2048.f;
+
+// Generic route: any count x >= 0 (non-integer, >= LGTAB_N), any r.  Out of line so that the hot epilogue loop
+// stays small (instruction cache); precision first.
+//   lgamma(r+x) - lgamma(r) and psi(r+x) - psi(r):
+//     r >= 32: Stirling without shift, differences formed analytically (u = x / r):
+//        (r - 1/2) log1p(u) + x (log(r+x) - 1) + [S(r+x) - S(r)],   S(y) = 1/(12y) - 1/(360y^3)
+//        log1p(u) - (i1 - i0)/2 - (i1^2 - i0^2)/12 + (i1^4 - i0^4)/120,   i0 = 1/r, i1 = 1/(r+x)
+//     r <  32: lgammaf / digamma differences (magnitudes <= ~100: no harmful cancellation)
+// returns (ll, a, ndrho) by value: reference outputs of an out-of-line function would live on the stack
+template <bool BWD>
+static __device__ __noinline__ float3 nb_elem_generic(float lsl, float rho, float x, float eps, float rshift_l2e) {
+  float ll, a, ndrho;
+  const float rexp = exp2f(__fmaf_rn(rho, 1.4426950408889634f, rshift_l2e));
+  const float r = rexp + eps;
+  const float ell = lsl - rho;
+  const float e = expf(-fabsf(ell));
+  const float L = log1pf(e);
+  const float spp = L + fmaxf(ell, 0.f), spn = L + fmaxf(-ell, 0.f);  // softplus(ell), softplus(-ell)
+  float cnt = 0.f, psd = 0.f;
+  if (x != 0.f) {
+    const float rx = r + x;
+    if (r >= 32.f) {
+      const float i0 = 1.f / r, i1 = 1.f / rx;
+      const float l1p = log1pf(x * i0);
+      const float d = -x * i0 * i1;  // i1 - i0
+      const float s = i0 + i1, p = i0 * i1, s2 = s * s;
+      cnt = (r - 0.5f) * l1p + x * (logf(rx) - 1.f) + d * (8.3333333333e-2f - (s2 - p) * 2.7777777778e-3f);
+      if (BWD) psd = l1p - d * (0.5f + s * (8.3333333333e-2f - (s2 - 2.f * p) * 8.3333333333e-3f));
+    } else {
+      cnt = lgammaf(rx) - lgammaf(r);
+      if (BWD) psd = digamma_pos(rx) - digamma_pos(r);
+    }
+    cnt -= lgammaf(1.f + x);
+  }
+  ll = cnt - x * spn - r * spp;
+  if (BWD) {
+    const float inv = 1.f / (1.f + e);
+    const float sg = ell >= 0.f ? inv : e * inv, sn = ell >= 0.f ? e * inv : inv;  // sigmoid(ell), sigmoid(-ell)
+    a = x * sn - r * sg;
+    ndrho = rexp * (spp - psd) + a;
+  } else {
+    a = 0.f;
+    ndrho = 0.f;
+  }
+  return make_float3(ll, a, ndrho);
+}
+
+// Two elements of the NB block on packed registers (straight-line code).
 //   lsl = library + s - logsumexp(s)  (so ell = lsl - rho),  rho = log_r,  x = count >= 0.
 // Follows torch.distributions.NegativeBinomial.log_prob (negative_binomial.py:130-150):
-//   r logsig(-ell) + x logsig(ell) + lgamma(r+x) - lgamma(1+x) - lgamma(r),   r = e^rho + eps
-// written as  x ell - (x + r) softplus(ell) + [lgamma(r+x) - lgamma(r)] - log(x!).
-// The bracket and psi(r+x) - psi(r) are formed as DIFFERENCES of shifted Stirling series
-//   lgamma(y) = F(y+4) - log(y(y+1)(y+2)(y+3)),  F(z) = (z-1/2) log z - z + 1/(12z) - 1/(360z^3)
-//   psi(y)    = G(y+4) - Q'(y)/Q(y),             G(z) = log z - 1/(2z) - 1/(12z^2) + 1/(120z^4)
-// (truncation error < 1e-6 for z >= 4; the constant log(2 pi)/2 cancels in the difference), with
-// log(x!) from a 32-entry shared-memory table; x = 0 returns exactly 0.  Counts >= 32 or
-// non-integer take the generic lgamma / digamma route.  No int<->float conversions (they share
-// the SFU pipe with the transcendentals).
-template <bool BWD, int NV>
+//   ll = r logsig(-ell) + x logsig(ell) + lgamma(r+x) - lgamma(1+x) - lgamma(r),   r = e^rho + eps
+//      = cnt - x softplus(-ell) - r softplus(ell),          cnt = lgamma(r+x) - lgamma(r) - log(x!)
+//   a     = dLL/d ell = x sigmoid(-ell) - r sigmoid(ell)                     
+//   ndrho = -dLL/d rho = e^rho (softplus(ell) - [psi(r+x) - psi(r)]) + a
+// lgamma(r+x) - lgamma(r) and psi(r+x) - psi(r) are DIFFERENCES of shifted Stirling series
+//   lgamma(y) = F(y+4) - log Q(y),  F(z) = (z-1/2) log z - z + 1/(12z) - 1/(360z^3),  Q(y) = y(y+1)(y+2)(y+3)
+//   psi(y)    = G(y+4) - Q'(y)/Q(y),  G(z) = log z - 1/(2z) - 1/(12z^2) + 1/(120z^4)
+// (truncation < 1e-6 for z >= 4) with every difference taken analytically, in terms of
+//   y0 = r+4, y1 = r+x+4, i01 = 1/(y0 y1), dpos = x i01 = 1/y0 - 1/y1, s = (y0+y1) i01 = 1/y0 + 1/y1:
+//   F(y1)-F(y0) = x log y1 + (y0-1/2) log(y1/y0) - x - dpos (1/12 - (s^2 - i01)/360)
+//   G(y1)-G(y0) = log(y1/y0) + dpos (1/2 + s (1/12 - (s^2 - 2 i01)/120))
+//   Q'/Q(r+x) - Q'/Q(r) = (Q'(r+x) Q(r) - Q'(r) Q(r+x)) / (Q(r) Q(r+x))
+// so x = 0 gives exactly 0 and nothing of size r log r is subtracted from anything.  8 MUFU per element
+// (2 ex2, 4 lg2, 2 rcp: the reciprocals of y0 y1 (1 + e^-|ell|) and of Q(r) Q(r+x) serve five quotients);
+// log(x!) from the shared-memory table.  No int<->float conversions (they share the SFU pipe).
 // rshift_l2e: log2(e) times the per-cell shift added to log_r for the COUNT parameter only
 // (r = exp(rho + shift) + eps; ell keeps the unshifted rho) - MCVNBVAE's data-split adjustment,
 // mcv_nbvae.py:78-79; 0 for NBVAE / DRNBVAE.  It rides in the FFMA that feeds ex2: no extra instruction.
-__device__ __forceinline__ void nb_elems(const float (&lsl)[NV], const float (&rho)[NV], const float (&x)[NV], float eps,
-                                         const float* __restrict__ lgtab, NbElem (&o)[NV], float rshift_l2e = 0.f) {
-  const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f, MAGIC = 8388608.f;
-#pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    const float rexp = ex2_approx(__fmaf_rn(rho[v], LOG2E, rshift_l2e));
-    const float r = rexp + eps;
-    const float ell = lsl[v] - rho[v];
-    const float e = ex2_approx(-fabsf(ell) * LOG2E);
-    const float t = 1.f + e;
-    const float sp = __fmaf_rn(lg2_approx(t), LN2, fmaxf(ell, 0.f));  // softplus(ell)
-    const float xr = x[v] + MAGIC;                                     // integer test without F2I/I2F
-    const bool fast = ((xr - MAGIC) == x[v]) && (x[v] < (float)LGTAB_N) && (r < 1.0e8f);
-    // shifted Stirling at y0 = r + 4 and y1 = r + x + 4
-    const float rx = r + x[v];
-    const float y0 = r + 4.f, y1 = rx + 4.f;
-    const float u0 = r * (r + 3.f), w0 = u0 + 2.f, q0 = u0 * w0;      // r(r+1)(r+2)(r+3)
-    const float u1 = rx * (rx + 3.f), w1 = u1 + 2.f, q1 = u1 * w1;
-    const float i0 = rcp_approx(y0), i1 = rcp_approx(y1);
-    const float l0 = lg2_approx(y0) * LN2, l1 = lg2_approx(y1) * LN2;
-    const float i0s = i0 * i0, i1s = i1 * i1;
-    const float iq0 = rcp_approx(q0);
-    const float c0 = i0 * __fmaf_rn(i0s, -2.7777777778e-3f, 8.3333333333e-2f);
-    const float c1 = i1 * __fmaf_rn(i1s, -2.7777777778e-3f, 8.3333333333e-2f);
-    float lgd = __fmaf_rn(y1 - 0.5f, l1, -(y0 - 0.5f) * l0) - x[v] + (c1 - c0) - lg2_approx(q1 * iq0) * LN2;
-    float cnt = lgd - lgtab[__float_as_int(xr) & (LGTAB_N - 1)];
-    float psd = 0.f;
-    if (BWD) {
-      const float iq1 = rcp_approx(q1);
-      const float g0 = l0 - 0.5f * i0 - i0s * __fmaf_rn(i0s, -8.3333333333e-3f, 8.3333333333e-2f);
-      const float g1 = l1 - 0.5f * i1 - i1s * __fmaf_rn(i1s, -8.3333333333e-3f, 8.3333333333e-2f);
-      const float qd0 = (u0 + w0) * __fmaf_rn(2.f, r, 3.f);          // Q'(r)
-      const float qd1 = (u1 + w1) * __fmaf_rn(2.f, rx, 3.f);
-      psd = (g1 - g0) - (qd1 * iq1 - qd0 * iq0);
-    }
-    if (x[v] == 0.f) {
-      cnt = 0.f;
-      psd = 0.f;
-    }
-    if (!fast) {
-      const float2 sl = nb_count_slow(r, x[v], BWD);
-      cnt = sl.x;
-      psd = sl.y;
-    }
-    o[v].ll = __fmaf_rn(x[v], ell, cnt) - rx * sp;
-    if (BWD) {
-      const float inv = rcp_approx(t);
-      const float sig = ell >= 0.f ? inv : e * inv;
-      o[v].a = x[v] - rx * sig;
-      o[v].drho = rexp * (psd - sp) - o[v].a;
-    } else {
-      o[v].a = 0.f;
-      o[v].drho = 0.f;
-    }
-  }
+// Returns false when one of the two elements is outside the fast route's domain (the caller then replaces
+// that element's results with nb_elem_generic's).
+// xb = (x + 2^23) - 2^23: the nearest integer for 0 <= x < 2^22
+__device__ __forceinline__ bool nb_fast_domain(float x, float xb, float r) {
+  return (__float_as_uint(x) < __float_as_uint((float)LGTAB_N)) && (xb == x) && (r < NB_R_BIG);
 }
+__device__ __forceinline__ bool nb_fast_domain(float x, float r) { return nb_fast_domain(x, (x + 8388608.f) - 8388608.f, r); }
 
 template <bool BWD>
-__device__ __forceinline__ NbElem nb_elem(float lsl, float rho, float x, float eps, const float* __restrict__ lgtab) {
-  const float a[1] = {lsl}, b[1] = {rho}, c[1] = {x};
-  NbElem o[1];
-  nb_elems<BWD, 1>(a, b, c, eps, lgtab, o);
-  return o[0];
+__device__ __forceinline__ bool nb_pair(f2 lsl, f2 rho, f2 x, float eps, const float* lgtab, float rshift_l2e, f2& ll,
+                                        f2& a, f2& ndrho) {
+  const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f, MAGIC = 8388608.f;
+  float s0, s1;
+  un2(fma2(rho, bc2(LOG2E), bc2(rshift_l2e)), s0, s1);
+  const f2 rexp = mk2(ex2_approx(s0), ex2_approx(s1));
+  const f2 r = add2(rexp, bc2(eps));
+  const f2 nr = fma2(rexp, bc2(-1.f), bc2(-eps));
+  const f2 ell = sub2(lsl, rho);
+  float el0, el1;
+  un2(ell, el0, el1);
+  const f2 e = mk2(ex2_approx(-fabsf(el0) * LOG2E), ex2_approx(-fabsf(el1) * LOG2E));
+  const f2 t = add2(e, bc2(1.f));
+  un2(t, s0, s1);
+  const f2 spp = fma2(mk2(lg2_approx(s0), lg2_approx(s1)), bc2(LN2), mk2(fmaxf(el0, 0.f), fmaxf(el1, 0.f)));  // softplus(ell)
+  const f2 nspn = sub2(ell, spp);                                                                             // -softplus(-ell)
+  // Q(r), Q(r+x), shifted arguments
+  const f2 rx = add2(r, x);
+  const f2 y0 = add2(r, bc2(4.f)), y1 = add2(rx, bc2(4.f));
+  const f2 u0 = mul2(r, add2(r, bc2(3.f))), q0 = mul2(u0, add2(u0, bc2(2.f)));
+  const f2 u1 = mul2(rx, add2(rx, bc2(3.f))), q1 = mul2(u1, add2(u1, bc2(2.f)));
+  // two reciprocals for five quotients
+  const f2 P = mul2(y0, y1);
+  un2(mul2(P, t), s0, s1);
+  const f2 rP = mk2(rcp_approx(s0), rcp_approx(s1));
+  const f2 i01 = mul2(rP, t), inv = mul2(rP, P);  // 1/(y0 y1), 1/(1 + e)
+  un2(mul2(q0, q1), s0, s1);
+  const f2 rQ = mk2(rcp_approx(s0), rcp_approx(s1));
+  un2(y0, s0, s1);
+  const f2 l0 = mk2(lg2_approx(s0), lg2_approx(s1));
+  un2(y1, s0, s1);
+  const f2 l1 = mk2(lg2_approx(s0), lg2_approx(s1));
+  un2(mul2(mul2(q1, rQ), q1), s0, s1);
+  const f2 lgr = mk2(lg2_approx(s0), lg2_approx(s1));  // log2(Q(r+x) / Q(r))
+  const f2 dl = sub2(l1, l0);                           // log2(y1 / y0)
+  const f2 main = fma2(x, l1, mul2(add2(y0, bc2(-0.5f)), dl));
+  const f2 dpos = mul2(x, i01);
+  const f2 s = mul2(add2(y0, y1), i01);
+  const f2 S2 = mul2(s, s);
+  const f2 cc = mul2(dpos, fma2(sub2(S2, i01), bc2(2.7777777778e-3f), bc2(-8.3333333333e-2f)));
+  // log(x!): table lookup on the integer part (entries outside the fast domain are replaced by the caller)
+  const f2 xr = add2(x, bc2(MAGIC));
+  un2(xr, s0, s1);
+  const f2 lf = mk2(lgtab[__float_as_int(s0) & (LGTAB_N - 1)], lgtab[__float_as_int(s1) & (LGTAB_N - 1)]);
+  const f2 cnt = sub2(fma2(sub2(main, lgr), bc2(LN2), cc), add2(x, lf));
+  ll = fma2(x, nspn, fma2(nr, spp, cnt));
+  float x0, x1, r0, r1, xb0, xb1;
+  un2(x, x0, x1);
+  un2(r, r0, r1);
+  un2(sub2(xr, bc2(MAGIC)), xb0, xb1);
+  const bool fast = nb_fast_domain(x0, xb0, r0) && nb_fast_domain(x1, xb1, r1);
+  if (BWD) {
+    const f2 gd = fma2(dl, bc2(LN2), mul2(dpos, fma2(s, fma2(fma2(i01, bc2(-2.f), S2), bc2(-8.3333333333e-3f), bc2(8.3333333333e-2f)), bc2(0.5f))));
+    // (Q'(r+x) Q(r) - Q'(r) Q(r+x)) / (Q(r) Q(r+x)),  Q'(y) = 2 (u+1) (2y+3),  u = y (y+3)
+    const f2 qd0n = mul2(add2(u0, bc2(1.f)), fma2(r, bc2(-2.f), bc2(-3.f)));
+    const f2 qd1 = mul2(add2(u1, bc2(1.f)), fma2(rx, bc2(2.f), bc2(3.f)));
+    const f2 zq = mul2(fma2(qd1, q0, mul2(qd0n, q1)), rQ);
+    const f2 psd = fma2(zq, bc2(-2.f), gd);  // psi(r+x) - psi(r)
+    const f2 einv = mul2(e, inv);
+    float i0, i1, ei0, ei1;
+    un2(inv, i0, i1);
+    un2(einv, ei0, ei1);
+    const f2 sg = mk2(el0 >= 0.f ? i0 : ei0, el1 >= 0.f ? i1 : ei1);  // sigmoid(ell)
+    const f2 sn = mk2(el0 >= 0.f ? ei0 : i0, el1 >= 0.f ? ei1 : i1);  // sigmoid(-ell)
+    a = fma2(x, sn, mul2(nr, sg));
+    ndrho = fma2(rexp, sub2(spp, psd), a);
+  }
+  return fast;
+}
+
+// Result of one (cell, gene) element of the NB block (scalar interface of the CUDA-core path).
+struct NbElem {
+  float ll;    // log NB(x | r, logits=ell)
+  float a;     // dLL/d ell = x sigmoid(-ell) - r sigmoid(ell)
+  float drho;  // dLL/d rho = e^rho (psi(r+x) - psi(r) - softplus(ell)) - a
+};
+
+// NV (even) elements per thread through nb_pair; elements outside the fast domain are redone by the generic route.
+template <bool BWD, int NV>
+__device__ __forceinline__ void nb_elems(const float (&lsl)[NV], const float (&rho)[NV], const float (&x)[NV], float eps,
+                                         const float* __restrict__ lgtab, NbElem (&o)[NV], float rshift_l2e = 0.f) {
+  static_assert(NV % 2 == 0, "pairs");
+  bool fast = true;
+#pragma unroll
+  for (int v = 0; v < NV; v += 2) {
+    f2 ll, a = bc2(0.f), nd = bc2(0.f);
+    fast &= nb_pair<BWD>(mk2(lsl[v], lsl[v + 1]), mk2(rho[v], rho[v + 1]), mk2(x[v], x[v + 1]), eps, lgtab, rshift_l2e, ll, a, nd);
+    un2(ll, o[v].ll, o[v + 1].ll);
+    un2(a, o[v].a, o[v + 1].a);
+    float n0, n1;
+    un2(nd, n0, n1);
+    o[v].drho = -n0;
+    o[v + 1].drho = -n1;
+  }
+  if (!fast) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const float r = exp2f(__fmaf_rn(rho[v], 1.4426950408889634f, rshift_l2e)) + eps;
+      if (!nb_fast_domain(x[v], r)) {
+        const float3 g = nb_elem_generic<BWD>(lsl[v], rho[v], x[v], eps, rshift_l2e);
+        o[v].ll = g.x;
+        o[v].a = g.y;
+        o[v].drho = -g.z;
+      }
+    }
+  }
 }
 
 // softplus / its derivative exactly as torch.nn.functional.softplus (beta=1, threshold=20)

@@ -239,7 +239,7 @@ __global__ void k_bump(int64_t* c, int n) {
 // loss (ll may be null: the CUDA-core NB kernel adds it itself), status word + NaN flag.
 __global__ void __launch_bounds__(256) k_finalize_step(drv_step_out* out, const uint32_t* status, int64_t* c, int n,
                                                        const float* __restrict__ ll, int B, float scale,
-                                                       float* __restrict__ loss_slot) {
+                                                       float* __restrict__ loss_slot, uint32_t path) {
   pdl_prologue();
   const int i = threadIdx.x;
   if (c && i < n) c[i] += 1;
@@ -255,10 +255,18 @@ __global__ void __launch_bounds__(256) k_finalize_step(drv_step_out* out, const 
     for (int w = 0; w < (int)blockDim.x / 32; ++w) s += sh[w];
     const double loss = out->loss - (double)scale * s;
     out->loss = loss;
-    if (loss_slot) *loss_slot = (float)loss;  // data parallel: the loss rides in the gradient buffer's tail slot
     uint32_t st = *status;
     if (isnan(loss)) st |= DRV_STATUS_NAN_LOSS;
+    if (loss_slot) {
+      // data parallel: the loss and the status bits ride in the gradient buffer's tail slots, one float per bit, so
+      // that the SUM all-reduce leaves "how many ranks raised it" and every rank sees the same loss and status
+      loss_slot[0] = (float)loss;
+      loss_slot[1] = (st & DRV_STATUS_NAN_LOSS) ? 1.f : 0.f;
+      loss_slot[2] = (st & DRV_STATUS_MISSING_CLASS) ? 1.f : 0.f;
+      loss_slot[3] = (st & DRV_STATUS_BAD_LABEL) ? 1.f : 0.f;
+    }
     out->status = st;
+    out->path = path;
   }
 }
 
@@ -332,8 +340,8 @@ void bump_counters(int64_t* counters, int n, cudaStream_t st) {
 }
 
 void finalize_step(drv_step_out* out, const uint32_t* status, int64_t* counters, int n, const float* ll, int B,
-                   float scale, cudaStream_t st, float* loss_slot) {
-  launch_k(k_finalize_step, 1, 256, 0, st, out, status, counters, n, ll, B, scale, loss_slot);
+                   float scale, cudaStream_t st, float* loss_slot, uint32_t path) {
+  launch_k(k_finalize_step, 1, 256, 0, st, out, status, counters, n, ll, B, scale, loss_slot, path);
   note_launch();
 }
 

@@ -77,9 +77,9 @@ void dr_prior_factor(const float* w_prior, const float* b_prior, const float* ep
                      float* d_bias_loc, float* d_bias_scale_unc, drv_step_out* out, cudaStream_t st);
 
 // counters[i] += 1 (BatchNorm num_batches_tracked; may be null), out->status = *status | NaN flag
-// ... and out->loss -= scale * sum_b ll[b] (ll may be null)
+// ... and out->loss -= scale * sum_b ll[b] (ll may be null); out->path = path (which kernels ran)
 void finalize_step(drv_step_out* out, const uint32_t* status, int64_t* counters, int n, const float* ll, int B,
-                   float scale, cudaStream_t st, float* loss_slot = nullptr);
+                   float scale, cudaStream_t st, float* loss_slot = nullptr, uint32_t path = 0);
 
 // ---- k_optim.cu ------------------------------------------------------------------------------------
 int aggmo_step(const long long* offs, const long long* lens, int n_tensors, const drv_aggmo& hp, float* params,

@@ -516,6 +516,9 @@ static int elbo_step_impl(const drv_dims* dims, const drv_hparams* hp, const flo
   // ---- model: decoder trunk (nbvae.py:70 -> modules.py:93) ------------------------------------
   const Block& last = n.dec[NB - 1];
   const bool use_tc = tc_decoder_supported(d, *hp) && !(hp->flags & 16);
+  // drv_step_out.path: bit 0 = tcgen05 decoder kernels, bit 1 = tcgen05 encoder input layer
+  const uint32_t path = (use_tc ? 1u : 0u) |
+                        ((p.tcb[0][0] && tc_block_forward_supported(B, n.enc[0].din, n.enc[0].dout, *hp) && !(hp->flags & 32)) ? 2u : 0u);
   bool dec_sd = false;
   for (int k = 0; k < NB - 1; ++k) dec_sd = block_forward(c, 1, k, z, true, dec_sd);
   block_forward(c, 1, NB - 1, z, false, dec_sd);  // statistics of the last BatchNorm only
@@ -575,7 +578,7 @@ static int elbo_step_impl(const drv_dims* dims, const drv_hparams* hp, const flo
       // decoder / dose-response gradients and the loss are final: hand back to the caller
       if (side) side->join(st);
       finalize_step(out, status, nullptr, 0, use_tc ? c.at<float>(p.ll) : nullptr, B, hp->scale_factor, st,
-                    grads + n.n_param_floats);  // loss -> tail slot of the gradient buffer (one collective carries both)
+                    grads + n.n_param_floats, path);  // loss -> tail slot of the gradient buffer (one collective carries both)
       return finish();
     }
     // ---- encoder backward ----------------------------------------------------------------------
@@ -587,7 +590,7 @@ static int elbo_step_impl(const drv_dims* dims, const drv_hparams* hp, const flo
   // BatchNorm batch counters + status word folded into the result record: one launch
   finalize_step(out, status, (bn_batches && !(hp->flags & DRV_FLAG_NO_BN_UPDATE)) ? bn_batches : nullptr, n.n_bn,
                 use_tc ? c.at<float>(p.ll) : nullptr, B, hp->scale_factor, st,
-                (bwd && (hp->flags & DRV_FLAG_LOSS_IN_GRADS)) ? grads + n.n_param_floats : nullptr);
+                (bwd && (hp->flags & DRV_FLAG_LOSS_IN_GRADS)) ? grads + n.n_param_floats : nullptr, path);
   if (prof::enabled && prof::n_steps < prof::MAX_STEPS) {
     if (!bwd) for (int i = 5; i <= DRV_N_SECTIONS; ++i) prof::mark(i, st);
     ++prof::n_steps;

@@ -132,6 +132,20 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// shared-memory accesses of the epilogue loops by 32-bit shared address: the tile pointers are derived from the
+// run-time-aligned dynamic buffer, which the compiler treats as generic (LD / ST + 64-bit address arithmetic)
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
 template <int PHASE, bool WITH_A, bool H16>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtensorMap tmW,
@@ -169,7 +183,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
   uint64_t* o_full = x_empty + 2;         // [2] output tile complete in shared memory (TSTORE)
   uint64_t* o_empty = o_full + 2;         // [2] output tile read by the TMA store (H16 phase 2)
   uint32_t* tmem_slot = (uint32_t*)(o_empty + 2);
-  float* lgtab = (float*)(tmem_slot + 4);
+  __shared__ float lgtab[LGTAB_N];  // static: the compiler then knows the table lookups are shared-memory loads
   load_lgamma_table(lgtab, threadIdx.x);
 
   constexpr int TN = PHASE == 2 ? 64 : 128;  // genes per tile (phases 1 and 3 cover the scale half only)
@@ -305,7 +319,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
     const int q = warp % 4;    // TMEM lane quarter
     const int cg = warp / 4;   // column group
     const int r = q * 32 + lane;
-    float ll_acc = 0.f, a_acc = 0.f;
+    f2 ll_acc2 = bc2(0.f), a_acc2 = bc2(0.f);  // phase 2: packed partial sums (both halves are added at the flush)
     float m_run = -INFINITY, s_run = 0.f;  // phase 1: online (max, sum exp) over this CTA's tiles of a cell tile
     auto flush_lse = [&](int ct_done, int row) {
       // slot = ordinal of this CTA among the CTAs whose tile range overlaps the cell tile
@@ -314,20 +328,33 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
       p.part_m[slot] = m_run;
       p.part_s[slot] = s_run;
     };
+    // shared-space addresses and swizzle terms of this thread's row, made opaque so that the compiler keeps them in
+    // registers (it otherwise re-derives them from %tid and the shared window in every trip of the hot loop)
+    uint32_t xbuf_row_s = smem_u32(xbuf) + (uint32_t)((cg >> 1) * (BM * 128) + r * 128);
+    uint32_t rbuf_row_s = smem_u32(rbuf) + (uint32_t)(r * 128);
+    uint32_t r7 = (uint32_t)(r & 7);
+    uint32_t c4 = (uint32_t)((cg & 1) * 4), cg2 = (uint32_t)(2 * cg), cg16 = (uint32_t)(cg * 16);
+    asm volatile("" : "+r"(xbuf_row_s), "+r"(rbuf_row_s), "+r"(r7), "+r"(c4), "+r"(cg2), "+r"(cg16));
     int cur_ct = -1;
     float lib_b = 0.f, lse_b = 0.f, asum_b = 0.f, rs_b = 0.f;
     int b = 0;
     bool row_ok = false;
+    auto flush_ll = [&]() {
+      float s0, s1;
+      un2(ll_acc2, s0, s1);
+      atomicAdd(&p.ll[b], s0 + s1);
+      if (WITH_A) {
+        un2(a_acc2, s0, s1);
+        atomicAdd(&p.asum[b], s0 + s1);
+      }
+    };
     for (int t = t0, it = 0; t < t1; ++t, ++it) {
       const int ct = t / n_gt, gt = t % n_gt;
       const int as = it & 1, aph = (it >> 1) & 1;
       if (ct != cur_ct) {
-        if (PHASE == 2 && cur_ct >= 0 && row_ok) {
-          atomicAdd(&p.ll[b], ll_acc);
-          if (WITH_A) atomicAdd(&p.asum[b], a_acc);
-        }
+        if (PHASE == 2 && cur_ct >= 0 && row_ok) flush_ll();
         if (PHASE == 1 && cur_ct >= 0 && row_ok) flush_lse(cur_ct, b);
-        ll_acc = a_acc = 0.f;
+        ll_acc2 = a_acc2 = bc2(0.f);
         m_run = -INFINITY;
         s_run = 0.f;
         cur_ct = ct;
@@ -510,13 +537,18 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
         mbar_wait(&x_full[xs], xph);
         if (H16 && WITH_A) mbar_wait(&o_empty[xs], xph ^ 1);  // the TMA store of this slot's previous tile has read it
         const int gbase = g0 + cg * 16;
-        const float lml = lib_b - lse_b;
-        uint8_t* xrow = xbuf + xs * XB + (cg >> 1) * (BM * 128) + r * 128;
-        uint8_t* rrow = rbuf + xs * RB + (cg >> 1) * (BM * 128) + r * 128;
+        const f2 lml2 = bc2(lib_b - lse_b);
+        // count tile: box (cg/2), row r; fp16 output tiles: ds' slot, drho slot = + BM * 128 (H16); fp32 tiles: ds'
+        // over the counts, drho in rbuf
+        const uint32_t xrow_s = xbuf_row_s + (uint32_t)(xs * XB);
+        const uint32_t orow_s = rbuf_row_s + (uint32_t)(xs * RB);
+        const uint32_t rrow_s = orow_s + (uint32_t)((cg >> 1) * (BM * 128));
+        const float* bias_s = p.bias + gbase;  // scale half; the log_r half is p.G floats further
         const bool full_cols = gbase + 16 <= p.G;
         float sv_n[4], rv_n[4];
-        tmem_ld4(tbase + cg * 16, sv_n);
-        tmem_ld4(tbase + 64 + cg * 16, rv_n);
+        const uint32_t tcol = tbase + cg16;  // this warp's 16 scale columns; the log_r columns are 64 further
+        tmem_ld4(tcol, sv_n);
+        tmem_ld4(tcol + 64, rv_n);
         tmem_ld_wait();
         // interior tiles (all 128 cells and 64 genes valid) take a copy of the loop without the validity
         // selects; TMA zero-fills / clips the edges, so only the edge tiles need masking for the sums
@@ -524,25 +556,22 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
         constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll 1
         for (int g4 = 0; g4 < 4; ++g4) {
-          float sv[4], rv[4], xv[4], bs[4], br[4];
+          float sv[4], rv[4], bs[4], br[4];
 #pragma unroll
           for (int v = 0; v < 4; ++v) { sv[v] = sv_n[v]; rv[v] = rv_n[v]; }
           {
             // next group's logits: in flight while this group's NB terms are evaluated
             const int gn = g4 + 1 < 4 ? g4 + 1 : g4;
-            tmem_ld4(tbase + cg * 16 + gn * 4, sv_n);
-            tmem_ld4(tbase + 64 + cg * 16 + gn * 4, rv_n);
+            tmem_ld4(tcol + gn * 4, sv_n);
+            tmem_ld4(tcol + 64 + gn * 4, rv_n);
           }
-          // count tile: box (cg/2), row r, 16-byte chunk (cg%2)*4 + g4, XOR-swizzled with r%8
-          const int chunk = ((cg & 1) * 4 + g4) ^ (r & 7);
-          {
-            const float4 f = *reinterpret_cast<const float4*>(xrow + chunk * 16);
-            xv[0] = f.x; xv[1] = f.y; xv[2] = f.z; xv[3] = f.w;
-          }
+          // count tile: 16-byte chunk (cg%2)*4 + g4, XOR-swizzled with r%8
+          const uint32_t chunk = (c4 + (uint32_t)g4) ^ r7;
+          float4 xf = lds128(xrow_s + chunk * 16);
           const int gq = gbase + 4 * g4;
           if (!MASKED || full_cols) {  // warp-uniform addresses -> broadcast loads
-            const float4 f = __ldg(reinterpret_cast<const float4*>(p.bias + gq));
-            const float4 h2 = __ldg(reinterpret_cast<const float4*>(p.bias + p.G + gq));
+            const float4 f = __ldg(reinterpret_cast<const float4*>(bias_s + 4 * g4));
+            const float4 h2 = __ldg(reinterpret_cast<const float4*>(bias_s + p.G + 4 * g4));
             bs[0] = f.x; bs[1] = f.y; bs[2] = f.z; bs[3] = f.w;
             br[0] = h2.x; br[1] = h2.y; br[2] = h2.z; br[3] = h2.w;
           } else {
@@ -553,52 +582,87 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
               br[v] = okg ? __ldg(&p.bias[p.G + gq + v]) : 0.f;
             }
           }
-          float a_lsl[4], a_rho[4], a_x[4];
           bool ok[4];
+          if (MASKED) {
+            // edge tile: out-of-range entries become benign (lsl = rho = x = 0) and are dropped from the sums
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            ok[v] = !MASKED || (row_ok && (gq + v < p.G));
-            a_lsl[v] = ok[v] ? lml + sv[v] + bs[v] : 0.f;
-            a_rho[v] = ok[v] ? rv[v] + br[v] : 0.f;
-            a_x[v] = ok[v] ? xv[v] : 0.f;
+            for (int v = 0; v < 4; ++v) ok[v] = row_ok && (gq + v < p.G);
+            if (!ok[0]) { sv[0] = bs[0] = rv[0] = br[0] = xf.x = 0.f; }
+            if (!ok[1]) { sv[1] = bs[1] = rv[1] = br[1] = xf.y = 0.f; }
+            if (!ok[2]) { sv[2] = bs[2] = rv[2] = br[2] = xf.z = 0.f; }
+            if (!ok[3]) { sv[3] = bs[3] = rv[3] = br[3] = xf.w = 0.f; }
           }
-          NbElem e[4];
-          nb_elems<WITH_A, 4>(a_lsl, a_rho, a_x, p.eps, lgtab, e, rs_b);
+          f2 lsl[2], rho[2], xv[2], ll[2], av[2], nd[2];
+          const f2 lmlA = MASKED ? mk2(ok[0] ? lib_b - lse_b : 0.f, ok[1] ? lib_b - lse_b : 0.f) : lml2;
+          const f2 lmlB = MASKED ? mk2(ok[2] ? lib_b - lse_b : 0.f, ok[3] ? lib_b - lse_b : 0.f) : lml2;
+          lsl[0] = add2(add2(mk2(sv[0], sv[1]), mk2(bs[0], bs[1])), lmlA);
+          lsl[1] = add2(add2(mk2(sv[2], sv[3]), mk2(bs[2], bs[3])), lmlB);
+          rho[0] = add2(mk2(rv[0], rv[1]), mk2(br[0], br[1]));
+          rho[1] = add2(mk2(rv[2], rv[3]), mk2(br[2], br[3]));
+          xv[0] = mk2(xf.x, xf.y);
+          xv[1] = mk2(xf.z, xf.w);
+          av[0] = av[1] = nd[0] = nd[1] = bc2(0.f);
+          bool fast = nb_pair<WITH_A>(lsl[0], rho[0], xv[0], p.eps, lgtab, rs_b, ll[0], av[0], nd[0]);
+          fast &= nb_pair<WITH_A>(lsl[1], rho[1], xv[1], p.eps, lgtab, rs_b, ll[1], av[1], nd[1]);
+          if (!fast) {
+            // rare: counts >= LGTAB_N / non-integer, or r >= NB_R_BIG - those elements are redone by the generic route
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            if (ok[v]) {
-              ll_acc += e[v].ll;
-              if (WITH_A) a_acc += e[v].a;
+            for (int h = 0; h < 2; ++h) {
+              float l2[2], r2[2], x2[2], o_ll[2], o_a[2], o_nd[2];
+              un2(lsl[h], l2[0], l2[1]); un2(rho[h], r2[0], r2[1]); un2(xv[h], x2[0], x2[1]);
+              un2(ll[h], o_ll[0], o_ll[1]); un2(av[h], o_a[0], o_a[1]); un2(nd[h], o_nd[0], o_nd[1]);
+#pragma unroll
+              for (int v = 0; v < 2; ++v) {
+                const float rr = exp2f(__fmaf_rn(r2[v], 1.4426950408889634f, rs_b)) + p.eps;
+                if (!nb_fast_domain(x2[v], rr)) {  // (scalar form of the test: this block is off the hot path)
+                  const float3 g = nb_elem_generic<WITH_A>(l2[v], r2[v], x2[v], p.eps, rs_b);
+                  o_ll[v] = g.x; o_a[v] = g.y; o_nd[v] = g.z;
+                }
+              }
+              ll[h] = mk2(o_ll[0], o_ll[1]); av[h] = mk2(o_a[0], o_a[1]); nd[h] = mk2(o_nd[0], o_nd[1]);
             }
           }
+          if (MASKED) {
+            float t0, t1, t2, t3;
+            un2(ll[0], t0, t1); un2(ll[1], t2, t3);
+            ll[0] = mk2(ok[0] ? t0 : 0.f, ok[1] ? t1 : 0.f); ll[1] = mk2(ok[2] ? t2 : 0.f, ok[3] ? t3 : 0.f);
+            if (WITH_A) {
+              un2(av[0], t0, t1); un2(av[1], t2, t3);
+              av[0] = mk2(ok[0] ? t0 : 0.f, ok[1] ? t1 : 0.f); av[1] = mk2(ok[2] ? t2 : 0.f, ok[3] ? t3 : 0.f);
+              un2(nd[0], t0, t1); un2(nd[1], t2, t3);
+              nd[0] = mk2(ok[0] ? t0 : 0.f, ok[1] ? t1 : 0.f); nd[1] = mk2(ok[2] ? t2 : 0.f, ok[3] ? t3 : 0.f);
+            }
+          }
+          ll_acc2 = add2(ll_acc2, add2(ll[0], ll[1]));
+          if (WITH_A) a_acc2 = add2(a_acc2, add2(av[0], av[1]));
           if (WITH_A && H16) {
-            // fp16 tiles, pre-scaled by DL_SCALE / c: 4 genes = 8 bytes of chunk 2 cg + g4 / 2 of this row
-            float dsp[4], drs[4], dr[4];
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              dsp[v] = ok[v] ? -DL_SCALE * e[v].a : 0.f;
-              drs[v] = ok[v] ? -DL_SCALE * e[v].drho : 0.f;
-              dr[v] = ok[v] ? -p.c * e[v].drho : 0.f;
-            }
-            uint8_t* ocell = rbuf + xs * RB + r * 128 + (((2 * cg + (g4 >> 1)) ^ (r & 7)) * 16) + (g4 & 1) * 8;
-            *reinterpret_cast<uint2*>(ocell) = make_uint2(pack_h2_sat(dsp[0], dsp[1]), pack_h2_sat(dsp[2], dsp[3]));
-            *reinterpret_cast<uint2*>(ocell + BM * 128) = make_uint2(pack_h2_sat(drs[0], drs[1]), pack_h2_sat(drs[2], drs[3]));
-            const int col = butterfly4(dr, lane);
-            if (col >= 0 && (!MASKED || gq + col < p.G)) atomicAdd(&p.db[p.G + gq + col], dr[0]);
+            // fp16 tiles, pre-scaled by DL_SCALE / c: ds' = -DL_SCALE a, drho' = -DL_SCALE dLL/drho = DL_SCALE ndrho;
+            // 4 genes = 8 bytes of chunk 2 cg + g4 / 2 of this row
+            float d[4], q[4];
+            un2(mul2(av[0], bc2(-DL_SCALE)), d[0], d[1]);
+            un2(mul2(av[1], bc2(-DL_SCALE)), d[2], d[3]);
+            un2(mul2(nd[0], bc2(DL_SCALE)), q[0], q[1]);
+            un2(mul2(nd[1], bc2(DL_SCALE)), q[2], q[3]);
+            const uint32_t ocell = orow_s + (((cg2 + (uint32_t)(g4 >> 1)) ^ r7) * 16) + (uint32_t)((g4 & 1) * 8);
+            sts64(ocell, pack_h2_sat(d[0], d[1]), pack_h2_sat(d[2], d[3]));
+            sts64(ocell + BM * 128, pack_h2_sat(q[0], q[1]), pack_h2_sat(q[2], q[3]));
+            // bias gradient of the log_r half: column sums over the 32 rows of this warp
+            const int col = butterfly4(q, lane);
+            if (col >= 0 && (!MASKED || gq + col < p.G)) atomicAdd(&p.db[p.G + gq + col], q[0] * (p.c * (1.f / DL_SCALE)));
           } else if (WITH_A) {
-            float dsp[4], dr[4];
+            float d[4], q[4];
+            un2(mul2(av[0], bc2(-p.c)), d[0], d[1]);
+            un2(mul2(av[1], bc2(-p.c)), d[2], d[3]);
+            un2(mul2(nd[0], bc2(p.c)), q[0], q[1]);
+            un2(mul2(nd[1], bc2(p.c)), q[2], q[3]);
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              dsp[v] = ok[v] ? -p.c * e[v].a : 0.f;
-              dr[v] = ok[v] ? rna_tf32(-p.c * e[v].drho) : 0.f;  // tf32 MMA operand of dW / dAct
-            }
+            for (int v = 0; v < 4; ++v) q[v] = rna_tf32(q[v]);  // tf32 MMA operand of dW / dAct
             // ds' overwrites the counts it was computed from (same swizzled chunk), drho goes to its own
             // tile; the store warp ships both (TMA clips rows >= B and genes >= G)
-            *reinterpret_cast<float4*>(xrow + chunk * 16) = make_float4(dsp[0], dsp[1], dsp[2], dsp[3]);
-            *reinterpret_cast<float4*>(rrow + chunk * 16) = make_float4(dr[0], dr[1], dr[2], dr[3]);
-            // bias gradient of the log_r half: column sums over the 32 rows of this warp
-            const int col = butterfly4(dr, lane);
-            if (col >= 0 && (!MASKED || gq + col < p.G)) atomicAdd(&p.db[p.G + gq + col], dr[0]);
+            sts128(xrow_s + chunk * 16, d[0], d[1], d[2], d[3]);
+            sts128(rrow_s + chunk * 16, q[0], q[1], q[2], q[3]);
+            const int col = butterfly4(q, lane);
+            if (col >= 0 && (!MASKED || gq + col < p.G)) atomicAdd(&p.db[p.G + gq + col], q[0]);
           }
           tmem_ld_wait();
         }
@@ -615,10 +679,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
         }
       }
     }
-    if (PHASE == 2 && cur_ct >= 0 && row_ok) {
-      atomicAdd(&p.ll[b], ll_acc);
-      if (WITH_A) atomicAdd(&p.asum[b], a_acc);
-    }
+    if (PHASE == 2 && cur_ct >= 0 && row_ok) flush_ll();
     if (PHASE == 1 && cur_ct >= 0 && row_ok) flush_lse(cur_ct, b);
   }
   tc_fence_before();

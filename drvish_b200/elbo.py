@@ -9,8 +9,12 @@ call into ``drv_elbo_step`` (no tracing, no autograd graph).  Gradients are left
 buffers are updated in place, and the Python float loss is returned.
 
 Data parallel: with ``torch.distributed`` initialised (one process per GPU) the
-flat gradient buffer is summed over ranks with ONE NCCL all-reduce per step; the loss rides in
-the tail slot of the same buffer.  The R-rank result is sum_r reference(shard_r).
+flat gradient buffer is summed over ranks with ONE all-reduce per step; the loss and the status
+bits ride in the tail slots of the same buffer, and every rank RETURNS the summed loss and raises
+on the status bits of ANY rank (so that control flow that depends on the loss - the plateau test of
+``train_until_plateau``, train/__init__.py:97-106 - and errors stay in step on all ranks).
+``loss()`` (``SVI.evaluate_loss``) all-reduces its (loss, status) record the same way.  The R-rank
+result is sum_r reference(shard_r).
 """
 from __future__ import annotations
 
@@ -36,6 +40,8 @@ class FusedTraceELBO:
     :param force_simt: never use the tcgen05 kernels (A/B parity checks).
     """
 
+    STAGING_AFTER_MISSES = 64  # first sightings in a row (per shape) before batches are copied into a staging tile
+
     def __init__(self, num_particles: int = 1, seed: int = 0, data_parallel: Optional[bool] = None,
                  process_group=None, include_guide_factor: bool = True, force_simt: bool = False,
                  update_bn_stats: bool = True, extra_flags: int = 0, use_cuda_graph: bool = True,
@@ -58,6 +64,7 @@ class FusedTraceELBO:
         self.dp_overlap = os.environ.get("DRV_DP_OVERLAP", "0") == "1"
         self._graphs = {}
         self._graph_seen = {}
+        self._staging = {}  # (shape, mode) -> fixed staging tile for loaders that never repeat a buffer address
         self._peer = {}  # id(runtime) -> PeerAllReduce or None (NCCL)
         self._step_ctr = None  # device uint64: steps taken (drives the Philox counters)
 
@@ -117,8 +124,8 @@ class FusedTraceELBO:
         if peer is not None:
             peer.all_reduce()
         else:
-            torch.distributed.all_reduce(rt.flat_grads[:rt.n_param_floats + 1], op=torch.distributed.ReduceOp.SUM,
-                                         group=self.process_group)
+            torch.distributed.all_reduce(rt.flat_grads[:rt.n_param_floats + _lib.DRV_GRAD_TAIL_FLOATS],
+                                         op=torch.distributed.ReduceOp.SUM, group=self.process_group)
 
     def dp_prepare(self, rt) -> None:
         """Set up the peer-memory all-reduce (collective call: every rank, before its first step)."""
@@ -129,6 +136,7 @@ class FusedTraceELBO:
             rt.rebase_grads(peer.data)
             self._graphs.clear()
             self._graph_seen.clear()
+            self._staging.clear()
         self._peer[id(rt)] = peer
 
     def _dp_enabled(self) -> bool:
@@ -197,13 +205,14 @@ class FusedTraceELBO:
         else:
             labels = args[1] if len(args) > 1 else None
             y = self._flatten_y(rt, args[2] if len(args) > 2 else None, rt.device)
-        if want_grads and self._dp_enabled() and not self.dp_overlap:
+        dp = self._dp_enabled()
+        if want_grads and dp and not self.dp_overlap:
             # whole step, then ONE all-reduce of the flat gradient buffer (loss in its tail slot)
             if id(rt) not in self._peer:
                 self.dp_prepare(rt)
             self._enqueue(rt, x, labels, y, True, part=3, mcv=mcv)
             self.dp_all_reduce(rt)
-        elif want_grads and self._dp_enabled():
+        elif want_grads and dp:
             # two-part step: the all-reduce of the decoder + dose-response slice (incl. the loss in the
             # tail slot) runs on NCCL's stream while the encoder backward is still computing
             self._enqueue(rt, x, labels, y, True, part=1, mcv=mcv)  # leaves the loss in flat_grads[n_param_floats]
@@ -219,7 +228,18 @@ class FusedTraceELBO:
         else:
             self._enqueue(rt, x, labels, y, want_grads, mcv=mcv)
         self.step_index += 1
-        loss, status = rt.read_out()
+        if want_grads and dp:
+            # the summed loss and the OR of all ranks' status bits, identical on every rank
+            loss, status = rt.read_tail()
+        else:
+            loss, status = rt.read_out()
+            if dp:  # evaluate_loss under data parallel: one small all-reduce of (loss, status bits)
+                rec = torch.tensor([loss, float(status & 1), float((status >> 1) & 1), float((status >> 2) & 1)],
+                                   dtype=torch.float64, device=rt.device)
+                torch.distributed.all_reduce(rec, op=torch.distributed.ReduceOp.SUM, group=self.process_group)
+                rec = rec.tolist()
+                loss = rec[0]
+                status = (1 if rec[1] > 0 else 0) | (2 if rec[2] > 0 else 0) | (4 if rec[3] > 0 else 0)
         self.last_status = status
         if status & (_lib.DRV_STATUS_MISSING_CLASS | _lib.DRV_STATUS_BAD_LABEL):
             raise RuntimeError("index out of bounds: every class 0..n_classes-1 must occur in the minibatch "
@@ -254,7 +274,36 @@ class FusedTraceELBO:
         if g is not None:
             g.replay()
             return
+        # A stock DataLoader hands over a FRESH tensor every step: no address ever repeats and no graph would ever be
+        # captured.  Once that pattern shows (several first sightings in a row for one shape), the batch is copied into a
+        # fixed staging tile per (shape, mode) - one device-to-device copy instead of ~60 direct launches - and the
+        # graph of the staging tile is replayed.  Loaders that cycle through a few buffers (PinnedBatchPrefetcher,
+        # resident datasets) keep their own addresses and never pay the copy.
+        skey = (tuple(x.shape), want_grads, part, labels is not None, None if mcv is None else tuple(tuple(t.shape) for t in mcv))
+        st = self._staging.get(skey)
+        if st is not None and st["active"] and x.data_ptr() != st["x"].data_ptr():
+            st["x"].copy_(x, non_blocking=True)
+            if labels is not None:
+                st["labels"].copy_(labels, non_blocking=True)
+            smcv = None
+            if mcv is not None:
+                for dst, src in zip(st["mcv"], mcv):
+                    dst.copy_(src, non_blocking=True)
+                smcv = st["mcv"]
+            return self._enqueue(rt, st["x"], st["labels"] if labels is not None else None, y, want_grads, part, smcv)
         seen = self._graph_seen.get(key, 0)
+        if seen == 0 and part != 2:
+            if st is None:
+                st = self._staging[skey] = {"active": False, "misses": 0, "x": None, "labels": None, "mcv": None}
+            st["misses"] += 1
+            if st["misses"] > self.STAGING_AFTER_MISSES and not st["active"]:
+                st["x"] = torch.empty_like(x)
+                st["labels"] = torch.empty_like(labels) if labels is not None else None
+                st["mcv"] = tuple(torch.empty_like(t) for t in mcv) if mcv is not None else None
+                st["active"] = True
+                return self._enqueue(rt, x, labels, y, want_grads, part, mcv)
+        elif st is not None and not st["active"]:
+            st["misses"] = 0  # an address came back: the loader recycles its buffers
         self._graph_seen[key] = seen + 1
         if seen < 1 or len(self._graphs) >= 64:
             if len(self._graph_seen) > 4096:
@@ -265,8 +314,11 @@ class FusedTraceELBO:
         try:
             with torch.cuda.graph(g):
                 eager()
-        except Exception:
-            self.use_cuda_graph = False  # capture unsupported here: stay on direct launches
+        except Exception as e:
+            # capture unsupported here: stay on direct launches - and say so (the step is ~60 launches instead of 1)
+            warnings.warn(f"drvish_b200: CUDA-graph capture of the ELBO step failed ({type(e).__name__}: {e}); "
+                          "continuing with direct kernel launches")
+            self.use_cuda_graph = False
             torch.cuda.synchronize()
             return eager()
         # the graph bakes in raw pointers only; whatever tensor later lives at the same address with

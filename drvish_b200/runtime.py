@@ -58,7 +58,11 @@ class ModelRuntime:
         self._dims: Dict[int, _lib.Dims] = {}
         self._out = None
         self._out_host = None
+        self._tail_host = None
         self.last_launches = 0
+        self.last_path = 0
+        self._scalars: Dict[int, tuple] = {}
+        self._hp_cache: Dict[tuple, _lib.HParams] = {}
         m = model
         self.n_genes = m.encoder.fc[0].num_features
         self.layers = [m.encoder.fc[i].out_features for i in range(2, len(m.encoder.fc) - 1, 3)]
@@ -82,22 +86,37 @@ class ModelRuntime:
             self._dims[n_cells] = d
         return d
 
+    def _scalar(self, v) -> float:
+        """Python float of a scalar hyper-parameter.  With the reference's ``device=`` constructor argument
+        ``epsilon`` / ``l_loc`` / ``l_scale`` / ``sigma_scale`` are CUDA tensors (nbvae.py:44-47): ``float()`` on them
+        is a blocking device-to-host copy - and illegal during CUDA-graph capture - so each tensor is read ONCE and
+        remembered by (identity, version counter)."""
+        if not torch.is_tensor(v):
+            return float(v)
+        key = (id(v), v._version)
+        hit = self._scalars.get(id(v))
+        if hit is None or hit[0] != key:
+            hit = (key, float(v.reshape(-1)[0]), v)  # the tensor is kept alive so that its id stays unique
+            self._scalars[id(v)] = hit
+        return hit[1]
+
     def hparams(self, flags: int = 0, include_guide_factor: bool = True) -> _lib.HParams:
         m = self.model
-        hp = _lib.HParams()
-        hp.scale_factor = float(m.scale_factor)
-        hp.epsilon = float(m.epsilon)
-        hp.lib_loc = float(m.l_loc)
-        hp.lib_scale = float(m.l_scale.reshape(-1)[0])
-        hp.lam_scale = float(self.lmbs[0].lam_scale) if self.lmbs else 1.0
-        hp.bias_scale = float(self.lmbs[0].prior_bias_scale) if self.lmbs else 1.0
-        hp.sigma_scale = float(getattr(m, "sigma_scale", 1.0))
-        hp.alpha = float(self.lmbs[0].alpha) if self.lmbs else 1.0
+        flags = int(flags) | int(os.environ.get("DRVISH_B200_DEBUG_FLAGS", "0"))
+        lmb = self.lmbs[0] if self.lmbs else None
         bn0 = m.encoder.fc[0]
-        hp.bn_eps = float(bn0.eps)
-        hp.bn_momentum = float(bn0.momentum)
-        hp.include_guide_factor = 1 if include_guide_factor else 0
-        hp.flags = int(flags) | int(os.environ.get("DRVISH_B200_DEBUG_FLAGS", "0"))
+        vals = (self._scalar(m.scale_factor), self._scalar(m.epsilon), self._scalar(m.l_loc), self._scalar(m.l_scale),
+                float(lmb.lam_scale) if lmb else 1.0, float(lmb.prior_bias_scale) if lmb else 1.0,
+                self._scalar(getattr(m, "sigma_scale", 1.0)), float(lmb.alpha) if lmb else 1.0, float(bn0.eps),
+                float(bn0.momentum), 1 if include_guide_factor else 0, flags)
+        hp = self._hp_cache.get(vals)
+        if hp is None:
+            hp = _lib.HParams()
+            (hp.scale_factor, hp.epsilon, hp.lib_loc, hp.lib_scale, hp.lam_scale, hp.bias_scale, hp.sigma_scale, hp.alpha,
+             hp.bn_eps, hp.bn_momentum, hp.include_guide_factor, hp.flags) = vals
+            if len(self._hp_cache) > 64:
+                self._hp_cache.clear()
+            self._hp_cache[vals] = hp
         return hp
 
     # ------------------------------------------------------------------------------------
@@ -139,7 +158,8 @@ class ModelRuntime:
         if got != n:
             raise RuntimeError(f"drvish_b200: parameter layout mismatch ({got} tensors from the library, {n} here)")
         flat = torch.zeros(total.value, dtype=torch.float32, device=dev)
-        gflat = torch.zeros(total.value + 32, dtype=torch.float32, device=dev)  # tail slot carries the loss under DP
+        # 32 spare floats: the first DRV_GRAD_TAIL_FLOATS carry the loss and the status bits under data parallel
+        gflat = torch.zeros(total.value + 32, dtype=torch.float32, device=dev)
         self._params, self._param_views, self._grad_views = [], [], []
         for gi, group in enumerate(groups):
             off = offs[gi]
@@ -253,12 +273,27 @@ class ModelRuntime:
         _lib.check(code, "drv_elbo_step")
         self.last_launches = self.lib.drv_last_launch_count()
 
+    def read_tail(self):
+        """Data parallel, after the all-reduce: one 16-byte D2H copy of the gradient buffer's tail slots ->
+        (summed loss, status bits raised by ANY rank).  Identical on every rank."""
+        if self._tail_host is None:
+            self._tail_host = torch.zeros(_lib.DRV_GRAD_TAIL_FLOATS, dtype=torch.float32).pin_memory()
+        n = self.n_param_floats
+        self._tail_host.copy_(self.flat_grads[n:n + _lib.DRV_GRAD_TAIL_FLOATS], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        t = self._tail_host.tolist()
+        status = ((_lib.DRV_STATUS_NAN_LOSS if t[1] > 0 else 0) | (_lib.DRV_STATUS_MISSING_CLASS if t[2] > 0 else 0)
+                  | (_lib.DRV_STATUS_BAD_LABEL if t[3] > 0 else 0))
+        return t[0], status
+
     def read_out(self):
         """One 16-byte D2H copy: (loss, status)."""
         self._out_host.copy_(self._out, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         loss = float(self._out_host[0])
-        status = int(self._out_host[1:2].view(torch.int32)[0])
+        words = self._out_host[1:2].view(torch.int32)
+        status = int(words[0])
+        self.last_path = int(words[1])  # drv_step_out.path: bit 0 tcgen05 decoder, bit 1 tcgen05 encoder input layer
         return loss, status
 
     # ------------------------------------------------------------------------------------

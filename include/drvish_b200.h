@@ -79,6 +79,10 @@ typedef struct drv_hparams {
                                                drv_param_offsets], so grads needs that one extra slot */
 #define DRV_FLAG_LOSS_IN_GRADS 2048         /* whole step in one call, loss also written to grads[total floats]
                                                (data parallel with ONE all-reduce after the step) */
+/* Tail slots of the gradient buffer written with DRV_FLAG_LOSS_IN_GRADS / DRV_FLAG_STOP_AFTER_DECODER (grads needs
+ * DRV_GRAD_TAIL_FLOATS extra floats): [0] loss, [1] 1.0 if DRV_STATUS_NAN_LOSS else 0, [2] MISSING_CLASS, [3] BAD_LABEL.
+ * After a SUM all-reduce every rank holds the summed loss and the number of ranks that raised each status bit. */
+#define DRV_GRAD_TAIL_FLOATS 4
 #define DRV_FLAG_ENCODER_BACKWARD_ONLY 256  /* part 2 of 2: encoder backward of the step started by part 1
                                                (same arguments, same workspace) */
 

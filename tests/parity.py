@@ -19,8 +19,17 @@ def zero_grad_biases(n_hidden_layers: int):
     return tuple(f"{s}.fc.{3 * k + 2}.bias" for s in ("encoder", "decoder") for k in range(n_hidden_layers))
 
 
-def make_case(cfg: dict, data_seed: int = 5, noise_seed: int = 1, model_seed: int = 0, bn_affine_random: bool = False):
+def make_case(cfg: dict, data_seed: int = 5, noise_seed: int = 1, model_seed: int = 0, bn_affine_random: bool = False,
+              log_r_shift: float = 0.0):
+    """``cfg`` may carry ``scale_factor`` (the ``poutine.scale`` of the data plate, nbvae.py:60).
+    ``log_r_shift`` is added to the log_r half of the last decoder bias (``decoder.fc.<last>.bias[G:]``), i.e. it
+    moves the NB dispersion r = exp(log_r) + eps by e^shift (PyTorch-default weights give r ~ 1)."""
     model = O.build_model(cfg, seed=model_seed)
+    if "scale_factor" in cfg:
+        model.scale_factor = float(cfg["scale_factor"])
+    if log_r_shift:
+        with torch.no_grad():
+            model.decoder.fc[-1].bias[cfg["n_input"]:] += float(log_r_shift)
     if bn_affine_random:
         g = torch.Generator().manual_seed(123)
         for m in model.modules():
@@ -41,6 +50,7 @@ def make_case(cfg: dict, data_seed: int = 5, noise_seed: int = 1, model_seed: in
 def oracle_step(case, dtype=torch.float64):
     cfg = case["cfg"]
     m = O.build_model(cfg, seed=0).to(dtype)
+    m.scale_factor = case["model"].scale_factor
     m.load_state_dict({k: (v.to(dtype) if v.is_floating_point() else v) for k, v in case["model"].state_dict().items()})
     cast = lambda v: [t.to(dtype) for t in v] if isinstance(v, list) else v.to(dtype)
     noise = {k: cast(v) for k, v in case["noise"].items()}
@@ -53,7 +63,8 @@ def build_cuda_model(case, device):
     import drvish_b200 as D
 
     cfg = case["cfg"]
-    kw = dict(n_input=cfg["n_input"], n_latent=cfg["n_latent"], layers=cfg["layers"])
+    kw = dict(n_input=cfg["n_input"], n_latent=cfg["n_latent"], layers=cfg["layers"],
+              scale_factor=float(case["model"].scale_factor))
     if cfg.get("drugs", 0):
         model = D.DRNBVAE(n_classes=cfg["classes"], n_drugs=cfg["drugs"], n_conditions=[cfg["doses"]] * cfg["drugs"],
                           lam_scale=cfg.get("lam_scale", 5.0), bias_scale=cfg.get("bias_scale", 10.0), **kw)
@@ -88,7 +99,8 @@ def compare_step(case, device="cuda:0", force_simt=False):
     loss32, grads32, _, _ = oracle_step(case, torch.float32)
     loss, grads, model = cuda_step(case, device, force_simt)
     rep = {"loss": loss, "loss64": loss64, "loss_rel": abs(loss - loss64) / abs(loss64),
-           "loss32_rel": abs(loss32 - loss64) / abs(loss64), "grads": {}, "launches": model._runtime().last_launches}
+           "loss32_rel": abs(loss32 - loss64) / abs(loss64), "grads": {}, "launches": model._runtime().last_launches,
+           "path": model._runtime().last_path}
     worst, worst_name = 0.0, ""
     zero_biases = zero_grad_biases(len(case["cfg"]["layers"]))
     for name, g64 in grads64.items():
