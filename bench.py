@@ -165,31 +165,307 @@ def oracle_cpu_rate(cfg, steps, warmup, batch=None):
     return B * steps / dt, dt / steps * 1e3, cores, B
 
 
+def config_dict(cfg, world, n_batches, cuda_graph=True):
+    """`config` of the JSON line - the SAME keys and values for both arms (the driver compares them)."""
+    B, G = cfg["batch"], cfg["n_input"]
+    return {"workload": cfg["name"], "minibatch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+            "l2": f"inputs rotate over {n_batches} resident minibatches ({n_batches * B * G * 4 / 1e9:.2f} GB > 126 MB L2), no flush",
+            "optimizer": "excluded from value/e2e (see with_optimizer)", "noise": "Philox in-kernel draws each step",
+            "cuda_graph": cuda_graph,
+            "all_reduce": "none (1 GPU)" if world == 1 else "one all-reduce of the flat gradient buffer per step (see `collective`)"}
+
+
 def run_reference(args, cfg):
+    """Reference arm: the reference's CPU implementation of the path (the oracle port - the reference itself cannot be
+    installed: pyro-ppl has no wheel here) on all host cores, same config / steps / warmup as the native arm; every step
+    is one 4096-cell minibatch of the workload.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = min(args.steps, 20)
-    rate, ms, cores, B = oracle_cpu_rate(cfg, steps, min(args.warmup, 3))
-    sample = f"{steps} steps of one {B}-cell minibatch of {cfg['name']}"
+    rate, ms, cores, B = oracle_cpu_rate(cfg, args.steps, args.warmup)
+    sample = f"{args.steps} timed steps ({args.warmup} warm-up) of one {B}-cell minibatch of {cfg['name']}"
     line = {
         "impl": "reference", "metric": "cells/sec per SVI step (ELBO fwd+bwd)", "value": rate, "unit": "cells/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["name"], "minibatch_per_step": B, "device": "host CPU"},
+        "config": config_dict(cfg, args.gpus, max(20, args.batches), not args.no_graph),
         "cpu_baseline": {"value": rate, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "device": "host CPU (PyTorch-eager restatement of the Pyro step, oracle/drvish_oracle.py)",
     }
     print(json.dumps(line), flush=True)
+
+
+MUFU_PER_ELEMENT = {"k_dec<1>": 1, "k_dec<2>": 8, "k_dec<3>": 1}  # MUFU (ex2 / lg2 / rcp) issued per (cell, gene) element
+
+
+def source_hash():
+    """Hash of the kernel sources the committed ncu traffic figures belong to (profiles/ncu_traffic.json is only
+    used while it matches: a stale capture must not be reported as this build's traffic)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for f in ("tc_decoder.cu", "tc_gemm.cu", "tc_common.cuh", "common.cuh"):
+        with open(os.path.join(ROOT, "drvish_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def bound_times(bytes_, flops, mufu, peaks, sm_mhz):
+    """Lower bounds (seconds) of a piece of work from the three rooflines that can bind it: HBM bytes, tensor-core
+    flops, SFU (MUFU) operations at 16 per clock and SM."""
+    return {"hbm": bytes_ / (peaks["hbm"] * 1e9), "tensor": flops / (peaks["tensor"] * 1e12),
+            "sfu": mufu / (148 * 16 * sm_mhz * 1e6)}
+
+
+def roof_entry(ms, bytes_, flops, mufu, peaks, sm_mhz):
+    t = bound_times(bytes_, flops, mufu, peaks, sm_mhz)
+    bound = max(t, key=t.get)
+    work, peak, unit = {"hbm": (bytes_ / 1e9, peaks["hbm"], "GB/s"), "tensor": (flops / 1e12, peaks["tensor"], "TFLOP/s"),
+                        "sfu": (mufu / 1e9, 148 * 16 * sm_mhz * 1e-3, "GMUFU/s")}[bound]
+    ach = work / (ms * 1e-3)
+    return {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+            "bound_us": {k: round(v * 1e6, 2) for k, v in t.items()}}
+
+
+class Workload:
+    """One bench config on this rank: model, resident synthetic minibatches, the fused ELBO."""
+
+    def __init__(self, args, cfg, device, world, rank):
+        import drvish_b200 as D
+
+        self.args, self.cfg, self.device, self.world, self.rank = args, cfg, device, world, rank
+        self.model = build_native_model(cfg, device)
+        self.rt = self.model._runtime()
+        self.elbo = D.FusedTraceELBO(seed=1234, data_parallel=(world > 1), use_cuda_graph=not args.no_graph)
+        self.n_batches = max(20, args.batches)
+        self.xs, self.labels, self.y = synth_batches(cfg, self.n_batches, 1234 + 3 + rank, device)
+        self.yflat = self.elbo._flatten_y(self.rt, self.y, device) if cfg["drugs"] else None
+        self.rt.ensure_flat()
+        if world > 1 and not self.elbo.dp_overlap:
+            self.elbo.dp_prepare(self.rt)  # peer-mapped gradient buffer (before any graph is captured)
+
+    def barrier(self):
+        import torch.distributed as dist
+
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        import torch.distributed as dist
+
+        t = torch.tensor([v], device=self.device, dtype=torch.float64)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def device_step(self, i, single_call=False, reduce=True):
+        """exactly what FusedTraceELBO.loss_and_grads enqueues, minus the per-step loss read-back"""
+        import torch.distributed as dist
+
+        e, rt = self.elbo, self.rt
+        xb = self.xs[i % self.n_batches]
+        if self.world > 1 and not single_call and not e.dp_overlap:
+            e._enqueue(rt, xb, self.labels, self.yflat, True, part=3)
+            if reduce:
+                e.dp_all_reduce(rt)
+        elif self.world > 1 and not single_call:
+            e._enqueue(rt, xb, self.labels, self.yflat, True, part=1)
+            w1 = dist.all_reduce(rt.flat_grads[rt.decoder_offset:], op=dist.ReduceOp.SUM, async_op=True)
+            e._enqueue(rt, xb, self.labels, self.yflat, True, part=2)
+            w2 = dist.all_reduce(rt.flat_grads[:rt.decoder_offset], op=dist.ReduceOp.SUM, async_op=True)
+            w1.wait()
+            w2.wait()
+        else:
+            e._enqueue(rt, xb, self.labels, self.yflat, True)
+        e.step_index += 1
+
+    def timed(self, steps, warmup, fn=None, sample_clocks=False):
+        """W untimed + K timed steps between barriers, CUDA events on the launching stream, max over ranks (ms/step)."""
+        fn = fn or self.device_step
+        for i in range(warmup):
+            fn(i)
+        self.barrier()
+        sampler = None
+        if sample_clocks:
+            sampler = ClockSampler(self.device.index)
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        ev1.record()
+        self.barrier()
+        clocks = sampler.finish() if sampler else None
+        return self.max_over_ranks(ev0.elapsed_time(ev1)) / steps, clocks
+
+    def capture_graphs(self):
+        if not self.args.no_graph:
+            for i in range(2 * self.n_batches):  # untimed: every resident minibatch is seen twice -> its graph is captured
+                self.device_step(i)
+
+    def dp_check(self):
+        """One untimed data-parallel step checked against an independent reduction: every rank's PRE-reduction flat
+        gradient buffer is all-gathered through NCCL and summed in fp64; the step's own collective must reproduce it."""
+        import torch.distributed as dist
+
+        rt, n = self.rt, self.rt.n_param_floats + 1
+        self.device_step(0, reduce=False)
+        torch.cuda.synchronize()
+        local = rt.flat_grads[:n].clone()
+        gathered = torch.empty(self.world * n, dtype=torch.float32, device=self.device)
+        dist.all_gather_into_tensor(gathered, local)
+        ref = gathered.view(self.world, n).double().sum(0)
+        self.elbo.dp_all_reduce(rt)
+        torch.cuda.synchronize()
+        got = rt.flat_grads[:n].double()
+        err = float(((got - ref).norm() / ref.norm()).item())
+        emax = float(((got - ref).abs().max() / ref.abs().max()).item())
+        # bit-identical on every rank?  compare an order-sensitive checksum of the bit patterns
+        bits = rt.flat_grads[:n].view(torch.int32).to(torch.int64)
+        chk = torch.stack([bits.sum(), (bits * torch.arange(1, n + 1, device=self.device) % 1000003).sum()])
+        allchk = torch.empty(self.world * 2, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(allchk, chk)
+        same = bool((allchk.view(self.world, 2) == allchk.view(self.world, 2)[0]).all().item())
+        return {"max_rel_err": max(err, emax), "norm_rel_err": err, "bit_identical_across_ranks": same,
+                "collective": self.collective(), "floats": n, "tolerance": 1e-6}
+
+    def collective(self):
+        if self.world == 1:
+            return "none (1 GPU)"
+        if self.elbo.dp_overlap:
+            return "two-part step, NCCL all-reduces overlapping the encoder backward"
+        if self.elbo._peer.get(id(self.rt)) is not None:
+            return "drv_peer_allreduce: one kernel over NVLink peer memory per step (k_comm.cu)"
+        return "one NCCL all-reduce per step"
+
+    def allreduce_alone_ms(self, iters=20):
+        """The step's collective timed back to back on the flat gradient buffer (not overlapped with anything)."""
+        if self.world == 1:
+            return 0.0
+        ms, _ = self.timed(iters, 3, fn=lambda i: self.elbo.dp_all_reduce(self.rt))
+        return ms
+
+    def profile_sections(self, lib, n_prof):
+        """Live kernel timing for the roofline: CUDA events recorded by the library on the step's own stream, around
+        the sections and around the single kernels of the fused decoder path.  The side stream is switched off
+        (flag 64) so that a section contains ALL of its work; direct launches (no graph)."""
+        os.environ["DRVISH_B200_DEBUG_FLAGS"] = "64"
+        graph = self.elbo.use_cuda_graph
+        self.elbo.use_cuda_graph = False
+        for i in range(3):
+            self.device_step(i, single_call=True)
+        torch.cuda.synchronize()
+        lib.drv_profile_enable(1)
+        for i in range(n_prof):
+            self.device_step(i, single_call=True)
+        torch.cuda.synchronize()
+        sec, kms, nprof = (C.c_float * 7)(), (C.c_float * 5)(), C.c_int()
+        lib.drv_profile_read(sec, C.byref(nprof))
+        lib.drv_profile_read_kernels(kms)
+        lib.drv_profile_enable(0)
+        os.environ["DRVISH_B200_DEBUG_FLAGS"] = "0"
+        self.elbo.use_cuda_graph = graph
+        return [float(v) for v in sec], [float(v) for v in kms], int(nprof.value)
+
+    def roofline(self, sec, kms, nprof, peaks, sm_mhz, config_id):
+        """Roofline of the fused decoder-last-layer + NB-likelihood step: algorithmic work / measured time
+        against the slowest of the HBM, tensor-core and SFU bounds."""
+        cfg = self.cfg
+        Bf, Gf, hf = float(cfg["batch"]), float(cfg["n_input"]), float(cfg["layers"][0])
+        bytes_alg, flops_alg = decoder_algorithmic(cfg)
+        mufu = sum(MUFU_PER_ELEMENT.values()) * Bf * Gf
+        t_dec_ms = sec[2] + sec[4]
+        roof = roof_entry(t_dec_ms, bytes_alg, flops_alg, mufu, peaks, sm_mhz)
+        traffic, tnote = {}, "no ncu capture committed for this config"
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            if tj.get("source_hash") == source_hash():
+                traffic = tj.get(f"cfg{config_id}", {})
+                tnote = tj.get("source", "")
+            else:
+                tnote = "profiles/ncu_traffic.json belongs to other kernel sources (hash mismatch): not reported"
+        roof["traffic"] = traffic.get("decoder_step_bytes")
+        roof["traffic_source"] = tnote
+        roof["kernel"] = ("fused decoder step = k_act + k_dec<1> (logsumexp) + k_dec<2> (NB likelihood + NB part of dlogits) + "
+                          "k_dec<3> (softmax coupling) + dAct and dW tcgen05 GEMMs (sections DEC_NB_FWD + DEC_NB_BWD, "
+                          "side stream off)")
+        roof["ms"] = round(t_dec_ms, 4)
+        roof["algorithmic"] = {"bytes": bytes_alg, "flops": flops_alg, "mufu_ops": mufu,
+                               "formula": "8BG+8Bh+16Gh bytes, 12BGh flops (SURVEY 8d); MUFU = (1 + 8 + 1) B G as issued by "
+                                          "phases 1/2/3 (2 ex2 + 4 lg2 + 2 rcp per element in the NB block, 1 ex2 each in the "
+                                          "softmax passes), 16 MUFU per clock and SM at the SM clock seen under load"}
+        roof["peak_source"] = peaks["which"] + (" (HBM: copy bandwidth; tensor: bf16 sustained cuBLAS - the decoder kernels use "
+                                                "kind::f16, fp16 operands with fp32 accumulation, whose nominal peak is the bf16 one; "
+                                                "SFU: 148 SMs x 16 lanes x SM clock)")
+        roof["section_ms"] = {k: round(sec[i], 4) for i, k in enumerate(
+            ["enc_fwd", "dec_trunk_fwd", "dec_nb_fwd", "dose_response", "dec_nb_bwd", "dec_trunk_bwd", "enc_bwd"])}
+        roof["profiled_steps"] = nprof
+        # per-kernel entries: the bytes / flops / MUFU each launch must move TODAY (fp16 operands and the fp16 dlogits
+        # hand-off between the kernels included - that hand-off is not algorithmic, which is why only the whole-step
+        # entry above is the roofline claim) over its own event-timed duration
+        kdefs = [
+            ("k_dec<1> logsumexp", 2 * Gf * hf + 2 * Bf * hf, 2 * Bf * Gf * hf, 1 * Bf * Gf),
+            ("k_dec<2> NB likelihood (+ NB part of dlogits)", 4 * Bf * Gf + 4 * Bf * Gf + 4 * Gf * hf + 2 * Bf * hf, 4 * Bf * Gf * hf, 8 * Bf * Gf),
+            ("k_dec<3> softmax coupling", 2 * Bf * Gf + 2 * Bf * Gf + 2 * Gf * hf + 2 * Bf * hf, 2 * Bf * Gf * hf, 1 * Bf * Gf),
+            ("dAct GEMM", 4 * Bf * Gf + 4 * Gf * hf + 4 * Bf * hf, 4 * Bf * Gf * hf, 0.0),
+            ("dW GEMM", 4 * Bf * Gf + 2 * Bf * hf + 8 * Gf * hf, 4 * Bf * Gf * hf, 0.0),
+        ]
+        rk = []
+        for i, (name, kb, kf, km) in enumerate(kdefs):
+            if kms[i] <= 0:
+                continue
+            ent = {"kernel": name, "ms": round(kms[i], 4)}
+            ent.update(roof_entry(kms[i], kb, kf, km, peaks, sm_mhz))
+            ent["traffic"] = traffic.get(name.split(" ")[0])
+            rk.append(ent)
+        roof["kernels"] = rk
+        return roof
+
+
+def cpu_baseline(cfg, steps, batch=None):
+    rate, ms, cores, Bc = oracle_cpu_rate(cfg, steps, 2, batch=batch)
+    return {"value": rate, "unit": "cells/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} timed steps (2 warm-up) of one {Bc}-cell minibatch, fp32, PyTorch-eager restatement of the "
+                      "Pyro step (oracle/drvish_oracle.py)", "ms_per_step": ms}
+
+
+def measure_other_config(args, config_id, device, world, rank, lib, peaks):
+    """A short device-timed run of another BASELINE.json config in the same process (value, ms/step, all-reduce,
+    decoder roofline, CPU baseline on a 512-cell sample)."""
+    cfg = CONFIGS[config_id]
+    w = Workload(args, cfg, device, world, rank)
+    w.capture_graphs()
+    steps = max(10, min(args.steps, 30))
+    ms, clocks = w.timed(steps, 3, sample_clocks=True)
+    ent = {"workload": cfg["name"], "n_gpus": world, "steps": steps, "ms_per_step": ms,
+           "value": world * cfg["batch"] / (ms * 1e-3), "unit": "cells/s", "launches_per_step": w.rt.last_launches + 1,
+           "grad_bytes": 4 * w.rt.n_param_floats, "clocks": clocks}
+    if world > 1:
+        ms_local, _ = w.timed(steps, 3, fn=lambda i: w.device_step(i, reduce=False))
+        ent["all_reduce"] = {"collective": w.collective(), "alone_ms": w.allreduce_alone_ms(),
+                             "exposed_ms": ms - ms_local, "ms_per_step_without": ms_local}
+        ent["dp_check"] = w.dp_check()
+    sec, kms, nprof = w.profile_sections(lib, min(steps, 16))
+    sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+    if rank == 0:
+        roof = w.roofline(sec, kms, nprof, peaks, sm_mhz, config_id)
+        ent["roofline"] = {k: roof[k] for k in ("bound", "achieved", "peak", "unit", "frac", "bound_us", "ms", "traffic")}
+        ent["roofline"]["kernels_ms"] = {k["kernel"].split(" ")[0]: k["ms"] for k in roof["kernels"]}
+        if not args.no_cpu_baseline:
+            ent["cpu_baseline"] = cpu_baseline(cfg, 3, batch=512)
+    del w
+    torch.cuda.empty_cache()
+    return ent
 
 
 def run_native(args, cfg):
     import torch.distributed as dist
 
-    import drvish_b200 as D
     from drvish_b200 import _lib
-    from drvish_b200.parallel import allreduce_grads_and_loss
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -201,117 +477,51 @@ def run_native(args, cfg):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     lib = _lib.load()
-    model = build_native_model(cfg, device)
-    rt = model._runtime()
-    elbo = D.FusedTraceELBO(seed=1234, data_parallel=(world > 1), use_cuda_graph=not args.no_graph)
-    n_batches = max(20, args.batches)
-    xs, labels, y = synth_batches(cfg, n_batches, 1234 + 3 + rank, device)
+    peaks = load_peaks()
+    w = Workload(args, cfg, device, world, rank)
+    model, rt, elbo, xs, labels, y = w.model, w.rt, w.elbo, w.xs, w.labels, w.y
+    n_batches = w.n_batches
     B, G = cfg["batch"], cfg["n_input"]
-
-    def batch_args(i, x=None):
-        a = [xs[i % n_batches] if x is None else x]
-        if cfg["drugs"]:
-            a += [labels, y]
-        return a
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    barrier = w.barrier
 
     # ---- device-resident timing (`value`) ----------------------------------------------------
     # same code path as loss_and_grads minus the per-step loss read-back (one sync at the end)
-    yflat = elbo._flatten_y(rt, y, device) if cfg["drugs"] else None
-    rt.ensure_flat()
-    if world > 1 and not elbo.dp_overlap:
-        elbo.dp_prepare(rt)  # peer-mapped gradient buffer (before any graph is captured)
-
-    def device_step(i, single_call=False):
-        # exactly what FusedTraceELBO.loss_and_grads enqueues, minus the per-step loss read-back
-        xb = xs[i % n_batches]
-        if world > 1 and not single_call and not elbo.dp_overlap:
-            elbo._enqueue(rt, xb, labels, yflat, True, part=3)
-            elbo.dp_all_reduce(rt)
-        elif world > 1 and not single_call:
-            elbo._enqueue(rt, xb, labels, yflat, True, part=1)
-            w1 = dist.all_reduce(rt.flat_grads[rt.decoder_offset:], op=dist.ReduceOp.SUM, async_op=True)
-            elbo._enqueue(rt, xb, labels, yflat, True, part=2)
-            w2 = dist.all_reduce(rt.flat_grads[:rt.decoder_offset], op=dist.ReduceOp.SUM, async_op=True)
-            w1.wait()
-            w2.wait()
-        else:
-            elbo._enqueue(rt, xb, labels, yflat, True)
-        elbo.step_index += 1
-
-    if not args.no_graph:
-        for i in range(2 * n_batches):  # untimed: every resident minibatch is seen twice -> its graph is captured
-            device_step(i)
-    for i in range(args.warmup):
-        device_step(i)
+    w.capture_graphs()
+    ms_per_step, clocks = w.timed(args.steps, args.warmup, sample_clocks=True)
     launches_per_step = rt.last_launches + 1  # + the noise draw (one launch)
-    barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for i in range(args.steps):
-        device_step(args.warmup + i)
-    ev1.record()
-    barrier()
-    clocks = sampler.finish()
-    ms_total = ev0.elapsed_time(ev1)
+    if world > 1 and not elbo.dp_overlap:
+        launches_per_step += 1  # + the all-reduce kernel
     loss_last, status = rt.read_out()
-    t = torch.tensor([ms_total], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_per_step = ms_total / args.steps
-    value = world * B * args.steps / (ms_total * 1e-3)
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---- data parallel: correctness of the collective + its cost ------------------------------
+    dp_check = all_reduce = None
+    if world > 1 and not elbo.dp_overlap:
+        dp_check = w.dp_check()
+        ms_local, _ = w.timed(args.steps, 3, fn=lambda i: w.device_step(i, reduce=False))
+        all_reduce = {"collective": w.collective(), "alone_ms": w.allreduce_alone_ms(), "exposed_ms": ms_per_step - ms_local,
+                      "ms_per_step_without": ms_local, "bytes": 4 * (rt.n_param_floats + 1)}
+        if dp_check["max_rel_err"] > dp_check["tolerance"]:
+            raise SystemExit(f"bench.py: data-parallel gradient check failed: {dp_check}")
 
     # ---- the same loop with the fused optimizer step behind every ELBO step (AggMo, 3 betas,
     # nesterov, per-tensor clip_norm 20 as in the reference notebook); an extra, the headline excludes it
+    import drvish_b200 as D
+
     opt = D.FusedAggMo(model, lr=5e-4, betas=[0.0, 0.9, 0.99], nesterov=True, clip_norm=20.0)
     params_before = rt.flat_params.clone()
-    for i in range(3):
-        device_step(i)
+
+    def step_opt(i):
+        w.device_step(i)
         opt.step()
-    barrier()
-    ev0.record()
-    for i in range(args.steps):
-        device_step(args.warmup + i)
-        opt.step()
-    ev1.record()
-    barrier()
-    t = torch.tensor([ev0.elapsed_time(ev1)], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_opt = float(t.item()) / args.steps
+
+    ms_opt, _ = w.timed(args.steps, 3, fn=step_opt)
     with_opt = {"value": world * B / (ms_opt * 1e-3), "unit": "cells/s", "ms_per_step": ms_opt,
                 "optimizer": "FusedAggMo(betas=[0,0.9,0.99], nesterov, clip_norm=20): drv_aggmo_step, 3-4 launches",
                 "optimizer_ms": ms_opt - ms_per_step}
     rt.flat_params.copy_(params_before)  # the measurements below run on the initial weights again
 
-    # ---- live kernel timing for the roofline: CUDA events recorded by the library on the step's
-    # own stream, around the sections and around the single kernels of the fused decoder path.
-    # The side stream is switched off here (flag 64) so that a section contains ALL of its work.
-    n_prof = min(args.steps, 32)
-    os.environ["DRVISH_B200_DEBUG_FLAGS"] = "64"
-    elbo.use_cuda_graph = False  # direct launches: the profiler's events are recorded by the library
-    for i in range(3):
-        device_step(i, single_call=True)
-    torch.cuda.synchronize()
-    lib.drv_profile_enable(1)
-    for i in range(n_prof):
-        device_step(i, single_call=True)
-    torch.cuda.synchronize()
-    sec = (C.c_float * 7)()
-    kms = (C.c_float * 5)()
-    nprof = C.c_int()
-    lib.drv_profile_read(sec, C.byref(nprof))
-    lib.drv_profile_read_kernels(kms)
-    lib.drv_profile_enable(0)
-    os.environ["DRVISH_B200_DEBUG_FLAGS"] = "0"
-    elbo.use_cuda_graph = not args.no_graph
+    sec, kms, nprof = w.profile_sections(lib, min(args.steps, 32))
 
     # ---- end-to-end through the public API, host minibatches --------------------------------
     # every step's inputs start in pinned HOST memory; PinnedBatchPrefetcher issues the H2D copy of
@@ -332,19 +542,17 @@ def run_native(args, cfg):
             last = elbo.loss_and_grads(model.model, model.guide, *batch)
         return last
 
-    def time_e2e(dataset, on_the_fly=False):
+    def time_e2e(dataset, on_the_fly=None):
         pf = PinnedBatchPrefetcher(None, device, pack_on_the_fly=on_the_fly)
         run_e2e(pf, dataset, 3 * pf.SLOTS)  # untimed: every staging slot gets its CUDA graph
         barrier()
-        pf.h2d_bytes = 0
+        pf.h2d_bytes, pf.pack_seconds, pf.packed_batches = 0, 0.0, 0
         t0 = time.perf_counter()
         run_e2e(pf, dataset, e2e_steps)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt], device=device, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return world * B * e2e_steps / float(t.item()), pf.h2d_bytes // e2e_steps
+        dt = w.max_over_ranks(time.perf_counter() - t0)
+        pack_ms = 1e3 * pf.pack_seconds / pf.packed_batches if pf.packed_batches else 0.0
+        return world * B * e2e_steps / dt, pf.h2d_bytes // e2e_steps, pack_ms
 
     # ---- the reference's GPU-resident sparse loader (data/cupy.py): CSR dataset on the device, every
     # batch densified by drv_csr_gather_rows, no host copy of counts (an extra: NOT an e2e number in the
@@ -366,101 +574,71 @@ def run_native(args, cfg):
     t0 = time.perf_counter()
     run_csr(e2e_steps)
     torch.cuda.synchronize()
-    t = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    csr_value = world * B * e2e_steps / float(t.item())
+    csr_value = world * B * e2e_steps / w.max_over_ranks(time.perf_counter() - t0)
     csr_nnz = int(csr.data.numel() // n_csr)
 
-    e2e_value, e2e_h2d = time_e2e(fp32_set)
-    e2e_u16, e2e_u16_h2d = time_e2e(u16_set)
-    e2e_fly, e2e_fly_h2d = time_e2e(fp32_set, on_the_fly=True)
+    # default transport: fp32 host minibatches packed to one byte per entry (+ escapes) by the prefetcher's worker
+    e2e_value, e2e_h2d, e2e_pack_ms = time_e2e(fp32_set, on_the_fly="u8")
+    e2e_f32, e2e_f32_h2d, _ = time_e2e(fp32_set, on_the_fly=None)
+    e2e_u16, e2e_u16_h2d, _ = time_e2e(u16_set, on_the_fly=None)
+    e2e_fly, e2e_fly_h2d, e2e_fly_ms = time_e2e(fp32_set, on_the_fly="u16")
+    from drvish_b200.data import default_pack_threads
+    pack_isa = lib.drv_host_pack_isa().decode()
+
+    # ---- the other BASELINE.json configs, short runs in the same process: cfg 2 on one GPU, cfgs 4 and 5 where
+    # BASELINE.json places them (8 GPUs); --other-configs forces a list
+    if args.other_configs is not None:
+        others = [int(v) for v in args.other_configs.split(",") if v]
+    else:
+        others = [2] if world == 1 else ([4, 5] if world == 8 else [])
+    others = [c for c in others if c != args.config]
+    del host_x, fp32_set, u16_set, csr, csr_idx
+    other_configs = {}
+    if others:
+        keep_sm = (clocks or {}).get("sm_mhz")
+        del w, model, rt, elbo, xs, labels, y, opt, params_before
+        torch.cuda.empty_cache()
+        for c in others:
+            other_configs[f"cfg{c}"] = measure_other_config(args, c, device, world, rank, lib, peaks)
+        w = None
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the fused decoder-last-layer + NB-likelihood step ----------------
-    peaks = load_peaks()
-    Bf, Gf, hf = float(B), float(G), float(cfg["layers"][0])
-    bytes_alg, flops_alg = decoder_algorithmic(cfg)
-    t_dec_ms = sec[2] + sec[4]
-    t_hbm = bytes_alg / (peaks["hbm"] * 1e9)
-    t_tensor = flops_alg / (peaks["tensor"] * 1e12)
-    if t_tensor >= t_hbm:
-        roof = {"bound": "tensor", "achieved": flops_alg / (t_dec_ms * 1e-3) / 1e12, "peak": peaks["tensor"],
-                "unit": "TFLOP/s"}
-    else:
-        roof = {"bound": "hbm", "achieved": bytes_alg / (t_dec_ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s"}
-    roof["frac"] = roof["achieved"] / roof["peak"]
-    traffic = {}
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            traffic = json.load(f).get(f"cfg{args.config}", {})
-    roof["traffic"] = traffic.get("decoder_step_bytes")
-    roof["kernel"] = ("fused decoder step = k_dec<1> (logsumexp) + k_dec<2> (NB likelihood + NB part of dlogits) + "
-                      "k_dec<3> (softmax coupling) + dAct and dW tcgen05 GEMMs (sections DEC_NB_FWD + DEC_NB_BWD, "
-                      "side stream off)")
-    roof["algorithmic"] = {"bytes": bytes_alg, "flops": flops_alg, "formula": "8BG+8Bh+16Gh bytes, 12BGh flops (SURVEY 8d)"}
-    roof["peak_source"] = peaks["which"] + " (bf16 sustained cuBLAS; the decoder kernels use kind::f16 - fp16 operands, fp32 accumulate - whose nominal peak is the bf16 one)"
-    roof["section_ms"] = {k: round(float(sec[i]), 4) for i, k in enumerate(
-        ["enc_fwd", "dec_trunk_fwd", "dec_nb_fwd", "dose_response", "dec_nb_bwd", "dec_trunk_bwd", "enc_bwd"])}
-    roof["profiled_steps"] = int(nprof.value)
-    # per-kernel entries: algorithmic work of that launch / its own event-timed duration
-    kdefs = [
-        ("k_dec<1> logsumexp", 4 * Gf * hf + 4 * Bf * hf, 2 * Bf * Gf * hf),
-        ("k_dec<2> NB likelihood (+ NB part of dlogits)", 4 * Bf * Gf + 8 * Bf * Gf + 8 * Gf * hf + 4 * Bf * hf, 4 * Bf * Gf * hf),
-        ("k_dec<3> softmax coupling", 8 * Bf * Gf + 4 * Gf * hf + 4 * Bf * hf, 2 * Bf * Gf * hf),
-        ("dAct GEMM", 8 * Bf * Gf + 8 * Gf * hf + 4 * Bf * hf, 4 * Bf * Gf * hf),
-        ("dW GEMM", 8 * Bf * Gf + 8 * Gf * hf + 4 * Bf * hf, 4 * Bf * Gf * hf),
-    ]
-    rk = []
-    for i, (name, kb, kf) in enumerate(kdefs):
-        ms = float(kms[i])
-        if ms <= 0:
-            continue
-        th, tt = kb / (peaks["hbm"] * 1e9), kf / (peaks["tensor"] * 1e12)
-        ent = {"kernel": name, "ms": round(ms, 4), "bound": "hbm" if th >= tt else "tensor"}
-        if th >= tt:
-            ent.update(achieved=kb / (ms * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s")
-        else:
-            ent.update(achieved=kf / (ms * 1e-3) / 1e12, peak=peaks["tensor"], unit="TFLOP/s")
-        ent["frac"] = ent["achieved"] / ent["peak"]
-        ent["traffic"] = traffic.get(name.split(" ")[0])
-        rk.append(ent)
-    roof["kernels"] = rk
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    if w is None:  # the main workload was released before the other configs ran: rebuild the roofline from its numbers
+        w = Workload.__new__(Workload)
+        w.cfg = cfg
+    roof = Workload.roofline(w, sec, kms, nprof, peaks, sm_mhz, args.config)
 
     # ---- CPU baseline on the host cores (bounded sample) ---------------------------------------
-    cpu = None
-    if not args.no_cpu_baseline:
-        rate, ms, cores, Bc = oracle_cpu_rate(cfg, args.cpu_steps, 2)
-        cpu = {"value": rate, "unit": "cells/s", "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_steps} timed steps (2 warm-up) of one {Bc}-cell minibatch, fp32, PyTorch-eager "
-                         "restatement of the Pyro step (oracle/drvish_oracle.py)", "ms_per_step": ms}
+    cpu = None if args.no_cpu_baseline else cpu_baseline(cfg, args.cpu_steps)
 
     line = {
         "metric": "cells/sec per SVI step (ELBO fwd+bwd)", "value": value, "unit": "cells/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp16 / tf32 tensor-core operands with fp32 accumulation where stated in DESIGN.md)",
         "data": "synthetic",
-        "config": {"workload": cfg["name"], "minibatch_per_gpu": B, "global_batch": B * world,
-                   "parallelism": f"dp{world}", "l2": f"inputs rotate over {n_batches} resident minibatches "
-                   f"({n_batches * B * G * 4 / 1e9:.2f} GB > 126 MB L2), no flush", "optimizer": "excluded from value/e2e (see with_optimizer)",
-                   "noise": "Philox in-kernel draws each step", "cuda_graph": not args.no_graph,
-                   "all_reduce": ("none (1 GPU)" if world == 1 else
-                                  "two-part step, NCCL all-reduces overlapping the encoder backward" if elbo.dp_overlap else
-                                  "one drv_peer_allreduce kernel over NVLink peer memory per step" if elbo._peer.get(id(rt)) is not None
-                                  else "one NCCL all-reduce per step")},
+        "config": config_dict(cfg, world, n_batches, not args.no_graph),
+        "collective": all_reduce["collective"] if all_reduce else "none (1 GPU)",
         "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": e2e_h2d, "d2h_bytes_per_step": 16,
-                "steps": e2e_steps, "api": "FusedTraceELBO.loss_and_grads(model.model, model.guide, *batch) fed by PinnedBatchPrefetcher "
-                       "(pinned host fp32 minibatches, H2D of the batches ahead overlapped with the running step)",
-                "bound": "PCIe: %.1f GB/s host->device" % (e2e_h2d * e2e_value / (world * B) / 1e9),
+                "steps": e2e_steps, "api": "FusedTraceELBO.loss_and_grads(model.model, model.guide, *batch) fed by PinnedBatchPrefetcher: "
+                       "every step's fp32 minibatch starts in pinned HOST memory; the prefetcher's worker packs it losslessly to one byte "
+                       "per entry + an escape list (drv_host_pack_counts_u8), copies the bytes H2D on a side stream while earlier "
+                       "steps run, and the device widens them back to the fp32 tile (drv_unpack_counts_u8); the loss is read back every step",
+                "transport": "u8 + escapes, packed on the fly from fp32 host tensors",
+                "pack_ms_per_batch": e2e_pack_ms, "pack_threads": default_pack_threads(), "pack_isa": pack_isa,
+                "h2d_GBps": e2e_h2d * e2e_value / (world * B) / 1e9,
+                # same API, the reference's transport: the fp32 tile itself crosses the bus (PCIe-bound)
+                "fp32_transport": {"value": e2e_f32, "unit": "cells/s", "h2d_bytes_per_step": e2e_f32_h2d,
+                                   "bound": "PCIe: %.1f GB/s host->device" % (e2e_f32_h2d * e2e_f32 / (world * B) / 1e9)},
                 # same API, minibatches packed ONCE to lossless uint16 when the dataset is built
                 "packed_u16_dataset": {"value": e2e_u16, "unit": "cells/s", "h2d_bytes_per_step": e2e_u16_h2d},
-                # same API, fp32 host minibatches packed by the prefetcher's worker thread every step
-                "packed_u16_on_the_fly": {"value": e2e_fly, "unit": "cells/s", "h2d_bytes_per_step": e2e_fly_h2d},
+                # same API, fp32 host minibatches packed to uint16 by the prefetcher's worker every step
+                "packed_u16_on_the_fly": {"value": e2e_fly, "unit": "cells/s", "h2d_bytes_per_step": e2e_fly_h2d,
+                                          "pack_ms_per_batch": e2e_fly_ms},
                 # same API, dataset resident on the device as CSR (reference data/cupy.py), tiles densified per step
                 "csr_resident_dataset": {"value": csr_value, "unit": "cells/s", "h2d_bytes_per_step": 0,
                                          "nnz_per_step": csr_nnz}},
@@ -468,6 +646,7 @@ def run_native(args, cfg):
         "gpu_launches": launches_per_step * args.steps,
         "launches_per_step": launches_per_step,
         "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "loss_last": loss_last, "status": status,
+        "all_reduce": all_reduce, "dp_check": dp_check, "other_configs": other_configs,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -485,8 +664,11 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels directly instead of replaying CUDA graphs")
+    ap.add_argument("--other-configs", default=None,
+                    help="comma-separated BASELINE.json configs measured briefly into `other_configs` (default: 2 on one "
+                         "GPU, 4 and 5 on eight; '' = none)")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    args.warmup = max(args.warmup, 3)
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
         run_reference(args, cfg)

@@ -78,6 +78,9 @@ SYMBOLS = {
     "drv_counter_add": (C.c_int, [_P, C.c_uint64, _P]),
     "drv_host_pack_counts_u16": (C.c_int64, [_P, _P, C.c_int64, C.c_int]),
     "drv_unpack_counts_u16": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "drv_host_pack_counts_u8": (C.c_int64, [_P, _P, C.c_int64, _P, _P, C.c_int64, C.c_int]),
+    "drv_host_pack_isa": (C.c_char_p, []),
+    "drv_unpack_counts_u8": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int64, _P]),
     "drv_elbo_step_mcv": (C.c_int, [_P] * 14 + [C.c_size_t, _P]),
     "drv_csr_gather_rows": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "drv_split_molecules": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P]),

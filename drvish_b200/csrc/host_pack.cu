@@ -51,6 +51,30 @@ __global__ void __launch_bounds__(256) k_unpack_u16(const uint16_t* __restrict__
   if (blockIdx.x == 0 && threadIdx.x < (int)(n - n8 * 8)) dst[n8 * 8 + threadIdx.x] = (float)src[n8 * 8 + threadIdx.x];
 }
 
+// 8-bit transport (host side: host_pack8.cpp): bytes 0..254 are the counts themselves, 255 marks an escape whose fp32
+// value follows in the escape list.  Widening is one 128-bit load -> four 128-bit stores per thread.
+__global__ void __launch_bounds__(256) k_unpack_u8(const uint8_t* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  pdl_prologue();
+  const int64_t n16 = n / 16;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 v = __ldcs(reinterpret_cast<const uint4*>(src) + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float4 a;
+      a.x = (float)(w[k] & 0xffu); a.y = (float)((w[k] >> 8) & 0xffu); a.z = (float)((w[k] >> 16) & 0xffu); a.w = (float)(w[k] >> 24);
+      reinterpret_cast<float4*>(dst)[4 * i + k] = a;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (int)(n - n16 * 16)) dst[n16 * 16 + threadIdx.x] = (float)src[n16 * 16 + threadIdx.x];
+}
+__global__ void __launch_bounds__(256) k_patch_escapes(const uint32_t* __restrict__ idx, const float* __restrict__ val, int n_esc,
+                                                       float* __restrict__ dst, int64_t n) {
+  pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_esc && (int64_t)idx[i] < n) dst[idx[i]] = val[i];
+}
+
 // Dense minibatch tile from a device-resident CSR count matrix (reference CupySparseDataLoader,
 // src/drvish/data/cupy.py:36-43: `t[indices].todense()` per batch).  One warp per output row: the
 // row is cleared with 128-bit stores, then its nonzeros are scattered.  HBM-bound on the dense
@@ -123,6 +147,28 @@ extern "C" int64_t drv_host_pack_counts_u16(const float* h_src, uint16_t* h_dst,
   }
   for (auto& th : pool) th.join();
   return first_bad.load();
+}
+
+extern "C" int drv_unpack_counts_u8(const uint8_t* src, const uint32_t* esc_idx, const float* esc_val, int n_escapes, float* dst,
+                                    int64_t n, void* stream) {
+  using namespace drv;
+  g_launches = 0;
+  g_err = cudaSuccess;
+  if (!src || !dst || n < 0 || n_escapes < 0 || (n_escapes > 0 && (!esc_idx || !esc_val))) return DRV_EINVAL;
+  if (n == 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15)) return DRV_EINVAL;
+  int64_t blocks = (n / 16 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  launch_k(k_unpack_u8, (unsigned)blocks, 256, 0, (cudaStream_t)stream, src, dst, n);
+  note_launch();
+  if (n_escapes > 0) {
+    launch_k(k_patch_escapes, (unsigned)((n_escapes + 255) / 256), 256, 0, (cudaStream_t)stream, esc_idx, esc_val, n_escapes, dst, n);
+    note_launch();
+  }
+  cudaError_t e = g_err;
+  g_err = cudaSuccess;
+  return (int)e;
 }
 
 extern "C" int drv_unpack_counts_u16(const uint16_t* src, float* dst, int64_t n, void* stream) {

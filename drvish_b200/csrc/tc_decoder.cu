@@ -42,7 +42,10 @@ constexpr int B_BYTES = 128 * BK * 4;      // 16 KB (128 weight rows)
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int X_BYTES = 2 * BM * 32 * 4;   // one count tile: two 128x32 boxes = 32 KB
 constexpr int N_EPI_WARPS = 16;
-constexpr int NTHREADS = (N_EPI_WARPS + 3) * 32;  // + TMA producer, MMA issuer, TMA store warp
+// + TMA producer, MMA issuer, TMA store warp and one idle warp that completes the fifth warpgroup: setmaxnreg acts on
+// whole warpgroups (phase 2 moves registers from the four service warps to the sixteen epilogue warps)
+constexpr int NTHREADS = (N_EPI_WARPS + 4) * 32;
+constexpr int EPI_REGS = 112, SERVICE_REGS = 32;  // 16 x 32 x 112 + 4 x 32 x 32 = 640 x 96, the launch-time allocation
 // phase 2 (training): 3 operand stages + 2 count tiles (overwritten in place by ds') + 2 drho tiles
 constexpr int SMEM_BYTES = 3 * STAGE_BYTES + 4 * X_BYTES + 1024 + 1024;
 // phases 1, 2 (forward only) and 3 need less: leave room for the small kernels of the other stream
@@ -218,6 +221,13 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Phase 2 (training): the NB epilogue needs two element pairs and the next group's operands in registers, the
+  // service warps need few - registers move from the fifth warpgroup to the four epilogue warpgroups.  The
+  // setmaxnreg sits at the top of every role branch, so that ptxas allocates each branch under its own budget.
+  constexpr bool REBALANCE = PHASE == 2 && WITH_A;
+  auto service_regs = [] {
+    if (REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SERVICE_REGS));
+  };
 
   // phase 2 is bound by its epilogue warps: the service warps back off between barrier polls
   auto swait = [](uint64_t* bar, uint32_t parity) {
@@ -226,6 +236,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
   };
   if (warp == N_EPI_WARPS) {
     // ===== TMA producer =====
+    service_regs();
     if (lane == 0) {
       int kit = 0;
       for (int t = t0, it = 0; t < t1; ++t, ++it) {
@@ -256,6 +267,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
     }
   } else if (warp == N_EPI_WARPS + 1) {
     // ===== MMA issuer =====
+    service_regs();
     if (lane == 0) {
       const uint32_t idesc = H16 ? idesc_f16(BM, 128, 0, 0) : idesc_tf32(BM, 128, 0, 0);
       int kit = 0;
@@ -287,6 +299,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
     }
   } else if (warp == N_EPI_WARPS + 2) {
     // ===== TMA store warp: finished gradient tiles, shared memory -> global =====
+    service_regs();
     if (TSTORE && lane == 0) {
       for (int t = t0, it = 0; t < t1; ++t, ++it) {
         const int ct = t / n_gt, gt = t % n_gt;
@@ -314,8 +327,11 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
       }
       tma_store_wait_all();
     }
+  } else if (warp > N_EPI_WARPS + 2) {
+    service_regs();  // idle warp: completes the service warpgroup
   } else {
     // ===== epilogue warps =====
+    if (REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EPI_REGS));
     const int q = warp % 4;    // TMEM lane quarter
     const int cg = warp / 4;   // column group
     const int r = q * 32 + lane;
@@ -554,34 +570,40 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
         // selects; TMA zero-fills / clips the edges, so only the edge tiles need masking for the sums
         auto tile_loop = [&](auto masked_tag) {
         constexpr bool MASKED = decltype(masked_tag)::value;
+        // count chunk and bias values of column group g: 16-byte chunk (cg%2)*4 + g of the row, XOR-swizzled with r%8
+        auto load_inputs = [&](int g, float4& xf, float4& fs, float4& fr) {
+          xf = lds128(xrow_s + (((c4 + (uint32_t)g) ^ r7) * 16));
+          if (!MASKED || full_cols) {  // warp-uniform addresses -> broadcast loads
+            fs = __ldg(reinterpret_cast<const float4*>(bias_s + 4 * g));
+            fr = __ldg(reinterpret_cast<const float4*>(bias_s + p.G + 4 * g));
+          } else {
+            const int gq = gbase + 4 * g;
+            fs.x = gq + 0 < p.G ? __ldg(&p.bias[gq + 0]) : 0.f; fr.x = gq + 0 < p.G ? __ldg(&p.bias[p.G + gq + 0]) : 0.f;
+            fs.y = gq + 1 < p.G ? __ldg(&p.bias[gq + 1]) : 0.f; fr.y = gq + 1 < p.G ? __ldg(&p.bias[p.G + gq + 1]) : 0.f;
+            fs.z = gq + 2 < p.G ? __ldg(&p.bias[gq + 2]) : 0.f; fr.z = gq + 2 < p.G ? __ldg(&p.bias[p.G + gq + 2]) : 0.f;
+            fs.w = gq + 3 < p.G ? __ldg(&p.bias[gq + 3]) : 0.f; fr.w = gq + 3 < p.G ? __ldg(&p.bias[p.G + gq + 3]) : 0.f;
+          }
+        };
+        // software pipeline: the TMEM loads, the count chunk and the bias values of group g + 1 are in flight while
+        // group g is evaluated (their latencies sat at the head of every trip: long / short scoreboard stalls)
+        float4 xf_n, fs_n, fr_n;
+        load_inputs(0, xf_n, fs_n, fr_n);
 #pragma unroll 1
         for (int g4 = 0; g4 < 4; ++g4) {
           float sv[4], rv[4], bs[4], br[4];
 #pragma unroll
           for (int v = 0; v < 4; ++v) { sv[v] = sv_n[v]; rv[v] = rv_n[v]; }
+          float4 xf = xf_n;
+          bs[0] = fs_n.x; bs[1] = fs_n.y; bs[2] = fs_n.z; bs[3] = fs_n.w;
+          br[0] = fr_n.x; br[1] = fr_n.y; br[2] = fr_n.z; br[3] = fr_n.w;
           {
-            // next group's logits: in flight while this group's NB terms are evaluated
             const int gn = g4 + 1 < 4 ? g4 + 1 : g4;
             tmem_ld4(tcol + gn * 4, sv_n);
             tmem_ld4(tcol + 64 + gn * 4, rv_n);
+            load_inputs(gn, xf_n, fs_n, fr_n);
           }
-          // count tile: 16-byte chunk (cg%2)*4 + g4, XOR-swizzled with r%8
           const uint32_t chunk = (c4 + (uint32_t)g4) ^ r7;
-          float4 xf = lds128(xrow_s + chunk * 16);
           const int gq = gbase + 4 * g4;
-          if (!MASKED || full_cols) {  // warp-uniform addresses -> broadcast loads
-            const float4 f = __ldg(reinterpret_cast<const float4*>(bias_s + 4 * g4));
-            const float4 h2 = __ldg(reinterpret_cast<const float4*>(bias_s + p.G + 4 * g4));
-            bs[0] = f.x; bs[1] = f.y; bs[2] = f.z; bs[3] = f.w;
-            br[0] = h2.x; br[1] = h2.y; br[2] = h2.z; br[3] = h2.w;
-          } else {
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              const bool okg = gq + v < p.G;
-              bs[v] = okg ? __ldg(&p.bias[gq + v]) : 0.f;
-              br[v] = okg ? __ldg(&p.bias[p.G + gq + v]) : 0.f;
-            }
-          }
           bool ok[4];
           if (MASKED) {
             // edge tile: out-of-range entries become benign (lsl = rho = x = 0) and are dropped from the sums

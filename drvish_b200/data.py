@@ -9,11 +9,15 @@ than the whole ELBO step on a B200.  Two pieces:
 stages the count tensor of the batches ahead through pinned memory on a copy stream (three device
 slots) while the current step runs.
 
-``PackedCounts`` is a lossless 16-bit host representation of a count tile (scRNA counts are
-non-negative integers): packed ONCE when the dataset is built (``pack_batches``), it halves the
-bytes every epoch moves over PCIe; the device widens it back to the fp32 tile the step reads,
-bit-exactly (``drv_unpack_counts_u16``).  A tile with a non-integer / negative / > 65535 entry is
-left as fp32."""
+``PackedCounts8`` is the default transport of count tiles: one BYTE per entry (an integer 0..254 is
+its own byte, anything else is the byte 255 plus an (index, fp32 value) escape), lossless for any fp32
+tile, a quarter of the bytes over PCIe.  The prefetcher's worker packs fp32 host minibatches on the
+fly (``drv_host_pack_counts_u8``: persistent thread pool, AVX-512 / AVX2) and the device widens them
+back to the fp32 tile the step reads, bit-exactly (``drv_unpack_counts_u8``).
+
+``PackedCounts`` is the older 16-bit representation: packed ONCE when the dataset is built
+(``pack_batches``), widened by ``drv_unpack_counts_u16``.  A tile with a non-integer / negative /
+> 65535 entry is left as fp32."""
 from __future__ import annotations
 
 import ctypes as C
@@ -59,6 +63,67 @@ class PackedCounts:
         import numpy as np
 
         return torch.from_numpy(self.data.numpy().view(np.uint16).astype(np.float32)).reshape(self.shape)
+
+
+class PackedCounts8:
+    """One byte per entry + escape list (``drv_host_pack_counts_u8``): lossless for ANY fp32 tile whose entries are
+    mostly integers in 0..254.  ``data`` uint8 [n] (pinned), ``esc_idx`` int32 view of uint32 indices, ``esc_val``
+    fp32, ``n_esc`` valid escapes."""
+
+    __slots__ = ("data", "esc_idx", "esc_val", "n_esc", "shape")
+    MAX_ESCAPE_FRACTION = 1.0 / 64  # more escapes than this: the tile is not worth packing (pack() returns None)
+
+    def __init__(self, data, esc_idx, esc_val, n_esc, shape):
+        self.data, self.esc_idx, self.esc_val, self.n_esc, self.shape = data, esc_idx, esc_val, int(n_esc), tuple(shape)
+
+    @staticmethod
+    def buffers(n: int, pin: bool = True):
+        cap = max(1024, int(n * PackedCounts8.MAX_ESCAPE_FRACTION))
+        bufs = [torch.empty(n, dtype=torch.uint8), torch.empty(cap, dtype=torch.int32), torch.empty(cap, dtype=torch.float32)]
+        if pin and torch.cuda.is_available():
+            bufs = [b.pin_memory() for b in bufs]
+        return bufs
+
+    @staticmethod
+    def pack(x: torch.Tensor, n_threads: Optional[int] = None, out=None) -> Optional["PackedCounts8"]:
+        """None when the tile has too many escapes (the caller then ships it in another format)."""
+        if x.is_cuda or x.dtype != torch.float32:
+            raise TypeError("PackedCounts8.pack expects a host fp32 tensor")
+        x = x.contiguous()
+        n = x.numel()
+        data, eidx, eval_ = out if out is not None else PackedCounts8.buffers(n)
+        lib = _lib.load()
+        nt = n_threads or default_pack_threads()
+        k = lib.drv_host_pack_counts_u8(C.c_void_p(x.data_ptr()), C.c_void_p(data.data_ptr()), n, C.c_void_p(eidx.data_ptr()),
+                                        C.c_void_p(eval_.data_ptr()), eidx.numel(), nt)
+        if k == -1:
+            raise RuntimeError("drv_host_pack_counts_u8: invalid arguments")
+        if k < 0:
+            return None
+        return PackedCounts8(data, eidx, eval_, k, x.shape)
+
+    def unpack_host(self) -> torch.Tensor:
+        """fp32 tile on the host (tests)."""
+        out = self.data.to(torch.float32)
+        if self.n_esc:
+            import numpy as np
+
+            idx = torch.from_numpy(self.esc_idx[:self.n_esc].numpy().view(np.uint32).astype(np.int64))
+            out[idx] = self.esc_val[:self.n_esc]
+        return out.reshape(self.shape)
+
+
+def default_pack_threads() -> int:
+    """Worker threads of the host packer: the cores this process may run on, minus two for the Python main thread and
+    the prefetcher's worker (``DRV_PACK_THREADS`` overrides)."""
+    env = os.environ.get("DRV_PACK_THREADS")
+    if env:
+        return max(1, int(env))
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(32, n - 2))
 
 
 def pack_batches(batches: Iterable[Sequence]) -> List[list]:
@@ -216,15 +281,22 @@ class MCVDataLoader(torch.utils.data.DataLoader):
 class PinnedBatchPrefetcher:
     """Iterate ``batches`` with the host->device copy of the next ones already in flight.
 
-    pack_on_the_fly: also pack fp32 host tiles to 16 bits in the worker thread before the copy (only
-    pays when the host packs faster than the bus moves the saved bytes; off by default)."""
+    pack_on_the_fly: how fp32 host count tiles cross the bus.  ``"u8"`` (default): packed to one byte per entry +
+    escapes by the worker (lossless, 4x fewer bytes; a tile with too many escapes falls back to fp32);
+    ``"u16"`` / ``True``: the older 16-bit packing; ``False`` / ``None``: fp32 as the reference ships it."""
 
     SLOTS = 3
 
-    def __init__(self, batches: Iterable[Sequence], device: torch.device, pack_on_the_fly: bool = False):
+    def __init__(self, batches: Iterable[Sequence], device: torch.device, pack_on_the_fly="u8"):
         self.batches = batches
         self.device = torch.device(device)
-        self.pack_on_the_fly = pack_on_the_fly
+        self.pack_on_the_fly = "u16" if pack_on_the_fly is True else (pack_on_the_fly or None)
+        if self.pack_on_the_fly not in (None, "u8", "u16"):
+            raise ValueError("pack_on_the_fly: 'u8', 'u16' or None")
+        self._host8 = [None] * self.SLOTS      # pinned (bytes, escape indices, escape values) for on-the-fly u8 packing
+        self._staged8 = [None] * self.SLOTS    # their device copies
+        self.pack_seconds = 0.0                 # host time spent packing (worker thread)
+        self.packed_batches = 0
         self.stream = torch.cuda.Stream(device=self.device)
         self._x = [None] * self.SLOTS          # fp32 device tiles handed to the step
         self._staged = [None] * self.SLOTS     # uint16 device staging
@@ -240,16 +312,42 @@ class PinnedBatchPrefetcher:
         with torch.cuda.stream(self.stream):
             if self._consumed[slot] is not None:
                 self.stream.wait_event(self._consumed[slot])
-            packed = x if isinstance(x, PackedCounts) else None
-            if packed is None and self.pack_on_the_fly and torch.is_tensor(x) and not x.is_cuda and x.dtype == torch.float32:
+            packed = x if isinstance(x, (PackedCounts, PackedCounts8)) else None
+            host_fp32 = torch.is_tensor(x) and not x.is_cuda and x.dtype == torch.float32
+            if packed is None and self.pack_on_the_fly and host_fp32:
+                import time as _time
+
+                t0 = _time.perf_counter()
                 n = x.numel()
-                if self._host16[slot] is None or self._host16[slot].numel() != n:
-                    self._host16[slot] = torch.empty(n, dtype=torch.int16).pin_memory()
-                packed = PackedCounts.pack(x, out=self._host16[slot])
+                if self.pack_on_the_fly == "u8":
+                    if self._host8[slot] is None or self._host8[slot][0].numel() != n:
+                        self._host8[slot] = PackedCounts8.buffers(n)
+                    packed = PackedCounts8.pack(x, out=self._host8[slot])
+                else:
+                    if self._host16[slot] is None or self._host16[slot].numel() != n:
+                        self._host16[slot] = torch.empty(n, dtype=torch.int16).pin_memory()
+                    packed = PackedCounts.pack(x, out=self._host16[slot])
+                self.pack_seconds += _time.perf_counter() - t0
+                self.packed_batches += 1
             shape = packed.shape if packed is not None else tuple(x.shape)
             if self._x[slot] is None or tuple(self._x[slot].shape) != shape:
                 self._x[slot] = torch.empty(shape, dtype=torch.float32, device=self.device)
-            if packed is not None:
+            if isinstance(packed, PackedCounts8):
+                n, k = packed.data.numel(), packed.n_esc
+                st8 = self._staged8[slot]
+                if st8 is None or st8[0].numel() != n or st8[1].numel() < packed.esc_idx.numel():
+                    st8 = self._staged8[slot] = [torch.empty(n, dtype=torch.uint8, device=self.device),
+                                                 torch.empty(packed.esc_idx.numel(), dtype=torch.int32, device=self.device),
+                                                 torch.empty(packed.esc_idx.numel(), dtype=torch.float32, device=self.device)]
+                st8[0].copy_(packed.data, non_blocking=True)
+                if k:
+                    st8[1][:k].copy_(packed.esc_idx[:k], non_blocking=True)
+                    st8[2][:k].copy_(packed.esc_val[:k], non_blocking=True)
+                _lib.check(lib.drv_unpack_counts_u8(C.c_void_p(st8[0].data_ptr()), C.c_void_p(st8[1].data_ptr()),
+                                                    C.c_void_p(st8[2].data_ptr()), k, C.c_void_p(self._x[slot].data_ptr()), n,
+                                                    C.c_void_p(self.stream.cuda_stream)), "drv_unpack_counts_u8")
+                self.h2d_bytes += n + 8 * k
+            elif packed is not None:
                 n = packed.data.numel()
                 if self._staged[slot] is None or self._staged[slot].numel() != n:
                     self._staged[slot] = torch.empty(n, dtype=torch.int16, device=self.device)

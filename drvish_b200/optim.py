@@ -9,7 +9,9 @@ over the flat parameter / gradient / momentum buffers.
 
 It is a ``torch.optim.Optimizer`` with ONE parameter group, so the stock torch LR schedulers
 (e.g. ``CosineAnnealingWarmRestarts``, what the reference's ``train_until_plateau`` uses) drive
-``param_groups[0]["lr"]``.  ``PyroFusedAggMo`` is the callable Pyro's ``SVI`` expects as ``optim``."""
+``param_groups[0]["lr"]``.  ``PyroFusedAggMo`` is the callable Pyro's ``SVI`` expects as ``optim``;
+``PyroFusedScheduler`` adds the LR-schedule surface ``train_until_plateau`` drives (``step(epoch)``,
+``optim_objs[*].T_cur / T_0``)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -118,3 +120,48 @@ class PyroFusedAggMo:
 
     def set_state(self, state) -> None:
         self.optim.load_state_dict(state)
+
+
+class PyroFusedScheduler:
+    """Drop-in for a Pyro LR scheduler over the reference optimizer - notebook cell 10:
+    ``pyro.optim.CosineAnnealingWarmRestarts({"optimizer": AggMo, "optim_args": {...}, "T_0": ..., ...}, clip_args)`` -
+    i.e. everything ``pyro.infer.SVI`` and ``train_until_plateau`` (train/__init__.py:54-110) touch:
+
+    * ``__call__(params)``: what ``SVI.step`` calls after ``loss_and_grads`` - one fused AggMo step;
+    * ``step(epoch)``: what ``train_until_plateau`` calls once per epoch (:95) - advances the schedule;
+    * ``optim_objs``: ``{key: scheduler}`` whose values expose ``T_cur`` / ``T_0`` (:96: "did a cosine cycle just
+      end?").  Pyro keeps one optimizer + scheduler per parameter tensor, all stepped in lock-step; here there is
+      ONE ``FusedAggMo`` over the flat buffers and hence one scheduler object, which answers the same question;
+    * ``get_state`` / ``set_state``.
+
+    ``scheduler_constructor`` is the torch scheduler class (default ``CosineAnnealingWarmRestarts``); ``optim_args``
+    has Pyro's layout: ``{"optimizer": <ignored: the fused AggMo is used>, "optim_args": {lr, betas, ...}, **scheduler_kwargs}``."""
+
+    def __init__(self, model: NBVAE, optim_args: dict, clip_args: Optional[dict] = None, scheduler_constructor=None):
+        if scheduler_constructor is None:
+            scheduler_constructor = torch.optim.lr_scheduler.CosineAnnealingWarmRestarts
+        args = dict(optim_args)
+        args.pop("optimizer", None)
+        inner = args.pop("optim_args", {})
+        clip = None if not clip_args else clip_args.get("clip_norm")
+        self.optim = FusedAggMo(model, clip_norm=clip, **inner)
+        self.scheduler = scheduler_constructor(self.optim, **args)
+        self.optim_objs = {"flat_buffers": self.scheduler}
+
+    def __call__(self, params, *args, **kwargs) -> None:
+        self.optim.step()
+
+    def step(self, *args, **kwargs) -> None:
+        import warnings
+
+        with warnings.catch_warnings():  # torch deprecates the epoch argument the reference passes
+            warnings.simplefilter("ignore", UserWarning)
+            for sched in self.optim_objs.values():
+                sched.step(*args, **kwargs)
+
+    def get_state(self):
+        return {"optimizer": self.optim.state_dict(), "scheduler": self.scheduler.state_dict()}
+
+    def set_state(self, state) -> None:
+        self.optim.load_state_dict(state["optimizer"])
+        self.scheduler.load_state_dict(state["scheduler"])

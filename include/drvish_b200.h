@@ -182,6 +182,19 @@ int drv_draw_step_noise(const drv_dims* dims, const drv_hparams* hp, uint64_t se
 int64_t drv_host_pack_counts_u16(const float* h_src, uint16_t* h_dst, int64_t n, int n_threads);
 int drv_unpack_counts_u16(const uint16_t* src, float* dst, int64_t n, void* stream);
 
+/* Lossless 8-bit staging (the default transport of integer count tiles): h_dst[i] = (uint8)h_src[i] where
+ * h_src[i] is an integer 0..254, otherwise 255 and (i, h_src[i]) is appended to the escape list - so ANY fp32 tile
+ * is reproduced bit-exactly, at one byte per entry over the bus when counts are small.  HOST pointers; h_dst
+ * 64-byte aligned; n < 2^32.  Runs on a persistent pool of n_threads workers (AVX-512 / AVX2 / scalar chosen at
+ * run time: drv_host_pack_isa).  Returns the number of escapes, -1 for invalid arguments, -2 when there are more
+ * than max_escapes.  drv_unpack_counts_u8 widens the device copy to fp32 and patches the escapes (DEVICE pointers,
+ * src and dst 16-byte aligned). */
+int64_t drv_host_pack_counts_u8(const float* h_src, uint8_t* h_dst, int64_t n, uint32_t* h_esc_idx, float* h_esc_val,
+                                int64_t max_escapes, int n_threads);
+const char* drv_host_pack_isa(void);
+int drv_unpack_counts_u8(const uint8_t* src, const uint32_t* esc_idx, const float* esc_val, int n_escapes, float* dst,
+                         int64_t n, void* stream);
+
 /* Fused optimizer step over the flat buffers: AggMo.step (reference
  * src/drvish/train/aggmo.py:42-79) applied to every parameter tensor, preceded by Pyro's per-tensor
  * gradient clipping (PyroOptim clip_args {"clip_norm": c} = torch.nn.utils.clip_grad_norm_ on each

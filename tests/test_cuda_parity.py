@@ -422,8 +422,9 @@ def test_forward_is_run_to_run_deterministic():
 
 def test_prefetcher_delivers_exact_tiles_fp32_packed_and_on_the_fly():
     """PinnedBatchPrefetcher: fp32 host tiles, PackedCounts (uint16 over the bus, drv_unpack_counts_u16 on
-    the device) and on-the-fly packing all hand the step the same fp32 tile, bit for bit; a tile that is
-    not representable in 16 bits travels as fp32."""
+    the device) and on-the-fly packing (uint16, and the default one byte per entry + escapes) all hand the step
+    the same fp32 tile, bit for bit; a tile that is not representable in 16 bits travels as fp32, in the 8-bit
+    transport a non-integer / large entry is an escape."""
     from drvish_b200.data import PackedCounts, PinnedBatchPrefetcher, pack_batches
 
     g = torch.Generator().manual_seed(5)
@@ -434,7 +435,7 @@ def test_prefetcher_delivers_exact_tiles_fp32_packed_and_on_the_fly():
     fp32 = [[t, labels] for t in tiles]
     packed = pack_batches(fp32)
     assert [isinstance(b[0], PackedCounts) for b in packed] == [True, True, True, False, True, True, True]
-    for dataset, fly in ((fp32, False), (packed, False), (fp32, True)):
+    for dataset, fly in ((fp32, None), (packed, None), (fp32, "u16"), (fp32, "u8"), (fp32, True)):
         pf = PinnedBatchPrefetcher(dataset, "cuda:0", pack_on_the_fly=fly)
         for epoch in range(2):
             got = []

@@ -167,3 +167,71 @@ def test_peer_allreduce_needs_an_nccl_group():
     from drvish_b200.parallel import PeerAllReduce
 
     assert PeerAllReduce.create(1024, "cpu") is None  # torch.distributed not initialised: NCCL / single rank path
+
+
+def test_host_pack_u8_with_escapes_is_lossless():
+    """drv_host_pack_counts_u8 (host side of the default count-tile transport): bytes + escape list reproduce ANY fp32
+    tile bit for bit - small integers as bytes, everything else (>= 255, non-integer, negative, inf) as escapes;
+    every vector width's tail, several thread counts; too many escapes -> refused."""
+    import torch
+
+    from drvish_b200.data import PackedCounts8
+
+    g = torch.Generator().manual_seed(3)
+    for n in (1, 15, 63, 64, 65, 257, 4099, 300_001):
+        x = torch.poisson(torch.full((n,), 2.5), generator=g)
+        x[n // 2] = 255.0
+        if n > 20:
+            x[3], x[7], x[11], x[n - 1] = 1.5, -1.0, 70000.0, float("inf")
+        for nt in (1, 3):
+            p = PackedCounts8.pack(x, n_threads=nt)
+            assert p is not None and p.n_esc == (5 if n > 20 else 1), (n, nt, p.n_esc)
+            assert torch.equal(p.unpack_host(), x), (n, nt)
+    dense = torch.full((100_000,), 1000.0)  # every entry an escape: over the cap
+    assert PackedCounts8.pack(dense, n_threads=2) is None
+
+
+def test_pyro_fused_scheduler_drives_train_until_plateau():
+    """The reference's train_until_plateau (train/__init__.py:89-108) restated verbatim around a stub SVI: it calls
+    scheduler.step(epoch) and looks at scheduler.optim_objs[*].T_cur / T_0 to detect the end of a cosine cycle."""
+    import itertools
+
+    import numpy as np
+
+    import drvish_b200 as D
+
+    model = D.NBVAE(n_input=16, n_latent=2, layers=[8, 8])
+    sched = D.PyroFusedScheduler(model, {"optimizer": None, "optim_args": {"lr": 5e-4, "betas": [0.0, 0.9, 0.99], "nesterov": True},
+                                         "T_0": 4, "T_mult": 1}, {"clip_norm": 20.0})
+    assert sched.optim.param_groups[0]["lr"] == pytest.approx(5e-4 / 3)  # aggmo.py:22
+
+    class StubSVI:  # losses improve for two cycles, then stall
+        def __init__(self):
+            self.k = 0
+
+        def step(self, *xs):
+            return 100.0
+
+        def evaluate_loss(self, *xs):
+            self.k += 1
+            return max(50.0, 100.0 - 5.0 * self.k)
+
+    svi, train_loss, val_loss = StubSVI(), [], []
+    best, threshold, min_cycles, cycle = np.inf, 0.01, 3, 0
+    lrs = []
+    for epoch in itertools.count():
+        train_loss.append(svi.step())
+        val_loss.append(svi.evaluate_loss())
+        sched.step(epoch)
+        lrs.append(sched.optim.param_groups[0]["lr"])
+        if any(opt.T_cur == opt.T_0 - 1 for opt in sched.optim_objs.values()):
+            cycle += 1
+            if 0 <= val_loss[-1] < best * (1.0 - threshold):
+                best = val_loss[-1]
+            elif cycle >= min_cycles:
+                break
+        assert epoch < 200
+    assert cycle >= min_cycles and len(train_loss) == len(val_loss) == epoch + 1
+    assert max(lrs) == pytest.approx(5e-4 / 3, rel=0.2) and min(lrs) < 0.3 * max(lrs)  # the cosine really moves the fused optimizer's lr
+    state = sched.get_state()
+    sched.set_state(state)
