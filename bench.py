@@ -267,9 +267,7 @@ class Workload:
         e, rt = self.elbo, self.rt
         xb = self.xs[i % self.n_batches]
         if self.world > 1 and not single_call and not e.dp_overlap:
-            e._enqueue(rt, xb, self.labels, self.yflat, True, part=3)
-            if reduce:
-                e.dp_all_reduce(rt)
+            e.dp_step(rt, xb, self.labels, self.yflat, reduce=reduce)
         elif self.world > 1 and not single_call:
             e._enqueue(rt, xb, self.labels, self.yflat, True, part=1)
             w1 = dist.all_reduce(rt.flat_grads[rt.decoder_offset:], op=dist.ReduceOp.SUM, async_op=True)
@@ -490,7 +488,7 @@ def run_native(args, cfg):
     ms_per_step, clocks = w.timed(args.steps, args.warmup, sample_clocks=True)
     launches_per_step = rt.last_launches + 1  # + the noise draw (one launch)
     if world > 1 and not elbo.dp_overlap:
-        launches_per_step += 1  # + the all-reduce kernel
+        launches_per_step += 1  # + the all-reduce kernel (inside the step's CUDA graph when it is the peer-memory one)
     loss_last, status = rt.read_out()
     value = world * B / (ms_per_step * 1e-3)
 
@@ -534,6 +532,7 @@ def run_native(args, cfg):
     fp32_set = [[hx] + tail for hx in host_x]
     # the same minibatches packed once to 16 bits (dataset-build-time work, lossless: data.PackedCounts)
     u16_set = pack_batches(fp32_set)
+    u8_set = pack_batches(fp32_set, kind="u8")  # ... or to one byte per entry + escapes (data.PackedCounts8)
 
     def run_e2e(pf, dataset, n):
         pf.batches = (dataset[i % len(dataset)] for i in range(n))
@@ -581,6 +580,7 @@ def run_native(args, cfg):
     e2e_value, e2e_h2d, e2e_pack_ms = time_e2e(fp32_set, on_the_fly="u8")
     e2e_f32, e2e_f32_h2d, _ = time_e2e(fp32_set, on_the_fly=None)
     e2e_u16, e2e_u16_h2d, _ = time_e2e(u16_set, on_the_fly=None)
+    e2e_u8d, e2e_u8d_h2d, _ = time_e2e(u8_set, on_the_fly=None)
     e2e_fly, e2e_fly_h2d, e2e_fly_ms = time_e2e(fp32_set, on_the_fly="u16")
     from drvish_b200.data import default_pack_threads
     pack_isa = lib.drv_host_pack_isa().decode()
@@ -592,7 +592,7 @@ def run_native(args, cfg):
     else:
         others = [2] if world == 1 else ([4, 5] if world == 8 else [])
     others = [c for c in others if c != args.config]
-    del host_x, fp32_set, u16_set, csr, csr_idx
+    del host_x, fp32_set, u16_set, u8_set, csr, csr_idx
     other_configs = {}
     if others:
         keep_sm = (clocks or {}).get("sm_mhz")
@@ -634,8 +634,9 @@ def run_native(args, cfg):
                 # same API, the reference's transport: the fp32 tile itself crosses the bus (PCIe-bound)
                 "fp32_transport": {"value": e2e_f32, "unit": "cells/s", "h2d_bytes_per_step": e2e_f32_h2d,
                                    "bound": "PCIe: %.1f GB/s host->device" % (e2e_f32_h2d * e2e_f32 / (world * B) / 1e9)},
-                # same API, minibatches packed ONCE to lossless uint16 when the dataset is built
+                # same API, minibatches packed ONCE when the dataset is built (pack_batches): lossless uint16, or bytes + escapes
                 "packed_u16_dataset": {"value": e2e_u16, "unit": "cells/s", "h2d_bytes_per_step": e2e_u16_h2d},
+                "packed_u8_dataset": {"value": e2e_u8d, "unit": "cells/s", "h2d_bytes_per_step": e2e_u8d_h2d},
                 # same API, fp32 host minibatches packed to uint16 by the prefetcher's worker every step
                 "packed_u16_on_the_fly": {"value": e2e_fly, "unit": "cells/s", "h2d_bytes_per_step": e2e_fly_h2d,
                                           "pack_ms_per_batch": e2e_fly_ms},

@@ -126,13 +126,17 @@ def default_pack_threads() -> int:
     return max(1, min(32, n - 2))
 
 
-def pack_batches(batches: Iterable[Sequence]) -> List[list]:
-    """Dataset-build-time packing: the count tile of every batch becomes ``PackedCounts`` where it is
-    representable (otherwise the fp32 tensor is kept, pinned)."""
+def pack_batches(batches: Iterable[Sequence], kind: str = "u16") -> List[list]:
+    """Dataset-build-time packing: the count tile of every batch becomes ``PackedCounts`` (``kind="u16"``) or
+    ``PackedCounts8`` (``kind="u8"``: one byte per entry + escapes) where it is representable (otherwise the fp32
+    tensor is kept, pinned)."""
+    if kind not in ("u8", "u16"):
+        raise ValueError("kind: 'u8' or 'u16'")
+    packer = PackedCounts8 if kind == "u8" else PackedCounts
     out = []
     for b in batches:
         x = b[0]
-        p = PackedCounts.pack(x) if (torch.is_tensor(x) and not x.is_cuda and x.dtype == torch.float32) else None
+        p = packer.pack(x) if (torch.is_tensor(x) and not x.is_cuda and x.dtype == torch.float32) else None
         if p is None and torch.is_tensor(x) and not x.is_cuda and not x.is_pinned() and torch.cuda.is_available():
             x = x.pin_memory()
         out.append([p if p is not None else x] + list(b[1:]))

@@ -127,6 +127,17 @@ class FusedTraceELBO:
             torch.distributed.all_reduce(rt.flat_grads[:rt.n_param_floats + _lib.DRV_GRAD_TAIL_FLOATS],
                                          op=torch.distributed.ReduceOp.SUM, group=self.process_group)
 
+    def dp_step(self, rt, x, labels, y, mcv=None, reduce: bool = True) -> None:
+        """One data-parallel step: the whole ELBO step, then ONE all-reduce of the flat gradient buffer.  With the
+        peer-memory kernel the all-reduce is part of the step's CUDA graph (its flag barriers are numbered by a device
+        epoch counter, so a replay is as good as a launch): no Python and no launch gap between the last gradient
+        kernel and the collective.  With NCCL it is issued after the graph."""
+        peer = self._peer.get(id(rt))
+        in_graph = reduce and peer is not None and self.use_cuda_graph and self._explicit_noise is None
+        self._enqueue(rt, x, labels, y, True, part=4 if in_graph else 3, mcv=mcv)
+        if reduce and not in_graph:
+            self.dp_all_reduce(rt)
+
     def dp_prepare(self, rt) -> None:
         """Set up the peer-memory all-reduce (collective call: every rank, before its first step)."""
         if id(rt) in self._peer:
@@ -210,8 +221,7 @@ class FusedTraceELBO:
             # whole step, then ONE all-reduce of the flat gradient buffer (loss in its tail slot)
             if id(rt) not in self._peer:
                 self.dp_prepare(rt)
-            self._enqueue(rt, x, labels, y, True, part=3, mcv=mcv)
-            self.dp_all_reduce(rt)
+            self.dp_step(rt, x, labels, y, mcv=mcv)
         elif want_grads and dp:
             # two-part step: the all-reduce of the decoder + dose-response slice (incl. the loss in the
             # tail slot) runs on NCCL's stream while the encoder backward is still computing
@@ -258,12 +268,14 @@ class FusedTraceELBO:
         kernel variant), so a training loop that cycles through a few staging buffers - e.g.
         PinnedBatchPrefetcher's two - replays ~70 kernel launches with one cudaGraphLaunch."""
         pflags = {0: 0, 1: _lib.DRV_FLAG_STOP_AFTER_DECODER, 2: _lib.DRV_FLAG_ENCODER_BACKWARD_ONLY,
-                  3: _lib.DRV_FLAG_LOSS_IN_GRADS}[part]
+                  3: _lib.DRV_FLAG_LOSS_IN_GRADS, 4: _lib.DRV_FLAG_LOSS_IN_GRADS}[part]
 
         def eager():
             # part 2 continues the step of part 1: same noise buffers, no new draws
             noise = self._noise(rt, x.shape[0], draw=(part != 2))
             rt.elbo_step(x, labels, y, noise, want_grads, self.flags | pflags, self.include_guide_factor, mcv=mcv)
+            if part == 4:  # the step's collective, same stream: captured into the same graph
+                self._peer[id(rt)].all_reduce()
 
         if not self.use_cuda_graph or self._explicit_noise is not None or not x.is_cuda:
             return eager()
