@@ -435,8 +435,12 @@ def test_prefetcher_delivers_exact_tiles_fp32_packed_and_on_the_fly():
     fp32 = [[t, labels] for t in tiles]
     packed = pack_batches(fp32)
     assert [isinstance(b[0], PackedCounts) for b in packed] == [True, True, True, False, True, True, True]
-    for dataset, fly in ((fp32, None), (packed, None), (fp32, "u16"), (fp32, "u8"), (fp32, True)):
+    pinned = [[t.pin_memory(), labels] for t in tiles]  # pinned fp32 tiles take the hybrid fp32-DMA + packed-bytes route
+    packed8 = pack_batches(fp32, kind="u8")
+    for dataset, fly in ((fp32, None), (packed, None), (fp32, "u16"), (fp32, "u8"), (fp32, True), (pinned, "u8"), (packed8, None)):
         pf = PinnedBatchPrefetcher(dataset, "cuda:0", pack_on_the_fly=fly)
+        if dataset is pinned:
+            pf.hybrid_fraction = 0.5
         for epoch in range(2):
             got = []
             for x, lab in pf:
