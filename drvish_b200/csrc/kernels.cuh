@@ -81,6 +81,24 @@ void dr_prior_factor(const float* w_prior, const float* b_prior, const float* ep
 void finalize_step(drv_step_out* out, const uint32_t* status, int64_t* counters, int n, const float* ll, int B,
                    float scale, cudaStream_t st, float* loss_slot = nullptr, uint32_t path = 0);
 
+// ---- k_pad.cu: shape padding for the tensor-core path (see the file header) ------------------------
+// One tensor of a flat buffer: real layout [n_blocks x src_rows][src_cols] at src_off, padded layout
+// [dst_rows][dst_cols] at dst_off; block b of the real rows starts at padded row b * blk_stride; pad[b] fills the
+// padded entries of block b (and all pad columns).
+struct PadSeg {
+  long long src_off, dst_off;
+  int src_rows, src_cols, dst_rows, dst_cols, n_blocks, blk_stride;
+  float pad[2];
+};
+struct PadSegs {
+  int n;
+  PadSeg seg[80];  // segments ordered by offset in both layouts (<= 2 x 9 blocks x 4 tensors + 4)
+};
+void pad_params(const float* src, float* dst, const PadSegs& s, long long n_dst, cudaStream_t st);
+void unpad(const float* padded, float* real, const PadSegs& s, long long n_real, int n_tail, long long tail_padded,
+           long long tail_real, cudaStream_t st);
+void pad_rows(const float* x, int B, int G, int Gp, float* xp, cudaStream_t st);
+
 // ---- k_optim.cu ------------------------------------------------------------------------------------
 int aggmo_step(const long long* offs, const long long* lens, int n_tensors, const drv_aggmo& hp, float* params,
                const float* grads, float* momentum, long long mom_stride, double* norms, cudaStream_t st);

@@ -204,6 +204,83 @@ Plan make_plan(const drv_dims& d, const Net& n) {
   return p;
 }
 
+
+// ---- shape padding (k_pad.cu): the next aligned problem for shapes the tensor-core kernels cannot take ----------
+inline int up_to(int v, int a) { return (v + a - 1) / a * a; }
+
+drv_dims padded_dims(const drv_dims& d) {
+  drv_dims p = d;
+  p.n_genes = up_to(d.n_genes, 8);
+  for (int i = 0; i < d.n_layers; ++i) p.layers[i] = up_to(d.layers[i], 32);
+  return p;
+}
+
+// pad when it turns a CUDA-core shape into a tensor-core one: genes not a multiple of 8 (16-byte-aligned halves of the
+// fp16 d logits, TMA row strides) or a hidden width not a multiple of 32 (k-blocks, MN-major GEMM tiles)
+bool pad_wanted(const drv_dims& d) {
+  bool ragged = d.n_genes % 8 != 0;
+  for (int i = 0; i < d.n_layers; ++i) ragged |= d.layers[i] % 32 != 0;
+  if (!ragged || d.n_genes < 64 || d.n_cells < 32) return false;
+  static const bool off = getenv("DRV_NO_PAD") != nullptr;  // debug / A-B
+  return !off && up_to(d.layers[0], 32) <= 512;  // the fused decoder takes hidden widths up to 512
+}
+
+struct PadPlan {
+  drv_dims dp;
+  Net nr, np;
+  PadSegs params, bn;
+  size_t off_params, off_grads, off_bn, off_x, off_x2, total;  // byte offsets in the workspace, behind the padded plan
+};
+
+void add_seg(PadSegs& S, long long src_off, long long dst_off, int src_rows, int src_cols, int dst_rows, int dst_cols, float pad0,
+             int n_blocks = 1, int blk_stride = 0, float pad1 = 0.f) {
+  PadSeg& g = S.seg[S.n++];
+  g.src_off = src_off; g.dst_off = dst_off; g.src_rows = src_rows; g.src_cols = src_cols; g.dst_rows = dst_rows; g.dst_cols = dst_cols;
+  g.n_blocks = n_blocks; g.blk_stride = blk_stride; g.pad[0] = pad0; g.pad[1] = pad1;
+}
+
+PadPlan make_pad_plan(const drv_dims& d, size_t plan_total) {
+  PadPlan P{};
+  P.dp = padded_dims(d);
+  P.nr = make_net(d);
+  P.np = make_net(P.dp);
+  const int G = d.n_genes, Gp = P.dp.n_genes;
+  for (int s = 0; s < 2; ++s)
+    for (int k = 0; k < P.nr.n_blocks; ++k) {
+      const Block& r = s == 0 ? P.nr.enc[k] : P.nr.dec[k];
+      const Block& q = s == 0 ? P.np.enc[k] : P.np.dec[k];
+      const bool last_dec = s == 1 && k == P.nr.n_blocks - 1;  // [scale half | log_r half] rows: each half is padded on its own
+      add_seg(P.params, r.gamma, q.gamma, r.din, 1, q.din, 1, 1.f);
+      add_seg(P.params, r.beta, q.beta, r.din, 1, q.din, 1, 0.f);
+      if (last_dec) {
+        add_seg(P.params, r.W, q.W, G, r.din, 2 * Gp, q.din, 0.f, 2, Gp, 0.f);
+        // pad genes: scale-half bias -1e30 (softmax probability exactly 0, NB terms exactly 0), log_r-half bias 0
+        add_seg(P.params, r.bias, q.bias, G, 1, 2 * Gp, 1, -1.0e30f, 2, Gp, 0.f);
+      } else {
+        add_seg(P.params, r.W, q.W, r.dout, r.din, q.dout, q.din, 0.f);
+        add_seg(P.params, r.bias, q.bias, r.dout, 1, q.dout, 1, 0.f);
+      }
+      add_seg(P.bn, r.rmean, q.rmean, r.din, 1, q.din, 1, 0.f);
+      add_seg(P.bn, r.rvar, q.rvar, r.din, 1, q.din, 1, 1.f);
+    }
+  if (d.n_drugs > 0) {
+    const int DL = d.n_drugs * d.n_latent, T = d.n_doses_total;
+    add_seg(P.params, P.nr.w_loc, P.np.w_loc, DL, 1, DL, 1, 0.f);
+    add_seg(P.params, P.nr.w_scale, P.np.w_scale, DL, 1, DL, 1, 0.f);
+    add_seg(P.params, P.nr.b_loc, P.np.b_loc, T, 1, T, 1, 0.f);
+    add_seg(P.params, P.nr.b_scale, P.np.b_scale, T, 1, T, 1, 0.f);
+  }
+  size_t o = (plan_total + 255) / 256 * 256;
+  auto take = [&](size_t bytes) { size_t r = o; o = (o + bytes + 255) / 256 * 256; return r; };
+  P.off_params = take(4 * (size_t)P.np.n_param_floats);
+  P.off_grads = take(4 * ((size_t)P.np.n_param_floats + 32));
+  P.off_bn = take(4 * (size_t)P.np.n_bn_floats);
+  P.off_x = take(4 * (size_t)d.n_cells * Gp);
+  P.off_x2 = take(4 * (size_t)d.n_cells * Gp);
+  P.total = o;
+  return P;
+}
+
 struct Ctx {
   const drv_dims& d;
   const drv_hparams& hp;
@@ -388,6 +465,10 @@ int drv_bn_offsets(const drv_dims* dims, int64_t* offsets, int64_t* sizes, int m
 
 size_t drv_workspace_bytes(const drv_dims* dims) {
   if (!valid(dims)) return 0;
+  if (pad_wanted(*dims)) {  // the step runs as the next aligned problem: its plan + the padded copies
+    const drv_dims dp = padded_dims(*dims);
+    return make_pad_plan(*dims, make_plan(dp, make_net(dp)).total).total;
+  }
   Net n = make_net(*dims);
   return make_plan(*dims, n).total;
 }
@@ -395,14 +476,12 @@ size_t drv_workspace_bytes(const drv_dims* dims) {
 // x feeds the encoder, x_lik is scored by the likelihood (the same tile except for MCVNBVAE: x0 / x1);
 // log_split / log_split_c (both or neither): per-cell data-split terms of MCVNBVAE, log_r += lsc - ls
 // for the NB count parameter (mcv_nbvae.py:78-79).
-static int elbo_step_impl(const drv_dims* dims, const drv_hparams* hp, const float* x, const float* x_lik,
+static int elbo_step_core(const drv_dims* dims, const drv_hparams* hp, const float* x, const float* x_lik,
                           const float* log_split, const float* log_split_c, const int64_t* labels, const float* y,
                           const float* eps_z, const float* eps_l, const float* w_prior, const float* b_prior,
                           const float* eps_bias, const int32_t* dose_offsets, const float* params, float* grads,
                           float* bn_running, int64_t* bn_batches, drv_step_out* out, void* workspace,
                           size_t workspace_bytes, void* stream) {
-  g_launches = 0;
-  g_err = cudaSuccess;
   if (!valid(dims) || !hp || !x || !x_lik || !eps_z || !eps_l || !params || !out || !workspace) return DRV_EINVAL;
   if ((log_split == nullptr) != (log_split_c == nullptr)) return DRV_EINVAL;
   const drv_dims& d = *dims;
@@ -595,6 +674,53 @@ static int elbo_step_impl(const drv_dims* dims, const drv_hparams* hp, const flo
     if (!bwd) for (int i = 5; i <= DRV_N_SECTIONS; ++i) prof::mark(i, st);
     ++prof::n_steps;
   }
+  return finish();
+}
+
+// Entry of both step flavours: shapes the tensor-core kernels cannot take are run as the next aligned problem (k_pad.cu).
+static int elbo_step_impl(const drv_dims* dims, const drv_hparams* hp, const float* x, const float* x_lik,
+                          const float* log_split, const float* log_split_c, const int64_t* labels, const float* y,
+                          const float* eps_z, const float* eps_l, const float* w_prior, const float* b_prior,
+                          const float* eps_bias, const int32_t* dose_offsets, const float* params, float* grads,
+                          float* bn_running, int64_t* bn_batches, drv_step_out* out, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  g_err = cudaSuccess;
+  if (!valid(dims) || !hp || !workspace) return DRV_EINVAL;
+  if (!pad_wanted(*dims) || (hp->flags & DRV_FLAG_FORCE_SIMT))
+    return elbo_step_core(dims, hp, x, x_lik, log_split, log_split_c, labels, y, eps_z, eps_l, w_prior, b_prior, eps_bias,
+                          dose_offsets, params, grads, bn_running, bn_batches, out, workspace, workspace_bytes, stream);
+  if (!x || !x_lik || !params) return DRV_EINVAL;
+  const drv_dims dp = padded_dims(*dims);
+  const size_t plan_total = make_plan(dp, make_net(dp)).total;
+  const PadPlan P = make_pad_plan(*dims, plan_total);
+  if (workspace_bytes < P.total) return DRV_ENOSPC;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  float* pp = (float*)(ws + P.off_params);
+  float* gp = grads ? (float*)(ws + P.off_grads) : nullptr;
+  float* bp = bn_running ? (float*)(ws + P.off_bn) : nullptr;
+  float* xp = (float*)(ws + P.off_x);
+  float* xp2 = x_lik != x ? (float*)(ws + P.off_x2) : xp;
+  const int B = dims->n_cells, G = dims->n_genes, Gp = dp.n_genes;
+  const bool part2 = grads && (hp->flags & DRV_FLAG_ENCODER_BACKWARD_ONLY);  // continues part 1: the padded copies are in place
+  if (!part2) {
+    pad_params(params, pp, P.params, P.np.n_param_floats, st);
+    if (bp) pad_params(bn_running, bp, P.bn, P.np.n_bn_floats, st);
+    if (Gp != G) {
+      pad_rows(x, B, G, Gp, xp, st);
+      if (x_lik != x) pad_rows(x_lik, B, G, Gp, xp2, st);
+    }
+  }
+  const float* xin = Gp != G ? xp : x;
+  const float* xlin = Gp != G ? xp2 : x_lik;
+  const int rc = elbo_step_core(&dp, hp, xin, xlin, log_split, log_split_c, labels, y, eps_z, eps_l, w_prior, b_prior, eps_bias,
+                                dose_offsets, pp, gp, bp, bn_batches, out, workspace, plan_total, stream);
+  if (rc != 0) return rc;
+  const bool tail = grads && (hp->flags & (DRV_FLAG_LOSS_IN_GRADS | DRV_FLAG_STOP_AFTER_DECODER));
+  if (grads)
+    unpad(gp, grads, P.params, P.nr.n_param_floats, tail ? DRV_GRAD_TAIL_FLOATS : 0, P.np.n_param_floats, P.nr.n_param_floats, st);
+  if (bp && !(hp->flags & DRV_FLAG_NO_BN_UPDATE)) unpad(bp, bn_running, P.bn, P.nr.n_bn_floats, 0, 0, 0, st);
   return finish();
 }
 

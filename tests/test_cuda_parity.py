@@ -217,6 +217,35 @@ def test_full_size_step_matches_oracle_cfg4_cfg5(name, seed):
     assert rep["bn_worst_rel"] <= 1e-5, _report(rep)
 
 
+# ---- shapes the tensor-core kernels cannot take directly ---------------------------------------------------
+# Gene counts that are not multiples of 8 and hidden widths that are not multiples of 32 are run as the next aligned
+# problem (k_pad.cu: pad genes / pad units are exactly inert) instead of falling back to the CUDA-core path: the
+# result record must say "tcgen05 decoder + encoder" and parity must hold as for any other shape.
+RAGGED = {
+    "ragged_genes": dict(n_input=1003, n_latent=10, layers=[96, 160], batch=300, drugs=0),
+    "ragged_hidden": dict(n_input=1000, n_latent=7, layers=[100, 300], batch=257, drugs=0),
+    "ragged_both_drugs": dict(n_input=1997, n_latent=10, layers=[300, 300], batch=1000, drugs=3, doses=5, classes=4,
+                              lam_scale=1.0, bias_scale=1.0),
+    "panel_19997_h300": dict(n_input=19997, n_latent=10, layers=[300, 300], batch=512, drugs=0),
+}
+
+
+@pytest.mark.parametrize("name", list(RAGGED))
+def test_ragged_shapes_run_on_the_tensor_core_path(name):
+    case = P.make_case(RAGGED[name], data_seed=23, bn_affine_random=True)
+    rep = P.compare_step(case)
+    print(name)
+    print(_report(rep))
+    assert rep["path"] & 3 == 3, "expected the tcgen05 decoder and encoder kernels (shape padding)"
+    assert rep["loss_rel"] <= ELBO_TOL, _report(rep)
+    assert rep["worst_grad_rel"] <= GRAD_TOL, _report(rep)
+    assert rep["bn_worst_rel"] <= 1e-5, _report(rep)
+    # evaluate_loss (forward only) through the same padding
+    loss64, _, _, _ = P.oracle_step(case)
+    loss, _, _ = P.cuda_step(case, want_grads=False)
+    assert abs(loss - loss64) <= ELBO_TOL * abs(loss64)
+
+
 # ---- dispersion regimes ----------------------------------------------------------------------------
 # PyTorch-default weights give r = exp(log_r) + eps ~ 1; trained NB-VAEs reach log_r in [-8, +8].  The log_r half
 # of the last decoder bias is shifted so that r runs from ~3e-4 to ~3e3 (and, at +11, beyond the fast path's
