@@ -220,7 +220,9 @@ drv_dims padded_dims(const drv_dims& d) {
 bool pad_wanted(const drv_dims& d) {
   bool ragged = d.n_genes % 8 != 0;
   for (int i = 0; i < d.n_layers; ++i) ragged |= d.layers[i] % 32 != 0;
-  if (!ragged || d.n_genes < 64 || d.n_cells < 32) return false;
+  // minibatches below one 128-cell tile stay on the fp32 CUDA-core path: nothing to gain there, and the tensor-core
+  // operands' 11-bit rounding noise is averaged over too few cells (measured: 3e-3 on a 7-entry BatchNorm gradient at 96 cells)
+  if (!ragged || d.n_genes < 64 || d.n_cells < 128) return false;
   static const bool off = getenv("DRV_NO_PAD") != nullptr;  // debug / A-B
   return !off && up_to(d.layers[0], 32) <= 512;  // the fused decoder takes hidden widths up to 512
 }
