@@ -279,6 +279,36 @@ class Workload:
             e._enqueue(rt, xb, self.labels, self.yflat, True)
         e.step_index += 1
 
+    def per_rank(self, v):
+        import torch.distributed as dist
+
+        if self.world == 1:
+            return [v]
+        t = torch.tensor([v], device=self.device, dtype=torch.float64)
+        out = torch.empty(self.world, device=self.device, dtype=torch.float64)
+        dist.all_gather_into_tensor(out, t)
+        return [round(float(x), 5) for x in out.tolist()]
+
+    def timed_local(self, steps, warmup):
+        """The step WITHOUT its collective (same CUDA-graph treatment as the full step), per rank: what every rank's
+        own work takes when nobody waits for anybody - the rest of ms_per_step is the collective plus the wait for
+        the slowest rank."""
+        fn = lambda i: self.device_step(i, reduce=False)
+        if not self.args.no_graph:
+            for i in range(2 * self.n_batches):
+                fn(i)
+        for i in range(warmup):
+            fn(i)
+        self.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        ev1.record()
+        self.barrier()
+        mine = ev0.elapsed_time(ev1) / steps
+        return self.max_over_ranks(mine), self.per_rank(mine)
+
     def timed(self, steps, warmup, fn=None, sample_clocks=False):
         """W untimed + K timed steps between barriers, CUDA events on the launching stream, max over ranks (ms/step)."""
         fn = fn or self.device_step
@@ -443,9 +473,9 @@ def measure_other_config(args, config_id, device, world, rank, lib, peaks):
            "value": world * cfg["batch"] / (ms * 1e-3), "unit": "cells/s", "launches_per_step": w.rt.last_launches + 1,
            "grad_bytes": 4 * w.rt.n_param_floats, "clocks": clocks}
     if world > 1:
-        ms_local, _ = w.timed(steps, 3, fn=lambda i: w.device_step(i, reduce=False))
+        ms_local, per_rank = w.timed_local(steps, 3)
         ent["all_reduce"] = {"collective": w.collective(), "alone_ms": w.allreduce_alone_ms(),
-                             "exposed_ms": ms - ms_local, "ms_per_step_without": ms_local}
+                             "exposed_ms": ms - ms_local, "ms_per_step_without": ms_local, "per_rank_ms_without": per_rank}
         ent["dp_check"] = w.dp_check()
     sec, kms, nprof = w.profile_sections(lib, min(steps, 16))
     sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
@@ -496,9 +526,9 @@ def run_native(args, cfg):
     dp_check = all_reduce = None
     if world > 1 and not elbo.dp_overlap:
         dp_check = w.dp_check()
-        ms_local, _ = w.timed(args.steps, 3, fn=lambda i: w.device_step(i, reduce=False))
+        ms_local, per_rank = w.timed_local(args.steps, 3)
         all_reduce = {"collective": w.collective(), "alone_ms": w.allreduce_alone_ms(), "exposed_ms": ms_per_step - ms_local,
-                      "ms_per_step_without": ms_local, "bytes": 4 * (rt.n_param_floats + 1)}
+                      "ms_per_step_without": ms_local, "per_rank_ms_without": per_rank, "bytes": 4 * (rt.n_param_floats + 1)}
         if dp_check["max_rel_err"] > dp_check["tolerance"]:
             raise SystemExit(f"bench.py: data-parallel gradient check failed: {dp_check}")
 
