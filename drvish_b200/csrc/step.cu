@@ -295,6 +295,7 @@ struct Ctx {
   cudaStream_t st;
   SideStream* side;  // may be null: everything then runs on st
   bool enc0_w_prepared = false;  // fp16 weight parts of the encoder input block were produced at the start of the step
+  bool w_prepared[2][DRV_MAX_LAYERS + 1] = {};  // ... and of the trunk blocks
   template <class T> T* at(size_t off) const { return reinterpret_cast<T*>(ws + off); }
   BnParams bn(int s, int k) const {
     const Block& b = s == 0 ? n.enc[k] : n.dec[k];
@@ -324,7 +325,7 @@ bool block_forward(const Ctx& c, int s, int k, const float* U0, bool do_linear, 
     a.W_hi = c.at<float>(c.p.p_hi) + b.W; a.W_lo = c.at<float>(c.p.p_lo) + b.W;
     a.B = B; a.din = b.din; a.dout = b.dout; a.V = c.at<float>(c.p.V[s][k]); a.scratch = c.ws + c.p.tcb[s][k];
     a.no_fused_prologue = (c.hp.flags & 512) != 0;
-    a.w_prepared = sq && c.enc0_w_prepared;
+    a.w_prepared = (sq && c.enc0_w_prepared) || c.w_prepared[s][k];
     ColStatsOut ns{};
     const int n_blocks = c.n.n_blocks;
     if (k + 1 < n_blocks && !(c.hp.flags & 1024)) {  // 1024 (debug): separate statistics kernels
@@ -535,6 +536,16 @@ static int elbo_step_core(const drv_dims* dims, const drv_hparams* hp, const flo
       a.B = B; a.din = n.enc[0].din; a.dout = n.enc[0].dout; a.scratch = c.ws + p.tcb[0][0];
       c.enc0_w_prepared = tc_block_prepare(a, ss);
     }
+    if (side && tc_any)
+      for (int s2 = 0; s2 < 2; ++s2)
+        for (int k = (s2 == 0 ? 1 : 0); k < NB - (s2 == 1 ? 1 : 0); ++k) {  // trunk blocks (not the input layer, not the fused decoder)
+          const Block& b = s2 == 0 ? n.enc[k] : n.dec[k];
+          if (!p.tcb[s2][k] || !tc_block_forward_supported(B, b.din, b.dout, *hp) || (hp->flags & 8)) continue;
+          TcBlockArgs a{};
+          a.sqrt_in = false; a.no_fused_prologue = (hp->flags & 512) != 0; a.W = params + b.W;
+          a.B = B; a.din = b.din; a.dout = b.dout; a.scratch = c.ws + p.tcb[s2][k];
+          c.w_prepared[s2][k] = tc_block_prepare(a, ss);
+        }
     bool enc_sd_ = false;
     if (side) {
       block_forward(c, 0, 0, x, false);  // statistics of x (main stream) overlap the side-stream work

@@ -60,7 +60,7 @@ bool reduce_parts(const float* parts, int n_parts, int M, int N, const float* bi
 // receives the fp16 hi part of the activations.
 int encfwd_fused(const float* x, int B, int G, BnParams bn, const float* w_hi, const float* w_lo, int h,
                  const float* bias, float* V, float* a_hi, float* partials, int max_parts, cudaStream_t st,
-                 const ColStatsOut* stats = nullptr, bool h16 = false);  // returns 1 when `stats` were produced
+                 const ColStatsOut* stats = nullptr, bool h16 = false, bool sqrt_in = true);  // returns 1 when `stats` were produced
 bool encfwd_h16_supported(int G, int h);
 void encfwd_split_weight_h16(const float* W, int h, int G, void* w_hi_h, void* w_lo_h, cudaStream_t st);
 // d gamma / d beta sums of the encoder's input BatchNorm from dH and W without materialising dA (tc_bn0grad.cu)

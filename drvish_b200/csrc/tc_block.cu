@@ -10,6 +10,7 @@
 // (dW = dH^T A, dA = dH W) tolerate single-pass tf32 and reuse A_hi / W_hi; dA is reduced to
 // the BatchNorm gradients (the input x is data, so no dX is needed).
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "kernels.cuh"
 #include "tc.cuh"
@@ -231,8 +232,16 @@ bool tc_block_backward_supported(int B, int din, int dout, const drv_hparams& hp
   return tc_block_forward_supported(B, din, dout, hp) && dout % 4 == 0;
 }
 
+// The fused-prologue fp16 kernel (tc_encfwd.cu) serves the encoder input layer (sqrt, any K) and the h x h trunk blocks
+// (no sqrt; K <= 1280 so that the whole K is one accumulation chain and bias + output statistics finish in its epilogue).
+static bool fused_prologue_h16(const TcBlockArgs& a) {
+  static const bool trunk_off = getenv("DRV_TRUNK_UNFUSED") != nullptr;  // debug / A-B: trunk blocks on the 3xTF32 GEMM
+  if (a.no_fused_prologue || !tc::encfwd_h16_supported(a.din, a.dout)) return false;
+  return a.sqrt_in || (!trunk_off && a.din <= 20 * 64);
+}
+
 bool tc_block_prepare(const TcBlockArgs& a, cudaStream_t st) {
-  if (!(a.sqrt_in && !a.no_fused_prologue && tc::encfwd_h16_supported(a.din, a.dout))) return false;
+  if (!fused_prologue_h16(a)) return false;
   Scratch s = carve(a.scratch, a.B, a.din, a.dout);
   tc::encfwd_split_weight_h16(a.W, a.dout, a.din, s.w_hi, s.w_lo, st);
   return true;
@@ -241,14 +250,14 @@ bool tc_block_prepare(const TcBlockArgs& a, cudaStream_t st) {
 bool tc_block_forward(const TcBlockArgs& a, cudaStream_t st) {
   Scratch s = carve(a.scratch, a.B, a.din, a.dout);
   const size_t n = (size_t)a.B * a.din;
-  if (a.sqrt_in && !a.no_fused_prologue) {
-    // encoder input layer: sqrt / BatchNorm / ReLU / hi-lo split fused into the GEMM's producer side
+  if ((a.sqrt_in && !a.no_fused_prologue) || fused_prologue_h16(a)) {
+    // encoder input layer / trunk block: (sqrt,) BatchNorm / ReLU / hi-lo split fused into the GEMM's producer side
     int rc;
-    if (tc::encfwd_h16_supported(a.din, a.dout)) {
+    if (fused_prologue_h16(a)) {
       // fp16 operands: the weight's fp16 hi / lo parts live in the (otherwise unused) w_hi / w_lo scratch
       if (!a.w_prepared) tc::encfwd_split_weight_h16(a.W, a.dout, a.din, s.w_hi, s.w_lo, st);
       rc = tc::encfwd_fused(a.U, a.B, a.din, a.bn, s.w_hi, s.w_lo, a.dout, a.bias, a.V, s.a_hi, s.parts, kMaxParts, st,
-                            a.next_stats, true);
+                            a.next_stats, true, a.sqrt_in);
     } else {
       rc = tc::encfwd_fused(a.U, a.B, a.din, a.bn, a.W_hi, a.W_lo, a.dout, a.bias, a.V, s.a_hi, s.parts, kMaxParts, st,
                             a.next_stats);
@@ -301,7 +310,7 @@ void tc_block_backward(const TcBlockArgs& a, cudaStream_t st) {
   cudaStream_t ws = st;
   if (a.side) { a.side->attach(); ws = a.side->side; }
   if (rc == 0) {
-    if (a.sqrt_in && !a.no_fused_prologue && tc::encfwd_h16_supported(a.din, a.dout)) {
+    if (fused_prologue_h16(a)) {
       // the forward left the fp16 hi part of the activations in a_hi: dynamically scaled fp16 copy of dV
       // (the a_lo scratch is free: [scale words | fp16 dV]), fp16 GEMM with the inverse scale as alpha
       unsigned* amax = reinterpret_cast<unsigned*>(s.a_lo);

@@ -56,11 +56,33 @@ __device__ __forceinline__ float rna_tf32_(float v) {
 // tile written back for the weight gradient is fp16 too (half the HBM bytes both ways).
 constexpr float LO_SCALE = 2048.f;
 
-template <bool H16>
+// Column sums of 16 values over the 32 lanes of a warp by a transposing butterfly: afterwards w[0] of lane l holds the
+// sum of column (l >> 1) (lanes l and l ^ 1 hold the same column); returns that column index.
+__device__ __forceinline__ int warp_colsum16(float (&w)[16], int lane) {
+#pragma unroll
+  for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+    const bool hi = lane & bit;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = hi ? w[i] : w[i + half];
+      const float keep = hi ? w[i + half] : w[i];
+      w[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+  w[0] += __shfl_xor_sync(0xffffffffu, w[0], 1);
+  // lane bits 4..1 selected halves 8, 4, 2, 1 in turn: column = bit4 * 8 + bit3 * 4 + bit2 * 2 + bit1
+  return (lane >> 1) & 15;
+}
+
+// SQRT: the encoder input layer (sqrt of the counts before the BatchNorm); without it the same kernel is one h x h
+// trunk block relu(bn(U)) W^T + b.  stats_acc (unsplit chunks only): the epilogue also accumulates the column sums /
+// sums of squares of the OUTPUT (the next block's BatchNorm statistics) and the last CTA finalises them.
+template <bool H16, bool SQRT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWhi,
          const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CUtensorMap tmAhi, BnParams bn, int B, int G,
-         int h, int n_tile, int splits, float* __restrict__ out, long long part_stride, const float* __restrict__ bias) {
+         int h, int n_tile, int splits, float* __restrict__ out, long long part_stride, const float* __restrict__ bias,
+         double* __restrict__ stats_acc, StatFinal stats_fin) {
   pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -76,6 +98,7 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
   uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
 
   constexpr int BKE = H16 ? 64 : BK;  // genes per k-block
+  auto pre = [](float v) { return SQRT ? sqrt_count(v) : v; };
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int kb_total = (G + BKE - 1) / BKE;
   const int m_tiles = (B + BM - 1) / BM, n_tiles = (h + n_tile - 1) / n_tile;
@@ -241,14 +264,14 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
               const float4 rstd = __ldg(reinterpret_cast<const float4*>(bn.rstd + col));
               const float4 gam = __ldg(reinterpret_cast<const float4*>(bn.gamma + col));
               const float4 bet = __ldg(reinterpret_cast<const float4*>(bn.beta + col));
-              a[4 * c] = bn_relu(sqrt_count(a[4 * c]), mean.x, rstd.x, gam.x, bet.x);
-              a[4 * c + 1] = bn_relu(sqrt_count(a[4 * c + 1]), mean.y, rstd.y, gam.y, bet.y);
-              a[4 * c + 2] = bn_relu(sqrt_count(a[4 * c + 2]), mean.z, rstd.z, gam.z, bet.z);
-              a[4 * c + 3] = bn_relu(sqrt_count(a[4 * c + 3]), mean.w, rstd.w, gam.w, bet.w);
+              a[4 * c] = bn_relu(pre(a[4 * c]), mean.x, rstd.x, gam.x, bet.x);
+              a[4 * c + 1] = bn_relu(pre(a[4 * c + 1]), mean.y, rstd.y, gam.y, bet.y);
+              a[4 * c + 2] = bn_relu(pre(a[4 * c + 2]), mean.z, rstd.z, gam.z, bet.z);
+              a[4 * c + 3] = bn_relu(pre(a[4 * c + 3]), mean.w, rstd.w, gam.w, bet.w);
             } else {
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                a[4 * c + j] = (col + j < G) ? bn_relu(sqrt_count(a[4 * c + j]), bn.mean[col + j], bn.rstd[col + j],
+                a[4 * c + j] = (col + j < G) ? bn_relu(pre(a[4 * c + j]), bn.mean[col + j], bn.rstd[col + j],
                                                        bn.gamma[col + j], bn.beta[col + j])
                                              : 0.f;
             }
@@ -289,7 +312,7 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
             const float gv[4] = {gam.x, gam.y, gam.z, gam.w}, bv[4] = {bet.x, bet.y, bet.z, bet.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float a = bn_relu(sqrt_count(in[j]), mv[j], rv[j], gv[j], bv[j]);
+              const float a = bn_relu(pre(in[j]), mv[j], rv[j], gv[j], bv[j]);
               hv[j] = rna_tf32_(a);
               lv[j] = rna_tf32_(a - hv[j]);
             }
@@ -297,7 +320,7 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float a = 0.f;
-              if (col + j < G) a = bn_relu(sqrt_count(in[j]), bn.mean[col + j], bn.rstd[col + j], bn.gamma[col + j], bn.beta[col + j]);
+              if (col + j < G) a = bn_relu(pre(in[j]), bn.mean[col + j], bn.rstd[col + j], bn.gamma[col + j], bn.beta[col + j]);
               hv[j] = rna_tf32_(a);
               lv[j] = rna_tf32_(a - hv[j]);
             }
@@ -353,13 +376,29 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
         } else {
           tmem_ld_wait();
         }
+        if (part_stride == 0 && bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0 + c + j < h) v[j] += __ldg(&bias[n0 + c + j]);
+        }
+        if (stats_acc != nullptr) {
+          // BatchNorm statistics of the output for the next block: column sums over this warp's 32 rows by a
+          // transposing butterfly (16 shuffles per moment), then one fp64 atomic per column, moment and warp
+          float s1[16], s2[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            s1[j] = m < B ? v[j] : 0.f;
+            s2[j] = s1[j] * s1[j];
+          }
+          const int col = warp_colsum16(s1, lane);
+          warp_colsum16(s2, lane);
+          if ((lane & 1) == 0 && n0 + c + col < h) {
+            atomicAdd(&stats_acc[n0 + c + col], (double)s1[0]);
+            atomicAdd(&stats_acc[h + n0 + c + col], (double)s2[0]);
+          }
+        }
         if (m < B) {
           float* dst = out + (size_t)part * part_stride + (size_t)m * h + n0 + c;
-          if (part_stride == 0 && bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (n0 + c + j < h) v[j] += __ldg(&bias[n0 + c + j]);
-          }
           if (n0 + c + 16 <= h && ((((uintptr_t)dst) & 15) == 0)) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -380,6 +419,29 @@ k_encfwd(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtens
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+  if (stats_acc != nullptr) {
+    // the last CTA to get here turns the sums into mean / rstd and updates the running buffers
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(stats_fin.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      for (int i = threadIdx.x; i < h; i += blockDim.x) {
+        const double mu = __ldcg(&stats_acc[i]) / stats_fin.B;
+        double var = __ldcg(&stats_acc[h + i]) / stats_fin.B - mu * mu;
+        if (var < 0.0) var = 0.0;
+        stats_fin.mean[i] = (float)mu;
+        stats_fin.rstd[i] = 1.0f / sqrtf((float)(var + (double)stats_fin.eps));
+        if (stats_fin.rmean) {
+          const float unbiased = (float)var * ((float)stats_fin.B / (float)(stats_fin.B - 1));
+          stats_fin.rmean[i] = (1.0f - stats_fin.momentum) * stats_fin.rmean[i] + stats_fin.momentum * (float)mu;
+          stats_fin.rvar[i] = (1.0f - stats_fin.momentum) * stats_fin.rvar[i] + stats_fin.momentum * unbiased;
+        }
+      }
+    }
   }
 }
 
@@ -423,10 +485,19 @@ void encfwd_split_weight_h16(const float* W, int h, int G, void* w_hi_h, void* w
 
 int encfwd_fused(const float* x, int B, int G, BnParams bn, const float* w_hi, const float* w_lo, int h,
                  const float* bias, float* V, float* a_hi, float* partials, int max_parts, cudaStream_t st,
-                 const ColStatsOut* stats, bool h16) {
+                 const ColStatsOut* stats, bool h16, bool sqrt_in) {
   CUtensorMap tX, tWh, tWl, tA;
-  const int n_tile = h >= BN ? BN : ((h + 15) / 16) * 16;
+  int n_tile = h >= BN ? BN : ((h + 15) / 16) * 16;
   const int bke = h16 ? 64 : BK;
+  const int kb_total = (G + bke - 1) / bke;
+  const int m_tiles = (B + BM - 1) / BM;
+  // Short K (the h x h trunk blocks: <= 20 k-blocks, one accumulation chain): no k-split, hence no slabs and no
+  // reduction pass - bias and the next block's BatchNorm statistics are finished in the epilogue.  Narrow N tiles
+  // spread the few cell tiles over the SMs (every CTA of a cell tile transforms the same small input tile).
+  const bool unsplit = kb_total <= 20 && h % 4 == 0;
+  if (unsplit) {
+    while (n_tile > 64 && n_tile % 32 == 0 && (long long)m_tiles * ((h + n_tile - 1) / n_tile) * 2 <= sms()) n_tile /= 2;
+  }
   if (!tmap_2d(&tX, x, B, G, G, BM, BK)) return -3;
   if (h16) {  // w_hi / w_lo / a_hi are fp16 buffers
     if (!tmap_2d_h(&tWh, w_hi, h, G, G, (uint32_t)n_tile, 64)) return -3;
@@ -437,13 +508,12 @@ int encfwd_fused(const float* x, int B, int G, BnParams bn, const float* w_hi, c
     if (!tmap_2d(&tWl, w_lo, h, G, G, (uint32_t)n_tile, BK)) return -3;
     if (!tmap_2d(&tA, a_hi, B, G, G, BM, BK)) return -3;
   }
-  const int kb_total = (G + bke - 1) / bke;
-  const long long tiles = (long long)((B + BM - 1) / BM) * ((h + n_tile - 1) / n_tile);
+  const long long tiles = (long long)m_tiles * ((h + n_tile - 1) / n_tile);
   // k-parts: minimise waves x k-blocks per chunk (chunks beyond a multiple of the SM count cost a
   // whole extra wave), with accumulation chains <= 20 k-blocks (240 MMA steps, bias ~1e-6, see
   // DESIGN.md) and at most max_parts slabs
   int splits = 1;
-  {
+  if (!unsplit) {
     long long best = -1;
     for (int sp = 1; sp <= max_parts && sp <= kb_total; ++sp) {
       const int per = (kb_total + sp - 1) / sp;
@@ -455,18 +525,20 @@ int encfwd_fused(const float* x, int B, int G, BnParams bn, const float* w_hi, c
   }
   const long long chunks = tiles * splits;
   const int grid = (int)(chunks < sms() ? chunks : sms());
-  auto kern = h16 ? k_encfwd<true> : k_encfwd<false>;
+  auto kern = h16 ? (sqrt_in ? k_encfwd<true, true> : k_encfwd<true, false>) : (sqrt_in ? k_encfwd<false, true> : k_encfwd<false, false>);
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  StatFinal nofin{};
   if (splits > 1) {
     launch_k(kern, grid, NTHREADS, SMEM_BYTES, st, tX, tWh, tWl, tA, bn, B, G, h, n_tile, splits, partials,
-                                             (long long)B * h, (const float*)nullptr);
+                                             (long long)B * h, (const float*)nullptr, (double*)nullptr, nofin);
     note_launch();
     return reduce_parts(partials, splits, B, h, bias, V, h, st, stats) ? 1 : 0;
-  } else {
-    launch_k(kern, grid, NTHREADS, SMEM_BYTES, st, tX, tWh, tWl, tA, bn, B, G, h, n_tile, 1, V, 0LL, bias);
-    note_launch();
   }
-  return 0;
+  const bool fuse_stats = stats != nullptr && B > 1;
+  launch_k(kern, grid, NTHREADS, SMEM_BYTES, st, tX, tWh, tWl, tA, bn, B, G, h, n_tile, 1, V, 0LL, bias,
+           fuse_stats ? stats->acc : (double*)nullptr, fuse_stats ? stats->fin : nofin);
+  note_launch();
+  return fuse_stats ? 1 : 0;
 }
 
 }  // namespace tc

@@ -324,7 +324,9 @@ class FusedTraceELBO:
         torch.cuda.current_stream(rt.device).synchronize()
         g = torch.cuda.CUDAGraph()
         try:
-            with torch.cuda.graph(g):
+            # thread-local capture mode: a loader's worker thread (PinnedBatchPrefetcher) may allocate, query events
+            # or synchronise its own stream while this thread captures - legal, but fatal under the default global mode
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 eager()
         except Exception as e:
             # capture unsupported here: stay on direct launches - and say so (the step is ~60 launches instead of 1)
