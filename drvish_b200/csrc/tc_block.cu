@@ -235,9 +235,13 @@ bool tc_block_backward_supported(int B, int din, int dout, const drv_hparams& hp
 // The fused-prologue fp16 kernel (tc_encfwd.cu) serves the encoder input layer (sqrt, any K) and the h x h trunk blocks
 // (no sqrt; K <= 1280 so that the whole K is one accumulation chain and bias + output statistics finish in its epilogue).
 static bool fused_prologue_h16(const TcBlockArgs& a) {
-  static const bool trunk_off = getenv("DRV_TRUNK_UNFUSED") != nullptr;  // debug / A-B: trunk blocks on the 3xTF32 GEMM
+  // Trunk blocks: opt-in (DRV_TRUNK_FUSED=1).  Measured at cfg 3: forward sections -15 us (no slabs, no reduction
+  // pass), backward sections +15 us (the fp16 weight-gradient GEMM needs the abs-max / rescale passes over dV) - no net
+  // gain - and the dynamically scaled fp16 dV costs precision where dV spans many decades (decoder trunk gradients
+  // 2.5e-3 at log_r - 8).  The default keeps the 3xTF32 forward / tf32 backward GEMMs for the trunk.
+  static const bool trunk_on = getenv("DRV_TRUNK_FUSED") != nullptr;
   if (a.no_fused_prologue || !tc::encfwd_h16_supported(a.din, a.dout)) return false;
-  return a.sqrt_in || (!trunk_off && a.din <= 20 * 64);
+  return a.sqrt_in || (trunk_on && a.din <= 20 * 64);
 }
 
 bool tc_block_prepare(const TcBlockArgs& a, cudaStream_t st) {
