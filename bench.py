@@ -309,6 +309,33 @@ class Workload:
         mine = ev0.elapsed_time(ev1) / steps
         return self.max_over_ranks(mine), self.per_rank(mine)
 
+    def step_jitter(self, steps=40):
+        """Per-step durations of the step WITHOUT its collective on every rank (one event pair per step, a device sync
+        between steps): mean, standard deviation and the mean over steps of (slowest rank - mean rank) - the wait a
+        blocking collective adds on top of its own duration."""
+        import torch.distributed as dist
+
+        fn = lambda i: self.device_step(i, reduce=False)
+        for i in range(3):
+            fn(i)
+        self.barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for i, (a, b) in enumerate(evs):
+            a.record()
+            fn(3 + i)
+            b.record()
+        torch.cuda.synchronize()
+        mine = torch.tensor([a.elapsed_time(b) for a, b in evs], device=self.device, dtype=torch.float64)
+        allr = torch.empty(self.world * steps, device=self.device, dtype=torch.float64)
+        if self.world > 1:
+            dist.all_gather_into_tensor(allr, mine)
+        else:
+            allr.copy_(mine)
+        m = allr.view(self.world, steps)
+        return {"mean_ms": float(m.mean()), "std_ms_per_rank": [round(float(v), 4) for v in m.std(dim=1).tolist()],
+                "mean_slowest_minus_mean_ms": float((m.max(dim=0).values - m.mean(dim=0)).mean()),
+                "note": "back-to-back graph replays, one event pair per step"}
+
     def timed(self, steps, warmup, fn=None, sample_clocks=False):
         """W untimed + K timed steps between barriers, CUDA events on the launching stream, max over ranks (ms/step)."""
         fn = fn or self.device_step
@@ -528,7 +555,8 @@ def run_native(args, cfg):
         dp_check = w.dp_check()
         ms_local, per_rank = w.timed_local(args.steps, 3)
         all_reduce = {"collective": w.collective(), "alone_ms": w.allreduce_alone_ms(), "exposed_ms": ms_per_step - ms_local,
-                      "ms_per_step_without": ms_local, "per_rank_ms_without": per_rank, "bytes": 4 * (rt.n_param_floats + 1)}
+                      "ms_per_step_without": ms_local, "per_rank_ms_without": per_rank, "bytes": 4 * (rt.n_param_floats + 1),
+                      "step_jitter": w.step_jitter()}
         if dp_check["max_rel_err"] > dp_check["tolerance"]:
             raise SystemExit(f"bench.py: data-parallel gradient check failed: {dp_check}")
 

@@ -123,7 +123,9 @@ def default_pack_threads() -> int:
         n = len(os.sched_getaffinity(0))
     except AttributeError:
         n = os.cpu_count() or 1
-    return max(1, min(32, n - 2))
+    # one process per GPU under torchrun: the ranks of a node share its cores
+    local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    return max(1, min(32, n // local_world - (2 if local_world == 1 else 1)))
 
 
 def pack_batches(batches: Iterable[Sequence], kind: str = "u16") -> List[list]:
