@@ -15,6 +15,7 @@ DRV_FLAG_NO_BN_UPDATE = 2
 DRV_FLAG_STOP_AFTER_DECODER = 128
 DRV_FLAG_ENCODER_BACKWARD_ONLY = 256
 DRV_FLAG_LOSS_IN_GRADS = 2048
+DRV_FLAG_FUSED_ALLREDUCE = 4096
 DRV_STATUS_NAN_LOSS = 1
 DRV_STATUS_MISSING_CLASS = 2
 DRV_STATUS_BAD_LABEL = 4
@@ -90,6 +91,8 @@ SYMBOLS = {
     "drv_comm_close": (C.c_int, [_P]),
     "drv_comm_free": (C.c_int, [_P]),
     "drv_peer_allreduce": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int64, _P]),
+    "drv_comm_bind": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int64]),
+    "drv_shape_padded": (C.c_int, [C.POINTER(Dims)]),
     "drv_aggmo_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "drv_draw_step_noise": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P, C.c_uint64, _P, _P, _P, _P, _P, _P]),
 }

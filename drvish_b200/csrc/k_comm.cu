@@ -47,8 +47,10 @@ __device__ __forceinline__ void st_sys_v4(float4* p, const float4& v) {
   asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// [off4, off4 + n4): the float4 range of the buffer this launch reduces (the whole buffer, or one of the two slices of
+// a step that overlaps the decoder slice with the encoder backward)
 template <int WORLD>
-__global__ void __launch_bounds__(512) k_peer_allreduce(Peers p, int rank, long long n4) {
+__global__ void __launch_bounds__(512) k_peer_allreduce(Peers p, int rank, long long off4, long long n4) {
   CommHeader* me = reinterpret_cast<CommHeader*>(p.base[rank]);
   const unsigned e = ld_acquire_sys(&me->epoch);  // read by every CTA before the last one advances it
   const unsigned b1 = 2 * e + 1, b2 = 2 * e + 2;
@@ -65,7 +67,7 @@ __global__ void __launch_bounds__(512) k_peer_allreduce(Peers p, int rank, long 
   __syncthreads();
   // my chunk of the buffer, in float4 units
   const long long per = (n4 + WORLD - 1) / WORLD;
-  const long long c0 = min((long long)rank * per, n4), c1 = min(c0 + per, n4);
+  const long long c0 = off4 + min((long long)rank * per, n4), c1 = min(c0 + per, off4 + n4);
   float4* data[WORLD];
 #pragma unroll
   for (int j = 0; j < WORLD; ++j) data[j] = reinterpret_cast<float4*>(reinterpret_cast<char*>(p.base[j]) + COMM_HEADER_BYTES);
@@ -141,6 +143,66 @@ extern "C" int drv_comm_open(const void* h_handle64, void** base_out) {
 extern "C" int drv_comm_close(void* base) { return base ? (int)cudaIpcCloseMemHandle(base) : 0; }
 extern "C" int drv_comm_free(void* base) { return base ? (int)cudaFree(base) : 0; }
 
+namespace drv {
+
+// launch of one (slice of an) all-reduce; max_ctas > 0 caps the grid (a collective that runs NEXT TO compute kernels)
+int peer_allreduce_launch(const Peers& p, int rank, int world, long long off4, long long n4, int max_ctas, cudaStream_t st) {
+  const long long per = (n4 + world - 1) / world;
+  int grid = (int)((per + 511) / 512);
+  if (grid > 148) grid = 148;  // one wave: every CTA must be able to poll the flags
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  if (grid < 1) grid = 1;
+  switch (world) {
+    case 2: launch_k_plain(k_peer_allreduce<2>, grid, 512, 0, st, p, rank, off4, n4); break;
+    case 4: launch_k_plain(k_peer_allreduce<4>, grid, 512, 0, st, p, rank, off4, n4); break;
+    case 8: launch_k_plain(k_peer_allreduce<8>, grid, 512, 0, st, p, rank, off4, n4); break;
+    default: return DRV_EINVAL;
+  }
+  note_launch();
+  return 0;
+}
+
+// Binding of the calling thread's step calls to a peer-mapped gradient buffer (drv_comm_bind): with
+// DRV_FLAG_FUSED_ALLREDUCE the step launches the collective itself.
+struct CommBinding {
+  bool on = false;
+  Peers p{};
+  int rank = 0, world = 0;
+  long long n_floats = 0;
+};
+static thread_local CommBinding g_comm;
+
+bool comm_bound(const float* grads, long long n_floats_needed) {
+  return g_comm.on && grads == reinterpret_cast<const float*>(reinterpret_cast<const char*>(g_comm.p.base[g_comm.rank]) + COMM_HEADER_BYTES) &&
+         g_comm.n_floats >= n_floats_needed;
+}
+
+int comm_allreduce_slice(long long off_floats, long long n_floats, int max_ctas, cudaStream_t st) {
+  if (!g_comm.on || (off_floats & 3)) return DRV_EINVAL;
+  return peer_allreduce_launch(g_comm.p, g_comm.rank, g_comm.world, off_floats / 4, (n_floats + 3) / 4, max_ctas, st);
+}
+
+}  // namespace drv
+
+extern "C" int drv_comm_bind(void* const* h_bases, int rank, int world, int64_t n_floats) {
+  using namespace drv;
+  if (!h_bases) {
+    g_comm.on = false;
+    return 0;
+  }
+  if (world < 2 || world > COMM_MAX_RANKS || rank < 0 || rank >= world || n_floats < 1) return DRV_EINVAL;
+  if (world != 2 && world != 4 && world != 8) return DRV_EINVAL;
+  for (int j = 0; j < world; ++j) {
+    if (!h_bases[j]) return DRV_EINVAL;
+    g_comm.p.base[j] = h_bases[j];
+  }
+  g_comm.rank = rank;
+  g_comm.world = world;
+  g_comm.n_floats = n_floats;
+  g_comm.on = true;
+  return 0;
+}
+
 extern "C" int drv_peer_allreduce(void* const* h_bases, int rank, int world, int64_t n_floats, void* stream) {
   using namespace drv;
   g_launches = 0;
@@ -151,19 +213,8 @@ extern "C" int drv_peer_allreduce(void* const* h_bases, int rank, int world, int
     if (!h_bases[j]) return DRV_EINVAL;
     p.base[j] = h_bases[j];
   }
-  const long long n4 = (n_floats + 3) / 4;
-  const long long per = (n4 + world - 1) / world;
-  int grid = (int)((per + 511) / 512);
-  if (grid > 148) grid = 148;  // one wave: every CTA must be able to poll the flags
-  if (grid < 1) grid = 1;
-  cudaStream_t st = (cudaStream_t)stream;
-  switch (world) {
-    case 2: launch_k_plain(k_peer_allreduce<2>, grid, 512, 0, st, p, rank, n4); break;
-    case 4: launch_k_plain(k_peer_allreduce<4>, grid, 512, 0, st, p, rank, n4); break;
-    case 8: launch_k_plain(k_peer_allreduce<8>, grid, 512, 0, st, p, rank, n4); break;
-    default: return DRV_EINVAL;  // the caller falls back to NCCL
-  }
-  note_launch();
+  const int rc = peer_allreduce_launch(p, rank, world, 0, (n_floats + 3) / 4, 0, (cudaStream_t)stream);
+  if (rc != 0) return rc;  // the caller falls back to NCCL
   cudaError_t e = g_err;
   g_err = cudaSuccess;
   return (int)e;

@@ -416,7 +416,9 @@ using namespace drv;
 
 extern "C" {
 
-const char* drv_version(void) { return "drvish_b200 0.1.0 sm_100a"; }
+const char* drv_version(void) { return "drvish_b200 0.2.0 sm_100a"; }
+
+int drv_shape_padded(const drv_dims* dims) { return valid(dims) && pad_wanted(*dims) ? 1 : 0; }
 
 int drv_last_launch_count(void) { return g_launches; }
 
@@ -505,6 +507,12 @@ static int elbo_step_core(const drv_dims* dims, const drv_hparams* hp, const flo
   // parts, so that it overlaps the encoder backward.
   const bool part2_only = bwd && (hp->flags & DRV_FLAG_ENCODER_BACKWARD_ONLY);
   const bool stop_after_decoder = bwd && (hp->flags & DRV_FLAG_STOP_AFTER_DECODER);
+  // Data parallel with the collective inside the step: the decoder / dose-response slice of the flat gradient buffer
+  // (and the loss / status tail slots) is final before the encoder backward starts - it is all-reduced on the side
+  // stream by a few CTAs next to the encoder backward; the encoder slice follows at the end of the step.
+  const bool fused_ar = bwd && (hp->flags & DRV_FLAG_FUSED_ALLREDUCE);
+  if (fused_ar && (part2_only || stop_after_decoder || !side || !comm_bound(grads, n.n_param_floats + DRV_GRAD_TAIL_FLOATS)))
+    return DRV_EINVAL;
   if (part2_only) {
     for (int k = NB - 1, prep = 0; k >= 0; --k)
       prep = block_backward(c, 0, k, x, k == NB - 1 ? c.at<float>(p.dO) : c.at<float>(p.Gb[0][k + 1]), false, prep);
@@ -673,10 +681,28 @@ static int elbo_step_core(const drv_dims* dims, const drv_hparams* hp, const flo
                     grads + n.n_param_floats, path);  // loss -> tail slot of the gradient buffer (one collective carries both)
       return finish();
     }
+    if (fused_ar) {
+      // loss, status and BatchNorm counters are final here (nothing behind this point feeds them): write the tail
+      // slots now, then reduce [first decoder tensor, tail] on the side stream - behind the weight-gradient GEMMs
+      // already queued there, next to the encoder backward on this one
+      finalize_step(out, status, (bn_batches && !(hp->flags & DRV_FLAG_NO_BN_UPDATE)) ? bn_batches : nullptr, n.n_bn,
+                    use_tc ? c.at<float>(p.ll) : nullptr, B, hp->scale_factor, st, grads + n.n_param_floats, path);
+      side->fork(st);
+      static const int early_ctas = getenv("DRV_AR_EARLY_CTAS") ? atoi(getenv("DRV_AR_EARLY_CTAS")) : 24;
+      const int rc = comm_allreduce_slice(n.dec[0].gamma, n.n_param_floats + DRV_GRAD_TAIL_FLOATS - n.dec[0].gamma, early_ctas, side->side);
+      if (rc != 0) return rc;
+    }
     // ---- encoder backward ----------------------------------------------------------------------
     for (int k = NB - 1, eprep = 0; k >= 0; --k)
       eprep = block_backward(c, 0, k, x, k == NB - 1 ? c.at<float>(p.dO) : c.at<float>(p.Gb[0][k + 1]), false, eprep);
     prof::mark(7, st);
+  }
+  if (fused_ar) {
+    side->join(st);
+    const int rc = comm_allreduce_slice(0, n.dec[0].gamma, 0, st);
+    if (rc != 0) return rc;
+    if (prof::enabled && prof::n_steps < prof::MAX_STEPS) ++prof::n_steps;
+    return finish();
   }
   if (side) side->join(st);
   // BatchNorm batch counters + status word folded into the result record: one launch
@@ -704,6 +730,7 @@ static int elbo_step_impl(const drv_dims* dims, const drv_hparams* hp, const flo
     return elbo_step_core(dims, hp, x, x_lik, log_split, log_split_c, labels, y, eps_z, eps_l, w_prior, b_prior, eps_bias,
                           dose_offsets, params, grads, bn_running, bn_batches, out, workspace, workspace_bytes, stream);
   if (!x || !x_lik || !params) return DRV_EINVAL;
+  if (hp->flags & DRV_FLAG_FUSED_ALLREDUCE) return DRV_EINVAL;  // the padded gradient buffer is internal: reduce after the step
   const drv_dims dp = padded_dims(*dims);
   const size_t plan_total = make_plan(dp, make_net(dp)).total;
   const PadPlan P = make_pad_plan(*dims, plan_total);

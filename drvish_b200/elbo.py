@@ -62,6 +62,9 @@ class FusedTraceELBO:
         # data parallel: True = two-part step, the all-reduce of the decoder slice overlaps the encoder backward;
         # False = one graph + one all-reduce after it (see DESIGN.md section 5 for the measurements)
         self.dp_overlap = os.environ.get("DRV_DP_OVERLAP", "0") == "1"
+        # the collective inside the step, decoder slice overlapped with the encoder backward (DRV_DP_FUSED=0: one
+        # all-reduce kernel behind the step)
+        self.dp_fused = os.environ.get("DRV_DP_FUSED", "1") == "1"
         self._graphs = {}
         self._graph_seen = {}
         self._staging = {}  # (shape, mode) -> fixed staging tile for loaders that never repeat a buffer address
@@ -133,6 +136,11 @@ class FusedTraceELBO:
         epoch counter, so a replay is as good as a launch): no Python and no launch gap between the last gradient
         kernel and the collective.  With NCCL it is issued after the graph."""
         peer = self._peer.get(id(rt))
+        if reduce and peer is not None and self.dp_fused and not rt.shape_padded(x.shape[0]):
+            # the step launches the collective itself: the decoder slice is reduced on the library's side stream next
+            # to the encoder backward, the encoder slice at the end (DRV_FLAG_FUSED_ALLREDUCE)
+            self._enqueue(rt, x, labels, y, True, part=5, mcv=mcv)
+            return
         in_graph = reduce and peer is not None and self.use_cuda_graph and self._explicit_noise is None
         self._enqueue(rt, x, labels, y, True, part=4 if in_graph else 3, mcv=mcv)
         if reduce and not in_graph:
@@ -145,6 +153,7 @@ class FusedTraceELBO:
         peer = PeerAllReduce.create(rt.flat_grads.numel(), rt.device, self.process_group)
         if peer is not None:
             rt.rebase_grads(peer.data)
+            peer.bind()  # drv_comm_bind: this thread's steps may launch the collective themselves
             self._graphs.clear()
             self._graph_seen.clear()
             self._staging.clear()
@@ -268,7 +277,8 @@ class FusedTraceELBO:
         kernel variant), so a training loop that cycles through a few staging buffers - e.g.
         PinnedBatchPrefetcher's two - replays ~70 kernel launches with one cudaGraphLaunch."""
         pflags = {0: 0, 1: _lib.DRV_FLAG_STOP_AFTER_DECODER, 2: _lib.DRV_FLAG_ENCODER_BACKWARD_ONLY,
-                  3: _lib.DRV_FLAG_LOSS_IN_GRADS, 4: _lib.DRV_FLAG_LOSS_IN_GRADS}[part]
+                  3: _lib.DRV_FLAG_LOSS_IN_GRADS, 4: _lib.DRV_FLAG_LOSS_IN_GRADS,
+                  5: _lib.DRV_FLAG_LOSS_IN_GRADS | _lib.DRV_FLAG_FUSED_ALLREDUCE}[part]
 
         def eager():
             # part 2 continues the step of part 1: same noise buffers, no new draws

@@ -120,6 +120,10 @@ class PeerAllReduce:
             warnings.warn(f"drvish_b200: peer-memory all-reduce unavailable ({e}); using NCCL")
             return None
 
+    def bind(self) -> None:
+        """Let the calling thread's ``drv_elbo_step`` calls launch the collective themselves (DRV_FLAG_FUSED_ALLREDUCE)."""
+        _lib.check(self.lib.drv_comm_bind(self._bases, self.rank, self.world, self.n_floats), "drv_comm_bind")
+
     def all_reduce(self) -> None:
         st = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self.lib.drv_peer_allreduce(self._bases, self.rank, self.world, self.n_floats, C.c_void_p(st)),

@@ -215,6 +215,10 @@ class ModelRuntime:
             self._workspaces[n_cells] = ws
         return ws
 
+    def shape_padded(self, n_cells: int) -> bool:
+        """Does drv_elbo_step run this shape as a padded (aligned) problem (k_pad.cu)?"""
+        return bool(self.lib.drv_shape_padded(C.byref(self.dims(n_cells))))
+
     def rebase_grads(self, new_flat: torch.Tensor) -> None:
         """Move the flat gradient buffer (and every ``param.grad`` view) onto ``new_flat`` - e.g. the peer-mapped
         buffer of ``parallel.PeerAllReduce``.  Same layout; graphs captured earlier must be dropped by the caller."""

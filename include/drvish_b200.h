@@ -83,6 +83,12 @@ typedef struct drv_hparams {
  * DRV_GRAD_TAIL_FLOATS extra floats): [0] loss, [1] 1.0 if DRV_STATUS_NAN_LOSS else 0, [2] MISSING_CLASS, [3] BAD_LABEL.
  * After a SUM all-reduce every rank holds the summed loss and the number of ranks that raised each status bit. */
 #define DRV_GRAD_TAIL_FLOATS 4
+#define DRV_FLAG_FUSED_ALLREDUCE 4096        /* the step performs the data-parallel gradient all-reduce itself (implies
+                                               LOSS_IN_GRADS): `grads` must be the data pointer of the peer-mapped buffer
+                                               bound with drv_comm_bind.  The decoder / dose-response slice (final before
+                                               the encoder backward starts) is reduced on an internal side stream by a
+                                               few CTAs NEXT TO the encoder backward; the encoder slice follows at the end
+                                               of the step.  DRV_EINVAL when nothing is bound or the shape is padded */
 #define DRV_FLAG_ENCODER_BACKWARD_ONLY 256  /* part 2 of 2: encoder backward of the step started by part 1
                                                (same arguments, same workspace) */
 
@@ -255,6 +261,11 @@ int drv_comm_open(const void* h_handle64, void** base_out);
 int drv_comm_close(void* base);
 int drv_comm_free(void* base);
 int drv_peer_allreduce(void* const* h_bases, int rank, int world, int64_t n_floats, void* stream);
+/* Binds the calling thread's drv_elbo_step calls to a peer-mapped gradient buffer (same arguments as
+ * drv_peer_allreduce) for DRV_FLAG_FUSED_ALLREDUCE; h_bases == NULL unbinds. */
+int drv_comm_bind(void* const* h_bases, int rank, int world, int64_t n_floats);
+/* 1 when drv_elbo_step runs this shape as a padded (aligned) problem - see k_pad.cu -, else 0 */
+int drv_shape_padded(const drv_dims* dims);
 
 /* Section timing with CUDA events recorded on the step's stream (bench.py's live roofline
  * measurement).  drv_profile_enable(1) arms it (up to 64 steps are kept); drv_profile_read
