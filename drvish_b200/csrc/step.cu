@@ -704,11 +704,14 @@ static int elbo_step_core(const drv_dims* dims, const drv_hparams* hp, const flo
     if (prof::enabled && prof::n_steps < prof::MAX_STEPS) ++prof::n_steps;
     return finish();
   }
-  if (side) side->join(st);
-  // BatchNorm batch counters + status word folded into the result record: one launch
+  // BatchNorm batch counters + status word folded into the result record: one launch.  In a training step everything
+  // that feeds the loss and the status was joined before the sampling backward (wait_aux), so the record is finished
+  // NEXT TO the weight-gradient GEMMs still running on the side stream instead of behind them.
+  if (side && !bwd) side->join(st);
   finalize_step(out, status, (bn_batches && !(hp->flags & DRV_FLAG_NO_BN_UPDATE)) ? bn_batches : nullptr, n.n_bn,
                 use_tc ? c.at<float>(p.ll) : nullptr, B, hp->scale_factor, st,
                 (bwd && (hp->flags & DRV_FLAG_LOSS_IN_GRADS)) ? grads + n.n_param_floats : nullptr, path);
+  if (side && bwd) side->join(st);
   if (prof::enabled && prof::n_steps < prof::MAX_STEPS) {
     if (!bwd) for (int i = 5; i <= DRV_N_SECTIONS; ++i) prof::mark(i, st);
     ++prof::n_steps;
