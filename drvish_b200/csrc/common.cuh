@@ -76,6 +76,24 @@ struct SideStream {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_aux = nullptr;
   bool used = false;
+  // third stream for a collective that runs next to the step (data parallel, DRV_FLAG_FUSED_ALLREDUCE): it waits for
+  // BOTH streams (comm_fork) and is joined to `main` before anything that must follow it (comm_join)
+  cudaStream_t comm = nullptr;
+  cudaEvent_t ev_cm = nullptr, ev_cs = nullptr, ev_cdone = nullptr;
+  bool comm_used = false;
+  void comm_fork(cudaStream_t main) {
+    cudaEventRecord(ev_cm, main);
+    cudaEventRecord(ev_cs, side);
+    cudaStreamWaitEvent(comm, ev_cm, 0);
+    cudaStreamWaitEvent(comm, ev_cs, 0);
+    comm_used = true;
+  }
+  void comm_join(cudaStream_t main) {
+    if (!comm_used) return;
+    cudaEventRecord(ev_cdone, comm);
+    cudaStreamWaitEvent(main, ev_cdone, 0);
+    comm_used = false;
+  }
   // work enqueued on `side` after this call sees everything enqueued on `main` so far
   void fork(cudaStream_t main) {
     cudaEventRecord(ev_fork, main);

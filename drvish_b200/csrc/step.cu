@@ -49,7 +49,11 @@ SideStream* side_stream() {
     if (cudaStreamCreateWithFlags(&ss.side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ss.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ss.ev_join, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ss.ev_aux, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&ss.ev_aux, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ss.comm, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ss.ev_cm, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ss.ev_cs, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ss.ev_cdone, cudaEventDisableTiming) != cudaSuccess) {
       ss.side = nullptr;
       cudaGetLastError();
     }
@@ -667,6 +671,18 @@ static int elbo_step_core(const drv_dims* dims, const drv_hparams* hp, const flo
                              c.bn(1, NB - 1), c.at<float>(p.Gb[1][NB - 1]), st);
     }
     prof::mark(5, st);
+    if (fused_ar) {
+      // The bulk of the gradient bytes - the last decoder Linear (2G x h), the dose-response head - and the loss / status
+      // tail slots are final once the weight-gradient GEMM just queued on the side stream has run: write the tail slots,
+      // then all-reduce [last decoder weight, tail] on the comm stream.  It runs next to the decoder-trunk backward, whose
+      // kernels are small grids, and is over before the full-machine kernels of the encoder backward start.
+      finalize_step(out, status, (bn_batches && !(hp->flags & DRV_FLAG_NO_BN_UPDATE)) ? bn_batches : nullptr, n.n_bn,
+                    use_tc ? c.at<float>(p.ll) : nullptr, B, hp->scale_factor, st, grads + n.n_param_floats, path);
+      side->comm_fork(st);
+      static const int early_ctas = getenv("DRV_AR_EARLY_CTAS") ? atoi(getenv("DRV_AR_EARLY_CTAS")) : 64;
+      const int rc = comm_allreduce_slice(last.W, n.n_param_floats + DRV_GRAD_TAIL_FLOATS - last.W, early_ctas, side->comm);
+      if (rc != 0) return rc;
+    }
     // ---- decoder trunk backward, sampling backward ---------------------------------------------
     bool prep = block_backward(c, 1, NB - 1, z, nullptr, true);
     for (int k = NB - 2; k >= 0; --k) prep = block_backward(c, 1, k, z, c.at<float>(p.Gb[1][k + 1]), false, prep);
@@ -681,17 +697,6 @@ static int elbo_step_core(const drv_dims* dims, const drv_hparams* hp, const flo
                     grads + n.n_param_floats, path);  // loss -> tail slot of the gradient buffer (one collective carries both)
       return finish();
     }
-    if (fused_ar) {
-      // loss, status and BatchNorm counters are final here (nothing behind this point feeds them): write the tail
-      // slots now, then reduce [first decoder tensor, tail] on the side stream - behind the weight-gradient GEMMs
-      // already queued there, next to the encoder backward on this one
-      finalize_step(out, status, (bn_batches && !(hp->flags & DRV_FLAG_NO_BN_UPDATE)) ? bn_batches : nullptr, n.n_bn,
-                    use_tc ? c.at<float>(p.ll) : nullptr, B, hp->scale_factor, st, grads + n.n_param_floats, path);
-      side->fork(st);
-      static const int early_ctas = getenv("DRV_AR_EARLY_CTAS") ? atoi(getenv("DRV_AR_EARLY_CTAS")) : 24;
-      const int rc = comm_allreduce_slice(n.dec[0].gamma, n.n_param_floats + DRV_GRAD_TAIL_FLOATS - n.dec[0].gamma, early_ctas, side->side);
-      if (rc != 0) return rc;
-    }
     // ---- encoder backward ----------------------------------------------------------------------
     for (int k = NB - 1, eprep = 0; k >= 0; --k)
       eprep = block_backward(c, 0, k, x, k == NB - 1 ? c.at<float>(p.dO) : c.at<float>(p.Gb[0][k + 1]), false, eprep);
@@ -699,7 +704,8 @@ static int elbo_step_core(const drv_dims* dims, const drv_hparams* hp, const flo
   }
   if (fused_ar) {
     side->join(st);
-    const int rc = comm_allreduce_slice(0, n.dec[0].gamma, 0, st);
+    side->comm_join(st);  // the two collectives share the flag words: strictly one after the other on every rank
+    const int rc = comm_allreduce_slice(0, last.W, 0, st);
     if (rc != 0) return rc;
     if (prof::enabled && prof::n_steps < prof::MAX_STEPS) ++prof::n_steps;
     return finish();

@@ -405,6 +405,55 @@ def test_cuda_graph_replay_matches_direct_launches():
     assert P.rel_err(runs[True][1], runs[False][1]) <= 1e-5
 
 
+def test_device_constructor_argument_captures_a_graph():
+    """The reference's construction path `DRNBVAE(..., device="cuda")` (drnbvae.py:35-52) makes epsilon / l_loc / l_scale /
+    sigma_scale CUDA tensors: reading them must not synchronise every step nor break CUDA-graph capture."""
+    import warnings
+
+    import drvish_b200 as D
+
+    cfg = dict(n_input=256, n_latent=6, layers=[64, 64], batch=256, drugs=2, doses=4, classes=4)
+    case = P.make_case(cfg)
+    model = D.DRNBVAE(n_input=256, n_classes=4, n_drugs=2, n_conditions=[4, 4], n_latent=6, layers=[64, 64], device="cuda")
+    model.load_state_dict(case["model"].state_dict())
+    assert model.epsilon.is_cuda and model.l_loc.is_cuda
+    args = [case["x"].cuda(), case["labels"].cuda(), [t.cuda() for t in case["y"]]]
+    elbo = D.FusedTraceELBO(seed=3, data_parallel=False)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")  # a failed capture warns
+        losses = [elbo.loss_and_grads(model.model, model.guide, *args) for _ in range(4)]
+    assert elbo.use_cuda_graph and len(elbo._graphs) == 1
+    assert all(np.isfinite(l) for l in losses)
+    rt = model._runtime()
+    assert len(rt._hp_cache) == 1  # one cached drv_hparams, the four device scalars read once
+
+
+def test_fresh_tensor_loader_is_served_through_a_staging_tile():
+    """A stock DataLoader hands over a NEW tensor every step: no buffer address ever repeats, so no graph would be captured.
+    After a run of first sightings the batches are copied into a fixed staging tile whose graph is replayed; losses equal
+    the direct-launch run with the same seed."""
+    import drvish_b200 as D
+
+    cfg = dict(n_input=256, n_latent=6, layers=[64, 64], batch=256, drugs=2, doses=4, classes=4)
+    case = P.make_case(cfg)
+    runs = {}
+    for graph in (False, True):
+        model = P.build_cuda_model(case, "cuda:0")
+        elbo = D.FusedTraceELBO(seed=11, data_parallel=False, use_cuda_graph=graph)
+        elbo.STAGING_AFTER_MISSES = 3
+        keep, losses = [], []
+        y = [t.cuda() for t in case["y"]]
+        for i in range(10):
+            x = case["x"].cuda() + 0.0  # fresh tensors, kept alive so that the allocator cannot recycle the addresses
+            labels = case["labels"].cuda().clone()
+            keep += [x, labels]
+            losses.append(elbo.loss_and_grads(model.model, model.guide, x, labels, y))
+        runs[graph] = (losses, len(elbo._graphs), any(st["active"] for st in elbo._staging.values()))
+    assert runs[True][1] == 1 and runs[True][2] and runs[False][1] == 0
+    for a, b in zip(runs[False][0], runs[True][0]):
+        assert abs(a - b) <= 1e-6 * abs(a)
+
+
 def test_two_part_step_equals_single_call():
     """DRV_FLAG_STOP_AFTER_DECODER + DRV_FLAG_ENCODER_BACKWARD_ONLY (used to overlap the data-parallel
     all-reduce with the encoder backward) give the same loss and gradients as one call."""
