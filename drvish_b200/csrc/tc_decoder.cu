@@ -57,9 +57,13 @@ constexpr int TMEM_COLS = 256;
 // as the tf32 operands they replace, half the bytes through HBM / L2 / shared memory, 64-element
 // k-blocks (half the pipeline hand-shakes) and twice the MMA rate.  d logits is stored divided by the
 // plate scale c and multiplied by DL_SCALE, so that its magnitude is that of the per-element count
-// residual whatever scale_factor is (fp16 range: |x - mu| up to 1e6 representable, values below 1e-3
-// keep 9.5e-7 absolute resolution); the backward GEMMs multiply by c / DL_SCALE (exact powers of two).
-constexpr float DL_SCALE = 0.0625f;
+// residual whatever scale_factor is; the backward GEMMs multiply by c / DL_SCALE (exact powers of two).
+// fp16 range with DL_SCALE = 4: residuals up to 1.6e4 are representable (larger ones saturate: cvt.satfinite),
+// residuals down to 1.5e-5 keep the full 11-bit significand (below: 1.5e-8 absolute resolution).  The lower end
+// matters: with a small dispersion parameter (r = e^rho ~ 3e-4, log_r ~ -8) EVERY entry is of size r, and the former
+// scale of 1/16 put all of them into fp16's subnormal range (measured: decoder-trunk gradients off by 2.7e-3,
+// tests/test_cuda_parity.py::test_dispersion_sweep[mid--8.0-False]).
+constexpr float DL_SCALE = 4.0f;
 
 // tcgen05 kind::tf32 TRUNCATES the low 13 mantissa bits of its fp32 operands, which biases every
 // product by ~2^-11; rounding the operands to nearest when they are produced keeps the error
@@ -81,6 +85,7 @@ struct DecParams {
   float* part_s;
   // phase 2/3: lse[b] is combined from the phase-1 partials when a CTA enters a cell tile
   int lse_n_gt, lse_n_tiles, lse_grid;  // phase 1's gene tiles per cell tile, tile count and grid
+  float* lse;         // [B] logsumexp per cell, written by phase 2 for the fused phase 3 (k_dec3w)
   float* ll;          // [B] (atomic accumulation, zeroed)
   float* asum;        // [B]
   float* dlogits;     // [B][2G]
@@ -379,6 +384,8 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
         if (PHASE != 1 && row_ok) {
           lib_b = p.lib[b];
           lse_b = combine_lse(p, ct, b);
+          // every CTA that enters this cell tile computes the same bits: the duplicate stores are benign
+          if (PHASE == 2 && WITH_A && cg == 0) p.lse[b] = lse_b;
           if (PHASE == 2) rs_b = p.rshift ? p.rshift[b] * 1.4426950408889634f : 0.f;
           if (PHASE == 3) asum_b = p.asum[b];
         }
@@ -712,6 +719,293 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fused phase 3 + weight gradient (north star item 3: "the fused backward emits dlogits directly into the
+// decoder weight-gradient GEMM").  The kernel that makes d loss / d logits(scale half) final -
+//     ds = ds' + DL_SCALE A[b] softmax(s)           (ds = a - p A)
+// - also consumes the finished fp16 tile, still in shared memory, as an operand of the weight-gradient MMA
+//     dW_s[g][i] = sum_b ds[b][g] act[b][i]
+// so the separate dW GEMM of the scale half and its 41 MB re-read of d logits disappear.
+//
+// Walk: GENE-major.  A CTA owns a contiguous range of (128-gene slab, 64-cell tile) tiles; the weight slab stays in
+// shared memory and the dW accumulator (128 genes x h, fp32) stays in TMEM across the cell tiles of a slab, so dW is
+// flushed (red.global.add) once per slab segment - twice per CTA - instead of once per tile.
+// Per tile (64 cells x 128 genes):
+//   MMA1  logits^T[128 genes][64 cells] = W_slab (A, K-major) act^T (B, K-major)                  -> TMEM D1 (2 stages)
+//   epilogue warps: TMEM lane = gene, 16 cells per warp; ds' from the TMA-staged fp16 tile [cells][genes],
+//                   ds written back in place (fp16), bias gradient summed in a register per gene
+//   MMA2  dW[128 genes][h] += ds^T (A, MN-major: the staged tile as it lies) act (B, MN-major: the SAME act boxes
+//                   MMA1 read as its K-major B operand)                                           -> TMEM D2
+//   TMA store of the finished ds tile (the dAct GEMM reads it; that product accumulates over genes and cannot stay here)
+// Shared memory: W slab 64 KB + 3 x (act tile 32 KB + ds tile 16 KB) = 208 KB; TMEM: 2 x 64 + 256 columns.
+// Needs h <= 256 (accumulator columns; h = 512 keeps phase 3 + the dW GEMM).
+constexpr int W3_SLAB = 128;                 // genes per slab
+constexpr int W3_BM = 64;                    // cells per tile
+constexpr int W3_NST = 3;                    // act / ds tile stages
+constexpr int W3_WBYTES = 4 * W3_SLAB * 128; // weight slab: up to 4 k-blocks of [128 genes][64 h] fp16
+constexpr int W3_ABYTES = 4 * W3_BM * 128;   // act tile: up to 4 boxes of [64 cells][64 h] fp16
+constexpr int W3_DBYTES = 2 * W3_BM * 128;   // ds tile: 2 boxes of [64 cells][64 genes] fp16
+constexpr int W3_SMEM = W3_WBYTES + W3_NST * (W3_ABYTES + W3_DBYTES) + 1024 + 512;
+static_assert(W3_SMEM <= 227 * 1024, "shared memory");
+constexpr int W3_D2_COL = 128;               // TMEM column of the dW accumulator (D1 stages at 0 and 64)
+
+__device__ __forceinline__ float lds_h(uint32_t a) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+  return __half2float(__ushort_as_half(v));
+}
+__device__ __forceinline__ void sts_h_sat(uint32_t a, float f) {
+  unsigned short v;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(v) : "f"(f));
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_dec3w(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtensorMap tmW,
+        const __grid_constant__ CUtensorMap tmD, DecParams p, float* __restrict__ dW) {
+  pdl_prologue();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* wbuf = smem;
+  uint8_t* abuf = wbuf + W3_WBYTES;            // [W3_NST][W3_ABYTES]
+  uint8_t* dbuf = abuf + W3_NST * W3_ABYTES;   // [W3_NST][W3_DBYTES]
+  uint64_t* bars = (uint64_t*)(dbuf + W3_NST * W3_DBYTES);
+  uint64_t* w_full = bars;                     // weight slab landed
+  uint64_t* w_empty = bars + 1;                // every MMA1 of the slab segment has read it
+  uint64_t* act_full = bars + 2;               // [3]
+  uint64_t* act_empty = act_full + W3_NST;     // [3] MMA2 of the tile has read the act stage
+  uint64_t* x_full = act_empty + W3_NST;       // [3] ds' tile landed
+  uint64_t* d_empty = x_full + W3_NST;         // [3] MMA2 and the TMA store have read the ds stage (2 arrivals)
+  uint64_t* o_full = d_empty + W3_NST;         // [3] ds tile final in shared memory (16 warp arrivals)
+  uint64_t* acc_full = o_full + W3_NST;        // [2] MMA1 complete
+  uint64_t* acc_empty = acc_full + 2;          // [2] epilogue has read D1 (16 warp arrivals)
+  uint64_t* d2_full = acc_empty + 2;           // dW accumulator of the segment complete
+  uint64_t* d2_empty = d2_full + 1;            // ... flushed (16 warp arrivals)
+  uint32_t* tmem_slot = (uint32_t*)(d2_empty + 1);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int n_slabs = (p.G + W3_SLAB - 1) / W3_SLAB;
+  const int n_ct = (p.B + W3_BM - 1) / W3_BM;
+  const int n_tiles = n_slabs * n_ct;
+  const int t0 = (int)((long long)n_tiles * blockIdx.x / gridDim.x);
+  const int t1 = (int)((long long)n_tiles * (blockIdx.x + 1) / gridDim.x);
+  const int nb = (p.h + 63) / 64;  // 64-element k-blocks of h (TMA zero-fills a partial one)
+
+  if (warp == N_EPI_WARPS && lane == 0) {
+    tma_prefetch_desc(&tmAct);
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmD);
+    mbar_init(w_full, 1);
+    mbar_init(w_empty, 1);
+    for (int s = 0; s < W3_NST; ++s) {
+      mbar_init(&act_full[s], 1);
+      mbar_init(&act_empty[s], 1);
+      mbar_init(&x_full[s], 1);
+      mbar_init(&d_empty[s], 2);
+      mbar_init(&o_full[s], N_EPI_WARPS);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], N_EPI_WARPS);
+    }
+    mbar_init(d2_full, 1);
+    mbar_init(d2_empty, N_EPI_WARPS);
+    fence_barrier_init();
+  }
+  if (warp == N_EPI_WARPS + 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto seg_first = [&](int t) { return t == t0 || t % n_ct == 0; };
+  auto seg_last = [&](int t) { return t == t1 - 1 || t % n_ct == n_ct - 1; };
+
+  if (warp == N_EPI_WARPS) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int seg = 0;
+      for (int t = t0, it = 0; t < t1; ++t, ++it) {
+        const int slab = t / n_ct, ct = t % n_ct;
+        const int g0 = slab * W3_SLAB, b0 = ct * W3_BM;
+        if (seg_first(t)) {
+          mbar_wait(w_empty, (seg & 1) ^ 1);
+          mbar_expect_tx(w_full, nb * (W3_SLAB * 128));
+          for (int j = 0; j < nb; ++j) tma_load_2d(wbuf + j * (W3_SLAB * 128), &tmW, w_full, j * 64, g0);
+          ++seg;
+        }
+        const int s = it % W3_NST, ph = (it / W3_NST) & 1;
+        mbar_wait(&act_empty[s], ph ^ 1);
+        mbar_expect_tx(&act_full[s], nb * (W3_BM * 128));
+        for (int j = 0; j < nb; ++j) tma_load_2d(abuf + s * W3_ABYTES + j * (W3_BM * 128), &tmAct, &act_full[s], j * 64, b0);
+        mbar_wait(&d_empty[s], ph ^ 1);
+        mbar_expect_tx(&x_full[s], W3_DBYTES);
+        for (int j = 0; j < 2; ++j) tma_load_2d(dbuf + s * W3_DBYTES + j * (W3_BM * 128), &tmD, &x_full[s], g0 + 64 * j, b0);
+      }
+    }
+  } else if (warp == N_EPI_WARPS + 1) {
+    // ===== MMA issuer: MMA1 of tile t is issued before MMA2 of tile t - 1 (which waits for that tile's epilogue) =====
+    if (lane == 0) {
+      const uint32_t idesc1 = idesc_f16(128, W3_BM, 0, 0);
+      const uint32_t idesc2 = idesc_f16(128, nb * 64, 1, 1);
+      const uint32_t d2_tmem = tmem_base + (uint32_t)W3_D2_COL;
+      int segW = 0, segD = 0;
+      auto mma2 = [&](int j) {
+        const int t = t0 + j;
+        const int s = j % W3_NST, ph = (j / W3_NST) & 1;
+        mbar_wait(&o_full[s], ph);
+        const bool first = seg_first(t);
+        if (first) mbar_wait(d2_empty, (segD & 1) ^ 1);  // the previous segment's accumulator has been flushed
+        tc_fence_after();
+        const uint32_t sd = smem_u32(dbuf + s * W3_DBYTES), sa = smem_u32(abuf + s * W3_ABYTES);
+#pragma unroll
+        for (int kk = 0; kk < W3_BM / 16; ++kk)  // K = 64 cells; MN-major operands: 2048 bytes per 16 k-rows
+          umma_f16(d2_tmem, smem_desc(sd + kk * 2048, 8192, 1024), smem_desc(sa + kk * 2048, 8192, 1024), idesc2,
+                   !first || kk != 0);
+        umma_commit(&act_empty[s]);
+        umma_commit(&d_empty[s]);
+        if (seg_last(t)) {
+          umma_commit(d2_full);
+          ++segD;
+        }
+      };
+      for (int t = t0, it = 0; t < t1; ++t, ++it) {
+        if (seg_first(t)) {
+          mbar_wait(w_full, segW & 1);
+          ++segW;
+        }
+        const int as = it & 1, aph = (it >> 1) & 1;
+        const int s = it % W3_NST, ph = (it / W3_NST) & 1;
+        mbar_wait(&acc_empty[as], aph ^ 1);
+        mbar_wait(&act_full[s], ph);
+        tc_fence_after();
+        const uint32_t d1 = tmem_base + (uint32_t)(as * W3_BM);
+        const uint32_t sw = smem_u32(wbuf), sa = smem_u32(abuf + s * W3_ABYTES);
+        for (int j = 0; j < nb; ++j) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_f16(d1, smem_desc(sw + j * (W3_SLAB * 128) + kk * 32, 16, 1024), smem_desc(sa + j * (W3_BM * 128) + kk * 32, 16, 1024),
+                     idesc1, (j | kk) != 0);
+        }
+        if (seg_last(t)) umma_commit(w_empty);
+        umma_commit(&acc_full[as]);
+        if (it > 0) mma2(it - 1);
+      }
+      if (t1 > t0) mma2(t1 - t0 - 1);
+    }
+  } else if (warp == N_EPI_WARPS + 2) {
+    // ===== TMA store warp: finished ds tiles -> d logits (scale half), read by the dAct GEMM =====
+    if (lane == 0) {
+      for (int t = t0, it = 0; t < t1; ++t, ++it) {
+        const int slab = t / n_ct, ct = t % n_ct;
+        const int g0 = slab * W3_SLAB, b0 = ct * W3_BM;
+        const int s = it % W3_NST, ph = (it / W3_NST) & 1;
+        mbar_wait(&o_full[s], ph);
+        for (int j = 0; j < 2; ++j) tma_store_2d(&tmD, dbuf + s * W3_DBYTES + j * (W3_BM * 128), g0 + 64 * j, b0);
+        tma_store_commit();
+        tma_store_wait_read0();
+        mbar_arrive(&d_empty[s]);
+      }
+      tma_store_wait_all();
+    }
+  } else if (warp < N_EPI_WARPS) {
+    // ===== epilogue warps: TMEM lane = gene r of the slab, column group cg = 16 cells of the tile =====
+    const int q = warp % 4, cg = warp / 4;
+    const int r = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    // byte offset of gene r inside a tile row: box r / 64, 16-byte chunk (r % 64) / 8 (XOR-swizzled with the row), 2 (r % 8)
+    const uint32_t d_gene = (uint32_t)((r >> 6) * (W3_BM * 128) + (r & 7) * 2);
+    const uint32_t chunk = (uint32_t)((r & 63) >> 3);
+    const float unscale = p.c * (1.f / DL_SCALE);
+    const float L2E = 1.4426950408889634f;
+    float bias_g = 0.f, dbacc = 0.f;
+    int segE = 0;
+    for (int t = t0, it = 0; t < t1; ++t, ++it) {
+      const int slab = t / n_ct, ct = t % n_ct;
+      const int gene = slab * W3_SLAB + r, b0 = ct * W3_BM + cg * 16;
+      const bool gene_ok = gene < p.G;
+      if (seg_first(t)) {
+        bias_g = gene_ok ? __ldg(&p.bias[gene]) * L2E : 0.f;
+        dbacc = 0.f;
+      }
+      // per-cell terms of this warp's 16 cells (warp-uniform addresses): -lse log2(e), DL_SCALE A[b]
+      float nl[16], sa[16];
+      if (b0 + 16 <= p.B) {
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(p.lse + b0) + j4);
+          const float4 b = __ldcg(reinterpret_cast<const float4*>(p.asum + b0) + j4);
+          nl[4 * j4] = a.x; nl[4 * j4 + 1] = a.y; nl[4 * j4 + 2] = a.z; nl[4 * j4 + 3] = a.w;
+          sa[4 * j4] = b.x; sa[4 * j4 + 1] = b.y; sa[4 * j4 + 2] = b.z; sa[4 * j4 + 3] = b.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const bool ok = b0 + j < p.B;
+          nl[j] = ok ? __ldg(&p.lse[b0 + j]) : 0.f;
+          sa[j] = ok ? __ldcg(&p.asum[b0 + j]) : 0.f;
+        }
+      }
+      const int as = it & 1, aph = (it >> 1) & 1;
+      const int s = it % W3_NST, ph = (it / W3_NST) & 1;
+      mbar_wait(&acc_full[as], aph);
+      tc_fence_after();
+      float sv[16];
+      tmem_ld16(lane_base + (uint32_t)(as * W3_BM + cg * 16), sv);
+      tmem_ld_wait();
+      mbar_wait(&x_full[s], ph);
+      const uint32_t drow = smem_u32(dbuf + s * W3_DBYTES) + d_gene + (uint32_t)(cg * 16 * 128);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const uint32_t addr = drow + (uint32_t)(j * 128) + ((chunk ^ (uint32_t)(j & 7)) << 4);
+        const float dsp = lds_h(addr);
+        const float pr = ex2_approx(__fmaf_rn(sv[j], L2E, bias_g) - nl[j] * L2E);
+        const bool ok = gene_ok && (b0 + j < p.B);
+        const float ds = ok ? __fmaf_rn(DL_SCALE * sa[j], pr, dsp) : 0.f;
+        sts_h_sat(addr, ds);
+        dbacc += ds;
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&acc_empty[as]);
+        mbar_arrive(&o_full[s]);
+      }
+      if (seg_last(t)) {
+        if (gene_ok) atomicAdd(&p.db[gene], dbacc * unscale);
+        mbar_wait(d2_full, segE & 1);
+        tc_fence_after();
+        // dW[gene][c .. c+15] += alpha D2[r][c ..]: this warp takes every fourth 16-column chunk
+        for (int c = cg * 16; c < p.h; c += 64) {
+          float v[16];
+          tmem_ld16(lane_base + (uint32_t)(W3_D2_COL + c), v);
+          tmem_ld_wait();
+          if (gene_ok) {
+            float* dst = dW + (size_t)gene * p.h + c;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              red_add_v4(dst + j, v[j] * unscale, v[j + 1] * unscale, v[j + 2] * unscale, v[j + 3] * unscale);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d2_empty);
+        ++segE;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == N_EPI_WARPS + 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // act = relu(bn(U)) materialised once (B x h fp32, L2 resident) as the TMA-fed A operand
 __global__ void k_act(const float* __restrict__ U, int B, int h, BnParams bn, float* __restrict__ act,
                       __half* __restrict__ act_h) {
@@ -862,7 +1156,7 @@ void tc_decoder_forward(const TcDecoderArgs& a, cudaStream_t st) {
   if (h16 && !a.w_prepared) tc_decoder_prepare(a, st);
   DecParams p{};
   p.B = a.B; p.G = a.G; p.h = a.h; p.bias = a.bias; p.lib = a.lib; p.rshift = a.rshift; p.eps = a.eps; p.c = a.c;
-  p.part_m = s.part_m; p.part_s = s.part_s; p.ll = a.ll; p.asum = a.asum;
+  p.part_m = s.part_m; p.part_s = s.part_s; p.lse = a.lse; p.ll = a.ll; p.asum = a.asum;
   p.dlogits = a.dlogits; p.db = a.db;
   const int n_ct = (a.B + BM - 1) / BM;
   // phase 1: logsumexp over genes
@@ -900,6 +1194,14 @@ void tc_decoder_forward(const TcDecoderArgs& a, cudaStream_t st) {
   // the row sums LL[b] are folded into the loss by the step's last launch (finalize_step)
 }
 
+// The fused phase 3 + dW kernel (k_dec3w) needs the fp16 operands and an h x 128-gene fp32 accumulator in TMEM.
+// DRV_DEC_FUSED_DW=0 selects phase 3 + the separate dW GEMM (A/B comparisons; also the path of h > 256).
+bool use_fused_dw(const TcDecoderArgs& a) {
+  const char* e = getenv("DRV_DEC_FUSED_DW");  // read per call: the parity tests toggle it
+  const bool off = e != nullptr && atoi(e) == 0;
+  return !off && use_h16(a) && a.h <= 256;
+}
+
 void tc_decoder_backward(const TcDecoderArgs& a, cudaStream_t st) {
   Scratch s = carve(a.scratch, a.B, a.G, a.h);
   CUtensorMap tAct, tW1, tW3, tX;
@@ -909,36 +1211,62 @@ void tc_decoder_backward(const TcDecoderArgs& a, cudaStream_t st) {
   }
   DecParams p{};
   p.B = a.B; p.G = a.G; p.h = a.h; p.bias = a.bias; p.lib = a.lib; p.eps = a.eps; p.c = a.c;
-  p.part_m = s.part_m; p.part_s = s.part_s; p.ll = a.ll; p.asum = a.asum; p.dlogits = a.dlogits; p.db = a.db;
+  p.part_m = s.part_m; p.part_s = s.part_s; p.lse = a.lse; p.ll = a.ll; p.asum = a.asum; p.dlogits = a.dlogits; p.db = a.db;
   const int n_ct = (a.B + BM - 1) / BM, n_gt1 = (a.G + 127) / 128;
   set_lse_layout(p, n_ct, n_gt1);
   const bool h16 = use_h16(a);
-  CUtensorMap tD;  // scale half of dlogits: [B][G] with row stride 2G
-  if (!(h16 ? tmap_2d_h(&tD, a.dlogits, a.B, a.G, 2 * (uint64_t)a.G, BM, 64)
-            : tmap_2d(&tD, a.dlogits, a.B, a.G, 2 * (uint64_t)a.G, BM, 32))) {
-    if (g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
-    return;
+  const bool fused = use_fused_dw(a);
+  const float alpha = a.c * (1.f / DL_SCALE);  // d logits is stored as DL_SCALE / c times its value
+  const __half* dl_h = reinterpret_cast<const __half*>(a.dlogits);
+  cudaStream_t ws = st;
+  int rc = 0;
+  if (fused) {
+    // the log_r half of d logits is final since phase 2: its weight gradient dW[G + g][i] = sum_b drho[b][g] act[b][i]
+    // (both operands MN-major, K = cells) starts on the side stream right away, next to the fused kernel
+    if (a.side) { a.side->mark(st); a.side->attach(); ws = a.side->side; }
+    drv_internal_kmark(4, 0, ws);
+    rc = gemm_f16(dl_h + a.G, 2 * a.G, true, s.act_h, a.h, true, a.dW + (size_t)a.G * a.h, a.h, a.G, a.h, a.B, 0, true, alpha, ws);
+    drv_internal_kmark(4, 1, ws);
+    // scale half: softmax coupling + weight gradient in one kernel, gene-major walk
+    CUtensorMap tA64, tD64;
+    if (!tmap_2d_h(&tA64, s.act_h, a.B, a.h, a.h, W3_BM, 64) || !tmap_2d_h(&tD64, dl_h, a.B, a.G, 2 * (uint64_t)a.G, W3_BM, 64)) {
+      if (g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
+      return;
+    }
+    const int n_tiles = ((a.G + W3_SLAB - 1) / W3_SLAB) * ((a.B + W3_BM - 1) / W3_BM);
+    drv_internal_kmark(2, 0, st);
+    cudaFuncSetAttribute(k_dec3w, cudaFuncAttributeMaxDynamicSharedMemorySize, W3_SMEM);
+    launch_k_plain(k_dec3w, n_tiles < sm_count() ? n_tiles : sm_count(), NTHREADS, W3_SMEM, st, tA64, tW1, tD64, p, a.dW);
+    note_launch();
+    drv_internal_kmark(2, 1, st);
+  } else {
+    CUtensorMap tD;  // scale half of dlogits: [B][G] with row stride 2G
+    if (!(h16 ? tmap_2d_h(&tD, a.dlogits, a.B, a.G, 2 * (uint64_t)a.G, BM, 64)
+              : tmap_2d(&tD, a.dlogits, a.B, a.G, 2 * (uint64_t)a.G, BM, 32))) {
+      if (g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
+      return;
+    }
+    drv_internal_kmark(2, 0, st);
+    if (h16) launch_dec(k_dec<3, true, true>, n_ct * n_gt1, tAct, tW1, tD, tD, tD, p, st);
+    else launch_dec(k_dec<3, true, false>, n_ct * n_gt1, tAct, tW1, tD, tD, tD, p, st);
+    drv_internal_kmark(2, 1, st);
+    if (a.side) a.side->mark(st);
   }
-  drv_internal_kmark(2, 0, st);
-  if (h16) launch_dec(k_dec<3, true, true>, n_ct * n_gt1, tAct, tW1, tD, tD, tD, p, st);
-  else launch_dec(k_dec<3, true, false>, n_ct * n_gt1, tAct, tW1, tD, tD, tD, p, st);
-  drv_internal_kmark(2, 1, st);
-  // dW[j][i] = sum_b dlogits[b][j] act[b][i]   (both operands MN-major, K = cells)
-  if (a.side) a.side->mark(st);
   // dAct[b][i] = sum_j dlogits[b][j] W[j][i]   (A K-major, B MN-major, K = 2G): critical path, submitted first
   drv_internal_kmark(3, 0, st);
-  const float alpha = a.c * (1.f / DL_SCALE);  // d logits is stored as DL_SCALE / c times its value
-  int rc = h16 ? gemm_f16(a.dlogits, 2 * a.G, false, s.W_h, a.h, true, a.dY, a.h, a.B, a.h, 2 * a.G, 0, true, alpha, st)
-               : gemm_tf32(a.dlogits, 2 * a.G, false, a.W_hi, a.h, true, a.dY, a.h, a.B, a.h, 2 * a.G, 0, /*accumulate (cleared at step start)=*/true, st);
-  drv_internal_kmark(3, 1, st);
-  // dW[j][i] = sum_b dlogits[b][j] act[b][i]   (both operands MN-major, K = cells): off the critical chain
-  cudaStream_t ws = st;
-  if (a.side) { a.side->attach(); ws = a.side->side; }
-  drv_internal_kmark(4, 0, ws);
   if (rc == 0)
-    rc = h16 ? gemm_f16(a.dlogits, 2 * a.G, true, s.act_h, a.h, true, a.dW, a.h, 2 * a.G, a.h, a.B, 0, true, alpha, ws)
-             : gemm_tf32(a.dlogits, 2 * a.G, true, s.act, a.h, true, a.dW, a.h, 2 * a.G, a.h, a.B, 0, true, ws);
-  drv_internal_kmark(4, 1, ws);
+    rc = h16 ? gemm_f16(a.dlogits, 2 * a.G, false, s.W_h, a.h, true, a.dY, a.h, a.B, a.h, 2 * a.G, 0, true, alpha, st)
+             : gemm_tf32(a.dlogits, 2 * a.G, false, a.W_hi, a.h, true, a.dY, a.h, a.B, a.h, 2 * a.G, 0, /*accumulate (cleared at step start)=*/true, st);
+  drv_internal_kmark(3, 1, st);
+  if (!fused) {
+    // dW[j][i] = sum_b dlogits[b][j] act[b][i]   (both operands MN-major, K = cells): off the critical chain
+    if (a.side) { a.side->attach(); ws = a.side->side; }
+    drv_internal_kmark(4, 0, ws);
+    if (rc == 0)
+      rc = h16 ? gemm_f16(a.dlogits, 2 * a.G, true, s.act_h, a.h, true, a.dW, a.h, 2 * a.G, a.h, a.B, 0, true, alpha, ws)
+               : gemm_tf32(a.dlogits, 2 * a.G, true, s.act, a.h, true, a.dW, a.h, 2 * a.G, a.h, a.B, 0, true, ws);
+    drv_internal_kmark(4, 1, ws);
+  }
   if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
   // the ReLU gate of dAct is applied by the BatchNorm backward kernels (block_backward)
 }

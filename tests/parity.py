@@ -55,7 +55,18 @@ def oracle_step(case, dtype=torch.float64):
     cast = lambda v: [t.to(dtype) for t in v] if isinstance(v, list) else v.to(dtype)
     noise = {k: cast(v) for k, v in case["noise"].items()}
     y = [t.to(dtype) for t in case["y"]] if case["y"] is not None else None
+    # ReLU gate margin: the smallest |pre-activation| of every BatchNorm -> ReLU, relative to the layer's rms.  The
+    # gradient is DISCONTINUOUS where a pre-activation crosses 0: an implementation whose forward error exceeds the
+    # margin flips that gate, and one flipped (cell, unit) moves a weight gradient by ~1/sqrt(cells x units) of its
+    # norm (2e-3 at 512 x 128) whatever the size of the forward error (tools/disp_probe2.py).
+    margins = []
+    hooks = [mod.register_forward_pre_hook(lambda _m, inp: margins.append(
+        float(inp[0].detach().abs().min() / inp[0].detach().pow(2).mean().sqrt())))
+        for mod in m.modules() if isinstance(mod, torch.nn.ReLU)]
     loss, grads, terms = O.step(m, case["x"].to(dtype), noise, case["labels"], y)
+    for h in hooks:
+        h.remove()
+    m.relu_gate_margin = min(margins) if margins else float("inf")
     return loss, grads, terms, m
 
 
@@ -100,7 +111,7 @@ def compare_step(case, device="cuda:0", force_simt=False):
     loss, grads, model = cuda_step(case, device, force_simt)
     rep = {"loss": loss, "loss64": loss64, "loss_rel": abs(loss - loss64) / abs(loss64),
            "loss32_rel": abs(loss32 - loss64) / abs(loss64), "grads": {}, "launches": model._runtime().last_launches,
-           "path": model._runtime().last_path}
+           "path": model._runtime().last_path, "relu_gate_margin": m64.relu_gate_margin}
     worst, worst_name = 0.0, ""
     zero_biases = zero_grad_biases(len(case["cfg"]["layers"]))
     for name, g64 in grads64.items():

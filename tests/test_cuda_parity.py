@@ -34,8 +34,9 @@ CASES = {
 
 
 def _report(rep):
-    lines = ["loss cuda=%.6f oracle64=%.6f rel=%.2e (oracle32 floor %.2e) bn=%.2e path=%d" % (
-        rep["loss"], rep["loss64"], rep["loss_rel"], rep["loss32_rel"], rep["bn_worst_rel"], rep.get("path", -1))]
+    lines = ["loss cuda=%.6f oracle64=%.6f rel=%.2e (oracle32 floor %.2e) bn=%.2e path=%d relu gate margin %.1e" % (
+        rep["loss"], rep["loss64"], rep["loss_rel"], rep["loss32_rel"], rep["bn_worst_rel"], rep.get("path", -1),
+        rep.get("relu_gate_margin", float("nan")))]
     for k, (kind, e, floor) in rep["grads"].items():
         lines.append("  %-44s %-8s %.2e (fp32-oracle floor %.2e)" % (k, kind, e, floor))
     return "\n".join(lines)
@@ -50,6 +51,19 @@ def test_step_matches_oracle(name, force_simt):
     assert rep["loss_rel"] <= ELBO_TOL, _report(rep)
     assert rep["worst_grad_rel"] <= GRAD_TOL, _report(rep)
     assert rep["bn_worst_rel"] <= 1e-5, _report(rep)
+
+
+@pytest.mark.parametrize("name", ["mid", "tc_ragged", "cfg5_head"])
+def test_unfused_weight_gradient_path_matches_oracle(name, monkeypatch):
+    """h <= 256 takes the fused phase 3 + dW kernel (k_dec3w: d logits consumed in place by the weight-gradient MMA);
+    DRV_DEC_FUSED_DW=0 selects phase 3 + the separate dW GEMM, which stays the path of h > 256 - both must match."""
+    monkeypatch.setenv("DRV_DEC_FUSED_DW", "0")
+    case = P.make_case(CASES[name], bn_affine_random=True)
+    rep = P.compare_step(case, force_simt=False)
+    print(_report(rep))
+    assert rep["path"] & 1
+    assert rep["loss_rel"] <= ELBO_TOL, _report(rep)
+    assert rep["worst_grad_rel"] <= GRAD_TOL, _report(rep)
 
 
 @pytest.mark.parametrize("fixture,cfg", [("oracle_step_tiny.npz", dict(n_input=203, n_latent=3, layers=[24, 40], batch=77, drugs=0)),
@@ -251,11 +265,20 @@ def test_ragged_shapes_run_on_the_tensor_core_path(name):
 # of the last decoder bias is shifted so that r runs from ~3e-4 to ~3e3 (and, at +11, beyond the fast path's
 # range: r ~ 6e4 takes the generic lgamma / digamma route of nb_elems).  The fp32-oracle floor (the reference's
 # own arithmetic against fp64) is printed next to every figure.
+# Data seeds: chosen so that no BatchNorm -> ReLU pre-activation of the fp64 oracle lies within 5e-6 (relative to the
+# layer's rms) of zero.  The gradient is discontinuous there: with data seed 11 the last decoder ReLU has an entry at
+# 1.5e-6, the tensor-core forward (error ~1e-6) lands on the other side of it, and that ONE flipped (cell, unit) moves the
+# decoder-trunk gradients by 2e-3 of their norm at 512 cells x 128 units - for every log_r shift, and equally in the
+# fp64 oracle when its first Linear output is perturbed by 1e-6 (tools/disp_probe2.py, profiles/r02_relu_gate_flip.txt).
+# tests/test_oracle.py::test_parity_seeds_keep_relu_gates_clear_of_zero checks the margins on the CPU.
+DISPERSION_SEEDS = {"mid": 15, "wide_hidden": 12}
+
+
 @pytest.mark.parametrize("force_simt", [True, False])
 @pytest.mark.parametrize("shift", [-8.0, -4.0, 4.0, 8.0, 11.0])
 @pytest.mark.parametrize("name", ["mid", "wide_hidden"])
 def test_dispersion_sweep(name, shift, force_simt):
-    case = P.make_case(CASES[name], data_seed=11, log_r_shift=shift)
+    case = P.make_case(CASES[name], data_seed=DISPERSION_SEEDS[name], log_r_shift=shift)
     rep = P.compare_step(case, force_simt=force_simt)
     print(name, "log_r shift", shift, "force_simt", force_simt)
     print(_report(rep))
