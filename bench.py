@@ -467,7 +467,8 @@ class Workload:
         roof["traffic"] = traffic.get("decoder_step_bytes")
         roof["traffic_source"] = tnote
         roof["kernel"] = ("fused decoder step = k_act + k_dec<1> (logsumexp) + k_dec<2> (NB likelihood + NB part of dlogits) + "
-                          "k_dec<3> (softmax coupling) + dAct and dW tcgen05 GEMMs (sections DEC_NB_FWD + DEC_NB_BWD, "
+                          "k_dec3w (softmax coupling + the scale half's weight gradient, d logits consumed in shared memory; "
+                          "h > 256: k_dec<3> + dW GEMM) + dAct GEMM + dW GEMM of the log_r half (sections DEC_NB_FWD + DEC_NB_BWD, "
                           "side stream off)")
         roof["ms"] = round(t_dec_ms, 4)
         roof["algorithmic"] = {"bytes": bytes_alg, "flops": flops_alg, "mufu_ops": mufu,
@@ -483,13 +484,26 @@ class Workload:
         # per-kernel entries: the bytes / flops / MUFU each launch must move TODAY (fp16 operands and the fp16 dlogits
         # hand-off between the kernels included - that hand-off is not algorithmic, which is why only the whole-step
         # entry above is the roofline claim) over its own event-timed duration
+        # h <= 256: phase 3 and the weight gradient of the scale half are ONE kernel (k_dec3w: the finished ds tile is an
+        # operand of the dW MMA while it is still in shared memory); the separate dW GEMM only covers the log_r half
+        fused_dw = hf <= 256 and os.environ.get("DRV_DEC_FUSED_DW", "1") != "0"
         kdefs = [
             ("k_dec<1> logsumexp", 2 * Gf * hf + 2 * Bf * hf, 2 * Bf * Gf * hf, 1 * Bf * Gf),
             ("k_dec<2> NB likelihood (+ NB part of dlogits)", 4 * Bf * Gf + 4 * Bf * Gf + 4 * Gf * hf + 2 * Bf * hf, 4 * Bf * Gf * hf, 8 * Bf * Gf),
-            ("k_dec<3> softmax coupling", 2 * Bf * Gf + 2 * Bf * Gf + 2 * Gf * hf + 2 * Bf * hf, 2 * Bf * Gf * hf, 1 * Bf * Gf),
-            ("dAct GEMM", 4 * Bf * Gf + 4 * Gf * hf + 4 * Bf * hf, 4 * Bf * Gf * hf, 0.0),
-            ("dW GEMM", 4 * Bf * Gf + 2 * Bf * hf + 8 * Gf * hf, 4 * Bf * Gf * hf, 0.0),
         ]
+        if fused_dw:
+            kdefs += [
+                ("k_dec3w softmax coupling + dW (scale half) in one kernel", 2 * Bf * Gf + 2 * Bf * Gf + 2 * Gf * hf + 2 * Bf * hf + 4 * Gf * hf,
+                 4 * Bf * Gf * hf, 1 * Bf * Gf),
+                ("dAct GEMM", 4 * Bf * Gf + 4 * Gf * hf + 4 * Bf * hf, 4 * Bf * Gf * hf, 0.0),
+                ("dW GEMM (log_r half)", 2 * Bf * Gf + 2 * Bf * hf + 4 * Gf * hf, 2 * Bf * Gf * hf, 0.0),
+            ]
+        else:
+            kdefs += [
+                ("k_dec<3> softmax coupling", 2 * Bf * Gf + 2 * Bf * Gf + 2 * Gf * hf + 2 * Bf * hf, 2 * Bf * Gf * hf, 1 * Bf * Gf),
+                ("dAct GEMM", 4 * Bf * Gf + 4 * Gf * hf + 4 * Bf * hf, 4 * Bf * Gf * hf, 0.0),
+                ("dW GEMM", 4 * Bf * Gf + 2 * Bf * hf + 8 * Gf * hf, 4 * Bf * Gf * hf, 0.0),
+            ]
         rk = []
         for i, (name, kb, kf, km) in enumerate(kdefs):
             if kms[i] <= 0:

@@ -219,6 +219,26 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
+// The same descriptor as two 32-bit halves: the MMA-issuing thread builds the constant parts once and only adds the
+// (16-byte granular) start-address offset of each MMA to the low word.  One thread issues every MMA of a CTA, and
+// rebuilding the 64-bit descriptor per instruction (shift / mask / or on the uniform datapath, ~10 dependent
+// instructions) took longer than a small MMA runs (tools/w3_trace.py: 107 cycles per M128 N64 K16 instruction).
+struct DescHalves {
+  uint32_t lo, hi;
+};
+__device__ __forceinline__ DescHalves desc_halves(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
+  DescHalves d;
+  d.lo = ((saddr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+  d.hi = ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (layout_type << 29);
+  return d;
+}
+// descriptor of the operand `byte_off` bytes further (multiple of 16; the sum stays inside the 14-bit address field)
+__device__ __forceinline__ uint64_t desc_at(DescHalves d, uint32_t byte_off) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(d.lo + (byte_off >> 4)), "r"(d.hi));
+  return r;
+}
+
 // Instruction descriptor: fp32 accumulate, tf32 A and B, M x N, majors (0 = K-major, 1 = MN-major)
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn, int b_mn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |

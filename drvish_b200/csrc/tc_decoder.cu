@@ -90,6 +90,7 @@ struct DecParams {
   float* asum;        // [B]
   float* dlogits;     // [B][2G]
   float* db;          // [2G] (atomic accumulation, zeroed)
+  const unsigned long long* trace;  // non-null: k_dec3w stamps its timeline (debug)
 };
 
 // Column sums of 4 values over the 32 lanes of a warp by a transposing butterfly (6 shuffles instead
@@ -745,7 +746,8 @@ constexpr int W3_NST = 3;                    // act / ds tile stages
 constexpr int W3_WBYTES = 4 * W3_SLAB * 128; // weight slab: up to 4 k-blocks of [128 genes][64 h] fp16
 constexpr int W3_ABYTES = 4 * W3_BM * 128;   // act tile: up to 4 boxes of [64 cells][64 h] fp16
 constexpr int W3_DBYTES = 2 * W3_BM * 128;   // ds tile: 2 boxes of [64 cells][64 genes] fp16
-constexpr int W3_SMEM = W3_WBYTES + W3_NST * (W3_ABYTES + W3_DBYTES) + 1024 + 512;
+constexpr int W3_CBYTES = 2 * W3_BM * 4;         // per-cell terms of a tile: lse[64], A[64] (fp32)
+constexpr int W3_SMEM = W3_WBYTES + W3_NST * (W3_ABYTES + W3_DBYTES + W3_CBYTES) + 1024 + 512;
 static_assert(W3_SMEM <= 227 * 1024, "shared memory");
 constexpr int W3_D2_COL = 128;               // TMEM column of the dW accumulator (D1 stages at 0 and 64)
 
@@ -753,6 +755,29 @@ __device__ __forceinline__ float lds_h(uint32_t a) {
   unsigned short v;
   asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
   return __half2float(__ushort_as_half(v));
+}
+__device__ __forceinline__ unsigned short lds_u16(uint32_t a) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ unsigned short lds_u16_off(uint32_t a) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1+%2];" : "=h"(v) : "r"(a), "n"(OFF) : "memory");
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ void sts_h_sat_off(uint32_t a, float f) {
+  unsigned short v;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(v) : "f"(f));
+  asm volatile("st.shared.u16 [%0+%2], %1;" ::"r"(a), "h"(v), "n"(OFF) : "memory");
+}
+// 1-D bulk copy global -> shared (bytes: multiple of 16, both addresses 16-byte aligned), completion on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 __device__ __forceinline__ void sts_h_sat(uint32_t a, float f) {
   unsigned short v;
@@ -763,16 +788,40 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Debug timeline of CTA 0 (DRV_W3_TRACE=1): globaltimer stamps per tile and role, read back with drv_debug_w3_trace
+constexpr int W3_TRACE_TILES = 24, W3_TRACE_EVENTS = 10;
+__device__ unsigned long long g_w3_trace[W3_TRACE_TILES * W3_TRACE_EVENTS];
+__device__ __forceinline__ void w3_stamp(const unsigned long long* on, int it, int ev) {
+  if (on && blockIdx.x == 0 && it < W3_TRACE_TILES) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_w3_trace[it * W3_TRACE_EVENTS + ev] = t;
+  }
+}
+
+// kernel-level stamps of the first / middle / last CTA: slots [tile 21..23][entry, set-up done, walk done, exit]
+__device__ __forceinline__ void w3_stamp_cta(const unsigned long long* on, int ev) {
+  if (!on || threadIdx.x != 0) return;
+  const int slot = blockIdx.x == 0 ? 21 : (blockIdx.x == gridDim.x / 2 ? 22 : (blockIdx.x == gridDim.x - 1 ? 23 : -1));
+  if (slot < 0) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  g_w3_trace[slot * W3_TRACE_EVENTS + ev] = t;
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_dec3w(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtensorMap tmW,
         const __grid_constant__ CUtensorMap tmD, DecParams p, float* __restrict__ dW) {
+  w3_stamp_cta(p.trace, 0);
   pdl_prologue();
+  w3_stamp_cta(p.trace, 1);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* wbuf = smem;
   uint8_t* abuf = wbuf + W3_WBYTES;            // [W3_NST][W3_ABYTES]
   uint8_t* dbuf = abuf + W3_NST * W3_ABYTES;   // [W3_NST][W3_DBYTES]
-  uint64_t* bars = (uint64_t*)(dbuf + W3_NST * W3_DBYTES);
+  uint8_t* cbuf = dbuf + W3_NST * W3_DBYTES;   // [W3_NST][lse[64] | A[64]]
+  uint64_t* bars = (uint64_t*)(cbuf + W3_NST * W3_CBYTES);
   uint64_t* w_full = bars;                     // weight slab landed
   uint64_t* w_empty = bars + 1;                // every MMA1 of the slab segment has read it
   uint64_t* act_full = bars + 2;               // [3]
@@ -820,6 +869,7 @@ k_dec3w(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUten
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  w3_stamp_cta(p.trace, 2);
 
   auto seg_first = [&](int t) { return t == t0 || t % n_ct == 0; };
   auto seg_last = [&](int t) { return t == t1 - 1 || t % n_ct == n_ct - 1; };
@@ -839,40 +889,35 @@ k_dec3w(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUten
         }
         const int s = it % W3_NST, ph = (it / W3_NST) & 1;
         mbar_wait(&act_empty[s], ph ^ 1);
+        w3_stamp(p.trace, it, 0);
         mbar_expect_tx(&act_full[s], nb * (W3_BM * 128));
         for (int j = 0; j < nb; ++j) tma_load_2d(abuf + s * W3_ABYTES + j * (W3_BM * 128), &tmAct, &act_full[s], j * 64, b0);
         mbar_wait(&d_empty[s], ph ^ 1);
-        mbar_expect_tx(&x_full[s], W3_DBYTES);
+        w3_stamp(p.trace, it, 1);
+        // per-cell terms of the tile (lse, A): whole 16-byte pieces; a ragged last piece reads into the 256-byte padding
+        // of the workspace arrays, the epilogue masks those cells
+        const uint32_t cb = (uint32_t)(((min(W3_BM, p.B - b0) + 3) / 4) * 16);
+        mbar_expect_tx(&x_full[s], W3_DBYTES + 2 * cb);
         for (int j = 0; j < 2; ++j) tma_load_2d(dbuf + s * W3_DBYTES + j * (W3_BM * 128), &tmD, &x_full[s], g0 + 64 * j, b0);
+        bulk_load_1d(cbuf + s * W3_CBYTES, p.lse + b0, cb, &x_full[s]);
+        bulk_load_1d(cbuf + s * W3_CBYTES + W3_BM * 4, p.asum + b0, cb, &x_full[s]);
       }
     }
   } else if (warp == N_EPI_WARPS + 1) {
-    // ===== MMA issuer: MMA1 of tile t is issued before MMA2 of tile t - 1 (which waits for that tile's epilogue) =====
-    if (lane == 0) {
+    // ===== MMA issuer =====
+    // Order per trigger "epilogue of tile t - 1 done" (o_full): MMA2(t - 1) first - its commit frees the act / ds stage
+    // for the TMA as early as possible - then MMA1(t + 1), which runs on the tensor pipe while the epilogue warps work
+    // on tile t.  (tools/w3_trace.py: MMA1 = 16 N=64 MMAs takes 0.8 us, MMA2 0.4 us, the epilogue 0.7 us per tile.)
+    // warp-uniform control flow (all lanes wait on the barriers), one elected lane issues: inside a divergent
+    // `if (lane == 0)` the compiler wraps every tcgen05 instruction in a uniformity loop (ELECT / BRA.U.ANY)
+    {
+      const bool leader = elect_one();
       const uint32_t idesc1 = idesc_f16(128, W3_BM, 0, 0);
       const uint32_t idesc2 = idesc_f16(128, nb * 64, 1, 1);
       const uint32_t d2_tmem = tmem_base + (uint32_t)W3_D2_COL;
       int segW = 0, segD = 0;
-      auto mma2 = [&](int j) {
-        const int t = t0 + j;
-        const int s = j % W3_NST, ph = (j / W3_NST) & 1;
-        mbar_wait(&o_full[s], ph);
-        const bool first = seg_first(t);
-        if (first) mbar_wait(d2_empty, (segD & 1) ^ 1);  // the previous segment's accumulator has been flushed
-        tc_fence_after();
-        const uint32_t sd = smem_u32(dbuf + s * W3_DBYTES), sa = smem_u32(abuf + s * W3_ABYTES);
-#pragma unroll
-        for (int kk = 0; kk < W3_BM / 16; ++kk)  // K = 64 cells; MN-major operands: 2048 bytes per 16 k-rows
-          umma_f16(d2_tmem, smem_desc(sd + kk * 2048, 8192, 1024), smem_desc(sa + kk * 2048, 8192, 1024), idesc2,
-                   !first || kk != 0);
-        umma_commit(&act_empty[s]);
-        umma_commit(&d_empty[s]);
-        if (seg_last(t)) {
-          umma_commit(d2_full);
-          ++segD;
-        }
-      };
-      for (int t = t0, it = 0; t < t1; ++t, ++it) {
+      auto mma1 = [&](int it) {
+        const int t = t0 + it;
         if (seg_first(t)) {
           mbar_wait(w_full, segW & 1);
           ++segW;
@@ -881,20 +926,50 @@ k_dec3w(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUten
         const int s = it % W3_NST, ph = (it / W3_NST) & 1;
         mbar_wait(&acc_empty[as], aph ^ 1);
         mbar_wait(&act_full[s], ph);
+        if (lane == 0) w3_stamp(p.trace, it, 2);
         tc_fence_after();
         const uint32_t d1 = tmem_base + (uint32_t)(as * W3_BM);
-        const uint32_t sw = smem_u32(wbuf), sa = smem_u32(abuf + s * W3_ABYTES);
-        for (int j = 0; j < nb; ++j) {
+        const DescHalves da = desc_halves(smem_u32(wbuf), 16, 1024), db = desc_halves(smem_u32(abuf + s * W3_ABYTES), 16, 1024);
+        const bool sl = seg_last(t);
+        if (leader) {
+          for (int j = 0; j < nb; ++j) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_f16(d1, smem_desc(sw + j * (W3_SLAB * 128) + kk * 32, 16, 1024), smem_desc(sa + j * (W3_BM * 128) + kk * 32, 16, 1024),
-                     idesc1, (j | kk) != 0);
+            for (int kk = 0; kk < 4; ++kk)
+              umma_f16(d1, desc_at(da, (uint32_t)(j * (W3_SLAB * 128) + kk * 32)), desc_at(db, (uint32_t)(j * (W3_BM * 128) + kk * 32)),
+                       idesc1, (j | kk) != 0);
+          }
+          if (sl) umma_commit(w_empty);
+          umma_commit(&acc_full[as]);
         }
-        if (seg_last(t)) umma_commit(w_empty);
-        umma_commit(&acc_full[as]);
-        if (it > 0) mma2(it - 1);
+        __syncwarp();
+      };
+      auto mma2 = [&](int j) {
+        const int t = t0 + j;
+        const int s = j % W3_NST, ph = (j / W3_NST) & 1;
+        mbar_wait(&o_full[s], ph);
+        const bool first = seg_first(t);
+        if (first) mbar_wait(d2_empty, (segD & 1) ^ 1);  // the previous segment's accumulator has been flushed
+        tc_fence_after();
+        if (lane == 0) w3_stamp(p.trace, j, 3);
+        const DescHalves dd = desc_halves(smem_u32(dbuf + s * W3_DBYTES), 8192, 1024), da = desc_halves(smem_u32(abuf + s * W3_ABYTES), 8192, 1024);
+        const bool sl = seg_last(t);
+        if (leader) {
+#pragma unroll
+          for (int kk = 0; kk < W3_BM / 16; ++kk)  // K = 64 cells; MN-major operands: 2048 bytes per 16 k-rows
+            umma_f16(d2_tmem, desc_at(dd, (uint32_t)(kk * 2048)), desc_at(da, (uint32_t)(kk * 2048)), idesc2, !first || kk != 0);
+          umma_commit(&act_empty[s]);
+          umma_commit(&d_empty[s]);
+          if (sl) umma_commit(d2_full);
+        }
+        __syncwarp();
+        if (sl) ++segD;
+      };
+      const int n_it = t1 - t0;
+      if (n_it > 0) mma1(0);
+      for (int it = 0; it < n_it; ++it) {
+        if (it + 1 < n_it) mma1(it + 1);  // issued right behind MMA2(it - 1): overlaps the epilogue of tile it
+        mma2(it);
       }
-      if (t1 > t0) mma2(t1 - t0 - 1);
     }
   } else if (warp == N_EPI_WARPS + 2) {
     // ===== TMA store warp: finished ds tiles -> d logits (scale half), read by the dAct GEMM =====
@@ -904,9 +979,11 @@ k_dec3w(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUten
         const int g0 = slab * W3_SLAB, b0 = ct * W3_BM;
         const int s = it % W3_NST, ph = (it / W3_NST) & 1;
         mbar_wait(&o_full[s], ph);
+        w3_stamp(p.trace, it, 4);
         for (int j = 0; j < 2; ++j) tma_store_2d(&tmD, dbuf + s * W3_DBYTES + j * (W3_BM * 128), g0 + 64 * j, b0);
         tma_store_commit();
         tma_store_wait_read0();
+        w3_stamp(p.trace, it, 5);
         mbar_arrive(&d_empty[s]);
       }
       tma_store_wait_all();
@@ -915,58 +992,85 @@ k_dec3w(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUten
     // ===== epilogue warps: TMEM lane = gene r of the slab, column group cg = 16 cells of the tile =====
     const int q = warp % 4, cg = warp / 4;
     const int r = q * 32 + lane;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    // byte offset of gene r inside a tile row: box r / 64, 16-byte chunk (r % 64) / 8 (XOR-swizzled with the row), 2 (r % 8)
-    const uint32_t d_gene = (uint32_t)((r >> 6) * (W3_BM * 128) + (r & 7) * 2);
-    const uint32_t chunk = (uint32_t)((r & 63) >> 3);
     const float unscale = p.c * (1.f / DL_SCALE);
     const float L2E = 1.4426950408889634f;
+    // shared-space addresses, made opaque so that they stay in registers (the compiler otherwise re-derives them from
+    // %tid and the shared window every tile).  Entry (cell c, gene r) of a ds tile: box r / 64, row c, 16-byte chunk
+    // ((r % 64) / 8) ^ (c % 8), byte 2 (r % 8); this warp's cells are c = 16 cg + j, so c % 8 = j % 8.
+    uint32_t d_row0 = smem_u32(dbuf) + (uint32_t)((r >> 6) * (W3_BM * 128) + (r & 7) * 2 + cg * 16 * 128);
+    uint32_t c_row0 = smem_u32(cbuf) + (uint32_t)(cg * 64);
+    uint32_t tm_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t sw[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sw[k] = (uint32_t)(((((r & 63) >> 3) ^ k) << 4));
+    asm volatile("" : "+r"(d_row0), "+r"(c_row0), "+r"(tm_lane));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) asm volatile("" : "+r"(sw[k]));
     float bias_g = 0.f, dbacc = 0.f;
     int segE = 0;
+    int slab = t0 / n_ct, ct = t0 % n_ct;  // walked incrementally (no division per tile)
+    int s = 0, sph = 0;
     for (int t = t0, it = 0; t < t1; ++t, ++it) {
-      const int slab = t / n_ct, ct = t % n_ct;
       const int gene = slab * W3_SLAB + r, b0 = ct * W3_BM + cg * 16;
       const bool gene_ok = gene < p.G;
-      if (seg_first(t)) {
-        bias_g = gene_ok ? __ldg(&p.bias[gene]) * L2E : 0.f;
+      const bool first = (it == 0) || (ct == 0), last = (t == t1 - 1) || (ct == n_ct - 1);
+      if (first) {
+        // exponent constant of this gene: (bias + log(DL_SCALE)) log2(e) - the softmax term comes out pre-scaled
+        bias_g = gene_ok ? __fmaf_rn(__ldg(&p.bias[gene]), L2E, 2.f) : 0.f;
+        static_assert(DL_SCALE == 4.0f, "log2(DL_SCALE) = 2 is folded into the exponent");
         dbacc = 0.f;
       }
-      // per-cell terms of this warp's 16 cells (warp-uniform addresses): -lse log2(e), DL_SCALE A[b]
-      float nl[16], sa[16];
-      if (b0 + 16 <= p.B) {
+      const int as = it & 1, aph = (it >> 1) & 1;
+      // the staged ds' tile and the per-cell terms first: their shared-memory latency hides behind the wait for MMA1
+      mbar_wait(&x_full[s], sph);
+      if (threadIdx.x == 0) w3_stamp(p.trace, it, 6);
+      const uint32_t drow = d_row0 + (uint32_t)(s * W3_DBYTES);
+      uint32_t base[8];
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(p.lse + b0) + j4);
-          const float4 b = __ldcg(reinterpret_cast<const float4*>(p.asum + b0) + j4);
-          nl[4 * j4] = a.x; nl[4 * j4 + 1] = a.y; nl[4 * j4 + 2] = a.z; nl[4 * j4 + 3] = a.w;
-          sa[4 * j4] = b.x; sa[4 * j4 + 1] = b.y; sa[4 * j4 + 2] = b.z; sa[4 * j4 + 3] = b.w;
+      for (int k = 0; k < 8; ++k) base[k] = drow + sw[k];
+      unsigned short raw[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        raw[j] = lds_u16_off<0>(base[j] + (uint32_t)(j * 128));
+        raw[j + 8] = lds_u16_off<8 * 128>(base[j] + (uint32_t)(j * 128));
+      }
+      const uint32_t crow = c_row0 + (uint32_t)(s * W3_CBYTES);
+      float nl[16], sa[16];
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 a = lds128(crow + j4 * 16), b = lds128(crow + W3_BM * 4 + j4 * 16);
+        nl[4 * j4] = a.x; nl[4 * j4 + 1] = a.y; nl[4 * j4 + 2] = a.z; nl[4 * j4 + 3] = a.w;
+        sa[4 * j4] = b.x; sa[4 * j4 + 1] = b.y; sa[4 * j4 + 2] = b.z; sa[4 * j4 + 3] = b.w;
+      }
+      mbar_wait(&acc_full[as], aph);
+      if (threadIdx.x == 0) w3_stamp(p.trace, it, 7);
+      tc_fence_after();
+      float sv[16];
+      tmem_ld16(tm_lane + (uint32_t)(as * W3_BM + cg * 16), sv);
+      tmem_ld_wait();
+      if (threadIdx.x == 0) w3_stamp(p.trace, it, 8);
+      // ds = ds' + DL_SCALE A[b] softmax(s)  (both stored pre-scaled by DL_SCALE / c)
+      float ds[16];
+      if (gene_ok && b0 + 16 <= p.B) {  // interior: no validity selects
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float pr = ex2_approx(__fmaf_rn(nl[j], -L2E, __fmaf_rn(sv[j], L2E, bias_g)));
+          ds[j] = __fmaf_rn(sa[j], pr, __half2float(__ushort_as_half(raw[j])));
+          dbacc += ds[j];
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const bool ok = b0 + j < p.B;
-          nl[j] = ok ? __ldg(&p.lse[b0 + j]) : 0.f;
-          sa[j] = ok ? __ldcg(&p.asum[b0 + j]) : 0.f;
+          const float pr = ex2_approx(__fmaf_rn(nl[j], -L2E, __fmaf_rn(sv[j], L2E, bias_g)));
+          const bool ok = gene_ok && (b0 + j < p.B);
+          ds[j] = ok ? __fmaf_rn(sa[j], pr, __half2float(__ushort_as_half(raw[j]))) : 0.f;
+          dbacc += ds[j];
         }
       }
-      const int as = it & 1, aph = (it >> 1) & 1;
-      const int s = it % W3_NST, ph = (it / W3_NST) & 1;
-      mbar_wait(&acc_full[as], aph);
-      tc_fence_after();
-      float sv[16];
-      tmem_ld16(lane_base + (uint32_t)(as * W3_BM + cg * 16), sv);
-      tmem_ld_wait();
-      mbar_wait(&x_full[s], ph);
-      const uint32_t drow = smem_u32(dbuf + s * W3_DBYTES) + d_gene + (uint32_t)(cg * 16 * 128);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const uint32_t addr = drow + (uint32_t)(j * 128) + ((chunk ^ (uint32_t)(j & 7)) << 4);
-        const float dsp = lds_h(addr);
-        const float pr = ex2_approx(__fmaf_rn(sv[j], L2E, bias_g) - nl[j] * L2E);
-        const bool ok = gene_ok && (b0 + j < p.B);
-        const float ds = ok ? __fmaf_rn(DL_SCALE * sa[j], pr, dsp) : 0.f;
-        sts_h_sat(addr, ds);
-        dbacc += ds;
+      for (int j = 0; j < 8; ++j) {
+        sts_h_sat_off<0>(base[j] + (uint32_t)(j * 128), ds[j]);
+        sts_h_sat_off<8 * 128>(base[j] + (uint32_t)(j * 128), ds[j + 8]);
       }
       fence_proxy_async();
       tc_fence_before();
@@ -975,14 +1079,15 @@ k_dec3w(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUten
         mbar_arrive(&acc_empty[as]);
         mbar_arrive(&o_full[s]);
       }
-      if (seg_last(t)) {
+      if (threadIdx.x == 0) w3_stamp(p.trace, it, 9);
+      if (last) {
         if (gene_ok) atomicAdd(&p.db[gene], dbacc * unscale);
         mbar_wait(d2_full, segE & 1);
         tc_fence_after();
         // dW[gene][c .. c+15] += alpha D2[r][c ..]: this warp takes every fourth 16-column chunk
         for (int c = cg * 16; c < p.h; c += 64) {
           float v[16];
-          tmem_ld16(lane_base + (uint32_t)(W3_D2_COL + c), v);
+          tmem_ld16(tm_lane + (uint32_t)(W3_D2_COL + c), v);
           tmem_ld_wait();
           if (gene_ok) {
             float* dst = dW + (size_t)gene * p.h + c;
@@ -996,10 +1101,14 @@ k_dec3w(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUten
         if (lane == 0) mbar_arrive(d2_empty);
         ++segE;
       }
+      if (++ct == n_ct) { ct = 0; ++slab; }
+      if (++s == W3_NST) { s = 0; sph ^= 1; }
     }
+    w3_stamp_cta(p.trace, 3);
   }
   tc_fence_before();
   __syncthreads();
+  w3_stamp_cta(p.trace, 4);
   if (warp == N_EPI_WARPS + 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -1234,6 +1343,10 @@ void tc_decoder_backward(const TcDecoderArgs& a, cudaStream_t st) {
       return;
     }
     const int n_tiles = ((a.G + W3_SLAB - 1) / W3_SLAB) * ((a.B + W3_BM - 1) / W3_BM);
+    if (getenv("DRV_W3_TRACE")) {
+      void* sym = nullptr;
+      if (cudaGetSymbolAddress(&sym, g_w3_trace) == cudaSuccess) p.trace = (const unsigned long long*)sym;
+    }
     drv_internal_kmark(2, 0, st);
     cudaFuncSetAttribute(k_dec3w, cudaFuncAttributeMaxDynamicSharedMemorySize, W3_SMEM);
     launch_k_plain(k_dec3w, n_tiles < sm_count() ? n_tiles : sm_count(), NTHREADS, W3_SMEM, st, tA64, tW1, tD64, p, a.dW);
@@ -1272,3 +1385,11 @@ void tc_decoder_backward(const TcDecoderArgs& a, cudaStream_t st) {
 }
 
 }  // namespace drv
+
+// debug: timeline stamps of k_dec3w's CTA 0 (DRV_W3_TRACE=1); returns the number of values copied
+extern "C" int drv_debug_w3_trace(unsigned long long* host, int n) {
+  const int m = drv::W3_TRACE_TILES * drv::W3_TRACE_EVENTS;
+  if (n > m) n = m;
+  if (cudaMemcpyFromSymbol(host, drv::g_w3_trace, sizeof(unsigned long long) * (size_t)n) != cudaSuccess) return -1;
+  return n;
+}

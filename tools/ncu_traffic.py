@@ -9,6 +9,7 @@ behind k_dec<3>: dAct, dW) go to profiles/ncu_traffic.json together with a hash 
 checks before it reports `roofline.traffic` (a capture of other sources is refused)."""
 import collections
 import csv
+import re
 import json
 import os
 import sys
@@ -33,9 +34,14 @@ for r in rows:
     else:
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
         ent[name] = v * scale
+# the last complete step of the capture (between the last two k_finalize_step launches): the warm one
+items = list(launch.items())
+fin = [i for i, (_, e) in enumerate(items) if 'k_finalize_step' in e['name']]
+if len(fin) >= 2:
+    items = items[fin[-2] + 1:fin[-1] + 1]
 out_lines = []
-dec, after3, tot_us, tot_b = {}, 0, 0.0, 0.0
-for k, e in launch.items():
+dec, after2, seen, tot_us, tot_b = {}, False, set(), 0.0, 0.0
+for k, e in items:
     b = e.get("dram__bytes_read.sum", 0.0) + e.get("dram__bytes_write.sum", 0.0)
     tot_us += e.get("us", 0.0)
     tot_b += b
@@ -45,12 +51,19 @@ for k, e in launch.items():
     for ph in (1, 2, 3):
         if f"k_dec<{ph}," in n or f"k_dec<(int){ph}" in n:
             dec[f"k_dec<{ph}>"] = b
-            if ph == 3:
-                after3 = 1
-    if "k_tc_gemm" in n and after3 in (1, 2) and "k_dec<3>" in dec:
-        dec["dAct" if after3 == 1 else "dW"] = b
-        after3 += 1
-out_lines.append(f"step total {tot_us:.1f} us (serialised, cold caches), {tot_b / 1e6:.1f} MB DRAM traffic, {len(launch)} launches")
+            if ph == 2:
+                after2, seen = True, set()
+    if "k_dec3w" in n:
+        dec["k_dec3w"] = b
+    mm = re.search(r"k_tc_gemm<\(?(?:bool\))?(\d), \(?(?:bool\))?(\d),", n)
+    if mm and after2:
+        # behind phase 2: the first GEMM with both operands MN-major is the decoder's dW (log_r half when k_dec3w runs),
+        # the first K-major x MN-major one is dAct
+        kind = "dW" if mm.group(1) == "1" and mm.group(2) == "1" else ("dAct" if mm.group(1) == "0" and mm.group(2) == "1" else None)
+        if kind and kind not in seen:
+            dec[kind] = b
+            seen.add(kind)
+out_lines.append(f"step total {tot_us:.1f} us (serialised, cold caches), {tot_b / 1e6:.1f} MB DRAM traffic, {len(items)} launches")
 text = "\n".join(out_lines)
 print(text)
 if len(sys.argv) > 3:
