@@ -46,7 +46,15 @@ SideStream* side_stream() {
   static thread_local bool tried = false;
   if (!tried) {
     tried = true;
-    if (cudaStreamCreateWithFlags(&ss.side, cudaStreamNonBlocking) != cudaSuccess ||
+    // high priority: the side stream's kernels are short (operand conversions at the start of the step, the dose-response
+    // head) or small grids (trunk weight gradients); without it the block scheduler drains every CTA of a full-machine
+    // main-stream kernel first (timeline: the encoder weight split waited 12 us behind the statistics pass of x and the
+    // encoder forward waited for the split).  DRV_SIDE_PRIORITY=0 restores the default priority.
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    const char* pe = getenv("DRV_SIDE_PRIORITY");
+    const int prio = (pe && atoi(pe) == 0) ? prio_lo : prio_hi;
+    if (cudaStreamCreateWithPriority(&ss.side, cudaStreamNonBlocking, prio) != cudaSuccess ||
         cudaEventCreateWithFlags(&ss.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ss.ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ss.ev_aux, cudaEventDisableTiming) != cudaSuccess ||
@@ -565,6 +573,16 @@ static int elbo_step_core(const drv_dims* dims, const drv_hparams* hp, const flo
       side->join(st);
       side->used = true;  // the rest of the start-up work stays behind on the side stream (joined after the sampling)
     }
+    enc_sd0 = enc_sd_;
+  }
+  // Start-of-step work the DECODER needs (tf32 parts / fp16 copy of its weights, the cleared gradient buffers): queued on
+  // the side stream BEHIND the encoder input layer, so that it runs next to the small grids of the encoder trunk.
+  // Submitted at the start it delayed the encoder forward by 8 us: the block scheduler drains the CTAs of earlier
+  // submitted kernels first, and the gradient memset competed with the x tiles for HBM (profiles/r02_graph_timeline_*.txt).
+  auto late_prep = [&]() {
+    cudaStream_t ss = st;
+    if (side) { side->fork(st); ss = side->side; }
+    const size_t enc_floats = (size_t)n.dec[0].gamma;
     if (tc_any)
       split_params_tf32(params + enc_floats, (size_t)n.n_param_floats - enc_floats, c.at<float>(p.p_hi) + enc_floats,
                         c.at<float>(p.p_lo) + enc_floats, ss);
@@ -578,11 +596,13 @@ static int elbo_step_core(const drv_dims* dims, const drv_hparams* hp, const flo
       // d loss / d (last decoder activation): split-K accumulation target of the fused decoder backward
       if (dec_tc) cudaMemsetAsync(c.at<float>(p.Gb[1][NB - 1]), 0, sizeof(float) * (size_t)B * n.dec[NB - 1].din, ss);
     }
-    enc_sd0 = enc_sd_;
-  }
+  };
   bool enc_sd = enc_sd0;
   // ---- guide: encoder + reparameterised draws (nbvae.py:81-90) --------------------------------
-  for (int k = 0; k < NB; ++k) enc_sd = block_forward(c, 0, k, x, true, enc_sd);
+  for (int k = 0; k < NB; ++k) {
+    enc_sd = block_forward(c, 0, k, x, true, enc_sd);
+    if (k == 0) late_prep();
+  }
   const float* O = c.at<float>(p.V[0][NB - 1]);
   float* z = c.at<float>(p.z);
   float* l = c.at<float>(p.l);

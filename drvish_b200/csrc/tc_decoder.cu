@@ -1330,12 +1330,6 @@ void tc_decoder_backward(const TcDecoderArgs& a, cudaStream_t st) {
   cudaStream_t ws = st;
   int rc = 0;
   if (fused) {
-    // the log_r half of d logits is final since phase 2: its weight gradient dW[G + g][i] = sum_b drho[b][g] act[b][i]
-    // (both operands MN-major, K = cells) starts on the side stream right away, next to the fused kernel
-    if (a.side) { a.side->mark(st); a.side->attach(); ws = a.side->side; }
-    drv_internal_kmark(4, 0, ws);
-    rc = gemm_f16(dl_h + a.G, 2 * a.G, true, s.act_h, a.h, true, a.dW + (size_t)a.G * a.h, a.h, a.G, a.h, a.B, 0, true, alpha, ws);
-    drv_internal_kmark(4, 1, ws);
     // scale half: softmax coupling + weight gradient in one kernel, gene-major walk
     CUtensorMap tA64, tD64;
     if (!tmap_2d_h(&tA64, s.act_h, a.B, a.h, a.h, W3_BM, 64) || !tmap_2d_h(&tD64, dl_h, a.B, a.G, 2 * (uint64_t)a.G, W3_BM, 64)) {
@@ -1371,7 +1365,20 @@ void tc_decoder_backward(const TcDecoderArgs& a, cudaStream_t st) {
     rc = h16 ? gemm_f16(a.dlogits, 2 * a.G, false, s.W_h, a.h, true, a.dY, a.h, a.B, a.h, 2 * a.G, 0, true, alpha, st)
              : gemm_tf32(a.dlogits, 2 * a.G, false, a.W_hi, a.h, true, a.dY, a.h, a.B, a.h, 2 * a.G, 0, /*accumulate (cleared at step start)=*/true, st);
   drv_internal_kmark(3, 1, st);
-  if (!fused) {
+  if (fused) {
+    // the log_r half of d logits is final since phase 2: dW[G + g][i] = sum_b drho[b][g] act[b][i] (both operands
+    // MN-major, K = cells) is the one weight-gradient GEMM left.  It is full-machine work off the critical chain: forked
+    // BEHIND the dAct GEMM, it runs next to the small grids of the decoder-trunk backward (launched next to k_dec3w it
+    // took 120 SMs for 20 us and stretched that kernel from 34 to 62 us - profiles/r02_graph_timeline_*.txt)
+    if (a.side) { a.side->mark(st); a.side->attach(); ws = a.side->side; }
+    drv_internal_kmark(4, 0, ws);
+    if (rc == 0)
+      // ... on a part of the SMs only when it shares the machine: the trunk's own tensor-core GEMMs (32-CTA grids with a
+      // full SM's shared memory each) need free SMs next to it
+      rc = gemm_f16(dl_h + a.G, 2 * a.G, true, s.act_h, a.h, true, a.dW + (size_t)a.G * a.h, a.h, a.G, a.h, a.B,
+                    a.side ? sm_count() - 56 : 0, true, alpha, ws);
+    drv_internal_kmark(4, 1, ws);
+  } else {
     // dW[j][i] = sum_b dlogits[b][j] act[b][i]   (both operands MN-major, K = cells): off the critical chain
     if (a.side) { a.side->attach(); ws = a.side->side; }
     drv_internal_kmark(4, 0, ws);

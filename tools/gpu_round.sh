@@ -23,8 +23,8 @@ timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_dec -s 9 -c 3 -o $O/${TAG}_kdec -f \
   python tools/prof_step.py 3 5 > $O/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 ncu -i $O/${TAG}_kdec.ncu-rep --page raw --csv > $O/${TAG}_kdec_raw.csv 2>/dev/null
-# compute-sanitizer on the smallest tensor-core case (smoke): mbarrier / TMEM kernels and shared-memory hazards
-for tool in memcheck racecheck synccheck; do
-  timeout 420 compute-sanitizer --tool $tool --print-limit 20 python __graft_entry__.py smoke > $O/${TAG}_sanitizer_$tool.log 2>&1; echo "sanitizer $tool rc=$?"
-  tail -4 $O/${TAG}_sanitizer_$tool.log
-done
+# the same launch list with the caches left alone between kernels (ncu's default flushes them before every kernel, which
+# turns every L2-resident hand-off between two kernels of the step into DRAM reads)
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none -c 600 --csv \
+  --log-file $O/${TAG}_launches_cfg3_warmcache.csv python tools/prof_step.py 3 5 > $O/${TAG}_ncu_list2.log 2>&1; echo "ncu list (cache-control none) rc=$?"
+# (compute-sanitizer is closed on this pool: profiles/r02_sanitizer_unavailable.txt)
