@@ -583,25 +583,47 @@ static int elbo_step_core(const drv_dims* dims, const drv_hparams* hp, const flo
     cudaStream_t ss = st;
     if (side) { side->fork(st); ss = side->side; }
     const size_t enc_floats = (size_t)n.dec[0].gamma;
-    if (tc_any)
-      split_params_tf32(params + enc_floats, (size_t)n.n_param_floats - enc_floats, c.at<float>(p.p_hi) + enc_floats,
-                        c.at<float>(p.p_lo) + enc_floats, ss);
+    if (tc_any) {
+      // the fp16-operand decoder reads its own fp16 copy of the last Linear's weight (2G x h, by far the largest
+      // tensor): its tf32 parts are not needed then
+      static const bool dec_tf32_env = getenv("DRV_DEC_TF32") != nullptr;
+      const Block& lastb = n.dec[NB - 1];
+      const bool skip_last = dec_tc && !dec_tf32_env && G % 8 == 0 && lastb.din >= 64;
+      const size_t w0 = (size_t)lastb.W, w1 = w0 + (size_t)lastb.dout * lastb.din;
+      auto split = [&](size_t a, size_t b) {
+        if (b > a) split_params_tf32(params + a, b - a, c.at<float>(p.p_hi) + a, c.at<float>(p.p_lo) + a, ss);
+      };
+      if (skip_last) {
+        split(enc_floats, w0);
+        split(w1, (size_t)n.n_param_floats);
+      } else {
+        split(enc_floats, (size_t)n.n_param_floats);
+      }
+    }
     if (side && dec_tc) {
       TcDecoderArgs a{};  // fp16 copy of the last decoder weight (joined before the decoder starts)
       a.W = params + n.dec[NB - 1].W; a.B = B; a.G = G; a.h = n.dec[NB - 1].din; a.scratch = c.ws + p.tc;
       dec_w_prepared = tc_decoder_prepare(a, ss);
     }
-    if (bwd) {
-      cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)n.n_param_floats, ss);
-      // d loss / d (last decoder activation): split-K accumulation target of the fused decoder backward
-      if (dec_tc) cudaMemsetAsync(c.at<float>(p.Gb[1][NB - 1]), 0, sizeof(float) * (size_t)B * n.dec[NB - 1].din, ss);
-    }
+  };
+  // ... and the cleared gradient buffers (same place: measured better than behind the sampling, where the memsets sat in
+  // front of the dose-response head on the side stream)
+  auto clear_grads = [&]() {
+    if (!bwd) return;
+    cudaStream_t ss = st;
+    if (side) { side->fork(st); ss = side->side; }
+    cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)n.n_param_floats, ss);
+    // d loss / d (last decoder activation): split-K accumulation target of the fused decoder backward
+    if (dec_tc) cudaMemsetAsync(c.at<float>(p.Gb[1][NB - 1]), 0, sizeof(float) * (size_t)B * n.dec[NB - 1].din, ss);
   };
   bool enc_sd = enc_sd0;
   // ---- guide: encoder + reparameterised draws (nbvae.py:81-90) --------------------------------
   for (int k = 0; k < NB; ++k) {
     enc_sd = block_forward(c, 0, k, x, true, enc_sd);
-    if (k == 0) late_prep();
+    if (k == 0) {
+      late_prep();
+      clear_grads();
+    }
   }
   const float* O = c.at<float>(p.V[0][NB - 1]);
   float* z = c.at<float>(p.z);
@@ -609,7 +631,7 @@ static int elbo_step_core(const drv_dims* dims, const drv_hparams* hp, const flo
   sample_forward(O, eps_z, eps_l, B, L, *hp, z, l, out, st);
   prof::mark(1, st);
 
-  if (side) side->join(st);  // decoder weights' tf32 parts, cleared gradients
+  if (side) side->join(st);  // decoder weights' tf32 parts / fp16 copy, cleared gradients
   // ---- dose-response head (drnbvae.py:110-116, 131-132): needs only z, runs on the side stream
   // concurrently with the decoder; joined before the sampling backward consumes dz_drs
   DrShape ds{B, L, d.n_drugs, d.n_classes, d.n_doses_total};
