@@ -146,16 +146,18 @@ extern "C" int drv_comm_free(void* base) { return base ? (int)cudaFree(base) : 0
 namespace drv {
 
 // launch of one (slice of an) all-reduce; max_ctas > 0 caps the grid (a collective that runs NEXT TO compute kernels)
-int peer_allreduce_launch(const Peers& p, int rank, int world, long long off4, long long n4, int max_ctas, cudaStream_t st) {
+// threads: 512, or 256 for a slice that has to fit NEXT TO a persistent compute kernel (registers of the SM)
+int peer_allreduce_launch(const Peers& p, int rank, int world, long long off4, long long n4, int max_ctas, cudaStream_t st,
+                          int threads = 512) {
   const long long per = (n4 + world - 1) / world;
-  int grid = (int)((per + 511) / 512);
+  int grid = (int)((per + threads - 1) / threads);
   if (grid > 148) grid = 148;  // one wave: every CTA must be able to poll the flags
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if (grid < 1) grid = 1;
   switch (world) {
-    case 2: launch_k_plain(k_peer_allreduce<2>, grid, 512, 0, st, p, rank, off4, n4); break;
-    case 4: launch_k_plain(k_peer_allreduce<4>, grid, 512, 0, st, p, rank, off4, n4); break;
-    case 8: launch_k_plain(k_peer_allreduce<8>, grid, 512, 0, st, p, rank, off4, n4); break;
+    case 2: launch_k_plain(k_peer_allreduce<2>, grid, threads, 0, st, p, rank, off4, n4); break;
+    case 4: launch_k_plain(k_peer_allreduce<4>, grid, threads, 0, st, p, rank, off4, n4); break;
+    case 8: launch_k_plain(k_peer_allreduce<8>, grid, threads, 0, st, p, rank, off4, n4); break;
     default: return DRV_EINVAL;
   }
   note_launch();
@@ -177,9 +179,9 @@ bool comm_bound(const float* grads, long long n_floats_needed) {
          g_comm.n_floats >= n_floats_needed;
 }
 
-int comm_allreduce_slice(long long off_floats, long long n_floats, int max_ctas, cudaStream_t st) {
-  if (!g_comm.on || (off_floats & 3)) return DRV_EINVAL;
-  return peer_allreduce_launch(g_comm.p, g_comm.rank, g_comm.world, off_floats / 4, (n_floats + 3) / 4, max_ctas, st);
+int comm_allreduce_slice(long long off_floats, long long n_floats, int max_ctas, cudaStream_t st, int threads) {
+  if (!g_comm.on || (off_floats & 3) || (threads != 256 && threads != 512)) return DRV_EINVAL;
+  return peer_allreduce_launch(g_comm.p, g_comm.rank, g_comm.world, off_floats / 4, (n_floats + 3) / 4, max_ctas, st, threads);
 }
 
 }  // namespace drv

@@ -362,8 +362,9 @@ bool block_forward(const Ctx& c, int s, int k, const float* U0, bool do_linear, 
 // reduced to d gamma / d beta on the fly.
 // dv_prepared: the block above already left this block's tf32-rounded dV and bias gradient
 // (bn_bwd_apply_round).  Returns whether this block did the same for block k - 1.
+// tc_part (tensor-core block only): 0 = everything, 1 = weight gradient only, 2 = the rest after a part-1 call.
 bool block_backward(const Ctx& c, int s, int k, const float* U0, const float* dV, bool linear_done,
-                    bool dv_prepared = false) {
+                    bool dv_prepared = false, int tc_part = 0) {
   bool gated = false;  // Gb holds the ungated dAct: the BatchNorm backward kernels apply the ReLU gate
   const int B = c.d.n_cells;
   const Block& b = s == 0 ? c.n.enc[k] : c.n.dec[k];
@@ -381,8 +382,10 @@ bool block_backward(const Ctx& c, int s, int k, const float* U0, const float* dV
       a.dY = sq ? nullptr : c.at<float>(c.p.Gb[s][k]); a.gacc = gacc; a.side = c.side;
       a.no_fused_prologue = (c.hp.flags & 512) != 0;
       a.dv_prepared = dv_prepared;
+      a.part = tc_part;
       tc_block_backward(a, c.st);
       gated = false;
+      if (tc_part == 1) return false;
     } else {
       // the weight gradient is off the critical chain: side stream
       cudaStream_t ws = c.st;
@@ -523,6 +526,7 @@ static int elbo_step_core(const drv_dims* dims, const drv_hparams* hp, const flo
   // (and the loss / status tail slots) is final before the encoder backward starts - it is all-reduced on the side
   // stream by a few CTAs next to the encoder backward; the encoder slice follows at the end of the step.
   const bool fused_ar = bwd && (hp->flags & DRV_FLAG_FUSED_ALLREDUCE);
+  long long ar_tail_floats = 0;  // what the collective at the end of the step still has to reduce: [0, ar_tail_floats)
   if (fused_ar && (part2_only || stop_after_decoder || !side || !comm_bound(grads, n.n_param_floats + DRV_GRAD_TAIL_FLOATS)))
     return DRV_EINVAL;
   if (part2_only) {
@@ -661,6 +665,7 @@ static int elbo_step_core(const drv_dims* dims, const drv_hparams* hp, const flo
 
   // ---- model: decoder trunk (nbvae.py:70 -> modules.py:93) ------------------------------------
   const Block& last = n.dec[NB - 1];
+  ar_tail_floats = last.W;
   const bool use_tc = tc_decoder_supported(d, *hp) && !(hp->flags & 16);
   // drv_step_out.path: bit 0 = tcgen05 decoder kernels, bit 1 = tcgen05 encoder input layer
   const uint32_t path = (use_tc ? 1u : 0u) |
@@ -740,14 +745,39 @@ static int elbo_step_core(const drv_dims* dims, const drv_hparams* hp, const flo
       return finish();
     }
     // ---- encoder backward ----------------------------------------------------------------------
-    for (int k = NB - 1, eprep = 0; k >= 0; --k)
-      eprep = block_backward(c, 0, k, x, k == NB - 1 ? c.at<float>(p.dO) : c.at<float>(p.Gb[0][k + 1]), false, eprep);
+    // Data parallel, collective inside the step - opt-in tail split (DRV_AR_TAIL_SPLIT=1): the input layer's WEIGHT gradient
+    // (G x h: nearly all of the encoder's gradient bytes) first, on the main stream; [encoder input weight, last decoder
+    // weight) is then all-reduced on the comm stream by 256-thread CTAs that fit next to the persistent CTAs of the input
+    // BatchNorm's gradient kernel, which follows; only that kernel's 2 G floats are left for the collective at the end.
+    // Measured at 2 GPUs (profiles/r02_dp_timeline_2gpu.txt): the mid slice does overlap, but the last collective costs
+    // 25 us however small it is (two flag round trips + the wait for the slower rank; 39 us with the 6 MB encoder slice),
+    // and the weight-gradient path no longer runs next to the BatchNorm-gradient kernel (+17 us): 0.705 vs 0.650 ms.
+    const bool enc0_tc = p.tcb[0][0] && tc_block_backward_supported(B, n.enc[0].din, n.enc[0].dout, *hp) && !(hp->flags & 32);
+    static const bool tail_split_on = getenv("DRV_AR_TAIL_SPLIT") != nullptr && atoi(getenv("DRV_AR_TAIL_SPLIT")) == 1;
+    const bool tail_split = fused_ar && enc0_tc && NB >= 2 && tail_split_on;
+    for (int k = NB - 1, eprep = 0; k >= 0; --k) {
+      const float* dVk = k == NB - 1 ? c.at<float>(p.dO) : c.at<float>(p.Gb[0][k + 1]);
+      if (k == 0 && tail_split) {
+        Ctx cm = c;
+        cm.side = nullptr;  // weight gradient on the main stream
+        block_backward(cm, 0, 0, x, dVk, false, eprep, 1);
+        side->join(st);       // the trunk weight gradients queued on the side stream
+        side->comm_fork(st);  // (the comm stream runs its collectives in order: this one behind the decoder slice)
+        static const int mid_ctas = getenv("DRV_AR_MID_CTAS") ? atoi(getenv("DRV_AR_MID_CTAS")) : 96;
+        const int rc = comm_allreduce_slice(n.enc[0].W, last.W - n.enc[0].W, mid_ctas, side->comm, 256);
+        if (rc != 0) return rc;
+        block_backward(c, 0, 0, x, dVk, false, true, 2);
+        ar_tail_floats = n.enc[0].W;
+        break;
+      }
+      eprep = block_backward(c, 0, k, x, dVk, false, eprep);
+    }
     prof::mark(7, st);
   }
   if (fused_ar) {
     side->join(st);
     side->comm_join(st);  // the two collectives share the flag words: strictly one after the other on every rank
-    const int rc = comm_allreduce_slice(0, last.W, 0, st);
+    const int rc = comm_allreduce_slice(0, ar_tail_floats, 0, st);
     if (rc != 0) return rc;
     if (prof::enabled && prof::n_steps < prof::MAX_STEPS) ++prof::n_steps;
     return finish();

@@ -94,6 +94,7 @@ struct TcBlockArgs {
   const ColStatsOut* next_stats;  // optional: BatchNorm statistics of V for the next block
   bool dv_prepared;   // backward: the tf32-rounded dV and the bias gradient were already produced (bn_bwd_apply_round)
   bool w_prepared;    // tc_block_prepare already left the fp16 hi / lo parts of W in the scratch
+  int part;           // backward: 0 = everything, 1 = weight gradient only, 2 = everything but the weight gradient (after part 1)
 };
 // where tc_block_backward expects the tf32-rounded dV of a block ([B][dout])
 float* tc_block_rounded_dv(void* scratch, int B, int din, int dout);

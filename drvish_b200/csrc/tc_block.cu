@@ -289,7 +289,8 @@ void tc_block_backward(const TcBlockArgs& a, cudaStream_t st) {
   int rb = (int)((nd + 255) / 256);
   if (rb > n_sm() * 2) rb = n_sm() * 2;
   (void)rb;
-  if (!a.dv_prepared) {
+  const bool do_wgrad = a.part != 2, do_dgrad = a.part != 1;
+  if (!a.dv_prepared && a.part != 2) {
     // one pass over dV: tf32-rounded copy (MMA operand) + column sums (bias gradient)
     dim3 cb(32, 8);
     int rows = 64;
@@ -303,7 +304,8 @@ void tc_block_backward(const TcBlockArgs& a, cudaStream_t st) {
   float* dA = a.dY ? a.dY : s.a_lo;  // the first encoder block reuses the A_lo buffer
   int rc = 0;
   const bool fused_bn0 = !a.dY && a.sqrt_in && !a.no_fused_prologue && a.din % 4 == 0 && a.dout % 4 == 0;
-  if (fused_bn0) {
+  if (!do_dgrad) {
+  } else if (fused_bn0) {
     // encoder input layer: dA is never stored - transposed GEMM with the reduction over the batch
     // inside the epilogue threads
     rc = tc::bn0grad_fused(s.dh_r, a.W_hi, a.U, a.B, a.din, a.dout, a.bn, a.gacc, st);
@@ -313,7 +315,7 @@ void tc_block_backward(const TcBlockArgs& a, cudaStream_t st) {
   // dW[j][i] = sum_b dV[b][j] A[b][i]: both operands MN-major (K = cells): off the critical chain
   cudaStream_t ws = st;
   if (a.side) { a.side->attach(); ws = a.side->side; }
-  if (rc == 0) {
+  if (rc == 0 && do_wgrad) {
     if (fused_prologue_h16(a)) {
       // the forward left the fp16 hi part of the activations in a_hi: dynamically scaled fp16 copy of dV
       // (the a_lo scratch is free: [scale words | fp16 dV]), fp16 GEMM with the inverse scale as alpha
@@ -335,7 +337,7 @@ void tc_block_backward(const TcBlockArgs& a, cudaStream_t st) {
     }
   }
   if (rc != 0 && g_err == cudaSuccess) g_err = cudaErrorInvalidValue;
-  if (a.dY || fused_bn0) return;  // (the ReLU gate is applied by the BatchNorm backward kernels)
+  if (a.dY || fused_bn0 || !do_dgrad) return;  // (the ReLU gate is applied by the BatchNorm backward kernels)
   // reduce dA to the input-BatchNorm gradients (gate and xhat recomputed from sqrt(x))
   int col_blocks = (a.din + CW * 4 - 1) / (CW * 4);
   int S = (n_sm() * 8 + col_blocks - 1) / col_blocks;
