@@ -179,6 +179,8 @@ bool comm_bound(const float* grads, long long n_floats_needed) {
          g_comm.n_floats >= n_floats_needed;
 }
 
+int comm_world() { return g_comm.on ? g_comm.world : 1; }
+
 int comm_allreduce_slice(long long off_floats, long long n_floats, int max_ctas, cudaStream_t st, int threads) {
   if (!g_comm.on || (off_floats & 3) || (threads != 256 && threads != 512)) return DRV_EINVAL;
   return peer_allreduce_launch(g_comm.p, g_comm.rank, g_comm.world, off_floats / 4, (n_floats + 3) / 4, max_ctas, st, threads);

@@ -103,6 +103,7 @@ void pad_rows(const float* x, int B, int G, int Gp, float* xp, cudaStream_t st);
 bool comm_bound(const float* grads, long long n_floats_needed);
 // all-reduce of floats [off, off + n) of the bound buffer on `st`; max_ctas > 0 caps the grid
 int comm_allreduce_slice(long long off_floats, long long n_floats, int max_ctas, cudaStream_t st, int threads = 512);
+int comm_world();  // ranks of the bound peer all-reduce (1 when none is bound)
 
 // ---- k_optim.cu ------------------------------------------------------------------------------------
 int aggmo_step(const long long* offs, const long long* lens, int n_tensors, const drv_aggmo& hp, float* params,
