@@ -179,15 +179,20 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
   // count tile is released by the epilogue warps, the output buffer by the store warp (o_empty)
   constexpr bool X_BY_STORE = TSTORE && !(H16 && PHASE == 2);
   constexpr int BKE = H16 ? 64 : BK;  // operand elements per k-block (one 128-byte swizzle row)
+  // TMEM accumulator stages.  Four stages in phase 2 (all 512 columns, the MMAs two to three tiles ahead of the epilogue)
+  // were tried because 48 % of the warp-tiles enter the spin loop on acc_full (ncu source page): no change, 110.3 us -
+  // the polls are cheap, the epilogue's own instruction stream is the bound.
+  constexpr int NACC = 2;
+  constexpr int TM_COLS = NACC * 128;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* xbuf = smem + NST * KG * STAGE_BYTES;
   uint8_t* rbuf = xbuf + 2 * XB;  // [2][RB]
   uint64_t* full = (uint64_t*)(rbuf + 2 * RB);
   uint64_t* empty = full + NST;
-  uint64_t* acc_full = empty + NST;       // [2]
-  uint64_t* acc_empty = acc_full + 2;     // [2]
-  uint64_t* x_full = acc_empty + 2;       // [2]
+  uint64_t* acc_full = empty + NST;       // [NACC]
+  uint64_t* acc_empty = acc_full + NACC;  // [NACC]
+  uint64_t* x_full = acc_empty + NACC;    // [2]
   uint64_t* x_empty = x_full + 2;         // [2]
   uint64_t* o_full = x_empty + 2;         // [2] output tile complete in shared memory (TSTORE)
   uint64_t* o_empty = o_full + 2;         // [2] output tile read by the TMA store (H16 phase 2)
@@ -212,9 +217,11 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NACC; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], N_EPI_WARPS);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&x_full[s], 1);
       mbar_init(&x_empty[s], X_BY_STORE ? 1 : N_EPI_WARPS);  // released by the store warp / the epilogue warps
       mbar_init(&o_full[s], N_EPI_WARPS);
@@ -222,7 +229,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
     }
     fence_barrier_init();
   }
-  if (warp == N_EPI_WARPS + 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == N_EPI_WARPS + 1) tmem_alloc<TM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -278,7 +285,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
       const uint32_t idesc = H16 ? idesc_f16(BM, 128, 0, 0) : idesc_tf32(BM, 128, 0, 0);
       int kit = 0;
       for (int t = t0, it = 0; t < t1; ++t, ++it) {
-        const int as = it & 1, aph = (it >> 1) & 1;
+        const int as = it % NACC, aph = (it / NACC) & 1;
         swait(&acc_empty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * 128);
@@ -372,7 +379,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
     };
     for (int t = t0, it = 0; t < t1; ++t, ++it) {
       const int ct = t / n_gt, gt = t % n_gt;
-      const int as = it & 1, aph = (it >> 1) & 1;
+      const int as = it % NACC, aph = (it / NACC) & 1;
       if (ct != cur_ct) {
         if (PHASE == 2 && cur_ct >= 0 && row_ok) flush_ll();
         if (PHASE == 1 && cur_ct >= 0 && row_ok) flush_lse(cur_ct, b);
@@ -716,7 +723,7 @@ k_dec(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtenso
   __syncthreads();
   if (warp == N_EPI_WARPS + 1) {
     tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    tmem_dealloc<TM_COLS>(tmem_base);
   }
 }
 
