@@ -64,6 +64,7 @@ _P, _I64P = C.c_void_p, C.POINTER(C.c_int64)
 SYMBOLS = {
     "drv_version": (C.c_char_p, []),
     "drv_last_launch_count": (C.c_int, []),
+    "drv_debug_w3_trace": (C.c_int, [C.POINTER(C.c_ulonglong), C.c_int]),
     "drv_param_offsets": (C.c_int, [C.POINTER(Dims), _I64P, _I64P, C.c_int, _I64P]),
     "drv_bn_offsets": (C.c_int, [C.POINTER(Dims), _I64P, _I64P, C.c_int, _I64P]),
     "drv_workspace_bytes": (C.c_size_t, [C.POINTER(Dims)]),

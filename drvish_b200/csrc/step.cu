@@ -42,14 +42,19 @@ bool pdl_enabled() {
 }
 
 SideStream* side_stream() {
-  static thread_local SideStream ss;
-  static thread_local bool tried = false;
-  if (!tried) {
-    tried = true;
+  // one set of streams / events per (thread, device): a stream belongs to the device that was current when it was
+  // created, and a thread may drive models on several GPUs
+  constexpr int MAX_DEV = 16;
+  static thread_local SideStream pool[MAX_DEV];
+  static thread_local bool tried[MAX_DEV] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return nullptr;
+  SideStream& ss = pool[dev];
+  if (!tried[dev]) {
+    tried[dev] = true;
     // high priority: the side stream's kernels are short (operand conversions at the start of the step, the dose-response
-    // head) or small grids (trunk weight gradients); without it the block scheduler drains every CTA of a full-machine
-    // main-stream kernel first (timeline: the encoder weight split waited 12 us behind the statistics pass of x and the
-    // encoder forward waited for the split).  DRV_SIDE_PRIORITY=0 restores the default priority.
+    // head) or small grids (trunk weight gradients); DRV_SIDE_PRIORITY=0 restores the default priority.  (No effect was
+    // seen inside a captured graph - profiles/r02_graph_timeline_cfg3.txt -; kept for the eager path.)
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     const char* pe = getenv("DRV_SIDE_PRIORITY");

@@ -311,6 +311,7 @@ class PinnedBatchPrefetcher:
         self._host16 = [None] * self.SLOTS     # pinned uint16 staging for on-the-fly packing
         self._ready = [torch.cuda.Event() for _ in range(self.SLOTS)]
         self._consumed = [None] * self.SLOTS   # recorded on the consumer's stream when a slot is handed back
+        self._rest = [[] for _ in range(self.SLOTS)]  # persistent device buffers of the non-count tensors (labels, y)
         self.h2d_bytes = 0
 
     # -- worker side --------------------------------------------------------------------------
@@ -371,7 +372,7 @@ class PinnedBatchPrefetcher:
                     x = x.pin_memory()
                 self._x[slot].copy_(x, non_blocking=True)
                 self.h2d_bytes += 0 if x.is_cuda else 4 * x.numel()
-            rest = [t.to(self.device, non_blocking=True) if torch.is_tensor(t) and not t.is_cuda else t for t in batch[1:]]
+            rest = self._stage_rest(slot, batch[1:])
             self._ready[slot].record(self.stream)
         return [self._x[slot]] + rest
 
@@ -433,9 +434,34 @@ class PinnedBatchPrefetcher:
             self.h2d_bytes += 4 * k * G + n + 8 * esc
             if k and n:
                 self._hyb_meas[slot] = (ev0, ev1, 4 * k * G, 4 * n, pack_s)
-        rest = [t.to(self.device, non_blocking=True) if torch.is_tensor(t) and not t.is_cuda else t for t in batch[1:]]
+        rest = self._stage_rest(slot, batch[1:])
         self._ready[slot].record(self.stream)
         return [dst] + rest
+
+    def _stage_rest(self, slot: int, items) -> list:
+        """The non-count tensors of a batch (labels, y, ...) go into per-slot PERSISTENT device buffers, guarded by the same
+        ready / consumed events as the count tile: a tensor allocated here (on the copy stream) and dropped by the
+        consumer could be handed back to this stream by the caching allocator and overwritten while step kernels still
+        read it; fixed addresses also keep the CUDA-graph keys of ``FusedTraceELBO`` stable.  Called on the copy stream."""
+        store = self._rest[slot]
+        pos = [0]
+
+        def put(t):
+            if isinstance(t, (list, tuple)):
+                return type(t)(put(u) for u in t)
+            if not torch.is_tensor(t) or t.is_cuda:
+                return t
+            i = pos[0]
+            pos[0] += 1
+            if i >= len(store):
+                store.append(None)
+            buf = store[i]
+            if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+                buf = store[i] = torch.empty(t.shape, dtype=t.dtype, device=self.device)
+            buf.copy_(t, non_blocking=True)
+            return buf
+
+        return [put(t) for t in items]
 
     def _worker(self, free: threading.Semaphore, out_q: "queue.Queue"):
         try:

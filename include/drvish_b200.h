@@ -282,9 +282,14 @@ int drv_profile_enable(int on);
 int drv_profile_read(float* h_ms_per_section, int* h_n_steps);
 /* Event pairs around single kernels of the fused decoder path (mean milliseconds per launch):
  * 0 = phase 1 (logsumexp), 1 = phase 2 (NB likelihood [+ NB part of dlogits]), 2 = phase 3 (softmax
- * coupling), 3 = dAct GEMM, 4 = dW GEMM.  0 when the kernel did not run. */
+ * coupling; hidden width <= 256: the fused coupling + weight-gradient kernel k_dec3w), 3 = dAct GEMM,
+ * 4 = dW GEMM (with k_dec3w: the log_r half only).  0 when the kernel did not run. */
 #define DRV_N_PROFILED_KERNELS 5
 int drv_profile_read_kernels(float* h_ms_per_kernel);
+
+/* Debug: %globaltimer stamps of k_dec3w's first CTA (and entry / exit of three CTAs), written while the environment
+ * variable DRV_W3_TRACE is set; 24 x 10 values, layout in tools/w3_trace.py.  Returns the number of values copied. */
+int drv_debug_w3_trace(unsigned long long* h_stamps, int n);
 
 /* Number of kernels the last drv_* call on this thread enqueued (for bench.py's gpu_launches). */
 int drv_last_launch_count(void);

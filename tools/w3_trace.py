@@ -26,7 +26,6 @@ torch.cuda.synchronize()
 lib = _lib.load()
 T, E = 24, 10
 buf = (C.c_ulonglong * (T * E))()
-lib.drv_debug_w3_trace.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]
 n = lib.drv_debug_w3_trace(buf, T * E)
 v = [buf[i] for i in range(n)]
 t0 = min(x for x in v if x)
