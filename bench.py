@@ -411,8 +411,9 @@ class Workload:
             return "two-part step, NCCL all-reduces overlapping the encoder backward"
         if self.elbo._peer.get(id(self.rt)) is not None:
             if self.elbo.dp_fused and not self.rt.shape_padded(self.cfg["batch"]):
-                return ("k_peer_allreduce over NVLink peer memory, launched by the step itself: decoder slice on the side "
-                        "stream next to the encoder backward, encoder slice at the end (k_comm.cu, DRV_FLAG_FUSED_ALLREDUCE)")
+                return ("k_peer_allreduce over NVLink peer memory, launched by the step itself inside its CUDA graph: slice "
+                        "[last decoder weight .. loss/status tail] on a comm stream (32 CTAs) next to the trunk backward, the "
+                        "rest at the end of the step (k_comm.cu, DRV_FLAG_FUSED_ALLREDUCE)")
             return "drv_peer_allreduce: one kernel over NVLink peer memory per step (k_comm.cu)"
         return "one NCCL all-reduce per step"
 
