@@ -52,7 +52,6 @@ constexpr int SMEM_BYTES = 3 * STAGE_BYTES + 4 * X_BYTES + 1024 + 1024;
 constexpr int SMEM_SMALL = STAGES * STAGE_BYTES + 2 * X_BYTES + 1024 + 1024;
 static_assert(SMEM_SMALL >= 2 * STAGE_BYTES + 4 * X_BYTES + 1024 + 1024, "phase 3 layout");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
-constexpr int TMEM_COLS = 256;
 // fp16-operand variant (H16): act, W and d loss/d logits are stored as fp16 - the same 10-bit mantissa
 // as the tf32 operands they replace, half the bytes through HBM / L2 / shared memory, 64-element
 // k-blocks (half the pipeline hand-shakes) and twice the MMA rate.  d logits is stored divided by the
@@ -758,16 +757,6 @@ constexpr int W3_SMEM = W3_WBYTES + W3_NST * (W3_ABYTES + W3_DBYTES + W3_CBYTES)
 static_assert(W3_SMEM <= 227 * 1024, "shared memory");
 constexpr int W3_D2_COL = 128;               // TMEM column of the dW accumulator (D1 stages at 0 and 64)
 
-__device__ __forceinline__ float lds_h(uint32_t a) {
-  unsigned short v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
-  return __half2float(__ushort_as_half(v));
-}
-__device__ __forceinline__ unsigned short lds_u16(uint32_t a) {
-  unsigned short v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
-  return v;
-}
 template <int OFF>
 __device__ __forceinline__ unsigned short lds_u16_off(uint32_t a) {
   unsigned short v;
@@ -785,11 +774,6 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
-}
-__device__ __forceinline__ void sts_h_sat(uint32_t a, float f) {
-  unsigned short v;
-  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(v) : "f"(f));
-  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(v) : "memory");
 }
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
