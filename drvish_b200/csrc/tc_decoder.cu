@@ -9,9 +9,11 @@
 //            training: the NB part of d loss/d logits (ds', drho) leaves in the same pass through
 //            shared-memory tiles and TMA stores
 //   phase 3  recompute the scale-half tile, add the softmax coupling ds = ds' + A[b] softmax(s) in place
-//            to the TMA-staged ds' tile, TMA store, bias gradient; dW = dlogits^T act
-//            and dAct = dlogits W then run as tcgen05 GEMMs that read dlogits / act / W in the layouts
-//            they already have (MN-major descriptors, tc_gemm.cu).
+//            to the TMA-staged ds' tile, TMA store, bias gradient.
+//            Hidden width <= 256 (k_dec3w, below): the same kernel feeds the finished tile, still in shared memory,
+//            into the weight-gradient MMA dW = ds^T act (gene-major walk, accumulator in TMEM); otherwise (k_dec<3>)
+//            dW = dlogits^T act is a tcgen05 GEMM.  dAct = dlogits W and the log_r half of dW are GEMMs that read
+//            dlogits / act / W in the layouts they already have (MN-major descriptors, tc_gemm.cu).
 //
 // Reference arithmetic: NBDecoder.forward modules.py:93-96, "obs" site nbvae.py:72-78.
 // Persistent CTAs (one per SM), 19 warps: 16 epilogue warps (4 per TMEM lane quarter, each a
