@@ -17,6 +17,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <atomic>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -139,13 +140,21 @@ class Pool {
     for (auto& t : th_) t.join();
   }
   int size() const { return (int)th_.size(); }
+  // Tasks are PULLED (atomic counter), not dealt out: a worker whose core is taken by another thread of the process
+  // (the Python main thread polls the GPU, the prefetcher's worker issues copies) does not hold its share back, the
+  // others take it over; the calling thread works too.
   void run(int n_tasks, const std::function<void(int)>& fn) {
-    std::unique_lock<std::mutex> g(m_);
-    fn_ = &fn;
-    n_tasks_ = n_tasks;
-    pending_ = (int)th_.size();
-    ++epoch_;
+    {
+      std::unique_lock<std::mutex> g(m_);
+      fn_ = &fn;
+      n_tasks_ = n_tasks;
+      next_.store(0, std::memory_order_relaxed);
+      pending_ = (int)th_.size();
+      ++epoch_;
+    }
     cv_.notify_all();
+    for (int k; (k = next_.fetch_add(1, std::memory_order_relaxed)) < n_tasks;) fn(k);
+    std::unique_lock<std::mutex> g(m_);
     done_.wait(g, [this] { return pending_ == 0; });
   }
 
@@ -163,7 +172,8 @@ class Pool {
         fn = fn_;
         n_tasks = n_tasks_;
       }
-      for (int k = t; k < n_tasks; k += (int)th_.size()) (*fn)(k);
+      (void)t;
+      for (int k; (k = next_.fetch_add(1, std::memory_order_relaxed)) < n_tasks;) (*fn)(k);
       {
         std::lock_guard<std::mutex> g(m_);
         if (--pending_ == 0) done_.notify_one();
@@ -175,6 +185,7 @@ class Pool {
   std::condition_variable cv_, done_;
   const std::function<void(int)>* fn_ = nullptr;
   int n_tasks_ = 0, pending_ = 0;
+  std::atomic<int> next_{0};
   uint64_t epoch_ = 0;
   bool stop_ = false;
 };
@@ -193,7 +204,7 @@ extern "C" int64_t drv_host_pack_counts_u8(const float* h_src, uint8_t* h_dst, i
     return -1;
   static const PackFn fn = pick();
   if (n_threads < 1) n_threads = 1;
-  const int64_t min_chunk = 1 << 16;
+  const int64_t min_chunk = 1 << 15;
   int n_tasks = (int)((n + min_chunk - 1) / min_chunk);
   if (n_tasks < 1) n_tasks = 1;
   std::lock_guard<std::mutex> serial(g_pool_mutex);
@@ -202,7 +213,7 @@ extern "C" int64_t drv_host_pack_counts_u8(const float* h_src, uint8_t* h_dst, i
     g_pool = new Pool(n_threads);
   }
   // slices of whole 64-byte output lines, a few per thread so that a slow core does not hold the others up
-  const int want = n_threads > 1 ? 4 * n_threads : 1;
+  const int want = n_threads > 1 ? 8 * n_threads : 1;
   if (n_tasks > want) n_tasks = want;
   const int64_t chunk = ((n + n_tasks - 1) / n_tasks + 63) / 64 * 64;
   std::vector<Escapes> esc((size_t)n_tasks);

@@ -387,16 +387,26 @@ class PinnedBatchPrefetcher:
         B, G = x.shape
         if self._x[slot] is None or tuple(self._x[slot].shape) != (B, G):
             self._x[slot] = torch.empty(B, G, dtype=torch.float32, device=self.device)
-        # fold in the rates measured for this slot's previous tile (its events have long completed)
+        # fold in the rates measured for this slot's previous tile (its events have long completed).  Both paths end on
+        # the same bus: with a = bus rate, b = packing rate (both in fp32 source bytes per second) and c = packed bytes per
+        # source byte, the bus carries (f + (1 - f) c) S / a per tile and the packer (1 - f) S / b; they balance at
+        #     f = (a - c b) / ((1 - c) b + a)        (0 when the bus is slower than the packer's output, c b >= a).
+        # (The first version balanced f S / a against (1 - f) S / b, without the packed rows' own bus time: 48 MB per step
+        # at cfg 3; with it 40 MB.  Measured next to a running step the packer reaches ~70 GB/s - 110 GB/s alone - and the
+        # bus ~45 GB/s, so both paths take ~0.9 ms per 82 MB tile: e2e 3.5 - 4.0 M cells/s either way.)
         m = self._hyb_meas[slot]
         if m is not None:
-            ev0, ev1, dma_bytes, pack_bytes, pack_s = m
+            ev0, ev1, dma_bytes, pack_bytes, pack_s, packed_bytes = m
             if dma_bytes and pack_bytes and ev1.query():
-                dma_s = max(ev0.elapsed_time(ev1) * 1e-3, 1e-6)
-                f = (dma_bytes / dma_s) / (dma_bytes / dma_s + pack_bytes / max(pack_s, 1e-6))
-                self.hybrid_fraction = min(0.9, max(0.0, 0.5 * self.hybrid_fraction + 0.5 * f))
+                a = dma_bytes / max(ev0.elapsed_time(ev1) * 1e-3, 1e-6)
+                b = pack_bytes / max(pack_s, 1e-6)
+                c = packed_bytes / pack_bytes
+                f = max(0.0, (a - c * b) / ((1.0 - c) * b + a))
+                self.hybrid_fraction = min(0.9, 0.5 * self.hybrid_fraction + 0.5 * f)
             self._hyb_meas[slot] = None
-        k = int(self.hybrid_fraction * B) // 4 * 4  # rows that travel as fp32 (a multiple of 4 keeps the rest 16-byte aligned)
+        # rows that travel as fp32 (a multiple of 4 keeps the rest 16-byte aligned; never none, so that the bus rate keeps
+        # being measured)
+        k = min(B, max(int(self.hybrid_fraction * B) // 4 * 4, 64)) if B >= 128 else 0
         dst = self._x[slot]
         ev0 = ev1 = None
         if k:
@@ -433,7 +443,7 @@ class PinnedBatchPrefetcher:
                                                     C.c_void_p(self.stream.cuda_stream)), "drv_unpack_counts_u8")
             self.h2d_bytes += 4 * k * G + n + 8 * esc
             if k and n:
-                self._hyb_meas[slot] = (ev0, ev1, 4 * k * G, 4 * n, pack_s)
+                self._hyb_meas[slot] = (ev0, ev1, 4 * k * G, 4 * n, pack_s, n + 8 * esc)
         rest = self._stage_rest(slot, batch[1:])
         self._ready[slot].record(self.stream)
         return [dst] + rest
