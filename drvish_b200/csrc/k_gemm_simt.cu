@@ -203,6 +203,62 @@ void simt_linear_forward(const float* U, int B, int din, int pro_mode, BnParams 
   note_launch();
 }
 
+// V = relu(bn(U)) W^T + b for a NARROW input (din <= 64: the decoder's first Linear, latent -> hidden) with the
+// BatchNorm batch statistics of V for the next block in the same launch (replaces the tiled GEMM, whose tiles are
+// mostly empty at K = 10, plus a separate statistics kernel: two latency-bound links of the critical chain, 12 + 17 us
+// at cfg 3).  Thread = output column (its W row in registers), CTA = NROWS cells whose normalised inputs sit in shared
+// memory; the column sums stay in registers, one fp64 atomic per column, moment and CTA, the last CTA of a column
+// block finalises (stat_finalize_if_last; grid = (column blocks, row blocks)).
+constexpr int NROWS = 32;
+template <int DIN_MAX>
+__global__ void __launch_bounds__(256) k_narrow_linear_stats(const float* __restrict__ U, int B, int din, BnParams bn,
+                                                             const float* __restrict__ W, const float* __restrict__ bias,
+                                                             int dout, float* __restrict__ V, double* __restrict__ acc,
+                                                             StatFinal fin) {
+  pdl_prologue();
+  __shared__ float a[NROWS][DIN_MAX];
+  const int r0 = blockIdx.y * NROWS;
+  for (int idx = threadIdx.x; idx < NROWS * din; idx += blockDim.x) {
+    const int r = idx / din, i = idx - r * din;
+    const int row = r0 + r;
+    a[r][i] = row < B ? bn_relu(U[(size_t)row * din + i], bn.mean[i], bn.rstd[i], bn.gamma[i], bn.beta[i]) : 0.f;
+  }
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool col_ok = j < dout;
+  float w[DIN_MAX];
+#pragma unroll
+  for (int i = 0; i < DIN_MAX; ++i) w[i] = (col_ok && i < din) ? __ldg(&W[(size_t)j * din + i]) : 0.f;
+  const float bj = col_ok ? __ldg(&bias[j]) : 0.f;
+  __syncthreads();
+  float s1 = 0.f, s2 = 0.f;
+  const int nr = min(NROWS, B - r0);
+  if (col_ok) {
+    for (int r = 0; r < nr; ++r) {
+      float v = bj;
+#pragma unroll
+      for (int i = 0; i < DIN_MAX; ++i)
+        if (i < din) v = __fmaf_rn(a[r][i], w[i], v);
+      V[(size_t)(r0 + r) * dout + j] = v;
+      s1 += v;
+      s2 = __fmaf_rn(v, v, s2);
+    }
+    atomicAdd(&acc[j], (double)s1);
+    atomicAdd(&acc[(size_t)dout + j], (double)s2);
+  }
+  stat_finalize_if_last(fin, acc, dout, blockIdx.x * blockDim.x, blockDim.x);
+}
+
+bool simt_narrow_linear_forward_stats(const float* U, int B, int din, BnParams bn, const float* W, const float* bias,
+                                      int dout, float* V, const ColStatsOut& ns, cudaStream_t st) {
+  if (din > 64 || din < 1) return false;
+  dim3 grid(cdiv(dout, 256), cdiv(B, NROWS));
+  if (din <= 16) launch_k(k_narrow_linear_stats<16>, grid, 256, 0, st, U, B, din, bn, W, bias, dout, V, ns.acc, ns.fin);
+  else if (din <= 32) launch_k(k_narrow_linear_stats<32>, grid, 256, 0, st, U, B, din, bn, W, bias, dout, V, ns.acc, ns.fin);
+  else launch_k(k_narrow_linear_stats<64>, grid, 256, 0, st, U, B, din, bn, W, bias, dout, V, ns.acc, ns.fin);
+  note_launch();
+  return true;
+}
+
 void simt_linear_wgrad(const float* dV, int B, int dout, const float* U, int din, int pro_mode, BnParams bn, float* dW,
                        float* db, cudaStream_t st) {
   Prologue pa{0, {}}, pb{pro_mode, bn};

@@ -25,6 +25,10 @@ void bump_counters(int64_t* counters, int n, cudaStream_t st);
 // ---- k_gemm_simt.cu ---------------------------------------------------------------------------
 void simt_linear_forward(const float* U, int B, int din, int pro_mode, BnParams bn, const float* W, const float* bias,
                          int dout, float* V, cudaStream_t st);
+// narrow input (din <= 64), BatchNorm + ReLU prologue, also the batch statistics of V for the next block;
+// false (nothing launched) when the shape does not qualify
+bool simt_narrow_linear_forward_stats(const float* U, int B, int din, BnParams bn, const float* W, const float* bias,
+                                      int dout, float* V, const ColStatsOut& ns, cudaStream_t st);
 void simt_linear_wgrad(const float* dV, int B, int dout, const float* U, int din, int pro_mode, BnParams bn, float* dW,
                        float* db, cudaStream_t st);
 void simt_linear_dgrad_gate(const float* dV, int B, int dout, const float* W, int din, const float* U, int pro_mode,

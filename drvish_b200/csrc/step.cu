@@ -355,6 +355,20 @@ bool block_forward(const Ctx& c, int s, int k, const float* U0, bool do_linear, 
     }
     return tc_block_forward(a, c.st);
   } else {
+    const int n_blocks = c.n.n_blocks;
+    static const bool narrow_off = getenv("DRV_NARROW_FUSED") != nullptr && atoi(getenv("DRV_NARROW_FUSED")) == 0;
+    if (!sq && b.din <= 64 && k + 1 < n_blocks && !narrow_off && !(c.hp.flags & (1024 | DRV_FLAG_FORCE_SIMT))) {
+      // narrow input (latent -> hidden): Linear + the next block's BatchNorm statistics in one launch
+      const Block& nb = s == 0 ? c.n.enc[k + 1] : c.n.dec[k + 1];
+      ColStatsOut ns{};
+      ns.acc = c.at<double>(c.p.stat_acc[s][k + 1]);
+      ns.fin = StatFinal{c.at<unsigned int>(c.p.ticket[s][k + 1]), B, c.hp.bn_eps, c.hp.bn_momentum,
+                         c.at<float>(c.p.mean[s][k + 1]), c.at<float>(c.p.rstd[s][k + 1]),
+                         update ? c.bnbuf + nb.rmean : nullptr, update ? c.bnbuf + nb.rvar : nullptr};
+      if (simt_narrow_linear_forward_stats(U, B, b.din, c.bn(s, k), c.params + b.W, c.params + b.bias, b.dout,
+                                           c.at<float>(c.p.V[s][k]), ns, c.st))
+        return true;
+    }
     simt_linear_forward(U, B, b.din, sq ? 2 : 1, c.bn(s, k), c.params + b.W, c.params + b.bias, b.dout,
                         c.at<float>(c.p.V[s][k]), c.st);
   }
