@@ -746,11 +746,12 @@ static int elbo_step_core(const drv_dims* dims, const drv_hparams* hp, const flo
                     use_tc ? c.at<float>(p.ll) : nullptr, B, hp->scale_factor, st, grads + n.n_param_floats, path);
       side->comm_fork(st);
       // Few CTAs: the slice has ~100 us of small-grid kernels to hide behind, and every CTA it takes slows those down
-      // (measured at cfg 3, ms per step: 8 GPUs 64 CTAs 0.733, 48 x 256 threads 0.716, 32 CTAs 0.686; 2 GPUs 64 CTAs 0.649,
-      // 32 CTAs 0.641, 32 x 256 threads 0.634, 16 CTAs 0.680 - too slow for the window).
+      // (measured at cfg 3, ms per step: 8 GPUs 64 CTAs 0.733, 48 x 256 threads 0.716, 32 x 256 threads 0.749, 32 CTAs
+      // 0.686-0.694; 4 GPUs 32 CTAs 0.674, 32 x 256 threads 0.664; 2 GPUs 64 CTAs 0.649, 32 CTAs 0.641, 32 x 256 threads
+      // 0.634, 16 CTAs 0.680 - too slow for the window).
       static const int early_ctas = getenv("DRV_AR_EARLY_CTAS") ? atoi(getenv("DRV_AR_EARLY_CTAS")) : 32;
       static const int early_threads_env = getenv("DRV_AR_EARLY_THREADS") ? atoi(getenv("DRV_AR_EARLY_THREADS")) : 0;
-      const int early_threads = early_threads_env ? early_threads_env : (comm_world() == 2 ? 256 : 512);
+      const int early_threads = early_threads_env ? early_threads_env : (comm_world() <= 4 ? 256 : 512);
       const int rc = comm_allreduce_slice(last.W, n.n_param_floats + DRV_GRAD_TAIL_FLOATS - last.W, early_ctas, side->comm, early_threads);
       if (rc != 0) return rc;
     }
