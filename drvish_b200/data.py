@@ -284,6 +284,19 @@ class MCVDataLoader(torch.utils.data.DataLoader):
     split_molecules = staticmethod(split_molecules)
 
 
+def hybrid_fp32_fraction(bus_rate: float, pack_rate: float, compression: float) -> float:
+    """Share f of a tile's rows that should cross the bus as fp32 while the host packs the rest, so that both paths
+    finish together.  Rates in fp32 SOURCE bytes per second (bus: bytes copied per second; packer: source bytes consumed
+    per second), ``compression`` = packed bytes per source byte.  The bus carries ``(f + (1 - f) c) S / a`` per tile of S
+    bytes, the packer ``(1 - f) S / b``; equal at ``f = (a - c b) / ((1 - c) b + a)``, 0 when the bus is slower than the
+    packer's OUTPUT (``c b >= a``: everything is packed)."""
+    a, b, c = float(bus_rate), float(pack_rate), float(compression)
+    if a <= 0.0 or b <= 0.0:
+        return 0.0 if a <= 0.0 else 1.0
+    c = min(max(c, 0.0), 1.0)
+    return min(1.0, max(0.0, (a - c * b) / ((1.0 - c) * b + a)))
+
+
 class PinnedBatchPrefetcher:
     """Iterate ``batches`` with the host->device copy of the next ones already in flight.
 
@@ -401,7 +414,7 @@ class PinnedBatchPrefetcher:
                 a = dma_bytes / max(ev0.elapsed_time(ev1) * 1e-3, 1e-6)
                 b = pack_bytes / max(pack_s, 1e-6)
                 c = packed_bytes / pack_bytes
-                f = max(0.0, (a - c * b) / ((1.0 - c) * b + a))
+                f = hybrid_fp32_fraction(a, b, c)
                 self.hybrid_fraction = min(0.9, 0.5 * self.hybrid_fraction + 0.5 * f)
             self._hyb_meas[slot] = None
         # rows that travel as fp32 (a multiple of 4 keeps the rest 16-byte aligned; never none, so that the bus rate keeps

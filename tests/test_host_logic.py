@@ -235,3 +235,21 @@ def test_pyro_fused_scheduler_drives_train_until_plateau():
     assert max(lrs) == pytest.approx(5e-4 / 3, rel=0.2) and min(lrs) < 0.3 * max(lrs)  # the cosine really moves the fused optimizer's lr
     state = sched.get_state()
     sched.set_state(state)
+
+
+def test_hybrid_transport_split_balances_bus_and_packer():
+    """PinnedBatchPrefetcher ships a fp32 host tile over two paths at once (data.py:_stage_hybrid); the split must
+    make the bus time - fp32 rows AND packed rows - equal to the packing time, and pack everything when the bus is
+    slower than the packer's output."""
+    from drvish_b200.data import hybrid_fp32_fraction as hf
+
+    for a, b, c in ((45e9, 110e9, 0.25), (45e9, 70e9, 0.26), (27e9, 110e9, 0.25), (55e9, 20e9, 0.5), (10e9, 10e9, 1.0)):
+        f = hf(a, b, c)
+        assert 0.0 <= f <= 1.0
+        bus, pack = (f + (1 - f) * c) / a, (1 - f) / b
+        if f > 0.0:
+            assert abs(bus - pack) <= 1e-9 * max(bus, pack), (a, b, c, f)
+        else:
+            assert c * b >= a  # the packed stream alone saturates the bus
+    assert hf(45e9, 110e9, 0.25) == pytest.approx(17.5 / 127.5)
+    assert hf(0.0, 1.0, 0.25) == 0.0 and hf(1.0, 0.0, 0.25) == 1.0
